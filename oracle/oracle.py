@@ -1,0 +1,130 @@
+"""ORACLE python wrapper (ctypes over oracle/liboracle.so) -- test infrastructure, NOT product.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  PARITY UNPINNED (see rbd_oracle.hpp): the oracle restates the published
+algorithms; the RaiSim binary is unavailable, parity with RaiSim itself is unverified.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+PARAM_ORDER = ("dt", "gx", "gy", "gz", "erp", "alpha_init", "alpha_min", "alpha_decay", "max_iter",
+               "threshold", "mu", "restitution", "rest_threshold")
+DEFAULT_PARAMS = dict(dt=0.0025, gx=0.0, gy=0.0, gz=-9.81, erp=0.0, alpha_init=1.0, alpha_min=1.0, alpha_decay=1.0,
+                      max_iter=150, threshold=1e-7, mu=0.8, restitution=0.0, rest_threshold=0.01)
+
+
+def build(force=False):
+    if force or not os.path.exists(_LIB_PATH) or any(
+            os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
+            for f in ("oracle_capi.cpp", "rbd_oracle.hpp")):
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s", "liboracle.so"])
+    return _LIB_PATH
+
+
+class _ModelDesc(C.Structure):
+    _fields_ = [("nb", C.c_int), ("nq", C.c_int), ("nv", C.c_int), ("floating", C.c_int),
+                ("parent", C.c_void_p), ("jtype", C.c_void_p), ("qidx", C.c_void_p), ("vidx", C.c_void_p),
+                ("jpos", C.c_void_p), ("jrot", C.c_void_p), ("axis", C.c_void_p), ("mass", C.c_void_p),
+                ("com", C.c_void_p), ("inertia", C.c_void_p),
+                ("npts", C.c_int), ("pt_body", C.c_void_p), ("pt_pos", C.c_void_p), ("pt_rad", C.c_void_p)]
+
+
+class _Debug(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("M", "h", "R", "p", "ncontacts", "c_pt", "c_body", "c_pair", "c_pos",
+                                          "c_normal", "c_depth", "c_lambda", "iters")]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_create.restype = C.c_void_p
+        _lib.orc_create.argtypes = [C.POINTER(_ModelDesc), C.c_int]
+        _lib.orc_destroy.argtypes = [C.c_void_p]
+        _lib.orc_set_params.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.orc_set_ground.argtypes = [C.c_void_p, C.c_double]
+        _lib.orc_set_heightmap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
+        _lib.orc_clear_terrain.argtypes = [C.c_void_p]
+        _lib.orc_step.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p]
+        _lib.orc_solve_one.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """CPU restatement of raisim::World::integrate() for a batch of independent environments."""
+
+    def __init__(self, tables, precision="f64", params=None):
+        self.t = tables
+        self.nb, self.nq, self.nv = tables["nb"], tables["nq"], tables["nv"]
+        self._keep = {k: np.ascontiguousarray(tables[k], dtype=(np.int32 if tables[k].dtype.kind == "i" else np.float64))
+                      for k in ("parent", "jtype", "qidx", "vidx", "jpos", "jrot", "axis", "mass", "com", "inertia",
+                                "pt_body", "pt_pos", "pt_rad")}
+        d = _ModelDesc(nb=self.nb, nq=self.nq, nv=self.nv, floating=tables["floating"], npts=tables["npts"])
+        for k, a in self._keep.items():
+            setattr(d, k, a.ctypes.data)
+        self.precision = precision
+        self.h = lib().orc_create(C.byref(d), 0 if precision == "f64" else 1)
+        self.kmax = lib().orc_kmax()
+        self.params = dict(DEFAULT_PARAMS)
+        self.set_params(**(params or {}))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_destroy(self.h)
+            self.h = None
+
+    def set_params(self, **kw):
+        self.params.update(kw)
+        arr = np.array([float(self.params[k]) for k in PARAM_ORDER], dtype=np.float64)
+        lib().orc_set_params(self.h, _p(arr))
+
+    def set_ground(self, z=0.0):
+        lib().orc_set_ground(self.h, float(z))
+
+    def set_heightmap(self, xs, ys, x_size, y_size, cx, cy, heights):
+        hh = np.ascontiguousarray(heights, dtype=np.float64).reshape(-1)
+        assert hh.size == xs * ys
+        lib().orc_set_heightmap(self.h, xs, ys, x_size, y_size, cx, cy, _p(hh))
+
+    def clear_terrain(self):
+        lib().orc_clear_terrain(self.h)
+
+    def step(self, gc, gv, n_steps=1, tau_ff=None, ptarget=None, vtarget=None, kp=None, kd=None, nthreads=0, debug=False):
+        """gc [n,nq], gv [n,nv] float64 C-contiguous, updated IN PLACE.  Returns debug dict or None."""
+        assert gc.dtype == np.float64 and gv.dtype == np.float64 and gc.flags.c_contiguous and gv.flags.c_contiguous
+        n = gc.shape[0]
+        assert gc.shape == (n, self.nq) and gv.shape == (n, self.nv)
+        f = lambda a, w: None if a is None else np.ascontiguousarray(np.broadcast_to(np.asarray(a, np.float64), (n, w)))
+        tau_ff, ptarget, vtarget = f(tau_ff, self.nv), f(ptarget, self.nq), f(vtarget, self.nv)
+        g = lambda a: None if a is None else np.ascontiguousarray(np.broadcast_to(np.asarray(a, np.float64), (self.nv,)))
+        kp, kd = g(kp), g(kd)
+        dbg, out = None, None
+        if debug:
+            K, nb, nv = self.kmax, self.nb, self.nv
+            out = dict(M=np.zeros((n, nv, nv)), h=np.zeros((n, nv)), R=np.zeros((n, nb, 3, 3)), p=np.zeros((n, nb, 3)),
+                       ncontacts=np.zeros(n, np.int32), c_pt=np.zeros((n, K), np.int32), c_body=np.zeros((n, K), np.int32),
+                       c_pair=np.zeros((n, K), np.int32), c_pos=np.zeros((n, K, 3)), c_normal=np.zeros((n, K, 3)),
+                       c_depth=np.zeros((n, K)), c_lambda=np.zeros((n, K, 3)), iters=np.zeros(n, np.int32))
+            dbg = _Debug(**{k: v.ctypes.data for k, v in out.items()})
+        lib().orc_step(self.h, n, n_steps, _p(gc), _p(gv), _p(tau_ff), _p(ptarget), _p(vtarget), _p(kp), _p(kd),
+                       int(nthreads), C.byref(dbg) if dbg is not None else None)
+        return out
+
+    def solve_one(self, G, c, mu):
+        G = np.ascontiguousarray(G, np.float64); c = np.ascontiguousarray(c, np.float64)
+        lam = np.zeros(3)
+        lib().orc_solve_one(self.h, _p(G), _p(c), float(mu), _p(lam))
+        return lam

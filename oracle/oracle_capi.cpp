@@ -1,0 +1,147 @@
+// ORACLE C API -- test infrastructure, NOT product code (see rbd_oracle.hpp header).
+// Builds liboracle.so: a double and a float instance of the restated World::integrate(),
+// OpenMP over environments the way RaisimGym's VectorizedEnvironment does
+// (`#pragma omp parallel for` over envs, SURVEY.md 3.1 [RECALL]).
+#include "rbd_oracle.hpp"
+#include <omp.h>
+#include <memory>
+
+using namespace orc;
+
+struct OrcDebug {       // every pointer optional; sized for n_envs; filled from the LAST step
+  double* M;            // [n][nv*nv]   mass matrix (no PD augmentation)
+  double* h;            // [n][nv]      bias force incl. gravity
+  double* R;            // [n][nb*9]
+  double* p;            // [n][nb*3]
+  int* ncontacts;       // [n]
+  int* c_pt;            // [n][KMAX]
+  int* c_body;          // [n][KMAX]
+  int* c_pair;          // [n][KMAX]
+  double* c_pos;        // [n][KMAX*3]
+  double* c_normal;     // [n][KMAX*3]
+  double* c_depth;      // [n][KMAX]
+  double* c_lambda;     // [n][KMAX*3]  contact-frame impulse (t1,t2,n)
+  int* iters;           // [n]
+};
+
+struct Handle {
+  int precision;
+  std::unique_ptr<Sim<double>> d;
+  std::unique_ptr<Sim<float>> f;
+};
+
+template <typename T>
+static void run(Sim<T>& sim, int n_envs, int n_steps, double* gc, double* gv, const double* tau, const double* pt, const double* vt,
+                const double* kp, const double* kd, int nthreads, OrcDebug* dbg) {
+  const int nq = sim.nq, nv = sim.nv, nb = sim.nb;
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel num_threads(nthreads)
+  {
+    Workspace<T> ws;
+    sim.init_ws(ws);
+    std::vector<T> q(nq), v(nv), tf(nv), ptt(nq), vtt(nv), kpp(nv), kdd(nv);
+#pragma omp for schedule(static)
+    for (int e = 0; e < n_envs; e++) {
+      for (int i = 0; i < nq; i++) q[i] = T(gc[(size_t)e * nq + i]);
+      for (int i = 0; i < nv; i++) v[i] = T(gv[(size_t)e * nv + i]);
+      if (tau) for (int i = 0; i < nv; i++) tf[i] = T(tau[(size_t)e * nv + i]);
+      if (pt) for (int i = 0; i < nq; i++) ptt[i] = T(pt[(size_t)e * nq + i]);
+      if (vt) for (int i = 0; i < nv; i++) vtt[i] = T(vt[(size_t)e * nv + i]);
+      if (kp) for (int i = 0; i < nv; i++) kpp[i] = T(kp[i]);
+      if (kd) for (int i = 0; i < nv; i++) kdd[i] = T(kd[i]);
+      for (int s = 0; s < n_steps; s++)
+        sim.step(q.data(), v.data(), tau ? tf.data() : nullptr, pt ? ptt.data() : nullptr, vt ? vtt.data() : nullptr,
+                 kp ? kpp.data() : nullptr, kd ? kdd.data() : nullptr, ws);
+      for (int i = 0; i < nq; i++) gc[(size_t)e * nq + i] = double(q[i]);
+      for (int i = 0; i < nv; i++) gv[(size_t)e * nv + i] = double(v[i]);
+      if (dbg) {
+        if (dbg->M) for (int i = 0; i < nv * nv; i++) dbg->M[(size_t)e * nv * nv + i] = double(ws.M[i]);
+        if (dbg->h) for (int i = 0; i < nv; i++) dbg->h[(size_t)e * nv + i] = double(ws.h[i]);
+        if (dbg->R) for (int i = 0; i < nb; i++) for (int k = 0; k < 9; k++) dbg->R[((size_t)e * nb + i) * 9 + k] = double(ws.R[i].m[k]);
+        if (dbg->p) for (int i = 0; i < nb; i++) { dbg->p[((size_t)e * nb + i) * 3] = ws.p[i].x; dbg->p[((size_t)e * nb + i) * 3 + 1] = ws.p[i].y; dbg->p[((size_t)e * nb + i) * 3 + 2] = ws.p[i].z; }
+        int K = int(ws.contacts.size());
+        if (dbg->ncontacts) dbg->ncontacts[e] = K;
+        if (dbg->iters) dbg->iters[e] = ws.iters;
+        for (int k = 0; k < KMAX; k++) {
+          size_t o = (size_t)e * KMAX + k;
+          bool on = k < K;
+          if (dbg->c_pt) dbg->c_pt[o] = on ? ws.contacts[k].pt : -1;
+          if (dbg->c_body) dbg->c_body[o] = on ? ws.contacts[k].body : -1;
+          if (dbg->c_pair) dbg->c_pair[o] = on ? ws.contacts[k].pair : -1;
+          if (dbg->c_depth) dbg->c_depth[o] = on ? double(ws.contacts[k].depth) : 0.0;
+          if (dbg->c_pos) { dbg->c_pos[3 * o] = on ? ws.contacts[k].pos.x : 0; dbg->c_pos[3 * o + 1] = on ? ws.contacts[k].pos.y : 0; dbg->c_pos[3 * o + 2] = on ? ws.contacts[k].pos.z : 0; }
+          if (dbg->c_normal) { dbg->c_normal[3 * o] = on ? ws.contacts[k].n.x : 0; dbg->c_normal[3 * o + 1] = on ? ws.contacts[k].n.y : 0; dbg->c_normal[3 * o + 2] = on ? ws.contacts[k].n.z : 0; }
+          if (dbg->c_lambda) { dbg->c_lambda[3 * o] = on ? ws.contacts[k].lam.x : 0; dbg->c_lambda[3 * o + 1] = on ? ws.contacts[k].lam.y : 0; dbg->c_lambda[3 * o + 2] = on ? ws.contacts[k].lam.z : 0; }
+        }
+      }
+    }
+  }
+}
+
+extern "C" {
+
+void* orc_create(const ModelDesc* d, int precision) {
+  Handle* h = new Handle;
+  h->precision = precision;
+  if (precision == 0) h->d.reset(new Sim<double>(*d)); else h->f.reset(new Sim<float>(*d));
+  return h;
+}
+void orc_destroy(void* hv) { delete static_cast<Handle*>(hv); }
+
+int orc_kmax() { return KMAX; }
+
+// p = {dt, gx, gy, gz, erp, alpha_init, alpha_min, alpha_decay, max_iter, threshold, mu, restitution, rest_threshold}
+void orc_set_params(void* hv, const double* p) {
+  Handle* h = static_cast<Handle*>(hv);
+  Params prm;
+  prm.dt = p[0]; prm.gravity[0] = p[1]; prm.gravity[1] = p[2]; prm.gravity[2] = p[3]; prm.erp = p[4];
+  prm.alpha_init = p[5]; prm.alpha_min = p[6]; prm.alpha_decay = p[7]; prm.max_iter = int(p[8]); prm.threshold = p[9];
+  prm.mu = p[10]; prm.restitution = p[11]; prm.rest_threshold = p[12];
+  if (h->d) h->d->prm = prm; else h->f->prm = prm;
+}
+
+void orc_set_ground(void* hv, double z) {
+  Handle* h = static_cast<Handle*>(hv);
+  Terrain t; t.type = 1; t.ground_z = z;
+  if (h->d) h->d->set_terrain(t); else h->f->set_terrain(t);
+}
+
+void orc_set_heightmap(void* hv, int xs, int ys, double x_size, double y_size, double cx, double cy, const double* heights) {
+  Handle* h = static_cast<Handle*>(hv);
+  Terrain t; t.type = 2; t.xs = xs; t.ys = ys; t.x_size = x_size; t.y_size = y_size; t.cx = cx; t.cy = cy;
+  t.h.assign(heights, heights + (size_t)xs * ys);
+  if (h->d) h->d->set_terrain(t); else h->f->set_terrain(t);
+}
+
+void orc_clear_terrain(void* hv) {
+  Handle* h = static_cast<Handle*>(hv);
+  Terrain t;
+  if (h->d) h->d->set_terrain(t); else h->f->set_terrain(t);
+}
+
+// n_steps of World::integrate() for n_envs environments; gc [n][nq], gv [n][nv] updated in place.
+// tau_ff [n][nv], ptarget [n][nq], vtarget [n][nv] per env (nullable); kp, kd [nv] shared (nullable).
+int orc_step(void* hv, int n_envs, int n_steps, double* gc, double* gv, const double* tau_ff, const double* ptarget,
+             const double* vtarget, const double* kp, const double* kd, int nthreads, OrcDebug* dbg) {
+  Handle* h = static_cast<Handle*>(hv);
+  if (h->d) run(*h->d, n_envs, n_steps, gc, gv, tau_ff, ptarget, vtarget, kp, kd, nthreads, dbg);
+  else run(*h->f, n_envs, n_steps, gc, gv, tau_ff, ptarget, vtarget, kp, kd, nthreads, dbg);
+  return 0;
+}
+
+// isolated per-contact solve, for the solver unit tests: G 3x3 row-major (t1,t2,n), c[3], mu -> lam[3]
+void orc_solve_one(void* hv, const double* G, const double* c, double mu, double* lam) {
+  Handle* h = static_cast<Handle*>(hv);
+  if (h->d) {
+    V3<double> l; h->d->solve_one(G, V3<double>{c[0], c[1], c[2]}, mu, l);
+    lam[0] = l.x; lam[1] = l.y; lam[2] = l.z;
+  } else {
+    float Gf[9]; for (int i = 0; i < 9; i++) Gf[i] = float(G[i]);
+    V3<float> l; h->f->solve_one(Gf, V3<float>{float(c[0]), float(c[1]), float(c[2])}, float(mu), l);
+    lam[0] = l.x; lam[1] = l.y; lam[2] = l.z;
+  }
+}
+
+int orc_max_threads() { return omp_get_max_threads(); }
+
+}  // extern "C"

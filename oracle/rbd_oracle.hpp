@@ -1,0 +1,600 @@
+// ORACLE -- test infrastructure, NOT product code.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// compile, link or call anything under oracle/.  The product path (raisimlib_b200/csrc) never does.
+//
+// PARITY UNPINNED: the reference snapshot (/root/reference) contains no source, binary, test or
+// golden vector for this path (.SUBMODULES.json:2 "bytes": 0; upstream's engine is the closed
+// libraisim.so).  This file restates the PUBLISHED algorithms the reference is documented to use
+// (SURVEY.md section 8c):
+//   * Featherstone, "Rigid Body Dynamics Algorithms" (2008): RNEA (Table 5.1), CRBA (Table 6.2),
+//     floating-base conventions (ch. 9)
+//   * Hwangbo, Lee, Hutter, "Per-Contact Iteration Method for Solving Contact Dynamics",
+//     IEEE RA-L 3(2) 2018, sections III-IV: per-contact Gauss-Seidel; opening / stick / slip with a
+//     1-D search along the (friction-cone surface) x (zero normal velocity plane) curve
+// and is validated by analytic known-answer tests (tests/test_oracle_*.py).
+// What it stands in for: raisim::World::integrate() = integrate1() + integrate2()  (SURVEY 3.2, a1-a10).
+//
+// Conventions (all [RECALL]):
+//   gc = [x y z | qw qx qy qz | joints],  gv = [v_base(world) | w_base(world) | joint rates]
+//   gravity (0,0,-9.81); semi-implicit Euler (v first, then q with v+); PD implicit in M
+//   contact normal points from terrain into the robot; contacts ordered by candidate-point index
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+namespace orc {
+
+constexpr int JT_FIXED = 0, JT_REVOLUTE = 1, JT_PRISMATIC = 2, JT_FLOATING = 3;
+constexpr int KMAX = 10;           // contacts kept per environment (deepest KMAX of the candidates)
+constexpr int NSEC = 32;           // sections per refinement round of the slip search
+constexpr int NROUNDS = 4;         // rounds: bracket 2*pi/32^r
+
+template <typename T> struct V3 { T x, y, z; };
+template <typename T> inline V3<T> operator+(V3<T> a, V3<T> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+template <typename T> inline V3<T> operator-(V3<T> a, V3<T> b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+template <typename T> inline V3<T> operator*(T s, V3<T> a) { return {s * a.x, s * a.y, s * a.z}; }
+template <typename T> inline T dot(V3<T> a, V3<T> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <typename T> inline V3<T> cross(V3<T> a, V3<T> b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+template <typename T> struct M3 {
+  T m[9];  // row-major
+  V3<T> operator*(V3<T> v) const { return {m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z}; }
+  M3 operator*(const M3& o) const {
+    M3 r;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.m[3 * i + j] = m[3 * i] * o.m[j] + m[3 * i + 1] * o.m[3 + j] + m[3 * i + 2] * o.m[6 + j];
+    return r;
+  }
+  V3<T> tmul(V3<T> v) const { return {m[0] * v.x + m[3] * v.y + m[6] * v.z, m[1] * v.x + m[4] * v.y + m[7] * v.z, m[2] * v.x + m[5] * v.y + m[8] * v.z}; }
+};
+
+// Rodrigues rotation about unit axis a by angle q
+template <typename T> inline M3<T> axis_angle(V3<T> a, T q) {
+  T c = std::cos(q), s = std::sin(q), t = T(1) - c;
+  return {{t * a.x * a.x + c, t * a.x * a.y - s * a.z, t * a.x * a.z + s * a.y,
+           t * a.x * a.y + s * a.z, t * a.y * a.y + c, t * a.y * a.z - s * a.x,
+           t * a.x * a.z - s * a.y, t * a.y * a.z + s * a.x, t * a.z * a.z + c}};
+}
+
+template <typename T> inline M3<T> quat_to_rot(T w, T x, T y, T z) {
+  return {{T(1) - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+           2 * (x * y + w * z), T(1) - 2 * (x * x + z * z), 2 * (y * z - w * x),
+           2 * (x * z - w * y), 2 * (y * z + w * x), T(1) - 2 * (x * x + y * y)}};
+}
+
+struct ModelDesc {   // plain-C description handed over the oracle's C API (all arrays double / int)
+  int nb, nq, nv, floating;
+  const int *parent, *jtype, *qidx, *vidx;
+  const double *jpos, *jrot, *axis, *mass, *com, *inertia;
+  int npts;
+  const int *pt_body;
+  const double *pt_pos, *pt_rad;
+};
+
+struct Params {
+  double dt = 0.0025;
+  double gravity[3] = {0, 0, -9.81};
+  double erp = 0.0;             // World::setERP
+  double alpha_init = 1.0, alpha_min = 1.0, alpha_decay = 1.0;   // World::setContactSolverParam
+  int max_iter = 150;
+  double threshold = 1e-7;
+  double mu = 0.8;              // World::setDefaultMaterial friction
+  double restitution = 0.0, rest_threshold = 0.01;
+};
+
+struct Terrain {
+  int type = 0;                 // 0 none, 1 ground plane (World::addGround), 2 height map (World::addHeightMap)
+  double ground_z = 0.0;
+  int xs = 0, ys = 0;
+  double x_size = 0, y_size = 0, cx = 0, cy = 0;
+  std::vector<double> h;        // h[iy * xs + ix]
+};
+
+template <typename T> struct Contact {
+  int pt;          // candidate-point index (defines the order)
+  int body;        // local body index on the robot  (raisim::Contact::getlocalBodyIndex)
+  int pair;        // terrain feature: 0 for the plane, 2*cell+tri for the height map
+  V3<T> pos;       // world position of the contact point on the robot surface
+  V3<T> n, t1, t2; // contact frame, n = normal into the robot
+  T depth;
+  V3<T> lam;       // impulse in the contact frame (t1, t2, n)
+};
+
+template <typename T> struct Workspace {
+  int nb, nv;
+  std::vector<M3<T>> R;
+  std::vector<V3<T>> p, a, w, v, wd, vd, F, N;
+  std::vector<T> Ic;             // 10 per body: m, h(3), I_O(6: xx xy xz yy yz zz)
+  std::vector<T> S;              // 6 per body: [ang(3); lin_at_O(3)]
+  std::vector<T> M, Mh, L, h, b, z, Jt, Y, G, u, rhs;
+  std::vector<Contact<T>> contacts, all;
+  int iters = 0;
+};
+
+template <typename T> class Sim {
+ public:
+  int nb, nq, nv, floating, npts;
+  std::vector<int> parent, jtype, qidx, vidx, pt_body;
+  std::vector<V3<T>> jpos, axis, com, pt_pos;
+  std::vector<M3<T>> jrot;
+  std::vector<T> mass, inertia, pt_rad;
+  Params prm;
+  Terrain ter;
+  std::vector<T> hmap;
+  T sec_c[NROUNDS][NSEC + 1], sec_s[NROUNDS][NSEC + 1];
+
+  explicit Sim(const ModelDesc& d) {
+    nb = d.nb; nq = d.nq; nv = d.nv; floating = d.floating; npts = d.npts;
+    parent.assign(d.parent, d.parent + nb); jtype.assign(d.jtype, d.jtype + nb);
+    qidx.assign(d.qidx, d.qidx + nb); vidx.assign(d.vidx, d.vidx + nb);
+    jpos.resize(nb); axis.resize(nb); com.resize(nb); jrot.resize(nb); mass.resize(nb); inertia.resize(6 * nb);
+    for (int i = 0; i < nb; i++) {
+      jpos[i] = {T(d.jpos[3 * i]), T(d.jpos[3 * i + 1]), T(d.jpos[3 * i + 2])};
+      axis[i] = {T(d.axis[3 * i]), T(d.axis[3 * i + 1]), T(d.axis[3 * i + 2])};
+      com[i] = {T(d.com[3 * i]), T(d.com[3 * i + 1]), T(d.com[3 * i + 2])};
+      for (int k = 0; k < 9; k++) jrot[i].m[k] = T(d.jrot[9 * i + k]);
+      mass[i] = T(d.mass[i]);
+      for (int k = 0; k < 6; k++) inertia[6 * i + k] = T(d.inertia[6 * i + k]);
+    }
+    pt_body.assign(d.pt_body, d.pt_body + npts); pt_pos.resize(npts); pt_rad.resize(npts);
+    for (int i = 0; i < npts; i++) {
+      pt_pos[i] = {T(d.pt_pos[3 * i]), T(d.pt_pos[3 * i + 1]), T(d.pt_pos[3 * i + 2])};
+      pt_rad[i] = T(d.pt_rad[i]);
+    }
+    // direction tables of the slip search: round r covers a bracket of width 2*pi/32^r in 32 sections
+    for (int r = 0; r < NROUNDS; r++) {
+      double width = 2.0 * M_PI / std::pow(double(NSEC), r);
+      for (int k = 0; k <= NSEC; k++) {
+        sec_c[r][k] = T(std::cos(width * k / NSEC));
+        sec_s[r][k] = T(std::sin(width * k / NSEC));
+      }
+    }
+  }
+
+  void set_terrain(const Terrain& t) {
+    ter = t;
+    hmap.resize(t.h.size());
+    for (size_t i = 0; i < t.h.size(); i++) hmap[i] = T(t.h[i]);
+  }
+
+  void init_ws(Workspace<T>& ws) const {
+    ws.nb = nb; ws.nv = nv;
+    ws.R.resize(nb); ws.p.resize(nb); ws.a.resize(nb); ws.w.resize(nb); ws.v.resize(nb); ws.wd.resize(nb); ws.vd.resize(nb);
+    ws.F.resize(nb); ws.N.resize(nb); ws.Ic.resize(10 * nb); ws.S.resize(6 * nb);
+    ws.M.resize(nv * nv); ws.Mh.resize(nv * nv); ws.L.resize(nv * nv); ws.h.resize(nv); ws.b.resize(nv); ws.z.resize(nv); ws.rhs.resize(nv);
+    ws.Jt.resize(nv * 3 * KMAX); ws.Y.resize(nv * 3 * KMAX); ws.G.resize(9 * KMAX * KMAX); ws.u.resize(3 * KMAX);
+  }
+
+  // ---- a2: forward kinematics (ArticulatedSystem::updateKinematics) -----------------------------
+  void fk(const T* gc, Workspace<T>& ws) const {
+    for (int i = 0; i < nb; i++) {
+      if (parent[i] < 0) {
+        if (floating) {
+          T qw = gc[3], qx = gc[4], qy = gc[5], qz = gc[6];
+          T inv = T(1) / std::sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
+          ws.R[i] = quat_to_rot(qw * inv, qx * inv, qy * inv, qz * inv);
+          ws.p[i] = {gc[0], gc[1], gc[2]};
+        } else {
+          ws.R[i] = jrot[i]; ws.p[i] = jpos[i];
+        }
+        ws.a[i] = {0, 0, 0};
+        continue;
+      }
+      int pr = parent[i];
+      M3<T> Rj = ws.R[pr] * jrot[i];
+      ws.a[i] = Rj * axis[i];
+      ws.p[i] = ws.p[pr] + ws.R[pr] * jpos[i];
+      T q = gc[qidx[i]];
+      if (jtype[i] == JT_REVOLUTE) ws.R[i] = Rj * axis_angle(axis[i], q);
+      else { ws.R[i] = Rj; ws.p[i] = ws.p[i] + q * ws.a[i]; }
+    }
+  }
+
+  // ---- a4: RNEA with zero joint acceleration, gravity included (getNonlinearities) ---------------
+  // classical (non-spatial) Newton-Euler in world coordinates, Featherstone Table 5.1 restated
+  void rnea_bias(const T* gv, Workspace<T>& ws) const {
+    V3<T> g = {T(prm.gravity[0]), T(prm.gravity[1]), T(prm.gravity[2])};
+    for (int i = 0; i < nb; i++) {
+      int pr = parent[i];
+      if (pr < 0) {
+        if (floating) { ws.v[i] = {gv[0], gv[1], gv[2]}; ws.w[i] = {gv[3], gv[4], gv[5]}; }
+        else { ws.v[i] = {0, 0, 0}; ws.w[i] = {0, 0, 0}; }
+        ws.wd[i] = {0, 0, 0};
+        ws.vd[i] = T(-1) * g;            // fictitious upward acceleration carries gravity to every body
+        continue;
+      }
+      V3<T> r = ws.p[i] - ws.p[pr];
+      T qd = gv[vidx[i]];
+      V3<T> wp = ws.w[pr];
+      if (jtype[i] == JT_REVOLUTE) {
+        ws.w[i] = wp + qd * ws.a[i];
+        ws.v[i] = ws.v[pr] + cross(wp, r);
+        ws.wd[i] = ws.wd[pr] + cross(wp, qd * ws.a[i]);
+        ws.vd[i] = ws.vd[pr] + cross(ws.wd[pr], r) + cross(wp, cross(wp, r));
+      } else {
+        ws.w[i] = wp;
+        ws.v[i] = ws.v[pr] + cross(wp, r) + qd * ws.a[i];
+        ws.wd[i] = ws.wd[pr];
+        ws.vd[i] = ws.vd[pr] + cross(ws.wd[pr], r) + cross(wp, cross(wp, r)) + T(2) * cross(wp, qd * ws.a[i]);
+      }
+    }
+    for (int i = 0; i < nb; i++) {
+      V3<T> c = ws.R[i] * com[i];                      // COM offset from the body origin, world axes
+      V3<T> ac = ws.vd[i] + cross(ws.wd[i], c) + cross(ws.w[i], cross(ws.w[i], c));
+      V3<T> f = mass[i] * ac;
+      // world inertia about the COM:  R I R^T
+      V3<T> Iw = world_inertia_mul(i, ws, ws.w[i]);
+      V3<T> Iwd = world_inertia_mul(i, ws, ws.wd[i]);
+      V3<T> n = Iwd + cross(ws.w[i], Iw);
+      ws.F[i] = f;
+      ws.N[i] = n + cross(c, f);                       // moment about the body origin
+    }
+    for (int i = nb - 1; i >= 0; i--) {
+      int pr = parent[i];
+      if (pr >= 0) {
+        if (jtype[i] == JT_REVOLUTE) ws.h[vidx[i]] = dot(ws.a[i], ws.N[i]);
+        else ws.h[vidx[i]] = dot(ws.a[i], ws.F[i]);
+        ws.F[pr] = ws.F[pr] + ws.F[i];
+        ws.N[pr] = ws.N[pr] + ws.N[i] + cross(ws.p[i] - ws.p[pr], ws.F[i]);
+      } else if (floating) {
+        ws.h[0] = ws.F[i].x; ws.h[1] = ws.F[i].y; ws.h[2] = ws.F[i].z;
+        ws.h[3] = ws.N[i].x; ws.h[4] = ws.N[i].y; ws.h[5] = ws.N[i].z;
+      }
+    }
+  }
+
+  V3<T> world_inertia_mul(int i, const Workspace<T>& ws, V3<T> x) const {
+    V3<T> xl = ws.R[i].tmul(x);
+    const T* I = &inertia[6 * i];
+    V3<T> yl = {I[0] * xl.x + I[1] * xl.y + I[2] * xl.z, I[1] * xl.x + I[3] * xl.y + I[4] * xl.z, I[2] * xl.x + I[4] * xl.y + I[5] * xl.z};
+    return ws.R[i] * yl;
+  }
+
+  // ---- a3: CRBA (getMassMatrix), Featherstone Table 6.2 in a world-aligned frame at O = p[0] ----
+  // spatial inertia about O stored as (m, h = m c, I_O); spatial motion = [ang; lin at O]
+  void crba(Workspace<T>& ws) const {
+    V3<T> O = ws.p[0];
+    for (int i = 0; i < nb; i++) {
+      V3<T> c = (ws.p[i] - O) + ws.R[i] * com[i];
+      T m = mass[i];
+      T* X = &ws.Ic[10 * i];
+      // R I R^T
+      const T* I = &inertia[6 * i];
+      const T* R = ws.R[i].m;
+      T Il[9] = {I[0], I[1], I[2], I[1], I[3], I[4], I[2], I[4], I[5]};
+      T RI[9];
+      for (int r = 0; r < 3; r++) for (int k = 0; k < 3; k++) RI[3 * r + k] = R[3 * r] * Il[k] + R[3 * r + 1] * Il[3 + k] + R[3 * r + 2] * Il[6 + k];
+      T Iw[9];
+      for (int r = 0; r < 3; r++) for (int k = 0; k < 3; k++) Iw[3 * r + k] = RI[3 * r] * R[3 * k] + RI[3 * r + 1] * R[3 * k + 1] + RI[3 * r + 2] * R[3 * k + 2];
+      T cc = dot(c, c);
+      X[0] = m; X[1] = m * c.x; X[2] = m * c.y; X[3] = m * c.z;
+      X[4] = Iw[0] + m * (cc - c.x * c.x); X[5] = Iw[1] - m * c.x * c.y; X[6] = Iw[2] - m * c.x * c.z;
+      X[7] = Iw[4] + m * (cc - c.y * c.y); X[8] = Iw[5] - m * c.y * c.z; X[9] = Iw[8] + m * (cc - c.z * c.z);
+      T* S = &ws.S[6 * i];
+      if (parent[i] >= 0) {
+        V3<T> r = ws.p[i] - O;
+        if (jtype[i] == JT_REVOLUTE) { V3<T> l = cross(r, ws.a[i]); S[0] = ws.a[i].x; S[1] = ws.a[i].y; S[2] = ws.a[i].z; S[3] = l.x; S[4] = l.y; S[5] = l.z; }
+        else { S[0] = S[1] = S[2] = 0; S[3] = ws.a[i].x; S[4] = ws.a[i].y; S[5] = ws.a[i].z; }
+      }
+    }
+    for (int i = nb - 1; i > 0; i--) for (int k = 0; k < 10; k++) ws.Ic[10 * parent[i] + k] += ws.Ic[10 * i + k];
+    std::fill(ws.M.begin(), ws.M.end(), T(0));
+    for (int i = nb - 1; i > 0; i--) {
+      // spatial force F = Ic_i * S_i  -> (n_O, f)
+      const T* X = &ws.Ic[10 * i]; const T* S = &ws.S[6 * i];
+      V3<T> wv = {S[0], S[1], S[2]}, vO = {S[3], S[4], S[5]}, hh = {X[1], X[2], X[3]};
+      V3<T> f = X[0] * vO + cross(wv, hh);
+      V3<T> Iw = {X[4] * wv.x + X[5] * wv.y + X[6] * wv.z, X[5] * wv.x + X[7] * wv.y + X[8] * wv.z, X[6] * wv.x + X[8] * wv.y + X[9] * wv.z};
+      V3<T> n = Iw + cross(hh, vO);
+      int vi = vidx[i];
+      ws.M[vi * nv + vi] = S[0] * n.x + S[1] * n.y + S[2] * n.z + S[3] * f.x + S[4] * f.y + S[5] * f.z;
+      for (int j = parent[i]; j > 0; j = parent[j]) {
+        const T* Sj = &ws.S[6 * j];
+        T val = Sj[0] * n.x + Sj[1] * n.y + Sj[2] * n.z + Sj[3] * f.x + Sj[4] * f.y + Sj[5] * f.z;
+        ws.M[vi * nv + vidx[j]] = val; ws.M[vidx[j] * nv + vi] = val;
+      }
+      if (floating) {   // base columns: generalized velocity order is [lin; ang] at O
+        T col[6] = {f.x, f.y, f.z, n.x, n.y, n.z};
+        for (int k = 0; k < 6; k++) { ws.M[vi * nv + k] = col[k]; ws.M[k * nv + vi] = col[k]; }
+      }
+    }
+    if (floating) {
+      const T* X = &ws.Ic[0];
+      T m = X[0]; V3<T> hh = {X[1], X[2], X[3]};
+      // [ m 1 , -[h]x ; [h]x , I_O ]  in (lin, ang) order
+      T hx[9] = {0, -hh.z, hh.y, hh.z, 0, -hh.x, -hh.y, hh.x, 0};
+      T IO[9] = {X[4], X[5], X[6], X[5], X[7], X[8], X[6], X[8], X[9]};
+      for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) {
+        ws.M[r * nv + c] = (r == c) ? m : T(0);
+        ws.M[r * nv + 3 + c] = -hx[3 * r + c];
+        ws.M[(3 + r) * nv + c] = hx[3 * r + c];
+        ws.M[(3 + r) * nv + 3 + c] = IO[3 * r + c];
+      }
+    }
+  }
+
+  // ---- a6: narrow phase (Ground / HeightMap vs collision bodies expanded to candidate points) ----
+  bool terrain_query(V3<T> P, T& dist, V3<T>& n, int& pair) const {
+    if (ter.type == 1) { dist = P.z - T(ter.ground_z); n = {0, 0, 1}; pair = 0; return true; }
+    if (ter.type != 2) return false;
+    T dx = T(ter.x_size) / T(ter.xs - 1), dy = T(ter.y_size) / T(ter.ys - 1);
+    T x0 = T(ter.cx) - T(0.5) * T(ter.x_size), y0 = T(ter.cy) - T(0.5) * T(ter.y_size);
+    T gx = (P.x - x0) / dx, gy = (P.y - y0) / dy;
+    if (!(gx >= T(0)) || !(gy >= T(0)) || !(gx < T(ter.xs - 1)) || !(gy < T(ter.ys - 1))) return false;
+    int ix = int(gx), iy = int(gy);
+    T fx = gx - T(ix), fy = gy - T(iy);
+    const T* H = hmap.data();
+    T h00 = H[iy * ter.xs + ix], h10 = H[iy * ter.xs + ix + 1], h01 = H[(iy + 1) * ter.xs + ix], h11 = H[(iy + 1) * ter.xs + ix + 1];
+    T sx, sy; int tri;
+    if (fx >= fy) { sx = (h10 - h00); sy = (h11 - h10); tri = 0; }
+    else { sx = (h11 - h01); sy = (h01 - h00); tri = 1; }
+    T zt = h00 + sx * fx + sy * fy;
+    T nx = -sx / dx, ny = -sy / dy;
+    T inv = T(1) / std::sqrt(nx * nx + ny * ny + T(1));
+    n = {nx * inv, ny * inv, inv};
+    dist = (P.z - zt) * inv;
+    pair = 2 * (iy * (ter.xs - 1) + ix) + tri;
+    return true;
+  }
+
+  void collide(Workspace<T>& ws) const {
+    ws.contacts.clear();
+    std::vector<Contact<T>>& all = ws.all;
+    all.clear();
+    for (int k = 0; k < npts; k++) {
+      int b = pt_body[k];
+      V3<T> P = ws.p[b] + ws.R[b] * pt_pos[k];
+      T dist; V3<T> n; int pair;
+      if (!terrain_query(P, dist, n, pair)) continue;
+      T depth = pt_rad[k] - dist;
+      if (!(depth > T(0))) continue;
+      Contact<T> c;
+      c.pt = k; c.body = b; c.pair = pair; c.n = n; c.depth = depth;
+      c.pos = P - pt_rad[k] * n;
+      // tangent basis: t1 = normalised projection of e_x (or e_y when n is nearly along x)
+      V3<T> e = (std::fabs(n.x) < T(0.9)) ? V3<T>{1, 0, 0} : V3<T>{0, 1, 0};
+      V3<T> t = e - dot(e, n) * n;
+      T inv = T(1) / std::sqrt(dot(t, t));
+      c.t1 = inv * t; c.t2 = cross(n, c.t1);
+      c.lam = {0, 0, 0};
+      all.push_back(c);
+    }
+    if ((int)all.size() > KMAX) {
+      // keep the KMAX deepest (ties: lower candidate index wins), emitted in candidate order
+      std::vector<int> idx(all.size());
+      for (size_t i = 0; i < idx.size(); i++) idx[i] = int(i);
+      std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return all[a].depth > all[b].depth; });
+      idx.resize(KMAX);
+      std::sort(idx.begin(), idx.end());
+      for (int i : idx) ws.contacts.push_back(all[i]);
+    } else ws.contacts = all;
+  }
+
+  // ---- dense Cholesky  A = L L^T (lower), a5 getInverseMassMatrix ---------------------------------
+  static void cholesky(const T* A, T* L, int n) {
+    for (int j = 0; j < n; j++) {
+      T s = A[j * n + j];
+      for (int k = 0; k < j; k++) s -= L[j * n + k] * L[j * n + k];
+      T d = std::sqrt(s); L[j * n + j] = d;
+      T inv = T(1) / d;
+      for (int i = j + 1; i < n; i++) {
+        T t = A[i * n + j];
+        for (int k = 0; k < j; k++) t -= L[i * n + k] * L[j * n + k];
+        L[i * n + j] = t * inv;
+      }
+      for (int i = 0; i < j; i++) L[i * n + j] = T(0);
+    }
+  }
+  static void fwd_solve(const T* L, T* x, int n, int stride = 1) {   // x <- L^-1 x
+    for (int i = 0; i < n; i++) {
+      T s = x[i * stride];
+      for (int k = 0; k < i; k++) s -= L[i * n + k] * x[k * stride];
+      x[i * stride] = s / L[i * n + i];
+    }
+  }
+  static void bwd_solve(const T* L, T* x, int n) {   // x <- L^-T x
+    for (int i = n - 1; i >= 0; i--) {
+      T s = x[i];
+      for (int k = i + 1; k < n; k++) s -= L[k * n + i] * x[k];
+      x[i] = s / L[i * n + i];
+    }
+  }
+
+  // ---- a7: contact Jacobian rows in the contact frame; Jt is nv x 3K (row r of Jt = dof r) -------
+  void jacobians(Workspace<T>& ws) const {
+    int K = int(ws.contacts.size()), C = 3 * K;
+    std::fill(ws.Jt.begin(), ws.Jt.begin() + nv * C, T(0));
+    for (int ci = 0; ci < K; ci++) {
+      const Contact<T>& c = ws.contacts[ci];
+      V3<T> ax[3] = {c.t1, c.t2, c.n};
+      if (floating) {
+        V3<T> r = c.pos - ws.p[0];
+        for (int d = 0; d < 3; d++) {
+          V3<T> rc = cross(r, ax[d]);        // (e_k x r) . ax = e_k . (r x ax)
+          ws.Jt[0 * C + 3 * ci + d] = ax[d].x; ws.Jt[1 * C + 3 * ci + d] = ax[d].y; ws.Jt[2 * C + 3 * ci + d] = ax[d].z;
+          ws.Jt[3 * C + 3 * ci + d] = rc.x; ws.Jt[4 * C + 3 * ci + d] = rc.y; ws.Jt[5 * C + 3 * ci + d] = rc.z;
+        }
+      }
+      for (int j = c.body; parent[j] >= 0; j = parent[j]) {
+        V3<T> col = (jtype[j] == JT_REVOLUTE) ? cross(ws.a[j], c.pos - ws.p[j]) : ws.a[j];
+        for (int d = 0; d < 3; d++) ws.Jt[vidx[j] * C + 3 * ci + d] = dot(col, ax[d]);
+      }
+    }
+  }
+
+  // ---- a8: per-contact solve (Hwangbo et al. 2018, section IV) ------------------------------------
+  // G: 3x3 (rows/cols t1,t2,n) block G_ii; c: contact velocity without this contact's own impulse
+  // (already shifted by the ERP / restitution target).  Returns the new impulse.
+  void solve_one(const T* G, V3<T> c, T mu, V3<T>& lam) const {
+    if (c.z > T(0)) { lam = {0, 0, 0}; return; }                 // opening
+    // stick candidate: lam = -G^-1 c
+    T a = G[0], b = G[1], cc = G[2], d = G[4], e = G[5], f = G[8];
+    T c00 = d * f - e * e, c01 = cc * e - b * f, c02 = b * e - cc * d;
+    T c11 = a * f - cc * cc, c12 = b * cc - a * e, c22 = a * d - b * b;
+    T det = a * c00 + b * c01 + cc * c02;
+    T id = T(1) / det;
+    V3<T> ls = {-(c00 * c.x + c01 * c.y + c02 * c.z) * id, -(c01 * c.x + c11 * c.y + c12 * c.z) * id, -(c02 * c.x + c12 * c.y + c22 * c.z) * id};
+    if (ls.z >= T(0) && ls.x * ls.x + ls.y * ls.y <= mu * mu * ls.z * ls.z) { lam = ls; return; }   // stick
+    // slip: lam(theta) = lz(theta) * (mu cos, mu sin, 1),  lz = -c_z / (G_zz + mu (G_zx cos + G_zy sin))
+    // minimise f = c.lam + 1/2 lam^T G lam on that curve: find the - to + sign change of
+    //   g(theta) = (v_t . u_perp) D - mu (G_zt . u_perp)(v_t . u),    v_t = tangential part of c + G lam
+    // by NSEC-section search (a bisection generalised to 32 simultaneous probes), NROUNDS rounds.
+    auto eval = [&](T cs, T sn, T& gval, T& fval, V3<T>& l) -> bool {
+      T D = f + mu * (cc * cs + e * sn);
+      if (!(D > T(1e-12))) return false;
+      T lz = -c.z / D;
+      l = {mu * lz * cs, mu * lz * sn, lz};
+      T vx = c.x + a * l.x + b * l.y + cc * l.z;
+      T vy = c.y + b * l.x + d * l.y + e * l.z;
+      gval = (-vx * sn + vy * cs) * D - mu * (-cc * sn + e * cs) * (vx * cs + vy * sn);
+      fval = c.x * l.x + c.y * l.y + c.z * l.z + T(0.5) * (l.x * vx + l.y * vy - l.z * c.z) - T(0.5) * (c.x * l.x + c.y * l.y);
+      return true;
+    };
+    // note: fval above equals c.lam + 1/2 lam^T G lam with (G lam)_z = -c_z on the curve:
+    //   1/2 lam.(G lam) = 1/2 (lx (vx - cx) + ly (vy - cy) + lz (-cz))
+    T base_c = T(1), base_s = T(0);       // bracket start direction (contact-frame +x for round 0)
+    V3<T> best = {0, 0, 0};
+    bool have = false;
+    T glo = 0, ghi = 0; T lo_c = 1, lo_s = 0, hi_c = 1, hi_s = 0;
+    for (int r = 0; r < NROUNDS; r++) {
+      T gk[NSEC + 1], fk[NSEC + 1]; bool ok[NSEC + 1]; V3<T> lk[NSEC + 1];
+      for (int k = 0; k <= NSEC; k++) {
+        T cs = base_c * sec_c[r][k] - base_s * sec_s[r][k];
+        T sn = base_s * sec_c[r][k] + base_c * sec_s[r][k];
+        ok[k] = eval(cs, sn, gk[k], fk[k], lk[k]);
+      }
+      int pick = -1; T fbest = 0;
+      for (int k = 0; k < NSEC; k++) {
+        if (!ok[k] || !ok[k + 1]) continue;
+        if (gk[k] < T(0) && gk[k + 1] >= T(0)) {
+          if (pick < 0 || fk[k] < fbest) { pick = k; fbest = fk[k]; }
+        }
+      }
+      if (pick < 0) {
+        if (!have) {   // no bracket on the whole circle: take the probe with the least energy
+          int kb = -1;
+          for (int k = 0; k < NSEC; k++) if (ok[k] && (kb < 0 || fk[k] < fk[kb])) kb = k;
+          if (kb >= 0) { lam = lk[kb]; } else { lam = {0, 0, std::max(T(0), -c.z / f)}; }
+          return;
+        }
+        break;         // keep the bracket of the previous round
+      }
+      T cs0 = base_c * sec_c[r][pick] - base_s * sec_s[r][pick], sn0 = base_s * sec_c[r][pick] + base_c * sec_s[r][pick];
+      T cs1 = base_c * sec_c[r][pick + 1] - base_s * sec_s[r][pick + 1], sn1 = base_s * sec_c[r][pick + 1] + base_c * sec_s[r][pick + 1];
+      lo_c = cs0; lo_s = sn0; hi_c = cs1; hi_s = sn1; glo = gk[pick]; ghi = gk[pick + 1];
+      base_c = cs0; base_s = sn0; have = true; best = lk[pick];
+    }
+    // secant step inside the final bracket, direction re-normalised
+    T tt = (ghi - glo) != T(0) ? (-glo / (ghi - glo)) : T(0.5);
+    T cs = lo_c + tt * (hi_c - lo_c), sn = lo_s + tt * (hi_s - lo_s);
+    T inv = T(1) / std::sqrt(cs * cs + sn * sn);
+    cs *= inv; sn *= inv;
+    T gv_, fv_; V3<T> l;
+    if (eval(cs, sn, gv_, fv_, l)) lam = l; else lam = best;
+  }
+
+  // ---- a1: one World::integrate() for one environment -------------------------------------------
+  // ctrl arrays may be null (treated as zero).  gc/gv updated in place.
+  void step(T* gc, T* gv, const T* tau_ff, const T* ptarget, const T* vtarget, const T* kp, const T* kd, Workspace<T>& ws) const {
+    T dt = T(prm.dt);
+    fk(gc, ws);
+    rnea_bias(gv, ws);
+    crba(ws);
+    collide(ws);
+    // a5: generalized force with implicit PD (ArticulatedSystem::setPdGains / setPdTarget):
+    //   b = tau_ff + Kp (q* - q - dt v) + Kd (v* - v) - h ;   Mhat = M + dt Kd + dt^2 Kp
+    for (int i = 0; i < nv; i++) ws.b[i] = (tau_ff ? tau_ff[i] : T(0)) - ws.h[i];
+    ws.Mh = ws.M;
+    std::vector<T>& Mh = ws.Mh;
+    for (int i = 1; i < nb; i++) {
+      int vi = vidx[i], qi = qidx[i];
+      T kpi = kp ? kp[vi] : T(0), kdi = kd ? kd[vi] : T(0);
+      if (kpi != T(0) || kdi != T(0)) {
+        T qt = ptarget ? ptarget[qi] : T(0), vt = vtarget ? vtarget[vi] : T(0);
+        ws.b[vi] += kpi * (qt - gc[qi] - dt * gv[vi]) + kdi * (vt - gv[vi]);
+        Mh[vi * nv + vi] += dt * kdi + dt * dt * kpi;
+      }
+    }
+    cholesky(Mh.data(), ws.L.data(), nv);
+    for (int i = 0; i < nv; i++) ws.z[i] = ws.b[i];
+    fwd_solve(ws.L.data(), ws.z.data(), nv);
+    int K = int(ws.contacts.size()), C = 3 * K;
+    for (int i = 0; i < nv; i++) ws.rhs[i] = dt * ws.z[i];
+    ws.iters = 0;
+    if (K > 0) {
+      jacobians(ws);
+      // Y = L^-1 J^T (nv x C);  G = Y^T Y;  u0 = J v + dt Y^T z - target
+      for (int i = 0; i < nv * C; i++) ws.Y[i] = ws.Jt[i];
+      for (int c = 0; c < C; c++) fwd_solve(ws.L.data(), ws.Y.data() + c, nv, C);
+      for (int a = 0; a < C; a++) for (int b2 = 0; b2 < C; b2++) {
+        T s = 0;
+        for (int r = 0; r < nv; r++) s += ws.Y[r * C + a] * ws.Y[r * C + b2];
+        ws.G[a * C + b2] = s;
+      }
+      for (int a = 0; a < C; a++) {
+        T s = 0, s0 = 0;
+        for (int r = 0; r < nv; r++) { s0 += ws.Jt[r * C + a] * gv[r]; s += ws.Y[r * C + a] * ws.z[r]; }
+        ws.u[a] = s0 + dt * s;
+        if (a % 3 == 2) {
+          const Contact<T>& ct = ws.contacts[a / 3];
+          T target = T(prm.erp) * ct.depth / dt;
+          if (prm.restitution > 0 && s0 < -T(prm.rest_threshold)) target += -T(prm.restitution) * s0;
+          ws.u[a] -= target;
+        }
+      }
+      // a8: Gauss-Seidel over contacts (BisectionContactSolver::solve)
+      T alpha = T(prm.alpha_init), mu = T(prm.mu);
+      for (int it = 0; it < prm.max_iter; it++) {
+        T err = 0;
+        for (int i = 0; i < K; i++) {
+          Contact<T>& ct = ws.contacts[i];
+          T Gii[9];
+          for (int r = 0; r < 3; r++) for (int c2 = 0; c2 < 3; c2++) Gii[3 * r + c2] = ws.G[(3 * i + r) * C + 3 * i + c2];
+          V3<T> l0 = ct.lam;
+          V3<T> c0 = {ws.u[3 * i] - (Gii[0] * l0.x + Gii[1] * l0.y + Gii[2] * l0.z),
+                      ws.u[3 * i + 1] - (Gii[3] * l0.x + Gii[4] * l0.y + Gii[5] * l0.z),
+                      ws.u[3 * i + 2] - (Gii[6] * l0.x + Gii[7] * l0.y + Gii[8] * l0.z)};
+          V3<T> ln;
+          solve_one(Gii, c0, mu, ln);
+          V3<T> dl = alpha * (ln - l0);
+          ct.lam = l0 + dl;
+          for (int a = 0; a < C; a++) ws.u[a] += ws.G[a * C + 3 * i] * dl.x + ws.G[a * C + 3 * i + 1] * dl.y + ws.G[a * C + 3 * i + 2] * dl.z;
+          err = std::max(err, std::max(std::fabs(dl.x), std::max(std::fabs(dl.y), std::fabs(dl.z))));
+        }
+        ws.iters = it + 1;
+        alpha = std::max(T(prm.alpha_min), alpha * T(prm.alpha_decay));
+        if (err < T(prm.threshold)) break;
+      }
+      for (int r = 0; r < nv; r++) {
+        T s = 0;
+        for (int i = 0; i < K; i++) {
+          const V3<T>& l = ws.contacts[i].lam;
+          s += ws.Y[r * C + 3 * i] * l.x + ws.Y[r * C + 3 * i + 1] * l.y + ws.Y[r * C + 3 * i + 2] * l.z;
+        }
+        ws.rhs[r] += s;
+      }
+    }
+    // a9: v+ = v + L^-T (dt z + Y lam);  q+ = q (+) dt v+
+    bwd_solve(ws.L.data(), ws.rhs.data(), nv);
+    for (int i = 0; i < nv; i++) gv[i] += ws.rhs[i];
+    if (floating) {
+      for (int k = 0; k < 3; k++) gc[k] += dt * gv[k];
+      V3<T> w = {gv[3], gv[4], gv[5]};
+      T wn = std::sqrt(dot(w, w)), ang = wn * dt;
+      T qw, qx, qy, qz;
+      if (ang > T(1e-10)) { T s = std::sin(T(0.5) * ang) / wn; qw = std::cos(T(0.5) * ang); qx = s * w.x; qy = s * w.y; qz = s * w.z; }
+      else { qw = 1; qx = T(0.5) * dt * w.x; qy = T(0.5) * dt * w.y; qz = T(0.5) * dt * w.z; }
+      T pw = gc[3], px = gc[4], py = gc[5], pz = gc[6];
+      T nw = qw * pw - qx * px - qy * py - qz * pz;     // dq (x) q : world-frame angular velocity
+      T nx = qw * px + qx * pw + qy * pz - qz * py;
+      T ny = qw * py - qx * pz + qy * pw + qz * px;
+      T nz = qw * pz + qx * py - qy * px + qz * pw;
+      T inv = T(1) / std::sqrt(nw * nw + nx * nx + ny * ny + nz * nz);
+      gc[3] = nw * inv; gc[4] = nx * inv; gc[5] = ny * inv; gc[6] = nz * inv;
+    }
+    for (int i = 1; i < nb; i++) gc[qidx[i]] += dt * gv[vidx[i]];
+  }
+};
+
+}  // namespace orc
