@@ -1,0 +1,314 @@
+#!/usr/bin/env python3
+"""bench.py -- env-steps/s of the batched World::integrate() hot path (BASELINE.json metric).
+
+Workload (BASELINE.json configs[2], weak-scaled per GPU -> configs[4] at 8 GPUs):
+  4096 ANYmal-C-like environments per GPU on a 513x513 random rough height field (51.2 m square,
+  3-octave value noise, +-0.10 m), PD stance control with per-control-step target jitter.
+A bench "step" is one RaisimGym control step: ONE fused launch of 4 sub-steps of World::integrate()
+for every environment (= 4 x 4096 env-steps per GPU), followed by the observation kernel and, at
+N > 1, the NCCL all-gather of the observation rows.
+
+  value   env-steps/s with state, targets and terrain resident in HBM (targets refreshed D2D)
+  e2e     same metric through the C-ABI with HOST buffers: pinned H2D of the PD targets and D2H of
+          the (all-gathered) observation rows inside the timed region
+  --impl reference   the CPU path (oracle port of World::integrate(), OpenMP over envs, all host
+          cores) on the same workload -- /root/reference holds no buildable source
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 4096
+SUBSTEPS = 4
+GC0 = np.array([0, 0, 0.57, 1, 0, 0, 0, 0.03, 0.4, -0.8, -0.03, 0.4, -0.8, 0.03, -0.4, 0.8, -0.03, -0.4, 0.8], dtype=np.float64)
+KP, KD = 300.0, 8.0
+HM = dict(xs=513, ys=513, size=51.2, amp=0.10)
+RING = 8            # distinct PD-target sets cycled through (synthetic "policy output")
+L2_FLUSH_BYTES = 256 << 20
+
+
+def value_noise(rng, n, size_cells):
+    """bilinear value noise on an n x n grid with lattice spacing size_cells"""
+    m = (n - 1) // size_cells + 2
+    lat = rng.uniform(-1, 1, (m, m))
+    x = np.arange(n) / size_cells
+    i = x.astype(int); f = x - i
+    a = lat[np.ix_(i, i)]; b = lat[np.ix_(i, i + 1)]; c = lat[np.ix_(i + 1, i)]; d = lat[np.ix_(i + 1, i + 1)]
+    fy, fx = f[:, None], f[None, :]
+    return a * (1 - fy) * (1 - fx) + b * (1 - fy) * fx + c * fy * (1 - fx) + d * fy * fx
+
+
+def make_workload(rank, n_envs):
+    rng = np.random.default_rng(3000 + rank)
+    n = HM["xs"]
+    H = value_noise(rng, n, 32) + 0.5 * value_noise(rng, n, 8) + 0.25 * value_noise(rng, n, 2)
+    H = (HM["amp"] * H / np.abs(H).max()).astype(np.float32)
+    gc = np.tile(GC0, (n_envs, 1))
+    gc[:, 0:2] = rng.uniform(-0.4 * HM["size"], 0.4 * HM["size"], (n_envs, 2))      # inner 80 % of the map
+    gc[:, 2] = 0.75
+    gc[:, 7:] += rng.uniform(-0.2, 0.2, (n_envs, 12))
+    yaw = rng.uniform(-np.pi, np.pi, n_envs)
+    gc[:, 3] = np.cos(yaw / 2); gc[:, 6] = np.sin(yaw / 2)
+    gv = np.zeros((n_envs, 18))
+    targets = np.tile(GC0, (RING, n_envs, 1))
+    targets[:, :, 7:] += rng.uniform(-0.15, 0.15, (RING, n_envs, 12))
+    kp = np.r_[np.zeros(6), KP * np.ones(12)]; kd = np.r_[np.zeros(6), KD * np.ones(12)]
+    return H, gc, gv, targets, kp, kd
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def algorithmic_bytes_per_env_step(nq, nv, nj, kbar):
+    # reads gc, gv, tau_ff, pTarget, vTarget; writes gc+, gv+, tau_applied, count, 12 words per contact
+    return 4.0 * (2 * nq + 3 * nv + 2 * nj + 1 + 12.0 * kbar)
+
+
+def cpu_baseline(sample_envs, max_steps, budget_s=12.0):
+    """the oracle (a port: no reference binary exists) on all host cores, bounded sample of the workload"""
+    from oracle.oracle import Oracle
+    from oracle.urdf_tables import load_tables
+    from raisimlib_b200 import RSC_DIR
+    H, gc, gv, targets, kp, kd = make_workload(0, sample_envs)
+    o = Oracle(load_tables(os.path.join(RSC_DIR, "anymal_c_like.urdf")), params=dict(threshold=1e-6))
+    o.set_heightmap(HM["xs"], HM["ys"], HM["size"], HM["size"], 0.0, 0.0, H.astype(np.float64))
+    cores = os.cpu_count()
+    vt = np.zeros((sample_envs, 18))
+    for k in range(20):     # warm-up: robots land on the terrain
+        o.step(gc, gv, n_steps=SUBSTEPS, ptarget=targets[k % RING], vtarget=vt, kp=kp, kd=kd)
+    t0 = time.perf_counter(); done = 0; k = 0
+    while done < max_steps and time.perf_counter() - t0 < budget_s:
+        o.step(gc, gv, n_steps=SUBSTEPS, ptarget=targets[k % RING], vtarget=vt, kp=kp, kd=kd)
+        done += SUBSTEPS; k += 1
+    dt = time.perf_counter() - t0
+    return {"value": sample_envs * done / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_envs} envs x {done} sub-steps of the same workload (float64 oracle, OpenMP over envs, after 80 warm-up sub-steps)"}
+
+
+def run_reference(args):
+    """--impl reference: the CPU path on this box's host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.oracle import Oracle
+    from oracle.urdf_tables import load_tables
+    from raisimlib_b200 import RSC_DIR
+    n = ENVS_PER_GPU
+    H, gc, gv, targets, kp, kd = make_workload(0, n)
+    o = Oracle(load_tables(os.path.join(RSC_DIR, "anymal_c_like.urdf")), params=dict(threshold=1e-6))
+    o.set_heightmap(HM["xs"], HM["ys"], HM["size"], HM["size"], 0.0, 0.0, H.astype(np.float64))
+    vt = np.zeros((n, 18))
+    for k in range(max(args.warmup, 3)):
+        o.step(gc, gv, n_steps=SUBSTEPS, ptarget=targets[k % RING], vtarget=vt, kp=kp, kd=kd)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        o.step(gc, gv, n_steps=SUBSTEPS, ptarget=targets[k % RING], vtarget=vt, kp=kp, kd=kd)
+    dt = time.perf_counter() - t0
+    val = n * SUBSTEPS * args.steps / dt
+    cores = os.cpu_count()
+    line = {"impl": "reference", "metric": "env-steps/s", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{n} ANYmal-C-like envs on 513x513 rough height field, PD stance, {SUBSTEPS} sub-steps per step (CPU oracle port, {cores} threads)"},
+            "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} envs x {SUBSTEPS * args.steps} sub-steps (the full per-GPU workload), float64, OpenMP over envs"},
+            "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=25)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from raisimlib_b200 import capi, RSC_DIR
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W = max(args.warmup, 3)
+    n = args.envs
+    H, gc, gv, targets, kp, kd = make_workload(rank, n)
+    model = capi.Model(os.path.join(RSC_DIR, "anymal_c_like.urdf"))
+    bt = capi.Batch(model, n, device=local)
+    bt.set_params(threshold=1e-6)
+    bt.set_heightmap(HM["xs"], HM["ys"], HM["size"], HM["size"], 0.0, 0.0, H)
+    bt.set_pd_gains(kp, kd)
+    stream = torch.cuda.current_stream()
+    bt.set_stream(stream.cuda_stream)
+    bt.set_state(gc.astype(np.float32), gv.astype(np.float32))
+    od = bt.ob_dim()
+    tg_dev = torch.tensor(targets, dtype=torch.float32, device="cuda")                  # [RING, n, nq] resident in HBM
+    tg_pin = torch.tensor(targets, dtype=torch.float32).pin_memory()                    # host copies for the e2e arm
+    vt_dev = torch.zeros((n, 18), dtype=torch.float32, device="cuda")
+    bt.set_pd_target(tg_dev[0], vt_dev)
+    obs = torch.empty((n, od), dtype=torch.float32, device="cuda")
+    obs_all = torch.empty((world * n, od), dtype=torch.float32, device="cuda") if world > 1 else obs
+    obs_host = torch.empty((world * n, od), dtype=torch.float32).pin_memory()
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device="cuda")
+
+    def control_step(k, host_io):
+        if host_io:
+            bt.set_pd_target(tg_pin[k % RING], None)        # pinned H2D inside the timed region
+        else:
+            bt.set_pd_target(tg_dev[k % RING], None)        # D2D refresh of the resident targets
+        bt.integrate(SUBSTEPS)                               # ONE fused launch: 4 x World::integrate()
+        bt.observe(obs)
+        if world > 1:
+            dist.all_gather_into_tensor(obs_all, obs)        # the only collective of the path
+        if host_io:
+            obs_host.copy_(obs_all, non_blocking=True)       # D2H of the step's result
+            stream.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(host_io, steps, step0):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for k in range(steps):
+            flush.fill_(float(k))                            # evict L2 between timed iterations (256 MiB > 126 MB L2)
+            ev[k][0].record(stream)
+            if host_io:
+                bt.set_pd_target(tg_pin[(step0 + k) % RING], None)
+            else:
+                bt.set_pd_target(tg_dev[(step0 + k) % RING], None)
+            kev[k][0].record(stream)
+            bt.integrate(SUBSTEPS)
+            kev[k][1].record(stream)
+            bt.observe(obs)
+            if world > 1:
+                dist.all_gather_into_tensor(obs_all, obs)
+            if host_io:
+                obs_host.copy_(obs_all, non_blocking=True)
+            ev[k][1].record(stream)
+            if host_io:
+                stream.synchronize()                         # the caller reads the observation before acting
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        kms = sum(a.elapsed_time(b) for a, b in kev)
+        t = torch.tensor([ms, kms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)         # max over ranks
+        return float(t[0]), float(t[1])
+
+    for k in range(W):
+        control_step(k, False)
+    barrier()
+    l0 = bt.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, ms_kernel = timed(False, args.steps, W)
+    launches = bt.launch_count() - l0
+    ms_e2e, _ = timed(True, args.steps, W + args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    _, cnt = bt.contacts()
+    it = bt.solver_iterations()
+    g, _v = bt.get_state()
+    stats = torch.tensor([float(cnt.mean()), float(it.mean()), float(it.max()), float((g[:, 2] > 0.25).mean())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        stats /= world
+    if rank == 0:
+        total_env_steps = world * n * SUBSTEPS * args.steps
+        value = total_env_steps / (ms_dev * 1e-3)
+        e2e = total_env_steps / (ms_e2e * 1e-3)
+        kbar = float(stats[0])
+        B = algorithmic_bytes_per_env_step(19, 18, 12, kbar)
+        launch_ms = ms_kernel / args.steps
+        achieved = B * n * SUBSTEPS / (launch_ms * 1e-3) / 1e9
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak, peak_src = float(mp["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        line = {
+            "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{n} ANYmal-C-like envs per GPU on 513x513 rough height field (+-0.10 m), PD stance kp={KP} kd={KD}, dt=0.0025, {SUBSTEPS} sub-steps fused per step",
+                       "envs_per_gpu": n, "substeps_per_step": SUBSTEPS, "l2": "flushed between timed iterations (256 MiB write)",
+                       "mean_contacts_per_env": kbar, "mean_solver_iters": float(stats[1]), "max_solver_iters": float(stats[2]),
+                       "standing_fraction": float(stats[3]), "parallelism": f"env-shard x{world}" + (", NCCL obs all-gather" if world > 1 else "")},
+            "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": int(n * 19 * 4), "d2h_bytes_per_step": int(world * n * od * 4)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "rsb_step_kernel (fused FK+CRBA+RNEA+narrow-phase+contact solver+integrate)",
+                         "algorithmic_bytes_per_env_step": B, "launch_ms": launch_ms, "peak_source": peak_src,
+                         "note": "path is FP32-latency/issue bound, not HBM bound (SURVEY.md 7 hard part 2); see DESIGN.md roofline"},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(1024, 400)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,152 @@
+/* rsb.h -- C-ABI of the B200-native batched rigid-body step ("raisim batch").
+ *
+ * This is the drop-in boundary for the hot path raisim::World::integrate() =
+ * integrate1() + integrate2() and the ArticulatedSystem state/force/PD accessors around it
+ * (SURVEY.md section 8b).  The reference exposes that path as C++ classes, not a plugin ABI, and the
+ * reference snapshot holds none of the headers (/root/reference/.SUBMODULES.json:2 records
+ * "bytes": 0; the only consumer build recorded is /root/reference/.travis.yml:11,
+ * -DRAISIM_EXAMPLE=ON).  Each entry point below therefore cites the upstream *symbol* it replaces
+ * ([RECALL] in SURVEY.md: include/raisim/World.hpp, object/ArticulatedSystem/ArticulatedSystem.hpp,
+ * contact/Contact.hpp); the header-only facade in include/raisim/ forwards those symbols here.
+ *
+ * Rules: plain C, opaque handles, int status (0 = OK, negative = error, text via rsb_last_error()),
+ * no exceptions across the boundary, all buffers caller-owned.  One handle <-> one host thread.
+ * All batched arrays are float32; `where` says whether a caller buffer is host or device memory.
+ * Device work is enqueued on the batch's stream (rsb_batch_set_stream) and is asynchronous unless a
+ * host buffer is read back.
+ */
+#ifndef RSB_H_
+#define RSB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSB_OK 0
+#define RSB_ERR_INVALID (-1)
+#define RSB_ERR_PARSE (-2)
+#define RSB_ERR_CUDA (-3)
+#define RSB_ERR_UNSUPPORTED (-4)
+
+#define RSB_HOST 0
+#define RSB_DEVICE 1
+
+#define RSB_KMAX 8 /* contacts kept per environment (the deepest RSB_KMAX candidates) */
+
+/* ArticulatedSystem::ControlMode */
+#define RSB_FORCE_AND_TORQUE 0
+#define RSB_PD_PLUS_FEEDFORWARD_TORQUE 1
+
+typedef struct rsb_model rsb_model; /* immutable robot description (URDF -> tables) */
+typedef struct rsb_batch rsb_batch; /* N environments of one model on one GPU        */
+
+/* World::setTimeStep, setGravity, setERP, setContactSolverParam, setDefaultMaterial */
+typedef struct rsb_params {
+  float dt;          /* World::setTimeStep                               (default 0.0025) */
+  float gravity[3];  /* World::setGravity                                (0,0,-9.81)      */
+  float erp;         /* World::setERP                                    (0)              */
+  float alpha_init;  /* World::setContactSolverParam(alpha_init, ...)    (1)              */
+  float alpha_min;   /*                                                  (1)              */
+  float alpha_decay; /*                                                  (1)              */
+  int max_iter;      /*                                                  (150)            */
+  float threshold;   /*                                                  (1e-6, float32)  */
+  float mu;          /* World::setDefaultMaterial friction               (0.8)            */
+  float restitution; /* World::setDefaultMaterial restitution            (0)              */
+  float rest_threshold; /* restitution threshold velocity               (0.01)           */
+} rsb_params;
+
+/* raisim::Contact as returned by ArticulatedSystem::getContacts(): 12 words */
+typedef struct rsb_contact {
+  int32_t local_body;  /* Contact::getlocalBodyIndex()                                      */
+  int32_t pair_index;  /* terrain feature: 0 = Ground plane, 2*cell+tri on a HeightMap     */
+  float position[3];   /* Contact::getPosition()  (world)                                   */
+  float normal[3];     /* Contact::getNormal()    (world, terrain -> robot)                 */
+  float impulse[3];    /* Contact::getImpulse()   (world, on the robot)                     */
+  float depth;         /* Contact::getDepth()                                               */
+} rsb_contact;
+
+/* host-side view of the model tables (doubles; arrays owned by the model) */
+typedef struct rsb_model_tables {
+  int nb, nq, nv, floating, ncoll, npts;
+  const int *parent, *jtype, *qidx, *vidx, *depth;
+  const double *jpos, *jrot, *axis, *mass, *com, *inertia, *jlimit;
+  const int *cbody, *ctype;
+  const double *csize, *cpos, *crot;
+  const int *pt_body, *pt_coll, *pt_feat;
+  const double *pt_pos, *pt_rad;
+} rsb_model_tables;
+
+/* zero-copy device view (rows are padded: element (env, i) of X lives at X[env * X_stride + i]) */
+typedef struct rsb_device_view {
+  int num_envs, nq, nv, gc_stride, gv_stride;
+  float *gc, *gv, *tau_ff, *ptarget, *vtarget;
+  int32_t* ncontacts;
+  rsb_contact* contacts; /* [num_envs][RSB_KMAX] */
+} rsb_device_view;
+
+const char* rsb_last_error(void);
+int rsb_version(void);
+
+/* ---- model: World::addArticulatedSystem(urdf) parsing half ---------------------- */
+int rsb_model_create_from_urdf(const char* path_or_xml, rsb_model** out);
+void rsb_model_destroy(rsb_model* m);
+int rsb_model_dims(const rsb_model* m, int* nq, int* nv, int* nb, int* ncoll, int* npts);
+int rsb_model_get_tables(const rsb_model* m, rsb_model_tables* out);
+int rsb_model_body_index(const rsb_model* m, const char* name);    /* ArticulatedSystem::getBodyIdx   */
+const char* rsb_model_body_name(const rsb_model* m, int body);
+const char* rsb_model_joint_name(const rsb_model* m, int body);
+int rsb_model_frame_index(const rsb_model* m, const char* name);   /* getFrameIdxByName (link frames) */
+int rsb_model_frame(const rsb_model* m, int frame, int* body, double pos[3], double rot[9]);
+
+/* ---- batch lifetime --------------------------------------------------------------------------- */
+int rsb_batch_create(const rsb_model* m, int num_envs, int device, rsb_batch** out);
+void rsb_batch_destroy(rsb_batch* b);
+int rsb_batch_set_stream(rsb_batch* b, void* cuda_stream);
+int rsb_batch_sync(rsb_batch* b);
+int rsb_batch_num_envs(const rsb_batch* b);
+
+/* ---- world set-up ----------------------------------------------------------------------------- */
+int rsb_batch_set_ground(rsb_batch* b, float z);                                   /* World::addGround    */
+int rsb_batch_set_heightmap(rsb_batch* b, int x_samples, int y_samples, float x_size, float y_size,
+                            float center_x, float center_y, const float* heights_host); /* World::addHeightMap */
+int rsb_batch_clear_terrain(rsb_batch* b);
+int rsb_batch_set_params(rsb_batch* b, const rsb_params* p);
+int rsb_batch_get_params(const rsb_batch* b, rsb_params* p);
+int rsb_params_default(rsb_params* p);
+
+/* ---- state and actuation (ArticulatedSystem::setState/getState/setPdGains/setPdTarget/
+ *      setGeneralizedForce/setControlMode); buffers are tight [env_count][nq|nv] float32 ---------- */
+int rsb_batch_set_state(rsb_batch* b, const float* gc, const float* gv, int env_begin, int env_count, int where);
+int rsb_batch_get_state(rsb_batch* b, float* gc, float* gv, int env_begin, int env_count, int where);
+int rsb_batch_set_pd_gains(rsb_batch* b, const float* kp, const float* kd);        /* [nv], host, all envs */
+int rsb_batch_set_pd_target(rsb_batch* b, const float* ptarget, const float* vtarget, int env_begin, int env_count, int where);
+int rsb_batch_set_generalized_force(rsb_batch* b, const float* tau, int env_begin, int env_count, int where);
+int rsb_batch_set_control_mode(rsb_batch* b, int mode);
+
+/* ---- the hot path: World::integrate1(), integrate2(), integrate() ----------------------------- */
+int rsb_batch_integrate1(rsb_batch* b);               /* kinematics, collision, M, h (for the getters)   */
+int rsb_batch_integrate2(rsb_batch* b);               /* contact solve + state integration               */
+int rsb_batch_integrate(rsb_batch* b, int substeps);  /* substeps x integrate(), one fused launch        */
+
+/* ---- read-backs (lazy getters of the reference); valid after integrate1/integrate --- */
+int rsb_batch_get_mass_matrix(rsb_batch* b, int env_begin, int env_count, float* out, int where);     /* [n][nv*nv] getMassMatrix     */
+int rsb_batch_get_nonlinearities(rsb_batch* b, int env_begin, int env_count, float* out, int where);  /* [n][nv]    getNonlinearities */
+int rsb_batch_get_body_poses(rsb_batch* b, int env_begin, int env_count, float* rot, float* pos, int where); /* [n][nb*9],[n][nb*3] */
+int rsb_batch_get_contacts(rsb_batch* b, rsb_contact* out, int32_t* counts, int env_begin, int env_count, int where); /* out [n][RSB_KMAX] */
+int rsb_batch_get_contact_points(rsb_batch* b, int32_t* pt_index, int env_begin, int env_count, int where);          /* [n][RSB_KMAX] candidate-point ids */
+int rsb_batch_get_solver_iterations(rsb_batch* b, int32_t* iters, int env_begin, int env_count, int where);          /* getContactSolver().getLoopCounter() */
+int rsb_batch_device_ptrs(rsb_batch* b, rsb_device_view* view);
+int64_t rsb_batch_launch_count(const rsb_batch* b);   /* kernels launched by this batch so far */
+
+/* ---- RaisimGym observation row (VectorizedEnvironment::observe), ANYmal locomotion layout:
+ *      [z, R^T e_z (3), joint q (nq-7), R^T v (3), R^T w (3), joint rates (nv-6)]  -> ob_dim = nq+nv-3 -- */
+int rsb_batch_ob_dim(const rsb_batch* b);
+int rsb_batch_observe(rsb_batch* b, float* obs, int env_begin, int env_count, int where);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSB_H_ */

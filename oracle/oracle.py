@@ -36,7 +36,7 @@ class _ModelDesc(C.Structure):
 
 class _Debug(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("M", "h", "R", "p", "ncontacts", "c_pt", "c_body", "c_pair", "c_pos",
-                                          "c_normal", "c_depth", "c_lambda", "iters")]
+                                          "c_normal", "c_depth", "c_lambda", "iters", "G", "u0")]
 
 
 _lib = None
@@ -117,7 +117,8 @@ class Oracle:
             out = dict(M=np.zeros((n, nv, nv)), h=np.zeros((n, nv)), R=np.zeros((n, nb, 3, 3)), p=np.zeros((n, nb, 3)),
                        ncontacts=np.zeros(n, np.int32), c_pt=np.zeros((n, K), np.int32), c_body=np.zeros((n, K), np.int32),
                        c_pair=np.zeros((n, K), np.int32), c_pos=np.zeros((n, K, 3)), c_normal=np.zeros((n, K, 3)),
-                       c_depth=np.zeros((n, K)), c_lambda=np.zeros((n, K, 3)), iters=np.zeros(n, np.int32))
+                       c_depth=np.zeros((n, K)), c_lambda=np.zeros((n, K, 3)), iters=np.zeros(n, np.int32),
+                       G=np.zeros((n, 3 * K, 3 * K)), u0=np.zeros((n, 3 * K)))
             dbg = _Debug(**{k: v.ctypes.data for k, v in out.items()})
         lib().orc_step(self.h, n, n_steps, _p(gc), _p(gv), _p(tau_ff), _p(ptarget), _p(vtarget), _p(kp), _p(kd),
                        int(nthreads), C.byref(dbg) if dbg is not None else None)

@@ -22,6 +22,8 @@ struct OrcDebug {       // every pointer optional; sized for n_envs; filled from
   double* c_depth;      // [n][KMAX]
   double* c_lambda;     // [n][KMAX*3]  contact-frame impulse (t1,t2,n)
   int* iters;           // [n]
+  double* G;            // [n][(3*KMAX)^2]  Delassus matrix of the kept contacts (row stride 3*KMAX)
+  double* u0;           // [n][3*KMAX]      free contact velocity minus target
 };
 
 struct Handle {
@@ -62,6 +64,8 @@ static void run(Sim<T>& sim, int n_envs, int n_steps, double* gc, double* gv, co
         int K = int(ws.contacts.size());
         if (dbg->ncontacts) dbg->ncontacts[e] = K;
         if (dbg->iters) dbg->iters[e] = ws.iters;
+        if (dbg->G) for (int a = 0; a < 3 * K; a++) for (int b2 = 0; b2 < 3 * K; b2++) dbg->G[(size_t)e * 9 * KMAX * KMAX + a * 3 * KMAX + b2] = double(ws.G[a * 3 * K + b2]);
+        if (dbg->u0) for (int a = 0; a < 3 * K; a++) dbg->u0[(size_t)e * 3 * KMAX + a] = double(ws.u0[a]);
         for (int k = 0; k < KMAX; k++) {
           size_t o = (size_t)e * KMAX + k;
           bool on = k < K;

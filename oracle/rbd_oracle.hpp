@@ -27,7 +27,7 @@
 namespace orc {
 
 constexpr int JT_FIXED = 0, JT_REVOLUTE = 1, JT_PRISMATIC = 2, JT_FLOATING = 3;
-constexpr int KMAX = 10;           // contacts kept per environment (deepest KMAX of the candidates)
+constexpr int KMAX = 8;            // contacts kept per environment (deepest KMAX of the candidates) == RSB_KMAX
 constexpr int NSEC = 32;           // sections per refinement round of the slip search
 constexpr int NROUNDS = 4;         // rounds: bracket 2*pi/32^r
 
@@ -107,7 +107,7 @@ template <typename T> struct Workspace {
   std::vector<V3<T>> p, a, w, v, wd, vd, F, N;
   std::vector<T> Ic;             // 10 per body: m, h(3), I_O(6: xx xy xz yy yz zz)
   std::vector<T> S;              // 6 per body: [ang(3); lin_at_O(3)]
-  std::vector<T> M, Mh, L, h, b, z, Jt, Y, G, u, rhs;
+  std::vector<T> M, Mh, L, h, b, z, Jt, Y, G, u, u0, rhs;
   std::vector<Contact<T>> contacts, all;
   int iters = 0;
 };
@@ -163,7 +163,7 @@ template <typename T> class Sim {
     ws.R.resize(nb); ws.p.resize(nb); ws.a.resize(nb); ws.w.resize(nb); ws.v.resize(nb); ws.wd.resize(nb); ws.vd.resize(nb);
     ws.F.resize(nb); ws.N.resize(nb); ws.Ic.resize(10 * nb); ws.S.resize(6 * nb);
     ws.M.resize(nv * nv); ws.Mh.resize(nv * nv); ws.L.resize(nv * nv); ws.h.resize(nv); ws.b.resize(nv); ws.z.resize(nv); ws.rhs.resize(nv);
-    ws.Jt.resize(nv * 3 * KMAX); ws.Y.resize(nv * 3 * KMAX); ws.G.resize(9 * KMAX * KMAX); ws.u.resize(3 * KMAX);
+    ws.Jt.resize(nv * 3 * KMAX); ws.Y.resize(nv * 3 * KMAX); ws.G.resize(9 * KMAX * KMAX); ws.u.resize(3 * KMAX); ws.u0.resize(3 * KMAX);
   }
 
   // ---- a2: forward kinematics (ArticulatedSystem::updateKinematics) -----------------------------
@@ -543,6 +543,7 @@ template <typename T> class Sim {
           ws.u[a] -= target;
         }
       }
+      for (int a = 0; a < C; a++) ws.u0[a] = ws.u[a];
       // a8: Gauss-Seidel over contacts (BisectionContactSolver::solve)
       T alpha = T(prm.alpha_init), mu = T(prm.mu);
       for (int it = 0; it < prm.max_iter; it++) {

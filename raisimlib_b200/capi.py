@@ -1,0 +1,327 @@
+"""ctypes binding of the C-ABI in include/rsb.h (raisimlib_b200/librsb.so).
+
+Thin by design: the product is the CUDA library; Python only drives it from tests and bench.py.
+There is NO CPU fallback -- if librsb.so is missing or no GPU is visible the calls fail loudly.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librsb.so")
+KMAX = 8
+HOST, DEVICE = 0, 1
+FORCE_AND_TORQUE, PD_PLUS_FEEDFORWARD_TORQUE = 0, 1
+
+
+class RsbError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("dt", C.c_float), ("gravity", C.c_float * 3), ("erp", C.c_float), ("alpha_init", C.c_float),
+                ("alpha_min", C.c_float), ("alpha_decay", C.c_float), ("max_iter", C.c_int), ("threshold", C.c_float),
+                ("mu", C.c_float), ("restitution", C.c_float), ("rest_threshold", C.c_float)]
+
+
+class Contact(C.Structure):
+    _fields_ = [("local_body", C.c_int32), ("pair_index", C.c_int32), ("position", C.c_float * 3),
+                ("normal", C.c_float * 3), ("impulse", C.c_float * 3), ("depth", C.c_float)]
+
+
+CONTACT_DTYPE = np.dtype([("local_body", np.int32), ("pair_index", np.int32), ("position", np.float32, 3),
+                          ("normal", np.float32, 3), ("impulse", np.float32, 3), ("depth", np.float32)])
+assert CONTACT_DTYPE.itemsize == C.sizeof(Contact) == 48
+
+
+class ModelTables(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("nb", "nq", "nv", "floating", "ncoll", "npts")] +
+                [(n, C.POINTER(C.c_int)) for n in ("parent", "jtype", "qidx", "vidx", "depth")] +
+                [(n, C.POINTER(C.c_double)) for n in ("jpos", "jrot", "axis", "mass", "com", "inertia", "jlimit")] +
+                [(n, C.POINTER(C.c_int)) for n in ("cbody", "ctype")] +
+                [(n, C.POINTER(C.c_double)) for n in ("csize", "cpos", "crot")] +
+                [(n, C.POINTER(C.c_int)) for n in ("pt_body", "pt_coll", "pt_feat")] +
+                [(n, C.POINTER(C.c_double)) for n in ("pt_pos", "pt_rad")])
+
+
+class DeviceView(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("num_envs", "nq", "nv", "gc_stride", "gv_stride")] +
+                [(n, C.c_void_p) for n in ("gc", "gv", "tau_ff", "ptarget", "vtarget", "ncontacts", "contacts")])
+
+
+EXPORTED = [
+    "rsb_last_error", "rsb_version", "rsb_params_default",
+    "rsb_model_create_from_urdf", "rsb_model_destroy", "rsb_model_dims", "rsb_model_get_tables", "rsb_model_body_index",
+    "rsb_model_body_name", "rsb_model_joint_name", "rsb_model_frame_index", "rsb_model_frame",
+    "rsb_batch_create", "rsb_batch_destroy", "rsb_batch_set_stream", "rsb_batch_sync", "rsb_batch_num_envs",
+    "rsb_batch_set_ground", "rsb_batch_set_heightmap", "rsb_batch_clear_terrain", "rsb_batch_set_params", "rsb_batch_get_params",
+    "rsb_batch_set_state", "rsb_batch_get_state", "rsb_batch_set_pd_gains", "rsb_batch_set_pd_target",
+    "rsb_batch_set_generalized_force", "rsb_batch_set_control_mode",
+    "rsb_batch_integrate1", "rsb_batch_integrate2", "rsb_batch_integrate",
+    "rsb_batch_get_mass_matrix", "rsb_batch_get_nonlinearities", "rsb_batch_get_body_poses", "rsb_batch_get_contacts",
+    "rsb_batch_get_contact_points", "rsb_batch_get_solver_iterations", "rsb_batch_device_ptrs", "rsb_batch_launch_count",
+    "rsb_batch_ob_dim", "rsb_batch_observe",
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RsbError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
+        L = C.CDLL(LIB_PATH)
+        L.rsb_last_error.restype = C.c_char_p
+        L.rsb_model_body_name.restype = C.c_char_p
+        L.rsb_model_joint_name.restype = C.c_char_p
+        L.rsb_batch_launch_count.restype = C.c_int64
+        L.rsb_model_create_from_urdf.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.rsb_model_destroy.argtypes = [C.c_void_p]
+        L.rsb_model_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5
+        L.rsb_model_get_tables.argtypes = [C.c_void_p, C.POINTER(ModelTables)]
+        L.rsb_model_body_index.argtypes = [C.c_void_p, C.c_char_p]
+        L.rsb_model_body_name.argtypes = [C.c_void_p, C.c_int]
+        L.rsb_model_joint_name.argtypes = [C.c_void_p, C.c_int]
+        L.rsb_model_frame_index.argtypes = [C.c_void_p, C.c_char_p]
+        L.rsb_model_frame.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+        L.rsb_batch_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.rsb_batch_destroy.argtypes = [C.c_void_p]
+        L.rsb_batch_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.rsb_batch_sync.argtypes = [C.c_void_p]
+        L.rsb_batch_num_envs.argtypes = [C.c_void_p]
+        L.rsb_batch_set_ground.argtypes = [C.c_void_p, C.c_float]
+        L.rsb_batch_set_heightmap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        L.rsb_batch_clear_terrain.argtypes = [C.c_void_p]
+        L.rsb_batch_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
+        L.rsb_batch_get_params.argtypes = [C.c_void_p, C.POINTER(Params)]
+        L.rsb_params_default.argtypes = [C.POINTER(Params)]
+        for n in ("rsb_batch_set_state", "rsb_batch_get_state", "rsb_batch_set_pd_target"):
+            getattr(L, n).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.rsb_batch_set_pd_gains.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rsb_batch_set_generalized_force.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.rsb_batch_set_control_mode.argtypes = [C.c_void_p, C.c_int]
+        L.rsb_batch_integrate1.argtypes = [C.c_void_p]
+        L.rsb_batch_integrate2.argtypes = [C.c_void_p]
+        L.rsb_batch_integrate.argtypes = [C.c_void_p, C.c_int]
+        for n in ("rsb_batch_get_mass_matrix", "rsb_batch_get_nonlinearities"):
+            getattr(L, n).argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.rsb_batch_get_body_poses.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.rsb_batch_get_contacts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.rsb_batch_get_contact_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.rsb_batch_get_solver_iterations.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.rsb_batch_device_ptrs.argtypes = [C.c_void_p, C.POINTER(DeviceView)]
+        L.rsb_batch_launch_count.argtypes = [C.c_void_p]
+        L.rsb_batch_ob_dim.argtypes = [C.c_void_p]
+        L.rsb_batch_observe.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _ck(rc):
+    if rc < 0:
+        raise RsbError(lib().rsb_last_error().decode())
+    return rc
+
+
+def _ptr(a):
+    """numpy array -> host pointer; torch CUDA tensor -> device pointer; int -> raw pointer."""
+    if a is None:
+        return None, HOST
+    if isinstance(a, np.ndarray):
+        assert a.flags.c_contiguous
+        return a.ctypes.data_as(C.c_void_p), HOST
+    if hasattr(a, "data_ptr"):
+        assert a.is_contiguous()
+        return C.c_void_p(a.data_ptr()), (DEVICE if a.is_cuda else HOST)
+    raise TypeError(type(a))
+
+
+class Model:
+    def __init__(self, path_or_xml):
+        h = C.c_void_p()
+        _ck(lib().rsb_model_create_from_urdf(path_or_xml.encode(), C.byref(h)))
+        self.h = h
+        d = [C.c_int() for _ in range(5)]
+        _ck(lib().rsb_model_dims(h, *[C.byref(x) for x in d]))
+        self.nq, self.nv, self.nb, self.ncoll, self.npts = [x.value for x in d]
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().rsb_model_destroy(self.h)
+            self.h = None
+
+    def tables(self):
+        t = ModelTables()
+        _ck(lib().rsb_model_get_tables(self.h, C.byref(t)))
+        nb, nc, npt = t.nb, t.ncoll, t.npts
+        arr = lambda p, n, dt: np.ctypeslib.as_array(p, shape=(n,)).astype(dt).copy() if n > 0 else np.zeros(0, dt)
+        out = dict(nb=nb, nq=t.nq, nv=t.nv, floating=t.floating, ncoll=nc, npts=npt)
+        for k in ("parent", "jtype", "qidx", "vidx", "depth"):
+            out[k] = arr(getattr(t, k), nb, np.int32)
+        for k, w in (("jpos", 3), ("jrot", 9), ("axis", 3), ("mass", 1), ("com", 3), ("inertia", 6), ("jlimit", 2)):
+            a = arr(getattr(t, k), nb * w, np.float64)
+            out[k] = a.reshape(nb, w) if w > 1 else a
+        for k in ("cbody", "ctype"):
+            out[k] = arr(getattr(t, k), nc, np.int32)
+        for k, w in (("csize", 3), ("cpos", 3), ("crot", 9)):
+            out[k] = arr(getattr(t, k), nc * w, np.float64).reshape(nc, w)
+        for k in ("pt_body", "pt_coll", "pt_feat"):
+            out[k] = arr(getattr(t, k), npt, np.int32)
+        out["pt_pos"] = arr(t.pt_pos, npt * 3, np.float64).reshape(npt, 3)
+        out["pt_rad"] = arr(t.pt_rad, npt, np.float64)
+        out["body_names"] = [lib().rsb_model_body_name(self.h, i).decode() for i in range(nb)]
+        out["joint_names"] = [lib().rsb_model_joint_name(self.h, i).decode() for i in range(nb)]
+        return out
+
+    def body_index(self, name):
+        return _ck(lib().rsb_model_body_index(self.h, name.encode()))
+
+
+class Batch:
+    """N environments of one model on one GPU; mirrors World/ArticulatedSystem calls batch-wide."""
+
+    def __init__(self, model, num_envs, device=0):
+        self.model = model
+        h = C.c_void_p()
+        _ck(lib().rsb_batch_create(model.h, num_envs, device, C.byref(h)))
+        self.h, self.n, self.nq, self.nv, self.nb = h, num_envs, model.nq, model.nv, model.nb
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().rsb_batch_destroy(self.h)
+            self.h = None
+
+    # world set-up
+    def set_stream(self, stream_ptr):
+        _ck(lib().rsb_batch_set_stream(self.h, C.c_void_p(stream_ptr)))
+
+    def sync(self):
+        _ck(lib().rsb_batch_sync(self.h))
+
+    def set_ground(self, z=0.0):
+        _ck(lib().rsb_batch_set_ground(self.h, z))
+
+    def set_heightmap(self, xs, ys, x_size, y_size, cx, cy, heights):
+        hh = np.ascontiguousarray(heights, dtype=np.float32).reshape(-1)
+        assert hh.size == xs * ys
+        _ck(lib().rsb_batch_set_heightmap(self.h, xs, ys, x_size, y_size, cx, cy, hh.ctypes.data_as(C.c_void_p)))
+
+    def clear_terrain(self):
+        _ck(lib().rsb_batch_clear_terrain(self.h))
+
+    def get_params(self):
+        p = Params()
+        _ck(lib().rsb_batch_get_params(self.h, C.byref(p)))
+        return p
+
+    def set_params(self, **kw):
+        p = self.get_params()
+        for k, v in kw.items():
+            if k == "gravity":
+                p.gravity[0], p.gravity[1], p.gravity[2] = v
+            else:
+                setattr(p, k, v)
+        _ck(lib().rsb_batch_set_params(self.h, C.byref(p)))
+
+    # state / actuation
+    def set_state(self, gc=None, gv=None, env_begin=0, env_count=None):
+        n = self.n - env_begin if env_count is None else env_count
+        pg, w1 = _ptr(gc); pv, w2 = _ptr(gv)
+        _ck(lib().rsb_batch_set_state(self.h, pg, pv, env_begin, n, w1 if gc is not None else w2))
+
+    def get_state(self, env_begin=0, env_count=None):
+        n = self.n - env_begin if env_count is None else env_count
+        gc, gv = np.empty((n, self.nq), np.float32), np.empty((n, self.nv), np.float32)
+        _ck(lib().rsb_batch_get_state(self.h, gc.ctypes.data_as(C.c_void_p), gv.ctypes.data_as(C.c_void_p), env_begin, n, HOST))
+        return gc, gv
+
+    def get_state_into(self, gc, gv, env_begin=0, env_count=None):
+        n = self.n - env_begin if env_count is None else env_count
+        pg, w1 = _ptr(gc); pv, w2 = _ptr(gv)
+        _ck(lib().rsb_batch_get_state(self.h, pg, pv, env_begin, n, w1 if gc is not None else w2))
+
+    def set_pd_gains(self, kp, kd):
+        kp = np.ascontiguousarray(np.broadcast_to(np.asarray(kp, np.float32), (self.nv,)))
+        kd = np.ascontiguousarray(np.broadcast_to(np.asarray(kd, np.float32), (self.nv,)))
+        _ck(lib().rsb_batch_set_pd_gains(self.h, kp.ctypes.data_as(C.c_void_p), kd.ctypes.data_as(C.c_void_p)))
+
+    def set_pd_target(self, ptarget=None, vtarget=None, env_begin=0, env_count=None):
+        n = self.n - env_begin if env_count is None else env_count
+        pp, w1 = _ptr(ptarget); pv, w2 = _ptr(vtarget)
+        _ck(lib().rsb_batch_set_pd_target(self.h, pp, pv, env_begin, n, w1 if ptarget is not None else w2))
+
+    def set_generalized_force(self, tau, env_begin=0, env_count=None):
+        n = self.n - env_begin if env_count is None else env_count
+        p, w = _ptr(tau)
+        _ck(lib().rsb_batch_set_generalized_force(self.h, p, env_begin, n, w))
+
+    def set_control_mode(self, mode):
+        _ck(lib().rsb_batch_set_control_mode(self.h, mode))
+
+    # hot path
+    def integrate1(self):
+        _ck(lib().rsb_batch_integrate1(self.h))
+
+    def integrate2(self):
+        _ck(lib().rsb_batch_integrate2(self.h))
+
+    def integrate(self, substeps=1):
+        _ck(lib().rsb_batch_integrate(self.h, substeps))
+
+    # read-backs
+    def mass_matrix(self, env_begin=0, env_count=None):
+        n = self.n - env_begin if env_count is None else env_count
+        out = np.empty((n, self.nv, self.nv), np.float32)
+        _ck(lib().rsb_batch_get_mass_matrix(self.h, env_begin, n, out.ctypes.data_as(C.c_void_p), HOST))
+        return out
+
+    def nonlinearities(self, env_begin=0, env_count=None):
+        n = self.n - env_begin if env_count is None else env_count
+        out = np.empty((n, self.nv), np.float32)
+        _ck(lib().rsb_batch_get_nonlinearities(self.h, env_begin, n, out.ctypes.data_as(C.c_void_p), HOST))
+        return out
+
+    def body_poses(self, env_begin=0, env_count=None):
+        n = self.n - env_begin if env_count is None else env_count
+        R, p = np.empty((n, self.nb, 3, 3), np.float32), np.empty((n, self.nb, 3), np.float32)
+        _ck(lib().rsb_batch_get_body_poses(self.h, env_begin, n, R.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p), HOST))
+        return R, p
+
+    def contacts(self, env_begin=0, env_count=None):
+        n = self.n - env_begin if env_count is None else env_count
+        out = np.empty((n, KMAX), CONTACT_DTYPE)
+        cnt = np.empty(n, np.int32)
+        _ck(lib().rsb_batch_get_contacts(self.h, out.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p), env_begin, n, HOST))
+        return out, cnt
+
+    def contact_points(self, env_begin=0, env_count=None):
+        n = self.n - env_begin if env_count is None else env_count
+        out = np.empty((n, KMAX), np.int32)
+        _ck(lib().rsb_batch_get_contact_points(self.h, out.ctypes.data_as(C.c_void_p), env_begin, n, HOST))
+        return out
+
+    def solver_iterations(self, env_begin=0, env_count=None):
+        n = self.n - env_begin if env_count is None else env_count
+        out = np.empty(n, np.int32)
+        _ck(lib().rsb_batch_get_solver_iterations(self.h, out.ctypes.data_as(C.c_void_p), env_begin, n, HOST))
+        return out
+
+    def device_view(self):
+        v = DeviceView()
+        _ck(lib().rsb_batch_device_ptrs(self.h, C.byref(v)))
+        return v
+
+    def launch_count(self):
+        return lib().rsb_batch_launch_count(self.h)
+
+    def ob_dim(self):
+        return lib().rsb_batch_ob_dim(self.h)
+
+    def observe(self, out=None, env_begin=0, env_count=None):
+        n = self.n - env_begin if env_count is None else env_count
+        if out is None:
+            out = np.empty((n, self.ob_dim()), np.float32)
+        p, w = _ptr(out)
+        _ck(lib().rsb_batch_observe(self.h, p, env_begin, n, w))
+        return out

@@ -1,0 +1,554 @@
+// C-ABI implementation (include/rsb.h): batch memory, model-constant blob, kernel launches.
+// No CPU fallback: every compute entry point launches the sm_100a kernel or fails loudly.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "model.hpp"
+#include "step_kernel.cuh"
+#include "aux_kernels.cuh"
+
+using namespace rsb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                           \
+  do {                                                                                                     \
+    cudaError_t e_ = (call);                                                                               \
+    if (e_ != cudaSuccess) return fail(RSB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct rsb_model { Model md; };
+
+struct rsb_batch {
+  const rsb_model* model = nullptr;
+  int N = 0, device = 0;
+  int nq = 0, nv = 0, nb = 0;
+  int gc_stride = 0, gv_stride = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  rsb_params prm{};
+  int control_mode = RSB_PD_PLUS_FEEDFORWARD_TORQUE;
+  bool pd_set = false;
+  // device buffers
+  float *gc = nullptr, *gv = nullptr, *tau = nullptr, *pt = nullptr, *vt = nullptr;
+  int *ncontacts = nullptr, *contact_pt = nullptr, *iters = nullptr;
+  rsb_contact* contacts = nullptr;
+  float *dbg_M = nullptr, *dbg_h = nullptr, *dbg_R = nullptr, *dbg_p = nullptr;
+  float* hmap = nullptr;
+  float* staging = nullptr;      // tight-row staging for host<->device repacking
+  size_t staging_words = 0;
+  uint32_t* blob = nullptr;
+  std::vector<uint32_t> blob_host;
+  BlobHeader hdr{};
+  WsLayout ws{};
+  TerrainDesc ter{};
+  std::vector<float> kp, kd;
+  int wpc = 0, grid = 0;
+  size_t smem_bytes = 0;
+  int64_t launches = 0;
+};
+
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------ blob ------------------------
+static void build_blob(rsb_batch* b) {
+  const Model& md = b->model->md;
+  BlobHeader& H = b->hdr;
+  H.nb = md.nb; H.nq = md.nq; H.nv = md.nv; H.npts = md.npts(); H.floating = md.floating; H.maxdepth = md.maxdepth;
+  H.nbp = md.nb | 1;                        // odd stride: field-major reads by body index stay conflict-free
+  H.nptp = std::max(1, md.npts());
+  H.nvp = round_up(std::max(md.nv, 1), 4);
+  H.nqp = round_up(std::max(md.nq, 1), 4);
+  int off = 16;
+  H.off_body = off; off += BF_COUNT * H.nbp;
+  H.off_anc = off; off += std::max(1, md.maxdepth) * H.nbp;
+  H.off_pts = off; off += 5 * H.nptp;
+  H.off_gain = off; off += 2 * H.nvp;
+  H.off_dofq = off; off += H.nvp;
+  H.off_sec = off; off += 2 * NROUNDS * SEC_STRIDE;
+  int words = round_up(off, 4);
+  std::vector<uint32_t>& B = b->blob_host;
+  B.assign(words, 0u);
+  std::memcpy(B.data(), &H, sizeof(H));
+  auto F = [&](int o, float v) { std::memcpy(&B[o], &v, 4); };
+  auto I = [&](int o, int v) { std::memcpy(&B[o], &v, 4); };
+  const int nbp = H.nbp;
+  for (int i = 0; i < md.nb; i++) {
+    I(H.off_body + BF_PARENT * nbp + i, md.parent[i]); I(H.off_body + BF_JTYPE * nbp + i, md.jtype[i]);
+    I(H.off_body + BF_QIDX * nbp + i, md.qidx[i]); I(H.off_body + BF_VIDX * nbp + i, md.vidx[i]);
+    I(H.off_body + BF_DEPTH * nbp + i, md.depth[i]); I(H.off_body + BF_SUBTREE * nbp + i, md.subtree[i]);
+    for (int k = 0; k < 3; k++) F(H.off_body + (BF_JPOS + k) * nbp + i, (float)md.jpos[3 * i + k]);
+    for (int k = 0; k < 9; k++) F(H.off_body + (BF_JROT + k) * nbp + i, (float)md.jrot[9 * i + k]);
+    for (int k = 0; k < 3; k++) F(H.off_body + (BF_AXIS + k) * nbp + i, (float)md.axis[3 * i + k]);
+    F(H.off_body + BF_MASS * nbp + i, (float)md.mass[i]);
+    for (int k = 0; k < 3; k++) F(H.off_body + (BF_COM + k) * nbp + i, (float)md.com[3 * i + k]);
+    for (int k = 0; k < 6; k++) F(H.off_body + (BF_INERTIA + k) * nbp + i, (float)md.inertia[6 * i + k]);
+    // ancestor at depth d (d = 1..depth[i]) stored at anc[(d-1)*nbp + i]
+    for (int d = 0; d < std::max(1, md.maxdepth); d++) I(H.off_anc + d * nbp + i, -1);
+    for (int j = i; md.parent[j] >= 0; j = md.parent[j]) I(H.off_anc + (md.depth[j] - 1) * nbp + i, j);
+  }
+  for (int k = 0; k < md.npts(); k++) {
+    I(H.off_pts + 0 * H.nptp + k, md.pt_body[k]);
+    for (int q = 0; q < 3; q++) F(H.off_pts + (1 + q) * H.nptp + k, (float)md.pt_pos[3 * k + q]);
+    F(H.off_pts + 4 * H.nptp + k, (float)md.pt_rad[k]);
+  }
+  for (int i = 0; i < md.nv; i++) {
+    F(H.off_gain + i, b->kp[i]); F(H.off_gain + H.nvp + i, b->kd[i]);
+    I(H.off_dofq + i, -1);
+  }
+  for (int i = 1; i < md.nb; i++) I(H.off_dofq + md.vidx[i], md.qidx[i]);
+  for (int r = 0; r < NROUNDS; r++) {
+    double width = 2.0 * M_PI / std::pow((double)NSEC, r);
+    for (int k = 0; k <= NSEC; k++) {
+      F(H.off_sec + r * SEC_STRIDE + k, (float)std::cos(width * k / NSEC));
+      F(H.off_sec + NROUNDS * SEC_STRIDE + r * SEC_STRIDE + k, (float)std::sin(width * k / NSEC));
+    }
+  }
+}
+
+static void build_ws_layout(rsb_batch* b) {
+  const BlobHeader& H = b->hdr;
+  WsLayout& L = b->ws;
+  int o = 0;
+  L.mp = H.nv | 1;
+  L.o_gc = o; o += H.nqp;
+  L.o_gv = o; o += H.nvp;
+  L.o_tau = o; o += H.nvp;
+  L.o_pt = o; o += H.nqp;
+  L.o_vt = o; o += H.nvp;
+  L.o_L = o; o += round_up(std::max(1, H.nv) * L.mp, 4);
+  L.o_invd = o; o += H.nvp;
+  L.o_rhs = o; o += H.nvp;
+  L.o_ct = o; o += KMAX * CT_WORDS;
+  L.o_Y = o; o += round_up(std::max(1, H.nv) * CP, 4);
+  L.o_lam = o; o += 32;
+  L.o_u = o; o += 12 * KMAX;
+  // union: {h, b, poses} (stages A-C) overlaid by G (stages C-D)
+  int ua = 0;
+  L.o_h = o + ua; ua += H.nvp;
+  L.o_b = o + ua; ua += H.nvp;
+  L.o_pose = o + ua; ua += round_up(PF_COUNT * H.nbp, 4);
+  L.o_G = o;
+  int ub = round_up(CMAX * GP, 4);
+  o += std::max(ua, ub);
+  L.words = round_up(o, 32);
+}
+
+// ------------------------------------------------------------------ launches --------------------
+template <int WPC>
+static cudaError_t launch_step(const StepArgs& a, int grid, size_t smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(rsb_step_kernel<WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  rsb_step_kernel<WPC><<<grid, WPC * 32, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+static int pick_config(rsb_batch* b) {
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, b->device));
+  if (prop.major < 10) return fail(RSB_ERR_UNSUPPORTED, "raisimlib_b200 needs an sm_100a (B200) device; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+  const size_t budget = prop.sharedMemPerBlockOptin;   // 227 KB on B200
+  const size_t blob_bytes = (size_t)round_up((int)b->blob_host.size(), 32) * 4;
+  const size_t per_warp = (size_t)b->ws.words * 4;
+  const int sms = prop.multiProcessorCount;
+  // one persistent CTA per SM; as many warps (= resident environments) as shared memory allows
+  static const int options[] = {28, 24, 16, 12, 8, 4, 2, 1};
+  int need = (b->N + sms - 1) / sms;    // warps per SM that make every environment resident at once
+  int best = 0;
+  for (int w : options) {
+    if (blob_bytes + (size_t)w * per_warp + 1024 > budget) continue;
+    if (best == 0) best = w;
+    if (w >= need) best = w;            // smallest option that still keeps every environment resident
+  }
+  if (best == 0) return fail(RSB_ERR_UNSUPPORTED, "model too large for one warp's shared-memory workspace");
+  b->wpc = best;
+  b->grid = std::min((b->N + best - 1) / best, sms);
+  b->smem_bytes = blob_bytes + (size_t)best * per_warp;
+  return RSB_OK;
+}
+
+static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug) {
+  StepArgs a{};
+  a.num_envs = b->N; a.substeps = substeps;
+  a.gc_stride = b->gc_stride; a.gv_stride = b->gv_stride;
+  a.gc = b->gc; a.gv = b->gv; a.tau = b->tau;
+  a.use_pd = (b->control_mode == RSB_PD_PLUS_FEEDFORWARD_TORQUE && b->pd_set) ? 1 : 0;
+  a.ptarget = b->pt; a.vtarget = b->vt;
+  a.prm = b->prm; a.ter = b->ter; a.ws = b->ws;
+  a.blob_words = (int)b->blob_host.size(); a.blob = b->blob;
+  a.ncontacts = b->ncontacts; a.contacts = b->contacts; a.contact_pt = b->contact_pt; a.iters = b->iters;
+  if (debug) { a.dbg_M = b->dbg_M; a.dbg_h = b->dbg_h; a.dbg_R = b->dbg_R; a.dbg_p = b->dbg_p; }
+  a.phase_mask = phase_mask;
+  cudaError_t e;
+  switch (b->wpc) {
+    case 28: e = launch_step<28>(a, b->grid, b->smem_bytes, b->stream); break;
+    case 24: e = launch_step<24>(a, b->grid, b->smem_bytes, b->stream); break;
+    case 16: e = launch_step<16>(a, b->grid, b->smem_bytes, b->stream); break;
+    case 12: e = launch_step<12>(a, b->grid, b->smem_bytes, b->stream); break;
+    case 8: e = launch_step<8>(a, b->grid, b->smem_bytes, b->stream); break;
+    case 4: e = launch_step<4>(a, b->grid, b->smem_bytes, b->stream); break;
+    case 2: e = launch_step<2>(a, b->grid, b->smem_bytes, b->stream); break;
+    default: e = launch_step<1>(a, b->grid, b->smem_bytes, b->stream); break;
+  }
+  if (e != cudaSuccess) return fail(RSB_ERR_CUDA, std::string("step kernel launch: ") + cudaGetErrorString(e));
+  b->launches++;
+  return RSB_OK;
+}
+
+// rows: tight [n][w] <-> padded [n][stride]
+static int copy_rows_in(rsb_batch* b, float* dst, int stride, const float* src, int w, int env_begin, int n, int where) {
+  if (!src) return RSB_OK;
+  cudaMemcpyKind kind = where == RSB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  CK(cudaMemcpy2DAsync(dst + (size_t)env_begin * stride, (size_t)stride * 4, src, (size_t)w * 4, (size_t)w * 4, n, kind, b->stream));
+  return RSB_OK;
+}
+static int copy_rows_out(rsb_batch* b, float* dst, const float* src, int stride, int w, int env_begin, int n, int where) {
+  if (!dst) return RSB_OK;
+  cudaMemcpyKind kind = where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  CK(cudaMemcpy2DAsync(dst, (size_t)w * 4, src + (size_t)env_begin * stride, (size_t)stride * 4, (size_t)w * 4, n, kind, b->stream));
+  if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
+  return RSB_OK;
+}
+static int check_range(const rsb_batch* b, int env_begin, int env_count) {
+  if (!b) return fail(RSB_ERR_INVALID, "null batch");
+  if (env_begin < 0 || env_count < 0 || env_begin + env_count > b->N) return fail(RSB_ERR_INVALID, "environment range out of bounds");
+  return RSB_OK;
+}
+
+extern "C" {
+
+const char* rsb_last_error(void) { return g_err.c_str(); }
+int rsb_version(void) { return 100; }
+
+int rsb_params_default(rsb_params* p) {
+  if (!p) return fail(RSB_ERR_INVALID, "null params");
+  p->dt = 0.0025f; p->gravity[0] = 0.f; p->gravity[1] = 0.f; p->gravity[2] = -9.81f; p->erp = 0.f;
+  p->alpha_init = 1.f; p->alpha_min = 1.f; p->alpha_decay = 1.f; p->max_iter = 150; p->threshold = 1e-6f;
+  p->mu = 0.8f; p->restitution = 0.f; p->rest_threshold = 0.01f;
+  return RSB_OK;
+}
+
+// ---- model ---------------------------------------------------------------------------------------
+int rsb_model_create_from_urdf(const char* path_or_xml, rsb_model** out) {
+  if (!path_or_xml || !out) return fail(RSB_ERR_INVALID, "null argument");
+  try {
+    rsb_model* m = new rsb_model;
+    m->md = load_urdf(path_or_xml);
+    if (m->md.nb > 32) { delete m; return fail(RSB_ERR_UNSUPPORTED, "more than 32 movable bodies (one lane per body)"); }
+    if (m->md.npts() > 32 * MAX_PT_SLOTS) { delete m; return fail(RSB_ERR_UNSUPPORTED, "more than 64 candidate contact points"); }
+    *out = m;
+    return RSB_OK;
+  } catch (const std::exception& e) { return fail(RSB_ERR_PARSE, e.what()); }
+}
+void rsb_model_destroy(rsb_model* m) { delete m; }
+int rsb_model_dims(const rsb_model* m, int* nq, int* nv, int* nb, int* ncoll, int* npts) {
+  if (!m) return fail(RSB_ERR_INVALID, "null model");
+  if (nq) *nq = m->md.nq; if (nv) *nv = m->md.nv; if (nb) *nb = m->md.nb; if (ncoll) *ncoll = m->md.ncoll(); if (npts) *npts = m->md.npts();
+  return RSB_OK;
+}
+int rsb_model_get_tables(const rsb_model* m, rsb_model_tables* t) {
+  if (!m || !t) return fail(RSB_ERR_INVALID, "null argument");
+  const Model& d = m->md;
+  t->nb = d.nb; t->nq = d.nq; t->nv = d.nv; t->floating = d.floating; t->ncoll = d.ncoll(); t->npts = d.npts();
+  t->parent = d.parent.data(); t->jtype = d.jtype.data(); t->qidx = d.qidx.data(); t->vidx = d.vidx.data(); t->depth = d.depth.data();
+  t->jpos = d.jpos.data(); t->jrot = d.jrot.data(); t->axis = d.axis.data(); t->mass = d.mass.data(); t->com = d.com.data();
+  t->inertia = d.inertia.data(); t->jlimit = d.jlimit.data();
+  t->cbody = d.cbody.data(); t->ctype = d.ctype.data(); t->csize = d.csize.data(); t->cpos = d.cpos.data(); t->crot = d.crot.data();
+  t->pt_body = d.pt_body.data(); t->pt_coll = d.pt_coll.data(); t->pt_feat = d.pt_feat.data(); t->pt_pos = d.pt_pos.data(); t->pt_rad = d.pt_rad.data();
+  return RSB_OK;
+}
+int rsb_model_body_index(const rsb_model* m, const char* name) {
+  if (!m || !name) return fail(RSB_ERR_INVALID, "null argument");
+  for (int i = 0; i < m->md.nb; i++) if (m->md.body_names[i] == name) return i;
+  for (const Frame& f : m->md.frames) if (f.name == name) return f.body;   // a link merged through a fixed joint
+  return fail(RSB_ERR_INVALID, std::string("no body named '") + name + "'");
+}
+const char* rsb_model_body_name(const rsb_model* m, int body) { return (m && body >= 0 && body < m->md.nb) ? m->md.body_names[body].c_str() : nullptr; }
+const char* rsb_model_joint_name(const rsb_model* m, int body) { return (m && body >= 0 && body < m->md.nb) ? m->md.joint_names[body].c_str() : nullptr; }
+int rsb_model_frame_index(const rsb_model* m, const char* name) {
+  if (!m || !name) return fail(RSB_ERR_INVALID, "null argument");
+  for (size_t i = 0; i < m->md.frames.size(); i++) if (m->md.frames[i].name == name) return (int)i;
+  return fail(RSB_ERR_INVALID, std::string("no frame named '") + name + "'");
+}
+int rsb_model_frame(const rsb_model* m, int frame, int* body, double pos[3], double rot[9]) {
+  if (!m || frame < 0 || frame >= (int)m->md.frames.size()) return fail(RSB_ERR_INVALID, "bad frame index");
+  const Frame& f = m->md.frames[frame];
+  if (body) *body = f.body;
+  if (pos) for (int k = 0; k < 3; k++) pos[k] = f.pos[k];
+  if (rot) for (int k = 0; k < 9; k++) rot[k] = f.rot[k];
+  return RSB_OK;
+}
+
+// ---- batch ---------------------------------------------------------------------------------------
+int rsb_batch_create(const rsb_model* m, int num_envs, int device, rsb_batch** out) {
+  if (!m || !out || num_envs <= 0) return fail(RSB_ERR_INVALID, "bad arguments to rsb_batch_create");
+  int ndev = 0;
+  cudaError_t e0 = cudaGetDeviceCount(&ndev);
+  if (e0 != cudaSuccess || ndev == 0) return fail(RSB_ERR_CUDA, "no CUDA device: raisimlib_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(RSB_ERR_INVALID, "device index out of range");
+  CK(cudaSetDevice(device));
+  rsb_batch* b = new rsb_batch;
+  b->model = m; b->N = num_envs; b->device = device;
+  const Model& md = m->md;
+  b->nq = md.nq; b->nv = md.nv; b->nb = md.nb;
+  b->gc_stride = round_up(std::max(1, md.nq), 8); b->gv_stride = round_up(std::max(1, md.nv), 8);   // 32-byte sector-aligned rows
+  rsb_params_default(&b->prm);
+  b->kp.assign(std::max(1, md.nv), 0.f); b->kd.assign(std::max(1, md.nv), 0.f);
+  build_blob(b);
+  build_ws_layout(b);
+  int rc = pick_config(b);
+  if (rc != RSB_OK) { delete b; return rc; }
+  size_t N = (size_t)num_envs;
+  auto alloc = [&](void** p, size_t bytes) { cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 16)); if (e == cudaSuccess) e = cudaMemset(*p, 0, std::max<size_t>(bytes, 16)); return e; };
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = alloc((void**)&b->gc, N * b->gc_stride * 4);
+  if (e == cudaSuccess) e = alloc((void**)&b->gv, N * b->gv_stride * 4);
+  if (e == cudaSuccess) e = alloc((void**)&b->tau, N * b->gv_stride * 4);
+  if (e == cudaSuccess) e = alloc((void**)&b->pt, N * b->gc_stride * 4);
+  if (e == cudaSuccess) e = alloc((void**)&b->vt, N * b->gv_stride * 4);
+  if (e == cudaSuccess) e = alloc((void**)&b->ncontacts, N * 4);
+  if (e == cudaSuccess) e = alloc((void**)&b->contact_pt, N * KMAX * 4);
+  if (e == cudaSuccess) e = alloc((void**)&b->iters, N * 4);
+  if (e == cudaSuccess) e = alloc((void**)&b->contacts, N * KMAX * sizeof(rsb_contact));
+  if (e == cudaSuccess) e = alloc((void**)&b->blob, b->blob_host.size() * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(b->blob, b->blob_host.data(), b->blob_host.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { std::string msg = cudaGetErrorString(e); rsb_batch_destroy(b); return fail(RSB_ERR_CUDA, "rsb_batch_create: " + msg); }
+  b->own_stream = true;
+  // identity quaternion so that a fresh batch is a valid state
+  if (md.floating) {
+    std::vector<float> q0((size_t)N * b->gc_stride, 0.f);
+    for (size_t i = 0; i < N; i++) q0[i * b->gc_stride + 3] = 1.f;
+    cudaMemcpy(b->gc, q0.data(), q0.size() * 4, cudaMemcpyHostToDevice);
+  }
+  *out = b;
+  return RSB_OK;
+}
+
+void rsb_batch_destroy(rsb_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  for (void* p : {(void*)b->gc, (void*)b->gv, (void*)b->tau, (void*)b->pt, (void*)b->vt, (void*)b->ncontacts, (void*)b->contact_pt, (void*)b->iters,
+                  (void*)b->contacts, (void*)b->dbg_M, (void*)b->dbg_h, (void*)b->dbg_R, (void*)b->dbg_p, (void*)b->hmap, (void*)b->staging, (void*)b->blob})
+    if (p) cudaFree(p);
+  if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+int rsb_batch_set_stream(rsb_batch* b, void* s) {
+  if (!b) return fail(RSB_ERR_INVALID, "null batch");
+  CK(cudaStreamSynchronize(b->stream));
+  if (b->own_stream) { cudaStreamDestroy(b->stream); b->own_stream = false; }
+  b->stream = (cudaStream_t)s;
+  return RSB_OK;
+}
+int rsb_batch_sync(rsb_batch* b) {
+  if (!b) return fail(RSB_ERR_INVALID, "null batch");
+  CK(cudaStreamSynchronize(b->stream));
+  return RSB_OK;
+}
+int rsb_batch_num_envs(const rsb_batch* b) { return b ? b->N : 0; }
+
+int rsb_batch_set_ground(rsb_batch* b, float z) {
+  if (!b) return fail(RSB_ERR_INVALID, "null batch");
+  b->ter = TerrainDesc{}; b->ter.type = 1; b->ter.ground_z = z;
+  return RSB_OK;
+}
+int rsb_batch_clear_terrain(rsb_batch* b) {
+  if (!b) return fail(RSB_ERR_INVALID, "null batch");
+  b->ter = TerrainDesc{};
+  return RSB_OK;
+}
+int rsb_batch_set_heightmap(rsb_batch* b, int xs, int ys, float x_size, float y_size, float cx, float cy, const float* h) {
+  if (!b || !h || xs < 2 || ys < 2 || !(x_size > 0) || !(y_size > 0)) return fail(RSB_ERR_INVALID, "bad height map");
+  CK(cudaSetDevice(b->device));
+  CK(cudaStreamSynchronize(b->stream));
+  if (b->hmap) { cudaFree(b->hmap); b->hmap = nullptr; }
+  CK(cudaMalloc((void**)&b->hmap, (size_t)xs * ys * 4));
+  CK(cudaMemcpy(b->hmap, h, (size_t)xs * ys * 4, cudaMemcpyHostToDevice));
+  TerrainDesc t{};
+  t.type = 2; t.xs = xs; t.ys = ys;
+  t.dx = x_size / (float)(xs - 1); t.dy = y_size / (float)(ys - 1);
+  t.x0 = cx - 0.5f * x_size; t.y0 = cy - 0.5f * y_size;
+  t.xmax = (float)(xs - 1); t.ymax = (float)(ys - 1);
+  t.h = b->hmap;
+  b->ter = t;
+  return RSB_OK;
+}
+int rsb_batch_set_params(rsb_batch* b, const rsb_params* p) {
+  if (!b || !p) return fail(RSB_ERR_INVALID, "null argument");
+  if (!(p->dt > 0) || p->max_iter < 1 || !(p->mu >= 0)) return fail(RSB_ERR_INVALID, "invalid params");
+  b->prm = *p;
+  return RSB_OK;
+}
+int rsb_batch_get_params(const rsb_batch* b, rsb_params* p) {
+  if (!b || !p) return fail(RSB_ERR_INVALID, "null argument");
+  *p = b->prm;
+  return RSB_OK;
+}
+
+int rsb_batch_set_state(rsb_batch* b, const float* gc, const float* gv, int env_begin, int env_count, int where) {
+  int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  rc = copy_rows_in(b, b->gc, b->gc_stride, gc, b->nq, env_begin, env_count, where); if (rc) return rc;
+  return copy_rows_in(b, b->gv, b->gv_stride, gv, b->nv, env_begin, env_count, where);
+}
+int rsb_batch_get_state(rsb_batch* b, float* gc, float* gv, int env_begin, int env_count, int where) {
+  int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  if (gc) CK(cudaMemcpy2DAsync(gc, (size_t)b->nq * 4, b->gc + (size_t)env_begin * b->gc_stride, (size_t)b->gc_stride * 4, (size_t)b->nq * 4, env_count,
+                               where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
+  if (gv) CK(cudaMemcpy2DAsync(gv, (size_t)b->nv * 4, b->gv + (size_t)env_begin * b->gv_stride, (size_t)b->gv_stride * 4, (size_t)b->nv * 4, env_count,
+                               where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
+  if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
+  return RSB_OK;
+}
+int rsb_batch_set_pd_gains(rsb_batch* b, const float* kp, const float* kd) {
+  if (!b || !kp || !kd) return fail(RSB_ERR_INVALID, "null argument");
+  const Model& md = b->model->md;
+  for (int i = 0; i < md.nv; i++) { b->kp[i] = kp[i]; b->kd[i] = kd[i]; }
+  if (md.floating) for (int i = 0; i < 6; i++) { b->kp[i] = 0.f; b->kd[i] = 0.f; }   // the base is not actuated
+  for (int i = 0; i < md.nv; i++) {
+    std::memcpy(&b->blob_host[b->hdr.off_gain + i], &b->kp[i], 4);
+    std::memcpy(&b->blob_host[b->hdr.off_gain + b->hdr.nvp + i], &b->kd[i], 4);
+  }
+  CK(cudaMemcpyAsync(b->blob + b->hdr.off_gain, b->blob_host.data() + b->hdr.off_gain, (size_t)2 * b->hdr.nvp * 4, cudaMemcpyHostToDevice, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  b->pd_set = true;
+  return RSB_OK;
+}
+int rsb_batch_set_pd_target(rsb_batch* b, const float* ptarget, const float* vtarget, int env_begin, int env_count, int where) {
+  int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  rc = copy_rows_in(b, b->pt, b->gc_stride, ptarget, b->nq, env_begin, env_count, where); if (rc) return rc;
+  return copy_rows_in(b, b->vt, b->gv_stride, vtarget, b->nv, env_begin, env_count, where);
+}
+int rsb_batch_set_generalized_force(rsb_batch* b, const float* tau, int env_begin, int env_count, int where) {
+  int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  return copy_rows_in(b, b->tau, b->gv_stride, tau, b->nv, env_begin, env_count, where);
+}
+int rsb_batch_set_control_mode(rsb_batch* b, int mode) {
+  if (!b || (mode != RSB_FORCE_AND_TORQUE && mode != RSB_PD_PLUS_FEEDFORWARD_TORQUE)) return fail(RSB_ERR_INVALID, "bad control mode");
+  b->control_mode = mode;
+  return RSB_OK;
+}
+
+static int ensure_debug(rsb_batch* b) {
+  if (b->dbg_M) return RSB_OK;
+  size_t N = (size_t)b->N;
+  CK(cudaMalloc((void**)&b->dbg_M, std::max<size_t>(16, N * b->nv * b->nv * 4)));
+  CK(cudaMalloc((void**)&b->dbg_h, std::max<size_t>(16, N * b->nv * 4)));
+  CK(cudaMalloc((void**)&b->dbg_R, N * b->nb * 9 * 4));
+  CK(cudaMalloc((void**)&b->dbg_p, N * b->nb * 3 * 4));
+  return RSB_OK;
+}
+
+int rsb_batch_integrate1(rsb_batch* b) {
+  if (!b) return fail(RSB_ERR_INVALID, "null batch");
+  CK(cudaSetDevice(b->device));
+  int rc = ensure_debug(b); if (rc) return rc;
+  return do_launch(b, 1, 1, true);
+}
+int rsb_batch_integrate2(rsb_batch* b) {
+  if (!b) return fail(RSB_ERR_INVALID, "null batch");
+  CK(cudaSetDevice(b->device));
+  // state is unchanged since integrate1(), so the fused step recomputes stage A-B on-chip and goes on;
+  // generalized forces / PD targets set between integrate1() and integrate2() are honoured
+  return do_launch(b, 1, 0, b->dbg_M != nullptr);
+}
+int rsb_batch_integrate(rsb_batch* b, int substeps) {
+  if (!b || substeps < 1) return fail(RSB_ERR_INVALID, "bad arguments to rsb_batch_integrate");
+  CK(cudaSetDevice(b->device));
+  return do_launch(b, substeps, 0, false);
+}
+
+int rsb_batch_get_mass_matrix(rsb_batch* b, int env_begin, int env_count, float* out, int where) {
+  int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  if (!b->dbg_M) return fail(RSB_ERR_INVALID, "call rsb_batch_integrate1() first");
+  size_t w = (size_t)b->nv * b->nv;
+  CK(cudaMemcpyAsync(out, b->dbg_M + env_begin * w, env_count * w * 4, where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
+  if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
+  return RSB_OK;
+}
+int rsb_batch_get_nonlinearities(rsb_batch* b, int env_begin, int env_count, float* out, int where) {
+  int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  if (!b->dbg_h) return fail(RSB_ERR_INVALID, "call rsb_batch_integrate1() first");
+  CK(cudaMemcpyAsync(out, b->dbg_h + (size_t)env_begin * b->nv, (size_t)env_count * b->nv * 4, where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
+  if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
+  return RSB_OK;
+}
+int rsb_batch_get_body_poses(rsb_batch* b, int env_begin, int env_count, float* rot, float* pos, int where) {
+  int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  if (!b->dbg_R) return fail(RSB_ERR_INVALID, "call rsb_batch_integrate1() first");
+  cudaMemcpyKind kind = where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (rot) CK(cudaMemcpyAsync(rot, b->dbg_R + (size_t)env_begin * b->nb * 9, (size_t)env_count * b->nb * 9 * 4, kind, b->stream));
+  if (pos) CK(cudaMemcpyAsync(pos, b->dbg_p + (size_t)env_begin * b->nb * 3, (size_t)env_count * b->nb * 3 * 4, kind, b->stream));
+  if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
+  return RSB_OK;
+}
+int rsb_batch_get_contacts(rsb_batch* b, rsb_contact* out, int32_t* counts, int env_begin, int env_count, int where) {
+  int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  cudaMemcpyKind kind = where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (out) CK(cudaMemcpyAsync(out, b->contacts + (size_t)env_begin * KMAX, (size_t)env_count * KMAX * sizeof(rsb_contact), kind, b->stream));
+  if (counts) CK(cudaMemcpyAsync(counts, b->ncontacts + env_begin, (size_t)env_count * 4, kind, b->stream));
+  if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
+  return RSB_OK;
+}
+int rsb_batch_get_contact_points(rsb_batch* b, int32_t* pt, int env_begin, int env_count, int where) {
+  int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  CK(cudaMemcpyAsync(pt, b->contact_pt + (size_t)env_begin * KMAX, (size_t)env_count * KMAX * 4, where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
+  if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
+  return RSB_OK;
+}
+int rsb_batch_get_solver_iterations(rsb_batch* b, int32_t* it, int env_begin, int env_count, int where) {
+  int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  CK(cudaMemcpyAsync(it, b->iters + env_begin, (size_t)env_count * 4, where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
+  if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
+  return RSB_OK;
+}
+int rsb_batch_device_ptrs(rsb_batch* b, rsb_device_view* v) {
+  if (!b || !v) return fail(RSB_ERR_INVALID, "null argument");
+  v->num_envs = b->N; v->nq = b->nq; v->nv = b->nv; v->gc_stride = b->gc_stride; v->gv_stride = b->gv_stride;
+  v->gc = b->gc; v->gv = b->gv; v->tau_ff = b->tau; v->ptarget = b->pt; v->vtarget = b->vt;
+  v->ncontacts = b->ncontacts; v->contacts = b->contacts;
+  return RSB_OK;
+}
+int64_t rsb_batch_launch_count(const rsb_batch* b) { return b ? b->launches : 0; }
+
+int rsb_batch_ob_dim(const rsb_batch* b) {
+  if (!b) return 0;
+  return b->model->md.floating ? (b->nq + b->nv - 3) : (b->nq + b->nv);
+}
+int rsb_batch_observe(rsb_batch* b, float* obs, int env_begin, int env_count, int where) {
+  int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  if (!obs) return fail(RSB_ERR_INVALID, "null obs");
+  CK(cudaSetDevice(b->device));
+  const int od = rsb_batch_ob_dim(b);
+  float* dst = obs;
+  if (where == RSB_HOST) {
+    size_t need = (size_t)env_count * od;
+    if (b->staging_words < need) {
+      if (b->staging) cudaFree(b->staging);
+      b->staging = nullptr; b->staging_words = 0;
+      CK(cudaMalloc((void**)&b->staging, need * 4));
+      b->staging_words = need;
+    }
+    dst = b->staging;
+  }
+  int threads = 128, blocks = (env_count * 32 + threads - 1) / threads;
+  rsb_observe_kernel<<<blocks, threads, 0, b->stream>>>(b->gc + (size_t)env_begin * b->gc_stride, b->gv + (size_t)env_begin * b->gv_stride,
+                                                         b->gc_stride, b->gv_stride, b->nq, b->nv, b->model->md.floating, env_count, dst, od);
+  CK(cudaGetLastError());
+  b->launches++;
+  if (where == RSB_HOST) {
+    CK(cudaMemcpyAsync(obs, dst, (size_t)env_count * od * 4, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+  }
+  return RSB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,332 @@
+// URDF subset loader (product, host side).  See model.hpp.
+// No XML library exists in the image (SURVEY.md section 0 [PROBE]), hence the small parser below.
+#include "model.hpp"
+
+#include <cmath>
+#include <cstdlib>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+
+namespace rsb {
+namespace {
+
+// ------------------------------------------------------------------ minimal XML ----------------
+struct XmlNode {
+  std::string tag;
+  std::map<std::string, std::string> attr;
+  std::vector<std::unique_ptr<XmlNode>> kids;
+  const XmlNode* child(const std::string& t) const {
+    for (auto& k : kids) if (k->tag == t) return k.get();
+    return nullptr;
+  }
+  std::vector<const XmlNode*> children(const std::string& t) const {
+    std::vector<const XmlNode*> r;
+    for (auto& k : kids) if (k->tag == t) r.push_back(k.get());
+    return r;
+  }
+  std::string get(const std::string& k, const std::string& dflt = "") const {
+    auto it = attr.find(k);
+    return it == attr.end() ? dflt : it->second;
+  }
+  bool has(const std::string& k) const { return attr.count(k) != 0; }
+};
+
+class XmlParser {
+ public:
+  explicit XmlParser(const std::string& s) : s_(s) {}
+  std::unique_ptr<XmlNode> parse() {
+    skip_misc();
+    auto n = element();
+    if (!n) fail("no root element");
+    return n;
+  }
+
+ private:
+  const std::string& s_;
+  size_t i_ = 0;
+  [[noreturn]] void fail(const std::string& m) const { throw std::runtime_error("XML parse error at byte " + std::to_string(i_) + ": " + m); }
+  bool starts(const char* t) const { return s_.compare(i_, std::char_traits<char>::length(t), t) == 0; }
+  void skip_ws() { while (i_ < s_.size() && isspace((unsigned char)s_[i_])) i_++; }
+  void skip_misc() {   // whitespace, <?...?>, <!--...-->, <!DOCTYPE ...>
+    for (;;) {
+      skip_ws();
+      if (starts("<?")) { size_t e = s_.find("?>", i_); if (e == std::string::npos) fail("unterminated <?"); i_ = e + 2; }
+      else if (starts("<!--")) { size_t e = s_.find("-->", i_); if (e == std::string::npos) fail("unterminated comment"); i_ = e + 3; }
+      else if (starts("<!")) { size_t e = s_.find('>', i_); if (e == std::string::npos) fail("unterminated <!"); i_ = e + 1; }
+      else return;
+    }
+  }
+  std::string name() {
+    size_t b = i_;
+    while (i_ < s_.size() && (isalnum((unsigned char)s_[i_]) || s_[i_] == '_' || s_[i_] == '-' || s_[i_] == ':' || s_[i_] == '.')) i_++;
+    if (b == i_) fail("expected a name");
+    return s_.substr(b, i_ - b);
+  }
+  std::unique_ptr<XmlNode> element() {
+    if (i_ >= s_.size() || s_[i_] != '<') return nullptr;
+    i_++;
+    auto n = std::make_unique<XmlNode>();
+    n->tag = name();
+    for (;;) {
+      skip_ws();
+      if (i_ >= s_.size()) fail("unterminated tag <" + n->tag);
+      if (s_[i_] == '/') { if (!starts("/>")) fail("bad tag end"); i_ += 2; return n; }
+      if (s_[i_] == '>') { i_++; break; }
+      std::string k = name();
+      skip_ws();
+      if (s_[i_] != '=') fail("expected '=' after attribute " + k);
+      i_++; skip_ws();
+      char q = s_[i_];
+      if (q != '"' && q != '\'') fail("expected quoted value for " + k);
+      size_t e = s_.find(q, i_ + 1);
+      if (e == std::string::npos) fail("unterminated attribute value");
+      n->attr[k] = s_.substr(i_ + 1, e - i_ - 1);
+      i_ = e + 1;
+    }
+    for (;;) {   // content
+      size_t lt = s_.find('<', i_);
+      if (lt == std::string::npos) fail("missing </" + n->tag + ">");
+      i_ = lt;
+      if (starts("</")) {
+        i_ += 2;
+        std::string t = name();
+        if (t != n->tag) fail("mismatched </" + t + "> for <" + n->tag + ">");
+        skip_ws();
+        if (s_[i_] != '>') fail("bad closing tag");
+        i_++;
+        return n;
+      }
+      if (starts("<!--")) { size_t e = s_.find("-->", i_); if (e == std::string::npos) fail("unterminated comment"); i_ = e + 3; continue; }
+      if (starts("<![CDATA[")) { size_t e = s_.find("]]>", i_); if (e == std::string::npos) fail("unterminated CDATA"); i_ = e + 3; continue; }
+      if (starts("<?")) { size_t e = s_.find("?>", i_); if (e == std::string::npos) fail("unterminated <?"); i_ = e + 2; continue; }
+      n->kids.push_back(element());
+    }
+  }
+};
+
+// ------------------------------------------------------------------ small linear algebra -------
+using V3 = std::array<double, 3>;
+using M3 = std::array<double, 9>;
+
+M3 mul(const M3& a, const M3& b) {
+  M3 r{};
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+  return r;
+}
+M3 transpose(const M3& a) { return {a[0], a[3], a[6], a[1], a[4], a[7], a[2], a[5], a[8]}; }
+V3 mul(const M3& a, const V3& v) { return {a[0] * v[0] + a[1] * v[1] + a[2] * v[2], a[3] * v[0] + a[4] * v[1] + a[5] * v[2], a[6] * v[0] + a[7] * v[1] + a[8] * v[2]}; }
+V3 add(const V3& a, const V3& b) { return {a[0] + b[0], a[1] + b[1], a[2] + b[2]}; }
+const M3 kEye = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+
+M3 rpy_to_rot(const V3& rpy) {   // URDF fixed-axis rpy: R = Rz(yaw) Ry(pitch) Rx(roll)
+  double cr = std::cos(rpy[0]), sr = std::sin(rpy[0]), cp = std::cos(rpy[1]), sp = std::sin(rpy[1]), cy = std::cos(rpy[2]), sy = std::sin(rpy[2]);
+  return {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr,
+          sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr,
+          -sp, cp * sr, cp * cr};
+}
+
+V3 parse_v3(const std::string& s, const V3& dflt) {
+  if (s.empty()) return dflt;
+  std::istringstream is(s);
+  V3 v{};
+  if (!(is >> v[0] >> v[1] >> v[2])) throw std::runtime_error("URDF: expected three numbers in \"" + s + "\"");
+  return v;
+}
+double parse_d(const std::string& s, const char* what) {
+  char* e = nullptr;
+  double v = std::strtod(s.c_str(), &e);
+  if (s.empty() || e == s.c_str()) throw std::runtime_error(std::string("URDF: bad number for ") + what);
+  return v;
+}
+void origin_of(const XmlNode* n, V3& pos, M3& rot) {
+  pos = {0, 0, 0}; rot = kEye;
+  const XmlNode* o = n ? n->child("origin") : nullptr;
+  if (!o) return;
+  pos = parse_v3(o->get("xyz"), {0, 0, 0});
+  rot = rpy_to_rot(parse_v3(o->get("rpy"), {0, 0, 0}));
+}
+
+// rigid-body inertia accumulator expressed in the owning body's frame
+struct Accum {
+  double m = 0;
+  V3 c{0, 0, 0};
+  M3 I{};   // about c
+  static M3 shift(double m, const V3& d) {   // m ((d.d) 1 - d d^T)
+    double dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+    return {m * (dd - d[0] * d[0]), -m * d[0] * d[1], -m * d[0] * d[2],
+            -m * d[1] * d[0], m * (dd - d[1] * d[1]), -m * d[1] * d[2],
+            -m * d[2] * d[0], -m * d[2] * d[1], m * (dd - d[2] * d[2])};
+  }
+  void add_body(double m2, const V3& c2, const M3& I2) {
+    if (m2 <= 0) return;
+    double mt = m + m2;
+    V3 cn = {(m * c[0] + m2 * c2[0]) / mt, (m * c[1] + m2 * c2[1]) / mt, (m * c[2] + m2 * c2[2]) / mt};
+    M3 s1 = shift(m, {c[0] - cn[0], c[1] - cn[1], c[2] - cn[2]});
+    M3 s2 = shift(m2, {c2[0] - cn[0], c2[1] - cn[1], c2[2] - cn[2]});
+    for (int k = 0; k < 9; k++) I[k] = I[k] + s1[k] + I2[k] + s2[k];
+    m = mt; c = cn;
+  }
+};
+
+struct Builder {
+  Model md;
+  std::map<std::string, const XmlNode*> links;
+  std::map<std::string, std::vector<const XmlNode*>> kids_of;   // parent link -> joints, file order
+  std::vector<Accum> acc;
+
+  int new_body(const std::string& name, int parent, int jt, const V3& jp, const M3& jr, const V3& ax, const std::string& jname, double lo, double hi) {
+    int i = md.nb++;
+    md.parent.push_back(parent); md.jtype.push_back(jt);
+    md.jpos.insert(md.jpos.end(), jp.begin(), jp.end());
+    md.jrot.insert(md.jrot.end(), jr.begin(), jr.end());
+    md.axis.insert(md.axis.end(), ax.begin(), ax.end());
+    md.body_names.push_back(name); md.joint_names.push_back(jname);
+    md.jlimit.push_back(lo); md.jlimit.push_back(hi);
+    acc.emplace_back();
+    return i;
+  }
+
+  // merge `link` (whose frame sits at (pos, rot) in body coordinates) into body `b`, then descend
+  void absorb(int b, const std::string& link_name, const V3& pos, const M3& rot) {
+    auto it = links.find(link_name);
+    if (it == links.end()) throw std::runtime_error("URDF: joint refers to unknown link '" + link_name + "'");
+    const XmlNode* l = it->second;
+    md.frames.push_back(Frame{link_name, b, pos, rot});
+    if (const XmlNode* in = l->child("inertial")) {
+      V3 cp; M3 cr;
+      origin_of(in, cp, cr);
+      const XmlNode* mn = in->child("mass");
+      const XmlNode* it2 = in->child("inertia");
+      if (!mn || !it2) throw std::runtime_error("URDF: <inertial> of link '" + link_name + "' needs <mass> and <inertia>");
+      double m = parse_d(mn->get("value"), "mass");
+      double ixx = parse_d(it2->get("ixx"), "ixx"), ixy = parse_d(it2->get("ixy", "0"), "ixy"), ixz = parse_d(it2->get("ixz", "0"), "ixz");
+      double iyy = parse_d(it2->get("iyy"), "iyy"), iyz = parse_d(it2->get("iyz", "0"), "iyz"), izz = parse_d(it2->get("izz"), "izz");
+      M3 Il = {ixx, ixy, ixz, ixy, iyy, iyz, ixz, iyz, izz};
+      M3 Rl = mul(rot, cr);
+      acc[b].add_body(m, add(pos, mul(rot, cp)), mul(mul(Rl, Il), transpose(Rl)));
+    }
+    for (const XmlNode* c : l->children("collision")) {
+      V3 cp; M3 cr;
+      origin_of(c, cp, cr);
+      const XmlNode* g = c->child("geometry");
+      if (!g) throw std::runtime_error("URDF: <collision> without <geometry> in link '" + link_name + "'");
+      V3 p = add(pos, mul(rot, cp));
+      M3 R = mul(rot, cr);
+      int type; V3 size{0, 0, 0};
+      if (const XmlNode* s = g->child("sphere")) { type = CT_SPHERE; size[0] = parse_d(s->get("radius"), "sphere radius"); }
+      else if (const XmlNode* bx = g->child("box")) { type = CT_BOX; V3 sz = parse_v3(bx->get("size"), {0, 0, 0}); size = {0.5 * sz[0], 0.5 * sz[1], 0.5 * sz[2]}; }
+      else if (const XmlNode* cp2 = g->child("capsule")) { type = CT_CAPSULE; size[0] = parse_d(cp2->get("radius"), "capsule radius"); size[1] = 0.5 * parse_d(cp2->get("length"), "capsule length"); }
+      else throw std::runtime_error("URDF: unsupported collision geometry in link '" + link_name + "' (sphere, box, capsule are supported)");
+      int ci = md.ncoll();
+      md.cbody.push_back(b); md.ctype.push_back(type);
+      md.csize.insert(md.csize.end(), size.begin(), size.end());
+      md.cpos.insert(md.cpos.end(), p.begin(), p.end());
+      md.crot.insert(md.crot.end(), R.begin(), R.end());
+      md.coll_names.push_back(link_name);
+      auto add_pt = [&](const V3& local, double rad, int feat) {
+        V3 w = add(p, mul(R, local));
+        md.pt_body.push_back(b); md.pt_coll.push_back(ci); md.pt_feat.push_back(feat);
+        md.pt_pos.insert(md.pt_pos.end(), w.begin(), w.end());
+        md.pt_rad.push_back(rad);
+      };
+      if (type == CT_SPHERE) add_pt({0, 0, 0}, size[0], 0);
+      else if (type == CT_CAPSULE) { add_pt({0, 0, -size[1]}, size[0], 0); add_pt({0, 0, size[1]}, size[0], 1); }
+      else for (int k = 0; k < 8; k++) add_pt({(k & 1) ? size[0] : -size[0], (k & 2) ? size[1] : -size[1], (k & 4) ? size[2] : -size[2]}, 0.0, k);
+    }
+    auto kit = kids_of.find(link_name);
+    if (kit == kids_of.end()) return;
+    for (const XmlNode* j : kit->second) {
+      V3 op; M3 orot;
+      origin_of(j, op, orot);
+      std::string type = j->get("type");
+      std::string child = j->child("child")->get("link");
+      V3 jp = add(pos, mul(rot, op));
+      M3 jr = mul(rot, orot);
+      if (type == "fixed") { absorb(b, child, jp, jr); continue; }
+      int jt;
+      if (type == "revolute" || type == "continuous") jt = JT_REVOLUTE;
+      else if (type == "prismatic") jt = JT_PRISMATIC;
+      else throw std::runtime_error("URDF: unsupported joint type '" + type + "' (joint '" + j->get("name") + "')");
+      V3 ax = {1, 0, 0};
+      if (const XmlNode* a = j->child("axis")) ax = parse_v3(a->get("xyz"), {1, 0, 0});
+      double nrm = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+      if (!(nrm > 0)) throw std::runtime_error("URDF: zero joint axis in joint '" + j->get("name") + "'");
+      for (double& v : ax) v /= nrm;
+      double lo = -1e30, hi = 1e30;
+      const XmlNode* lim = j->child("limit");
+      if (lim && type != "continuous") {
+        if (lim->has("lower")) lo = parse_d(lim->get("lower"), "limit lower");
+        if (lim->has("upper")) hi = parse_d(lim->get("upper"), "limit upper");
+      }
+      int nb = new_body(child, b, jt, jp, jr, ax, j->get("name"), lo, hi);
+      absorb(nb, child, {0, 0, 0}, kEye);
+    }
+  }
+};
+
+}  // namespace
+
+Model load_urdf(const std::string& path_or_xml) {
+  std::string text;
+  size_t first = path_or_xml.find_first_not_of(" \t\r\n");
+  if (first != std::string::npos && path_or_xml[first] == '<') text = path_or_xml;
+  else {
+    std::ifstream f(path_or_xml);
+    if (!f) throw std::runtime_error("cannot open URDF file '" + path_or_xml + "'");
+    std::stringstream ss; ss << f.rdbuf();
+    text = ss.str();
+  }
+  XmlParser parser(text);
+  std::unique_ptr<XmlNode> root = parser.parse();
+  if (root->tag != "robot") throw std::runtime_error("URDF: root element must be <robot>");
+  Builder bd;
+  std::map<std::string, bool> is_child;
+  for (const XmlNode* l : root->children("link")) {
+    std::string n = l->get("name");
+    if (n.empty()) throw std::runtime_error("URDF: <link> without a name");
+    if (bd.links.count(n)) throw std::runtime_error("URDF: duplicate link '" + n + "'");
+    bd.links[n] = l;
+  }
+  for (const XmlNode* j : root->children("joint")) {
+    const XmlNode *p = j->child("parent"), *c = j->child("child");
+    if (!p || !c) throw std::runtime_error("URDF: joint '" + j->get("name") + "' needs <parent> and <child>");
+    if (is_child[c->get("link")]) throw std::runtime_error("URDF: link '" + c->get("link") + "' has two parents (kinematic loops are unsupported)");
+    is_child[c->get("link")] = true;
+    bd.kids_of[p->get("link")].push_back(j);
+  }
+  std::string root_link;
+  for (const XmlNode* l : root->children("link"))
+    if (!is_child[l->get("name")]) {
+      if (!root_link.empty()) throw std::runtime_error("URDF: more than one root link ('" + root_link + "', '" + l->get("name") + "')");
+      root_link = l->get("name");
+    }
+  if (root_link.empty()) throw std::runtime_error("URDF: no root link");
+  Model& md = bd.md;
+  md.floating = (root_link != "world") ? 1 : 0;
+  bd.new_body(root_link, -1, md.floating ? JT_FLOATING : JT_FIXED, {0, 0, 0}, kEye, {0, 0, 1}, "root", -1e30, 1e30);
+  bd.absorb(0, root_link, {0, 0, 0}, kEye);
+
+  md.qidx.assign(md.nb, 0); md.vidx.assign(md.nb, 0); md.depth.assign(md.nb, 0); md.subtree.assign(md.nb, 1);
+  md.nq = md.floating ? 7 : 0; md.nv = md.floating ? 6 : 0;
+  for (int i = 1; i < md.nb; i++) {
+    md.qidx[i] = md.nq++; md.vidx[i] = md.nv++;
+    md.depth[i] = md.depth[md.parent[i]] + 1;
+    md.maxdepth = std::max(md.maxdepth, md.depth[i]);
+  }
+  for (int i = md.nb - 1; i > 0; i--) md.subtree[md.parent[i]] += md.subtree[i];
+  md.mass.resize(md.nb); md.com.resize(3 * md.nb); md.inertia.resize(6 * md.nb);
+  for (int i = 0; i < md.nb; i++) {
+    const Accum& a = bd.acc[i];
+    md.mass[i] = a.m;
+    for (int k = 0; k < 3; k++) md.com[3 * i + k] = a.c[k];
+    md.inertia[6 * i + 0] = a.I[0]; md.inertia[6 * i + 1] = a.I[1]; md.inertia[6 * i + 2] = a.I[2];
+    md.inertia[6 * i + 3] = a.I[4]; md.inertia[6 * i + 4] = a.I[5]; md.inertia[6 * i + 5] = a.I[8];
+    if (i > 0 && !(a.m > 0)) throw std::runtime_error("URDF: movable body '" + md.body_names[i] + "' has no mass");
+  }
+  return md;
+}
+
+}  // namespace rsb

@@ -1,0 +1,41 @@
+// Host-side robot model: URDF subset -> constant tables consumed by the CUDA step kernel.
+// Replaces the model-building half of raisim::World::addArticulatedSystem(urdf)
+// (upstream source is not in the reference snapshot -- closed libraisim.so).
+#pragma once
+#include <array>
+#include <string>
+#include <vector>
+
+namespace rsb {
+
+enum JointType { JT_FIXED = 0, JT_REVOLUTE = 1, JT_PRISMATIC = 2, JT_FLOATING = 3 };
+enum CollType { CT_SPHERE = 0, CT_BOX = 1, CT_CAPSULE = 2 };
+
+struct Frame {
+  std::string name;
+  int body;
+  std::array<double, 3> pos;
+  std::array<double, 9> rot;
+};
+
+struct Model {
+  int nb = 0, nq = 0, nv = 0, floating = 0, maxdepth = 0;
+  std::vector<int> parent, jtype, qidx, vidx, depth, subtree;
+  std::vector<double> jpos, jrot, axis, mass, com, inertia, jlimit;   // 3,9,3,1,3,6,2 per body
+  std::vector<std::string> body_names, joint_names;
+  // collision bodies
+  std::vector<int> cbody, ctype;
+  std::vector<double> csize, cpos, crot;                               // 3,3,9 per collision body
+  std::vector<std::string> coll_names;
+  // candidate contact points (sphere -> 1, capsule -> 2 end spheres, box -> 8 corners)
+  std::vector<int> pt_body, pt_coll, pt_feat;
+  std::vector<double> pt_pos, pt_rad;
+  std::vector<Frame> frames;                                            // one per URDF link
+  int ncoll() const { return (int)cbody.size(); }
+  int npts() const { return (int)pt_body.size(); }
+};
+
+// Throws std::runtime_error with a readable message on malformed input.
+Model load_urdf(const std::string& path_or_xml);
+
+}  // namespace rsb

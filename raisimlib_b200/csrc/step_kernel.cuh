@@ -1,0 +1,784 @@
+// Fused World::integrate() for a batch of environments -- hand-written sm_100a CUDA.
+//
+// One warp == one environment (BASELINE.json north_star).  A CTA of WPC warps shares the model
+// constant block, staged global -> shared ONCE per CTA by a TMA bulk copy (cp.async.bulk +
+// mbarrier; SASS: UBLKCP).  Every per-environment intermediate (body poses, M / its Cholesky
+// factor, contact Jacobians, Delassus matrix) lives in that warp's shared-memory workspace; HBM is
+// touched only for the coalesced state rows in, state rows + contact records out.
+//
+// Stages (same math as oracle/rbd_oracle.hpp):
+//   A  lane = body   : FK + RNEA forward walk down each body's own ancestor chain (registers),
+//                      per-body force / composite-inertia terms, subtree sums by warp shuffles
+//                      -> h, M (CRBA in a world-aligned frame centred on the base)
+//   B  lane = point  : candidate point vs Ground / HeightMap, ballot-compacted contact list
+//   C  lane = column : b, Mhat = M + dt Kd + dt^2 Kp, Cholesky, Y = L^-1 J^T, G = Y^T Y
+//   D  lane = row    : per-contact Gauss-Seidel; slip by a 32-way section search (all lanes probe)
+//   E  lane = dof    : v+ = v + L^-T (dt z + Y lam), q+ = q (+) dt v+
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/rsb.h"
+
+namespace rsb {
+
+constexpr int KMAX = RSB_KMAX;
+constexpr int CMAX = 3 * KMAX;      // contact rows
+constexpr int CP = CMAX + 1;        // Y row stride: columns 0..C-1 = contact rows, column C = b
+constexpr int GP = CMAX + 1;        // G row stride (odd: conflict-free row access by lane)
+constexpr int NSEC = 32;
+constexpr int NROUNDS = 4;
+constexpr int SEC_STRIDE = 36;      // (NSEC+1) padded
+constexpr int CT_WORDS = 16;        // per-contact shared record
+constexpr int MAX_PT_SLOTS = 2;     // candidate points per lane (npts <= 64)
+constexpr unsigned FULL = 0xffffffffu;
+
+enum BodyField {
+  BF_PARENT = 0, BF_JTYPE = 1, BF_QIDX = 2, BF_VIDX = 3, BF_DEPTH = 4, BF_SUBTREE = 5,
+  BF_JPOS = 6, BF_JROT = 9, BF_AXIS = 18, BF_MASS = 21, BF_COM = 22, BF_INERTIA = 25, BF_COUNT = 31
+};
+enum PoseField { PF_R = 0, PF_P = 9, PF_A = 12, PF_COUNT = 15 };
+enum CtField { CF_POS = 0, CF_N = 3, CF_T1 = 6, CF_T2 = 9, CF_DEPTH = 12, CF_PT = 13, CF_BODY = 14, CF_PAIR = 15 };
+
+// header of the model constant blob (first 16 words)
+struct BlobHeader {
+  int nb, nq, nv, npts, floating, maxdepth, nbp, nptp, nvp, nqp;
+  int off_body, off_anc, off_pts, off_gain, off_dofq, off_sec;
+};
+static_assert(sizeof(BlobHeader) == 64, "header is 16 words");
+
+// per-warp workspace layout (word offsets), computed on the host
+struct WsLayout {
+  int o_gc, o_gv, o_tau, o_pt, o_vt, o_L, o_invd, o_rhs, o_ct, o_Y, o_lam, o_u;   // persistent
+  int o_h, o_b, o_pose;                                                             // union A
+  int o_G;                                                                          // union B
+  int mp;                                                                           // L row stride
+  int words;
+};
+
+struct TerrainDesc {
+  int type;            // 0 none, 1 Ground, 2 HeightMap
+  float ground_z;
+  int xs, ys;
+  float x0, y0, dx, dy, xmax, ymax;   // grid origin, pitch, index bounds (xs-1, ys-1 as float)
+  const float* h;
+};
+
+struct StepArgs {
+  int num_envs, substeps;
+  int gc_stride, gv_stride;
+  float *gc, *gv;
+  const float *tau, *ptarget, *vtarget;
+  int use_pd;
+  rsb_params prm;
+  TerrainDesc ter;
+  WsLayout ws;
+  int blob_words;
+  const uint32_t* blob;
+  // outputs
+  int* ncontacts;
+  rsb_contact* contacts;
+  int* contact_pt;     // [N][KMAX]
+  int* iters;          // [N]
+  float *dbg_M, *dbg_h, *dbg_R, *dbg_p;   // optional (integrate1 / getters)
+  int phase_mask;      // bit0: stop after stage C (integrate1: no state update)
+};
+
+// ------------------------------------------------------------------ small device math ----------
+struct f3 { float x, y, z; };
+__device__ __forceinline__ f3 mk(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ f3 operator+(f3 a, f3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ f3 operator*(float s, f3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ f3 cross(f3 a, f3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ f3 mulR(const float* R, f3 v) {
+  return mk(R[0] * v.x + R[1] * v.y + R[2] * v.z, R[3] * v.x + R[4] * v.y + R[5] * v.z, R[6] * v.x + R[7] * v.y + R[8] * v.z);
+}
+__device__ __forceinline__ f3 mulRt(const float* R, f3 v) {
+  return mk(R[0] * v.x + R[3] * v.y + R[6] * v.z, R[1] * v.x + R[4] * v.y + R[7] * v.z, R[2] * v.x + R[5] * v.y + R[8] * v.z);
+}
+__device__ __forceinline__ void matmul3(const float* A, const float* B, float* C) {
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+__device__ __forceinline__ f3 shfl3(f3 v, int src) {
+  return mk(__shfl_sync(FULL, v.x, src), __shfl_sync(FULL, v.y, src), __shfl_sync(FULL, v.z, src));
+}
+
+// ------------------------------------------------------------------ TMA bulk copy + mbarrier ---
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // bounded spin: a TMA that never lands must trap, not hang the GPU
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); spin++)
+    if (spin > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------------ slip search ----------------
+// One probe of the (cone surface) x (zero normal velocity) curve; see oracle solve_one().
+struct Probe { float g, f, lx, ly, lz; bool ok; };
+__device__ __forceinline__ Probe slip_probe(float cs, float sn, float a, float b, float cc, float d, float e, float f, f3 c, float mu) {
+  Probe p;
+  float D = f + mu * (cc * cs + e * sn);
+  p.ok = D > 1e-12f;
+  float lz = -c.z / D;
+  p.lx = mu * lz * cs; p.ly = mu * lz * sn; p.lz = lz;
+  float vx = c.x + a * p.lx + b * p.ly + cc * lz;
+  float vy = c.y + b * p.lx + d * p.ly + e * lz;
+  p.g = (-vx * sn + vy * cs) * D - mu * (-cc * sn + e * cs) * (vx * cs + vy * sn);
+  p.f = c.x * p.lx + c.y * p.ly + c.z * lz + 0.5f * (p.lx * vx + p.ly * vy - lz * c.z) - 0.5f * (c.x * p.lx + c.y * p.ly);
+  return p;
+}
+
+// Per-contact rule (opening / stick / slip).  G = [a b cc; b d e; cc e f], Gi = its inverse (sym, 6),
+// c = contact velocity without this contact's impulse.  All lanes call with identical arguments;
+// the slip branch spreads NSEC probes over the lanes.  Result identical on all lanes.
+__device__ __forceinline__ f3 solve_contact(const float* Gs, const float* Gi, f3 c, float mu, const float* sec_c, const float* sec_s, int lane) {
+  if (c.z > 0.f) return mk(0.f, 0.f, 0.f);
+  f3 ls = mk(-(Gi[0] * c.x + Gi[1] * c.y + Gi[2] * c.z), -(Gi[1] * c.x + Gi[3] * c.y + Gi[4] * c.z), -(Gi[2] * c.x + Gi[4] * c.y + Gi[5] * c.z));
+  if (ls.z >= 0.f && ls.x * ls.x + ls.y * ls.y <= mu * mu * ls.z * ls.z) return ls;
+  const float a = Gs[0], b = Gs[1], cc = Gs[2], d = Gs[3], e = Gs[4], f = Gs[5];
+  float base_c = 1.f, base_s = 0.f;
+  float lo_c = 1.f, lo_s = 0.f, hi_c = 1.f, hi_s = 0.f, glo = 0.f, ghi = 0.f;
+  f3 best = mk(0.f, 0.f, 0.f);
+  bool have = false;
+#pragma unroll 1
+  for (int r = 0; r < NROUNDS; r++) {
+    // lane k probes direction k; direction NSEC comes from lane 0 of the NEXT position (k+1) via shuffle
+    float tc = sec_c[r * SEC_STRIDE + lane], ts = sec_s[r * SEC_STRIDE + lane];
+    float cs = base_c * tc - base_s * ts, sn = base_s * tc + base_c * ts;
+    Probe p = slip_probe(cs, sn, a, b, cc, d, e, f, c, mu);
+    // the closing probe (k = NSEC) is evaluated by every lane redundantly (same value everywhere)
+    float tc2 = sec_c[r * SEC_STRIDE + NSEC], ts2 = sec_s[r * SEC_STRIDE + NSEC];
+    float cs2 = base_c * tc2 - base_s * ts2, sn2 = base_s * tc2 + base_c * ts2;
+    Probe pe = slip_probe(cs2, sn2, a, b, cc, d, e, f, c, mu);
+    float g_next = __shfl_down_sync(FULL, p.g, 1);
+    bool ok_next = __shfl_down_sync(FULL, (int)p.ok, 1) != 0;
+    float cs_next = __shfl_down_sync(FULL, cs, 1), sn_next = __shfl_down_sync(FULL, sn, 1);
+    if (lane == NSEC - 1) { g_next = pe.g; ok_next = pe.ok; cs_next = cs2; sn_next = sn2; }
+    bool cand = p.ok && ok_next && (p.g < 0.f) && (g_next >= 0.f);
+    unsigned m = __ballot_sync(FULL, cand);
+    if (m == 0u) {
+      if (!have) {   // no bracket on the whole circle: least-energy probe (lowest index on ties)
+        unsigned okm = __ballot_sync(FULL, p.ok);
+        if (okm == 0u) return mk(0.f, 0.f, fmaxf(0.f, -c.z / f));
+        float fv = p.ok ? p.f : 3.0e38f;
+        float fm = fv;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) fm = fminf(fm, __shfl_xor_sync(FULL, fm, o));
+        unsigned w = __ballot_sync(FULL, p.ok && fv == fm);
+        int src = __ffs(w) - 1;
+        return mk(__shfl_sync(FULL, p.lx, src), __shfl_sync(FULL, p.ly, src), __shfl_sync(FULL, p.lz, src));
+      }
+      break;
+    }
+    // among sign changes pick the one with the least energy at its left end (lowest index on ties)
+    int pick;
+    if ((m & (m - 1)) == 0u) pick = __ffs(m) - 1;
+    else {
+      float fv = cand ? p.f : 3.0e38f;
+      float fm = fv;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) fm = fminf(fm, __shfl_xor_sync(FULL, fm, o));
+      unsigned w = __ballot_sync(FULL, cand && fv == fm);
+      pick = __ffs(w) - 1;
+    }
+    lo_c = __shfl_sync(FULL, cs, pick); lo_s = __shfl_sync(FULL, sn, pick);
+    hi_c = __shfl_sync(FULL, cs_next, pick); hi_s = __shfl_sync(FULL, sn_next, pick);
+    glo = __shfl_sync(FULL, p.g, pick); ghi = __shfl_sync(FULL, g_next, pick);
+    best = mk(__shfl_sync(FULL, p.lx, pick), __shfl_sync(FULL, p.ly, pick), __shfl_sync(FULL, p.lz, pick));
+    base_c = lo_c; base_s = lo_s; have = true;
+  }
+  float tt = (ghi - glo) != 0.f ? (-glo / (ghi - glo)) : 0.5f;
+  float cs = lo_c + tt * (hi_c - lo_c), sn = lo_s + tt * (hi_s - lo_s);
+  float inv = 1.0f / sqrtf(cs * cs + sn * sn);
+  cs *= inv; sn *= inv;
+  Probe p = slip_probe(cs, sn, a, b, cc, d, e, f, c, mu);
+  return p.ok ? mk(p.lx, p.ly, p.lz) : best;
+}
+
+// ------------------------------------------------------------------ terrain --------------------
+__device__ __forceinline__ bool terrain_query(const TerrainDesc& t, f3 P, float& dist, f3& n, int& pair) {
+  if (t.type == 1) { dist = P.z - t.ground_z; n = mk(0.f, 0.f, 1.f); pair = 0; return true; }
+  if (t.type != 2) return false;
+  float gx = (P.x - t.x0) / t.dx, gy = (P.y - t.y0) / t.dy;
+  if (!(gx >= 0.f) || !(gy >= 0.f) || !(gx < t.xmax) || !(gy < t.ymax)) return false;
+  int ix = (int)gx, iy = (int)gy;
+  float fx = gx - (float)ix, fy = gy - (float)iy;
+  const float* H = t.h + iy * t.xs + ix;
+  float h00 = __ldg(H), h10 = __ldg(H + 1), h01 = __ldg(H + t.xs), h11 = __ldg(H + t.xs + 1);
+  float sx, sy; int tri;
+  if (fx >= fy) { sx = h10 - h00; sy = h11 - h10; tri = 0; }
+  else { sx = h11 - h01; sy = h01 - h00; tri = 1; }
+  float zt = h00 + sx * fx + sy * fy;
+  float nx = -sx / t.dx, ny = -sy / t.dy;
+  float inv = 1.0f / sqrtf(nx * nx + ny * ny + 1.0f);
+  n = mk(nx * inv, ny * inv, inv);
+  dist = (P.z - zt) * inv;
+  pair = 2 * (iy * (t.xs - 1) + ix) + tri;
+  return true;
+}
+
+// ------------------------------------------------------------------ the kernel -----------------
+template <int WPC>
+__global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_constant__ StepArgs args) {
+  extern __shared__ __align__(128) uint32_t smem[];
+  __shared__ __align__(8) uint64_t tma_bar;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // ---- stage the model constant block once per CTA with one TMA bulk copy ----------------------
+  if (threadIdx.x == 0) {
+    mbar_init(&tma_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&tma_bar, (uint32_t)args.blob_words * 4u);
+    tma_bulk_g2s(smem, args.blob, (uint32_t)args.blob_words * 4u, &tma_bar);
+  }
+  mbar_wait(&tma_bar, 0);
+
+  const BlobHeader& H = *reinterpret_cast<const BlobHeader*>(smem);
+  const int nb = H.nb, nq = H.nq, nv = H.nv, npts = H.npts, floating = H.floating, maxdepth = H.maxdepth;
+  const int nbp = H.nbp, nptp = H.nptp, nvp = H.nvp;
+  const float* bodyf = reinterpret_cast<const float*>(smem + H.off_body);
+  const int* bodyi = reinterpret_cast<const int*>(smem + H.off_body);
+  const int* anc = reinterpret_cast<const int*>(smem + H.off_anc);
+  const float* ptsf = reinterpret_cast<const float*>(smem + H.off_pts);
+  const int* ptsi = reinterpret_cast<const int*>(smem + H.off_pts);
+  const float* kp = reinterpret_cast<const float*>(smem + H.off_gain);
+  const float* kd = kp + nvp;
+  const int* dofq = reinterpret_cast<const int*>(smem + H.off_dofq);
+  const float* sec_c = reinterpret_cast<const float*>(smem + H.off_sec);
+  const float* sec_s = sec_c + NROUNDS * SEC_STRIDE;
+
+  const WsLayout& L = args.ws;
+  float* ws = reinterpret_cast<float*>(smem + ((args.blob_words + 31) & ~31) + warp * L.words);
+  float* s_gc = ws + L.o_gc; float* s_gv = ws + L.o_gv; float* s_tau = ws + L.o_tau; float* s_pt = ws + L.o_pt; float* s_vt = ws + L.o_vt;
+  float* s_L = ws + L.o_L; float* s_invd = ws + L.o_invd; float* s_rhs = ws + L.o_rhs; float* s_ct = ws + L.o_ct;
+  float* s_Y = ws + L.o_Y; float* s_lam = ws + L.o_lam; float* s_u = ws + L.o_u;
+  float* s_h = ws + L.o_h; float* s_b = ws + L.o_b; float* s_pose = ws + L.o_pose; float* s_G = ws + L.o_G;
+  const int MP = L.mp;
+  const float dt = args.prm.dt;
+  const float mu = args.prm.mu;
+  const f3 grav = mk(args.prm.gravity[0], args.prm.gravity[1], args.prm.gravity[2]);
+
+  // body constants of this lane (lane == body)
+  const int b = lane;
+  const bool bvalid = b < nb;
+  const int bb = bvalid ? b : 0;
+  const int my_parent = bodyi[BF_PARENT * nbp + bb], my_jtype = bodyi[BF_JTYPE * nbp + bb];
+  const int my_vidx = bodyi[BF_VIDX * nbp + bb], my_depth = bodyi[BF_DEPTH * nbp + bb], my_sub = bodyi[BF_SUBTREE * nbp + bb];
+  int max_inner = 0;   // largest non-root subtree size - 1 (loop bound of the subtree accumulation)
+  {
+    int v = (bvalid && b > 0) ? my_sub - 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
+    max_inner = v;
+  }
+
+  const int warps_total = gridDim.x * WPC;
+  for (int env = blockIdx.x * WPC + warp; env < args.num_envs; env += warps_total) {
+    // ---- load this environment's rows (coalesced: one row per warp) -----------------------------
+    {
+      const float* g_gc = args.gc + (size_t)env * args.gc_stride;
+      const float* g_gv = args.gv + (size_t)env * args.gv_stride;
+      for (int i = lane; i < nq; i += 32) s_gc[i] = g_gc[i];
+      for (int i = lane; i < nv; i += 32) s_gv[i] = g_gv[i];
+      for (int i = lane; i < nv; i += 32) s_tau[i] = args.tau ? args.tau[(size_t)env * args.gv_stride + i] : 0.f;
+      if (args.use_pd) {
+        for (int i = lane; i < nq; i += 32) s_pt[i] = args.ptarget[(size_t)env * args.gc_stride + i];
+        for (int i = lane; i < nv; i += 32) s_vt[i] = args.vtarget[(size_t)env * args.gv_stride + i];
+      }
+    }
+    __syncwarp();
+    int K = 0, iters = 0;
+
+    for (int sub = 0; sub < args.substeps; sub++) {
+      // =========================== stage A: FK + RNEA + CRBA =====================================
+      float R[9]; f3 p, w, v, wd, vd, ax;
+      if (floating) {
+        float qw = s_gc[3], qx = s_gc[4], qy = s_gc[5], qz = s_gc[6];
+        float inv = 1.0f / sqrtf(qw * qw + qx * qx + qy * qy + qz * qz);
+        qw *= inv; qx *= inv; qy *= inv; qz *= inv;
+        R[0] = 1.f - 2.f * (qy * qy + qz * qz); R[1] = 2.f * (qx * qy - qw * qz); R[2] = 2.f * (qx * qz + qw * qy);
+        R[3] = 2.f * (qx * qy + qw * qz); R[4] = 1.f - 2.f * (qx * qx + qz * qz); R[5] = 2.f * (qy * qz - qw * qx);
+        R[6] = 2.f * (qx * qz - qw * qy); R[7] = 2.f * (qy * qz + qw * qx); R[8] = 1.f - 2.f * (qx * qx + qy * qy);
+        p = mk(s_gc[0], s_gc[1], s_gc[2]);
+        v = mk(s_gv[0], s_gv[1], s_gv[2]); w = mk(s_gv[3], s_gv[4], s_gv[5]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 9; k++) R[k] = bodyf[(BF_JROT + k) * nbp];
+        p = mk(bodyf[(BF_JPOS + 0) * nbp], bodyf[(BF_JPOS + 1) * nbp], bodyf[(BF_JPOS + 2) * nbp]);
+        v = mk(0.f, 0.f, 0.f); w = mk(0.f, 0.f, 0.f);
+      }
+      const f3 O = p;                      // base origin: centre of the world-aligned CRBA frame
+      wd = mk(0.f, 0.f, 0.f); vd = mk(-grav.x, -grav.y, -grav.z); ax = mk(0.f, 0.f, 0.f);
+#pragma unroll 1
+      for (int d = 1; d <= maxdepth; d++) {
+        int j = (bvalid && d <= my_depth) ? anc[(d - 1) * nbp + b] : -1;
+        if (j >= 0) {
+          f3 jp = mk(bodyf[(BF_JPOS + 0) * nbp + j], bodyf[(BF_JPOS + 1) * nbp + j], bodyf[(BF_JPOS + 2) * nbp + j]);
+          float Jr[9], Rj[9];
+#pragma unroll
+          for (int k = 0; k < 9; k++) Jr[k] = bodyf[(BF_JROT + k) * nbp + j];
+          f3 al = mk(bodyf[(BF_AXIS + 0) * nbp + j], bodyf[(BF_AXIS + 1) * nbp + j], bodyf[(BF_AXIS + 2) * nbp + j]);
+          f3 r = mulR(R, jp);
+          matmul3(R, Jr, Rj);
+          f3 aj = mulR(Rj, al);
+          float q = s_gc[bodyi[BF_QIDX * nbp + j]], qd = s_gv[bodyi[BF_VIDX * nbp + j]];
+          const bool rev = bodyi[BF_JTYPE * nbp + j] == 1;
+          if (!rev) r = r + q * aj;
+          f3 wxr = cross(w, r);
+          f3 vn = v + wxr;
+          f3 vdn = vd + cross(wd, r) + cross(w, wxr);
+          f3 qa = qd * aj;
+          if (rev) {
+            float sq, cq;
+            sincosf(q, &sq, &cq);
+            float t = 1.f - cq;
+            float Rq[9] = {t * al.x * al.x + cq, t * al.x * al.y - sq * al.z, t * al.x * al.z + sq * al.y,
+                           t * al.x * al.y + sq * al.z, t * al.y * al.y + cq, t * al.y * al.z - sq * al.x,
+                           t * al.x * al.z - sq * al.y, t * al.y * al.z + sq * al.x, t * al.z * al.z + cq};
+            matmul3(Rj, Rq, R);
+            wd = wd + cross(w, qa);
+            w = w + qa;
+          } else {
+#pragma unroll
+            for (int k = 0; k < 9; k++) R[k] = Rj[k];
+            vn = vn + qa;
+            vdn = vdn + 2.f * cross(w, qa);
+          }
+          p = p + r; v = vn; vd = vdn; ax = aj;
+        }
+      }
+      // publish poses for stages B and C
+      if (bvalid) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) s_pose[(PF_R + k) * nbp + b] = R[k];
+        s_pose[(PF_P + 0) * nbp + b] = p.x; s_pose[(PF_P + 1) * nbp + b] = p.y; s_pose[(PF_P + 2) * nbp + b] = p.z;
+        s_pose[(PF_A + 0) * nbp + b] = ax.x; s_pose[(PF_A + 1) * nbp + b] = ax.y; s_pose[(PF_A + 2) * nbp + b] = ax.z;
+      }
+      // per-body force and inertia terms about O
+      float X[16];   // F(3) N_O(3) m h(3) I_O(6)
+      {
+        float m = bvalid ? bodyf[BF_MASS * nbp + bb] : 0.f;
+        f3 cl = mk(bodyf[(BF_COM + 0) * nbp + bb], bodyf[(BF_COM + 1) * nbp + bb], bodyf[(BF_COM + 2) * nbp + bb]);
+        f3 c = mulR(R, cl);
+        f3 cO = (p - O) + c;
+        f3 ac = vd + cross(wd, c) + cross(w, cross(w, c));
+        f3 f = m * ac;
+        float I0 = bodyf[(BF_INERTIA + 0) * nbp + bb], I1 = bodyf[(BF_INERTIA + 1) * nbp + bb], I2 = bodyf[(BF_INERTIA + 2) * nbp + bb];
+        float I3 = bodyf[(BF_INERTIA + 3) * nbp + bb], I4 = bodyf[(BF_INERTIA + 4) * nbp + bb], I5 = bodyf[(BF_INERTIA + 5) * nbp + bb];
+        if (!bvalid) { I0 = I1 = I2 = I3 = I4 = I5 = 0.f; }
+        // Iw = R I R^T
+        float RI[9];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+          RI[3 * r + 0] = R[3 * r] * I0 + R[3 * r + 1] * I1 + R[3 * r + 2] * I2;
+          RI[3 * r + 1] = R[3 * r] * I1 + R[3 * r + 1] * I3 + R[3 * r + 2] * I4;
+          RI[3 * r + 2] = R[3 * r] * I2 + R[3 * r + 1] * I4 + R[3 * r + 2] * I5;
+        }
+        float W0 = RI[0] * R[0] + RI[1] * R[1] + RI[2] * R[2], W1 = RI[0] * R[3] + RI[1] * R[4] + RI[2] * R[5], W2 = RI[0] * R[6] + RI[1] * R[7] + RI[2] * R[8];
+        float W3 = RI[3] * R[3] + RI[4] * R[4] + RI[5] * R[5], W4 = RI[3] * R[6] + RI[4] * R[7] + RI[5] * R[8], W5 = RI[6] * R[6] + RI[7] * R[7] + RI[8] * R[8];
+        f3 Iw = mk(W0 * w.x + W1 * w.y + W2 * w.z, W1 * w.x + W3 * w.y + W4 * w.z, W2 * w.x + W4 * w.y + W5 * w.z);
+        f3 Iwd = mk(W0 * wd.x + W1 * wd.y + W2 * wd.z, W1 * wd.x + W3 * wd.y + W4 * wd.z, W2 * wd.x + W4 * wd.y + W5 * wd.z);
+        f3 n = Iwd + cross(w, Iw) + cross(cO, f);
+        float cc = dot(cO, cO);
+        X[0] = f.x; X[1] = f.y; X[2] = f.z; X[3] = n.x; X[4] = n.y; X[5] = n.z;
+        X[6] = m; X[7] = m * cO.x; X[8] = m * cO.y; X[9] = m * cO.z;
+        X[10] = W0 + m * (cc - cO.x * cO.x); X[11] = W1 - m * cO.x * cO.y; X[12] = W2 - m * cO.x * cO.z;
+        X[13] = W3 + m * (cc - cO.y * cO.y); X[14] = W4 - m * cO.y * cO.z; X[15] = W5 + m * (cc - cO.z * cO.z);
+      }
+      // subtree sums: bodies are in DFS pre-order, so subtree(b) = lanes [b, b + size)
+      float A[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) A[k] = X[k];
+#pragma unroll 1
+      for (int s = 1; s <= max_inner; s++) {
+        bool take = (b > 0) && (s < my_sub);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          float x = __shfl_down_sync(FULL, X[k], s);
+          if (take) A[k] += x;
+        }
+      }
+      {   // root: everything
+        float T[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          float t = X[k];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+          T[k] = t;
+        }
+        if (b == 0) {
+#pragma unroll
+          for (int k = 0; k < 16; k++) A[k] = T[k];
+        }
+      }
+      // bias force h and CRBA columns
+      for (int i = lane; i < nv * MP; i += 32) s_L[i] = 0.f;
+      __syncwarp();
+      f3 rO = p - O;
+      const bool rev = my_jtype == 1;
+      f3 Sw = rev ? ax : mk(0.f, 0.f, 0.f);
+      f3 Sv = rev ? cross(rO, ax) : ax;
+      f3 Fc = mk(A[0], A[1], A[2]), Nc = mk(A[3], A[4], A[5]);
+      f3 hh = mk(A[7], A[8], A[9]);
+      f3 ff = A[6] * Sv + cross(Sw, hh);
+      f3 nn = mk(A[10] * Sw.x + A[11] * Sw.y + A[12] * Sw.z, A[11] * Sw.x + A[13] * Sw.y + A[14] * Sw.z, A[12] * Sw.x + A[14] * Sw.y + A[15] * Sw.z) + cross(hh, Sv);
+      if (bvalid && b > 0) {
+        s_h[my_vidx] = dot(Sw, Nc) + dot(Sv, Fc);      // S^T [N_O; F]  (moment about O)
+        s_L[my_vidx * MP + my_vidx] = dot(Sw, nn) + dot(Sv, ff);
+        if (floating) {
+          s_L[my_vidx * MP + 0] = ff.x; s_L[my_vidx * MP + 1] = ff.y; s_L[my_vidx * MP + 2] = ff.z;
+          s_L[my_vidx * MP + 3] = nn.x; s_L[my_vidx * MP + 4] = nn.y; s_L[my_vidx * MP + 5] = nn.z;
+        }
+      }
+      if (b == 0 && floating) {
+        s_h[0] = Fc.x; s_h[1] = Fc.y; s_h[2] = Fc.z; s_h[3] = Nc.x; s_h[4] = Nc.y; s_h[5] = Nc.z;
+        // lower triangle of [ m 1, -[h]x ; [h]x, I_O ]
+        s_L[0 * MP + 0] = A[6]; s_L[1 * MP + 1] = A[6]; s_L[2 * MP + 2] = A[6];
+        s_L[3 * MP + 1] = -hh.z; s_L[3 * MP + 2] = hh.y;
+        s_L[4 * MP + 0] = hh.z; s_L[4 * MP + 2] = -hh.x;
+        s_L[5 * MP + 0] = -hh.y; s_L[5 * MP + 1] = hh.x;
+        s_L[3 * MP + 3] = A[10]; s_L[4 * MP + 3] = A[11]; s_L[5 * MP + 3] = A[12];
+        s_L[4 * MP + 4] = A[13]; s_L[5 * MP + 4] = A[14]; s_L[5 * MP + 5] = A[15];
+      }
+      {   // M[vi][vj] for proper ancestors j (excluding the root)
+        int j = (bvalid && b > 0) ? my_parent : 0;
+#pragma unroll 1
+        for (int d = 2; d <= maxdepth; d++) {
+          int src = j > 0 ? j : 0;
+          f3 Swj = shfl3(Sw, src), Svj = shfl3(Sv, src);
+          int vj = __shfl_sync(FULL, my_vidx, src);
+          if (j > 0) {
+            s_L[my_vidx * MP + vj] = dot(Swj, nn) + dot(Svj, ff);
+            j = bodyi[BF_PARENT * nbp + j];
+          }
+        }
+      }
+      __syncwarp();
+      if (args.dbg_M) {   // getters: full symmetric M, h, poses
+        float* gM = args.dbg_M + (size_t)env * nv * nv;
+        for (int i = lane; i < nv * nv; i += 32) { int r = i / nv, c = i % nv; gM[i] = r >= c ? s_L[r * MP + c] : s_L[c * MP + r]; }
+        float* gh = args.dbg_h + (size_t)env * nv;
+        for (int i = lane; i < nv; i += 32) gh[i] = s_h[i];
+        if (bvalid) {
+          float* gR = args.dbg_R + ((size_t)env * nb + b) * 9;
+          float* gp = args.dbg_p + ((size_t)env * nb + b) * 3;
+#pragma unroll
+          for (int k = 0; k < 9; k++) gR[k] = R[k];
+          gp[0] = p.x; gp[1] = p.y; gp[2] = p.z;
+        }
+      }
+
+      // =========================== stage B: narrow phase ========================================
+      float c_depth[MAX_PT_SLOTS]; f3 c_pos[MAX_PT_SLOTS], c_n[MAX_PT_SLOTS]; int c_pair[MAX_PT_SLOTS], c_body[MAX_PT_SLOTS];
+      bool c_hit[MAX_PT_SLOTS];
+#pragma unroll
+      for (int s = 0; s < MAX_PT_SLOTS; s++) {
+        int k = lane + 32 * s;
+        c_hit[s] = false; c_depth[s] = 0.f; c_pair[s] = 0; c_body[s] = 0; c_pos[s] = mk(0, 0, 0); c_n[s] = mk(0, 0, 1);
+        if (k < npts) {
+          int pb = ptsi[0 * nptp + k];
+          f3 pl = mk(ptsf[1 * nptp + k], ptsf[2 * nptp + k], ptsf[3 * nptp + k]);
+          float rad = ptsf[4 * nptp + k];
+          float Rb[9];
+#pragma unroll
+          for (int q = 0; q < 9; q++) Rb[q] = s_pose[(PF_R + q) * nbp + pb];
+          f3 P = mk(s_pose[(PF_P + 0) * nbp + pb], s_pose[(PF_P + 1) * nbp + pb], s_pose[(PF_P + 2) * nbp + pb]) + mulR(Rb, pl);
+          float dist; f3 n; int pair;
+          if (terrain_query(args.ter, P, dist, n, pair)) {
+            float depth = rad - dist;
+            if (depth > 0.f) { c_hit[s] = true; c_depth[s] = depth; c_pair[s] = pair; c_body[s] = pb; c_n[s] = n; c_pos[s] = P - rad * n; }
+          }
+        }
+      }
+      unsigned hm[MAX_PT_SLOTS];
+      int total = 0;
+#pragma unroll
+      for (int s = 0; s < MAX_PT_SLOTS; s++) { hm[s] = __ballot_sync(FULL, c_hit[s]); total += __popc(hm[s]); }
+      while (total > KMAX) {   // drop the shallowest (ties: highest candidate index) until KMAX remain
+        float dmin = 3.0e38f; int imin = -1;
+#pragma unroll
+        for (int s = 0; s < MAX_PT_SLOTS; s++)
+          if (c_hit[s] && (c_depth[s] < dmin || (c_depth[s] == dmin && lane + 32 * s > imin))) { dmin = c_depth[s]; imin = lane + 32 * s; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          float d2 = __shfl_xor_sync(FULL, dmin, o); int i2 = __shfl_xor_sync(FULL, imin, o);
+          if (d2 < dmin || (d2 == dmin && i2 > imin)) { dmin = d2; imin = i2; }
+        }
+#pragma unroll
+        for (int s = 0; s < MAX_PT_SLOTS; s++) if (lane + 32 * s == imin) c_hit[s] = false;
+        total = 0;
+#pragma unroll
+        for (int s = 0; s < MAX_PT_SLOTS; s++) { hm[s] = __ballot_sync(FULL, c_hit[s]); total += __popc(hm[s]); }
+      }
+      K = total;
+      {
+        int base = 0;
+#pragma unroll
+        for (int s = 0; s < MAX_PT_SLOTS; s++) {
+          if (c_hit[s]) {
+            int slot = base + __popc(hm[s] & ((1u << lane) - 1u));
+            float* ct = s_ct + slot * CT_WORDS;
+            f3 n = c_n[s];
+            f3 e = (fabsf(n.x) < 0.9f) ? mk(1.f, 0.f, 0.f) : mk(0.f, 1.f, 0.f);
+            f3 t = e - dot(e, n) * n;
+            float inv = 1.0f / sqrtf(dot(t, t));
+            f3 t1 = inv * t, t2 = cross(n, t1);
+            ct[CF_POS] = c_pos[s].x; ct[CF_POS + 1] = c_pos[s].y; ct[CF_POS + 2] = c_pos[s].z;
+            ct[CF_N] = n.x; ct[CF_N + 1] = n.y; ct[CF_N + 2] = n.z;
+            ct[CF_T1] = t1.x; ct[CF_T1 + 1] = t1.y; ct[CF_T1 + 2] = t1.z;
+            ct[CF_T2] = t2.x; ct[CF_T2 + 1] = t2.y; ct[CF_T2 + 2] = t2.z;
+            ct[CF_DEPTH] = c_depth[s];
+            ct[CF_PT] = __int_as_float(lane + 32 * s); ct[CF_BODY] = __int_as_float(c_body[s]); ct[CF_PAIR] = __int_as_float(c_pair[s]);
+          }
+          base += __popc(hm[s]);
+        }
+      }
+      const int C = 3 * K;
+      if (args.phase_mask & 1) { __syncwarp(); break; }   // integrate1(): kinematics, collision, M, h only
+
+      // =========================== stage C: b, Mhat, Cholesky, Y, G ==============================
+      for (int i = lane; i < nv; i += 32) {
+        float bi = s_tau[i] - s_h[i];
+        if (args.use_pd) {
+          float kpi = kp[i], kdi = kd[i];
+          if (kpi != 0.f || kdi != 0.f) {
+            int qi = dofq[i];
+            bi += kpi * (s_pt[qi] - s_gc[qi] - dt * s_gv[i]) + kdi * (s_vt[i] - s_gv[i]);
+            s_L[i * MP + i] += dt * kdi + dt * dt * kpi;
+          }
+        }
+        s_b[i] = bi;
+      }
+      __syncwarp();
+      // Cholesky, right-looking, lane = row
+#pragma unroll 1
+      for (int j = 0; j < nv; j++) {
+        float djj = sqrtf(s_L[j * MP + j]);
+        float inv = 1.0f / djj;
+        __syncwarp();
+        for (int i = j + lane; i < nv; i += 32) {
+          float lij = (i == j) ? djj : s_L[i * MP + j] * inv;
+          s_L[i * MP + j] = lij;
+        }
+        if (lane == 0) s_invd[j] = inv;
+        __syncwarp();
+        for (int i = j + 1 + lane; i < nv; i += 32) {
+          float lij = s_L[i * MP + j];
+          for (int k = j + 1; k <= i; k++) s_L[i * MP + k] -= lij * s_L[k * MP + j];
+        }
+        __syncwarp();
+      }
+      // J^T columns (contact frame rows) into Y, plus column C = b ; u0 = J v
+      float u_c = 0.f;
+      if (lane <= C) {
+        const int c = lane;
+        for (int r = 0; r < nv; r++) s_Y[r * CP + c] = (c == C) ? s_b[r] : 0.f;
+        if (c < C) {
+          const float* ct = s_ct + (c / 3) * CT_WORDS;
+          const int d = c % 3;
+          const int fo = (d == 0) ? CF_T1 : (d == 1 ? CF_T2 : CF_N);
+          f3 axd = mk(ct[fo], ct[fo + 1], ct[fo + 2]);
+          f3 pos = mk(ct[CF_POS], ct[CF_POS + 1], ct[CF_POS + 2]);
+          if (floating) {
+            f3 rc = cross(pos - O, axd);
+            s_Y[0 * CP + c] = axd.x; s_Y[1 * CP + c] = axd.y; s_Y[2 * CP + c] = axd.z;
+            s_Y[3 * CP + c] = rc.x; s_Y[4 * CP + c] = rc.y; s_Y[5 * CP + c] = rc.z;
+            u_c = axd.x * s_gv[0] + axd.y * s_gv[1] + axd.z * s_gv[2] + rc.x * s_gv[3] + rc.y * s_gv[4] + rc.z * s_gv[5];
+          }
+          int j = __float_as_int(ct[CF_BODY]);
+          while (bodyi[BF_PARENT * nbp + j] >= 0) {
+            f3 aj = mk(s_pose[(PF_A + 0) * nbp + j], s_pose[(PF_A + 1) * nbp + j], s_pose[(PF_A + 2) * nbp + j]);
+            f3 col;
+            if (bodyi[BF_JTYPE * nbp + j] == 1) {
+              f3 pj = mk(s_pose[(PF_P + 0) * nbp + j], s_pose[(PF_P + 1) * nbp + j], s_pose[(PF_P + 2) * nbp + j]);
+              col = cross(aj, pos - pj);
+            } else col = aj;
+            int vj = bodyi[BF_VIDX * nbp + j];
+            float val = dot(col, axd);
+            s_Y[vj * CP + c] = val;
+            u_c += val * s_gv[vj];
+            j = bodyi[BF_PARENT * nbp + j];
+          }
+        }
+        // forward substitution down this lane's column
+        for (int r = 0; r < nv; r++) {
+          float s = s_Y[r * CP + c];
+          for (int k = 0; k < r; k++) s -= s_L[r * MP + k] * s_Y[k * CP + c];
+          s_Y[r * CP + c] = s * s_invd[r];
+        }
+      }
+      __syncwarp();
+      if (lane < C) {
+        float s = 0.f;
+        for (int r = 0; r < nv; r++) s += s_Y[r * CP + lane] * s_Y[r * CP + C];
+        float jv = u_c;
+        u_c = jv + dt * s;
+        if (lane % 3 == 2) {
+          float target = args.prm.erp * s_ct[(lane / 3) * CT_WORDS + CF_DEPTH] / dt;
+          if (args.prm.restitution > 0.f && jv < -args.prm.rest_threshold) target += -args.prm.restitution * jv;
+          u_c -= target;
+        }
+      }
+      for (int i = lane; i < nv; i += 32) s_rhs[i] = dt * s_Y[i * CP + C];
+      iters = 0;
+      float lam_c = 0.f;
+      if (K > 0) {
+        __syncwarp();      // h / b / poses are dead from here: G overlays them
+        // G = Y^T Y, lanes = (row a, offset group)
+        {
+          const int ng = 32 / C;                    // C <= 24 -> ng >= 1
+          const int a = lane % C, g = lane / C;
+          if (g < ng) {
+            for (int dd = g; dd <= C / 2; dd += ng) {
+              int bcol = a + dd; if (bcol >= C) bcol -= C;
+              float s = 0.f;
+              for (int r = 0; r < nv; r++) s += s_Y[r * CP + a] * s_Y[r * CP + bcol];
+              s_G[a * GP + bcol] = s; s_G[bcol * GP + a] = s;
+            }
+          }
+        }
+        __syncwarp();
+        // per-contact constants: symmetric 3x3 block and its inverse (lane i < K computes, all read)
+        float* s_Gii = s_u;   // 12 words per contact: G(6) Ginv(6)
+        if (lane < K) {
+          const int i3 = 3 * lane;
+          float a = s_G[i3 * GP + i3], bq = s_G[i3 * GP + i3 + 1], cc = s_G[i3 * GP + i3 + 2];
+          float d = s_G[(i3 + 1) * GP + i3 + 1], e = s_G[(i3 + 1) * GP + i3 + 2], f = s_G[(i3 + 2) * GP + i3 + 2];
+          float c00 = d * f - e * e, c01 = cc * e - bq * f, c02 = bq * e - cc * d;
+          float c11 = a * f - cc * cc, c12 = bq * cc - a * e, c22 = a * d - bq * bq;
+          float id = 1.0f / (a * c00 + bq * c01 + cc * c02);
+          float* o = s_Gii + 12 * lane;
+          o[0] = a; o[1] = bq; o[2] = cc; o[3] = d; o[4] = e; o[5] = f;
+          o[6] = c00 * id; o[7] = c01 * id; o[8] = c02 * id; o[9] = c11 * id; o[10] = c12 * id; o[11] = c22 * id;
+        }
+        __syncwarp();
+        // =========================== stage D: per-contact Gauss-Seidel ===========================
+        float alpha = args.prm.alpha_init;
+#pragma unroll 1
+        for (int it = 0; it < args.prm.max_iter; it++) {
+          float err = 0.f;
+#pragma unroll 1
+          for (int i = 0; i < K; i++) {
+            const int i3 = 3 * i;
+            f3 ui = mk(__shfl_sync(FULL, u_c, i3), __shfl_sync(FULL, u_c, i3 + 1), __shfl_sync(FULL, u_c, i3 + 2));
+            f3 l0 = mk(__shfl_sync(FULL, lam_c, i3), __shfl_sync(FULL, lam_c, i3 + 1), __shfl_sync(FULL, lam_c, i3 + 2));
+            const float* Gs = s_Gii + 12 * i;
+            f3 c0 = mk(ui.x - (Gs[0] * l0.x + Gs[1] * l0.y + Gs[2] * l0.z), ui.y - (Gs[1] * l0.x + Gs[3] * l0.y + Gs[4] * l0.z),
+                       ui.z - (Gs[2] * l0.x + Gs[4] * l0.y + Gs[5] * l0.z));
+            f3 ln = solve_contact(Gs, Gs + 6, c0, mu, sec_c, sec_s, lane);
+            f3 dl = alpha * (ln - l0);
+            if (lane < C) u_c += s_G[lane * GP + i3] * dl.x + s_G[lane * GP + i3 + 1] * dl.y + s_G[lane * GP + i3 + 2] * dl.z;
+            if (lane == i3) lam_c = l0.x + dl.x; else if (lane == i3 + 1) lam_c = l0.y + dl.y; else if (lane == i3 + 2) lam_c = l0.z + dl.z;
+            err = fmaxf(err, fmaxf(fabsf(dl.x), fmaxf(fabsf(dl.y), fabsf(dl.z))));
+          }
+          iters = it + 1;
+          alpha = fmaxf(args.prm.alpha_min, alpha * args.prm.alpha_decay);
+          if (err < args.prm.threshold) break;
+        }
+        if (lane < C) s_lam[lane] = lam_c;
+        __syncwarp();
+        for (int r = lane; r < nv; r += 32) {
+          float s = s_rhs[r];
+          for (int c = 0; c < C; c++) s += s_Y[r * CP + c] * s_lam[c];
+          s_rhs[r] = s;
+        }
+      }
+      __syncwarp();
+      // =========================== stage E: back-substitution and integration ====================
+#pragma unroll 1
+      for (int i = nv - 1; i >= 0; i--) {
+        float xi = s_rhs[i] * s_invd[i];
+        __syncwarp();
+        if (lane == 0) s_rhs[i] = xi;
+        for (int k = lane; k < i; k += 32) s_rhs[k] -= s_L[i * MP + k] * xi;
+        __syncwarp();
+      }
+      for (int i = lane; i < nv; i += 32) s_gv[i] += s_rhs[i];
+      __syncwarp();
+      if (floating) {
+        if (lane < 3) s_gc[lane] += dt * s_gv[lane];
+        f3 wn = mk(s_gv[3], s_gv[4], s_gv[5]);
+        float wnorm = sqrtf(dot(wn, wn)), ang = wnorm * dt;
+        float qw, qx, qy, qz;
+        if (ang > 1e-10f) { float sh, ch; sincosf(0.5f * ang, &sh, &ch); float s = sh / wnorm; qw = ch; qx = s * wn.x; qy = s * wn.y; qz = s * wn.z; }
+        else { qw = 1.f; qx = 0.5f * dt * wn.x; qy = 0.5f * dt * wn.y; qz = 0.5f * dt * wn.z; }
+        float pw = s_gc[3], px = s_gc[4], py = s_gc[5], pz = s_gc[6];
+        float nw = qw * pw - qx * px - qy * py - qz * pz;
+        float nx = qw * px + qx * pw + qy * pz - qz * py;
+        float ny = qw * py - qx * pz + qy * pw + qz * px;
+        float nz = qw * pz + qx * py - qy * px + qz * pw;
+        float inv = 1.0f / sqrtf(nw * nw + nx * nx + ny * ny + nz * nz);
+        __syncwarp();
+        if (lane == 0) { s_gc[3] = nw * inv; s_gc[4] = nx * inv; s_gc[5] = ny * inv; s_gc[6] = nz * inv; }
+      }
+      for (int i = lane; i < nv; i += 32) {
+        int qi = dofq[i];
+        if (qi >= (floating ? 7 : 0)) s_gc[qi] += dt * s_gv[i];
+      }
+      __syncwarp();
+    }   // substeps
+
+    // ---- store state rows and contact records -----------------------------------------------------
+    if (!(args.phase_mask & 1)) {
+      float* g_gc = args.gc + (size_t)env * args.gc_stride;
+      float* g_gv = args.gv + (size_t)env * args.gv_stride;
+      for (int i = lane; i < nq; i += 32) g_gc[i] = s_gc[i];
+      for (int i = lane; i < nv; i += 32) g_gv[i] = s_gv[i];
+    }
+    if (lane == 0) { args.ncontacts[env] = K; args.iters[env] = iters; }
+    if (lane < KMAX) {
+      rsb_contact rc;
+      int pt = -1;
+      if (lane < K) {
+        const float* ct = s_ct + lane * CT_WORDS;
+        float lx = 0.f, ly = 0.f, lz = 0.f;
+        if (!(args.phase_mask & 1)) { lx = s_lam[3 * lane]; ly = s_lam[3 * lane + 1]; lz = s_lam[3 * lane + 2]; }
+        rc.local_body = __float_as_int(ct[CF_BODY]); rc.pair_index = __float_as_int(ct[CF_PAIR]);
+        pt = __float_as_int(ct[CF_PT]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          rc.position[k] = ct[CF_POS + k]; rc.normal[k] = ct[CF_N + k];
+          rc.impulse[k] = ct[CF_T1 + k] * lx + ct[CF_T2 + k] * ly + ct[CF_N + k] * lz;
+        }
+        rc.depth = ct[CF_DEPTH];
+      } else {
+        rc.local_body = -1; rc.pair_index = -1; rc.depth = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { rc.position[k] = 0.f; rc.normal[k] = 0.f; rc.impulse[k] = 0.f; }
+      }
+      args.contacts[(size_t)env * KMAX + lane] = rc;
+      args.contact_pt[(size_t)env * KMAX + lane] = pt;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace rsb

@@ -1,0 +1,74 @@
+"""CPU-side checks of the product: the C-ABI library loads, exports every symbol include/rsb.h declares,
+and its URDF loader agrees table-by-table with the oracle's independent Python restatement."""
+import os
+import re
+import ctypes
+import numpy as np
+import pytest
+
+from conftest import ROOT, RSC
+from raisimlib_b200 import capi
+from oracle.urdf_tables import load_tables
+from helpers import PENDULUM_URDF, BOX_URDF
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "rsb.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rsb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = capi.lib()
+    names = _declared_symbols()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/rsb.h but not exported by librsb.so"
+    assert sorted(capi.EXPORTED) == names
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(capi.Contact) == 48       # 12 words, SURVEY 8d algorithmic-bytes formula
+    assert ctypes.sizeof(capi.Params) == 4 * 13
+
+
+@pytest.mark.parametrize("src", ["anymal_c_like.urdf", "atlas_like.urdf", PENDULUM_URDF, BOX_URDF])
+def test_model_tables_match_python_restatement(src):
+    path = os.path.join(RSC, src) if src.endswith(".urdf") else src
+    a = capi.Model(path).tables()
+    b = load_tables(path)
+    for k in ("nb", "nq", "nv", "floating", "ncoll", "npts"):
+        assert a[k] == b[k], k
+    for k in ("parent", "jtype", "qidx", "vidx", "depth", "cbody", "ctype", "pt_body", "pt_coll", "pt_feat"):
+        assert (a[k] == b[k]).all(), k
+    for k in ("jpos", "jrot", "axis", "mass", "com", "inertia", "jlimit", "csize", "cpos", "crot", "pt_pos", "pt_rad"):
+        assert np.allclose(a[k], b[k], rtol=1e-13, atol=1e-15), k
+    assert a["body_names"] == b["body_names"] and a["joint_names"] == b["joint_names"]
+
+
+def test_model_errors_are_reported_not_thrown():
+    with pytest.raises(capi.RsbError, match="cannot open"):
+        capi.Model("/nonexistent/robot.urdf")
+    with pytest.raises(capi.RsbError, match="mismatched"):
+        capi.Model("<robot><link name='a'></robot>")
+    with pytest.raises(capi.RsbError, match="unsupported joint type"):
+        capi.Model("<robot><link name='a'/><link name='b'><inertial><mass value='1'/><inertia ixx='1' iyy='1' izz='1'/></inertial></link>"
+                   "<joint name='j' type='planar'><parent link='a'/><child link='b'/></joint></robot>")
+
+
+def test_body_index_resolves_merged_links():
+    m = capi.Model(os.path.join(RSC, "anymal_c_like.urdf"))
+    assert m.body_index("base") == 0
+    assert m.body_index("LF_SHANK") == 3
+    assert m.body_index("LF_FOOT") == 3            # merged through the fixed joint
+    with pytest.raises(capi.RsbError):
+        m.body_index("nope")
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = capi.Model(os.path.join(RSC, "anymal_c_like.urdf"))
+    with pytest.raises(capi.RsbError, match="no CPU fallback"):
+        capi.Batch(m, 4)
