@@ -344,6 +344,7 @@ template <typename T> class Sim {
     all.clear();
     for (int k = 0; k < npts; k++) {
       int b = pt_body[k];
+      if (b == 0 && !floating) continue;               // a body welded to the world cannot collide
       V3<T> P = ws.p[b] + ws.R[b] * pt_pos[k];
       T dist; V3<T> n; int pair;
       if (!terrain_query(P, dist, n, pair)) continue;

@@ -65,17 +65,48 @@ static void build_blob(rsb_batch* b) {
   H.nptp = std::max(1, md.npts());
   H.nvp = round_up(std::max(md.nv, 1), 4);
   H.nqp = round_up(std::max(md.nq, 1), 4);
-  int off = 16;
+  // dof tree: a floating base is a chain of 6 dofs; dof order is DFS pre-order so subtrees are contiguous
+  const int nv = md.nv;
+  std::vector<int> dparent(std::max(1, nv), -1), ddepth(std::max(1, nv), 0), dsub(std::max(1, nv), 1), dbody(std::max(1, nv), 0), bdof(md.nb, -1);
+  H.nbase = md.floating ? 6 : 0;
+  for (int k = 1; k < H.nbase; k++) dparent[k] = k - 1;
+  if (md.floating) bdof[0] = 5;
+  for (int i = 1; i < md.nb; i++) {
+    bdof[i] = md.vidx[i]; dbody[md.vidx[i]] = i;
+    dparent[md.vidx[i]] = bdof[md.parent[i]];
+  }
+  H.maxdd = 0;
+  for (int i = 0; i < nv; i++) { ddepth[i] = dparent[i] >= 0 ? ddepth[dparent[i]] + 1 : 0; H.maxdd = std::max(H.maxdd, ddepth[i]); }
+  for (int i = nv - 1; i > 0; i--) if (dparent[i] >= 0) dsub[dparent[i]] += dsub[i];
+  const int DL = H.maxdd + 1;
+  H.dlp = DL | 1;
+  std::vector<int> lvl(DL + 1, 0), lvldofs, entstart(DL + 1, 0), ent;
+  for (int d = 0; d < DL; d++) {
+    lvl[d] = (int)lvldofs.size(); entstart[d] = (int)ent.size();
+    for (int i = 0; i < nv; i++) if (ddepth[i] == d) { lvldofs.push_back(i); for (int t = 0; t <= d; t++) ent.push_back(i | (t << 8)); }
+  }
+  lvl[DL] = (int)lvldofs.size(); entstart[DL] = (int)ent.size();
+  H.nent = (int)ent.size();
+  int off = HEADER_WORDS;
   H.off_body = off; off += BF_COUNT * H.nbp;
   H.off_anc = off; off += std::max(1, md.maxdepth) * H.nbp;
   H.off_pts = off; off += 5 * H.nptp;
   H.off_gain = off; off += 2 * H.nvp;
   H.off_dofq = off; off += H.nvp;
   H.off_sec = off; off += 2 * NROUNDS * SEC_STRIDE;
+  H.off_ddepth = off; off += H.nvp;
+  H.off_dsub = off; off += H.nvp;
+  H.off_danc = off; off += DL * H.nvp;
+  H.off_dbody = off; off += H.nvp;
+  H.off_bdof = off; off += H.nbp;
+  H.off_lvl = off; off += DL + 1;
+  H.off_lvldofs = off; off += H.nvp;
+  H.off_entstart = off; off += DL + 1;
+  H.off_ent = off; off += std::max(1, H.nent);
+  H.off_lcad = off; off += (md.nb * H.nbp + 3) / 4;
   int words = round_up(off, 4);
   std::vector<uint32_t>& B = b->blob_host;
   B.assign(words, 0u);
-  std::memcpy(B.data(), &H, sizeof(H));
   auto F = [&](int o, float v) { std::memcpy(&B[o], &v, 4); };
   auto I = [&](int o, int v) { std::memcpy(&B[o], &v, 4); };
   const int nbp = H.nbp;
@@ -103,6 +134,23 @@ static void build_blob(rsb_batch* b) {
     I(H.off_dofq + i, -1);
   }
   for (int i = 1; i < md.nb; i++) I(H.off_dofq + md.vidx[i], md.qidx[i]);
+  for (int i = 0; i < nv; i++) {
+    I(H.off_ddepth + i, ddepth[i]); I(H.off_dsub + i, dsub[i]); I(H.off_dbody + i, dbody[i]);
+    int a = i;
+    for (int t = ddepth[i]; t >= 0; t--) { I(H.off_danc + t * H.nvp + i, a); a = dparent[a]; }
+  }
+  for (int i = 0; i < md.nb; i++) I(H.off_bdof + i, bdof[i]);
+  for (int d = 0; d <= DL; d++) { I(H.off_lvl + d, lvl[d]); I(H.off_entstart + d, entstart[d]); }
+  for (size_t k = 0; k < lvldofs.size(); k++) I(H.off_lvldofs + (int)k, lvldofs[k]);
+  for (size_t k = 0; k < ent.size(); k++) I(H.off_ent + (int)k, ent[k]);
+  {   // depth (in the dof tree) of the lowest common ancestor dof of two bodies; -1 when they share none
+    int8_t* tab = reinterpret_cast<int8_t*>(&B[H.off_lcad]);
+    for (int a = 0; a < md.nb; a++) for (int c = 0; c < md.nb; c++) {
+      int x = a, y = c;
+      while (x != y) { if (md.depth[x] >= md.depth[y]) x = md.parent[x]; else y = md.parent[y]; }
+      tab[a * H.nbp + c] = (int8_t)(bdof[x] >= 0 ? ddepth[bdof[x]] : -1);
+    }
+  }
   for (int r = 0; r < NROUNDS; r++) {
     double width = 2.0 * M_PI / std::pow((double)NSEC, r);
     for (int k = 0; k <= NSEC; k++) {
@@ -110,23 +158,24 @@ static void build_blob(rsb_batch* b) {
       F(H.off_sec + NROUNDS * SEC_STRIDE + r * SEC_STRIDE + k, (float)std::sin(width * k / NSEC));
     }
   }
+  std::memcpy(B.data(), &H, sizeof(H));
 }
 
 static void build_ws_layout(rsb_batch* b) {
   const BlobHeader& H = b->hdr;
   WsLayout& L = b->ws;
   int o = 0;
-  L.mp = H.nv | 1;
   L.o_gc = o; o += H.nqp;
   L.o_gv = o; o += H.nvp;
   L.o_tau = o; o += H.nvp;
   L.o_pt = o; o += H.nqp;
   L.o_vt = o; o += H.nvp;
-  L.o_L = o; o += round_up(std::max(1, H.nv) * L.mp, 4);
+  L.o_L = o; o += round_up(std::max(1, H.nv) * H.dlp, 4);           // compact rows: [dof][ancestor depth]
   L.o_invd = o; o += H.nvp;
   L.o_rhs = o; o += H.nvp;
+  L.o_z = o; o += H.nvp;
   L.o_ct = o; o += KMAX * CT_WORDS;
-  L.o_Y = o; o += round_up(std::max(1, H.nv) * CP, 4);
+  L.o_Y = o; o += round_up((H.maxdd + 1) * CP, 4);                   // [ancestor depth][contact row]
   L.o_lam = o; o += 32;
   L.o_u = o; o += 12 * KMAX;
   // union: {h, b, poses} (stages A-C) overlaid by G (stages C-D)

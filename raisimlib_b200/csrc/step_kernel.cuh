@@ -11,9 +11,16 @@
 //                      per-body force / composite-inertia terms, subtree sums by warp shuffles
 //                      -> h, M (CRBA in a world-aligned frame centred on the base)
 //   B  lane = point  : candidate point vs Ground / HeightMap, ballot-compacted contact list
-//   C  lane = column : b, Mhat = M + dt Kd + dt^2 Kp, Cholesky, Y = L^-1 J^T, G = Y^T Y
+//   C  lane = entry / column : b, Mhat = M + dt Kd + dt^2 Kp, branch-sparse Mhat = L^T L (Featherstone RBDA
+//                      6.5) in compact-by-depth storage, z = L^-T b, Y = L^-T J^T (only the contact's own
+//                      ancestor chain is touched), G = Y^T Y (sum up to the LCA depth)
 //   D  lane = row    : per-contact Gauss-Seidel; slip by a 32-way section search (all lanes probe)
-//   E  lane = dof    : v+ = v + L^-T (dt z + Y lam), q+ = q (+) dt v+
+//   E  lane = dof    : v+ = v + L^-1 (dt z + Y lam), q+ = q (+) dt v+
+//
+// Compact-by-depth storage: the ancestors of a dof have distinct depths 0..d, so row i of the lower
+// triangle of M (non-zero only at ancestors) is stored as Lc[i][t], t = depth of the ancestor.  For
+// k in subtree(i), "the ancestor of k at depth(i)" IS i, which turns every tree-sparse update into
+// plain strided loops over the contiguous DFS range of descendants.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -43,15 +50,19 @@ enum CtField { CF_POS = 0, CF_N = 3, CF_T1 = 6, CF_T2 = 9, CF_DEPTH = 12, CF_PT 
 struct BlobHeader {
   int nb, nq, nv, npts, floating, maxdepth, nbp, nptp, nvp, nqp;
   int off_body, off_anc, off_pts, off_gain, off_dofq, off_sec;
+  // dof tree (floating base = chain of 6 dofs) for the branch-sparse factorisation
+  int nbase, maxdd, dlp, nent;
+  int off_ddepth, off_dsub, off_danc, off_dbody, off_bdof, off_lvl, off_lvldofs, off_entstart, off_ent, off_lcad;
+  int pad[2];
 };
-static_assert(sizeof(BlobHeader) == 64, "header is 16 words");
+static_assert(sizeof(BlobHeader) == 128, "header is 32 words");
+constexpr int HEADER_WORDS = 32;
 
 // per-warp workspace layout (word offsets), computed on the host
 struct WsLayout {
-  int o_gc, o_gv, o_tau, o_pt, o_vt, o_L, o_invd, o_rhs, o_ct, o_Y, o_lam, o_u;   // persistent
-  int o_h, o_b, o_pose;                                                             // union A
-  int o_G;                                                                          // union B
-  int mp;                                                                           // L row stride
+  int o_gc, o_gv, o_tau, o_pt, o_vt, o_L, o_invd, o_rhs, o_z, o_ct, o_Y, o_lam, o_u;   // persistent
+  int o_h, o_b, o_pose;                                                                  // union A
+  int o_G;                                                                               // union B
   int words;
 };
 
@@ -273,14 +284,24 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
   const int* dofq = reinterpret_cast<const int*>(smem + H.off_dofq);
   const float* sec_c = reinterpret_cast<const float*>(smem + H.off_sec);
   const float* sec_s = sec_c + NROUNDS * SEC_STRIDE;
+  const int nbase = H.nbase, maxdd = H.maxdd, DLP = H.dlp;
+  const int* ddepth = reinterpret_cast<const int*>(smem + H.off_ddepth);
+  const int* dsub = reinterpret_cast<const int*>(smem + H.off_dsub);
+  const int* danc = reinterpret_cast<const int*>(smem + H.off_danc);
+  const int* dbody = reinterpret_cast<const int*>(smem + H.off_dbody);
+  const int* bdof = reinterpret_cast<const int*>(smem + H.off_bdof);
+  const int* lvl = reinterpret_cast<const int*>(smem + H.off_lvl);
+  const int* lvldofs = reinterpret_cast<const int*>(smem + H.off_lvldofs);
+  const int* entstart = reinterpret_cast<const int*>(smem + H.off_entstart);
+  const int* ent = reinterpret_cast<const int*>(smem + H.off_ent);
+  const int8_t* lcad = reinterpret_cast<const int8_t*>(smem + H.off_lcad);
 
   const WsLayout& L = args.ws;
   float* ws = reinterpret_cast<float*>(smem + ((args.blob_words + 31) & ~31) + warp * L.words);
   float* s_gc = ws + L.o_gc; float* s_gv = ws + L.o_gv; float* s_tau = ws + L.o_tau; float* s_pt = ws + L.o_pt; float* s_vt = ws + L.o_vt;
-  float* s_L = ws + L.o_L; float* s_invd = ws + L.o_invd; float* s_rhs = ws + L.o_rhs; float* s_ct = ws + L.o_ct;
+  float* s_L = ws + L.o_L; float* s_invd = ws + L.o_invd; float* s_rhs = ws + L.o_rhs; float* s_z = ws + L.o_z; float* s_ct = ws + L.o_ct;
   float* s_Y = ws + L.o_Y; float* s_lam = ws + L.o_lam; float* s_u = ws + L.o_u;
   float* s_h = ws + L.o_h; float* s_b = ws + L.o_b; float* s_pose = ws + L.o_pose; float* s_G = ws + L.o_G;
-  const int MP = L.mp;
   const float dt = args.prm.dt;
   const float mu = args.prm.mu;
   const f3 grav = mk(args.prm.gravity[0], args.prm.gravity[1], args.prm.gravity[2]);
@@ -291,6 +312,8 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
   const int bb = bvalid ? b : 0;
   const int my_parent = bodyi[BF_PARENT * nbp + bb], my_jtype = bodyi[BF_JTYPE * nbp + bb];
   const int my_vidx = bodyi[BF_VIDX * nbp + bb], my_depth = bodyi[BF_DEPTH * nbp + bb], my_sub = bodyi[BF_SUBTREE * nbp + bb];
+  int er = 0, ec = 0;   // (row, col) of the base 6x6 lower triangle owned by lanes 0..20
+  for (int r = 0, e = 0; r < 6; r++) for (int c = 0; c <= r; c++, e++) if (e == lane) { er = r; ec = c; }
   int max_inner = 0;   // largest non-root subtree size - 1 (loop bound of the subtree accumulation)
   {
     int v = (bvalid && b > 0) ? my_sub - 1 : 0;
@@ -300,22 +323,29 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
   }
 
   const int warps_total = gridDim.x * WPC;
+#pragma unroll 1
   for (int env = blockIdx.x * WPC + warp; env < args.num_envs; env += warps_total) {
     // ---- load this environment's rows (coalesced: one row per warp) -----------------------------
     {
       const float* g_gc = args.gc + (size_t)env * args.gc_stride;
       const float* g_gv = args.gv + (size_t)env * args.gv_stride;
+#pragma unroll 1
       for (int i = lane; i < nq; i += 32) s_gc[i] = g_gc[i];
+#pragma unroll 1
       for (int i = lane; i < nv; i += 32) s_gv[i] = g_gv[i];
+#pragma unroll 1
       for (int i = lane; i < nv; i += 32) s_tau[i] = args.tau ? args.tau[(size_t)env * args.gv_stride + i] : 0.f;
       if (args.use_pd) {
+#pragma unroll 1
         for (int i = lane; i < nq; i += 32) s_pt[i] = args.ptarget[(size_t)env * args.gc_stride + i];
+#pragma unroll 1
         for (int i = lane; i < nv; i += 32) s_vt[i] = args.vtarget[(size_t)env * args.gv_stride + i];
       }
     }
     __syncwarp();
     int K = 0, iters = 0;
 
+#pragma unroll 1
     for (int sub = 0; sub < args.substeps; sub++) {
       // =========================== stage A: FK + RNEA + CRBA =====================================
       float R[9]; f3 p, w, v, wd, vd, ax;
@@ -439,9 +469,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
           for (int k = 0; k < 16; k++) A[k] = T[k];
         }
       }
-      // bias force h and CRBA columns
-      for (int i = lane; i < nv * MP; i += 32) s_L[i] = 0.f;
-      __syncwarp();
+      // bias force h and CRBA columns (row i of M stored compactly: column index = ancestor depth)
       f3 rO = p - O;
       const bool rev = my_jtype == 1;
       f3 Sw = rev ? ax : mk(0.f, 0.f, 0.f);
@@ -450,42 +478,50 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
       f3 hh = mk(A[7], A[8], A[9]);
       f3 ff = A[6] * Sv + cross(Sw, hh);
       f3 nn = mk(A[10] * Sw.x + A[11] * Sw.y + A[12] * Sw.z, A[11] * Sw.x + A[13] * Sw.y + A[14] * Sw.z, A[12] * Sw.x + A[14] * Sw.y + A[15] * Sw.z) + cross(hh, Sv);
+      const int my_dd = nbase + my_depth - 1;          // depth of this body's dof in the dof tree
       if (bvalid && b > 0) {
+        float* row = s_L + my_vidx * DLP;
         s_h[my_vidx] = dot(Sw, Nc) + dot(Sv, Fc);      // S^T [N_O; F]  (moment about O)
-        s_L[my_vidx * MP + my_vidx] = dot(Sw, nn) + dot(Sv, ff);
-        if (floating) {
-          s_L[my_vidx * MP + 0] = ff.x; s_L[my_vidx * MP + 1] = ff.y; s_L[my_vidx * MP + 2] = ff.z;
-          s_L[my_vidx * MP + 3] = nn.x; s_L[my_vidx * MP + 4] = nn.y; s_L[my_vidx * MP + 5] = nn.z;
-        }
+        row[my_dd] = dot(Sw, nn) + dot(Sv, ff);
+        if (floating) { row[0] = ff.x; row[1] = ff.y; row[2] = ff.z; row[3] = nn.x; row[4] = nn.y; row[5] = nn.z; }
       }
       if (b == 0 && floating) {
         s_h[0] = Fc.x; s_h[1] = Fc.y; s_h[2] = Fc.z; s_h[3] = Nc.x; s_h[4] = Nc.y; s_h[5] = Nc.z;
         // lower triangle of [ m 1, -[h]x ; [h]x, I_O ]
-        s_L[0 * MP + 0] = A[6]; s_L[1 * MP + 1] = A[6]; s_L[2 * MP + 2] = A[6];
-        s_L[3 * MP + 1] = -hh.z; s_L[3 * MP + 2] = hh.y;
-        s_L[4 * MP + 0] = hh.z; s_L[4 * MP + 2] = -hh.x;
-        s_L[5 * MP + 0] = -hh.y; s_L[5 * MP + 1] = hh.x;
-        s_L[3 * MP + 3] = A[10]; s_L[4 * MP + 3] = A[11]; s_L[5 * MP + 3] = A[12];
-        s_L[4 * MP + 4] = A[13]; s_L[5 * MP + 4] = A[14]; s_L[5 * MP + 5] = A[15];
+        s_L[0 * DLP + 0] = A[6]; s_L[1 * DLP + 0] = 0.f; s_L[1 * DLP + 1] = A[6];
+        s_L[2 * DLP + 0] = 0.f; s_L[2 * DLP + 1] = 0.f; s_L[2 * DLP + 2] = A[6];
+        s_L[3 * DLP + 0] = 0.f; s_L[3 * DLP + 1] = -hh.z; s_L[3 * DLP + 2] = hh.y;
+        s_L[4 * DLP + 0] = hh.z; s_L[4 * DLP + 1] = 0.f; s_L[4 * DLP + 2] = -hh.x;
+        s_L[5 * DLP + 0] = -hh.y; s_L[5 * DLP + 1] = hh.x; s_L[5 * DLP + 2] = 0.f;
+        s_L[3 * DLP + 3] = A[10]; s_L[4 * DLP + 3] = A[11]; s_L[5 * DLP + 3] = A[12];
+        s_L[4 * DLP + 4] = A[13]; s_L[5 * DLP + 4] = A[14]; s_L[5 * DLP + 5] = A[15];
       }
-      {   // M[vi][vj] for proper ancestors j (excluding the root)
+      {   // M[vi][vj] for proper ancestors j (excluding the root): column = depth of j's dof
         int j = (bvalid && b > 0) ? my_parent : 0;
+        int tj = my_dd - 1;
 #pragma unroll 1
         for (int d = 2; d <= maxdepth; d++) {
           int src = j > 0 ? j : 0;
           f3 Swj = shfl3(Sw, src), Svj = shfl3(Sv, src);
-          int vj = __shfl_sync(FULL, my_vidx, src);
           if (j > 0) {
-            s_L[my_vidx * MP + vj] = dot(Swj, nn) + dot(Svj, ff);
+            s_L[my_vidx * DLP + tj] = dot(Swj, nn) + dot(Svj, ff);
             j = bodyi[BF_PARENT * nbp + j];
+            tj--;
           }
         }
       }
       __syncwarp();
       if (args.dbg_M) {   // getters: full symmetric M, h, poses
         float* gM = args.dbg_M + (size_t)env * nv * nv;
-        for (int i = lane; i < nv * nv; i += 32) { int r = i / nv, c = i % nv; gM[i] = r >= c ? s_L[r * MP + c] : s_L[c * MP + r]; }
+#pragma unroll 1
+        for (int i = lane; i < nv * nv; i += 32) {
+          int r = i / nv, c = i % nv;
+          if (r < c) { int t = r; r = c; c = t; }
+          int dc = ddepth[c];
+          gM[i] = (dc <= ddepth[r] && danc[dc * nvp + r] == c) ? s_L[r * DLP + dc] : 0.f;
+        }
         float* gh = args.dbg_h + (size_t)env * nv;
+#pragma unroll 1
         for (int i = lane; i < nv; i += 32) gh[i] = s_h[i];
         if (bvalid) {
           float* gR = args.dbg_R + ((size_t)env * nb + b) * 9;
@@ -512,7 +548,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
           for (int q = 0; q < 9; q++) Rb[q] = s_pose[(PF_R + q) * nbp + pb];
           f3 P = mk(s_pose[(PF_P + 0) * nbp + pb], s_pose[(PF_P + 1) * nbp + pb], s_pose[(PF_P + 2) * nbp + pb]) + mulR(Rb, pl);
           float dist; f3 n; int pair;
-          if (terrain_query(args.ter, P, dist, n, pair)) {
+          if (bdof[pb] >= 0 && terrain_query(args.ter, P, dist, n, pair)) {   // bodies welded to the world cannot collide
             float depth = rad - dist;
             if (depth > 0.f) { c_hit[s] = true; c_depth[s] = depth; c_pair[s] = pair; c_body[s] = pb; c_n[s] = n; c_pos[s] = P - rad * n; }
           }
@@ -522,6 +558,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
       int total = 0;
 #pragma unroll
       for (int s = 0; s < MAX_PT_SLOTS; s++) { hm[s] = __ballot_sync(FULL, c_hit[s]); total += __popc(hm[s]); }
+#pragma unroll 1
       while (total > KMAX) {   // drop the shallowest (ties: highest candidate index) until KMAX remain
         float dmin = 3.0e38f; int imin = -1;
 #pragma unroll
@@ -564,7 +601,8 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
       const int C = 3 * K;
       if (args.phase_mask & 1) { __syncwarp(); break; }   // integrate1(): kinematics, collision, M, h only
 
-      // =========================== stage C: b, Mhat, Cholesky, Y, G ==============================
+      // =========================== stage C: b, Mhat = L^T L, z, Y, G ==============================
+#pragma unroll 1
       for (int i = lane; i < nv; i += 32) {
         float bi = s_tau[i] - s_h[i];
         if (args.use_pd) {
@@ -572,96 +610,159 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
           if (kpi != 0.f || kdi != 0.f) {
             int qi = dofq[i];
             bi += kpi * (s_pt[qi] - s_gc[qi] - dt * s_gv[i]) + kdi * (s_vt[i] - s_gv[i]);
-            s_L[i * MP + i] += dt * kdi + dt * dt * kpi;
+            s_L[i * DLP + ddepth[i]] += dt * kdi + dt * dt * kpi;
           }
         }
         s_b[i] = bi;
       }
       __syncwarp();
-      // Cholesky, right-looking, lane = row
+      // ---- branch-sparse factorisation Mhat = L^T L, "pull" form, one dof-tree level at a time (deepest first):
+      //      L[i][t] = (M[i][t] - sum_{k in subtree(i), k != i} L[k][depth i] L[k][t]) / L[i][i]
 #pragma unroll 1
-      for (int j = 0; j < nv; j++) {
-        float djj = sqrtf(s_L[j * MP + j]);
-        float inv = 1.0f / djj;
-        __syncwarp();
-        for (int i = j + lane; i < nv; i += 32) {
-          float lij = (i == j) ? djj : s_L[i * MP + j] * inv;
-          s_L[i * MP + j] = lij;
+      for (int lev = maxdd; lev >= nbase; lev--) {
+        const int e0 = entstart[lev], ne = entstart[lev + 1] - e0;
+#pragma unroll 1
+        for (int e = lane; e < ne; e += 32) {
+          const int pk = ent[e0 + e], i = pk & 255, t = pk >> 8;
+          float acc = s_L[i * DLP + t];
+          const int kend = i + dsub[i];
+#pragma unroll 1
+          for (int k = i + 1; k < kend; k++) acc -= s_L[k * DLP + lev] * s_L[k * DLP + t];
+          s_L[i * DLP + t] = acc;
         }
-        if (lane == 0) s_invd[j] = inv;
         __syncwarp();
-        for (int i = j + 1 + lane; i < nv; i += 32) {
-          float lij = s_L[i * MP + j];
-          for (int k = j + 1; k <= i; k++) s_L[i * MP + k] -= lij * s_L[k * MP + j];
+        const int d0 = lvl[lev], nd = lvl[lev + 1] - d0;
+        if (lane < nd) {
+          const int i = lvldofs[d0 + lane];
+          float d = sqrtf(s_L[i * DLP + lev]);
+          s_L[i * DLP + lev] = d;
+          s_invd[i] = 1.0f / d;
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int e = lane; e < ne; e += 32) {
+          const int pk = ent[e0 + e], i = pk & 255, t = pk >> 8;
+          if (t < lev) s_L[i * DLP + t] *= s_invd[i];
         }
         __syncwarp();
       }
-      // J^T columns (contact frame rows) into Y, plus column C = b ; u0 = J v
+      if (floating) {   // base 6x6 block: every other dof is a descendant of every base dof
+        float val = 0.f;
+        if (lane < 21) {
+          val = s_L[er * DLP + ec];
+#pragma unroll 1
+          for (int k = 6; k < nv; k++) val -= s_L[k * DLP + er] * s_L[k * DLP + ec];
+        }
+#pragma unroll 1
+        for (int i = 5; i >= 0; i--) {
+          const int ti = i * (i + 1) / 2;
+          float d = sqrtf(__shfl_sync(FULL, val, ti + i));
+          float inv = 1.0f / d;
+          if (er == i) val = (ec == i) ? d : val * inv;
+          float lir = __shfl_sync(FULL, val, ti + min(er, i));
+          float lic = __shfl_sync(FULL, val, ti + min(ec, i));
+          if (lane < 21 && er < i) val -= lir * lic;
+          if (lane == 0) s_invd[i] = inv;
+        }
+        if (lane < 21) s_L[er * DLP + ec] = val;
+        __syncwarp();
+      }
+      // ---- z = L^-T b  (leaves to root)
+#pragma unroll 1
+      for (int lev = maxdd; lev >= nbase; lev--) {
+        const int d0 = lvl[lev], nd = lvl[lev + 1] - d0;
+        if (lane < nd) {
+          const int i = lvldofs[d0 + lane];
+          float acc = s_b[i];
+          const int kend = i + dsub[i];
+#pragma unroll 1
+          for (int k = i + 1; k < kend; k++) acc -= s_L[k * DLP + lev] * s_z[k];
+          s_z[i] = acc * s_invd[i];
+        }
+        __syncwarp();
+      }
+      if (floating) {
+        float acc = 0.f;
+        if (lane < 6) {
+          acc = s_b[lane];
+#pragma unroll 1
+          for (int k = 6; k < nv; k++) acc -= s_L[k * DLP + lane] * s_z[k];
+        }
+#pragma unroll 1
+        for (int i = 5; i >= 0; i--) {
+          float zi = __shfl_sync(FULL, acc, i) * s_invd[i];
+          if (lane < i) acc -= s_L[i * DLP + lane] * zi;
+          if (lane == i) s_z[i] = zi;
+        }
+        __syncwarp();
+      }
+      // ---- Y = L^-T J^T, one contact row per lane, only along the contact body's own ancestor chain
       float u_c = 0.f;
-      if (lane <= C) {
-        const int c = lane;
-        for (int r = 0; r < nv; r++) s_Y[r * CP + c] = (c == C) ? s_b[r] : 0.f;
-        if (c < C) {
-          const float* ct = s_ct + (c / 3) * CT_WORDS;
-          const int d = c % 3;
-          const int fo = (d == 0) ? CF_T1 : (d == 1 ? CF_T2 : CF_N);
-          f3 axd = mk(ct[fo], ct[fo + 1], ct[fo + 2]);
-          f3 pos = mk(ct[CF_POS], ct[CF_POS + 1], ct[CF_POS + 2]);
-          if (floating) {
-            f3 rc = cross(pos - O, axd);
-            s_Y[0 * CP + c] = axd.x; s_Y[1 * CP + c] = axd.y; s_Y[2 * CP + c] = axd.z;
-            s_Y[3 * CP + c] = rc.x; s_Y[4 * CP + c] = rc.y; s_Y[5 * CP + c] = rc.z;
-            u_c = axd.x * s_gv[0] + axd.y * s_gv[1] + axd.z * s_gv[2] + rc.x * s_gv[3] + rc.y * s_gv[4] + rc.z * s_gv[5];
-          }
-          int j = __float_as_int(ct[CF_BODY]);
-          while (bodyi[BF_PARENT * nbp + j] >= 0) {
-            f3 aj = mk(s_pose[(PF_A + 0) * nbp + j], s_pose[(PF_A + 1) * nbp + j], s_pose[(PF_A + 2) * nbp + j]);
-            f3 col;
-            if (bodyi[BF_JTYPE * nbp + j] == 1) {
-              f3 pj = mk(s_pose[(PF_P + 0) * nbp + j], s_pose[(PF_P + 1) * nbp + j], s_pose[(PF_P + 2) * nbp + j]);
-              col = cross(aj, pos - pj);
-            } else col = aj;
-            int vj = bodyi[BF_VIDX * nbp + j];
-            float val = dot(col, axd);
-            s_Y[vj * CP + c] = val;
-            u_c += val * s_gv[vj];
-            j = bodyi[BF_PARENT * nbp + j];
-          }
-        }
-        // forward substitution down this lane's column
-        for (int r = 0; r < nv; r++) {
-          float s = s_Y[r * CP + c];
-          for (int k = 0; k < r; k++) s -= s_L[r * MP + k] * s_Y[k * CP + c];
-          s_Y[r * CP + c] = s * s_invd[r];
-        }
-      }
-      __syncwarp();
       if (lane < C) {
-        float s = 0.f;
-        for (int r = 0; r < nv; r++) s += s_Y[r * CP + lane] * s_Y[r * CP + C];
-        float jv = u_c;
-        u_c = jv + dt * s;
-        if (lane % 3 == 2) {
-          float target = args.prm.erp * s_ct[(lane / 3) * CT_WORDS + CF_DEPTH] / dt;
+        const int c = lane;
+        const float* ct = s_ct + (c / 3) * CT_WORDS;
+        const int d = c % 3;
+        const int fo = (d == 0) ? CF_T1 : (d == 1 ? CF_T2 : CF_N);
+        const f3 axd = mk(ct[fo], ct[fo + 1], ct[fo + 2]);
+        const f3 pos = mk(ct[CF_POS], ct[CF_POS + 1], ct[CF_POS + 2]);
+        const int i0 = bdof[__float_as_int(ct[CF_BODY])];
+        const int m = i0 >= 0 ? ddepth[i0] : -1;
+        float jv = 0.f;
+        if (floating) {
+          f3 rc = cross(pos - O, axd);
+          s_Y[0 * CP + c] = axd.x; s_Y[1 * CP + c] = axd.y; s_Y[2 * CP + c] = axd.z;
+          s_Y[3 * CP + c] = rc.x; s_Y[4 * CP + c] = rc.y; s_Y[5 * CP + c] = rc.z;
+          jv = axd.x * s_gv[0] + axd.y * s_gv[1] + axd.z * s_gv[2] + rc.x * s_gv[3] + rc.y * s_gv[4] + rc.z * s_gv[5];
+        }
+#pragma unroll 1
+        for (int t = nbase; t <= m; t++) {
+          const int a_t = danc[t * nvp + i0], j = dbody[a_t];
+          f3 aj = mk(s_pose[(PF_A + 0) * nbp + j], s_pose[(PF_A + 1) * nbp + j], s_pose[(PF_A + 2) * nbp + j]);
+          f3 col = aj;
+          if (bodyi[BF_JTYPE * nbp + j] == 1) {
+            f3 pj = mk(s_pose[(PF_P + 0) * nbp + j], s_pose[(PF_P + 1) * nbp + j], s_pose[(PF_P + 2) * nbp + j]);
+            col = cross(aj, pos - pj);
+          }
+          float val = dot(col, axd);
+          s_Y[t * CP + c] = val;
+          jv += val * s_gv[a_t];
+        }
+        float yz = 0.f;
+#pragma unroll 1
+        for (int sI = m; sI >= 0; sI--) {
+          const int a_s = danc[sI * nvp + i0];
+          float y = s_Y[sI * CP + c] * s_invd[a_s];
+          s_Y[sI * CP + c] = y;
+          yz += y * s_z[a_s];
+#pragma unroll 1
+          for (int t = 0; t < sI; t++) s_Y[t * CP + c] -= s_L[a_s * DLP + t] * y;
+        }
+        u_c = jv + dt * yz;
+        if (d == 2) {
+          float target = args.prm.erp * ct[CF_DEPTH] / dt;
           if (args.prm.restitution > 0.f && jv < -args.prm.rest_threshold) target += -args.prm.restitution * jv;
           u_c -= target;
         }
       }
-      for (int i = lane; i < nv; i += 32) s_rhs[i] = dt * s_Y[i * CP + C];
       iters = 0;
       float lam_c = 0.f;
       if (K > 0) {
         __syncwarp();      // h / b / poses are dead from here: G overlays them
-        // G = Y^T Y, lanes = (row a, offset group)
+        // G = Y^T Y; rows a, b share ancestors exactly up to the depth of their bodies' LCA
         {
           const int ng = 32 / C;                    // C <= 24 -> ng >= 1
           const int a = lane % C, g = lane / C;
           if (g < ng) {
+            const int ba = __float_as_int(s_ct[(a / 3) * CT_WORDS + CF_BODY]);
+#pragma unroll 1
             for (int dd = g; dd <= C / 2; dd += ng) {
               int bcol = a + dd; if (bcol >= C) bcol -= C;
-              float s = 0.f;
-              for (int r = 0; r < nv; r++) s += s_Y[r * CP + a] * s_Y[r * CP + bcol];
-              s_G[a * GP + bcol] = s; s_G[bcol * GP + a] = s;
+              const int bbody = __float_as_int(s_ct[(bcol / 3) * CT_WORDS + CF_BODY]);
+              const int tmax = lcad[ba * nbp + bbody];
+              float sacc = 0.f;
+#pragma unroll 1
+              for (int t = 0; t <= tmax; t++) sacc += s_Y[t * CP + a] * s_Y[t * CP + bcol];
+              s_G[a * GP + bcol] = sacc; s_G[bcol * GP + a] = sacc;
             }
           }
         }
@@ -705,22 +806,45 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
         }
         if (lane < C) s_lam[lane] = lam_c;
         __syncwarp();
-        for (int r = lane; r < nv; r += 32) {
-          float s = s_rhs[r];
-          for (int c = 0; c < C; c++) s += s_Y[r * CP + c] * s_lam[c];
-          s_rhs[r] = s;
-        }
       }
       __syncwarp();
-      // =========================== stage E: back-substitution and integration ====================
+      // =========================== stage E: v+ = v + L^-1 (dt z + Y lam), integration ============
 #pragma unroll 1
-      for (int i = nv - 1; i >= 0; i--) {
-        float xi = s_rhs[i] * s_invd[i];
-        __syncwarp();
-        if (lane == 0) s_rhs[i] = xi;
-        for (int k = lane; k < i; k += 32) s_rhs[k] -= s_L[i * MP + k] * xi;
+      for (int i = lane; i < nv; i += 32) {   // w = dt z + Y lam, gathered per dof over the contacts whose chain holds it
+        float sacc = dt * s_z[i];
+        const int di = ddepth[i];
+#pragma unroll 1
+        for (int k = 0; k < K; k++) {
+          const int i0 = bdof[__float_as_int(s_ct[k * CT_WORDS + CF_BODY])];
+          if (i0 >= 0 && ddepth[i0] >= di && danc[di * nvp + i0] == i)
+            sacc += s_Y[di * CP + 3 * k] * s_lam[3 * k] + s_Y[di * CP + 3 * k + 1] * s_lam[3 * k + 1] + s_Y[di * CP + 3 * k + 2] * s_lam[3 * k + 2];
+        }
+        s_rhs[i] = sacc;
+      }
+      __syncwarp();
+      if (floating) {   // x = L^-1 w, root to leaves: base chain by shuffles, then one tree level at a time
+        float acc = lane < 6 ? s_rhs[lane] : 0.f;
+#pragma unroll 1
+        for (int t = 0; t < 6; t++) {
+          float xt = __shfl_sync(FULL, acc, t) * s_invd[t];
+          if (lane > t && lane < 6) acc -= s_L[lane * DLP + t] * xt;
+          if (lane == t) s_rhs[t] = xt;
+        }
         __syncwarp();
       }
+#pragma unroll 1
+      for (int lev = nbase; lev <= maxdd; lev++) {
+        const int d0 = lvl[lev], nd = lvl[lev + 1] - d0;
+        if (lane < nd) {
+          const int i = lvldofs[d0 + lane];
+          float acc = s_rhs[i];
+#pragma unroll 1
+          for (int t = 0; t < lev; t++) acc -= s_L[i * DLP + t] * s_rhs[danc[t * nvp + i]];
+          s_rhs[i] = acc * s_invd[i];
+        }
+        __syncwarp();
+      }
+#pragma unroll 1
       for (int i = lane; i < nv; i += 32) s_gv[i] += s_rhs[i];
       __syncwarp();
       if (floating) {
@@ -739,6 +863,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) { s_gc[3] = nw * inv; s_gc[4] = nx * inv; s_gc[5] = ny * inv; s_gc[6] = nz * inv; }
       }
+#pragma unroll 1
       for (int i = lane; i < nv; i += 32) {
         int qi = dofq[i];
         if (qi >= (floating ? 7 : 0)) s_gc[qi] += dt * s_gv[i];
@@ -750,7 +875,9 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
     if (!(args.phase_mask & 1)) {
       float* g_gc = args.gc + (size_t)env * args.gc_stride;
       float* g_gv = args.gv + (size_t)env * args.gv_stride;
+#pragma unroll 1
       for (int i = lane; i < nq; i += 32) g_gc[i] = s_gc[i];
+#pragma unroll 1
       for (int i = lane; i < nv; i += 32) g_gv[i] = s_gv[i];
     }
     if (lane == 0) { args.ncontacts[env] = K; args.iters[env] = iters; }

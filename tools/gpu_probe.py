@@ -77,7 +77,7 @@ def stage_errors(urdf, n=256, seed=0, base_z=0.45, terrain="ground"):
         print(f"  {nsteps} steps: gc err gpu-vs-f64 median={np.median(e):.2e} p90={np.quantile(e, 0.9):.2e} max={e.max():.2e} | f32-vs-f64 median={np.median(e32):.2e} p90={np.quantile(e32, 0.9):.2e} max={e32.max():.2e}", flush=True)
 
 
-def timing(urdf, n=4096, terrain="ground", substeps=4, reps=50):
+def timing(urdf, n=4096, terrain="ground", substeps=4, reps=50, z0=None, kp_val=300.0, kd_val=8.0):
     import torch
     path = os.path.join(RSC_DIR, urdf)
     t = load_tables(path)
@@ -87,22 +87,23 @@ def timing(urdf, n=4096, terrain="ground", substeps=4, reps=50):
     if t["nq"] == 19:
         gc = np.tile(ANYMAL_GC0, (n, 1)); gc[:, 7:] += rng.uniform(-0.2, 0.2, (n, 12)); gc[:, 2] = rng.uniform(0.55, 0.65, n)
         gc[:, :2] = rng.uniform(-5, 5, (n, 2))
+        if z0 is not None: gc[:, 2] = z0
     else:
         gc = np.zeros((n, t["nq"])); gc[:, 2] = 0.95; gc[:, 3] = 1.0
     gv = 0.1 * rng.standard_normal((n, t["nv"]))
     if terrain == "ground":
         bt.set_ground(0.0)
-    else:
+    elif terrain == "hm":
         xs = ys = 129
         bt.set_heightmap(xs, ys, 12.8, 12.8, 0.0, 0.0, 0.05 * rng.uniform(-1, 1, (ys, xs)))
-    kp = np.r_[np.zeros(6), 50 * np.ones(t["nv"] - 6)]; kd = np.r_[np.zeros(6), 0.5 * np.ones(t["nv"] - 6)]
+    kp = np.r_[np.zeros(6), kp_val * np.ones(t["nv"] - 6)]; kd = np.r_[np.zeros(6), kd_val * np.ones(t["nv"] - 6)]
     bt.set_pd_gains(kp, kd)
     bt.set_state(gc.astype(np.float32), gv.astype(np.float32))
     bt.set_pd_target(gc.astype(np.float32), np.zeros((n, t["nv"]), np.float32))
     s = torch.cuda.Stream()
     bt.set_stream(s.cuda_stream)
     with torch.cuda.stream(s):
-        for _ in range(10): bt.integrate(substeps)
+        for _ in range(40): bt.integrate(substeps)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.synchronize()
         e0.record(s)
@@ -122,8 +123,14 @@ if __name__ == "__main__":
         stage_errors("anymal_c_like.urdf")
         stage_errors("anymal_c_like.urdf", terrain="hm", seed=3)
         stage_errors("atlas_like.urdf", base_z=0.9)
+    if which == "prof":     # one scenario for ncu: -k regex:rsb_step -s 42 -c 1
+        timing("anymal_c_like.urdf", reps=3)
     if which in ("all", "time"):
-        timing("anymal_c_like.urdf")
+        timing("anymal_c_like.urdf", terrain="none", z0=1000.0, reps=20)      # airborne: no contacts at all
+        timing("anymal_c_like.urdf", terrain="none", z0=1000.0, substeps=1, reps=20)
+        timing("anymal_c_like.urdf")                                            # standing on flat ground
         timing("anymal_c_like.urdf", substeps=1)
         timing("anymal_c_like.urdf", terrain="hm")
+        timing("anymal_c_like.urdf", kp_val=50.0, kd_val=0.5)                   # weak PD: robots kneel (knee + foot contacts)
+        timing("atlas_like.urdf", terrain="none", z0=1000.0, reps=10)
         timing("atlas_like.urdf")
