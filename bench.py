@@ -172,6 +172,7 @@ def main():
     import torch
     import torch.distributed as dist
     from raisimlib_b200 import capi, RSC_DIR
+    from raisimlib_b200.sharding import allgather_observations
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -210,7 +211,7 @@ def main():
         bt.integrate(SUBSTEPS)                               # ONE fused launch: 4 x World::integrate()
         bt.observe(obs)
         if world > 1:
-            dist.all_gather_into_tensor(obs_all, obs)        # the only collective of the path
+            allgather_observations(obs, obs_all)             # the only collective of the path
         if host_io:
             obs_host.copy_(obs_all, non_blocking=True)       # D2H of the step's result
             stream.synchronize()
@@ -236,7 +237,7 @@ def main():
             kev[k][1].record(stream)
             bt.observe(obs)
             if world > 1:
-                dist.all_gather_into_tensor(obs_all, obs)
+                allgather_observations(obs, obs_all)
             if host_io:
                 obs_host.copy_(obs_all, non_blocking=True)
             ev[k][1].record(stream)

@@ -1,0 +1,258 @@
+// raisim::World / raisim::ArticulatedSystem / raisim::Contact -- header-only facade over the C-ABI
+// (include/rsb.h).  Keeps the reference's API surface for the hot path so RaisimGym-style
+// ENVIRONMENT code compiles against it (SURVEY.md 8b lists the upstream signatures, [RECALL]:
+// include/raisim/World.hpp, object/ArticulatedSystem/ArticulatedSystem.hpp, contact/Contact.hpp;
+// none of them is in the reference snapshot).
+//
+// Design inversion: the batch lives UNDER World.  A raisim::BatchedWorld owns N environments of
+// SoA state on one GPU; raisim::World and raisim::ArticulatedSystem are thin per-environment VIEWS
+// {batch, env index}.  A World constructed standalone owns a batch of one (config 1 semantics).
+// VectorizedEnvironment.hpp issues ONE batched launch per control step instead of N OpenMP iterations.
+//
+// Errors: the reference aborts through RSFATAL; here every failing C-ABI call throws
+// std::runtime_error with rsb_last_error() (define RAISIM_B200_ABORT_ON_ERROR to abort instead).
+// Units and conventions are the reference's: gc = [xyz | qw qx qy qz | joints], gv = [v | w | joint rates].
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../rsb.h"
+#include "math.hpp"
+
+namespace raisim {
+
+using CollisionGroup = unsigned long;
+
+inline void rsbCheck(int rc, const char* what) {
+  if (rc >= 0) return;
+#ifdef RAISIM_B200_ABORT_ON_ERROR
+  std::fprintf(stderr, "[RSFATAL] %s: %s\n", what, rsb_last_error());
+  std::abort();
+#else
+  throw std::runtime_error(std::string(what) + ": " + rsb_last_error());
+#endif
+}
+
+namespace ControlMode {
+enum Type : int { FORCE_AND_TORQUE = RSB_FORCE_AND_TORQUE, PD_PLUS_FEEDFORWARD_TORQUE = RSB_PD_PLUS_FEEDFORWARD_TORQUE };
+}
+
+// contact::Contact read-back (ArticulatedSystem::getContacts())
+class Contact {
+ public:
+  explicit Contact(const rsb_contact& c) : c_(c) {}
+  size_t getlocalBodyIndex() const { return size_t(c_.local_body); }
+  size_t getPairObjectIndex() const { return 0; }            // the terrain is object 0 of the world
+  int getPairContactIndexInPairObject() const { return c_.pair_index; }
+  Vec<3> getPosition() const { return {c_.position[0], c_.position[1], c_.position[2]}; }
+  Vec<3> getNormal() const { return {c_.normal[0], c_.normal[1], c_.normal[2]}; }
+  Vec<3> getImpulse() const { return {c_.impulse[0], c_.impulse[1], c_.impulse[2]}; }   // world frame, on the robot
+  double getDepth() const { return c_.depth; }
+  bool isObjectA() const { return true; }
+  bool skip() const { return false; }
+ private:
+  rsb_contact c_;
+};
+
+// One GPU batch of N identical worlds (new; the reference has no equivalent -- its batching is the
+// OpenMP loop of VectorizedEnvironment).
+class BatchedWorld {
+ public:
+  BatchedWorld(const std::string& urdfPathOrXml, int numEnvs, int device = 0) {
+    rsbCheck(rsb_model_create_from_urdf(urdfPathOrXml.c_str(), &model_), "addArticulatedSystem");
+    rsbCheck(rsb_batch_create(model_, numEnvs, device, &batch_), "BatchedWorld");
+    rsbCheck(rsb_model_dims(model_, &nq_, &nv_, &nb_, nullptr, nullptr), "dims");
+    n_ = numEnvs;
+  }
+  ~BatchedWorld() { if (batch_) rsb_batch_destroy(batch_); if (model_) rsb_model_destroy(model_); }
+  BatchedWorld(const BatchedWorld&) = delete;
+  BatchedWorld& operator=(const BatchedWorld&) = delete;
+  rsb_batch* batch() const { return batch_; }
+  rsb_model* model() const { return model_; }
+  int numEnvs() const { return n_; }
+  int nq() const { return nq_; }
+  int nv() const { return nv_; }
+  int nb() const { return nb_; }
+  rsb_params params() const { rsb_params p; rsbCheck(rsb_batch_get_params(batch_, &p), "getParams"); return p; }
+  void setParams(const rsb_params& p) { rsbCheck(rsb_batch_set_params(batch_, &p), "setParams"); }
+  void integrate(int substeps = 1) { rsbCheck(rsb_batch_integrate(batch_, substeps), "integrate"); worldTime_ += substeps * params().dt; }
+  void integrate1() { rsbCheck(rsb_batch_integrate1(batch_), "integrate1"); }
+  void integrate2() { rsbCheck(rsb_batch_integrate2(batch_), "integrate2"); worldTime_ += params().dt; }
+  double worldTime() const { return worldTime_; }
+ private:
+  rsb_model* model_ = nullptr;
+  rsb_batch* batch_ = nullptr;
+  int n_ = 0, nq_ = 0, nv_ = 0, nb_ = 0;
+  double worldTime_ = 0;
+};
+
+class Ground {};
+class HeightMap {};
+
+// raisim::ArticulatedSystem -- a view of one environment's robot
+class ArticulatedSystem {
+ public:
+  ArticulatedSystem(BatchedWorld* w, int env) : w_(w), env_(env) {}
+  size_t getGeneralizedCoordinateDim() const { return size_t(w_->nq()); }
+  size_t getDOF() const { return size_t(w_->nv()); }
+  void setName(const std::string& n) { name_ = n; }
+  const std::string& getName() const { return name_; }
+
+  void getState(VecDyn& gc, VecDyn& gv) const {
+    std::vector<float> q(w_->nq()), v(w_->nv());
+    rsbCheck(rsb_batch_get_state(w_->batch(), q.data(), v.data(), env_, 1, RSB_HOST), "getState");
+    gc.resize(q.size()); gv.resize(v.size());
+    for (size_t i = 0; i < q.size(); i++) gc[i] = q[i];
+    for (size_t i = 0; i < v.size(); i++) gv[i] = v[i];
+  }
+  VecDyn getGeneralizedCoordinate() const { VecDyn q, v; getState(q, v); return q; }
+  VecDyn getGeneralizedVelocity() const { VecDyn q, v; getState(q, v); return v; }
+  template <class VQ, class VV> void setState(const VQ& gc, const VV& gv) {
+    std::vector<float> q(w_->nq()), v(w_->nv());
+    for (size_t i = 0; i < q.size(); i++) q[i] = float(gc[i]);
+    for (size_t i = 0; i < v.size(); i++) v[i] = float(gv[i]);
+    rsbCheck(rsb_batch_set_state(w_->batch(), q.data(), v.data(), env_, 1, RSB_HOST), "setState");
+  }
+  template <class VQ> void setGeneralizedCoordinate(const VQ& gc) {
+    std::vector<float> q(w_->nq());
+    for (size_t i = 0; i < q.size(); i++) q[i] = float(gc[i]);
+    rsbCheck(rsb_batch_set_state(w_->batch(), q.data(), nullptr, env_, 1, RSB_HOST), "setGeneralizedCoordinate");
+  }
+  template <class VV> void setGeneralizedVelocity(const VV& gv) {
+    std::vector<float> v(w_->nv());
+    for (size_t i = 0; i < v.size(); i++) v[i] = float(gv[i]);
+    rsbCheck(rsb_batch_set_state(w_->batch(), nullptr, v.data(), env_, 1, RSB_HOST), "setGeneralizedVelocity");
+  }
+  template <class VV> void setGeneralizedForce(const VV& tau) {
+    std::vector<float> t(w_->nv());
+    for (size_t i = 0; i < t.size(); i++) t[i] = float(tau[i]);
+    rsbCheck(rsb_batch_set_generalized_force(w_->batch(), t.data(), env_, 1, RSB_HOST), "setGeneralizedForce");
+  }
+  // gains are shared by every environment of the batch (they are per-robot-model constants in RaisimGym)
+  template <class VV> void setPdGains(const VV& p, const VV& d) {
+    std::vector<float> kp(w_->nv()), kd(w_->nv());
+    for (size_t i = 0; i < kp.size(); i++) { kp[i] = float(p[i]); kd[i] = float(d[i]); }
+    rsbCheck(rsb_batch_set_pd_gains(w_->batch(), kp.data(), kd.data()), "setPdGains");
+  }
+  template <class VQ, class VV> void setPdTarget(const VQ& posTarget, const VV& velTarget) {
+    std::vector<float> q(w_->nq()), v(w_->nv());
+    for (size_t i = 0; i < q.size(); i++) q[i] = float(posTarget[i]);
+    for (size_t i = 0; i < v.size(); i++) v[i] = float(velTarget[i]);
+    rsbCheck(rsb_batch_set_pd_target(w_->batch(), q.data(), v.data(), env_, 1, RSB_HOST), "setPdTarget");
+  }
+  void setControlMode(ControlMode::Type m) { rsbCheck(rsb_batch_set_control_mode(w_->batch(), int(m)), "setControlMode"); }
+
+  // lazy getters: valid after integrate1() (or integrate1()+integrate2())
+  MatDyn getMassMatrix() const {
+    const int nv = w_->nv();
+    std::vector<float> m(size_t(nv) * nv);
+    rsbCheck(rsb_batch_get_mass_matrix(w_->batch(), env_, 1, m.data(), RSB_HOST), "getMassMatrix");
+    MatDyn M; M.resize(nv, nv);
+    for (int i = 0; i < nv; i++) for (int j = 0; j < nv; j++) M(i, j) = m[size_t(i) * nv + j];
+    return M;
+  }
+  VecDyn getNonlinearities() const {
+    std::vector<float> h(w_->nv());
+    rsbCheck(rsb_batch_get_nonlinearities(w_->batch(), env_, 1, h.data(), RSB_HOST), "getNonlinearities");
+    VecDyn r(h.size());
+    for (size_t i = 0; i < h.size(); i++) r[i] = h[i];
+    return r;
+  }
+  size_t getBodyIdx(const std::string& name) const {
+    int i = rsb_model_body_index(w_->model(), name.c_str());
+    rsbCheck(i, "getBodyIdx");
+    return size_t(i);
+  }
+  size_t getFrameIdxByName(const std::string& name) const {
+    int i = rsb_model_frame_index(w_->model(), name.c_str());
+    rsbCheck(i, "getFrameIdxByName");
+    return size_t(i);
+  }
+  void getPosition(size_t bodyIdx, const Vec<3>& pointInBody, Vec<3>& out) const {
+    std::vector<float> R(size_t(w_->nb()) * 9), p(size_t(w_->nb()) * 3);
+    rsbCheck(rsb_batch_get_body_poses(w_->batch(), env_, 1, R.data(), p.data(), RSB_HOST), "getPosition");
+    for (int r = 0; r < 3; r++) out[r] = p[bodyIdx * 3 + r] + R[bodyIdx * 9 + 3 * r] * pointInBody[0] + R[bodyIdx * 9 + 3 * r + 1] * pointInBody[1] + R[bodyIdx * 9 + 3 * r + 2] * pointInBody[2];
+  }
+  std::vector<Contact>& getContacts() {
+    rsb_contact c[RSB_KMAX]; int32_t n = 0;
+    rsbCheck(rsb_batch_get_contacts(w_->batch(), c, &n, env_, 1, RSB_HOST), "getContacts");
+    contacts_.clear();
+    for (int i = 0; i < n; i++) contacts_.emplace_back(c[i]);
+    return contacts_;
+  }
+  int env() const { return env_; }
+ private:
+  BatchedWorld* w_;
+  int env_;
+  std::string name_;
+  std::vector<Contact> contacts_;
+};
+
+// raisim::World -- standalone it owns a batch of one environment; as a view it forwards to a shared batch
+class World {
+ public:
+  World() = default;
+  World(BatchedWorld* shared, int env) : w_(shared), env_(env) { robot_.reset(new ArticulatedSystem(w_, env_)); }
+  static void setActivationKey(const std::string&) {}          // licence check of the reference: not a capability
+
+  ArticulatedSystem* addArticulatedSystem(const std::string& urdfPathOrXml, const std::string& = "", const std::vector<std::string>& = {},
+                                          CollisionGroup = 1, CollisionGroup = CollisionGroup(-1)) {
+    if (w_) throw std::runtime_error("addArticulatedSystem: this World is a view of a BatchedWorld (one robot per environment)");
+    owned_.reset(new BatchedWorld(urdfPathOrXml, 1));
+    w_ = owned_.get(); env_ = 0;
+    rsb_params p = w_->params();
+    p.dt = float(dt_); p.gravity[0] = float(g_[0]); p.gravity[1] = float(g_[1]); p.gravity[2] = float(g_[2]);
+    w_->setParams(p);
+    if (haveGround_) rsbCheck(rsb_batch_set_ground(w_->batch(), float(groundZ_)), "addGround");
+    robot_.reset(new ArticulatedSystem(w_, 0));
+    return robot_.get();
+  }
+  Ground* addGround(double zHeight = 0.0, const std::string& = "default", CollisionGroup = CollisionGroup(-1)) {
+    haveGround_ = true; groundZ_ = zHeight;
+    if (w_) rsbCheck(rsb_batch_set_ground(w_->batch(), float(zHeight)), "addGround");
+    return &ground_;
+  }
+  HeightMap* addHeightMap(size_t xSamples, size_t ySamples, double xSize, double ySize, double centerX, double centerY,
+                          const std::vector<double>& height, const std::string& = "default", CollisionGroup = 1, CollisionGroup = CollisionGroup(-1)) {
+    need();
+    std::vector<float> h(height.begin(), height.end());
+    rsbCheck(rsb_batch_set_heightmap(w_->batch(), int(xSamples), int(ySamples), float(xSize), float(ySize), float(centerX), float(centerY), h.data()), "addHeightMap");
+    return &hm_;
+  }
+  void setTimeStep(double dt) { dt_ = dt; if (w_) { rsb_params p = w_->params(); p.dt = float(dt); w_->setParams(p); } }
+  double getTimeStep() const { return dt_; }
+  void setGravity(const Vec<3>& g) { g_ = g; if (w_) { rsb_params p = w_->params(); for (int k = 0; k < 3; k++) p.gravity[k] = float(g[k]); w_->setParams(p); } }
+  void setERP(double erp, double = 0) { need(); rsb_params p = w_->params(); p.erp = float(erp); w_->setParams(p); }
+  void setContactSolverParam(double alpha_init, double alpha_min, double alpha_decay, int maxIter, double threshold) {
+    need(); rsb_params p = w_->params();
+    p.alpha_init = float(alpha_init); p.alpha_min = float(alpha_min); p.alpha_decay = float(alpha_decay); p.max_iter = maxIter; p.threshold = float(threshold);
+    w_->setParams(p);
+  }
+  void setDefaultMaterial(double friction, double restitution, double resThreshold) {
+    need(); rsb_params p = w_->params(); p.mu = float(friction); p.restitution = float(restitution); p.rest_threshold = float(resThreshold); w_->setParams(p);
+  }
+  // one World::integrate() of THIS environment's batch.  Views of a shared batch must not call this
+  // per environment -- the vectorized wrapper steps the whole batch once (see VectorizedEnvironment.hpp).
+  void integrate() { need(); w_->integrate(1); }
+  void integrate1() { need(); w_->integrate1(); }
+  void integrate2() { need(); w_->integrate2(); }
+  double getWorldTime() const { return w_ ? w_->worldTime() : 0.0; }
+  ArticulatedSystem* getRobot() { return robot_.get(); }
+  BatchedWorld* batched() { return w_; }
+ private:
+  void need() const { if (!w_) throw std::runtime_error("World: call addArticulatedSystem() first (the batch is created with the robot)"); }
+  std::unique_ptr<BatchedWorld> owned_;
+  BatchedWorld* w_ = nullptr;
+  int env_ = 0;
+  std::unique_ptr<ArticulatedSystem> robot_;
+  Ground ground_; HeightMap hm_;
+  bool haveGround_ = false;
+  double groundZ_ = 0, dt_ = 0.005;
+  Vec<3> g_{0, 0, -9.81};
+};
+
+}  // namespace raisim

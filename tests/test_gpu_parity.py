@@ -349,3 +349,17 @@ def test_full_size_properties_4096(capi):
     assert (g[:, 2] > 0.2).mean() > 0.99         # robots are standing on the terrain, not through it
     it = bt.solver_iterations()
     print(f"4096-env rough terrain: mean K {cnt.mean():.2f}, mean solver iterations {it.mean():.1f}, max {it.max()}")
+
+
+def test_cpp_facade_example_program(capi):
+    """BASELINE configs[0]: the raisim:: facade (include/raisim/World.hpp) driving a batch of one through
+    1000 World::integrate() calls; the program checks that the robot stands on four feet."""
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "examples", "anymal_flat")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")])
+    out = subprocess.run([exe, os.path.join(RSC, "anymal_c_like.urdf"), "1000"], capture_output=True, text=True, timeout=120)
+    print(out.stdout)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "contacts=4" in out.stdout
