@@ -56,6 +56,12 @@ typedef struct rsb_params {
   float mu;          /* World::setDefaultMaterial friction               (0.8)            */
   float restitution; /* World::setDefaultMaterial restitution            (0)              */
   float rest_threshold; /* restitution threshold velocity               (0.01)           */
+  /* Stagnation exit of the Gauss-Seidel loop (NOT in the reference; stall_window = 0 restores the
+   * plain maxIter behaviour): every stall_window iterations, stop if the largest impulse update has
+   * not dropped below stall_ratio x its value one window earlier.  Rank-deficient Delassus blocks
+   * (two contacts on one body) make the published per-contact rule cycle; see DESIGN.md section 5. */
+  int stall_window;     /*                                               (8)              */
+  float stall_ratio;    /*                                               (0.5)            */
 } rsb_params;
 
 /* raisim::Contact as returned by ArticulatedSystem::getContacts(): 12 words */

@@ -81,6 +81,8 @@ struct Params {
   double threshold = 1e-7;
   double mu = 0.8;              // World::setDefaultMaterial friction
   double restitution = 0.0, rest_threshold = 0.01;
+  int stall_window = 8;         // stagnation exit of the Gauss-Seidel loop (0 = off), see include/rsb.h
+  double stall_ratio = 0.5;
 };
 
 struct Terrain {
@@ -547,6 +549,8 @@ template <typename T> class Sim {
       for (int a = 0; a < C; a++) ws.u0[a] = ws.u[a];
       // a8: Gauss-Seidel over contacts (BisectionContactSolver::solve)
       T alpha = T(prm.alpha_init), mu = T(prm.mu);
+      T err_ckpt = T(3.0e38);
+      int next_ckpt = prm.stall_window;
       for (int it = 0; it < prm.max_iter; it++) {
         T err = 0;
         for (int i = 0; i < K; i++) {
@@ -567,6 +571,10 @@ template <typename T> class Sim {
         ws.iters = it + 1;
         alpha = std::max(T(prm.alpha_min), alpha * T(prm.alpha_decay));
         if (err < T(prm.threshold)) break;
+        if (it + 1 == next_ckpt) {
+          if (it + 1 >= 2 * prm.stall_window && err > T(prm.stall_ratio) * err_ckpt) break;
+          err_ckpt = err; next_ckpt += prm.stall_window;
+        }
       }
       for (int r = 0; r < nv; r++) {
         T s = 0;

@@ -279,7 +279,7 @@ int rsb_params_default(rsb_params* p) {
   if (!p) return fail(RSB_ERR_INVALID, "null params");
   p->dt = 0.0025f; p->gravity[0] = 0.f; p->gravity[1] = 0.f; p->gravity[2] = -9.81f; p->erp = 0.f;
   p->alpha_init = 1.f; p->alpha_min = 1.f; p->alpha_decay = 1.f; p->max_iter = 150; p->threshold = 1e-6f;
-  p->mu = 0.8f; p->restitution = 0.f; p->rest_threshold = 0.01f;
+  p->mu = 0.8f; p->restitution = 0.f; p->rest_threshold = 0.01f; p->stall_window = 8; p->stall_ratio = 0.5f;
   return RSB_OK;
 }
 

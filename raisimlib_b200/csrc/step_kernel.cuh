@@ -783,6 +783,8 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
         __syncwarp();
         // =========================== stage D: per-contact Gauss-Seidel ===========================
         float alpha = args.prm.alpha_init;
+        float err_ckpt = 3.0e38f;
+        int next_ckpt = args.prm.stall_window;
 #pragma unroll 1
         for (int it = 0; it < args.prm.max_iter; it++) {
           float err = 0.f;
@@ -803,6 +805,10 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
           iters = it + 1;
           alpha = fmaxf(args.prm.alpha_min, alpha * args.prm.alpha_decay);
           if (err < args.prm.threshold) break;
+          if (it + 1 == next_ckpt) {      // stagnation exit (see rsb_params.stall_window)
+            if (it + 1 >= 2 * args.prm.stall_window && err > args.prm.stall_ratio * err_ckpt) break;
+            err_ckpt = err; next_ckpt += args.prm.stall_window;
+          }
         }
         if (lane < C) s_lam[lane] = lam_c;
         __syncwarp();

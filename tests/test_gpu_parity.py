@@ -42,7 +42,7 @@ def _setup(capi, urdf, n, seed, terrain="ground", base_z=0.45, vel=0.5, tau_scal
     tau = rng.uniform(-tau_scale, tau_scale, (n, t["nv"]))
     if t["floating"]:
         tau[:, :6] = 0
-    prm = dict(threshold=THRESH)
+    prm = dict(threshold=THRESH, stall_window=0)     # plain maxIter semantics unless a test asks for the stagnation exit
     prm.update(params or {})
     o64, o32 = Oracle(t, params=prm), Oracle(t, precision="f32", params=prm)
     bt.set_params(**{k: v for k, v in prm.items() if k not in ("gx", "gy", "gz")})
@@ -363,3 +363,22 @@ def test_cpp_facade_example_program(capi):
     print(out.stdout)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "contacts=4" in out.stdout
+
+
+def test_stagnation_exit_matches_oracle(capi):
+    """Default solver parameters (stall_window = 8): same exit decisions as the oracle, short tail."""
+    n = 1024
+    t, bt, o64, o32, gc, gv, tau = _setup(capi, "anymal_c_like.urdf", n, seed=111, base_z=0.35, params=dict(stall_window=8, stall_ratio=0.5))
+    bt.integrate(1)
+    it = bt.solver_iterations()
+    g1, v1 = bt.get_state()
+    a, b = gc.copy(), gv.copy()
+    d = o64.step(a, b, tau_ff=tau, debug=True)
+    pts = bt.contact_points()
+    same = (pts == d["c_pt"]).all(1)
+    assert it.max() <= 48 and d["iters"].max() <= 48           # the 150-iteration tail is gone on both sides
+    agree = (it == d["iters"])[same].mean()
+    print(f"stagnation exit: max iters gpu {it.max()} oracle {d['iters'].max()}; identical iteration counts in {100 * agree:.1f}% of envs")
+    assert agree > 0.97
+    ok = same & (it == d["iters"]) & (it < 16)                  # converged before any stall check could fire
+    assert np.abs(v1 - b)[ok].max() < 5e-3
