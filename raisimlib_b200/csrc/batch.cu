@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -46,7 +47,10 @@ struct rsb_batch {
   uint32_t* blob = nullptr;
   std::vector<uint32_t> blob_host;
   BlobHeader hdr{};
+  Dims dims{};
   WsLayout ws{};
+  int spec = 0;                  // 0 generic, 1 quadruped-12 static dims, 2 humanoid-30 static dims
+  int slots = 1;
   TerrainDesc ter{};
   std::vector<float> kp, kd;
   int wpc = 0, grid = 0;
@@ -60,51 +64,29 @@ static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static void build_blob(rsb_batch* b) {
   const Model& md = b->model->md;
   BlobHeader& H = b->hdr;
-  H.nb = md.nb; H.nq = md.nq; H.nv = md.nv; H.npts = md.npts(); H.floating = md.floating; H.maxdepth = md.maxdepth;
-  H.nbp = md.nb | 1;                        // odd stride: field-major reads by body index stay conflict-free
-  H.nptp = std::max(1, md.npts());
-  H.nvp = round_up(std::max(md.nv, 1), 4);
-  H.nqp = round_up(std::max(md.nq, 1), 4);
   // dof tree: a floating base is a chain of 6 dofs; dof order is DFS pre-order so subtrees are contiguous
   const int nv = md.nv;
   std::vector<int> dparent(std::max(1, nv), -1), ddepth(std::max(1, nv), 0), dsub(std::max(1, nv), 1), dbody(std::max(1, nv), 0), bdof(md.nb, -1);
-  H.nbase = md.floating ? 6 : 0;
-  for (int k = 1; k < H.nbase; k++) dparent[k] = k - 1;
+  const int nbase = md.floating ? 6 : 0;
+  for (int k = 1; k < nbase; k++) dparent[k] = k - 1;
   if (md.floating) bdof[0] = 5;
   for (int i = 1; i < md.nb; i++) {
     bdof[i] = md.vidx[i]; dbody[md.vidx[i]] = i;
     dparent[md.vidx[i]] = bdof[md.parent[i]];
   }
-  H.maxdd = 0;
-  for (int i = 0; i < nv; i++) { ddepth[i] = dparent[i] >= 0 ? ddepth[dparent[i]] + 1 : 0; H.maxdd = std::max(H.maxdd, ddepth[i]); }
+  int maxdd = 0;
+  for (int i = 0; i < nv; i++) { ddepth[i] = dparent[i] >= 0 ? ddepth[dparent[i]] + 1 : 0; maxdd = std::max(maxdd, ddepth[i]); }
   for (int i = nv - 1; i > 0; i--) if (dparent[i] >= 0) dsub[dparent[i]] += dsub[i];
-  const int DL = H.maxdd + 1;
-  H.dlp = DL | 1;
+  const int DL = maxdd + 1;
   std::vector<int> lvl(DL + 1, 0), lvldofs, entstart(DL + 1, 0), ent;
   for (int d = 0; d < DL; d++) {
     lvl[d] = (int)lvldofs.size(); entstart[d] = (int)ent.size();
     for (int i = 0; i < nv; i++) if (ddepth[i] == d) { lvldofs.push_back(i); for (int t = 0; t <= d; t++) ent.push_back(i | (t << 8)); }
   }
   lvl[DL] = (int)lvldofs.size(); entstart[DL] = (int)ent.size();
-  H.nent = (int)ent.size();
-  int off = HEADER_WORDS;
-  H.off_body = off; off += BF_COUNT * H.nbp;
-  H.off_anc = off; off += std::max(1, md.maxdepth) * H.nbp;
-  H.off_pts = off; off += 5 * H.nptp;
-  H.off_gain = off; off += 2 * H.nvp;
-  H.off_dofq = off; off += H.nvp;
-  H.off_sec = off; off += 2 * NROUNDS * SEC_STRIDE;
-  H.off_ddepth = off; off += H.nvp;
-  H.off_dsub = off; off += H.nvp;
-  H.off_danc = off; off += DL * H.nvp;
-  H.off_dbody = off; off += H.nvp;
-  H.off_bdof = off; off += H.nbp;
-  H.off_lvl = off; off += DL + 1;
-  H.off_lvldofs = off; off += H.nvp;
-  H.off_entstart = off; off += DL + 1;
-  H.off_ent = off; off += std::max(1, H.nent);
-  H.off_lcad = off; off += (md.nb * H.nbp + 3) / 4;
-  int words = round_up(off, 4);
+  b->dims = Dims{md.nb, md.nq, md.nv, md.floating, md.maxdepth, maxdd};
+  H = make_blob_header(b->dims, md.npts(), (int)ent.size());
+  const int words = H.words;
   std::vector<uint32_t>& B = b->blob_host;
   B.assign(words, 0u);
   auto F = [&](int o, float v) { std::memcpy(&B[o], &v, 4); };
@@ -161,40 +143,23 @@ static void build_blob(rsb_batch* b) {
   std::memcpy(B.data(), &H, sizeof(H));
 }
 
-static void build_ws_layout(rsb_batch* b) {
-  const BlobHeader& H = b->hdr;
-  WsLayout& L = b->ws;
-  int o = 0;
-  L.o_gc = o; o += H.nqp;
-  L.o_gv = o; o += H.nvp;
-  L.o_tau = o; o += H.nvp;
-  L.o_pt = o; o += H.nqp;
-  L.o_vt = o; o += H.nvp;
-  L.o_L = o; o += round_up(std::max(1, H.nv) * H.dlp, 4);           // compact rows: [dof][ancestor depth]
-  L.o_invd = o; o += H.nvp;
-  L.o_rhs = o; o += H.nvp;
-  L.o_z = o; o += H.nvp;
-  L.o_ct = o; o += KMAX * CT_WORDS;
-  L.o_Y = o; o += round_up((H.maxdd + 1) * CP, 4);                   // [ancestor depth][contact row]
-  L.o_lam = o; o += 32;
-  L.o_u = o; o += 12 * KMAX;
-  // union: {h, b, poses} (stages A-C) overlaid by G (stages C-D)
-  int ua = 0;
-  L.o_h = o + ua; ua += H.nvp;
-  L.o_b = o + ua; ua += H.nvp;
-  L.o_pose = o + ua; ua += round_up(PF_COUNT * H.nbp, 4);
-  L.o_G = o;
-  int ub = round_up(CMAX * GP, 4);
-  o += std::max(ua, ub);
-  L.words = round_up(o, 32);
-}
+static void build_ws_layout(rsb_batch* b) { b->ws = make_ws_layout(b->dims); }
 
 // ------------------------------------------------------------------ launches --------------------
-template <int WPC>
+// static specialisations: every 12-joint quadruped (ANYmal, A1, Go1, ...) shares (13,19,18,floating,3,8);
+// the Atlas-like humanoid is (31,37,36,floating,10,15).  Anything else takes the generic kernel.
+constexpr Dims kQuad12{13, 19, 18, 1, 3, 8};
+constexpr Dims kHumanoid30{31, 37, 36, 1, 10, 15};
+static bool same_dims(const Dims& a, const Dims& b) {
+  return a.nb == b.nb && a.nq == b.nq && a.nv == b.nv && a.floating == b.floating && a.maxdepth == b.maxdepth && a.maxdd == b.maxdd;
+}
+
+template <int WPC, int SLOTS, int NB, int NQ, int NV, int FL, int MD, int MDD>
 static cudaError_t launch_step(const StepArgs& a, int grid, size_t smem, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(rsb_step_kernel<WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = rsb_step_kernel<WPC, SLOTS, NB, NQ, NV, FL, MD, MDD>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  rsb_step_kernel<WPC><<<grid, WPC * 32, smem, s>>>(a);
+  kern<<<grid, WPC * 32, smem, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -203,11 +168,14 @@ static int pick_config(rsb_batch* b) {
   CK(cudaGetDeviceProperties(&prop, b->device));
   if (prop.major < 10) return fail(RSB_ERR_UNSUPPORTED, "raisimlib_b200 needs an sm_100a (B200) device; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
   const size_t budget = prop.sharedMemPerBlockOptin;   // 227 KB on B200
-  const size_t blob_bytes = (size_t)round_up((int)b->blob_host.size(), 32) * 4;
+  const size_t blob_bytes = (size_t)b->blob_host.size() * 4;
   const size_t per_warp = (size_t)b->ws.words * 4;
   const int sms = prop.multiProcessorCount;
+  b->slots = b->model->md.npts() > 32 ? 2 : 1;
+  b->spec = same_dims(b->dims, kQuad12) && b->slots == 1 ? 1 : (same_dims(b->dims, kHumanoid30) ? 2 : 0);
+  if (const char* e = getenv("RSB_FORCE_GENERIC")) if (atoi(e)) b->spec = 0;
   // one persistent CTA per SM; as many warps (= resident environments) as shared memory allows
-  static const int options[] = {28, 24, 16, 12, 8, 4, 2, 1};
+  static const int options[] = {28, 16, 8, 4, 1};
   int need = (b->N + sms - 1) / sms;    // warps per SM that make every environment resident at once
   int best = 0;
   for (int w : options) {
@@ -215,11 +183,20 @@ static int pick_config(rsb_batch* b) {
     if (best == 0) best = w;
     if (w >= need) best = w;            // smallest option that still keeps every environment resident
   }
+  if (const char* e = getenv("RSB_FORCE_WPC")) { int w = atoi(e); if (w == 28 || w == 16 || w == 8 || w == 4 || w == 1) if (blob_bytes + (size_t)w * per_warp + 1024 <= budget) best = w; }
   if (best == 0) return fail(RSB_ERR_UNSUPPORTED, "model too large for one warp's shared-memory workspace");
   b->wpc = best;
   b->grid = std::min((b->N + best - 1) / best, sms);
   b->smem_bytes = blob_bytes + (size_t)best * per_warp;
   return RSB_OK;
+}
+
+template <int WPC>
+static cudaError_t dispatch_spec(const rsb_batch* b, const StepArgs& a) {
+  if (b->spec == 1) return launch_step<WPC, 1, 13, 19, 18, 1, 3, 8>(a, b->grid, b->smem_bytes, b->stream);
+  if (b->spec == 2) return launch_step<WPC, 2, 31, 37, 36, 1, 10, 15>(a, b->grid, b->smem_bytes, b->stream);
+  if (b->slots == 1) return launch_step<WPC, 1, 0, 0, 0, 0, 0, 0>(a, b->grid, b->smem_bytes, b->stream);
+  return launch_step<WPC, 2, 0, 0, 0, 0, 0, 0>(a, b->grid, b->smem_bytes, b->stream);
 }
 
 static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug) {
@@ -236,14 +213,11 @@ static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug) {
   a.phase_mask = phase_mask;
   cudaError_t e;
   switch (b->wpc) {
-    case 28: e = launch_step<28>(a, b->grid, b->smem_bytes, b->stream); break;
-    case 24: e = launch_step<24>(a, b->grid, b->smem_bytes, b->stream); break;
-    case 16: e = launch_step<16>(a, b->grid, b->smem_bytes, b->stream); break;
-    case 12: e = launch_step<12>(a, b->grid, b->smem_bytes, b->stream); break;
-    case 8: e = launch_step<8>(a, b->grid, b->smem_bytes, b->stream); break;
-    case 4: e = launch_step<4>(a, b->grid, b->smem_bytes, b->stream); break;
-    case 2: e = launch_step<2>(a, b->grid, b->smem_bytes, b->stream); break;
-    default: e = launch_step<1>(a, b->grid, b->smem_bytes, b->stream); break;
+    case 28: e = dispatch_spec<28>(b, a); break;
+    case 16: e = dispatch_spec<16>(b, a); break;
+    case 8: e = dispatch_spec<8>(b, a); break;
+    case 4: e = dispatch_spec<4>(b, a); break;
+    default: e = dispatch_spec<1>(b, a); break;
   }
   if (e != cudaSuccess) return fail(RSB_ERR_CUDA, std::string("step kernel launch: ") + cudaGetErrorString(e));
   b->launches++;

@@ -46,25 +46,93 @@ enum BodyField {
 enum PoseField { PF_R = 0, PF_P = 9, PF_A = 12, PF_COUNT = 15 };
 enum CtField { CF_POS = 0, CF_N = 3, CF_T1 = 6, CF_T2 = 9, CF_DEPTH = 12, CF_PT = 13, CF_BODY = 14, CF_PAIR = 15 };
 
-// header of the model constant blob (first 16 words)
+// Model dimensions that fix every table offset.  A kernel can be compiled for a given Dims
+// (offsets become immediates) or read them from the blob header at run time (generic path).
+struct Dims { int nb, nq, nv, floating, maxdepth, maxdd; };
+
+__host__ __device__ constexpr int round_up_c(int x, int m) { return (x + m - 1) / m * m; }
+__host__ __device__ constexpr int max_c(int a, int b) { return a > b ? a : b; }
+
+// header of the model constant blob (first 32 words)
 struct BlobHeader {
   int nb, nq, nv, npts, floating, maxdepth, nbp, nptp, nvp, nqp;
   int off_body, off_anc, off_pts, off_gain, off_dofq, off_sec;
   // dof tree (floating base = chain of 6 dofs) for the branch-sparse factorisation
   int nbase, maxdd, dlp, nent;
   int off_ddepth, off_dsub, off_danc, off_dbody, off_bdof, off_lvl, off_lvldofs, off_entstart, off_ent, off_lcad;
-  int pad[2];
+  int words, pad;
 };
 static_assert(sizeof(BlobHeader) == 128, "header is 32 words");
 constexpr int HEADER_WORDS = 32;
 
-// per-warp workspace layout (word offsets), computed on the host
+// Every offset except off_ent / words depends on Dims only: the two variable-size tables
+// (candidate points, factorisation entry list) sit at the end.
+__host__ __device__ constexpr BlobHeader make_blob_header(Dims d, int npts, int nent) {
+  BlobHeader H{};
+  H.nb = d.nb; H.nq = d.nq; H.nv = d.nv; H.npts = npts; H.floating = d.floating; H.maxdepth = d.maxdepth;
+  H.nbp = d.nb | 1;                       // odd stride: field-major reads by body index stay conflict-free
+  H.nptp = max_c(1, npts);
+  H.nvp = round_up_c(max_c(d.nv, 1), 4);
+  H.nqp = round_up_c(max_c(d.nq, 1), 4);
+  H.nbase = d.floating ? 6 : 0; H.maxdd = d.maxdd; H.dlp = (d.maxdd + 1) | 1; H.nent = nent;
+  const int DL = d.maxdd + 1;
+  int off = HEADER_WORDS;
+  H.off_body = off; off += 31 * H.nbp;
+  H.off_anc = off; off += max_c(1, d.maxdepth) * H.nbp;
+  H.off_gain = off; off += 2 * H.nvp;
+  H.off_dofq = off; off += H.nvp;
+  H.off_sec = off; off += 2 * 4 * 36;
+  H.off_ddepth = off; off += H.nvp;
+  H.off_dsub = off; off += H.nvp;
+  H.off_danc = off; off += DL * H.nvp;
+  H.off_dbody = off; off += H.nvp;
+  H.off_bdof = off; off += H.nbp;
+  H.off_lvl = off; off += DL + 1;
+  H.off_lvldofs = off; off += H.nvp;
+  H.off_entstart = off; off += DL + 1;
+  H.off_lcad = off; off += (d.nb * H.nbp + 3) / 4;
+  H.off_pts = off; off += 5 * H.nptp;
+  H.off_ent = off; off += max_c(1, nent);
+  H.words = round_up_c(off, 4);
+  return H;
+}
+
+// per-warp workspace layout (word offsets)
 struct WsLayout {
   int o_gc, o_gv, o_tau, o_pt, o_vt, o_L, o_invd, o_rhs, o_z, o_ct, o_Y, o_lam, o_u;   // persistent
   int o_h, o_b, o_pose;                                                                  // union A
   int o_G;                                                                               // union B
   int words;
 };
+
+__host__ __device__ constexpr WsLayout make_ws_layout(Dims d) {
+  WsLayout L{};
+  const int nvp = round_up_c(max_c(d.nv, 1), 4), nqp = round_up_c(max_c(d.nq, 1), 4), nbp = d.nb | 1, dlp = (d.maxdd + 1) | 1;
+  int o = 0;
+  L.o_gc = o; o += nqp;
+  L.o_gv = o; o += nvp;
+  L.o_tau = o; o += nvp;
+  L.o_pt = o; o += nqp;
+  L.o_vt = o; o += nvp;
+  L.o_L = o; o += round_up_c(max_c(1, d.nv) * dlp, 4);            // compact rows: [dof][ancestor depth]
+  L.o_invd = o; o += nvp;
+  L.o_rhs = o; o += nvp;
+  L.o_z = o; o += nvp;
+  L.o_ct = o; o += KMAX * CT_WORDS;
+  L.o_Y = o; o += round_up_c((d.maxdd + 1) * CP, 4);              // [ancestor depth][contact row]
+  L.o_lam = o; o += 32;
+  L.o_u = o; o += 12 * KMAX;
+  // union: {h, b, poses} (stages A-C) overlaid by G (stages C-D)
+  int ua = 0;
+  L.o_h = o + ua; ua += nvp;
+  L.o_b = o + ua; ua += nvp;
+  L.o_pose = o + ua; ua += round_up_c(15 * nbp, 4);
+  L.o_G = o;
+  const int ub = round_up_c(CMAX * GP, 4);
+  o += max_c(ua, ub);
+  L.words = round_up_c(o, 32);
+  return L;
+}
 
 struct TerrainDesc {
   int type;            // 0 none, 1 Ground, 2 HeightMap
@@ -253,11 +321,20 @@ __device__ __forceinline__ bool terrain_query(const TerrainDesc& t, f3 P, float&
 }
 
 // ------------------------------------------------------------------ the kernel -----------------
-template <int WPC>
+// SNB > 0: compiled for the model dimensions (SNB, SNQ, SNV, SFL, SMAXDEPTH, SMAXDD) -- every table and
+// workspace offset is an immediate.  SNB == 0: generic, dimensions read from the blob header.
+template <int WPC, int SLOTS, int SNB, int SNQ, int SNV, int SFL, int SMAXDEPTH, int SMAXDD>
 __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_constant__ StepArgs args) {
   extern __shared__ __align__(128) uint32_t smem[];
   __shared__ __align__(8) uint64_t tma_bar;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr bool ST = SNB > 0;
+  constexpr Dims SD{SNB, SNQ, SNV, SFL, SMAXDEPTH, SMAXDD};
+  constexpr WsLayout LS = make_ws_layout(SD);
+  constexpr BlobHeader HS = make_blob_header(SD, 0, 0);
+#define WSO(f) (ST ? LS.f : args.ws.f)
+  // shared memory: [WPC workspaces][model constant blob]
+  uint32_t* const blob_s = smem + WPC * WSO(words);
 
   // ---- stage the model constant block once per CTA with one TMA bulk copy ----------------------
   if (threadIdx.x == 0) {
@@ -267,41 +344,43 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_expect_tx(&tma_bar, (uint32_t)args.blob_words * 4u);
-    tma_bulk_g2s(smem, args.blob, (uint32_t)args.blob_words * 4u, &tma_bar);
+    tma_bulk_g2s(blob_s, args.blob, (uint32_t)args.blob_words * 4u, &tma_bar);
   }
   mbar_wait(&tma_bar, 0);
 
-  const BlobHeader& H = *reinterpret_cast<const BlobHeader*>(smem);
-  const int nb = H.nb, nq = H.nq, nv = H.nv, npts = H.npts, floating = H.floating, maxdepth = H.maxdepth;
-  const int nbp = H.nbp, nptp = H.nptp, nvp = H.nvp;
-  const float* bodyf = reinterpret_cast<const float*>(smem + H.off_body);
-  const int* bodyi = reinterpret_cast<const int*>(smem + H.off_body);
-  const int* anc = reinterpret_cast<const int*>(smem + H.off_anc);
-  const float* ptsf = reinterpret_cast<const float*>(smem + H.off_pts);
-  const int* ptsi = reinterpret_cast<const int*>(smem + H.off_pts);
-  const float* kp = reinterpret_cast<const float*>(smem + H.off_gain);
+  const BlobHeader& H = *reinterpret_cast<const BlobHeader*>(blob_s);
+#define HO(f) (ST ? HS.f : H.f)
+  const int nb = HO(nb), nq = HO(nq), nv = HO(nv), npts = H.npts, floating = HO(floating), maxdepth = HO(maxdepth);
+  const int nbp = HO(nbp), nptp = H.nptp, nvp = HO(nvp);
+  const float* bodyf = reinterpret_cast<const float*>(blob_s + HO(off_body));
+  const int* bodyi = reinterpret_cast<const int*>(blob_s + HO(off_body));
+  const int* anc = reinterpret_cast<const int*>(blob_s + HO(off_anc));
+  const float* ptsf = reinterpret_cast<const float*>(blob_s + HO(off_pts));
+  const int* ptsi = reinterpret_cast<const int*>(blob_s + HO(off_pts));
+  const float* kp = reinterpret_cast<const float*>(blob_s + HO(off_gain));
   const float* kd = kp + nvp;
-  const int* dofq = reinterpret_cast<const int*>(smem + H.off_dofq);
-  const float* sec_c = reinterpret_cast<const float*>(smem + H.off_sec);
+  const int* dofq = reinterpret_cast<const int*>(blob_s + HO(off_dofq));
+  const float* sec_c = reinterpret_cast<const float*>(blob_s + HO(off_sec));
   const float* sec_s = sec_c + NROUNDS * SEC_STRIDE;
-  const int nbase = H.nbase, maxdd = H.maxdd, DLP = H.dlp;
-  const int* ddepth = reinterpret_cast<const int*>(smem + H.off_ddepth);
-  const int* dsub = reinterpret_cast<const int*>(smem + H.off_dsub);
-  const int* danc = reinterpret_cast<const int*>(smem + H.off_danc);
-  const int* dbody = reinterpret_cast<const int*>(smem + H.off_dbody);
-  const int* bdof = reinterpret_cast<const int*>(smem + H.off_bdof);
-  const int* lvl = reinterpret_cast<const int*>(smem + H.off_lvl);
-  const int* lvldofs = reinterpret_cast<const int*>(smem + H.off_lvldofs);
-  const int* entstart = reinterpret_cast<const int*>(smem + H.off_entstart);
-  const int* ent = reinterpret_cast<const int*>(smem + H.off_ent);
-  const int8_t* lcad = reinterpret_cast<const int8_t*>(smem + H.off_lcad);
+  const int nbase = HO(nbase), maxdd = HO(maxdd), DLP = HO(dlp);
+  const int* ddepth = reinterpret_cast<const int*>(blob_s + HO(off_ddepth));
+  const int* dsub = reinterpret_cast<const int*>(blob_s + HO(off_dsub));
+  const int* danc = reinterpret_cast<const int*>(blob_s + HO(off_danc));
+  const int* dbody = reinterpret_cast<const int*>(blob_s + HO(off_dbody));
+  const int* bdof = reinterpret_cast<const int*>(blob_s + HO(off_bdof));
+  const int* lvl = reinterpret_cast<const int*>(blob_s + HO(off_lvl));
+  const int* lvldofs = reinterpret_cast<const int*>(blob_s + HO(off_lvldofs));
+  const int* entstart = reinterpret_cast<const int*>(blob_s + HO(off_entstart));
+  const int* ent = reinterpret_cast<const int*>(blob_s + H.off_ent);
+  const int8_t* lcad = reinterpret_cast<const int8_t*>(blob_s + HO(off_lcad));
 
-  const WsLayout& L = args.ws;
-  float* ws = reinterpret_cast<float*>(smem + ((args.blob_words + 31) & ~31) + warp * L.words);
-  float* s_gc = ws + L.o_gc; float* s_gv = ws + L.o_gv; float* s_tau = ws + L.o_tau; float* s_pt = ws + L.o_pt; float* s_vt = ws + L.o_vt;
-  float* s_L = ws + L.o_L; float* s_invd = ws + L.o_invd; float* s_rhs = ws + L.o_rhs; float* s_z = ws + L.o_z; float* s_ct = ws + L.o_ct;
-  float* s_Y = ws + L.o_Y; float* s_lam = ws + L.o_lam; float* s_u = ws + L.o_u;
-  float* s_h = ws + L.o_h; float* s_b = ws + L.o_b; float* s_pose = ws + L.o_pose; float* s_G = ws + L.o_G;
+  float* const ws = reinterpret_cast<float*>(smem) + warp * WSO(words);
+  float* s_gc = ws + WSO(o_gc); float* s_gv = ws + WSO(o_gv); float* s_tau = ws + WSO(o_tau); float* s_pt = ws + WSO(o_pt); float* s_vt = ws + WSO(o_vt);
+  float* s_L = ws + WSO(o_L); float* s_invd = ws + WSO(o_invd); float* s_rhs = ws + WSO(o_rhs); float* s_z = ws + WSO(o_z); float* s_ct = ws + WSO(o_ct);
+  float* s_Y = ws + WSO(o_Y); float* s_lam = ws + WSO(o_lam); float* s_u = ws + WSO(o_u);
+  float* s_h = ws + WSO(o_h); float* s_b = ws + WSO(o_b); float* s_pose = ws + WSO(o_pose); float* s_G = ws + WSO(o_G);
+#undef WSO
+#undef HO
   const float dt = args.prm.dt;
   const float mu = args.prm.mu;
   const f3 grav = mk(args.prm.gravity[0], args.prm.gravity[1], args.prm.gravity[2]);
@@ -533,10 +612,10 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
       }
 
       // =========================== stage B: narrow phase ========================================
-      float c_depth[MAX_PT_SLOTS]; f3 c_pos[MAX_PT_SLOTS], c_n[MAX_PT_SLOTS]; int c_pair[MAX_PT_SLOTS], c_body[MAX_PT_SLOTS];
-      bool c_hit[MAX_PT_SLOTS];
+      float c_depth[SLOTS]; f3 c_pos[SLOTS], c_n[SLOTS]; int c_pair[SLOTS], c_body[SLOTS];
+      bool c_hit[SLOTS];
 #pragma unroll
-      for (int s = 0; s < MAX_PT_SLOTS; s++) {
+      for (int s = 0; s < SLOTS; s++) {
         int k = lane + 32 * s;
         c_hit[s] = false; c_depth[s] = 0.f; c_pair[s] = 0; c_body[s] = 0; c_pos[s] = mk(0, 0, 0); c_n[s] = mk(0, 0, 1);
         if (k < npts) {
@@ -554,15 +633,15 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
           }
         }
       }
-      unsigned hm[MAX_PT_SLOTS];
+      unsigned hm[SLOTS];
       int total = 0;
 #pragma unroll
-      for (int s = 0; s < MAX_PT_SLOTS; s++) { hm[s] = __ballot_sync(FULL, c_hit[s]); total += __popc(hm[s]); }
+      for (int s = 0; s < SLOTS; s++) { hm[s] = __ballot_sync(FULL, c_hit[s]); total += __popc(hm[s]); }
 #pragma unroll 1
       while (total > KMAX) {   // drop the shallowest (ties: highest candidate index) until KMAX remain
         float dmin = 3.0e38f; int imin = -1;
 #pragma unroll
-        for (int s = 0; s < MAX_PT_SLOTS; s++)
+        for (int s = 0; s < SLOTS; s++)
           if (c_hit[s] && (c_depth[s] < dmin || (c_depth[s] == dmin && lane + 32 * s > imin))) { dmin = c_depth[s]; imin = lane + 32 * s; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -570,16 +649,16 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
           if (d2 < dmin || (d2 == dmin && i2 > imin)) { dmin = d2; imin = i2; }
         }
 #pragma unroll
-        for (int s = 0; s < MAX_PT_SLOTS; s++) if (lane + 32 * s == imin) c_hit[s] = false;
+        for (int s = 0; s < SLOTS; s++) if (lane + 32 * s == imin) c_hit[s] = false;
         total = 0;
 #pragma unroll
-        for (int s = 0; s < MAX_PT_SLOTS; s++) { hm[s] = __ballot_sync(FULL, c_hit[s]); total += __popc(hm[s]); }
+        for (int s = 0; s < SLOTS; s++) { hm[s] = __ballot_sync(FULL, c_hit[s]); total += __popc(hm[s]); }
       }
       K = total;
       {
         int base = 0;
 #pragma unroll
-        for (int s = 0; s < MAX_PT_SLOTS; s++) {
+        for (int s = 0; s < SLOTS; s++) {
           if (c_hit[s]) {
             int slot = base + __popc(hm[s] & ((1u << lane) - 1u));
             float* ct = s_ct + slot * CT_WORDS;
