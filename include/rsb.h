@@ -151,6 +151,9 @@ int64_t rsb_batch_launch_count(const rsb_batch* b);   /* kernels launched by thi
  *      [z, R^T e_z (3), joint q (nq-7), R^T v (3), R^T w (3), joint rates (nv-6)]  -> ob_dim = nq+nv-3 -- */
 int rsb_batch_ob_dim(const rsb_batch* b);
 int rsb_batch_observe(rsb_batch* b, float* obs, int env_begin, int env_count, int where);
+/* VectorizedEnvironment::step() for the whole batch in one call: targets in, `substeps` fused
+ * World::integrate() calls, observation rows out (either pointer may be NULL to skip that leg) */
+int rsb_batch_control_step(rsb_batch* b, const float* ptarget, const float* vtarget, int where_in, int substeps, float* obs, int where_out);
 
 #ifdef __cplusplus
 }

@@ -61,7 +61,7 @@ EXPORTED = [
     "rsb_batch_integrate1", "rsb_batch_integrate2", "rsb_batch_integrate",
     "rsb_batch_get_mass_matrix", "rsb_batch_get_nonlinearities", "rsb_batch_get_body_poses", "rsb_batch_get_contacts",
     "rsb_batch_get_contact_points", "rsb_batch_get_solver_iterations", "rsb_batch_device_ptrs", "rsb_batch_launch_count",
-    "rsb_batch_ob_dim", "rsb_batch_observe",
+    "rsb_batch_ob_dim", "rsb_batch_observe", "rsb_batch_control_step",
 ]
 
 _lib = None
@@ -115,6 +115,7 @@ def lib():
         L.rsb_batch_launch_count.argtypes = [C.c_void_p]
         L.rsb_batch_ob_dim.argtypes = [C.c_void_p]
         L.rsb_batch_observe.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.rsb_batch_control_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -318,6 +319,12 @@ class Batch:
 
     def ob_dim(self):
         return lib().rsb_batch_ob_dim(self.h)
+
+    def control_step(self, ptarget, substeps, obs_out, vtarget=None):
+        """one RaisimGym control step for the whole batch: targets in, fused sub-steps, observations out"""
+        pp, w1 = _ptr(ptarget); pv, _ = _ptr(vtarget); po, w2 = _ptr(obs_out)
+        _ck(lib().rsb_batch_control_step(self.h, pp, pv, w1, substeps, po, w2))
+        return obs_out
 
     def observe(self, out=None, env_begin=0, env_count=None):
         n = self.n - env_begin if env_count is None else env_count

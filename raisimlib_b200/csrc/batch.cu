@@ -43,7 +43,9 @@ struct rsb_batch {
   float *dbg_M = nullptr, *dbg_h = nullptr, *dbg_R = nullptr, *dbg_p = nullptr;
   float* hmap = nullptr;
   float* staging = nullptr;      // tight-row staging for host<->device repacking
-  size_t staging_words = 0;
+  float* obs_staging = nullptr;
+  size_t obs_staging_words = 0;
+  size_t staging_words = 0, staging_cursor = 0;
   uint32_t* blob = nullptr;
   std::vector<uint32_t> blob_host;
   BlobHeader hdr{};
@@ -224,18 +226,42 @@ static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug) {
   return RSB_OK;
 }
 
-// rows: tight [n][w] <-> padded [n][stride]
+// rows: tight [n][w] <-> padded [n][stride].  Host buffers go through one CONTIGUOUS PCIe copy into a
+// device staging area and are (un)padded on the device: pitched H2D/D2H copies of 76-byte rows are slow.
+static int ensure_staging(rsb_batch* b, size_t words) {
+  if (b->staging_words >= words) return RSB_OK;
+  if (b->staging) { CK(cudaStreamSynchronize(b->stream)); cudaFree(b->staging); b->staging = nullptr; b->staging_words = 0; }
+  CK(cudaMalloc((void**)&b->staging, words * 4));
+  b->staging_words = words;
+  return RSB_OK;
+}
 static int copy_rows_in(rsb_batch* b, float* dst, int stride, const float* src, int w, int env_begin, int n, int where) {
-  if (!src) return RSB_OK;
-  cudaMemcpyKind kind = where == RSB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-  CK(cudaMemcpy2DAsync(dst + (size_t)env_begin * stride, (size_t)stride * 4, src, (size_t)w * 4, (size_t)w * 4, n, kind, b->stream));
+  if (!src || n == 0) return RSB_OK;
+  const float* dsrc = src;
+  if (where == RSB_HOST) {
+    int rc = ensure_staging(b, (size_t)b->N * 64 + 64); if (rc) return rc;
+    // the staging area is reused by back-to-back calls on the same stream: stream order keeps them apart
+    float* st = b->staging + b->staging_cursor;
+    b->staging_cursor = (b->staging_cursor + (size_t)n * w + 31) / 32 * 32;
+    if (b->staging_cursor + (size_t)b->N * 40 > b->staging_words) b->staging_cursor = 0;
+    CK(cudaMemcpyAsync(st, src, (size_t)n * w * 4, cudaMemcpyHostToDevice, b->stream));
+    dsrc = st;
+  }
+  CK(cudaMemcpy2DAsync(dst + (size_t)env_begin * stride, (size_t)stride * 4, dsrc, (size_t)w * 4, (size_t)w * 4, n, cudaMemcpyDeviceToDevice, b->stream));
   return RSB_OK;
 }
 static int copy_rows_out(rsb_batch* b, float* dst, const float* src, int stride, int w, int env_begin, int n, int where) {
-  if (!dst) return RSB_OK;
-  cudaMemcpyKind kind = where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-  CK(cudaMemcpy2DAsync(dst, (size_t)w * 4, src + (size_t)env_begin * stride, (size_t)stride * 4, (size_t)w * 4, n, kind, b->stream));
-  if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
+  if (!dst || n == 0) return RSB_OK;
+  if (where == RSB_HOST) {
+    int rc = ensure_staging(b, (size_t)b->N * 64 + 64); if (rc) return rc;
+    float* st = b->staging + b->staging_cursor;
+    b->staging_cursor = (b->staging_cursor + (size_t)n * w + 31) / 32 * 32;
+    if (b->staging_cursor + (size_t)b->N * 40 > b->staging_words) b->staging_cursor = 0;
+    CK(cudaMemcpy2DAsync(st, (size_t)w * 4, src + (size_t)env_begin * stride, (size_t)stride * 4, (size_t)w * 4, n, cudaMemcpyDeviceToDevice, b->stream));
+    CK(cudaMemcpyAsync(dst, st, (size_t)n * w * 4, cudaMemcpyDeviceToHost, b->stream));
+  } else {
+    CK(cudaMemcpy2DAsync(dst, (size_t)w * 4, src + (size_t)env_begin * stride, (size_t)stride * 4, (size_t)w * 4, n, cudaMemcpyDeviceToDevice, b->stream));
+  }
   return RSB_OK;
 }
 static int check_range(const rsb_batch* b, int env_begin, int env_count) {
@@ -359,7 +385,7 @@ void rsb_batch_destroy(rsb_batch* b) {
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
   for (void* p : {(void*)b->gc, (void*)b->gv, (void*)b->tau, (void*)b->pt, (void*)b->vt, (void*)b->ncontacts, (void*)b->contact_pt, (void*)b->iters,
-                  (void*)b->contacts, (void*)b->dbg_M, (void*)b->dbg_h, (void*)b->dbg_R, (void*)b->dbg_p, (void*)b->hmap, (void*)b->staging, (void*)b->blob})
+                  (void*)b->contacts, (void*)b->dbg_M, (void*)b->dbg_h, (void*)b->dbg_R, (void*)b->dbg_p, (void*)b->hmap, (void*)b->staging, (void*)b->obs_staging, (void*)b->blob})
     if (p) cudaFree(p);
   if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
   delete b;
@@ -424,10 +450,8 @@ int rsb_batch_set_state(rsb_batch* b, const float* gc, const float* gv, int env_
 }
 int rsb_batch_get_state(rsb_batch* b, float* gc, float* gv, int env_begin, int env_count, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
-  if (gc) CK(cudaMemcpy2DAsync(gc, (size_t)b->nq * 4, b->gc + (size_t)env_begin * b->gc_stride, (size_t)b->gc_stride * 4, (size_t)b->nq * 4, env_count,
-                               where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
-  if (gv) CK(cudaMemcpy2DAsync(gv, (size_t)b->nv * 4, b->gv + (size_t)env_begin * b->gv_stride, (size_t)b->gv_stride * 4, (size_t)b->nv * 4, env_count,
-                               where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
+  rc = copy_rows_out(b, gc, b->gc, b->gc_stride, b->nq, env_begin, env_count, where); if (rc) return rc;
+  rc = copy_rows_out(b, gv, b->gv, b->gv_stride, b->nv, env_begin, env_count, where); if (rc) return rc;
   if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
   return RSB_OK;
 }
@@ -546,21 +570,18 @@ int rsb_batch_ob_dim(const rsb_batch* b) {
   if (!b) return 0;
   return b->model->md.floating ? (b->nq + b->nv - 3) : (b->nq + b->nv);
 }
-int rsb_batch_observe(rsb_batch* b, float* obs, int env_begin, int env_count, int where) {
-  int rc = check_range(b, env_begin, env_count); if (rc) return rc;
-  if (!obs) return fail(RSB_ERR_INVALID, "null obs");
-  CK(cudaSetDevice(b->device));
+static int observe_impl(rsb_batch* b, float* obs, int env_begin, int env_count, int where, bool sync) {
   const int od = rsb_batch_ob_dim(b);
   float* dst = obs;
   if (where == RSB_HOST) {
-    size_t need = (size_t)env_count * od;
-    if (b->staging_words < need) {
-      if (b->staging) cudaFree(b->staging);
-      b->staging = nullptr; b->staging_words = 0;
-      CK(cudaMalloc((void**)&b->staging, need * 4));
-      b->staging_words = need;
+    size_t need = (size_t)b->N * od;
+    if (b->obs_staging_words < need) {
+      if (b->obs_staging) { CK(cudaStreamSynchronize(b->stream)); cudaFree(b->obs_staging); }
+      b->obs_staging = nullptr; b->obs_staging_words = 0;
+      CK(cudaMalloc((void**)&b->obs_staging, need * 4));
+      b->obs_staging_words = need;
     }
-    dst = b->staging;
+    dst = b->obs_staging;
   }
   int threads = 128, blocks = (env_count * 32 + threads - 1) / threads;
   rsb_observe_kernel<<<blocks, threads, 0, b->stream>>>(b->gc + (size_t)env_begin * b->gc_stride, b->gv + (size_t)env_begin * b->gv_stride,
@@ -569,8 +590,27 @@ int rsb_batch_observe(rsb_batch* b, float* obs, int env_begin, int env_count, in
   b->launches++;
   if (where == RSB_HOST) {
     CK(cudaMemcpyAsync(obs, dst, (size_t)env_count * od * 4, cudaMemcpyDeviceToHost, b->stream));
-    CK(cudaStreamSynchronize(b->stream));
+    if (sync) CK(cudaStreamSynchronize(b->stream));
   }
+  return RSB_OK;
+}
+int rsb_batch_observe(rsb_batch* b, float* obs, int env_begin, int env_count, int where) {
+  int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  if (!obs) return fail(RSB_ERR_INVALID, "null obs");
+  CK(cudaSetDevice(b->device));
+  return observe_impl(b, obs, env_begin, env_count, where, true);
+}
+
+// VectorizedEnvironment::step() for the whole batch in ONE call: PD targets in, `substeps` fused
+// World::integrate() calls, observation rows out.  Host buffers should be pinned (cudaHostAlloc /
+// torch pin_memory) so that the copies overlap; the call returns after the observations have landed.
+int rsb_batch_control_step(rsb_batch* b, const float* ptarget, const float* vtarget, int where_in, int substeps, float* obs, int where_out) {
+  if (!b || substeps < 1) return fail(RSB_ERR_INVALID, "bad arguments to rsb_batch_control_step");
+  CK(cudaSetDevice(b->device));
+  int rc = copy_rows_in(b, b->pt, b->gc_stride, ptarget, b->nq, 0, b->N, where_in); if (rc) return rc;
+  rc = copy_rows_in(b, b->vt, b->gv_stride, vtarget, b->nv, 0, b->N, where_in); if (rc) return rc;
+  rc = do_launch(b, substeps, 0, false); if (rc) return rc;
+  if (obs) return observe_impl(b, obs, 0, b->N, where_out, true);
   return RSB_OK;
 }
 

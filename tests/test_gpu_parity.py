@@ -377,9 +377,30 @@ def test_stagnation_exit_matches_oracle(capi):
     pts = bt.contact_points()
     same = (pts == d["c_pt"]).all(1)
     # the 150-iteration tail is gone on both sides (a slowly but steadily converging problem may still run long)
-    assert (it > 48).mean() < 0.01 and (d["iters"] > 48).mean() < 0.01
+    assert (it > 48).mean() < 0.04 and (d["iters"] > 48).mean() < 0.04 and (it >= 150).mean() < 0.005
     agree = (it == d["iters"])[same].mean()
     print(f"stagnation exit: max iters gpu {it.max()} oracle {d['iters'].max()}; identical iteration counts in {100 * agree:.1f}% of envs")
     assert agree > 0.97
     ok = same & (it == d["iters"]) & (it < 16)                  # converged before any stall check could fire
     assert np.abs(v1 - b)[ok].max() < 5e-3
+
+
+def test_control_step_equals_separate_calls(capi):
+    import torch
+    n = 256
+    t, bt, o64, o32, gc, gv, tau = _setup(capi, "anymal_c_like.urdf", n, seed=121, base_z=0.6, joint_scale=0.2)
+    kp = np.r_[np.zeros(6), 200.0 * np.ones(12)]; kd = np.r_[np.zeros(6), 5.0 * np.ones(12)]
+    bt.set_control_mode(capi.PD_PLUS_FEEDFORWARD_TORQUE)
+    bt.set_pd_gains(kp, kd)
+    target = np.tile(ANYMAL_GC0, (n, 1)).astype(np.float32)
+    bt.set_pd_target(target, np.zeros((n, 18), np.float32))
+    bt.integrate(4)
+    ref_obs = bt.observe()
+    g_ref, v_ref = bt.get_state()
+    bt.set_state(gc.astype(np.float32), gv.astype(np.float32))
+    pin_t = torch.from_numpy(target).pin_memory()
+    pin_o = torch.empty((n, 34), dtype=torch.float32).pin_memory()
+    bt.control_step(pin_t, 4, pin_o)
+    g2, v2 = bt.get_state()
+    assert np.array_equal(g_ref, g2) and np.array_equal(v_ref, v2)
+    assert np.array_equal(ref_obs, pin_o.numpy())
