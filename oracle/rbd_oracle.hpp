@@ -462,11 +462,16 @@ template <typename T> class Sim {
     T glo = 0, ghi = 0; T lo_c = 1, lo_s = 0, hi_c = 1, hi_s = 0;
     for (int r = 0; r < NROUNDS; r++) {
       T gk[NSEC + 1], fk[NSEC + 1]; bool ok[NSEC + 1]; V3<T> lk[NSEC + 1];
-      for (int k = 0; k <= NSEC; k++) {
-        T cs = base_c * sec_c[r][k] - base_s * sec_s[r][k];
-        T sn = base_s * sec_c[r][k] + base_c * sec_s[r][k];
-        ok[k] = eval(cs, sn, gk[k], fk[k], lk[k]);
+      T dc[NSEC + 1], ds[NSEC + 1];
+      for (int k = 0; k < NSEC; k++) {
+        dc[k] = base_c * sec_c[r][k] - base_s * sec_s[r][k];
+        ds[k] = base_s * sec_c[r][k] + base_c * sec_s[r][k];
+        ok[k] = eval(dc[k], ds[k], gk[k], fk[k], lk[k]);
       }
+      // the closing direction is never re-evaluated: probe 0 again in round 0 (full circle), the
+      // previous round's upper end afterwards
+      if (r == 0) { dc[NSEC] = dc[0]; ds[NSEC] = ds[0]; ok[NSEC] = ok[0]; gk[NSEC] = gk[0]; fk[NSEC] = fk[0]; lk[NSEC] = lk[0]; }
+      else { dc[NSEC] = hi_c; ds[NSEC] = hi_s; ok[NSEC] = true; gk[NSEC] = ghi; fk[NSEC] = T(0); lk[NSEC] = best; }
       int pick = -1; T fbest = 0;
       for (int k = 0; k < NSEC; k++) {
         if (!ok[k] || !ok[k + 1]) continue;
@@ -483,8 +488,7 @@ template <typename T> class Sim {
         }
         break;         // keep the bracket of the previous round
       }
-      T cs0 = base_c * sec_c[r][pick] - base_s * sec_s[r][pick], sn0 = base_s * sec_c[r][pick] + base_c * sec_s[r][pick];
-      T cs1 = base_c * sec_c[r][pick + 1] - base_s * sec_s[r][pick + 1], sn1 = base_s * sec_c[r][pick + 1] + base_c * sec_s[r][pick + 1];
+      T cs0 = dc[pick], sn0 = ds[pick], cs1 = dc[pick + 1], sn1 = ds[pick + 1];
       lo_c = cs0; lo_s = sn0; hi_c = cs1; hi_s = sn1; glo = gk[pick]; ghi = gk[pick + 1];
       base_c = cs0; base_s = sn0; have = true; best = lk[pick];
     }

@@ -245,18 +245,23 @@ __device__ __forceinline__ f3 solve_contact(const float* Gs, const float* Gi, f3
   bool have = false;
 #pragma unroll 1
   for (int r = 0; r < NROUNDS; r++) {
-    // lane k probes direction k; direction NSEC comes from lane 0 of the NEXT position (k+1) via shuffle
+    // lane k probes direction k of this round's bracket.  The closing direction (k = NSEC) is never
+    // re-evaluated: in round 0 it is probe 0 again (full circle), later it is the previous round's
+    // upper end, whose values are already known.
     float tc = sec_c[r * SEC_STRIDE + lane], ts = sec_s[r * SEC_STRIDE + lane];
     float cs = base_c * tc - base_s * ts, sn = base_s * tc + base_c * ts;
     Probe p = slip_probe(cs, sn, a, b, cc, d, e, f, c, mu);
-    // the closing probe (k = NSEC) is evaluated by every lane redundantly (same value everywhere)
-    float tc2 = sec_c[r * SEC_STRIDE + NSEC], ts2 = sec_s[r * SEC_STRIDE + NSEC];
-    float cs2 = base_c * tc2 - base_s * ts2, sn2 = base_s * tc2 + base_c * ts2;
-    Probe pe = slip_probe(cs2, sn2, a, b, cc, d, e, f, c, mu);
     float g_next = __shfl_down_sync(FULL, p.g, 1);
     bool ok_next = __shfl_down_sync(FULL, (int)p.ok, 1) != 0;
     float cs_next = __shfl_down_sync(FULL, cs, 1), sn_next = __shfl_down_sync(FULL, sn, 1);
-    if (lane == NSEC - 1) { g_next = pe.g; ok_next = pe.ok; cs_next = cs2; sn_next = sn2; }
+    {
+      float g0 = __shfl_sync(FULL, p.g, 0), c0 = __shfl_sync(FULL, cs, 0), s0 = __shfl_sync(FULL, sn, 0);
+      bool ok0 = __shfl_sync(FULL, (int)p.ok, 0) != 0;
+      if (lane == NSEC - 1) {
+        if (r == 0) { g_next = g0; ok_next = ok0; cs_next = c0; sn_next = s0; }
+        else { g_next = ghi; ok_next = true; cs_next = hi_c; sn_next = hi_s; }
+      }
+    }
     bool cand = p.ok && ok_next && (p.g < 0.f) && (g_next >= 0.f);
     unsigned m = __ballot_sync(FULL, cand);
     if (m == 0u) {
@@ -318,6 +323,26 @@ __device__ __forceinline__ bool terrain_query(const TerrainDesc& t, f3 P, float&
   dist = (P.z - zt) * inv;
   pair = 2 * (iy * (t.xs - 1) + ix) + tri;
   return true;
+}
+
+// getters of integrate1(): full symmetric M rebuilt from the compact rows, h, body poses (cold path)
+__device__ __noinline__ void write_debug(const StepArgs& args, int env, int lane, int nv, int nb, int nvp, int DLP, const float* s_L,
+                                         const float* s_h, const int* ddepth, const int* danc, bool bvalid, const float* R, f3 p) {
+  float* gM = args.dbg_M + (size_t)env * nv * nv;
+  for (int i = lane; i < nv * nv; i += 32) {
+    int r = i / nv, c = i % nv;
+    if (r < c) { int t = r; r = c; c = t; }
+    int dc = ddepth[c];
+    gM[i] = (dc <= ddepth[r] && danc[dc * nvp + r] == c) ? s_L[r * DLP + dc] : 0.f;
+  }
+  float* gh = args.dbg_h + (size_t)env * nv;
+  for (int i = lane; i < nv; i += 32) gh[i] = s_h[i];
+  if (bvalid) {
+    float* gR = args.dbg_R + ((size_t)env * nb + lane) * 9;
+    float* gp = args.dbg_p + ((size_t)env * nb + lane) * 3;
+    for (int k = 0; k < 9; k++) gR[k] = R[k];
+    gp[0] = p.x; gp[1] = p.y; gp[2] = p.z;
+  }
 }
 
 // ------------------------------------------------------------------ the kernel -----------------
@@ -590,26 +615,8 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
         }
       }
       __syncwarp();
-      if (args.dbg_M) {   // getters: full symmetric M, h, poses
-        float* gM = args.dbg_M + (size_t)env * nv * nv;
-#pragma unroll 1
-        for (int i = lane; i < nv * nv; i += 32) {
-          int r = i / nv, c = i % nv;
-          if (r < c) { int t = r; r = c; c = t; }
-          int dc = ddepth[c];
-          gM[i] = (dc <= ddepth[r] && danc[dc * nvp + r] == c) ? s_L[r * DLP + dc] : 0.f;
-        }
-        float* gh = args.dbg_h + (size_t)env * nv;
-#pragma unroll 1
-        for (int i = lane; i < nv; i += 32) gh[i] = s_h[i];
-        if (bvalid) {
-          float* gR = args.dbg_R + ((size_t)env * nb + b) * 9;
-          float* gp = args.dbg_p + ((size_t)env * nb + b) * 3;
-#pragma unroll
-          for (int k = 0; k < 9; k++) gR[k] = R[k];
-          gp[0] = p.x; gp[1] = p.y; gp[2] = p.z;
-        }
-      }
+      if (args.dbg_M)   // getters (integrate1): cold path, kept out of line to spare the instruction cache
+        write_debug(args, env, lane, nv, nb, nvp, DLP, s_L, s_h, ddepth, danc, bvalid, R, p);
 
       // =========================== stage B: narrow phase ========================================
       float c_depth[SLOTS]; f3 c_pos[SLOTS], c_n[SLOTS]; int c_pair[SLOTS], c_body[SLOTS];
@@ -729,7 +736,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
         float val = 0.f;
         if (lane < 21) {
           val = s_L[er * DLP + ec];
-#pragma unroll 1
+#pragma unroll 4
           for (int k = 6; k < nv; k++) val -= s_L[k * DLP + er] * s_L[k * DLP + ec];
         }
 #pragma unroll 1
@@ -764,7 +771,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
         float acc = 0.f;
         if (lane < 6) {
           acc = s_b[lane];
-#pragma unroll 1
+#pragma unroll 4
           for (int k = 6; k < nv; k++) acc -= s_L[k * DLP + lane] * s_z[k];
         }
 #pragma unroll 1
@@ -807,14 +814,35 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
           jv += val * s_gv[a_t];
         }
         float yz = 0.f;
+        if constexpr (ST && SMAXDD + 1 <= 9) {
+          // whole chain in registers (compile-time indices): 2 instructions per multiply-add instead of 4
+          constexpr int DLc = SMAXDD + 1;
+          float y[DLc];
+#pragma unroll
+          for (int t = 0; t < DLc; t++) y[t] = (t <= m) ? s_Y[t * CP + c] : 0.f;
+#pragma unroll
+          for (int sI = DLc - 1; sI >= 0; sI--) {
+            if (sI <= m) {
+              const int a_s = danc[sI * nvp + i0];
+              const float ys = y[sI] * s_invd[a_s];
+              y[sI] = ys;
+              yz += ys * s_z[a_s];
+#pragma unroll
+              for (int t = 0; t < sI; t++) y[t] -= s_L[a_s * DLP + t] * ys;
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < DLc; t++) if (t <= m) s_Y[t * CP + c] = y[t];
+        } else {
 #pragma unroll 1
-        for (int sI = m; sI >= 0; sI--) {
-          const int a_s = danc[sI * nvp + i0];
-          float y = s_Y[sI * CP + c] * s_invd[a_s];
-          s_Y[sI * CP + c] = y;
-          yz += y * s_z[a_s];
+          for (int sI = m; sI >= 0; sI--) {
+            const int a_s = danc[sI * nvp + i0];
+            float y = s_Y[sI * CP + c] * s_invd[a_s];
+            s_Y[sI * CP + c] = y;
+            yz += y * s_z[a_s];
 #pragma unroll 1
-          for (int t = 0; t < sI; t++) s_Y[t * CP + c] -= s_L[a_s * DLP + t] * y;
+            for (int t = 0; t < sI; t++) s_Y[t * CP + c] -= s_L[a_s * DLP + t] * y;
+          }
         }
         u_c = jv + dt * yz;
         if (d == 2) {
