@@ -13,9 +13,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 PARAM_ORDER = ("dt", "gx", "gy", "gz", "erp", "alpha_init", "alpha_min", "alpha_decay", "max_iter",
-               "threshold", "mu", "restitution", "rest_threshold", "stall_window", "stall_ratio")
+               "threshold", "mu", "restitution", "rest_threshold", "stall_window", "stall_ratio", "warm_start")
 DEFAULT_PARAMS = dict(dt=0.0025, gx=0.0, gy=0.0, gz=-9.81, erp=0.0, alpha_init=1.0, alpha_min=1.0, alpha_decay=1.0,
-                      max_iter=150, threshold=1e-7, mu=0.8, restitution=0.0, rest_threshold=0.01, stall_window=8, stall_ratio=0.5)
+                      max_iter=150, threshold=1e-7, mu=0.8, restitution=0.0, rest_threshold=0.01, stall_window=8, stall_ratio=0.5, warm_start=0)
 
 
 def build(force=False):
@@ -36,7 +36,7 @@ class _ModelDesc(C.Structure):
 
 class _Debug(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("M", "h", "R", "p", "ncontacts", "c_pt", "c_body", "c_pair", "c_pos",
-                                          "c_normal", "c_depth", "c_lambda", "iters", "G", "u0")]
+                                          "c_normal", "c_depth", "c_lambda", "iters", "G", "u0", "warm_pt", "warm_imp")]
 
 
 _lib = None
@@ -80,6 +80,7 @@ class Oracle:
         self.kmax = lib().orc_kmax()
         self.params = dict(DEFAULT_PARAMS)
         self.set_params(**(params or {}))
+        self.warm_pt = self.warm_imp = None      # contact cache carried across step() calls (per environment)
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -111,7 +112,9 @@ class Oracle:
         tau_ff, ptarget, vtarget = f(tau_ff, self.nv), f(ptarget, self.nq), f(vtarget, self.nv)
         g = lambda a: None if a is None else np.ascontiguousarray(np.broadcast_to(np.asarray(a, np.float64), (self.nv,)))
         kp, kd = g(kp), g(kd)
-        dbg, out = None, None
+        if self.warm_pt is None or self.warm_pt.shape[0] != n:
+            self.reset_warm_start(n)
+        out = {}
         if debug:
             K, nb, nv = self.kmax, self.nb, self.nv
             out = dict(M=np.zeros((n, nv, nv)), h=np.zeros((n, nv)), R=np.zeros((n, nb, 3, 3)), p=np.zeros((n, nb, 3)),
@@ -119,10 +122,18 @@ class Oracle:
                        c_pair=np.zeros((n, K), np.int32), c_pos=np.zeros((n, K, 3)), c_normal=np.zeros((n, K, 3)),
                        c_depth=np.zeros((n, K)), c_lambda=np.zeros((n, K, 3)), iters=np.zeros(n, np.int32),
                        G=np.zeros((n, 3 * K, 3 * K)), u0=np.zeros((n, 3 * K)))
-            dbg = _Debug(**{k: v.ctypes.data for k, v in out.items()})
+        ptrs = {k: v.ctypes.data for k, v in out.items()}
+        ptrs["warm_pt"], ptrs["warm_imp"] = self.warm_pt.ctypes.data, self.warm_imp.ctypes.data
+        dbg = _Debug(**ptrs)
         lib().orc_step(self.h, n, n_steps, _p(gc), _p(gv), _p(tau_ff), _p(ptarget), _p(vtarget), _p(kp), _p(kd),
-                       int(nthreads), C.byref(dbg) if dbg is not None else None)
-        return out
+                       int(nthreads), C.byref(dbg))
+        return out if debug else None
+
+    def reset_warm_start(self, n=None):
+        """forget the contact cache (what rsb_batch_set_state does for the environments it touches)"""
+        n = n if n is not None else (self.warm_pt.shape[0] if self.warm_pt is not None else 0)
+        self.warm_pt = np.full((n, self.kmax), -1, np.int32)
+        self.warm_imp = np.zeros((n, self.kmax, 3))
 
     def solve_one(self, G, c, mu):
         G = np.ascontiguousarray(G, np.float64); c = np.ascontiguousarray(c, np.float64)

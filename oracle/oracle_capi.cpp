@@ -24,6 +24,8 @@ struct OrcDebug {       // every pointer optional; sized for n_envs; filled from
   int* iters;           // [n]
   double* G;            // [n][(3*KMAX)^2]  Delassus matrix of the kept contacts (row stride 3*KMAX)
   double* u0;           // [n][3*KMAX]      free contact velocity minus target
+  int* warm_pt;         // [n][KMAX]   IN/OUT contact cache (candidate-point ids, -1 = empty); null = cold start
+  double* warm_imp;     // [n][KMAX*3] IN/OUT world-frame impulses of the cache
 };
 
 struct Handle {
@@ -51,11 +53,19 @@ static void run(Sim<T>& sim, int n_envs, int n_steps, double* gc, double* gv, co
       if (vt) for (int i = 0; i < nv; i++) vtt[i] = T(vt[(size_t)e * nv + i]);
       if (kp) for (int i = 0; i < nv; i++) kpp[i] = T(kp[i]);
       if (kd) for (int i = 0; i < nv; i++) kdd[i] = T(kd[i]);
+      for (int k = 0; k < KMAX; k++) {
+        ws.prev_pt[k] = (dbg && dbg->warm_pt) ? dbg->warm_pt[(size_t)e * KMAX + k] : -1;
+        if (dbg && dbg->warm_imp) ws.prev_imp[k] = {T(dbg->warm_imp[((size_t)e * KMAX + k) * 3]), T(dbg->warm_imp[((size_t)e * KMAX + k) * 3 + 1]), T(dbg->warm_imp[((size_t)e * KMAX + k) * 3 + 2])};
+      }
       for (int s = 0; s < n_steps; s++)
         sim.step(q.data(), v.data(), tau ? tf.data() : nullptr, pt ? ptt.data() : nullptr, vt ? vtt.data() : nullptr,
                  kp ? kpp.data() : nullptr, kd ? kdd.data() : nullptr, ws);
       for (int i = 0; i < nq; i++) gc[(size_t)e * nq + i] = double(q[i]);
       for (int i = 0; i < nv; i++) gv[(size_t)e * nv + i] = double(v[i]);
+      if (dbg && dbg->warm_pt) for (int k = 0; k < KMAX; k++) {
+        dbg->warm_pt[(size_t)e * KMAX + k] = ws.prev_pt[k];
+        if (dbg->warm_imp) { dbg->warm_imp[((size_t)e * KMAX + k) * 3] = double(ws.prev_imp[k].x); dbg->warm_imp[((size_t)e * KMAX + k) * 3 + 1] = double(ws.prev_imp[k].y); dbg->warm_imp[((size_t)e * KMAX + k) * 3 + 2] = double(ws.prev_imp[k].z); }
+      }
       if (dbg) {
         if (dbg->M) for (int i = 0; i < nv * nv; i++) dbg->M[(size_t)e * nv * nv + i] = double(ws.M[i]);
         if (dbg->h) for (int i = 0; i < nv; i++) dbg->h[(size_t)e * nv + i] = double(ws.h[i]);
@@ -94,13 +104,13 @@ void orc_destroy(void* hv) { delete static_cast<Handle*>(hv); }
 
 int orc_kmax() { return KMAX; }
 
-// p = {dt, gx, gy, gz, erp, alpha_init, alpha_min, alpha_decay, max_iter, threshold, mu, restitution, rest_threshold, stall_window, stall_ratio}
+// p = {dt, gx, gy, gz, erp, alpha_init, alpha_min, alpha_decay, max_iter, threshold, mu, restitution, rest_threshold, stall_window, stall_ratio, warm_start}
 void orc_set_params(void* hv, const double* p) {
   Handle* h = static_cast<Handle*>(hv);
   Params prm;
   prm.dt = p[0]; prm.gravity[0] = p[1]; prm.gravity[1] = p[2]; prm.gravity[2] = p[3]; prm.erp = p[4];
   prm.alpha_init = p[5]; prm.alpha_min = p[6]; prm.alpha_decay = p[7]; prm.max_iter = int(p[8]); prm.threshold = p[9];
-  prm.mu = p[10]; prm.restitution = p[11]; prm.rest_threshold = p[12]; prm.stall_window = int(p[13]); prm.stall_ratio = p[14];
+  prm.mu = p[10]; prm.restitution = p[11]; prm.rest_threshold = p[12]; prm.stall_window = int(p[13]); prm.stall_ratio = p[14]; prm.warm_start = int(p[15]);
   if (h->d) h->d->prm = prm; else h->f->prm = prm;
 }
 

@@ -83,6 +83,9 @@ struct Params {
   double restitution = 0.0, rest_threshold = 0.01;
   int stall_window = 8;         // stagnation exit of the Gauss-Seidel loop (0 = off), see include/rsb.h
   double stall_ratio = 0.5;
+  int warm_start = 0;           // EXPERIMENT, oracle only (the kernel starts from zero like the published method): start
+                                // Gauss-Seidel from the previous step's impulses matched by candidate point.  Measured on the
+                                // Atlas-like model standing on box feet: 29 -> 17 iterations, not enough to justify it yet.
 };
 
 struct Terrain {
@@ -112,6 +115,9 @@ template <typename T> struct Workspace {
   std::vector<T> M, Mh, L, h, b, z, Jt, Y, G, u, u0, rhs;
   std::vector<Contact<T>> contacts, all;
   int iters = 0;
+  // warm-start cache: candidate-point id and WORLD-frame impulse of the previous step's contacts
+  int prev_pt[KMAX]; V3<T> prev_imp[KMAX];
+  Workspace() { for (int k = 0; k < KMAX; k++) { prev_pt[k] = -1; prev_imp[k] = {0, 0, 0}; } }
 };
 
 template <typename T> class Sim {
@@ -551,6 +557,23 @@ template <typename T> class Sim {
         }
       }
       for (int a = 0; a < C; a++) ws.u0[a] = ws.u[a];
+      if (prm.warm_start) {
+        for (int i = 0; i < K; i++) {
+          Contact<T>& ct = ws.contacts[i];
+          for (int j = 0; j < KMAX; j++) if (ws.prev_pt[j] == ct.pt) {
+            const V3<T>& w = ws.prev_imp[j];
+            ct.lam = {dot(ct.t1, w), dot(ct.t2, w), dot(ct.n, w)};
+          }
+        }
+        for (int a = 0; a < C; a++) {
+          T s = 0;
+          for (int i = 0; i < K; i++) {
+            const V3<T>& l = ws.contacts[i].lam;
+            s += ws.G[a * C + 3 * i] * l.x + ws.G[a * C + 3 * i + 1] * l.y + ws.G[a * C + 3 * i + 2] * l.z;
+          }
+          ws.u[a] += s;
+        }
+      }
       // a8: Gauss-Seidel over contacts (BisectionContactSolver::solve)
       T alpha = T(prm.alpha_init), mu = T(prm.mu);
       T err_ckpt = T(3.0e38);
@@ -588,6 +611,13 @@ template <typename T> class Sim {
         }
         ws.rhs[r] += s;
       }
+    }
+    for (int k = 0; k < KMAX; k++) {   // contact cache for the next step's warm start
+      if (k < K) {
+        const Contact<T>& ct = ws.contacts[k];
+        ws.prev_pt[k] = ct.pt;
+        ws.prev_imp[k] = ct.lam.x * ct.t1 + ct.lam.y * ct.t2 + ct.lam.z * ct.n;
+      } else ws.prev_pt[k] = -1;
     }
     // a9: v+ = v + L^-T (dt z + Y lam);  q+ = q (+) dt v+
     bwd_solve(ws.L.data(), ws.rhs.data(), nv);
