@@ -131,6 +131,8 @@ int rsb_batch_set_pd_gains(rsb_batch* b, const float* kp, const float* kd);     
 int rsb_batch_set_pd_target(rsb_batch* b, const float* ptarget, const float* vtarget, int env_begin, int env_count, int where);
 int rsb_batch_set_generalized_force(rsb_batch* b, const float* tau, int env_begin, int env_count, int where);
 int rsb_batch_set_control_mode(rsb_batch* b, int mode);
+/* ArticulatedSystem::getGeneralizedForce(): feed-forward + PD force applied over the last integrate() */
+int rsb_batch_get_generalized_force(rsb_batch* b, float* tau, int env_begin, int env_count, int where);
 
 /* ---- the hot path: World::integrate1(), integrate2(), integrate() ----------------------------- */
 int rsb_batch_integrate1(rsb_batch* b);               /* kinematics, collision, M, h (for the getters)   */
@@ -154,6 +156,15 @@ int rsb_batch_observe(rsb_batch* b, float* obs, int env_begin, int env_count, in
 /* VectorizedEnvironment::step() for the whole batch in one call: targets in, `substeps` fused
  * World::integrate() calls, observation rows out (either pointer may be NULL to skip that leg) */
 int rsb_batch_control_step(rsb_batch* b, const float* ptarget, const float* vtarget, int where_in, int substeps, float* obs, int where_out);
+
+/* ---- RaisimGym task on the device (raisimGymTorch VectorizedEnvironment.hpp / envs/rsg_anymal/Environment.hpp,
+ *      [RECALL]): pTarget = action * std + mean; reward = torque_coeff * |tau|^2 + forward_vel_coeff * min(4, v_body_x);
+ *      an episode terminates on any contact whose local body is not in foot_bodies (reward += terminal_reward, state reset) -- */
+int rsb_batch_gym_configure(rsb_batch* b, const float* gc_init, const float* gv_init, const float* action_mean, const float* action_std,
+                            const int32_t* foot_bodies, int n_foot, float torque_coeff, float forward_vel_coeff, float terminal_reward);
+int rsb_batch_gym_reset(rsb_batch* b);                                             /* VectorizedEnvironment::reset() */
+int rsb_batch_gym_step(rsb_batch* b, const float* action, int where_in, int substeps, float* obs, float* reward, unsigned char* done,
+                       int where_out);                                             /* ::step() + ::observe()          */
 
 #ifdef __cplusplus
 }

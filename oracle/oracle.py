@@ -36,7 +36,7 @@ class _ModelDesc(C.Structure):
 
 class _Debug(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("M", "h", "R", "p", "ncontacts", "c_pt", "c_body", "c_pair", "c_pos",
-                                          "c_normal", "c_depth", "c_lambda", "iters", "G", "u0", "warm_pt", "warm_imp")]
+                                          "c_normal", "c_depth", "c_lambda", "iters", "G", "u0", "warm_pt", "warm_imp", "tau_applied")]
 
 
 _lib = None
@@ -121,7 +121,7 @@ class Oracle:
                        ncontacts=np.zeros(n, np.int32), c_pt=np.zeros((n, K), np.int32), c_body=np.zeros((n, K), np.int32),
                        c_pair=np.zeros((n, K), np.int32), c_pos=np.zeros((n, K, 3)), c_normal=np.zeros((n, K, 3)),
                        c_depth=np.zeros((n, K)), c_lambda=np.zeros((n, K, 3)), iters=np.zeros(n, np.int32),
-                       G=np.zeros((n, 3 * K, 3 * K)), u0=np.zeros((n, 3 * K)))
+                       G=np.zeros((n, 3 * K, 3 * K)), u0=np.zeros((n, 3 * K)), tau_applied=np.zeros((n, nv)))
         ptrs = {k: v.ctypes.data for k, v in out.items()}
         ptrs["warm_pt"], ptrs["warm_imp"] = self.warm_pt.ctypes.data, self.warm_imp.ctypes.data
         dbg = _Debug(**ptrs)

@@ -26,6 +26,7 @@ struct OrcDebug {       // every pointer optional; sized for n_envs; filled from
   double* u0;           // [n][3*KMAX]      free contact velocity minus target
   int* warm_pt;         // [n][KMAX]   IN/OUT contact cache (candidate-point ids, -1 = empty); null = cold start
   double* warm_imp;     // [n][KMAX*3] IN/OUT world-frame impulses of the cache
+  double* tau_applied;  // [n][nv]     generalized force applied over the last step
 };
 
 struct Handle {
@@ -69,6 +70,7 @@ static void run(Sim<T>& sim, int n_envs, int n_steps, double* gc, double* gv, co
       if (dbg) {
         if (dbg->M) for (int i = 0; i < nv * nv; i++) dbg->M[(size_t)e * nv * nv + i] = double(ws.M[i]);
         if (dbg->h) for (int i = 0; i < nv; i++) dbg->h[(size_t)e * nv + i] = double(ws.h[i]);
+        if (dbg->tau_applied) for (int i = 0; i < nv; i++) dbg->tau_applied[(size_t)e * nv + i] = double(ws.tau_applied[i]);
         if (dbg->R) for (int i = 0; i < nb; i++) for (int k = 0; k < 9; k++) dbg->R[((size_t)e * nb + i) * 9 + k] = double(ws.R[i].m[k]);
         if (dbg->p) for (int i = 0; i < nb; i++) { dbg->p[((size_t)e * nb + i) * 3] = ws.p[i].x; dbg->p[((size_t)e * nb + i) * 3 + 1] = ws.p[i].y; dbg->p[((size_t)e * nb + i) * 3 + 2] = ws.p[i].z; }
         int K = int(ws.contacts.size());

@@ -112,7 +112,7 @@ template <typename T> struct Workspace {
   std::vector<V3<T>> p, a, w, v, wd, vd, F, N;
   std::vector<T> Ic;             // 10 per body: m, h(3), I_O(6: xx xy xz yy yz zz)
   std::vector<T> S;              // 6 per body: [ang(3); lin_at_O(3)]
-  std::vector<T> M, Mh, L, h, b, z, Jt, Y, G, u, u0, rhs;
+  std::vector<T> M, Mh, L, h, b, z, Jt, Y, G, u, u0, rhs, tau_applied;
   std::vector<Contact<T>> contacts, all;
   int iters = 0;
   // warm-start cache: candidate-point id and WORLD-frame impulse of the previous step's contacts
@@ -170,7 +170,7 @@ template <typename T> class Sim {
     ws.nb = nb; ws.nv = nv;
     ws.R.resize(nb); ws.p.resize(nb); ws.a.resize(nb); ws.w.resize(nb); ws.v.resize(nb); ws.wd.resize(nb); ws.vd.resize(nb);
     ws.F.resize(nb); ws.N.resize(nb); ws.Ic.resize(10 * nb); ws.S.resize(6 * nb);
-    ws.M.resize(nv * nv); ws.Mh.resize(nv * nv); ws.L.resize(nv * nv); ws.h.resize(nv); ws.b.resize(nv); ws.z.resize(nv); ws.rhs.resize(nv);
+    ws.M.resize(nv * nv); ws.Mh.resize(nv * nv); ws.L.resize(nv * nv); ws.h.resize(nv); ws.tau_applied.resize(nv); ws.b.resize(nv); ws.z.resize(nv); ws.rhs.resize(nv);
     ws.Jt.resize(nv * 3 * KMAX); ws.Y.resize(nv * 3 * KMAX); ws.G.resize(9 * KMAX * KMAX); ws.u.resize(3 * KMAX); ws.u0.resize(3 * KMAX);
   }
 
@@ -622,6 +622,16 @@ template <typename T> class Sim {
     // a9: v+ = v + L^-T (dt z + Y lam);  q+ = q (+) dt v+
     bwd_solve(ws.L.data(), ws.rhs.data(), nv);
     for (int i = 0; i < nv; i++) gv[i] += ws.rhs[i];
+    // generalized force applied over this step (implicit PD at q + dt v+, v+): ArticulatedSystem::getGeneralizedForce()
+    for (int i = 0; i < nv; i++) ws.tau_applied[i] = tau_ff ? tau_ff[i] : T(0);
+    for (int i = 1; i < nb; i++) {
+      int vi = vidx[i], qi = qidx[i];
+      T kpi = kp ? kp[vi] : T(0), kdi = kd ? kd[vi] : T(0);
+      if (kpi != T(0) || kdi != T(0)) {
+        T qt = ptarget ? ptarget[qi] : T(0), vt = vtarget ? vtarget[vi] : T(0);
+        ws.tau_applied[vi] += kpi * (qt - gc[qi] - dt * gv[vi]) + kdi * (vt - gv[vi]);
+      }
+    }
     if (floating) {
       for (int k = 0; k < 3; k++) gc[k] += dt * gv[k];
       V3<T> w = {gv[3], gv[4], gv[5]};

@@ -57,11 +57,12 @@ EXPORTED = [
     "rsb_batch_create", "rsb_batch_destroy", "rsb_batch_set_stream", "rsb_batch_sync", "rsb_batch_num_envs",
     "rsb_batch_set_ground", "rsb_batch_set_heightmap", "rsb_batch_clear_terrain", "rsb_batch_set_params", "rsb_batch_get_params",
     "rsb_batch_set_state", "rsb_batch_get_state", "rsb_batch_set_pd_gains", "rsb_batch_set_pd_target",
-    "rsb_batch_set_generalized_force", "rsb_batch_set_control_mode",
+    "rsb_batch_set_generalized_force", "rsb_batch_set_control_mode", "rsb_batch_get_generalized_force",
     "rsb_batch_integrate1", "rsb_batch_integrate2", "rsb_batch_integrate",
     "rsb_batch_get_mass_matrix", "rsb_batch_get_nonlinearities", "rsb_batch_get_body_poses", "rsb_batch_get_contacts",
     "rsb_batch_get_contact_points", "rsb_batch_get_solver_iterations", "rsb_batch_device_ptrs", "rsb_batch_launch_count",
     "rsb_batch_ob_dim", "rsb_batch_observe", "rsb_batch_control_step",
+    "rsb_batch_gym_configure", "rsb_batch_gym_reset", "rsb_batch_gym_step",
 ]
 
 _lib = None
@@ -102,6 +103,7 @@ def lib():
         L.rsb_batch_set_pd_gains.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rsb_batch_set_generalized_force.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.rsb_batch_set_control_mode.argtypes = [C.c_void_p, C.c_int]
+        L.rsb_batch_get_generalized_force.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.rsb_batch_integrate1.argtypes = [C.c_void_p]
         L.rsb_batch_integrate2.argtypes = [C.c_void_p]
         L.rsb_batch_integrate.argtypes = [C.c_void_p, C.c_int]
@@ -116,6 +118,9 @@ def lib():
         L.rsb_batch_ob_dim.argtypes = [C.c_void_p]
         L.rsb_batch_observe.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.rsb_batch_control_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.rsb_batch_gym_configure.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int, C.c_float, C.c_float, C.c_float]
+        L.rsb_batch_gym_reset.argtypes = [C.c_void_p]
+        L.rsb_batch_gym_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -258,6 +263,12 @@ class Batch:
         p, w = _ptr(tau)
         _ck(lib().rsb_batch_set_generalized_force(self.h, p, env_begin, n, w))
 
+    def generalized_force(self, env_begin=0, env_count=None):
+        n = self.n - env_begin if env_count is None else env_count
+        out = np.empty((n, self.nv), np.float32)
+        _ck(lib().rsb_batch_get_generalized_force(self.h, out.ctypes.data_as(C.c_void_p), env_begin, n, HOST))
+        return out
+
     def set_control_mode(self, mode):
         _ck(lib().rsb_batch_set_control_mode(self.h, mode))
 
@@ -325,6 +336,20 @@ class Batch:
         pp, w1 = _ptr(ptarget); pv, _ = _ptr(vtarget); po, w2 = _ptr(obs_out)
         _ck(lib().rsb_batch_control_step(self.h, pp, pv, w1, substeps, po, w2))
         return obs_out
+
+    # RaisimGym task (VectorizedEnvironment)
+    def gym_configure(self, gc_init, gv_init, action_mean, action_std, foot_bodies, torque_coeff=-4e-5, forward_vel_coeff=0.3, terminal_reward=-10.0):
+        f = lambda a: np.ascontiguousarray(a, np.float32)
+        a, b_, c, d = f(gc_init), f(gv_init), f(action_mean), f(action_std)
+        fb = np.ascontiguousarray(foot_bodies, np.int32)
+        _ck(lib().rsb_batch_gym_configure(self.h, *[x.ctypes.data_as(C.c_void_p) for x in (a, b_, c, d, fb)], len(fb), torque_coeff, forward_vel_coeff, terminal_reward))
+
+    def gym_reset(self):
+        _ck(lib().rsb_batch_gym_reset(self.h))
+
+    def gym_step(self, action, substeps, obs, reward, done):
+        pa, w1 = _ptr(action); po, w2 = _ptr(obs); pr, _ = _ptr(reward); pd, _ = _ptr(done)
+        _ck(lib().rsb_batch_gym_step(self.h, pa, w1, substeps, po, pr, pd, w2))
 
     def observe(self, out=None, env_begin=0, env_count=None):
         n = self.n - env_begin if env_count is None else env_count

@@ -37,7 +37,7 @@ struct rsb_batch {
   int control_mode = RSB_PD_PLUS_FEEDFORWARD_TORQUE;
   bool pd_set = false;
   // device buffers
-  float *gc = nullptr, *gv = nullptr, *tau = nullptr, *pt = nullptr, *vt = nullptr;
+  float *gc = nullptr, *gv = nullptr, *tau = nullptr, *pt = nullptr, *vt = nullptr, *tau_applied = nullptr;
   int *ncontacts = nullptr, *contact_pt = nullptr, *iters = nullptr;
   rsb_contact* contacts = nullptr;
   float *dbg_M = nullptr, *dbg_h = nullptr, *dbg_R = nullptr, *dbg_p = nullptr;
@@ -58,6 +58,12 @@ struct rsb_batch {
   int wpc = 0, grid = 0;
   size_t smem_bytes = 0;
   int64_t launches = 0;
+  // RaisimGym task state (rsb_batch_gym_*)
+  float* gym_const = nullptr;     // device: gc_init | gv_init | action_mean | action_std
+  GymConfig gym{};
+  bool gym_ready = false;
+  float *gym_action = nullptr, *gym_obs = nullptr, *gym_reward = nullptr;
+  unsigned char* gym_done = nullptr;
 };
 
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -210,6 +216,7 @@ static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug) {
   a.ptarget = b->pt; a.vtarget = b->vt;
   a.prm = b->prm; a.ter = b->ter; a.ws = b->ws;
   a.blob_words = (int)b->blob_host.size(); a.blob = b->blob;
+  a.tau_applied = b->tau_applied;
   a.ncontacts = b->ncontacts; a.contacts = b->contacts; a.contact_pt = b->contact_pt; a.iters = b->iters;
   if (debug) { a.dbg_M = b->dbg_M; a.dbg_h = b->dbg_h; a.dbg_R = b->dbg_R; a.dbg_p = b->dbg_p; }
   a.phase_mask = phase_mask;
@@ -361,6 +368,7 @@ int rsb_batch_create(const rsb_model* m, int num_envs, int device, rsb_batch** o
   if (e == cudaSuccess) e = alloc((void**)&b->tau, N * b->gv_stride * 4);
   if (e == cudaSuccess) e = alloc((void**)&b->pt, N * b->gc_stride * 4);
   if (e == cudaSuccess) e = alloc((void**)&b->vt, N * b->gv_stride * 4);
+  if (e == cudaSuccess) e = alloc((void**)&b->tau_applied, N * b->gv_stride * 4);
   if (e == cudaSuccess) e = alloc((void**)&b->ncontacts, N * 4);
   if (e == cudaSuccess) e = alloc((void**)&b->contact_pt, N * KMAX * 4);
   if (e == cudaSuccess) e = alloc((void**)&b->iters, N * 4);
@@ -384,8 +392,9 @@ void rsb_batch_destroy(rsb_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
-  for (void* p : {(void*)b->gc, (void*)b->gv, (void*)b->tau, (void*)b->pt, (void*)b->vt, (void*)b->ncontacts, (void*)b->contact_pt, (void*)b->iters,
-                  (void*)b->contacts, (void*)b->dbg_M, (void*)b->dbg_h, (void*)b->dbg_R, (void*)b->dbg_p, (void*)b->hmap, (void*)b->staging, (void*)b->obs_staging, (void*)b->blob})
+  for (void* p : {(void*)b->tau_applied, (void*)b->gc, (void*)b->gv, (void*)b->tau, (void*)b->pt, (void*)b->vt, (void*)b->ncontacts, (void*)b->contact_pt, (void*)b->iters,
+                  (void*)b->contacts, (void*)b->dbg_M, (void*)b->dbg_h, (void*)b->dbg_R, (void*)b->dbg_p, (void*)b->hmap, (void*)b->staging, (void*)b->obs_staging, (void*)b->blob, (void*)b->gym_const, (void*)b->gym_action,
+                  (void*)b->gym_obs, (void*)b->gym_reward, (void*)b->gym_done})
     if (p) cudaFree(p);
   if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
   delete b;
@@ -477,6 +486,12 @@ int rsb_batch_set_pd_target(rsb_batch* b, const float* ptarget, const float* vta
 int rsb_batch_set_generalized_force(rsb_batch* b, const float* tau, int env_begin, int env_count, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
   return copy_rows_in(b, b->tau, b->gv_stride, tau, b->nv, env_begin, env_count, where);
+}
+int rsb_batch_get_generalized_force(rsb_batch* b, float* tau, int env_begin, int env_count, int where) {
+  int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  rc = copy_rows_out(b, tau, b->tau_applied, b->gv_stride, b->nv, env_begin, env_count, where); if (rc) return rc;
+  if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
+  return RSB_OK;
 }
 int rsb_batch_set_control_mode(rsb_batch* b, int mode) {
   if (!b || (mode != RSB_FORCE_AND_TORQUE && mode != RSB_PD_PLUS_FEEDFORWARD_TORQUE)) return fail(RSB_ERR_INVALID, "bad control mode");
@@ -611,6 +626,85 @@ int rsb_batch_control_step(rsb_batch* b, const float* ptarget, const float* vtar
   rc = copy_rows_in(b, b->vt, b->gv_stride, vtarget, b->nv, 0, b->N, where_in); if (rc) return rc;
   rc = do_launch(b, substeps, 0, false); if (rc) return rc;
   if (obs) return observe_impl(b, obs, 0, b->N, where_out, true);
+  return RSB_OK;
+}
+
+// ---- RaisimGym ANYmal task: VectorizedEnvironment::{reset, step, observe} for the whole batch ----
+int rsb_batch_gym_configure(rsb_batch* b, const float* gc_init, const float* gv_init, const float* action_mean, const float* action_std,
+                            const int32_t* foot_bodies, int n_foot, float torque_coeff, float forward_vel_coeff, float terminal_reward) {
+  if (!b || !gc_init || !gv_init || !action_mean || !action_std || (n_foot > 0 && !foot_bodies)) return fail(RSB_ERR_INVALID, "null argument");
+  if (!b->model->md.floating) return fail(RSB_ERR_UNSUPPORTED, "the gym task needs a floating-base robot");
+  CK(cudaSetDevice(b->device));
+  const int nq = b->nq, nv = b->nv, nj = nq - 7;
+  std::vector<float> h((size_t)nq + nv + 2 * nj);
+  std::memcpy(h.data(), gc_init, nq * 4); std::memcpy(h.data() + nq, gv_init, nv * 4);
+  std::memcpy(h.data() + nq + nv, action_mean, nj * 4); std::memcpy(h.data() + nq + nv + nj, action_std, nj * 4);
+  if (!b->gym_const) {
+    CK(cudaMalloc((void**)&b->gym_const, h.size() * 4));
+    CK(cudaMalloc((void**)&b->gym_action, (size_t)b->N * nj * 4));
+    CK(cudaMalloc((void**)&b->gym_obs, (size_t)b->N * rsb_batch_ob_dim(b) * 4));
+    CK(cudaMalloc((void**)&b->gym_reward, (size_t)b->N * 4));
+    CK(cudaMalloc((void**)&b->gym_done, (size_t)b->N));
+  }
+  CK(cudaMemcpyAsync(b->gym_const, h.data(), h.size() * 4, cudaMemcpyHostToDevice, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  b->gym.gc_init = b->gym_const; b->gym.gv_init = b->gym_const + nq; b->gym.action_mean = b->gym_const + nq + nv; b->gym.action_std = b->gym_const + nq + nv + nj;
+  b->gym.foot_mask = 0;
+  for (int i = 0; i < n_foot; i++) {
+    if (foot_bodies[i] < 0 || foot_bodies[i] >= b->nb) return fail(RSB_ERR_INVALID, "foot body index out of range");
+    b->gym.foot_mask |= 1u << foot_bodies[i];
+  }
+  b->gym.torque_coeff = torque_coeff; b->gym.forward_vel_coeff = forward_vel_coeff; b->gym.terminal_reward = terminal_reward;
+  b->gym_ready = true;
+  return RSB_OK;
+}
+
+// ENVIRONMENT::reset() for every environment: state and PD target back to the initial configuration
+int rsb_batch_gym_reset(rsb_batch* b) {
+  if (!b || !b->gym_ready) return fail(RSB_ERR_INVALID, "call rsb_batch_gym_configure() first");
+  CK(cudaSetDevice(b->device));
+  int threads = 128, blocks = (b->N * 32 + threads - 1) / threads;
+  rsb_gym_reset_kernel<<<blocks, threads, 0, b->stream>>>(b->gc, b->gv, b->pt, b->vt, b->gym, b->gc_stride, b->gv_stride, b->nq, b->nv, b->N);
+  CK(cudaGetLastError());
+  b->launches++;
+  return RSB_OK;
+}
+
+// VectorizedEnvironment::step(action, reward, done) + observe(ob): action rows [N][nq-7] in; `substeps` fused
+// World::integrate() calls; reward [N], done [N] (uint8) and observation rows [N][ob_dim] out.
+int rsb_batch_gym_step(rsb_batch* b, const float* action, int where_in, int substeps, float* obs, float* reward, unsigned char* done, int where_out) {
+  if (!b || !b->gym_ready) return fail(RSB_ERR_INVALID, "call rsb_batch_gym_configure() first");
+  if (!action || substeps < 1) return fail(RSB_ERR_INVALID, "bad arguments to rsb_batch_gym_step");
+  CK(cudaSetDevice(b->device));
+  const int nj = b->nq - 7, od = rsb_batch_ob_dim(b);
+  const float* act = action;
+  if (where_in == RSB_HOST) {
+    CK(cudaMemcpyAsync(b->gym_action, action, (size_t)b->N * nj * 4, cudaMemcpyHostToDevice, b->stream));
+    act = b->gym_action;
+  }
+  {
+    int threads = 256, blocks = (b->N * nj + threads - 1) / threads;
+    rsb_gym_action_kernel<<<blocks, threads, 0, b->stream>>>(act, b->gym, b->nq, b->gc_stride, b->N, b->pt);
+    CK(cudaGetLastError());
+    b->launches++;
+  }
+  int rc = do_launch(b, substeps, 0, false); if (rc) return rc;
+  float* d_obs = (where_out == RSB_HOST || !obs) ? b->gym_obs : obs;
+  float* d_rew = (where_out == RSB_HOST || !reward) ? b->gym_reward : reward;
+  unsigned char* d_done = (where_out == RSB_HOST || !done) ? b->gym_done : done;
+  {
+    int threads = 128, blocks = (b->N * 32 + threads - 1) / threads;
+    rsb_gym_post_kernel<<<blocks, threads, 0, b->stream>>>(b->gc, b->gv, b->tau_applied, b->pt, b->ncontacts, b->contacts, b->gym, b->gc_stride, b->gv_stride,
+                                                            b->nq, b->nv, b->N, d_obs, od, d_rew, d_done);
+    CK(cudaGetLastError());
+    b->launches++;
+  }
+  if (where_out == RSB_HOST) {
+    if (obs) CK(cudaMemcpyAsync(obs, d_obs, (size_t)b->N * od * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (reward) CK(cudaMemcpyAsync(reward, d_rew, (size_t)b->N * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (done) CK(cudaMemcpyAsync(done, d_done, (size_t)b->N, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+  }
   return RSB_OK;
 }
 

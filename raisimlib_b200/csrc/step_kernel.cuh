@@ -158,6 +158,7 @@ struct StepArgs {
   rsb_contact* contacts;
   int* contact_pt;     // [N][KMAX]
   int* iters;          // [N]
+  float* tau_applied;  // [N][gv_stride] generalized force actually applied in the last sub-step (getGeneralizedForce)
   float *dbg_M, *dbg_h, *dbg_R, *dbg_p;   // optional (integrate1 / getters)
   int phase_mask;      // bit0: stop after stage C (integrate1: no state update)
 };
@@ -958,7 +959,17 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
         __syncwarp();
       }
 #pragma unroll 1
-      for (int i = lane; i < nv; i += 32) s_gv[i] += s_rhs[i];
+      for (int i = lane; i < nv; i += 32) {
+        const float vp = s_gv[i] + s_rhs[i];
+        s_gv[i] = vp;
+        // generalized force applied over this step (implicit PD evaluated at q + dt v+, v+): getGeneralizedForce()
+        float ta = s_tau[i];
+        if (args.use_pd) {
+          const float kpi = kp[i], kdi = kd[i];
+          if (kpi != 0.f || kdi != 0.f) { const int qi = dofq[i]; ta += kpi * (s_pt[qi] - s_gc[qi] - dt * vp) + kdi * (s_vt[i] - vp); }
+        }
+        s_b[i] = ta;
+      }
       __syncwarp();
       if (floating) {
         if (lane < 3) s_gc[lane] += dt * s_gv[lane];
@@ -991,7 +1002,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
 #pragma unroll 1
       for (int i = lane; i < nq; i += 32) g_gc[i] = s_gc[i];
 #pragma unroll 1
-      for (int i = lane; i < nv; i += 32) g_gv[i] = s_gv[i];
+      for (int i = lane; i < nv; i += 32) { g_gv[i] = s_gv[i]; args.tau_applied[(size_t)env * args.gv_stride + i] = s_b[i]; }
     }
     if (lane == 0) { args.ncontacts[env] = K; args.iters[env] = iters; }
     if (lane < KMAX) {
