@@ -29,7 +29,7 @@ namespace orc {
 constexpr int JT_FIXED = 0, JT_REVOLUTE = 1, JT_PRISMATIC = 2, JT_FLOATING = 3;
 constexpr int KMAX = 8;            // contacts kept per environment (deepest KMAX of the candidates) == RSB_KMAX
 constexpr int NSEC = 32;           // sections per refinement round of the slip search
-constexpr int NROUNDS = 4;         // rounds: bracket 2*pi/32^r
+constexpr int NROUNDS = 3;         // rounds: bracket 2*pi/32^(r+1), then one secant step (error ~ bracket^2 = 4e-8 rad)
 
 template <typename T> struct V3 { T x, y, z; };
 template <typename T> inline V3<T> operator+(V3<T> a, V3<T> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }

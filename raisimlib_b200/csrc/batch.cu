@@ -220,6 +220,11 @@ static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug) {
   a.ncontacts = b->ncontacts; a.contacts = b->contacts; a.contact_pt = b->contact_pt; a.iters = b->iters;
   if (debug) { a.dbg_M = b->dbg_M; a.dbg_h = b->dbg_h; a.dbg_R = b->dbg_R; a.dbg_p = b->dbg_p; }
   a.phase_mask = phase_mask;
+  {
+    const char* e = getenv("RSB_SUBSTEP_BARRIER");
+    const int level = e ? atoi(e) : 1;
+    a.substep_barrier = ((size_t)b->grid * b->wpc >= (size_t)b->N && phase_mask == 0) ? level : 0;
+  }
   cudaError_t e;
   switch (b->wpc) {
     case 28: e = dispatch_spec<28>(b, a); break;

@@ -33,7 +33,7 @@ constexpr int CMAX = 3 * KMAX;      // contact rows
 constexpr int CP = CMAX + 1;        // Y row stride: columns 0..C-1 = contact rows, column C = b
 constexpr int GP = CMAX + 1;        // G row stride (odd: conflict-free row access by lane)
 constexpr int NSEC = 32;
-constexpr int NROUNDS = 4;
+constexpr int NROUNDS = 3;         // 32-section rounds: bracket 2*pi/32^(r+1); the closing secant step is then exact to float32
 constexpr int SEC_STRIDE = 36;      // (NSEC+1) padded
 constexpr int CT_WORDS = 16;        // per-contact shared record
 constexpr int MAX_PT_SLOTS = 2;     // candidate points per lane (npts <= 64)
@@ -81,7 +81,7 @@ __host__ __device__ constexpr BlobHeader make_blob_header(Dims d, int npts, int 
   H.off_anc = off; off += max_c(1, d.maxdepth) * H.nbp;
   H.off_gain = off; off += 2 * H.nvp;
   H.off_dofq = off; off += H.nvp;
-  H.off_sec = off; off += 2 * 4 * 36;
+  H.off_sec = off; off += 2 * NROUNDS * SEC_STRIDE;
   H.off_ddepth = off; off += H.nvp;
   H.off_dsub = off; off += H.nvp;
   H.off_danc = off; off += DL * H.nvp;
@@ -161,6 +161,7 @@ struct StepArgs {
   float* tau_applied;  // [N][gv_stride] generalized force actually applied in the last sub-step (getGeneralizedForce)
   float *dbg_M, *dbg_h, *dbg_R, *dbg_p;   // optional (integrate1 / getters)
   int phase_mask;      // bit0: stop after stage C (integrate1: no state update)
+  int substep_barrier; // 1: re-align the CTA's warps at every sub-step (instruction-cache locality experiment)
 };
 
 // ------------------------------------------------------------------ small device math ----------
@@ -218,7 +219,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 
 // ------------------------------------------------------------------ slip search ----------------
 // One probe of the (cone surface) x (zero normal velocity) curve; see oracle solve_one().
-struct Probe { float g, f, lx, ly, lz; bool ok; };
+struct Probe { float g, lx, ly, lz; bool ok; };
 __device__ __forceinline__ Probe slip_probe(float cs, float sn, float a, float b, float cc, float d, float e, float f, f3 c, float mu) {
   Probe p;
   float D = f + mu * (cc * cs + e * sn);
@@ -228,8 +229,13 @@ __device__ __forceinline__ Probe slip_probe(float cs, float sn, float a, float b
   float vx = c.x + a * p.lx + b * p.ly + cc * lz;
   float vy = c.y + b * p.lx + d * p.ly + e * lz;
   p.g = (-vx * sn + vy * cs) * D - mu * (-cc * sn + e * cs) * (vx * cs + vy * sn);
-  p.f = c.x * p.lx + c.y * p.ly + c.z * lz + 0.5f * (p.lx * vx + p.ly * vy - lz * c.z) - 0.5f * (c.x * p.lx + c.y * p.ly);
   return p;
+}
+// energy c.lam + 1/2 lam^T G lam of a probe (only needed to rank several sign changes: rare)
+__device__ __forceinline__ float slip_energy(const Probe& p, float a, float b, float cc, float d, float e, f3 c) {
+  float vx = c.x + a * p.lx + b * p.ly + cc * p.lz;
+  float vy = c.y + b * p.lx + d * p.ly + e * p.lz;
+  return c.x * p.lx + c.y * p.ly + c.z * p.lz + 0.5f * (p.lx * vx + p.ly * vy - p.lz * c.z) - 0.5f * (c.x * p.lx + c.y * p.ly);
 }
 
 // Per-contact rule (opening / stick / slip).  G = [a b cc; b d e; cc e f], Gi = its inverse (sym, 6),
@@ -242,7 +248,6 @@ __device__ __forceinline__ f3 solve_contact(const float* Gs, const float* Gi, f3
   const float a = Gs[0], b = Gs[1], cc = Gs[2], d = Gs[3], e = Gs[4], f = Gs[5];
   float base_c = 1.f, base_s = 0.f;
   float lo_c = 1.f, lo_s = 0.f, hi_c = 1.f, hi_s = 0.f, glo = 0.f, ghi = 0.f;
-  f3 best = mk(0.f, 0.f, 0.f);
   bool have = false;
 #pragma unroll 1
   for (int r = 0; r < NROUNDS; r++) {
@@ -255,21 +260,18 @@ __device__ __forceinline__ f3 solve_contact(const float* Gs, const float* Gi, f3
     float g_next = __shfl_down_sync(FULL, p.g, 1);
     bool ok_next = __shfl_down_sync(FULL, (int)p.ok, 1) != 0;
     float cs_next = __shfl_down_sync(FULL, cs, 1), sn_next = __shfl_down_sync(FULL, sn, 1);
-    {
+    if (r == 0) {   // full circle: the direction after probe 31 is probe 0 again
       float g0 = __shfl_sync(FULL, p.g, 0), c0 = __shfl_sync(FULL, cs, 0), s0 = __shfl_sync(FULL, sn, 0);
       bool ok0 = __shfl_sync(FULL, (int)p.ok, 0) != 0;
-      if (lane == NSEC - 1) {
-        if (r == 0) { g_next = g0; ok_next = ok0; cs_next = c0; sn_next = s0; }
-        else { g_next = ghi; ok_next = true; cs_next = hi_c; sn_next = hi_s; }
-      }
-    }
+      if (lane == NSEC - 1) { g_next = g0; ok_next = ok0; cs_next = c0; sn_next = s0; }
+    } else if (lane == NSEC - 1) { g_next = ghi; ok_next = true; cs_next = hi_c; sn_next = hi_s; }
     bool cand = p.ok && ok_next && (p.g < 0.f) && (g_next >= 0.f);
     unsigned m = __ballot_sync(FULL, cand);
     if (m == 0u) {
       if (!have) {   // no bracket on the whole circle: least-energy probe (lowest index on ties)
         unsigned okm = __ballot_sync(FULL, p.ok);
         if (okm == 0u) return mk(0.f, 0.f, fmaxf(0.f, -c.z / f));
-        float fv = p.ok ? p.f : 3.0e38f;
+        float fv = p.ok ? slip_energy(p, a, b, cc, d, e, c) : 3.0e38f;
         float fm = fv;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) fm = fminf(fm, __shfl_xor_sync(FULL, fm, o));
@@ -283,7 +285,7 @@ __device__ __forceinline__ f3 solve_contact(const float* Gs, const float* Gi, f3
     int pick;
     if ((m & (m - 1)) == 0u) pick = __ffs(m) - 1;
     else {
-      float fv = cand ? p.f : 3.0e38f;
+      float fv = cand ? slip_energy(p, a, b, cc, d, e, c) : 3.0e38f;
       float fm = fv;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) fm = fminf(fm, __shfl_xor_sync(FULL, fm, o));
@@ -293,7 +295,6 @@ __device__ __forceinline__ f3 solve_contact(const float* Gs, const float* Gi, f3
     lo_c = __shfl_sync(FULL, cs, pick); lo_s = __shfl_sync(FULL, sn, pick);
     hi_c = __shfl_sync(FULL, cs_next, pick); hi_s = __shfl_sync(FULL, sn_next, pick);
     glo = __shfl_sync(FULL, p.g, pick); ghi = __shfl_sync(FULL, g_next, pick);
-    best = mk(__shfl_sync(FULL, p.lx, pick), __shfl_sync(FULL, p.ly, pick), __shfl_sync(FULL, p.lz, pick));
     base_c = lo_c; base_s = lo_s; have = true;
   }
   float tt = (ghi - glo) != 0.f ? (-glo / (ghi - glo)) : 0.5f;
@@ -301,7 +302,9 @@ __device__ __forceinline__ f3 solve_contact(const float* Gs, const float* Gi, f3
   float inv = 1.0f / sqrtf(cs * cs + sn * sn);
   cs *= inv; sn *= inv;
   Probe p = slip_probe(cs, sn, a, b, cc, d, e, f, c, mu);
-  return p.ok ? mk(p.lx, p.ly, p.lz) : best;
+  if (p.ok) return mk(p.lx, p.ly, p.lz);
+  p = slip_probe(lo_c, lo_s, a, b, cc, d, e, f, c, mu);   // lower bracket end (valid by construction)
+  return mk(p.lx, p.ly, p.lz);
 }
 
 // ------------------------------------------------------------------ terrain --------------------
@@ -452,6 +455,11 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
 
 #pragma unroll 1
     for (int sub = 0; sub < args.substeps; sub++) {
+      // Re-align the CTA's warps (instruction-cache locality: 28 warps drifting through a 75 KB kernel miss the
+      // instruction cache far more often than 28 warps in the same stage).  Only set by the host when every warp
+      // owns exactly one environment, so all of them reach the barrier the same number of times.
+      const int bar_threads = min(WPC, args.num_envs - (int)blockIdx.x * WPC) * 32;
+      if (args.substep_barrier >= 1) asm volatile("bar.sync 1, %0;" ::"r"(bar_threads));
       // =========================== stage A: FK + RNEA + CRBA =====================================
       float R[9]; f3 p, w, v, wd, vd, ax;
       if (floating) {
@@ -688,6 +696,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
       const int C = 3 * K;
       if (args.phase_mask & 1) { __syncwarp(); break; }   // integrate1(): kinematics, collision, M, h only
 
+      if (args.substep_barrier >= 2) asm volatile("bar.sync 1, %0;" ::"r"(bar_threads));
       // =========================== stage C: b, Mhat = L^T L, z, Y, G ==============================
 #pragma unroll 1
       for (int i = lane; i < nv; i += 32) {
@@ -922,6 +931,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
         __syncwarp();
       }
       __syncwarp();
+      if (args.substep_barrier >= 3) asm volatile("bar.sync 1, %0;" ::"r"(bar_threads));
       // =========================== stage E: v+ = v + L^-1 (dt z + Y lam), integration ============
 #pragma unroll 1
       for (int i = lane; i < nv; i += 32) {   // w = dt z + Y lam, gathered per dof over the contacts whose chain holds it
