@@ -120,19 +120,19 @@ def cpu_baseline(sample_envs, max_steps, budget_s=12.0):
     from oracle.urdf_tables import load_tables
     from raisimlib_b200 import RSC_DIR
     H, gc, gv, targets, kp, kd = make_workload(0, sample_envs)
-    o = Oracle(load_tables(os.path.join(RSC_DIR, "anymal_c_like.urdf")), params=dict(threshold=1e-6))
+    o = Oracle(load_tables(os.path.join(RSC_DIR, "anymal_c_like.urdf")), params=dict(threshold=1e-6, slip_bisect=1))   # CPU-tuned slip search
     o.set_heightmap(HM["xs"], HM["ys"], HM["size"], HM["size"], 0.0, 0.0, H.astype(np.float64))
     cores = os.cpu_count()
     vt = np.zeros((sample_envs, 18))
-    for k in range(20):     # warm-up: robots land on the terrain
-        o.step(gc, gv, n_steps=SUBSTEPS, ptarget=targets[k % RING], vtarget=vt, kp=kp, kd=kd)
+    for k in range(30):     # warm-up: robots land on the terrain and settle (the GPU arm's timed region is the settled phase too)
+        o.step(gc, gv, n_steps=SUBSTEPS, ptarget=targets[k % RING], vtarget=vt, kp=kp, kd=kd, nthreads=cores)
     t0 = time.perf_counter(); done = 0; k = 0
     while done < max_steps and time.perf_counter() - t0 < budget_s:
-        o.step(gc, gv, n_steps=SUBSTEPS, ptarget=targets[k % RING], vtarget=vt, kp=kp, kd=kd)
+        o.step(gc, gv, n_steps=SUBSTEPS, ptarget=targets[k % RING], vtarget=vt, kp=kp, kd=kd, nthreads=cores)
         done += SUBSTEPS; k += 1
     dt = time.perf_counter() - t0
     return {"value": sample_envs * done / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{sample_envs} envs x {done} sub-steps of the same workload (float64 oracle, OpenMP over envs, after 80 warm-up sub-steps)"}
+            "sample": f"{sample_envs} envs x {done} sub-steps of the same workload (float64 oracle, bisection slip search, OpenMP over envs, after 120 warm-up sub-steps)"}
 
 
 def run_reference(args):
@@ -145,17 +145,17 @@ def run_reference(args):
     from raisimlib_b200 import RSC_DIR
     n = ENVS_PER_GPU
     H, gc, gv, targets, kp, kd = make_workload(0, n)
-    o = Oracle(load_tables(os.path.join(RSC_DIR, "anymal_c_like.urdf")), params=dict(threshold=1e-6))
+    o = Oracle(load_tables(os.path.join(RSC_DIR, "anymal_c_like.urdf")), params=dict(threshold=1e-6, slip_bisect=1))   # CPU-tuned slip search
     o.set_heightmap(HM["xs"], HM["ys"], HM["size"], HM["size"], 0.0, 0.0, H.astype(np.float64))
     vt = np.zeros((n, 18))
+    cores = os.cpu_count()          # explicit: torchrun exports OMP_NUM_THREADS=1
     for k in range(max(args.warmup, 3)):
-        o.step(gc, gv, n_steps=SUBSTEPS, ptarget=targets[k % RING], vtarget=vt, kp=kp, kd=kd)
+        o.step(gc, gv, n_steps=SUBSTEPS, ptarget=targets[k % RING], vtarget=vt, kp=kp, kd=kd, nthreads=cores)
     t0 = time.perf_counter()
     for k in range(args.steps):
-        o.step(gc, gv, n_steps=SUBSTEPS, ptarget=targets[k % RING], vtarget=vt, kp=kp, kd=kd)
+        o.step(gc, gv, n_steps=SUBSTEPS, ptarget=targets[k % RING], vtarget=vt, kp=kp, kd=kd, nthreads=cores)
     dt = time.perf_counter() - t0
     val = n * SUBSTEPS * args.steps / dt
-    cores = os.cpu_count()
     line = {"impl": "reference", "metric": "env-steps/s", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -321,7 +321,7 @@ def main():
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(1024, 400)
+            line["cpu_baseline"] = cpu_baseline(n, 400)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -83,6 +83,9 @@ struct Params {
   double restitution = 0.0, rest_threshold = 0.01;
   int stall_window = 8;         // stagnation exit of the Gauss-Seidel loop (0 = off), see include/rsb.h
   double stall_ratio = 0.5;
+  int slip_bisect = 0;          // 1: after the first 32-probe round, refine the bracket by plain bisection (what a CPU
+                                // implementation of the published method does); 0: 32-section rounds, probe-for-probe the
+                                // kernel's search.  Both end in the same bracket width; results agree to ~1e-7.
   int warm_start = 0;           // EXPERIMENT, oracle only (the kernel starts from zero like the published method): start
                                 // Gauss-Seidel from the previous step's impulses matched by candidate point.  Measured on the
                                 // Atlas-like model standing on box feet: 29 -> 17 iterations, not enough to justify it yet.
@@ -466,7 +469,7 @@ template <typename T> class Sim {
     V3<T> best = {0, 0, 0};
     bool have = false;
     T glo = 0, ghi = 0; T lo_c = 1, lo_s = 0, hi_c = 1, hi_s = 0;
-    for (int r = 0; r < NROUNDS; r++) {
+    for (int r = 0; r < (prm.slip_bisect ? 1 : NROUNDS); r++) {
       T gk[NSEC + 1], fk[NSEC + 1]; bool ok[NSEC + 1]; V3<T> lk[NSEC + 1];
       T dc[NSEC + 1], ds[NSEC + 1];
       for (int k = 0; k < NSEC; k++) {
@@ -497,6 +500,16 @@ template <typename T> class Sim {
       T cs0 = dc[pick], sn0 = ds[pick], cs1 = dc[pick + 1], sn1 = ds[pick + 1];
       lo_c = cs0; lo_s = sn0; hi_c = cs1; hi_s = sn1; glo = gk[pick]; ghi = gk[pick + 1];
       base_c = cs0; base_s = sn0; have = true; best = lk[pick];
+    }
+    if (prm.slip_bisect) {   // 5 * (NROUNDS - 1) halvings: same final bracket width as the 32-section rounds
+      for (int it = 0; it < 5 * (NROUNDS - 1); it++) {
+        T mc = lo_c + hi_c, ms = lo_s + hi_s;
+        T inv = T(1) / std::sqrt(mc * mc + ms * ms);
+        mc *= inv; ms *= inv;
+        T gm, fm; V3<T> lm;
+        if (!eval(mc, ms, gm, fm, lm)) break;
+        if (gm < T(0)) { lo_c = mc; lo_s = ms; glo = gm; best = lm; } else { hi_c = mc; hi_s = ms; ghi = gm; }
+      }
     }
     // secant step inside the final bracket, direction re-normalised
     T tt = (ghi - glo) != T(0) ? (-glo / (ghi - glo)) : T(0.5);

@@ -414,3 +414,29 @@ def test_stagnation_exit_only_hits_cycling_problems(anymal_tables):
     # robots dropped in random orientations half inside the ground; 0 of 600 in a kneeling-robot batch)
     assert untouched.mean() > 0.85
     assert (~conv).sum() > 0 and it8[~conv].max() <= 48       # cycling cases leave after a few windows
+
+
+def test_bisection_and_32_section_slip_search_agree(anymal_tables):
+    """slip_bisect=1 (CPU-tuned search used for the CPU baseline timing) vs the kernel-identical 32-section rounds"""
+    oa, ob = Oracle(anymal_tables), Oracle(anymal_tables, params=dict(slip_bisect=1))
+    rng = np.random.default_rng(15)
+    n_slip = 0
+    for trial in range(300):
+        A = rng.standard_normal((3, 5))
+        Gm = A @ A.T * 0.02 + 0.01 * np.eye(3)
+        c = rng.standard_normal(3) * np.array([1.0, 1.0, 0.5])
+        mu = rng.uniform(0.2, 1.2)
+        la, lb = oa.solve_one(Gm, c, mu), ob.solve_one(Gm, c, mu)
+        assert np.allclose(la, lb, rtol=1e-6, atol=1e-9 * max(1.0, np.abs(la).max()))
+        n_slip += int(c[2] <= 0 and abs(np.hypot(la[0], la[1]) - mu * la[2]) < 1e-9 and la[2] > 0)
+    assert n_slip > 50
+    t = anymal_tables
+    gc, gv = random_state(t, np.random.default_rng(16), 64, vel_scale=0.5, base_z=0.5)
+    outs = []
+    for o in (Oracle(t, params=dict(threshold=1e-8, stall_window=0)), Oracle(t, params=dict(threshold=1e-8, stall_window=0, slip_bisect=1))):
+        o.set_ground(0.0)
+        a, b = gc.copy(), gv.copy()
+        d = o.step(a, b, n_steps=5, debug=True)
+        outs.append((a, b, d["iters"]))
+    conv = (outs[0][2] < 150) & (outs[1][2] < 150)
+    assert np.abs(outs[0][1] - outs[1][1])[conv].max() < 1e-5
