@@ -109,6 +109,23 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
+def usable_cores():
+    """host threads this process may really use: CPU affinity, capped by the cgroup CPU quota"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); p_ = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = max(1, min(n, q // p_))
+        except Exception:
+            pass
+    return n
+
+
 def algorithmic_bytes_per_env_step(nq, nv, nj, kbar):
     # SURVEY.md 8(d): reads gc, gv, tau_ff, pTarget, vTarget; writes gc+, gv+, tau_applied, count, 12 words per contact
     return 4.0 * (2 * nq + 3 * nv + 2 * nj + 1 + 12.0 * kbar)
@@ -122,7 +139,7 @@ def cpu_baseline(sample_envs, max_steps, budget_s=12.0):
     H, gc, gv, targets, kp, kd = make_workload(0, sample_envs)
     o = Oracle(load_tables(os.path.join(RSC_DIR, "anymal_c_like.urdf")), params=dict(threshold=1e-6, slip_bisect=1))   # CPU-tuned slip search
     o.set_heightmap(HM["xs"], HM["ys"], HM["size"], HM["size"], 0.0, 0.0, H.astype(np.float64))
-    cores = os.cpu_count()
+    cores = usable_cores()
     vt = np.zeros((sample_envs, 18))
     for k in range(30):     # warm-up: robots land on the terrain and settle (the GPU arm's timed region is the settled phase too)
         o.step(gc, gv, n_steps=SUBSTEPS, ptarget=targets[k % RING], vtarget=vt, kp=kp, kd=kd, nthreads=cores)
@@ -148,7 +165,7 @@ def run_reference(args):
     o = Oracle(load_tables(os.path.join(RSC_DIR, "anymal_c_like.urdf")), params=dict(threshold=1e-6, slip_bisect=1))   # CPU-tuned slip search
     o.set_heightmap(HM["xs"], HM["ys"], HM["size"], HM["size"], 0.0, 0.0, H.astype(np.float64))
     vt = np.zeros((n, 18))
-    cores = os.cpu_count()          # explicit: torchrun exports OMP_NUM_THREADS=1
+    cores = usable_cores()          # explicit: torchrun exports OMP_NUM_THREADS=1
     for k in range(max(args.warmup, 3)):
         o.step(gc, gv, n_steps=SUBSTEPS, ptarget=targets[k % RING], vtarget=vt, kp=kp, kd=kd, nthreads=cores)
     t0 = time.perf_counter()

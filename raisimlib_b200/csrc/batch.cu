@@ -94,6 +94,11 @@ static void build_blob(rsb_batch* b) {
   lvl[DL] = (int)lvldofs.size(); entstart[DL] = (int)ent.size();
   b->dims = Dims{md.nb, md.nq, md.nv, md.floating, md.maxdepth, maxdd};
   H = make_blob_header(b->dims, md.npts(), (int)ent.size());
+  {
+    bool ident = true;
+    for (int i = 1; i < md.nb; i++) for (int k = 0; k < 9; k++) if (std::fabs(md.jrot[9 * i + k] - ((k % 4 == 0) ? 1.0 : 0.0)) > 0.0) ident = false;
+    H.flags = ident ? 1 : 0;
+  }
   const int words = H.words;
   std::vector<uint32_t>& B = b->blob_host;
   B.assign(words, 0u);

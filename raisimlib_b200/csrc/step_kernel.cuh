@@ -60,7 +60,7 @@ struct BlobHeader {
   // dof tree (floating base = chain of 6 dofs) for the branch-sparse factorisation
   int nbase, maxdd, dlp, nent;
   int off_ddepth, off_dsub, off_danc, off_dbody, off_bdof, off_lvl, off_lvldofs, off_entstart, off_ent, off_lcad;
-  int words, pad;
+  int words, flags;    // flags bit0: every joint origin has identity rotation (rpy = 0 in the URDF)
 };
 static_assert(sizeof(BlobHeader) == 128, "header is 32 words");
 constexpr int HEADER_WORDS = 32;
@@ -392,6 +392,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
   const float* sec_c = reinterpret_cast<const float*>(blob_s + HO(off_sec));
   const float* sec_s = sec_c + NROUNDS * SEC_STRIDE;
   const int nbase = HO(nbase), maxdd = HO(maxdd), DLP = HO(dlp);
+  const bool jrot_identity = (H.flags & 1) != 0;
   const int* ddepth = reinterpret_cast<const int*>(blob_s + HO(off_ddepth));
   const int* dsub = reinterpret_cast<const int*>(blob_s + HO(off_dsub));
   const int* danc = reinterpret_cast<const int*>(blob_s + HO(off_danc));
@@ -485,11 +486,16 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
         if (j >= 0) {
           f3 jp = mk(bodyf[(BF_JPOS + 0) * nbp + j], bodyf[(BF_JPOS + 1) * nbp + j], bodyf[(BF_JPOS + 2) * nbp + j]);
           float Jr[9], Rj[9];
+          if (!jrot_identity) {
 #pragma unroll
-          for (int k = 0; k < 9; k++) Jr[k] = bodyf[(BF_JROT + k) * nbp + j];
+            for (int k = 0; k < 9; k++) Jr[k] = bodyf[(BF_JROT + k) * nbp + j];
+          }
           f3 al = mk(bodyf[(BF_AXIS + 0) * nbp + j], bodyf[(BF_AXIS + 1) * nbp + j], bodyf[(BF_AXIS + 2) * nbp + j]);
           f3 r = mulR(R, jp);
-          matmul3(R, Jr, Rj);
+          if (jrot_identity) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) Rj[k] = R[k];
+          } else matmul3(R, Jr, Rj);
           f3 aj = mulR(Rj, al);
           float q = s_gc[bodyi[BF_QIDX * nbp + j]], qd = s_gv[bodyi[BF_VIDX * nbp + j]];
           const bool rev = bodyi[BF_JTYPE * nbp + j] == 1;
@@ -962,8 +968,11 @@ __global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_cons
         if (lane < nd) {
           const int i = lvldofs[d0 + lane];
           float acc = s_rhs[i];
+          // base dofs are ancestors of every other dof and are their own index: no ancestor lookup
+#pragma unroll
+          for (int t = 0; t < 6; t++) if (t < nbase) acc -= s_L[i * DLP + t] * s_rhs[t];
 #pragma unroll 1
-          for (int t = 0; t < lev; t++) acc -= s_L[i * DLP + t] * s_rhs[danc[t * nvp + i]];
+          for (int t = nbase; t < lev; t++) acc -= s_L[i * DLP + t] * s_rhs[danc[t * nvp + i]];
           s_rhs[i] = acc * s_invd[i];
         }
         __syncwarp();
