@@ -188,7 +188,7 @@ static int pick_config(rsb_batch* b) {
   b->spec = same_dims(b->dims, kQuad12) && b->slots == 1 ? 1 : (same_dims(b->dims, kHumanoid30) ? 2 : 0);
   if (const char* e = getenv("RSB_FORCE_GENERIC")) if (atoi(e)) b->spec = 0;
   // one persistent CTA per SM; as many warps (= resident environments) as shared memory allows
-  static const int options[] = {28, 16, 8, 4, 1};
+  static const int options[] = {28, 16, 8, 4, 1};   // 14 = two 14-warp CTAs per SM (experiment: RSB_FORCE_WPC=14)
   int need = (b->N + sms - 1) / sms;    // warps per SM that make every environment resident at once
   int best = 0;
   for (int w : options) {
@@ -196,10 +196,10 @@ static int pick_config(rsb_batch* b) {
     if (best == 0) best = w;
     if (w >= need) best = w;            // smallest option that still keeps every environment resident
   }
-  if (const char* e = getenv("RSB_FORCE_WPC")) { int w = atoi(e); if (w == 28 || w == 16 || w == 8 || w == 4 || w == 1) if (blob_bytes + (size_t)w * per_warp + 1024 <= budget) best = w; }
+  if (const char* e = getenv("RSB_FORCE_WPC")) { int w = atoi(e); if (w == 28 || w == 16 || w == 14 || w == 8 || w == 4 || w == 1) if (blob_bytes + (size_t)w * per_warp + 1024 <= budget) best = w; }
   if (best == 0) return fail(RSB_ERR_UNSUPPORTED, "model too large for one warp's shared-memory workspace");
   b->wpc = best;
-  b->grid = std::min((b->N + best - 1) / best, sms);
+  b->grid = std::min((b->N + best - 1) / best, best == 14 ? 2 * sms : sms);
   b->smem_bytes = blob_bytes + (size_t)best * per_warp;
   return RSB_OK;
 }
@@ -234,6 +234,7 @@ static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug) {
   switch (b->wpc) {
     case 28: e = dispatch_spec<28>(b, a); break;
     case 16: e = dispatch_spec<16>(b, a); break;
+    case 14: e = dispatch_spec<14>(b, a); break;
     case 8: e = dispatch_spec<8>(b, a); break;
     case 4: e = dispatch_spec<4>(b, a); break;
     default: e = dispatch_spec<1>(b, a); break;

@@ -353,7 +353,7 @@ __device__ __noinline__ void write_debug(const StepArgs& args, int env, int lane
 // SNB > 0: compiled for the model dimensions (SNB, SNQ, SNV, SFL, SMAXDEPTH, SMAXDD) -- every table and
 // workspace offset is an immediate.  SNB == 0: generic, dimensions read from the blob header.
 template <int WPC, int SLOTS, int SNB, int SNQ, int SNV, int SFL, int SMAXDEPTH, int SMAXDD>
-__global__ void __launch_bounds__(WPC * 32, 1) rsb_step_kernel(const __grid_constant__ StepArgs args) {
+__global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel(const __grid_constant__ StepArgs args) {
   extern __shared__ __align__(128) uint32_t smem[];
   __shared__ __align__(8) uint64_t tma_bar;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
