@@ -72,7 +72,12 @@ def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise RsbError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
+            # not a fallback: the same CUDA library, compiled on the spot when the prebuilt one did not travel
+            import subprocess
+            try:
+                subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc")], stdout=subprocess.DEVNULL)
+            except Exception as e:
+                raise RsbError(f"{LIB_PATH} is missing and could not be built ({e}): run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
         L = C.CDLL(LIB_PATH)
         L.rsb_last_error.restype = C.c_char_p
         L.rsb_model_body_name.restype = C.c_char_p

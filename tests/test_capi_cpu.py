@@ -72,3 +72,27 @@ def test_no_gpu_means_loud_failure():
     m = capi.Model(os.path.join(RSC, "anymal_c_like.urdf"))
     with pytest.raises(capi.RsbError, match="no CPU fallback"):
         capi.Batch(m, 4)
+
+
+def test_argument_validation_without_gpu():
+    """empty / negative sizes and null handles are rejected with a message, never a crash (no GPU needed)"""
+    import ctypes as C
+    L = capi.lib()
+    m = capi.Model(os.path.join(RSC, "anymal_c_like.urdf"))
+    h = C.c_void_p()
+    assert L.rsb_batch_create(m.h, 0, 0, C.byref(h)) < 0 and b"bad arguments" in L.rsb_last_error()
+    assert L.rsb_batch_create(m.h, -5, 0, C.byref(h)) < 0
+    assert L.rsb_batch_create(None, 4, 0, C.byref(h)) < 0
+    assert L.rsb_batch_integrate(None, 1) < 0
+    assert L.rsb_batch_num_envs(None) == 0
+    assert L.rsb_model_body_index(None, b"x") < 0
+    p = capi.Params()
+    assert L.rsb_params_default(C.byref(p)) == 0
+    assert abs(p.dt - 0.0025) < 1e-9 and p.max_iter == 150 and p.stall_window == 8 and abs(p.mu - 0.8) < 1e-7
+
+
+def test_too_many_bodies_is_reported():
+    links = "".join(f"<link name='l{i}'><inertial><mass value='1'/><inertia ixx='1' iyy='1' izz='1'/></inertial></link>" for i in range(40))
+    joints = "".join(f"<joint name='j{i}' type='revolute'><parent link='l{i}'/><child link='l{i+1}'/><axis xyz='0 0 1'/></joint>" for i in range(39))
+    with pytest.raises(capi.RsbError, match="more than 32 movable bodies"):
+        capi.Model(f"<robot name='chain'>{links}{joints}</robot>")
