@@ -33,6 +33,8 @@ GC0 = np.array([0, 0, 0.57, 1, 0, 0, 0, 0.03, 0.4, -0.8, -0.03, 0.4, -0.8, 0.03,
 KP, KD = 300.0, 8.0
 HM = dict(xs=513, ys=513, size=51.2, amp=0.10)
 RING = 8            # distinct PD-target sets cycled through (synthetic "policy output")
+SETTLE = 40         # untimed control steps run while BUILDING the workload: robots are dropped from 0.75 m and must stand
+                    # on the terrain before warm-up starts, whatever --warmup the caller passes
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -141,7 +143,7 @@ def cpu_baseline(sample_envs, max_steps, budget_s=12.0):
     o.set_heightmap(HM["xs"], HM["ys"], HM["size"], HM["size"], 0.0, 0.0, H.astype(np.float64))
     cores = usable_cores()
     vt = np.zeros((sample_envs, 18))
-    for k in range(30):     # warm-up: robots land on the terrain and settle (the GPU arm's timed region is the settled phase too)
+    for k in range(SETTLE + 3):     # workload construction + warm-up: robots land on the terrain and settle, like the GPU arm
         o.step(gc, gv, n_steps=SUBSTEPS, ptarget=targets[k % RING], vtarget=vt, kp=kp, kd=kd, nthreads=cores)
     t0 = time.perf_counter(); done = 0; k = 0
     while done < max_steps and time.perf_counter() - t0 < budget_s:
@@ -149,7 +151,7 @@ def cpu_baseline(sample_envs, max_steps, budget_s=12.0):
         done += SUBSTEPS; k += 1
     dt = time.perf_counter() - t0
     return {"value": sample_envs * done / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{sample_envs} envs x {done} sub-steps of the same workload (float64 oracle, bisection slip search, OpenMP over envs, after 120 warm-up sub-steps)"}
+            "sample": f"{sample_envs} envs x {done} sub-steps of the same workload (float64 oracle, bisection slip search, OpenMP over envs, after the same settling phase as the GPU arm)"}
 
 
 def run_reference(args):
@@ -166,7 +168,7 @@ def run_reference(args):
     o.set_heightmap(HM["xs"], HM["ys"], HM["size"], HM["size"], 0.0, 0.0, H.astype(np.float64))
     vt = np.zeros((n, 18))
     cores = usable_cores()          # explicit: torchrun exports OMP_NUM_THREADS=1
-    for k in range(max(args.warmup, 3)):
+    for k in range(SETTLE + max(args.warmup, 3)):
         o.step(gc, gv, n_steps=SUBSTEPS, ptarget=targets[k % RING], vtarget=vt, kp=kp, kd=kd, nthreads=cores)
     t0 = time.perf_counter()
     for k in range(args.steps):
@@ -284,6 +286,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)         # max over ranks
         return float(t[0]), float(t[1])
 
+    for k in range(SETTLE):          # workload construction (untimed): land and settle
+        control_step(k, False)
     for k in range(W):
         control_step(k, False)
     barrier()
