@@ -18,13 +18,15 @@ Conventions fixed here (parity unpinned -- no reference artefact can confirm the
   * body frame == child-link frame of the body's movable joint
   * inertia stored as (xx, xy, xz, yy, yz, zz) about the body COM, in body axes
   * collision shapes expand to candidate points (sphere -> 1, capsule -> 2 end spheres,
-    box -> 8 zero-radius corners; corner k has sign bits x=k&1, y=k&2, z=k&4)
+    box -> 8 zero-radius corners, corner k has sign bits x=k&1, y=k&2, z=k&4;
+    cylinder -> 4 zero-radius rim points per end cap, point k at angle 90deg*(k&3), cap z sign k&4;
+    mesh collision bodies are skipped)
 """
 import xml.etree.ElementTree as ET
 import numpy as np
 
 JT_FIXED, JT_REVOLUTE, JT_PRISMATIC, JT_FLOATING = 0, 1, 2, 3
-CT_SPHERE, CT_BOX, CT_CAPSULE = 0, 1, 2
+CT_SPHERE, CT_BOX, CT_CAPSULE, CT_CYLINDER = 0, 1, 2, 3
 
 
 def rpy_to_rot(rpy):
@@ -120,6 +122,11 @@ def load_tables(path_or_xml):
             elif g.find("capsule") is not None:
                 e = g.find("capsule")
                 body.colls.append((CT_CAPSULE, [float(e.get("radius")), 0.5 * float(e.get("length")), 0], pos, rot, link_name))
+            elif g.find("cylinder") is not None:
+                e = g.find("cylinder")
+                body.colls.append((CT_CYLINDER, [float(e.get("radius")), 0.5 * float(e.get("length")), 0], pos, rot, link_name))
+            elif g.find("mesh") is not None:
+                continue                                 # mesh collision bodies are outside this path
             else:
                 raise ValueError("unsupported collision geometry in link " + link_name)
         my_index = bodies.index(body)
@@ -183,6 +190,9 @@ def load_tables(path_or_xml):
                 pts = [(pos, size[0])]
             elif ty == CT_CAPSULE:
                 pts = [(pos + rot @ np.array([0, 0, -size[1]]), size[0]), (pos + rot @ np.array([0, 0, size[1]]), size[0])]
+            elif ty == CT_CYLINDER:
+                cx, sy = [1.0, 0.0, -1.0, 0.0], [0.0, 1.0, 0.0, -1.0]
+                pts = [(pos + rot @ np.array([size[0] * cx[k & 3], size[0] * sy[k & 3], size[1] if k & 4 else -size[1]]), 0.0) for k in range(8)]
             else:
                 pts = []
                 for k in range(8):

@@ -219,7 +219,9 @@ struct Builder {
       if (const XmlNode* s = g->child("sphere")) { type = CT_SPHERE; size[0] = parse_d(s->get("radius"), "sphere radius"); }
       else if (const XmlNode* bx = g->child("box")) { type = CT_BOX; V3 sz = parse_v3(bx->get("size"), {0, 0, 0}); size = {0.5 * sz[0], 0.5 * sz[1], 0.5 * sz[2]}; }
       else if (const XmlNode* cp2 = g->child("capsule")) { type = CT_CAPSULE; size[0] = parse_d(cp2->get("radius"), "capsule radius"); size[1] = 0.5 * parse_d(cp2->get("length"), "capsule length"); }
-      else throw std::runtime_error("URDF: unsupported collision geometry in link '" + link_name + "' (sphere, box, capsule are supported)");
+      else if (const XmlNode* cy = g->child("cylinder")) { type = CT_CYLINDER; size[0] = parse_d(cy->get("radius"), "cylinder radius"); size[1] = 0.5 * parse_d(cy->get("length"), "cylinder length"); }
+      else if (g->child("mesh")) { md.skipped_collisions++; continue; }   // mesh collision bodies are not part of this path
+      else throw std::runtime_error("URDF: unsupported collision geometry in link '" + link_name + "' (sphere, box, capsule, cylinder are supported)");
       int ci = md.ncoll();
       md.cbody.push_back(b); md.ctype.push_back(type);
       md.csize.insert(md.csize.end(), size.begin(), size.end());
@@ -234,6 +236,12 @@ struct Builder {
       };
       if (type == CT_SPHERE) add_pt({0, 0, 0}, size[0], 0);
       else if (type == CT_CAPSULE) { add_pt({0, 0, -size[1]}, size[0], 0); add_pt({0, 0, size[1]}, size[0], 1); }
+      else if (type == CT_CYLINDER) {   // four rim points per end cap (axis = local z)
+        for (int k = 0; k < 8; k++) {
+          const double cx[4] = {1, 0, -1, 0}, sy[4] = {0, 1, 0, -1};
+          add_pt({size[0] * cx[k & 3], size[0] * sy[k & 3], (k & 4) ? size[1] : -size[1]}, 0.0, k);
+        }
+      }
       else for (int k = 0; k < 8; k++) add_pt({(k & 1) ? size[0] : -size[0], (k & 2) ? size[1] : -size[1], (k & 4) ? size[2] : -size[2]}, 0.0, k);
     }
     auto kit = kids_of.find(link_name);

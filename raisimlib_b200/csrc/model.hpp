@@ -9,7 +9,7 @@
 namespace rsb {
 
 enum JointType { JT_FIXED = 0, JT_REVOLUTE = 1, JT_PRISMATIC = 2, JT_FLOATING = 3 };
-enum CollType { CT_SPHERE = 0, CT_BOX = 1, CT_CAPSULE = 2 };
+enum CollType { CT_SPHERE = 0, CT_BOX = 1, CT_CAPSULE = 2, CT_CYLINDER = 3 };
 
 struct Frame {
   std::string name;
@@ -27,10 +27,11 @@ struct Model {
   std::vector<int> cbody, ctype;
   std::vector<double> csize, cpos, crot;                               // 3,3,9 per collision body
   std::vector<std::string> coll_names;
-  // candidate contact points (sphere -> 1, capsule -> 2 end spheres, box -> 8 corners)
+  // candidate contact points (sphere -> 1, capsule -> 2 end spheres, box -> 8 corners, cylinder -> 2 x 4 rim points)
   std::vector<int> pt_body, pt_coll, pt_feat;
   std::vector<double> pt_pos, pt_rad;
   std::vector<Frame> frames;                                            // one per URDF link
+  int skipped_collisions = 0;                                           // <mesh> collision bodies ignored by the loader
   int ncoll() const { return (int)cbody.size(); }
   int npts() const { return (int)pt_body.size(); }
 };

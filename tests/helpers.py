@@ -133,3 +133,27 @@ def random_state(t, rng, n, pos_scale=0.0, vel_scale=1.0, joint_scale=0.5, base_
     else:
         gc[:] = joint_scale * rng.uniform(-1, 1, (n, t["nq"]))
     return gc, gv
+
+# a link set as real robot descriptions have it: visuals, meshes, cylinders, gazebo / transmission tags
+REALISTIC_URDF = """<?xml version="1.0" ?>
+<!-- generated by xacro -->
+<robot name="mini" xmlns:xacro="http://www.ros.org/wiki/xacro">
+  <material name="grey"><color rgba="0.5 0.5 0.5 1"/></material>
+  <link name="trunk">
+    <visual><origin xyz="0 0 0" rpy="0 0 0"/><geometry><mesh filename="package://x/meshes/trunk.dae" scale="1 1 1"/></geometry><material name="grey"/></visual>
+    <collision><geometry><box size="0.4 0.2 0.1"/></geometry></collision>
+    <collision><geometry><mesh filename="package://x/meshes/trunk_col.stl"/></geometry></collision>
+    <inertial><origin xyz="0.01 0 0"/><mass value="5"/><inertia ixx="0.02" ixy="0" ixz="0" iyy="0.06" iyz="0" izz="0.07"/></inertial>
+  </link>
+  <link name="imu_link"/>
+  <joint name="imu_joint" type="fixed"><parent link="trunk"/><child link="imu_link"/><origin rpy="0 0 0" xyz="0 0 0.05"/></joint>
+  <link name="leg">
+    <visual><geometry><cylinder length="0.3" radius="0.02"/></geometry></visual>
+    <collision><origin xyz="0 0 -0.15" rpy="0 0 0"/><geometry><cylinder length="0.3" radius="0.025"/></geometry></collision>
+    <inertial><origin xyz="0 0 -0.15"/><mass value="0.8"/><inertia ixx="0.006" ixy="0" ixz="0" iyy="0.006" iyz="0" izz="0.0003"/></inertial>
+  </link>
+  <joint name="hip" type="continuous"><parent link="trunk"/><child link="leg"/><origin xyz="0.15 0.1 0"/><axis xyz="0 1 0"/>
+    <dynamics damping="0.0" friction="0.0"/><limit effort="30" velocity="20"/></joint>
+  <transmission name="t"><type>transmission_interface/SimpleTransmission</type><joint name="hip"><hardwareInterface>hardware_interface/EffortJointInterface</hardwareInterface></joint></transmission>
+  <gazebo reference="leg"><mu1>0.8</mu1><self_collide>1</self_collide></gazebo>
+</robot>"""

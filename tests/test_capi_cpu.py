@@ -9,7 +9,7 @@ import pytest
 from conftest import ROOT, RSC
 from raisimlib_b200 import capi
 from oracle.urdf_tables import load_tables
-from helpers import PENDULUM_URDF, BOX_URDF
+from helpers import PENDULUM_URDF, BOX_URDF, REALISTIC_URDF
 
 
 def _declared_symbols():
@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(capi.Params) == 4 * 15
 
 
-@pytest.mark.parametrize("src", ["anymal_c_like.urdf", "atlas_like.urdf", PENDULUM_URDF, BOX_URDF])
+@pytest.mark.parametrize("src", ["anymal_c_like.urdf", "atlas_like.urdf", PENDULUM_URDF, BOX_URDF, REALISTIC_URDF])
 def test_model_tables_match_python_restatement(src):
     path = os.path.join(RSC, src) if src.endswith(".urdf") else src
     a = capi.Model(path).tables()
@@ -96,3 +96,14 @@ def test_too_many_bodies_is_reported():
     joints = "".join(f"<joint name='j{i}' type='revolute'><parent link='l{i}'/><child link='l{i+1}'/><axis xyz='0 0 1'/></joint>" for i in range(39))
     with pytest.raises(capi.RsbError, match="more than 32 movable bodies"):
         capi.Model(f"<robot name='chain'>{links}{joints}</robot>")
+
+
+def test_realistic_description_features():
+    """visual / mesh / gazebo / transmission tags are skipped, a massless fixed link merges, a cylinder yields 8 rim points"""
+    t = capi.Model(REALISTIC_URDF).tables()
+    assert (t["nb"], t["nq"], t["nv"]) == (2, 8, 7)
+    assert t["ncoll"] == 2 and list(t["ctype"]) == [1, 3]          # box + cylinder; the mesh collision body is skipped
+    assert t["npts"] == 16
+    rim = t["pt_pos"][8:]
+    assert np.allclose(np.hypot(rim[:, 0], rim[:, 1]), 0.025) and np.allclose(sorted(set(np.round(rim[:, 2], 6))), [-0.3, 0.0])
+    assert t["jlimit"][1, 0] < -1e29                               # continuous joint: no limits
