@@ -8,7 +8,7 @@ A bench "step" is one RaisimGym control step: ONE fused launch of 4 sub-steps of
 for every environment (= 4 x 4096 env-steps per GPU), followed by the observation kernel and, at
 N > 1, the NCCL all-gather of the observation rows.
 
-  value   env-steps/s with state, targets and terrain resident in HBM (targets refreshed D2D)
+  value   env-steps/s with state, targets and terrain resident in HBM (targets read in place)
   e2e     same metric through the C-ABI with HOST buffers: pinned H2D of the PD targets and D2H of
           the (all-gathered) observation rows inside the timed region
   --impl reference   the CPU path (oracle port of World::integrate(), OpenMP over envs, all host
@@ -235,9 +235,8 @@ def main():
         if host_io:
             bt.set_pd_target(tg_pin[k % RING], None)        # pinned H2D inside the timed region
         else:
-            bt.set_pd_target(tg_dev[k % RING], None)        # D2D refresh of the resident targets
-        bt.integrate(SUBSTEPS)                               # ONE fused launch: 4 x World::integrate()
-        bt.observe(obs)
+            bt.bind_pd_target(tg_dev[k % RING])             # resident targets read in place (zero-copy)
+        bt.control_step(None, SUBSTEPS, obs)                 # ONE fused launch: 4 x World::integrate() + observation rows
         if world > 1:
             allgather_observations(obs, obs_all)             # the only collective of the path
         if host_io:
@@ -266,11 +265,10 @@ def main():
             if host_io:
                 bt.set_pd_target(tg_pin[(step0 + k) % RING], None)
             else:
-                bt.set_pd_target(tg_dev[(step0 + k) % RING], None)
+                bt.bind_pd_target(tg_dev[(step0 + k) % RING])    # resident targets read in place (zero-copy)
             kev[k][0].record(stream)
-            bt.integrate(SUBSTEPS)
+            bt.control_step(None, SUBSTEPS, obs)             # ONE launch: 4 fused sub-steps + observation rows
             kev[k][1].record(stream)
-            bt.observe(obs)
             if world > 1:
                 allgather_observations(obs, obs_all)
             if host_io:

@@ -129,6 +129,9 @@ int rsb_batch_set_state(rsb_batch* b, const float* gc, const float* gv, int env_
 int rsb_batch_get_state(rsb_batch* b, float* gc, float* gv, int env_begin, int env_count, int where);
 int rsb_batch_set_pd_gains(rsb_batch* b, const float* kp, const float* kd);        /* [nv], host, all envs */
 int rsb_batch_set_pd_target(rsb_batch* b, const float* ptarget, const float* vtarget, int env_begin, int env_count, int where);
+/* zero-copy PD targets for trainers on the same GPU: the step kernel reads rows [env][0..nq) straight from the
+ * caller's device buffer (row_stride floats apart) until targets are copied in again or NULL is bound */
+int rsb_batch_bind_pd_target(rsb_batch* b, const float* ptarget_device, int row_stride);
 int rsb_batch_set_generalized_force(rsb_batch* b, const float* tau, int env_begin, int env_count, int where);
 int rsb_batch_set_control_mode(rsb_batch* b, int mode);
 /* ArticulatedSystem::getGeneralizedForce(): feed-forward + PD force applied over the last integrate() */

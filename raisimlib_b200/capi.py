@@ -57,7 +57,7 @@ EXPORTED = [
     "rsb_batch_create", "rsb_batch_destroy", "rsb_batch_set_stream", "rsb_batch_sync", "rsb_batch_num_envs",
     "rsb_batch_set_ground", "rsb_batch_set_heightmap", "rsb_batch_clear_terrain", "rsb_batch_set_params", "rsb_batch_get_params",
     "rsb_batch_set_state", "rsb_batch_get_state", "rsb_batch_set_pd_gains", "rsb_batch_set_pd_target",
-    "rsb_batch_set_generalized_force", "rsb_batch_set_control_mode", "rsb_batch_get_generalized_force",
+    "rsb_batch_set_generalized_force", "rsb_batch_set_control_mode", "rsb_batch_get_generalized_force", "rsb_batch_bind_pd_target",
     "rsb_batch_integrate1", "rsb_batch_integrate2", "rsb_batch_integrate",
     "rsb_batch_get_mass_matrix", "rsb_batch_get_nonlinearities", "rsb_batch_get_body_poses", "rsb_batch_get_contacts",
     "rsb_batch_get_contact_points", "rsb_batch_get_solver_iterations", "rsb_batch_device_ptrs", "rsb_batch_launch_count",
@@ -108,6 +108,7 @@ def lib():
         L.rsb_batch_set_pd_gains.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rsb_batch_set_generalized_force.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.rsb_batch_set_control_mode.argtypes = [C.c_void_p, C.c_int]
+        L.rsb_batch_bind_pd_target.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.rsb_batch_get_generalized_force.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.rsb_batch_integrate1.argtypes = [C.c_void_p]
         L.rsb_batch_integrate2.argtypes = [C.c_void_p]
@@ -262,6 +263,14 @@ class Batch:
         n = self.n - env_begin if env_count is None else env_count
         pp, w1 = _ptr(ptarget); pv, w2 = _ptr(vtarget)
         _ck(lib().rsb_batch_set_pd_target(self.h, pp, pv, env_begin, n, w1 if ptarget is not None else w2))
+
+    def bind_pd_target(self, ptarget_dev, row_stride=None):
+        """zero-copy: the kernel reads PD-target rows from this device tensor (None unbinds)"""
+        if ptarget_dev is None:
+            _ck(lib().rsb_batch_bind_pd_target(self.h, None, 0)); return
+        assert ptarget_dev.is_cuda and ptarget_dev.is_contiguous()
+        self._bound = ptarget_dev        # keep alive
+        _ck(lib().rsb_batch_bind_pd_target(self.h, C.c_void_p(ptarget_dev.data_ptr()), row_stride or ptarget_dev.shape[-1]))
 
     def set_generalized_force(self, tau, env_begin=0, env_count=None):
         n = self.n - env_begin if env_count is None else env_count

@@ -36,6 +36,8 @@ struct rsb_batch {
   rsb_params prm{};
   int control_mode = RSB_PD_PLUS_FEEDFORWARD_TORQUE;
   bool pd_set = false;
+  const float* pt_bound = nullptr;   // caller-owned device buffer read in place of the internal PD-target rows
+  int pt_bound_stride = 0;
   // device buffers
   float *gc = nullptr, *gv = nullptr, *tau = nullptr, *pt = nullptr, *vt = nullptr, *tau_applied = nullptr;
   int *ncontacts = nullptr, *contact_pt = nullptr, *iters = nullptr;
@@ -176,6 +178,8 @@ static cudaError_t launch_step(const StepArgs& a, int grid, size_t smem, cudaStr
   return cudaGetLastError();
 }
 
+extern "C" int rsb_batch_ob_dim(const rsb_batch* b);
+
 static int pick_config(rsb_batch* b) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, b->device));
@@ -212,19 +216,20 @@ static cudaError_t dispatch_spec(const rsb_batch* b, const StepArgs& a) {
   return launch_step<WPC, 2, 0, 0, 0, 0, 0, 0>(a, b->grid, b->smem_bytes, b->stream);
 }
 
-static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug) {
+static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug, float* obs_dev = nullptr) {
   StepArgs a{};
   a.num_envs = b->N; a.substeps = substeps;
   a.gc_stride = b->gc_stride; a.gv_stride = b->gv_stride;
   a.gc = b->gc; a.gv = b->gv; a.tau = b->tau;
   a.use_pd = (b->control_mode == RSB_PD_PLUS_FEEDFORWARD_TORQUE && b->pd_set) ? 1 : 0;
-  a.ptarget = b->pt; a.vtarget = b->vt;
+  a.ptarget = b->pt_bound ? b->pt_bound : b->pt; a.pt_stride = b->pt_bound ? b->pt_bound_stride : b->gc_stride; a.vtarget = b->vt;
   a.prm = b->prm; a.ter = b->ter; a.ws = b->ws;
   a.blob_words = (int)b->blob_host.size(); a.blob = b->blob;
   a.tau_applied = b->tau_applied;
   a.ncontacts = b->ncontacts; a.contacts = b->contacts; a.contact_pt = b->contact_pt; a.iters = b->iters;
   if (debug) { a.dbg_M = b->dbg_M; a.dbg_h = b->dbg_h; a.dbg_R = b->dbg_R; a.dbg_p = b->dbg_p; }
   a.phase_mask = phase_mask;
+  a.obs = obs_dev; a.ob_dim = rsb_batch_ob_dim(b);
   {
     const char* e = getenv("RSB_SUBSTEP_BARRIER");
     const int level = e ? atoi(e) : 1;
@@ -491,8 +496,15 @@ int rsb_batch_set_pd_gains(rsb_batch* b, const float* kp, const float* kd) {
 }
 int rsb_batch_set_pd_target(rsb_batch* b, const float* ptarget, const float* vtarget, int env_begin, int env_count, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  if (ptarget) b->pt_bound = nullptr;     // copying targets in ends a zero-copy binding
   rc = copy_rows_in(b, b->pt, b->gc_stride, ptarget, b->nq, env_begin, env_count, where); if (rc) return rc;
   return copy_rows_in(b, b->vt, b->gv_stride, vtarget, b->nv, env_begin, env_count, where);
+}
+int rsb_batch_bind_pd_target(rsb_batch* b, const float* ptarget_device, int row_stride) {
+  if (!b) return fail(RSB_ERR_INVALID, "null batch");
+  if (ptarget_device && row_stride < b->nq) return fail(RSB_ERR_INVALID, "row stride smaller than nq");
+  b->pt_bound = ptarget_device; b->pt_bound_stride = row_stride;
+  return RSB_OK;
 }
 int rsb_batch_set_generalized_force(rsb_batch* b, const float* tau, int env_begin, int env_count, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
@@ -633,10 +645,32 @@ int rsb_batch_observe(rsb_batch* b, float* obs, int env_begin, int env_count, in
 int rsb_batch_control_step(rsb_batch* b, const float* ptarget, const float* vtarget, int where_in, int substeps, float* obs, int where_out) {
   if (!b || substeps < 1) return fail(RSB_ERR_INVALID, "bad arguments to rsb_batch_control_step");
   CK(cudaSetDevice(b->device));
+  if (ptarget) b->pt_bound = nullptr;
   int rc = copy_rows_in(b, b->pt, b->gc_stride, ptarget, b->nq, 0, b->N, where_in); if (rc) return rc;
   rc = copy_rows_in(b, b->vt, b->gv_stride, vtarget, b->nv, 0, b->N, where_in); if (rc) return rc;
-  rc = do_launch(b, substeps, 0, false); if (rc) return rc;
-  if (obs) return observe_impl(b, obs, 0, b->N, where_out, true);
+  if (!obs || !b->model->md.floating) {
+    rc = do_launch(b, substeps, 0, false); if (rc) return rc;
+    if (obs) return observe_impl(b, obs, 0, b->N, where_out, true);
+    return RSB_OK;
+  }
+  // observation rows are written by the step kernel itself (no separate observe launch)
+  float* dst = obs;
+  const int od = rsb_batch_ob_dim(b);
+  if (where_out == RSB_HOST) {
+    size_t need = (size_t)b->N * od;
+    if (b->obs_staging_words < need) {
+      if (b->obs_staging) { CK(cudaStreamSynchronize(b->stream)); cudaFree(b->obs_staging); }
+      b->obs_staging = nullptr; b->obs_staging_words = 0;
+      CK(cudaMalloc((void**)&b->obs_staging, need * 4));
+      b->obs_staging_words = need;
+    }
+    dst = b->obs_staging;
+  }
+  rc = do_launch(b, substeps, 0, false, dst); if (rc) return rc;
+  if (where_out == RSB_HOST) {
+    CK(cudaMemcpyAsync(obs, dst, (size_t)b->N * od * 4, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+  }
   return RSB_OK;
 }
 
@@ -688,6 +722,7 @@ int rsb_batch_gym_step(rsb_batch* b, const float* action, int where_in, int subs
   if (!action || substeps < 1) return fail(RSB_ERR_INVALID, "bad arguments to rsb_batch_gym_step");
   CK(cudaSetDevice(b->device));
   const int nj = b->nq - 7, od = rsb_batch_ob_dim(b);
+  b->pt_bound = nullptr;              // the task writes its own PD-target rows
   const float* act = action;
   if (where_in == RSB_HOST) {
     CK(cudaMemcpyAsync(b->gym_action, action, (size_t)b->N * nj * 4, cudaMemcpyHostToDevice, b->stream));

@@ -144,7 +144,7 @@ struct TerrainDesc {
 
 struct StepArgs {
   int num_envs, substeps;
-  int gc_stride, gv_stride;
+  int gc_stride, gv_stride, pt_stride;   // pt_stride: row stride of ptarget (own padded buffer or a bound caller buffer)
   float *gc, *gv;
   const float *tau, *ptarget, *vtarget;
   int use_pd;
@@ -160,6 +160,8 @@ struct StepArgs {
   int* iters;          // [N]
   float* tau_applied;  // [N][gv_stride] generalized force actually applied in the last sub-step (getGeneralizedForce)
   float *dbg_M, *dbg_h, *dbg_R, *dbg_p;   // optional (integrate1 / getters)
+  float* obs;          // optional [N][ob_dim]: RaisimGym observation row of the final state, written by this kernel
+  int ob_dim;
   int phase_mask;      // bit0: stop after stage C (integrate1: no state update)
   int substep_barrier; // 1: re-align the CTA's warps at every sub-step (instruction-cache locality experiment)
 };
@@ -446,7 +448,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       for (int i = lane; i < nv; i += 32) s_tau[i] = args.tau ? args.tau[(size_t)env * args.gv_stride + i] : 0.f;
       if (args.use_pd) {
 #pragma unroll 1
-        for (int i = lane; i < nq; i += 32) s_pt[i] = args.ptarget[(size_t)env * args.gc_stride + i];
+        for (int i = lane; i < nq; i += 32) s_pt[i] = args.ptarget[(size_t)env * args.pt_stride + i];
 #pragma unroll 1
         for (int i = lane; i < nv; i += 32) s_vt[i] = args.vtarget[(size_t)env * args.gv_stride + i];
       }
@@ -1022,6 +1024,24 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       for (int i = lane; i < nq; i += 32) g_gc[i] = s_gc[i];
 #pragma unroll 1
       for (int i = lane; i < nv; i += 32) { g_gv[i] = s_gv[i]; args.tau_applied[(size_t)env * args.gv_stride + i] = s_b[i]; }
+    }
+    if (args.obs && floating) {   // VectorizedEnvironment::observe() fused into the step: [z, R^T e_z, q_j, R^T v, R^T w, qdot_j]
+      float qw = s_gc[3], qx = s_gc[4], qy = s_gc[5], qz = s_gc[6];
+      const float inv = 1.0f / sqrtf(qw * qw + qx * qx + qy * qy + qz * qz);
+      qw *= inv; qx *= inv; qy *= inv; qz *= inv;
+      const float Ro[9] = {1.f - 2.f * (qy * qy + qz * qz), 2.f * (qx * qy - qw * qz), 2.f * (qx * qz + qw * qy),
+                           2.f * (qx * qy + qw * qz), 1.f - 2.f * (qx * qx + qz * qz), 2.f * (qy * qz - qw * qx),
+                           2.f * (qx * qz - qw * qy), 2.f * (qy * qz + qw * qx), 1.f - 2.f * (qx * qx + qy * qy)};
+      float* o = args.obs + (size_t)env * args.ob_dim;
+      const int nj = nq - 7;
+      if (lane == 0) o[0] = s_gc[2];
+      if (lane < 3) {
+        o[1 + lane] = Ro[6 + lane];
+        o[4 + nj + lane] = Ro[0 + lane] * s_gv[0] + Ro[3 + lane] * s_gv[1] + Ro[6 + lane] * s_gv[2];
+        o[7 + nj + lane] = Ro[0 + lane] * s_gv[3] + Ro[3 + lane] * s_gv[4] + Ro[6 + lane] * s_gv[5];
+      }
+#pragma unroll 1
+      for (int i = lane; i < nj; i += 32) { o[4 + i] = s_gc[7 + i]; o[10 + nj + i] = s_gv[6 + i]; }
     }
     if (lane == 0) { args.ncontacts[env] = K; args.iters[env] = iters; }
     if (lane < KMAX) {

@@ -406,7 +406,15 @@ def test_control_step_equals_separate_calls(capi):
     bt.control_step(pin_t, 4, pin_o)
     g2, v2 = bt.get_state()
     assert np.array_equal(g_ref, g2) and np.array_equal(v_ref, v2)
-    assert np.array_equal(ref_obs, pin_o.numpy())
+    # zero-copy binding of device-resident targets gives the same step again
+    bt.set_state(gc.astype(np.float32), gv.astype(np.float32))
+    dev_t = torch.from_numpy(target).cuda()
+    bt.bind_pd_target(dev_t)
+    bt.integrate(4)
+    g3, v3 = bt.get_state()
+    bt.bind_pd_target(None)
+    assert np.array_equal(g_ref, g3) and np.array_equal(v_ref, v3)
+    assert np.array_equal(ref_obs, pin_o.numpy())          # observation rows written by the step kernel == observe kernel
 
 
 @pytest.mark.parametrize("n", [1, 5, 4097, 9000])
