@@ -149,6 +149,7 @@ int rsb_batch_get_body_poses(rsb_batch* b, int env_begin, int env_count, float* 
 int rsb_batch_get_contacts(rsb_batch* b, rsb_contact* out, int32_t* counts, int env_begin, int env_count, int where); /* out [n][RSB_KMAX] */
 int rsb_batch_get_contact_points(rsb_batch* b, int32_t* pt_index, int env_begin, int env_count, int where);          /* [n][RSB_KMAX] candidate-point ids */
 int rsb_batch_get_solver_iterations(rsb_batch* b, int32_t* iters, int env_begin, int env_count, int where);          /* getContactSolver().getLoopCounter() */
+int rsb_batch_get_diverged(rsb_batch* b, int32_t* flags, int env_begin, int env_count, int where);                   /* 1 = state went non-finite in the last step: reset it */
 int rsb_batch_device_ptrs(rsb_batch* b, rsb_device_view* view);
 int64_t rsb_batch_launch_count(const rsb_batch* b);   /* kernels launched by this batch so far */
 

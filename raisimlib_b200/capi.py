@@ -60,7 +60,7 @@ EXPORTED = [
     "rsb_batch_set_generalized_force", "rsb_batch_set_control_mode", "rsb_batch_get_generalized_force", "rsb_batch_bind_pd_target",
     "rsb_batch_integrate1", "rsb_batch_integrate2", "rsb_batch_integrate",
     "rsb_batch_get_mass_matrix", "rsb_batch_get_nonlinearities", "rsb_batch_get_body_poses", "rsb_batch_get_contacts",
-    "rsb_batch_get_contact_points", "rsb_batch_get_solver_iterations", "rsb_batch_device_ptrs", "rsb_batch_launch_count",
+    "rsb_batch_get_contact_points", "rsb_batch_get_solver_iterations", "rsb_batch_get_diverged", "rsb_batch_device_ptrs", "rsb_batch_launch_count",
     "rsb_batch_ob_dim", "rsb_batch_observe", "rsb_batch_control_step",
     "rsb_batch_gym_configure", "rsb_batch_gym_reset", "rsb_batch_gym_step",
 ]
@@ -119,6 +119,7 @@ def lib():
         L.rsb_batch_get_contacts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.rsb_batch_get_contact_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.rsb_batch_get_solver_iterations.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.rsb_batch_get_diverged.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.rsb_batch_device_ptrs.argtypes = [C.c_void_p, C.POINTER(DeviceView)]
         L.rsb_batch_launch_count.argtypes = [C.c_void_p]
         L.rsb_batch_ob_dim.argtypes = [C.c_void_p]
@@ -333,6 +334,26 @@ class Batch:
         out = np.empty(n, np.int32)
         _ck(lib().rsb_batch_get_solver_iterations(self.h, out.ctypes.data_as(C.c_void_p), env_begin, n, HOST))
         return out
+
+    def diverged(self, env_begin=0, env_count=None):
+        n = self.n - env_begin if env_count is None else env_count
+        out = np.empty(n, np.int32)
+        _ck(lib().rsb_batch_get_diverged(self.h, out.ctypes.data_as(C.c_void_p), env_begin, n, HOST))
+        return out
+
+    def state_tensors(self):
+        """zero-copy torch views of the batch state on its GPU: (gc [N, nq], gv [N, nv]) as strided views of the
+        padded rows.  Writes through these tensors are seen by the next integrate()."""
+        import torch
+        v = self.device_view()
+
+        class _Raw:
+            def __init__(self, ptr, rows, stride):
+                self.__cuda_array_interface__ = {"shape": (rows, stride), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+        gc = torch.as_tensor(_Raw(v.gc, v.num_envs, v.gc_stride), device="cuda")[:, :v.nq]
+        gv = torch.as_tensor(_Raw(v.gv, v.num_envs, v.gv_stride), device="cuda")[:, :v.nv]
+        return gc, gv
 
     def device_view(self):
         v = DeviceView()

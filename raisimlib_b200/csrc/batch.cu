@@ -40,7 +40,7 @@ struct rsb_batch {
   int pt_bound_stride = 0;
   // device buffers
   float *gc = nullptr, *gv = nullptr, *tau = nullptr, *pt = nullptr, *vt = nullptr, *tau_applied = nullptr;
-  int *ncontacts = nullptr, *contact_pt = nullptr, *iters = nullptr;
+  int *ncontacts = nullptr, *contact_pt = nullptr, *iters = nullptr, *diverged = nullptr;
   rsb_contact* contacts = nullptr;
   float *dbg_M = nullptr, *dbg_h = nullptr, *dbg_R = nullptr, *dbg_p = nullptr;
   float* hmap = nullptr;
@@ -226,7 +226,7 @@ static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug, flo
   a.prm = b->prm; a.ter = b->ter; a.ws = b->ws;
   a.blob_words = (int)b->blob_host.size(); a.blob = b->blob;
   a.tau_applied = b->tau_applied;
-  a.ncontacts = b->ncontacts; a.contacts = b->contacts; a.contact_pt = b->contact_pt; a.iters = b->iters;
+  a.ncontacts = b->ncontacts; a.contacts = b->contacts; a.contact_pt = b->contact_pt; a.iters = b->iters; a.diverged = b->diverged;
   if (debug) { a.dbg_M = b->dbg_M; a.dbg_h = b->dbg_h; a.dbg_R = b->dbg_R; a.dbg_p = b->dbg_p; }
   a.phase_mask = phase_mask;
   a.obs = obs_dev; a.ob_dim = rsb_batch_ob_dim(b);
@@ -388,6 +388,7 @@ int rsb_batch_create(const rsb_model* m, int num_envs, int device, rsb_batch** o
   if (e == cudaSuccess) e = alloc((void**)&b->ncontacts, N * 4);
   if (e == cudaSuccess) e = alloc((void**)&b->contact_pt, N * KMAX * 4);
   if (e == cudaSuccess) e = alloc((void**)&b->iters, N * 4);
+  if (e == cudaSuccess) e = alloc((void**)&b->diverged, N * 4);
   if (e == cudaSuccess) e = alloc((void**)&b->contacts, N * KMAX * sizeof(rsb_contact));
   if (e == cudaSuccess) e = alloc((void**)&b->blob, b->blob_host.size() * 4);
   if (e == cudaSuccess) e = cudaMemcpy(b->blob, b->blob_host.data(), b->blob_host.size() * 4, cudaMemcpyHostToDevice);
@@ -408,7 +409,7 @@ void rsb_batch_destroy(rsb_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
-  for (void* p : {(void*)b->tau_applied, (void*)b->gc, (void*)b->gv, (void*)b->tau, (void*)b->pt, (void*)b->vt, (void*)b->ncontacts, (void*)b->contact_pt, (void*)b->iters,
+  for (void* p : {(void*)b->diverged, (void*)b->tau_applied, (void*)b->gc, (void*)b->gv, (void*)b->tau, (void*)b->pt, (void*)b->vt, (void*)b->ncontacts, (void*)b->contact_pt, (void*)b->iters,
                   (void*)b->contacts, (void*)b->dbg_M, (void*)b->dbg_h, (void*)b->dbg_R, (void*)b->dbg_p, (void*)b->hmap, (void*)b->staging, (void*)b->obs_staging, (void*)b->blob, (void*)b->gym_const, (void*)b->gym_action,
                   (void*)b->gym_obs, (void*)b->gym_reward, (void*)b->gym_done})
     if (p) cudaFree(p);
@@ -592,6 +593,12 @@ int rsb_batch_get_contact_points(rsb_batch* b, int32_t* pt, int env_begin, int e
 int rsb_batch_get_solver_iterations(rsb_batch* b, int32_t* it, int env_begin, int env_count, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
   CK(cudaMemcpyAsync(it, b->iters + env_begin, (size_t)env_count * 4, where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
+  if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
+  return RSB_OK;
+}
+int rsb_batch_get_diverged(rsb_batch* b, int32_t* flags, int env_begin, int env_count, int where) {
+  int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  CK(cudaMemcpyAsync(flags, b->diverged + env_begin, (size_t)env_count * 4, where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
   if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
   return RSB_OK;
 }

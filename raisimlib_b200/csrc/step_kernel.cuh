@@ -158,6 +158,7 @@ struct StepArgs {
   rsb_contact* contacts;
   int* contact_pt;     // [N][KMAX]
   int* iters;          // [N]
+  int* diverged;       // [N] 1 when the stored state holds a non-finite value (caller resets those environments)
   float* tau_applied;  // [N][gv_stride] generalized force actually applied in the last sub-step (getGeneralizedForce)
   float *dbg_M, *dbg_h, *dbg_R, *dbg_p;   // optional (integrate1 / getters)
   float* obs;          // optional [N][ob_dim]: RaisimGym observation row of the final state, written by this kernel
@@ -1042,6 +1043,15 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       }
 #pragma unroll 1
       for (int i = lane; i < nj; i += 32) { o[4 + i] = s_gc[7 + i]; o[10 + nj + i] = s_gv[6 + i]; }
+    }
+    {   // failure detection: a non-finite coordinate or velocity marks the environment as diverged
+      bool bad = false;
+#pragma unroll 1
+      for (int i = lane; i < nq; i += 32) bad |= !isfinite(s_gc[i]);
+#pragma unroll 1
+      for (int i = lane; i < nv; i += 32) bad |= !isfinite(s_gv[i]);
+      const bool any_bad = __any_sync(FULL, bad);
+      if (lane == 0) args.diverged[env] = any_bad ? 1 : 0;
     }
     if (lane == 0) { args.ncontacts[env] = K; args.iters[env] = iters; }
     if (lane < KMAX) {

@@ -545,3 +545,22 @@ def test_cpp_vectorized_environment_example(capi):
     out = subprocess.run([exe, os.path.join(RSC, "anymal_c_like.urdf"), "512"], capture_output=True, text=True, timeout=120)
     print(out.stdout)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_zero_copy_state_tensors_and_divergence_flag(capi):
+    import torch
+    n = 64
+    t, bt, o64, o32, gc, gv, tau = _setup(capi, "anymal_c_like.urdf", n, seed=151, base_z=0.6)
+    tg, tv = bt.state_tensors()
+    assert tg.shape == (n, 19) and tv.shape == (n, 18) and tg.is_cuda
+    assert np.array_equal(tg.cpu().numpy(), gc.astype(np.float32))
+    tg[3, 2] = 1.25                                   # write through the view ...
+    assert abs(bt.get_state()[0][3, 2] - 1.25) < 1e-7  # ... is seen by the C-ABI
+    bt.integrate(1)
+    assert (bt.diverged() == 0).all()
+    tv[5, 7] = float("nan")                            # poison one environment
+    bt.integrate(1)
+    d = bt.diverged()
+    assert d[5] == 1 and d.sum() == 1
+    g, v = bt.get_state()
+    assert np.isfinite(np.delete(g, 5, 0)).all()        # its neighbours are untouched
