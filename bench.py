@@ -240,7 +240,8 @@ def main():
         if world > 1:
             allgather_observations(obs, obs_all)             # the only collective of the path
         if host_io:
-            obs_host.copy_(obs_all, non_blocking=True)       # D2H of the step's result
+            if rank == 0:
+                obs_host.copy_(obs_all, non_blocking=True)   # D2H of the step's result
             stream.synchronize()
 
     def barrier():
@@ -271,8 +272,8 @@ def main():
             kev[k][1].record(stream)
             if world > 1:
                 allgather_observations(obs, obs_all)
-            if host_io:
-                obs_host.copy_(obs_all, non_blocking=True)
+            if host_io and rank == 0:
+                obs_host.copy_(obs_all, non_blocking=True)   # the gathered rows go back to the host once, on the trainer's rank
             ev[k][1].record(stream)
             if host_io:
                 stream.synchronize()                         # the caller reads the observation before acting
