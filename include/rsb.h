@@ -161,6 +161,13 @@ int rsb_batch_observe(rsb_batch* b, float* obs, int env_begin, int env_count, in
  * World::integrate() calls, observation rows out (either pointer may be NULL to skip that leg) */
 int rsb_batch_control_step(rsb_batch* b, const float* ptarget, const float* vtarget, int where_in, int substeps, float* obs, int where_out);
 
+/* ---- multi-GPU inside one process: one rsb_batch per GPU, NCCL all-gather of the observation rows ----
+ *      (NCCL is bound at run time; bench.py uses torch.distributed for the same collective, one process per GPU) */
+typedef struct rsb_comm rsb_comm;
+int rsb_comm_init(rsb_batch** batches, int ndev, rsb_comm** out);             /* ncclCommInitAll over the batches' devices */
+int rsb_comm_allgather_obs(rsb_comm* c, float* const* obs_all_per_device);     /* observe + ncclAllGather on every device     */
+void rsb_comm_destroy(rsb_comm* c);
+
 /* ---- RaisimGym task on the device (raisimGymTorch VectorizedEnvironment.hpp / envs/rsg_anymal/Environment.hpp,
  *      [RECALL]): pTarget = action * std + mean; reward = torque_coeff * |tau|^2 + forward_vel_coeff * min(4, v_body_x);
  *      an episode terminates on any contact whose local body is not in foot_bodies (reward += terminal_reward, state reset) -- */

@@ -63,6 +63,7 @@ EXPORTED = [
     "rsb_batch_get_contact_points", "rsb_batch_get_solver_iterations", "rsb_batch_get_diverged", "rsb_batch_device_ptrs", "rsb_batch_launch_count",
     "rsb_batch_ob_dim", "rsb_batch_observe", "rsb_batch_control_step",
     "rsb_batch_gym_configure", "rsb_batch_gym_reset", "rsb_batch_gym_step",
+    "rsb_comm_init", "rsb_comm_allgather_obs", "rsb_comm_destroy",
 ]
 
 _lib = None
@@ -128,6 +129,9 @@ def lib():
         L.rsb_batch_gym_configure.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int, C.c_float, C.c_float, C.c_float]
         L.rsb_batch_gym_reset.argtypes = [C.c_void_p]
         L.rsb_batch_gym_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.rsb_comm_init.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
+        L.rsb_comm_allgather_obs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.rsb_comm_destroy.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 

@@ -761,4 +761,14 @@ int rsb_batch_gym_step(rsb_batch* b, const float* action, int where_in, int subs
   return RSB_OK;
 }
 
+// ---- hooks for comm.cu -----------------------------------------------------------------------------
+int rsb_internal_batch_info(rsb_batch* b, int* device, void** stream, int* num_envs) {
+  if (!b) return fail(RSB_ERR_INVALID, "null batch");
+  if (device) *device = b->device;
+  if (stream) *stream = (void*)b->stream;
+  if (num_envs) *num_envs = b->N;
+  return RSB_OK;
+}
+void rsb_internal_set_error(const char* msg) { g_err = msg ? msg : ""; }
+
 }  // extern "C"

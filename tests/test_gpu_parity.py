@@ -564,3 +564,17 @@ def test_zero_copy_state_tensors_and_divergence_flag(capi):
     assert d[5] == 1 and d.sum() == 1
     g, v = bt.get_state()
     assert np.isfinite(np.delete(g, 5, 0)).all()        # its neighbours are untouched
+
+
+def test_cpp_multi_gpu_allgather_example(capi):
+    """rsb_comm_* (native NCCL all-gather of the observation rows) on however many GPUs are visible"""
+    import subprocess, torch
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "examples", "multi_gpu")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")])
+    ndev = torch.cuda.device_count()
+    out = subprocess.run([exe, os.path.join(RSC, "anymal_c_like.urdf"), str(ndev), "512"], capture_output=True, text=True, timeout=300)
+    print(out.stdout, out.stderr[-500:])
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert f"{ndev} GPU(s)" in out.stdout and "ok" in out.stdout
