@@ -35,6 +35,7 @@ extern "C" {
 #define RSB_DEVICE 1
 
 #define RSB_KMAX 8 /* contacts kept per environment (the deepest RSB_KMAX candidates) */
+#define RSB_LMAX 4 /* joint-limit constraints kept per environment (the first RSB_LMAX violated joints) */
 
 /* ArticulatedSystem::ControlMode */
 #define RSB_FORCE_AND_TORQUE 0
@@ -62,6 +63,7 @@ typedef struct rsb_params {
    * (two contacts on one body) make the published per-contact rule cycle; see DESIGN.md section 5. */
   int stall_window;     /*                                               (8)              */
   float stall_ratio;    /*                                               (0.5)            */
+  int joint_limits;     /* enforce URDF <limit lower upper> as unilateral rows of the same solve (1) */
 } rsb_params;
 
 /* raisim::Contact as returned by ArticulatedSystem::getContacts(): 12 words */

@@ -13,9 +13,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 PARAM_ORDER = ("dt", "gx", "gy", "gz", "erp", "alpha_init", "alpha_min", "alpha_decay", "max_iter",
-               "threshold", "mu", "restitution", "rest_threshold", "stall_window", "stall_ratio", "warm_start", "slip_bisect")
+               "threshold", "mu", "restitution", "rest_threshold", "stall_window", "stall_ratio", "warm_start", "slip_bisect", "joint_limits")
 DEFAULT_PARAMS = dict(dt=0.0025, gx=0.0, gy=0.0, gz=-9.81, erp=0.0, alpha_init=1.0, alpha_min=1.0, alpha_decay=1.0,
-                      max_iter=150, threshold=1e-7, mu=0.8, restitution=0.0, rest_threshold=0.01, stall_window=8, stall_ratio=0.5, warm_start=0, slip_bisect=0)
+                      max_iter=150, threshold=1e-7, mu=0.8, restitution=0.0, rest_threshold=0.01, stall_window=8, stall_ratio=0.5, warm_start=0, slip_bisect=0, joint_limits=1)
 
 
 def build(force=False):
@@ -30,13 +30,13 @@ class _ModelDesc(C.Structure):
     _fields_ = [("nb", C.c_int), ("nq", C.c_int), ("nv", C.c_int), ("floating", C.c_int),
                 ("parent", C.c_void_p), ("jtype", C.c_void_p), ("qidx", C.c_void_p), ("vidx", C.c_void_p),
                 ("jpos", C.c_void_p), ("jrot", C.c_void_p), ("axis", C.c_void_p), ("mass", C.c_void_p),
-                ("com", C.c_void_p), ("inertia", C.c_void_p),
+                ("com", C.c_void_p), ("inertia", C.c_void_p), ("jlimit", C.c_void_p),
                 ("npts", C.c_int), ("pt_body", C.c_void_p), ("pt_pos", C.c_void_p), ("pt_rad", C.c_void_p)]
 
 
 class _Debug(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("M", "h", "R", "p", "ncontacts", "c_pt", "c_body", "c_pair", "c_pos",
-                                          "c_normal", "c_depth", "c_lambda", "iters", "G", "u0", "warm_pt", "warm_imp", "tau_applied")]
+                                          "c_normal", "c_depth", "c_lambda", "iters", "G", "u0", "warm_pt", "warm_imp", "tau_applied", "nlimits", "lim_dof", "lim_lambda")]
 
 
 _lib = None
@@ -70,7 +70,7 @@ class Oracle:
         self.t = tables
         self.nb, self.nq, self.nv = tables["nb"], tables["nq"], tables["nv"]
         self._keep = {k: np.ascontiguousarray(tables[k], dtype=(np.int32 if tables[k].dtype.kind == "i" else np.float64))
-                      for k in ("parent", "jtype", "qidx", "vidx", "jpos", "jrot", "axis", "mass", "com", "inertia",
+                      for k in ("parent", "jtype", "qidx", "vidx", "jpos", "jrot", "axis", "mass", "com", "inertia", "jlimit",
                                 "pt_body", "pt_pos", "pt_rad")}
         d = _ModelDesc(nb=self.nb, nq=self.nq, nv=self.nv, floating=tables["floating"], npts=tables["npts"])
         for k, a in self._keep.items():
@@ -121,7 +121,8 @@ class Oracle:
                        ncontacts=np.zeros(n, np.int32), c_pt=np.zeros((n, K), np.int32), c_body=np.zeros((n, K), np.int32),
                        c_pair=np.zeros((n, K), np.int32), c_pos=np.zeros((n, K, 3)), c_normal=np.zeros((n, K, 3)),
                        c_depth=np.zeros((n, K)), c_lambda=np.zeros((n, K, 3)), iters=np.zeros(n, np.int32),
-                       G=np.zeros((n, 3 * K, 3 * K)), u0=np.zeros((n, 3 * K)), tau_applied=np.zeros((n, nv)))
+                       G=np.zeros((n, 3 * K, 3 * K)), u0=np.zeros((n, 3 * K)), tau_applied=np.zeros((n, nv)),
+                       nlimits=np.zeros(n, np.int32), lim_dof=np.full((n, 4), -1, np.int32), lim_lambda=np.zeros((n, 4)))
         ptrs = {k: v.ctypes.data for k, v in out.items()}
         ptrs["warm_pt"], ptrs["warm_imp"] = self.warm_pt.ctypes.data, self.warm_imp.ctypes.data
         dbg = _Debug(**ptrs)

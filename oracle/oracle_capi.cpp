@@ -27,6 +27,9 @@ struct OrcDebug {       // every pointer optional; sized for n_envs; filled from
   int* warm_pt;         // [n][KMAX]   IN/OUT contact cache (candidate-point ids, -1 = empty); null = cold start
   double* warm_imp;     // [n][KMAX*3] IN/OUT world-frame impulses of the cache
   double* tau_applied;  // [n][nv]     generalized force applied over the last step
+  int* nlimits;         // [n]         active joint-limit rows
+  int* lim_dof;         // [n][LMAX]   their dofs (-1 = none)
+  double* lim_lambda;   // [n][LMAX]   their impulses
 };
 
 struct Handle {
@@ -76,8 +79,11 @@ static void run(Sim<T>& sim, int n_envs, int n_steps, double* gc, double* gv, co
         int K = int(ws.contacts.size());
         if (dbg->ncontacts) dbg->ncontacts[e] = K;
         if (dbg->iters) dbg->iters[e] = ws.iters;
-        if (dbg->G) for (int a = 0; a < 3 * K; a++) for (int b2 = 0; b2 < 3 * K; b2++) dbg->G[(size_t)e * 9 * KMAX * KMAX + a * 3 * KMAX + b2] = double(ws.G[a * 3 * K + b2]);
+        const int Crows = 3 * K + int(ws.limits.size());
+        if (dbg->G) for (int a = 0; a < 3 * K; a++) for (int b2 = 0; b2 < 3 * K; b2++) dbg->G[(size_t)e * 9 * KMAX * KMAX + a * 3 * KMAX + b2] = double(ws.G[a * Crows + b2]);
         if (dbg->u0) for (int a = 0; a < 3 * K; a++) dbg->u0[(size_t)e * 3 * KMAX + a] = double(ws.u0[a]);
+        if (dbg->nlimits) dbg->nlimits[e] = int(ws.limits.size());
+        if (dbg->lim_dof) for (int l = 0; l < LMAX; l++) { dbg->lim_dof[(size_t)e * LMAX + l] = l < (int)ws.limits.size() ? ws.limits[l].dof : -1; if (dbg->lim_lambda) dbg->lim_lambda[(size_t)e * LMAX + l] = l < (int)ws.limits.size() ? double(ws.limits[l].lam) : 0.0; }
         for (int k = 0; k < KMAX; k++) {
           size_t o = (size_t)e * KMAX + k;
           bool on = k < K;
@@ -106,13 +112,13 @@ void orc_destroy(void* hv) { delete static_cast<Handle*>(hv); }
 
 int orc_kmax() { return KMAX; }
 
-// p = {dt, gx, gy, gz, erp, alpha_init, alpha_min, alpha_decay, max_iter, threshold, mu, restitution, rest_threshold, stall_window, stall_ratio, warm_start, slip_bisect}
+// p = {dt, gx, gy, gz, erp, alpha_init, alpha_min, alpha_decay, max_iter, threshold, mu, restitution, rest_threshold, stall_window, stall_ratio, warm_start, slip_bisect, joint_limits}
 void orc_set_params(void* hv, const double* p) {
   Handle* h = static_cast<Handle*>(hv);
   Params prm;
   prm.dt = p[0]; prm.gravity[0] = p[1]; prm.gravity[1] = p[2]; prm.gravity[2] = p[3]; prm.erp = p[4];
   prm.alpha_init = p[5]; prm.alpha_min = p[6]; prm.alpha_decay = p[7]; prm.max_iter = int(p[8]); prm.threshold = p[9];
-  prm.mu = p[10]; prm.restitution = p[11]; prm.rest_threshold = p[12]; prm.stall_window = int(p[13]); prm.stall_ratio = p[14]; prm.warm_start = int(p[15]); prm.slip_bisect = int(p[16]);
+  prm.mu = p[10]; prm.restitution = p[11]; prm.rest_threshold = p[12]; prm.stall_window = int(p[13]); prm.stall_ratio = p[14]; prm.warm_start = int(p[15]); prm.slip_bisect = int(p[16]); prm.joint_limits = int(p[17]);
   if (h->d) h->d->prm = prm; else h->f->prm = prm;
 }
 

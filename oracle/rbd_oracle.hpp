@@ -28,6 +28,8 @@ namespace orc {
 
 constexpr int JT_FIXED = 0, JT_REVOLUTE = 1, JT_PRISMATIC = 2, JT_FLOATING = 3;
 constexpr int KMAX = 8;            // contacts kept per environment (deepest KMAX of the candidates) == RSB_KMAX
+constexpr int LMAX = 4;            // joint-limit constraints kept per environment (first LMAX violated joints) == RSB_LMAX
+constexpr int RMAX = 3 * KMAX + LMAX;   // constraint rows
 constexpr int NSEC = 32;           // sections per refinement round of the slip search
 constexpr int NROUNDS = 3;         // rounds: bracket 2*pi/32^(r+1), then one secant step (error ~ bracket^2 = 4e-8 rad)
 
@@ -67,6 +69,7 @@ struct ModelDesc {   // plain-C description handed over the oracle's C API (all 
   int nb, nq, nv, floating;
   const int *parent, *jtype, *qidx, *vidx;
   const double *jpos, *jrot, *axis, *mass, *com, *inertia;
+  const double* jlimit;   // [nb][2] lower/upper (|.| >= 1e29 = none); may be null
   int npts;
   const int *pt_body;
   const double *pt_pos, *pt_rad;
@@ -81,6 +84,7 @@ struct Params {
   double threshold = 1e-7;
   double mu = 0.8;              // World::setDefaultMaterial friction
   double restitution = 0.0, rest_threshold = 0.01;
+  int joint_limits = 1;         // enforce the URDF <limit lower upper> of revolute/prismatic joints (unilateral rows in the solver)
   int stall_window = 8;         // stagnation exit of the Gauss-Seidel loop (0 = off), see include/rsb.h
   double stall_ratio = 0.5;
   int slip_bisect = 0;          // 1: after the first 32-probe round, refine the bracket by plain bisection (what a CPU
@@ -109,6 +113,8 @@ template <typename T> struct Contact {
   V3<T> lam;       // impulse in the contact frame (t1, t2, n)
 };
 
+template <typename T> struct Limit { int dof; T sign, viol, lam; };   // joint-limit row: sign * qdot >= 0
+
 template <typename T> struct Workspace {
   int nb, nv;
   std::vector<M3<T>> R;
@@ -117,6 +123,7 @@ template <typename T> struct Workspace {
   std::vector<T> S;              // 6 per body: [ang(3); lin_at_O(3)]
   std::vector<T> M, Mh, L, h, b, z, Jt, Y, G, u, u0, rhs, tau_applied;
   std::vector<Contact<T>> contacts, all;
+  std::vector<Limit<T>> limits;
   int iters = 0;
   // warm-start cache: candidate-point id and WORLD-frame impulse of the previous step's contacts
   int prev_pt[KMAX]; V3<T> prev_imp[KMAX];
@@ -129,7 +136,7 @@ template <typename T> class Sim {
   std::vector<int> parent, jtype, qidx, vidx, pt_body;
   std::vector<V3<T>> jpos, axis, com, pt_pos;
   std::vector<M3<T>> jrot;
-  std::vector<T> mass, inertia, pt_rad;
+  std::vector<T> mass, inertia, pt_rad, jlo, jhi;
   Params prm;
   Terrain ter;
   std::vector<T> hmap;
@@ -148,6 +155,8 @@ template <typename T> class Sim {
       mass[i] = T(d.mass[i]);
       for (int k = 0; k < 6; k++) inertia[6 * i + k] = T(d.inertia[6 * i + k]);
     }
+    jlo.assign(nb, T(-1e30)); jhi.assign(nb, T(1e30));
+    if (d.jlimit) for (int i = 0; i < nb; i++) { jlo[i] = T(d.jlimit[2 * i]); jhi[i] = T(d.jlimit[2 * i + 1]); }
     pt_body.assign(d.pt_body, d.pt_body + npts); pt_pos.resize(npts); pt_rad.resize(npts);
     for (int i = 0; i < npts; i++) {
       pt_pos[i] = {T(d.pt_pos[3 * i]), T(d.pt_pos[3 * i + 1]), T(d.pt_pos[3 * i + 2])};
@@ -174,7 +183,7 @@ template <typename T> class Sim {
     ws.R.resize(nb); ws.p.resize(nb); ws.a.resize(nb); ws.w.resize(nb); ws.v.resize(nb); ws.wd.resize(nb); ws.vd.resize(nb);
     ws.F.resize(nb); ws.N.resize(nb); ws.Ic.resize(10 * nb); ws.S.resize(6 * nb);
     ws.M.resize(nv * nv); ws.Mh.resize(nv * nv); ws.L.resize(nv * nv); ws.h.resize(nv); ws.tau_applied.resize(nv); ws.b.resize(nv); ws.z.resize(nv); ws.rhs.resize(nv);
-    ws.Jt.resize(nv * 3 * KMAX); ws.Y.resize(nv * 3 * KMAX); ws.G.resize(9 * KMAX * KMAX); ws.u.resize(3 * KMAX); ws.u0.resize(3 * KMAX);
+    ws.Jt.resize(nv * RMAX); ws.Y.resize(nv * RMAX); ws.G.resize(RMAX * RMAX); ws.u.resize(RMAX); ws.u0.resize(RMAX);
   }
 
   // ---- a2: forward kinematics (ArticulatedSystem::updateKinematics) -----------------------------
@@ -415,8 +424,9 @@ template <typename T> class Sim {
 
   // ---- a7: contact Jacobian rows in the contact frame; Jt is nv x 3K (row r of Jt = dof r) -------
   void jacobians(Workspace<T>& ws) const {
-    int K = int(ws.contacts.size()), C = 3 * K;
+    int K = int(ws.contacts.size()), C = 3 * K + int(ws.limits.size());
     std::fill(ws.Jt.begin(), ws.Jt.begin() + nv * C, T(0));
+    for (size_t l = 0; l < ws.limits.size(); l++) ws.Jt[ws.limits[l].dof * C + 3 * K + int(l)] = ws.limits[l].sign;
     for (int ci = 0; ci < K; ci++) {
       const Contact<T>& c = ws.contacts[ci];
       V3<T> ax[3] = {c.t1, c.t2, c.n};
@@ -545,10 +555,19 @@ template <typename T> class Sim {
     cholesky(Mh.data(), ws.L.data(), nv);
     for (int i = 0; i < nv; i++) ws.z[i] = ws.b[i];
     fwd_solve(ws.L.data(), ws.z.data(), nv);
-    int K = int(ws.contacts.size()), C = 3 * K;
+    int K = int(ws.contacts.size());
+    // a9 (joint limits): the first LMAX joints found beyond their limit become unilateral rows  sign * qdot >= erp * viol / dt
+    ws.limits.clear();
+    if (prm.joint_limits)
+      for (int i = 1; i < nb && (int)ws.limits.size() < LMAX; i++) {
+        T q = gc[qidx[i]];
+        if (q < jlo[i]) ws.limits.push_back({vidx[i], T(1), jlo[i] - q, T(0)});
+        else if (q > jhi[i]) ws.limits.push_back({vidx[i], T(-1), q - jhi[i], T(0)});
+      }
+    const int Lm = int(ws.limits.size()), C3 = 3 * K, C = C3 + Lm;
     for (int i = 0; i < nv; i++) ws.rhs[i] = dt * ws.z[i];
     ws.iters = 0;
-    if (K > 0) {
+    if (C > 0) {
       jacobians(ws);
       // Y = L^-1 J^T (nv x C);  G = Y^T Y;  u0 = J v + dt Y^T z - target
       for (int i = 0; i < nv * C; i++) ws.Y[i] = ws.Jt[i];
@@ -562,7 +581,8 @@ template <typename T> class Sim {
         T s = 0, s0 = 0;
         for (int r = 0; r < nv; r++) { s0 += ws.Jt[r * C + a] * gv[r]; s += ws.Y[r * C + a] * ws.z[r]; }
         ws.u[a] = s0 + dt * s;
-        if (a % 3 == 2) {
+        if (a >= C3) ws.u[a] -= T(prm.erp) * ws.limits[a - C3].viol / dt;
+        else if (a % 3 == 2) {
           const Contact<T>& ct = ws.contacts[a / 3];
           T target = T(prm.erp) * ct.depth / dt;
           if (prm.restitution > 0 && s0 < -T(prm.rest_threshold)) target += -T(prm.restitution) * s0;
@@ -608,6 +628,17 @@ template <typename T> class Sim {
           for (int a = 0; a < C; a++) ws.u[a] += ws.G[a * C + 3 * i] * dl.x + ws.G[a * C + 3 * i + 1] * dl.y + ws.G[a * C + 3 * i + 2] * dl.z;
           err = std::max(err, std::max(std::fabs(dl.x), std::max(std::fabs(dl.y), std::fabs(dl.z))));
         }
+        for (int l = 0; l < Lm; l++) {   // joint limits: lam >= 0, sign * qdot+ >= target, complementary
+          const int r = C3 + l;
+          Limit<T>& lm = ws.limits[l];
+          T Grr = ws.G[r * C + r];
+          T c0 = ws.u[r] - Grr * lm.lam;
+          T ln = std::max(T(0), -c0 / Grr);
+          T dl = alpha * (ln - lm.lam);
+          lm.lam += dl;
+          for (int a = 0; a < C; a++) ws.u[a] += ws.G[a * C + r] * dl;
+          err = std::max(err, std::fabs(dl));
+        }
         ws.iters = it + 1;
         alpha = std::max(T(prm.alpha_min), alpha * T(prm.alpha_decay));
         if (err < T(prm.threshold)) break;
@@ -622,6 +653,7 @@ template <typename T> class Sim {
           const V3<T>& l = ws.contacts[i].lam;
           s += ws.Y[r * C + 3 * i] * l.x + ws.Y[r * C + 3 * i + 1] * l.y + ws.Y[r * C + 3 * i + 2] * l.z;
         }
+        for (int l = 0; l < Lm; l++) s += ws.Y[r * C + C3 + l] * ws.limits[l].lam;
         ws.rhs[r] += s;
       }
     }

@@ -22,7 +22,7 @@ class Params(C.Structure):
     _fields_ = [("dt", C.c_float), ("gravity", C.c_float * 3), ("erp", C.c_float), ("alpha_init", C.c_float),
                 ("alpha_min", C.c_float), ("alpha_decay", C.c_float), ("max_iter", C.c_int), ("threshold", C.c_float),
                 ("mu", C.c_float), ("restitution", C.c_float), ("rest_threshold", C.c_float),
-                ("stall_window", C.c_int), ("stall_ratio", C.c_float)]
+                ("stall_window", C.c_int), ("stall_ratio", C.c_float), ("joint_limits", C.c_int)]
 
 
 class Contact(C.Structure):

@@ -117,6 +117,7 @@ static void build_blob(rsb_batch* b) {
     F(H.off_body + BF_MASS * nbp + i, (float)md.mass[i]);
     for (int k = 0; k < 3; k++) F(H.off_body + (BF_COM + k) * nbp + i, (float)md.com[3 * i + k]);
     for (int k = 0; k < 6; k++) F(H.off_body + (BF_INERTIA + k) * nbp + i, (float)md.inertia[6 * i + k]);
+    F(H.off_body + BF_LO * nbp + i, (float)std::max(-3.0e38, md.jlimit[2 * i])); F(H.off_body + BF_HI * nbp + i, (float)std::min(3.0e38, md.jlimit[2 * i + 1]));
     // ancestor at depth d (d = 1..depth[i]) stored at anc[(d-1)*nbp + i]
     for (int d = 0; d < std::max(1, md.maxdepth); d++) I(H.off_anc + d * nbp + i, -1);
     for (int j = i; md.parent[j] >= 0; j = md.parent[j]) I(H.off_anc + (md.depth[j] - 1) * nbp + i, j);
@@ -302,7 +303,7 @@ int rsb_params_default(rsb_params* p) {
   if (!p) return fail(RSB_ERR_INVALID, "null params");
   p->dt = 0.0025f; p->gravity[0] = 0.f; p->gravity[1] = 0.f; p->gravity[2] = -9.81f; p->erp = 0.f;
   p->alpha_init = 1.f; p->alpha_min = 1.f; p->alpha_decay = 1.f; p->max_iter = 150; p->threshold = 1e-6f;
-  p->mu = 0.8f; p->restitution = 0.f; p->rest_threshold = 0.01f; p->stall_window = 8; p->stall_ratio = 0.5f;
+  p->mu = 0.8f; p->restitution = 0.f; p->rest_threshold = 0.01f; p->stall_window = 8; p->stall_ratio = 0.5f; p->joint_limits = 1;
   return RSB_OK;
 }
 

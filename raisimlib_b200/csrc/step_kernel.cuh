@@ -30,8 +30,11 @@ namespace rsb {
 
 constexpr int KMAX = RSB_KMAX;
 constexpr int CMAX = 3 * KMAX;      // contact rows
-constexpr int CP = CMAX + 1;        // Y row stride: columns 0..C-1 = contact rows, column C = b
-constexpr int GP = CMAX + 1;        // G row stride (odd: conflict-free row access by lane)
+constexpr int LMAX = RSB_LMAX;      // joint-limit rows (first LMAX violated joints)
+constexpr int RMAX = CMAX + LMAX;   // constraint rows: one lane each (<= 32)
+constexpr int CP = RMAX + 1;        // Y row stride (odd)
+constexpr int GP = RMAX + 1;        // G row stride (odd: conflict-free row access by lane)
+static_assert(RMAX <= 32, "one constraint row per lane");
 constexpr int NSEC = 32;
 constexpr int NROUNDS = 3;         // 32-section rounds: bracket 2*pi/32^(r+1); the closing secant step is then exact to float32
 constexpr int SEC_STRIDE = 36;      // (NSEC+1) padded
@@ -41,7 +44,7 @@ constexpr unsigned FULL = 0xffffffffu;
 
 enum BodyField {
   BF_PARENT = 0, BF_JTYPE = 1, BF_QIDX = 2, BF_VIDX = 3, BF_DEPTH = 4, BF_SUBTREE = 5,
-  BF_JPOS = 6, BF_JROT = 9, BF_AXIS = 18, BF_MASS = 21, BF_COM = 22, BF_INERTIA = 25, BF_COUNT = 31
+  BF_JPOS = 6, BF_JROT = 9, BF_AXIS = 18, BF_MASS = 21, BF_COM = 22, BF_INERTIA = 25, BF_LO = 31, BF_HI = 32, BF_COUNT = 33
 };
 enum PoseField { PF_R = 0, PF_P = 9, PF_A = 12, PF_COUNT = 15 };
 enum CtField { CF_POS = 0, CF_N = 3, CF_T1 = 6, CF_T2 = 9, CF_DEPTH = 12, CF_PT = 13, CF_BODY = 14, CF_PAIR = 15 };
@@ -77,7 +80,7 @@ __host__ __device__ constexpr BlobHeader make_blob_header(Dims d, int npts, int 
   H.nbase = d.floating ? 6 : 0; H.maxdd = d.maxdd; H.dlp = (d.maxdd + 1) | 1; H.nent = nent;
   const int DL = d.maxdd + 1;
   int off = HEADER_WORDS;
-  H.off_body = off; off += 31 * H.nbp;
+  H.off_body = off; off += 33 * H.nbp;
   H.off_anc = off; off += max_c(1, d.maxdepth) * H.nbp;
   H.off_gain = off; off += 2 * H.nvp;
   H.off_dofq = off; off += H.nvp;
@@ -99,7 +102,7 @@ __host__ __device__ constexpr BlobHeader make_blob_header(Dims d, int npts, int 
 
 // per-warp workspace layout (word offsets)
 struct WsLayout {
-  int o_gc, o_gv, o_tau, o_pt, o_vt, o_L, o_invd, o_rhs, o_z, o_ct, o_Y, o_lam, o_u;   // persistent
+  int o_gc, o_gv, o_tau, o_pt, o_vt, o_L, o_invd, o_rhs, o_z, o_ct, o_Y, o_lam, o_u, o_lim;   // persistent
   int o_h, o_b, o_pose;                                                                  // union A
   int o_G;                                                                               // union B
   int words;
@@ -122,13 +125,14 @@ __host__ __device__ constexpr WsLayout make_ws_layout(Dims d) {
   L.o_Y = o; o += round_up_c((d.maxdd + 1) * CP, 4);              // [ancestor depth][contact row]
   L.o_lam = o; o += 32;
   L.o_u = o; o += 12 * KMAX;
+  L.o_lim = o; o += 4 * LMAX;                                     // joint-limit rows: dof, sign, violation
   // union: {h, b, poses} (stages A-C) overlaid by G (stages C-D)
   int ua = 0;
   L.o_h = o + ua; ua += nvp;
   L.o_b = o + ua; ua += nvp;
   L.o_pose = o + ua; ua += round_up_c(15 * nbp, 4);
   L.o_G = o;
-  const int ub = round_up_c(CMAX * GP, 4);
+  const int ub = round_up_c(RMAX * GP, 4);
   o += max_c(ua, ub);
   L.words = round_up_c(o, 32);
   return L;
@@ -410,7 +414,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
   float* const ws = reinterpret_cast<float*>(smem) + warp * WSO(words);
   float* s_gc = ws + WSO(o_gc); float* s_gv = ws + WSO(o_gv); float* s_tau = ws + WSO(o_tau); float* s_pt = ws + WSO(o_pt); float* s_vt = ws + WSO(o_vt);
   float* s_L = ws + WSO(o_L); float* s_invd = ws + WSO(o_invd); float* s_rhs = ws + WSO(o_rhs); float* s_z = ws + WSO(o_z); float* s_ct = ws + WSO(o_ct);
-  float* s_Y = ws + WSO(o_Y); float* s_lam = ws + WSO(o_lam); float* s_u = ws + WSO(o_u);
+  float* s_Y = ws + WSO(o_Y); float* s_lam = ws + WSO(o_lam); float* s_u = ws + WSO(o_u); float* s_lim = ws + WSO(o_lim);
   float* s_h = ws + WSO(o_h); float* s_b = ws + WSO(o_b); float* s_pose = ws + WSO(o_pose); float* s_G = ws + WSO(o_G);
 #undef WSO
 #undef HO
@@ -707,6 +711,23 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
 
       if (args.substep_barrier >= 2) asm volatile("bar.sync 1, %0;" ::"r"(bar_threads));
       // =========================== stage C: b, Mhat = L^T L, z, Y, G ==============================
+      // a9 joint limits: the first LMAX joints found beyond their URDF limit become unilateral rows sign * qdot >= target
+      int Lm = 0;
+      if (args.prm.joint_limits) {
+        float q = 0.f, lo = -3.0e38f, hi = 3.0e38f;
+        if (bvalid && b > 0) { q = s_gc[bodyi[BF_QIDX * nbp + b]]; lo = bodyf[BF_LO * nbp + b]; hi = bodyf[BF_HI * nbp + b]; }
+        const bool act = q < lo || q > hi;
+        const unsigned lm_mask = __ballot_sync(FULL, act);
+        const int slot = __popc(lm_mask & ((1u << lane) - 1u));
+        if (act && slot < LMAX) {
+          s_lim[4 * slot + 0] = __int_as_float(my_vidx);
+          s_lim[4 * slot + 1] = q < lo ? 1.f : -1.f;
+          s_lim[4 * slot + 2] = q < lo ? lo - q : q - hi;
+        }
+        Lm = min(__popc(lm_mask), LMAX);
+        __syncwarp();
+      }
+      const int C3 = C, CR = C3 + Lm;   // contact rows, all constraint rows
 #pragma unroll 1
       for (int i = lane; i < nv; i += 32) {
         float bi = s_tau[i] - s_h[i];
@@ -801,36 +822,45 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         }
         __syncwarp();
       }
-      // ---- Y = L^-T J^T, one contact row per lane, only along the contact body's own ancestor chain
+      // ---- Y = L^-T J^T, one constraint row per lane, only along the row's own ancestor chain
       float u_c = 0.f;
-      if (lane < C) {
+      if (lane < CR) {
         const int c = lane;
-        const float* ct = s_ct + (c / 3) * CT_WORDS;
+        const bool is_lim = c >= C3;
+        const float* ct = s_ct + (is_lim ? 0 : c / 3) * CT_WORDS;
+        const float* lm = s_lim + 4 * (is_lim ? c - C3 : 0);
         const int d = c % 3;
         const int fo = (d == 0) ? CF_T1 : (d == 1 ? CF_T2 : CF_N);
         const f3 axd = mk(ct[fo], ct[fo + 1], ct[fo + 2]);
         const f3 pos = mk(ct[CF_POS], ct[CF_POS + 1], ct[CF_POS + 2]);
-        const int i0 = bdof[__float_as_int(ct[CF_BODY])];
+        const int i0 = is_lim ? __float_as_int(lm[0]) : bdof[__float_as_int(ct[CF_BODY])];
         const int m = i0 >= 0 ? ddepth[i0] : -1;
         float jv = 0.f;
-        if (floating) {
-          f3 rc = cross(pos - O, axd);
-          s_Y[0 * CP + c] = axd.x; s_Y[1 * CP + c] = axd.y; s_Y[2 * CP + c] = axd.z;
-          s_Y[3 * CP + c] = rc.x; s_Y[4 * CP + c] = rc.y; s_Y[5 * CP + c] = rc.z;
-          jv = axd.x * s_gv[0] + axd.y * s_gv[1] + axd.z * s_gv[2] + rc.x * s_gv[3] + rc.y * s_gv[4] + rc.z * s_gv[5];
-        }
+        if (is_lim) {   // J = sign * e_dof
 #pragma unroll 1
-        for (int t = nbase; t <= m; t++) {
-          const int a_t = danc[t * nvp + i0], j = dbody[a_t];
-          f3 aj = mk(s_pose[(PF_A + 0) * nbp + j], s_pose[(PF_A + 1) * nbp + j], s_pose[(PF_A + 2) * nbp + j]);
-          f3 col = aj;
-          if (bodyi[BF_JTYPE * nbp + j] == 1) {
-            f3 pj = mk(s_pose[(PF_P + 0) * nbp + j], s_pose[(PF_P + 1) * nbp + j], s_pose[(PF_P + 2) * nbp + j]);
-            col = cross(aj, pos - pj);
+          for (int t = 0; t < m; t++) s_Y[t * CP + c] = 0.f;
+          s_Y[m * CP + c] = lm[1];
+          jv = lm[1] * s_gv[i0];
+        } else {
+          if (floating) {
+            f3 rc = cross(pos - O, axd);
+            s_Y[0 * CP + c] = axd.x; s_Y[1 * CP + c] = axd.y; s_Y[2 * CP + c] = axd.z;
+            s_Y[3 * CP + c] = rc.x; s_Y[4 * CP + c] = rc.y; s_Y[5 * CP + c] = rc.z;
+            jv = axd.x * s_gv[0] + axd.y * s_gv[1] + axd.z * s_gv[2] + rc.x * s_gv[3] + rc.y * s_gv[4] + rc.z * s_gv[5];
           }
-          float val = dot(col, axd);
-          s_Y[t * CP + c] = val;
-          jv += val * s_gv[a_t];
+#pragma unroll 1
+          for (int t = nbase; t <= m; t++) {
+            const int a_t = danc[t * nvp + i0], j = dbody[a_t];
+            f3 aj = mk(s_pose[(PF_A + 0) * nbp + j], s_pose[(PF_A + 1) * nbp + j], s_pose[(PF_A + 2) * nbp + j]);
+            f3 col = aj;
+            if (bodyi[BF_JTYPE * nbp + j] == 1) {
+              f3 pj = mk(s_pose[(PF_P + 0) * nbp + j], s_pose[(PF_P + 1) * nbp + j], s_pose[(PF_P + 2) * nbp + j]);
+              col = cross(aj, pos - pj);
+            }
+            float val = dot(col, axd);
+            s_Y[t * CP + c] = val;
+            jv += val * s_gv[a_t];
+          }
         }
         float yz = 0.f;
         if constexpr (ST && SMAXDD + 1 <= 9) {
@@ -864,7 +894,8 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
           }
         }
         u_c = jv + dt * yz;
-        if (d == 2) {
+        if (is_lim) u_c -= args.prm.erp * lm[2] / dt;
+        else if (d == 2) {
           float target = args.prm.erp * ct[CF_DEPTH] / dt;
           if (args.prm.restitution > 0.f && jv < -args.prm.rest_threshold) target += -args.prm.restitution * jv;
           u_c -= target;
@@ -872,18 +903,18 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       }
       iters = 0;
       float lam_c = 0.f;
-      if (K > 0) {
+      if (CR > 0) {
         __syncwarp();      // h / b / poses are dead from here: G overlays them
         // G = Y^T Y; rows a, b share ancestors exactly up to the depth of their bodies' LCA
         {
-          const int ng = 32 / C;                    // C <= 24 -> ng >= 1
-          const int a = lane % C, g = lane / C;
+          const int ng = 32 / CR;                   // CR <= 28 -> ng >= 1
+          const int a = lane % CR, g = lane / CR;
           if (g < ng) {
-            const int ba = __float_as_int(s_ct[(a / 3) * CT_WORDS + CF_BODY]);
+            const int ba = a < C3 ? __float_as_int(s_ct[(a / 3) * CT_WORDS + CF_BODY]) : dbody[__float_as_int(s_lim[4 * (a - C3)])];
 #pragma unroll 1
-            for (int dd = g; dd <= C / 2; dd += ng) {
-              int bcol = a + dd; if (bcol >= C) bcol -= C;
-              const int bbody = __float_as_int(s_ct[(bcol / 3) * CT_WORDS + CF_BODY]);
+            for (int dd = g; dd <= CR / 2; dd += ng) {
+              int bcol = a + dd; if (bcol >= CR) bcol -= CR;
+              const int bbody = bcol < C3 ? __float_as_int(s_ct[(bcol / 3) * CT_WORDS + CF_BODY]) : dbody[__float_as_int(s_lim[4 * (bcol - C3)])];
               const int tmax = lcad[ba * nbp + bbody];
               float sacc = 0.f;
 #pragma unroll 1
@@ -924,9 +955,20 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
                        ui.z - (Gs[2] * l0.x + Gs[4] * l0.y + Gs[5] * l0.z));
             f3 ln = solve_contact(Gs, Gs + 6, c0, mu, sec_c, sec_s, lane);
             f3 dl = alpha * (ln - l0);
-            if (lane < C) u_c += s_G[lane * GP + i3] * dl.x + s_G[lane * GP + i3 + 1] * dl.y + s_G[lane * GP + i3 + 2] * dl.z;
+            if (lane < CR) u_c += s_G[lane * GP + i3] * dl.x + s_G[lane * GP + i3 + 1] * dl.y + s_G[lane * GP + i3 + 2] * dl.z;
             if (lane == i3) lam_c = l0.x + dl.x; else if (lane == i3 + 1) lam_c = l0.y + dl.y; else if (lane == i3 + 2) lam_c = l0.z + dl.z;
             err = fmaxf(err, fmaxf(fabsf(dl.x), fmaxf(fabsf(dl.y), fabsf(dl.z))));
+          }
+#pragma unroll 1
+          for (int l = 0; l < Lm; l++) {   // joint limits: lam >= 0, complementary to sign * qdot+ - target >= 0
+            const int r = C3 + l;
+            const float ur = __shfl_sync(FULL, u_c, r), lr = __shfl_sync(FULL, lam_c, r);
+            const float Grr = s_G[r * GP + r];
+            const float ln = fmaxf(0.f, -(ur - Grr * lr) / Grr);
+            const float dl = alpha * (ln - lr);
+            if (lane < CR) u_c += s_G[lane * GP + r] * dl;
+            if (lane == r) lam_c = lr + dl;
+            err = fmaxf(err, fabsf(dl));
           }
           iters = it + 1;
           alpha = fmaxf(args.prm.alpha_min, alpha * args.prm.alpha_decay);
@@ -936,7 +978,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
             err_ckpt = err; next_ckpt += args.prm.stall_window;
           }
         }
-        if (lane < C) s_lam[lane] = lam_c;
+        if (lane < CR) s_lam[lane] = lam_c;
         __syncwarp();
       }
       __syncwarp();
@@ -951,6 +993,11 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
           const int i0 = bdof[__float_as_int(s_ct[k * CT_WORDS + CF_BODY])];
           if (i0 >= 0 && ddepth[i0] >= di && danc[di * nvp + i0] == i)
             sacc += s_Y[di * CP + 3 * k] * s_lam[3 * k] + s_Y[di * CP + 3 * k + 1] * s_lam[3 * k + 1] + s_Y[di * CP + 3 * k + 2] * s_lam[3 * k + 2];
+        }
+#pragma unroll 1
+        for (int l = 0; l < Lm; l++) {
+          const int i0 = __float_as_int(s_lim[4 * l]);
+          if (ddepth[i0] >= di && danc[di * nvp + i0] == i) sacc += s_Y[di * CP + C3 + l] * s_lam[C3 + l];
         }
         s_rhs[i] = sacc;
       }

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(capi.Contact) == 48       # 12 words, SURVEY 8d algorithmic-bytes formula
-    assert ctypes.sizeof(capi.Params) == 4 * 15
+    assert ctypes.sizeof(capi.Params) == 4 * 16
 
 
 @pytest.mark.parametrize("src", ["anymal_c_like.urdf", "atlas_like.urdf", PENDULUM_URDF, BOX_URDF, REALISTIC_URDF])

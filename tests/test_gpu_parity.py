@@ -578,3 +578,61 @@ def test_cpp_multi_gpu_allgather_example(capi):
     print(out.stdout, out.stderr[-500:])
     assert out.returncode == 0, out.stdout + out.stderr
     assert f"{ndev} GPU(s)" in out.stdout and "ok" in out.stdout
+
+
+def test_joint_limits_match_oracle(capi):
+    """a9 joint limits as unilateral rows of the same Gauss-Seidel solve: generic kernel (fixed-base pendulum with a
+    stop) and specialised kernel (ANYmal-like HAA joints swung into their stops, on the ground with contacts)."""
+    from test_oracle_kat import LIMIT_PENDULUM
+    # 1. pendulum hitting its stop
+    t = load_tables(LIMIT_PENDULUM)
+    bt = capi.Batch(capi.Model(LIMIT_PENDULUM), 8)
+    bt.set_params(gravity=(0.0, 0.0, 0.0), threshold=THRESH, stall_window=0)
+    q0 = np.linspace(0.4013, 0.4679, 8)[:, None]; v0 = np.full((8, 1), 2.1)     # never lands exactly on the stop
+    bt.set_state(q0.astype(np.float32), v0.astype(np.float32))
+    o = Oracle(t, params=dict(gz=0.0, threshold=THRESH, stall_window=0))
+    a, b = q0.astype(np.float32).astype(np.float64), v0.copy()
+    for k in range(60):
+        bt.integrate(1)
+        o.step(a, b)
+    g, v = bt.get_state()
+    assert np.abs(g - a).max() < 1e-5 and np.abs(v - b).max() < 1e-5
+    assert (g <= 0.5 + 2.1 * 0.0025 + 1e-6).all() and np.abs(v).max() < 1e-6
+    # 2. quadruped: HAA joints driven into their stops by PD targets beyond the limits
+    n = 128
+    path = os.path.join(RSC, "anymal_c_like.urdf")
+    t = load_tables(path)
+    bt = capi.Batch(capi.Model(path), n)
+    bt.set_ground(0.0)
+    bt.set_params(threshold=THRESH, stall_window=0)
+    rng = np.random.default_rng(161)
+    gc = np.tile(ANYMAL_GC0, (n, 1)); gc[:, 2] = 0.58; gc[:, 7:] += rng.uniform(-0.1, 0.1, (n, 12))
+    gv = np.zeros((n, 18))
+    target = np.tile(ANYMAL_GC0, (n, 1)); target[:, [7, 10, 13, 16]] = rng.choice([-1.2, 0.9], (n, 4))   # beyond (-0.72, 0.49)
+    kp = np.r_[np.zeros(6), 150.0 * np.ones(12)]; kd = np.r_[np.zeros(6), 3.0 * np.ones(12)]
+    bt.set_pd_gains(kp, kd)
+    gc32, t32 = gc.astype(np.float32), target.astype(np.float32)
+    bt.set_state(gc32, gv.astype(np.float32)); bt.set_pd_target(t32, np.zeros((n, 18), np.float32))
+    o = Oracle(t, params=dict(threshold=THRESH, stall_window=0))
+    o.set_ground(0.0)
+    a, b = gc32.astype(np.float64), gv.copy()
+    active = 0
+    for k in range(12):
+        bt.integrate(5)
+        d = o.step(a, b, n_steps=5, ptarget=t32.astype(np.float64), vtarget=np.zeros((n, 18)), kp=kp, kd=kd, debug=True)
+        active += int(d["nlimits"].sum())
+    g, v = bt.get_state()
+    haa = g[:, [7, 10, 13, 16]]
+    print(f"joint-limit parity: {active} active limit rows seen; HAA range [{haa.min():.3f}, {haa.max():.3f}]")
+    assert active > n                                   # the stops are really engaged
+    ref_haa = a[:, [7, 10, 13, 16]]
+    # the overshoot past a stop is one step of the arrival velocity (several rad/s under this PD drive)
+    assert haa.max() < 0.49 + 0.1 and haa.min() > -0.72 - 0.1
+    assert abs(haa.max() - ref_haa.max()) < 5e-3 and abs(haa.min() - ref_haa.min()) < 5e-3
+    e = np.abs(g - a).max(1)
+    assert np.median(e) < 5e-5 and np.quantile(e, 0.9) < 5e-3
+    # switched off, the joints leave their range
+    bt.set_params(joint_limits=0)
+    bt.set_state(gc32, gv.astype(np.float32))
+    bt.integrate(60)
+    assert bt.get_state()[0][:, [7, 10, 13, 16]].max() > 0.6

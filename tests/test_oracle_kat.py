@@ -440,3 +440,71 @@ def test_bisection_and_32_section_slip_search_agree(anymal_tables):
         outs.append((a, b, d["iters"]))
     conv = (outs[0][2] < 150) & (outs[1][2] < 150)
     assert np.abs(outs[0][1] - outs[1][1])[conv].max() < 1e-5
+
+
+LIMIT_PENDULUM = """<robot name="p"><link name="world"/>
+  <link name="l"><inertial><origin xyz="0 0 -0.5"/><mass value="2.0"/><inertia ixx="0.1" ixy="0" ixz="0" iyy="0.1" iyz="0" izz="0.01"/></inertial></link>
+  <joint name="j" type="revolute"><parent link="world"/><child link="l"/><origin xyz="0 0 1"/><axis xyz="0 1 0"/>
+    <limit lower="-0.5" upper="0.5" effort="10" velocity="10"/></joint></robot>"""
+
+
+def test_joint_limit_stops_motion_inelastically():
+    t = load_tables(LIMIT_PENDULUM)
+    o = Oracle(t, params=dict(gz=0.0))
+    gc, gv = np.array([[0.45]]), np.array([[2.0]])
+    qs = []
+    for k in range(40):
+        d = o.step(gc, gv, n_steps=1, debug=True)
+        qs.append(gc[0, 0])
+    assert max(qs) <= 0.5 + 2.0 * 0.0025 + 1e-12        # at most one step of overshoot
+    assert abs(gv[0, 0]) < 1e-12 and d["nlimits"][0] == 1 and d["lim_dof"][0, 0] == 0
+    # ERP turns the overshoot into an inward velocity erp * viol / dt; the row releases once the joint is back inside
+    q_over = gc[0, 0]
+    o.set_params(erp=0.2)
+    o.step(gc, gv, n_steps=1)
+    assert abs(gv[0, 0] + 0.2 * (q_over - 0.5) / 0.0025) < 1e-9
+    o.step(gc, gv, n_steps=100)
+    assert gc[0, 0] < 0.5 and gv[0, 0] < 0
+    # switched off: the joint sails through
+    o2 = Oracle(t, params=dict(gz=0.0, joint_limits=0))
+    gc, gv = np.array([[0.45]]), np.array([[2.0]])
+    o2.step(gc, gv, n_steps=40)
+    assert gc[0, 0] > 0.6
+
+
+def test_joint_limit_reaction_balances_gravity():
+    t = load_tables(LIMIT_PENDULUM)
+    o = Oracle(t)
+    q0 = 0.5004                                          # resting just beyond the upper stop, gravity pulls it back? no: push it out
+    o.set_params(gx=3.0)                                 # a sideways "gravity" component presses the link against the stop
+    gc, gv = np.array([[q0]]), np.array([[0.0]])
+    d = o.step(gc, gv, n_steps=1, debug=True)
+    m, l, I, dt = 2.0, 0.5, 0.1, 0.0025
+    # generalized force of gravity about +y at angle q: COM at (-l sin q, 0, -l cos q)
+    tau_g = m * (3.0 * (-l * np.cos(q0)) - (-9.81) * (-l * np.sin(q0)))
+    if tau_g > 0:                                        # gravity drives q further past the stop: the stop must hold it
+        assert d["nlimits"][0] == 1
+        assert abs(d["lim_lambda"][0, 0] - tau_g * dt) < 1e-9
+        assert abs(gv[0, 0]) < 1e-12
+    else:                                                # gravity pulls it back inside: the row stays passive
+        assert abs(d["lim_lambda"][0, 0]) < 1e-15 and gv[0, 0] < 0
+
+
+def test_joint_limit_is_internal_momentum_conserved(anymal_tables):
+    """a limit impulse is an internal generalized force: total momentum of the free-floating robot is unchanged"""
+    t = anymal_tables
+    o = Oracle(t, params=dict(gz=0.0, dt=1e-3))
+    gc = ANYMAL_GC0[None].copy(); gc[0, 2] = 5.0
+    gc[0, 7] = 0.49 - 1e-4                               # LF_HAA just inside its upper stop (0.49)
+    gv = np.zeros((1, 18)); gv[0, 6] = 3.0               # swinging into it
+    M0 = mass_matrix_numpy(t, gc[0]); P0, L0 = M0[0:3] @ gv[0], M0[3:6] @ gv[0] + np.cross(gc[0, 0:3], M0[0:3] @ gv[0])
+    hit = 0
+    for k in range(30):
+        d = o.step(gc, gv, n_steps=1, debug=True)
+        hit += int(d["nlimits"][0] > 0 and d["lim_lambda"][0, 0] > 0)
+    M1 = mass_matrix_numpy(t, gc[0]); P1, L1 = M1[0:3] @ gv[0], M1[3:6] @ gv[0] + np.cross(gc[0, 0:3], M1[0:3] @ gv[0])
+    assert hit >= 1
+    assert gc[0, 7] < 0.49 + 3.0 * 1e-3 + 1e-9           # stopped within one step of overshoot
+    # an impulsive stop changes v by 3 rad/s inside one step while the bias force was evaluated with the pre-impact
+    # velocity: the discrete momentum error of that single step is O(dt * |h|) ~ 6e-3, then it stays constant
+    assert np.allclose(P1, P0, atol=1e-2) and np.allclose(L1, L0, atol=1e-2 * np.abs(L0).max() + 1e-6)
