@@ -13,6 +13,8 @@
 // std::runtime_error with rsb_last_error() (define RAISIM_B200_ABORT_ON_ERROR to abort instead).
 // Units and conventions are the reference's: gc = [xyz | qw qx qy qz | joints], gv = [v | w | joint rates].
 #pragma once
+#include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -93,6 +95,13 @@ class BatchedWorld {
 class Ground {};
 class HeightMap {};
 
+// raisim::TerrainProperties ([RECALL] include/raisim/object/terrain/HeightMap.hpp)
+struct TerrainProperties {
+  double frequency = 0.1, xSize = 10.0, ySize = 10.0, zScale = 2.0, fractalLacunarity = 2.0, fractalGain = 0.5, stepSize = 0.0, heightOffset = 0.0;
+  size_t xSamples = 100, ySamples = 100, fractalOctaves = 5;
+  std::uint32_t seed = 1;
+};
+
 // raisim::ArticulatedSystem -- a view of one environment's robot
 class ArticulatedSystem {
  public:
@@ -154,6 +163,43 @@ class ArticulatedSystem {
     MatDyn M; M.resize(nv, nv);
     for (int i = 0; i < nv; i++) for (int j = 0; j < nv; j++) M(i, j) = m[size_t(i) * nv + j];
     return M;
+  }
+  // M^-1 from the lazy M getter (dense Cholesky on the host: a convenience getter, not the hot path -- the kernel
+  // never forms M^-1, it keeps the branch-sparse factor on chip)
+  MatDyn getInverseMassMatrix() const {
+    MatDyn M = getMassMatrix();
+    const int n = int(M.rows());
+    std::vector<double> L(size_t(n) * n, 0.0);
+    for (int j = 0; j < n; j++) {
+      double s = M(j, j);
+      for (int k = 0; k < j; k++) s -= L[j * n + k] * L[j * n + k];
+      const double d = std::sqrt(s);
+      L[j * n + j] = d;
+      for (int i = j + 1; i < n; i++) {
+        double t = M(i, j);
+        for (int k = 0; k < j; k++) t -= L[i * n + k] * L[j * n + k];
+        L[i * n + j] = t / d;
+      }
+    }
+    MatDyn Minv; Minv.resize(n, n);
+    std::vector<double> x(n);
+    for (int c = 0; c < n; c++) {
+      for (int i = 0; i < n; i++) { double s = (i == c) ? 1.0 : 0.0; for (int k = 0; k < i; k++) s -= L[i * n + k] * x[k]; x[i] = s / L[i * n + i]; }
+      for (int i = n - 1; i >= 0; i--) { double s = x[i]; for (int k = i + 1; k < n; k++) s -= L[k * n + i] * x[k]; x[i] = s / L[i * n + i]; }
+      for (int i = 0; i < n; i++) Minv(i, c) = x[i];
+    }
+    return Minv;
+  }
+  VecDyn getGeneralizedForce() const {
+    std::vector<float> t(w_->nv());
+    rsbCheck(rsb_batch_get_generalized_force(w_->batch(), t.data(), env_, 1, RSB_HOST), "getGeneralizedForce");
+    VecDyn r(t.size());
+    for (size_t i = 0; i < t.size(); i++) r[i] = t[i];
+    return r;
+  }
+  // friction of one collision body against the terrain (upstream: getCollisionBody(name).setMaterial + setMaterialPairProp)
+  void setCollisionBodyFriction(size_t collisionBodyIdx, double mu) {
+    rsbCheck(rsb_batch_set_collision_friction(w_->batch(), int(collisionBodyIdx), float(mu)), "setCollisionBodyFriction");
   }
   VecDyn getNonlinearities() const {
     std::vector<float> h(w_->nv());
@@ -221,6 +267,16 @@ class World {
     need();
     std::vector<float> h(height.begin(), height.end());
     rsbCheck(rsb_batch_set_heightmap(w_->batch(), int(xSamples), int(ySamples), float(xSize), float(ySize), float(centerX), float(centerY), h.data()), "addHeightMap");
+    return &hm_;
+  }
+  HeightMap* addHeightMap(double centerX, double centerY, const TerrainProperties& tp, const std::string& = "default", CollisionGroup = 1,
+                          CollisionGroup = CollisionGroup(-1)) {
+    need();
+    rsb_terrain_properties p{int(tp.xSamples), int(tp.ySamples), tp.xSize, tp.ySize, tp.frequency, tp.zScale, int(tp.fractalOctaves), tp.fractalLacunarity,
+                             tp.fractalGain, tp.stepSize, tp.heightOffset, tp.seed};
+    std::vector<float> h(tp.xSamples * tp.ySamples);
+    rsbCheck(rsb_terrain_generate(&p, h.data()), "TerrainGenerator");
+    rsbCheck(rsb_batch_set_heightmap(w_->batch(), int(tp.xSamples), int(tp.ySamples), float(tp.xSize), float(tp.ySize), float(centerX), float(centerY), h.data()), "addHeightMap");
     return &hm_;
   }
   void setTimeStep(double dt) { dt_ = dt; if (w_) { rsb_params p = w_->params(); p.dt = float(dt); w_->setParams(p); } }

@@ -124,6 +124,9 @@ int rsb_batch_clear_terrain(rsb_batch* b);
 int rsb_batch_set_params(rsb_batch* b, const rsb_params* p);
 int rsb_batch_get_params(const rsb_batch* b, rsb_params* p);
 int rsb_params_default(rsb_params* p);
+/* friction of one collision body (index in rsb_model_tables order) against the terrain; mu < 0 = default material.
+ * The per-body half of World::setMaterialPairProp / getCollisionBody(name).setMaterial */
+int rsb_batch_set_collision_friction(rsb_batch* b, int collision_body, float mu);
 
 /* ---- state and actuation (ArticulatedSystem::setState/getState/setPdGains/setPdTarget/
  *      setGeneralizedForce/setControlMode); buffers are tight [env_count][nq|nv] float32 ---------- */
@@ -162,6 +165,21 @@ int rsb_batch_observe(rsb_batch* b, float* obs, int env_begin, int env_count, in
 /* VectorizedEnvironment::step() for the whole batch in one call: targets in, `substeps` fused
  * World::integrate() calls, observation rows out (either pointer may be NULL to skip that leg) */
 int rsb_batch_control_step(rsb_batch* b, const float* ptarget, const float* vtarget, int where_in, int substeps, float* obs, int where_out);
+
+/* ---- terrain generation (raisim::TerrainProperties, World::addHeightMap(centerX, centerY, terrainProperties)) ------ */
+typedef struct rsb_terrain_properties {
+  int x_samples, y_samples;      /* TerrainProperties::xSamples, ySamples */
+  double x_size, y_size;         /* xSize, ySize [m]                       */
+  double frequency;              /* base frequency of the noise [1/m]      */
+  double z_scale;                /* zScale                                 */
+  int fractal_octaves;           /* fractalOctaves                         */
+  double fractal_lacunarity;     /* fractalLacunarity                      */
+  double fractal_gain;           /* fractalGain                            */
+  double step_size;              /* stepSize (0 = smooth)                  */
+  double height_offset;          /* heightOffset                           */
+  uint32_t seed;                 /* seed                                   */
+} rsb_terrain_properties;
+int rsb_terrain_generate(const rsb_terrain_properties* p, float* heights_out /* [y_samples][x_samples] */);
 
 /* ---- multi-GPU inside one process: one rsb_batch per GPU, NCCL all-gather of the observation rows ----
  *      (NCCL is bound at run time; bench.py uses torch.distributed for the same collective, one process per GPU) */

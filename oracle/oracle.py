@@ -56,6 +56,7 @@ def lib():
         _lib.orc_clear_terrain.argtypes = [C.c_void_p]
         _lib.orc_step.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p]
         _lib.orc_solve_one.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        _lib.orc_set_point_mu.argtypes = [C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -102,6 +103,13 @@ class Oracle:
 
     def clear_terrain(self):
         lib().orc_clear_terrain(self.h)
+
+    def set_collision_friction(self, collision_body, mu):
+        """friction of every candidate point of one collision body (mu < 0: default material)"""
+        if not hasattr(self, "_pt_mu"):
+            self._pt_mu = np.full(self.t["npts"], -1.0)
+        self._pt_mu[np.asarray(self.t["pt_coll"]) == collision_body] = mu
+        lib().orc_set_point_mu(self.h, _p(self._pt_mu))
 
     def step(self, gc, gv, n_steps=1, tau_ff=None, ptarget=None, vtarget=None, kp=None, kd=None, nthreads=0, debug=False):
         """gc [n,nq], gv [n,nv] float64 C-contiguous, updated IN PLACE.  Returns debug dict or None."""

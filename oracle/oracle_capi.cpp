@@ -164,6 +164,13 @@ void orc_solve_one(void* hv, const double* G, const double* c, double mu, double
   }
 }
 
+// per-candidate-point friction override (< 0: default material)
+void orc_set_point_mu(void* hv, const double* mu) {
+  Handle* h = static_cast<Handle*>(hv);
+  if (h->d) for (int i = 0; i < h->d->npts; i++) h->d->pt_mu[i] = mu[i];
+  else for (int i = 0; i < h->f->npts; i++) h->f->pt_mu[i] = float(mu[i]);
+}
+
 int orc_max_threads() { return omp_get_max_threads(); }
 
 }  // extern "C"

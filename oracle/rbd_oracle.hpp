@@ -136,7 +136,7 @@ template <typename T> class Sim {
   std::vector<int> parent, jtype, qidx, vidx, pt_body;
   std::vector<V3<T>> jpos, axis, com, pt_pos;
   std::vector<M3<T>> jrot;
-  std::vector<T> mass, inertia, pt_rad, jlo, jhi;
+  std::vector<T> mass, inertia, pt_rad, jlo, jhi, pt_mu;   // pt_mu < 0: default material friction
   Params prm;
   Terrain ter;
   std::vector<T> hmap;
@@ -157,7 +157,7 @@ template <typename T> class Sim {
     }
     jlo.assign(nb, T(-1e30)); jhi.assign(nb, T(1e30));
     if (d.jlimit) for (int i = 0; i < nb; i++) { jlo[i] = T(d.jlimit[2 * i]); jhi[i] = T(d.jlimit[2 * i + 1]); }
-    pt_body.assign(d.pt_body, d.pt_body + npts); pt_pos.resize(npts); pt_rad.resize(npts);
+    pt_body.assign(d.pt_body, d.pt_body + npts); pt_pos.resize(npts); pt_rad.resize(npts); pt_mu.assign(npts, T(-1));
     for (int i = 0; i < npts; i++) {
       pt_pos[i] = {T(d.pt_pos[3 * i]), T(d.pt_pos[3 * i + 1]), T(d.pt_pos[3 * i + 2])};
       pt_rad[i] = T(d.pt_rad[i]);
@@ -622,7 +622,7 @@ template <typename T> class Sim {
                       ws.u[3 * i + 1] - (Gii[3] * l0.x + Gii[4] * l0.y + Gii[5] * l0.z),
                       ws.u[3 * i + 2] - (Gii[6] * l0.x + Gii[7] * l0.y + Gii[8] * l0.z)};
           V3<T> ln;
-          solve_one(Gii, c0, mu, ln);
+          solve_one(Gii, c0, pt_mu[ct.pt] >= T(0) ? pt_mu[ct.pt] : mu, ln);
           V3<T> dl = alpha * (ln - l0);
           ct.lam = l0 + dl;
           for (int a = 0; a < C; a++) ws.u[a] += ws.G[a * C + 3 * i] * dl.x + ws.G[a * C + 3 * i + 1] * dl.y + ws.G[a * C + 3 * i + 2] * dl.z;

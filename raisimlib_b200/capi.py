@@ -45,6 +45,22 @@ class ModelTables(C.Structure):
                 [(n, C.POINTER(C.c_double)) for n in ("pt_pos", "pt_rad")])
 
 
+class TerrainProperties(C.Structure):
+    _fields_ = [("x_samples", C.c_int), ("y_samples", C.c_int), ("x_size", C.c_double), ("y_size", C.c_double), ("frequency", C.c_double),
+                ("z_scale", C.c_double), ("fractal_octaves", C.c_int), ("fractal_lacunarity", C.c_double), ("fractal_gain", C.c_double),
+                ("step_size", C.c_double), ("height_offset", C.c_double), ("seed", C.c_uint32)]
+
+
+def generate_terrain(x_samples=129, y_samples=129, x_size=12.8, y_size=12.8, frequency=0.2, z_scale=0.5, fractal_octaves=3,
+                     fractal_lacunarity=2.0, fractal_gain=0.25, step_size=0.0, height_offset=0.0, seed=1):
+    """raisim::TerrainProperties -> heights [y_samples, x_samples] float32 (host)"""
+    p = TerrainProperties(x_samples, y_samples, x_size, y_size, frequency, z_scale, fractal_octaves, fractal_lacunarity, fractal_gain,
+                          step_size, height_offset, seed)
+    out = np.empty((y_samples, x_samples), np.float32)
+    _ck(lib().rsb_terrain_generate(C.byref(p), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
 class DeviceView(C.Structure):
     _fields_ = ([(n, C.c_int) for n in ("num_envs", "nq", "nv", "gc_stride", "gv_stride")] +
                 [(n, C.c_void_p) for n in ("gc", "gv", "tau_ff", "ptarget", "vtarget", "ncontacts", "contacts")])
@@ -56,6 +72,7 @@ EXPORTED = [
     "rsb_model_body_name", "rsb_model_joint_name", "rsb_model_frame_index", "rsb_model_frame",
     "rsb_batch_create", "rsb_batch_destroy", "rsb_batch_set_stream", "rsb_batch_sync", "rsb_batch_num_envs",
     "rsb_batch_set_ground", "rsb_batch_set_heightmap", "rsb_batch_clear_terrain", "rsb_batch_set_params", "rsb_batch_get_params",
+    "rsb_batch_set_collision_friction",
     "rsb_batch_set_state", "rsb_batch_get_state", "rsb_batch_set_pd_gains", "rsb_batch_set_pd_target",
     "rsb_batch_set_generalized_force", "rsb_batch_set_control_mode", "rsb_batch_get_generalized_force", "rsb_batch_bind_pd_target",
     "rsb_batch_integrate1", "rsb_batch_integrate2", "rsb_batch_integrate",
@@ -63,7 +80,7 @@ EXPORTED = [
     "rsb_batch_get_contact_points", "rsb_batch_get_solver_iterations", "rsb_batch_get_diverged", "rsb_batch_device_ptrs", "rsb_batch_launch_count",
     "rsb_batch_ob_dim", "rsb_batch_observe", "rsb_batch_control_step",
     "rsb_batch_gym_configure", "rsb_batch_gym_reset", "rsb_batch_gym_step",
-    "rsb_comm_init", "rsb_comm_allgather_obs", "rsb_comm_destroy",
+    "rsb_comm_init", "rsb_comm_allgather_obs", "rsb_comm_destroy", "rsb_terrain_generate",
 ]
 
 _lib = None
@@ -101,6 +118,7 @@ def lib():
         L.rsb_batch_set_ground.argtypes = [C.c_void_p, C.c_float]
         L.rsb_batch_set_heightmap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.rsb_batch_clear_terrain.argtypes = [C.c_void_p]
+        L.rsb_batch_set_collision_friction.argtypes = [C.c_void_p, C.c_int, C.c_float]
         L.rsb_batch_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
         L.rsb_batch_get_params.argtypes = [C.c_void_p, C.POINTER(Params)]
         L.rsb_params_default.argtypes = [C.POINTER(Params)]
@@ -132,6 +150,7 @@ def lib():
         L.rsb_comm_init.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
         L.rsb_comm_allgather_obs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.rsb_comm_destroy.argtypes = [C.c_void_p]
+        L.rsb_terrain_generate.argtypes = [C.POINTER(TerrainProperties), C.c_void_p]
         _lib = L
     return _lib
 
@@ -227,6 +246,9 @@ class Batch:
 
     def clear_terrain(self):
         _ck(lib().rsb_batch_clear_terrain(self.h))
+
+    def set_collision_friction(self, collision_body, mu):
+        _ck(lib().rsb_batch_set_collision_friction(self.h, collision_body, mu))
 
     def get_params(self):
         p = Params()

@@ -126,6 +126,7 @@ static void build_blob(rsb_batch* b) {
     I(H.off_pts + 0 * H.nptp + k, md.pt_body[k]);
     for (int q = 0; q < 3; q++) F(H.off_pts + (1 + q) * H.nptp + k, (float)md.pt_pos[3 * k + q]);
     F(H.off_pts + 4 * H.nptp + k, (float)md.pt_rad[k]);
+    F(H.off_pts + 5 * H.nptp + k, -1.0f);
   }
   for (int i = 0; i < md.nv; i++) {
     F(H.off_gain + i, b->kp[i]); F(H.off_gain + H.nvp + i, b->kd[i]);
@@ -494,6 +495,18 @@ int rsb_batch_set_pd_gains(rsb_batch* b, const float* kp, const float* kd) {
   CK(cudaMemcpyAsync(b->blob + b->hdr.off_gain, b->blob_host.data() + b->hdr.off_gain, (size_t)2 * b->hdr.nvp * 4, cudaMemcpyHostToDevice, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   b->pd_set = true;
+  return RSB_OK;
+}
+// friction coefficient of one collision body against the terrain (mu < 0 restores the default material):
+// the per-body half of World::setMaterialPairProp / CollisionDefinition::setMaterial
+int rsb_batch_set_collision_friction(rsb_batch* b, int collision_body, float mu) {
+  if (!b) return fail(RSB_ERR_INVALID, "null batch");
+  const Model& md = b->model->md;
+  if (collision_body < 0 || collision_body >= md.ncoll()) return fail(RSB_ERR_INVALID, "collision body index out of range");
+  const BlobHeader& H = b->hdr;
+  for (int k = 0; k < md.npts(); k++) if (md.pt_coll[k] == collision_body) std::memcpy(&b->blob_host[H.off_pts + 5 * H.nptp + k], &mu, 4);
+  CK(cudaMemcpyAsync(b->blob + H.off_pts + 5 * H.nptp, b->blob_host.data() + H.off_pts + 5 * H.nptp, (size_t)H.nptp * 4, cudaMemcpyHostToDevice, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
   return RSB_OK;
 }
 int rsb_batch_set_pd_target(rsb_batch* b, const float* ptarget, const float* vtarget, int env_begin, int env_count, int where) {

@@ -94,7 +94,7 @@ __host__ __device__ constexpr BlobHeader make_blob_header(Dims d, int npts, int 
   H.off_lvldofs = off; off += H.nvp;
   H.off_entstart = off; off += DL + 1;
   H.off_lcad = off; off += (d.nb * H.nbp + 3) / 4;
-  H.off_pts = off; off += 5 * H.nptp;
+  H.off_pts = off; off += 6 * H.nptp;                 // body, pos(3), radius, friction override (< 0: default material)
   H.off_ent = off; off += max_c(1, nent);
   H.words = round_up_c(off, 4);
   return H;
@@ -124,7 +124,7 @@ __host__ __device__ constexpr WsLayout make_ws_layout(Dims d) {
   L.o_ct = o; o += KMAX * CT_WORDS;
   L.o_Y = o; o += round_up_c((d.maxdd + 1) * CP, 4);              // [ancestor depth][contact row]
   L.o_lam = o; o += 32;
-  L.o_u = o; o += 12 * KMAX;
+  L.o_u = o; o += 13 * KMAX;                                      // per contact: G_ii (6), its inverse (6), friction
   L.o_lim = o; o += 4 * LMAX;                                     // joint-limit rows: dof, sign, violation
   // union: {h, b, poses} (stages A-C) overlaid by G (stages C-D)
   int ua = 0;
@@ -933,7 +933,11 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
           float c00 = d * f - e * e, c01 = cc * e - bq * f, c02 = bq * e - cc * d;
           float c11 = a * f - cc * cc, c12 = bq * cc - a * e, c22 = a * d - bq * bq;
           float id = 1.0f / (a * c00 + bq * c01 + cc * c02);
-          float* o = s_Gii + 12 * lane;
+          float* o = s_Gii + 13 * lane;
+          {
+            const float pm = ptsf[5 * nptp + __float_as_int(s_ct[lane * CT_WORDS + CF_PT])];
+            o[12] = pm >= 0.f ? pm : mu;     // per-collision-body friction (World::setMaterialPairProp analogue)
+          }
           o[0] = a; o[1] = bq; o[2] = cc; o[3] = d; o[4] = e; o[5] = f;
           o[6] = c00 * id; o[7] = c01 * id; o[8] = c02 * id; o[9] = c11 * id; o[10] = c12 * id; o[11] = c22 * id;
         }
@@ -950,10 +954,10 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
             const int i3 = 3 * i;
             f3 ui = mk(__shfl_sync(FULL, u_c, i3), __shfl_sync(FULL, u_c, i3 + 1), __shfl_sync(FULL, u_c, i3 + 2));
             f3 l0 = mk(__shfl_sync(FULL, lam_c, i3), __shfl_sync(FULL, lam_c, i3 + 1), __shfl_sync(FULL, lam_c, i3 + 2));
-            const float* Gs = s_Gii + 12 * i;
+            const float* Gs = s_Gii + 13 * i;
             f3 c0 = mk(ui.x - (Gs[0] * l0.x + Gs[1] * l0.y + Gs[2] * l0.z), ui.y - (Gs[1] * l0.x + Gs[3] * l0.y + Gs[4] * l0.z),
                        ui.z - (Gs[2] * l0.x + Gs[4] * l0.y + Gs[5] * l0.z));
-            f3 ln = solve_contact(Gs, Gs + 6, c0, mu, sec_c, sec_s, lane);
+            f3 ln = solve_contact(Gs, Gs + 6, c0, Gs[12], sec_c, sec_s, lane);
             f3 dl = alpha * (ln - l0);
             if (lane < CR) u_c += s_G[lane * GP + i3] * dl.x + s_G[lane * GP + i3 + 1] * dl.y + s_G[lane * GP + i3 + 2] * dl.z;
             if (lane == i3) lam_c = l0.x + dl.x; else if (lane == i3 + 1) lam_c = l0.y + dl.y; else if (lane == i3 + 2) lam_c = l0.z + dl.z;

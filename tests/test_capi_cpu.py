@@ -107,3 +107,16 @@ def test_realistic_description_features():
     rim = t["pt_pos"][8:]
     assert np.allclose(np.hypot(rim[:, 0], rim[:, 1]), 0.025) and np.allclose(sorted(set(np.round(rim[:, 2], 6))), [-0.3, 0.0])
     assert t["jlimit"][1, 0] < -1e29                               # continuous joint: no limits
+
+
+def test_terrain_generator_properties():
+    """raisim::TerrainProperties analogue: deterministic per seed, bounded by the octave sum, frequency and steps honoured"""
+    a = capi.generate_terrain(seed=7); b = capi.generate_terrain(seed=7); c = capi.generate_terrain(seed=8)
+    assert a.shape == (129, 129) and np.array_equal(a, b) and not np.array_equal(a, c)
+    assert np.abs(a).max() <= 0.5 * (1 + 0.25 + 0.0625) and a.std() > 0.02
+    rough = capi.generate_terrain(seed=7, frequency=1.0)
+    assert np.abs(np.diff(rough, axis=1)).mean() > 2 * np.abs(np.diff(a, axis=1)).mean()     # higher frequency, steeper
+    st = capi.generate_terrain(seed=7, step_size=0.05)
+    assert np.allclose(st / 0.05, np.round(st / 0.05), atol=1e-4)
+    off = capi.generate_terrain(seed=7, height_offset=1.5)
+    assert np.allclose(off - a, 1.5, atol=1e-6)

@@ -636,3 +636,32 @@ def test_joint_limits_match_oracle(capi):
     bt.set_state(gc32, gv.astype(np.float32))
     bt.integrate(60)
     assert bt.get_state()[0][:, [7, 10, 13, 16]].max() > 0.6
+
+
+def test_per_body_friction_matches_oracle(capi):
+    """rsb_batch_set_collision_friction: feet with different friction on the quadruped, and the box-on-slope KAT"""
+    n = 128
+    t, bt, o64, o32, gc, gv, tau = _setup(capi, "anymal_c_like.urdf", n, seed=171, base_z=0.55, joint_scale=0.2, vel=1.0)
+    feet = [i for i, nme in enumerate(t["coll_names"]) if nme.endswith("_FOOT")]
+    assert len(feet) == 4
+    for k, ci in enumerate(feet):
+        bt.set_collision_friction(ci, 0.1 + 0.2 * k); o64.set_collision_friction(ci, 0.1 + 0.2 * k)
+    bt.integrate(20)
+    g, v = bt.get_state()
+    a, b = gc.copy(), gv.copy()
+    o64.step(a, b, n_steps=20, tau_ff=tau)
+    e = np.abs(g - a).max(1)
+    print(f"per-body friction 20-step error median {np.median(e):.2e} p90 {np.quantile(e, 0.9):.2e}")
+    assert np.median(e) < 2e-5 and np.quantile(e, 0.9) < 2e-3
+    mb = capi.Model(BOX_URDF)
+    th = np.deg2rad(20.0)
+    out = {}
+    for mu in (-1.0, 0.2):
+        bb = capi.Batch(mb, 1)
+        bb.set_ground(0.0)
+        bb.set_params(gravity=(9.81 * np.sin(th), 0.0, -9.81 * np.cos(th)))
+        bb.set_collision_friction(0, mu)
+        bb.set_state(np.array([[0, 0, 0.0999, 1, 0, 0, 0]], np.float32), np.zeros((1, 6), np.float32))
+        bb.integrate(100)
+        out[mu] = bb.get_state()[1][0, 0]
+    assert abs(out[-1.0]) < 1e-4 and 0.3 < out[0.2] < 0.45

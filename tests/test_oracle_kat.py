@@ -508,3 +508,20 @@ def test_joint_limit_is_internal_momentum_conserved(anymal_tables):
     # an impulsive stop changes v by 3 rad/s inside one step while the bias force was evaluated with the pre-impact
     # velocity: the discrete momentum error of that single step is O(dt * |h|) ~ 6e-3, then it stays constant
     assert np.allclose(P1, P0, atol=1e-2) and np.allclose(L1, L0, atol=1e-2 * np.abs(L0).max() + 1e-6)
+
+
+def test_per_body_friction_override():
+    """a low-friction collision body slides where the default material sticks (World::setMaterialPairProp analogue)"""
+    t = load_tables(BOX_URDF)
+    th = np.deg2rad(20.0)                                # tan 20 deg = 0.364: sticks at mu 0.8, slides at mu 0.2
+    res = {}
+    for mu in (-1.0, 0.2):
+        o = Oracle(t, params=dict(gx=G * np.sin(th), gz=-G * np.cos(th)))
+        o.set_ground(0.0)
+        o.set_collision_friction(0, mu)
+        gc = np.array([[0, 0, 0.0999, 1, 0, 0, 0.0]]); gv = np.zeros((1, 6))
+        o.step(gc, gv, n_steps=100)
+        res[mu] = gv[0, 0]
+    assert abs(res[-1.0]) < 1e-6
+    acc = G * (np.sin(th) - 0.2 * np.cos(th))
+    assert 0.9 * acc * 0.25 < res[0.2] <= 1.08 * acc * 0.25
