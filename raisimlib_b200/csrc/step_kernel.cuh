@@ -248,7 +248,14 @@ __device__ __forceinline__ float slip_energy(const Probe& p, float a, float b, f
 // Per-contact rule (opening / stick / slip).  G = [a b cc; b d e; cc e f], Gi = its inverse (sym, 6),
 // c = contact velocity without this contact's impulse.  All lanes call with identical arguments;
 // the slip branch spreads NSEC probes over the lanes.  Result identical on all lanes.
-__device__ __forceinline__ f3 solve_contact(const float* Gs, const float* Gi, f3 c, float mu, const float* sec_c, const float* sec_s, int lane) {
+// Slip direction carried between Gauss-Seidel iterations of one step (oracle SlipDir): when valid, the
+// search first probes a 2*pi/32 fan around it (31 sections of the round-1 table) and only falls back to
+// the full circle when the fan holds no sign change.
+struct SlipDir { float cs, sn; bool valid; };
+__device__ __forceinline__ f3 solve_contact(const float* Gs, const float* Gi, f3 c, float mu, const float* sec_c, const float* sec_s, int lane,
+                                            SlipDir& sd) {
+  const SlipDir prev = sd;
+  sd.valid = false;
   if (c.z > 0.f) return mk(0.f, 0.f, 0.f);
   f3 ls = mk(-(Gi[0] * c.x + Gi[1] * c.y + Gi[2] * c.z), -(Gi[1] * c.x + Gi[3] * c.y + Gi[4] * c.z), -(Gi[2] * c.x + Gi[4] * c.y + Gi[5] * c.z));
   if (ls.z >= 0.f && ls.x * ls.x + ls.y * ls.y <= mu * mu * ls.z * ls.z) return ls;
@@ -256,18 +263,26 @@ __device__ __forceinline__ f3 solve_contact(const float* Gs, const float* Gi, f3
   float base_c = 1.f, base_s = 0.f;
   float lo_c = 1.f, lo_s = 0.f, hi_c = 1.f, hi_s = 0.f, glo = 0.f, ghi = 0.f;
   bool have = false;
+  bool local = prev.valid;
+  int r = 0;
+  if (local) {   // fan start = previous direction turned back by pi/32
+    const float hc = 0.99518472667219693f, hs = 0.09801714032956060f;
+    base_c = prev.cs * hc + prev.sn * hs; base_s = prev.sn * hc - prev.cs * hs;
+    r = 1;
+  }
 #pragma unroll 1
-  for (int r = 0; r < NROUNDS; r++) {
+  for (;;) {
     // lane k probes direction k of this round's bracket.  The closing direction (k = NSEC) is never
     // re-evaluated: in round 0 it is probe 0 again (full circle), later it is the previous round's
-    // upper end, whose values are already known.
+    // upper end, whose values are already known; the local fan has no closing direction (31 sections).
     float tc = sec_c[r * SEC_STRIDE + lane], ts = sec_s[r * SEC_STRIDE + lane];
     float cs = base_c * tc - base_s * ts, sn = base_s * tc + base_c * ts;
     Probe p = slip_probe(cs, sn, a, b, cc, d, e, f, c, mu);
     float g_next = __shfl_down_sync(FULL, p.g, 1);
     bool ok_next = __shfl_down_sync(FULL, (int)p.ok, 1) != 0;
     float cs_next = __shfl_down_sync(FULL, cs, 1), sn_next = __shfl_down_sync(FULL, sn, 1);
-    if (r == 0) {   // full circle: the direction after probe 31 is probe 0 again
+    if (local) { if (lane == NSEC - 1) ok_next = false; }
+    else if (r == 0) {   // full circle: the direction after probe 31 is probe 0 again
       float g0 = __shfl_sync(FULL, p.g, 0), c0 = __shfl_sync(FULL, cs, 0), s0 = __shfl_sync(FULL, sn, 0);
       bool ok0 = __shfl_sync(FULL, (int)p.ok, 0) != 0;
       if (lane == NSEC - 1) { g_next = g0; ok_next = ok0; cs_next = c0; sn_next = s0; }
@@ -275,6 +290,7 @@ __device__ __forceinline__ f3 solve_contact(const float* Gs, const float* Gi, f3
     bool cand = p.ok && ok_next && (p.g < 0.f) && (g_next >= 0.f);
     unsigned m = __ballot_sync(FULL, cand);
     if (m == 0u) {
+      if (local) { local = false; r = 0; base_c = 1.f; base_s = 0.f; continue; }   // nothing in the fan: full search
       if (!have) {   // no bracket on the whole circle: least-energy probe (lowest index on ties)
         unsigned okm = __ballot_sync(FULL, p.ok);
         if (okm == 0u) return mk(0.f, 0.f, fmaxf(0.f, -c.z / f));
@@ -303,13 +319,17 @@ __device__ __forceinline__ f3 solve_contact(const float* Gs, const float* Gi, f3
     hi_c = __shfl_sync(FULL, cs_next, pick); hi_s = __shfl_sync(FULL, sn_next, pick);
     glo = __shfl_sync(FULL, p.g, pick); ghi = __shfl_sync(FULL, g_next, pick);
     base_c = lo_c; base_s = lo_s; have = true;
+    if (local) { local = false; r = 2; } else r++;
+    if (r >= NROUNDS) break;
   }
   float tt = (ghi - glo) != 0.f ? (-glo / (ghi - glo)) : 0.5f;
   float cs = lo_c + tt * (hi_c - lo_c), sn = lo_s + tt * (hi_s - lo_s);
   float inv = 1.0f / sqrtf(cs * cs + sn * sn);
   cs *= inv; sn *= inv;
   Probe p = slip_probe(cs, sn, a, b, cc, d, e, f, c, mu);
-  if (p.ok) return mk(p.lx, p.ly, p.lz);
+  sd.valid = true;
+  if (p.ok) { sd.cs = cs; sd.sn = sn; return mk(p.lx, p.ly, p.lz); }
+  sd.cs = lo_c; sd.sn = lo_s;
   p = slip_probe(lo_c, lo_s, a, b, cc, d, e, f, c, mu);   // lower bracket end (valid by construction)
   return mk(p.lx, p.ly, p.lz);
 }
@@ -944,6 +964,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         __syncwarp();
         // =========================== stage D: per-contact Gauss-Seidel ===========================
         float alpha = args.prm.alpha_init;
+        float sd_c = 1.f, sd_s = 0.f; int sd_v = 0;
         float err_ckpt = 3.0e38f;
         int next_ckpt = args.prm.stall_window;
 #pragma unroll 1
@@ -957,7 +978,10 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
             const float* Gs = s_Gii + 13 * i;
             f3 c0 = mk(ui.x - (Gs[0] * l0.x + Gs[1] * l0.y + Gs[2] * l0.z), ui.y - (Gs[1] * l0.x + Gs[3] * l0.y + Gs[4] * l0.z),
                        ui.z - (Gs[2] * l0.x + Gs[4] * l0.y + Gs[5] * l0.z));
-            f3 ln = solve_contact(Gs, Gs + 6, c0, Gs[12], sec_c, sec_s, lane);
+            SlipDir sd;   // lane i keeps contact i's last slip direction in registers
+            sd.cs = __shfl_sync(FULL, sd_c, i); sd.sn = __shfl_sync(FULL, sd_s, i); sd.valid = __shfl_sync(FULL, sd_v, i) != 0;
+            f3 ln = solve_contact(Gs, Gs + 6, c0, Gs[12], sec_c, sec_s, lane, sd);
+            if (lane == i) { sd_c = sd.cs; sd_s = sd.sn; sd_v = sd.valid ? 1 : 0; }
             f3 dl = alpha * (ln - l0);
             if (lane < CR) u_c += s_G[lane * GP + i3] * dl.x + s_G[lane * GP + i3 + 1] * dl.y + s_G[lane * GP + i3 + 2] * dl.z;
             if (lane == i3) lam_c = l0.x + dl.x; else if (lane == i3 + 1) lam_c = l0.y + dl.y; else if (lane == i3 + 2) lam_c = l0.z + dl.z;
