@@ -223,6 +223,31 @@ class ArticulatedSystem {
     rsbCheck(rsb_batch_get_body_poses(w_->batch(), env_, 1, R.data(), p.data(), RSB_HOST), "getPosition");
     for (int r = 0; r < 3; r++) out[r] = p[bodyIdx * 3 + r] + R[bodyIdx * 9 + 3 * r] * pointInBody[0] + R[bodyIdx * 9 + 3 * r + 1] * pointInBody[1] + R[bodyIdx * 9 + 3 * r + 2] * pointInBody[2];
   }
+  // ---- kinematic getters (host algebra on body poses the kernel computes for the current state) ----
+  // upstream: getBodyPosition/Orientation, getFramePosition/Orientation/Velocity/AngularVelocity,
+  // getVelocity/getAngularVelocity(bodyIdx), getDenseJacobian(bodyIdx, point_W, J), getDenseRotationalJacobian,
+  // getDenseFrameJacobian / getDenseFrameRotationalJacobian ([RECALL] ArticulatedSystem.hpp)
+  void getBodyPosition(size_t bodyIdx, Vec<3>& out) const { Poses P = poses(); for (int r = 0; r < 3; r++) out[r] = P.p[bodyIdx * 3 + r]; }
+  void getBodyOrientation(size_t bodyIdx, Mat<3, 3>& out) const {
+    Poses P = poses();
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) out(r, c) = P.R[bodyIdx * 9 + 3 * r + c];
+  }
+  void getBasePosition(Vec<3>& out) const { getBodyPosition(0, out); }
+  void getBaseOrientation(Mat<3, 3>& out) const { getBodyOrientation(0, out); }
+  void getFramePosition(size_t frameIdx, Vec<3>& out) const { Poses P = poses(); FrameW f = frameWorld(P, frameIdx); out = f.pos; }
+  void getFrameOrientation(size_t frameIdx, Mat<3, 3>& out) const { Poses P = poses(); FrameW f = frameWorld(P, frameIdx); out = f.rot; }
+  void getDenseJacobian(size_t bodyIdx, const Vec<3>& point_W, MatDyn& J) const { Poses P = poses(); jacobian(P, bodyIdx, point_W, &J, nullptr); }
+  void getDenseRotationalJacobian(size_t bodyIdx, MatDyn& J) const { Poses P = poses(); jacobian(P, bodyIdx, Vec<3>{0, 0, 0}, nullptr, &J); }
+  void getDenseFrameJacobian(size_t frameIdx, MatDyn& J) const { Poses P = poses(); FrameW f = frameWorld(P, frameIdx); jacobian(P, size_t(f.body), f.pos, &J, nullptr); }
+  void getDenseFrameRotationalJacobian(size_t frameIdx, MatDyn& J) const { Poses P = poses(); FrameW f = frameWorld(P, frameIdx); jacobian(P, size_t(f.body), f.pos, nullptr, &J); }
+  void getVelocity(size_t bodyIdx, const Vec<3>& point_W, Vec<3>& out) const {
+    Poses P = poses(); MatDyn J; jacobian(P, bodyIdx, point_W, &J, nullptr); mulGv(J, out);
+  }
+  void getVelocity(size_t bodyIdx, Vec<3>& out) const { Vec<3> o; getBodyPosition(bodyIdx, o); getVelocity(bodyIdx, o, out); }
+  void getAngularVelocity(size_t bodyIdx, Vec<3>& out) const { Poses P = poses(); MatDyn J; jacobian(P, bodyIdx, Vec<3>{0, 0, 0}, nullptr, &J); mulGv(J, out); }
+  void getFrameVelocity(size_t frameIdx, Vec<3>& out) const { MatDyn J; getDenseFrameJacobian(frameIdx, J); mulGv(J, out); }
+  void getFrameAngularVelocity(size_t frameIdx, Vec<3>& out) const { MatDyn J; getDenseFrameRotationalJacobian(frameIdx, J); mulGv(J, out); }
+
   std::vector<Contact>& getContacts() {
     rsb_contact c[RSB_KMAX]; int32_t n = 0;
     rsbCheck(rsb_batch_get_contacts(w_->batch(), c, &n, env_, 1, RSB_HOST), "getContacts");
@@ -232,6 +257,54 @@ class ArticulatedSystem {
   }
   int env() const { return env_; }
  private:
+  struct Poses { std::vector<float> R, p; };
+  struct FrameW { int body; Vec<3> pos; Mat<3, 3> rot; };
+  Poses poses() const {
+    Poses P; P.R.resize(size_t(w_->nb()) * 9); P.p.resize(size_t(w_->nb()) * 3);
+    w_->integrate1();   // kinematics pass at the CURRENT state (idempotent; no state change): upstream's updateKinematics()
+    rsbCheck(rsb_batch_get_body_poses(w_->batch(), env_, 1, P.R.data(), P.p.data(), RSB_HOST), "getBodyPoses");
+    return P;
+  }
+  FrameW frameWorld(const Poses& P, size_t frameIdx) const {
+    FrameW f; double pos[3], rot[9];
+    rsbCheck(rsb_model_frame(w_->model(), int(frameIdx), &f.body, pos, rot), "getFrame");
+    const float* R = &P.R[size_t(f.body) * 9];
+    for (int r = 0; r < 3; r++) {
+      f.pos[r] = P.p[size_t(f.body) * 3 + r] + R[3 * r] * pos[0] + R[3 * r + 1] * pos[1] + R[3 * r + 2] * pos[2];
+      for (int c = 0; c < 3; c++) f.rot(r, c) = R[3 * r] * rot[c] + R[3 * r + 1] * rot[3 + c] + R[3 * r + 2] * rot[6 + c];
+    }
+    return f;
+  }
+  // geometric Jacobians of a world point attached to `body`: v_point = Jp gv, omega_body = Jr gv
+  void jacobian(const Poses& P, size_t body, const Vec<3>& pt, MatDyn* Jp, MatDyn* Jr) const {
+    rsb_model_tables t; rsbCheck(rsb_model_get_tables(w_->model(), &t), "getTables");
+    if (Jp) Jp->resize(3, size_t(t.nv));
+    if (Jr) Jr->resize(3, size_t(t.nv));
+    for (int i = int(body); i >= 0; i = t.parent[i]) {
+      const float* R = &P.R[size_t(i) * 9]; const float* o = &P.p[size_t(i) * 3];
+      const double r[3] = {pt[0] - o[0], pt[1] - o[1], pt[2] - o[2]};
+      if (t.jtype[i] == 3) {          // floating base: [v_world | omega_world]
+        if (Jp) {
+          for (int k = 0; k < 3; k++) (*Jp)(k, k) = 1.0;
+          (*Jp)(0, 4) = r[2]; (*Jp)(0, 5) = -r[1]; (*Jp)(1, 3) = -r[2]; (*Jp)(1, 5) = r[0]; (*Jp)(2, 3) = r[1]; (*Jp)(2, 4) = -r[0];   // -[r]x
+        }
+        if (Jr) for (int k = 0; k < 3; k++) (*Jr)(k, 3 + k) = 1.0;
+      } else if (t.jtype[i] == 1 || t.jtype[i] == 2) {
+        const double* ab = &t.axis[size_t(i) * 3];
+        double a[3];
+        for (int k = 0; k < 3; k++) a[k] = R[3 * k] * ab[0] + R[3 * k + 1] * ab[1] + R[3 * k + 2] * ab[2];
+        const size_t c = size_t(t.vidx[i]);
+        if (t.jtype[i] == 1) {
+          if (Jp) { (*Jp)(0, c) = a[1] * r[2] - a[2] * r[1]; (*Jp)(1, c) = a[2] * r[0] - a[0] * r[2]; (*Jp)(2, c) = a[0] * r[1] - a[1] * r[0]; }
+          if (Jr) for (int k = 0; k < 3; k++) (*Jr)(k, c) = a[k];
+        } else if (Jp) for (int k = 0; k < 3; k++) (*Jp)(k, c) = a[k];
+      }
+    }
+  }
+  void mulGv(const MatDyn& J, Vec<3>& out) const {
+    VecDyn gv = getGeneralizedVelocity();
+    for (int r = 0; r < 3; r++) { double s = 0; for (size_t c = 0; c < J.cols(); c++) s += J(r, c) * gv[c]; out[r] = s; }
+  }
   BatchedWorld* w_;
   int env_;
   std::string name_;

@@ -38,6 +38,7 @@ struct rsb_batch {
   bool pd_set = false;
   const float* pt_bound = nullptr;   // caller-owned device buffer read in place of the internal PD-target rows
   int pt_bound_stride = 0;
+  unsigned* prof = nullptr;          // rsb_internal_set_profile
   // device buffers
   float *gc = nullptr, *gv = nullptr, *tau = nullptr, *pt = nullptr, *vt = nullptr, *tau_applied = nullptr;
   int *ncontacts = nullptr, *contact_pt = nullptr, *iters = nullptr, *diverged = nullptr;
@@ -99,7 +100,9 @@ static void build_blob(rsb_batch* b) {
   {
     bool ident = true;
     for (int i = 1; i < md.nb; i++) for (int k = 0; k < 9; k++) if (std::fabs(md.jrot[9 * i + k] - ((k % 4 == 0) ? 1.0 : 0.0)) > 0.0) ident = false;
-    H.flags = ident ? 1 : 0;
+    int max_inner = 0;
+    for (int i = 1; i < md.nb; i++) max_inner = std::max(max_inner, md.subtree[i] - 1);
+    H.flags = (ident ? 1 : 0) | (max_inner << 8);
   }
   const int words = H.words;
   std::vector<uint32_t>& B = b->blob_host;
@@ -230,7 +233,7 @@ static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug, flo
   a.tau_applied = b->tau_applied;
   a.ncontacts = b->ncontacts; a.contacts = b->contacts; a.contact_pt = b->contact_pt; a.iters = b->iters; a.diverged = b->diverged;
   if (debug) { a.dbg_M = b->dbg_M; a.dbg_h = b->dbg_h; a.dbg_R = b->dbg_R; a.dbg_p = b->dbg_p; }
-  a.phase_mask = phase_mask;
+  a.phase_mask = phase_mask; a.prof = b->prof;
   a.obs = obs_dev; a.ob_dim = rsb_batch_ob_dim(b);
   {
     const char* e = getenv("RSB_SUBSTEP_BARRIER");
@@ -348,6 +351,7 @@ const char* rsb_model_joint_name(const rsb_model* m, int body) { return (m && bo
 int rsb_model_frame_index(const rsb_model* m, const char* name) {
   if (!m || !name) return fail(RSB_ERR_INVALID, "null argument");
   for (size_t i = 0; i < m->md.frames.size(); i++) if (m->md.frames[i].name == name) return (int)i;
+  for (size_t i = 0; i < m->md.frames.size(); i++) if (!m->md.frames[i].joint.empty() && m->md.frames[i].joint == name) return (int)i;   // joint-name alias
   return fail(RSB_ERR_INVALID, std::string("no frame named '") + name + "'");
 }
 int rsb_model_frame(const rsb_model* m, int frame, int* body, double pos[3], double rot[9]) {
@@ -783,6 +787,8 @@ int rsb_internal_batch_info(rsb_batch* b, int* device, void** stream, int* num_e
   if (num_envs) *num_envs = b->N;
   return RSB_OK;
 }
+// profiling hook (tools/balance_probe.py): device buffer [num_envs][4][8] of SM-clock stamps, or null to switch off
+int rsb_internal_set_profile(rsb_batch* b, unsigned* dev) { if (!b) return -1; b->prof = dev; return 0; }
 void rsb_internal_set_error(const char* msg) { g_err = msg ? msg : ""; }
 
 }  // extern "C"

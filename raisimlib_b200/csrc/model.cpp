@@ -176,6 +176,7 @@ struct Builder {
   std::map<std::string, const XmlNode*> links;
   std::map<std::string, std::vector<const XmlNode*>> kids_of;   // parent link -> joints, file order
   std::vector<Accum> acc;
+  std::map<std::string, std::string> joint_of_link;              // child link -> name of the joint that carries it
 
   int new_body(const std::string& name, int parent, int jt, const V3& jp, const M3& jr, const V3& ax, const std::string& jname, double lo, double hi) {
     int i = md.nb++;
@@ -194,7 +195,7 @@ struct Builder {
     auto it = links.find(link_name);
     if (it == links.end()) throw std::runtime_error("URDF: joint refers to unknown link '" + link_name + "'");
     const XmlNode* l = it->second;
-    md.frames.push_back(Frame{link_name, b, pos, rot});
+    md.frames.push_back(Frame{link_name, joint_of_link.count(link_name) ? joint_of_link[link_name] : std::string(), b, pos, rot});
     if (const XmlNode* in = l->child("inertial")) {
       V3 cp; M3 cr;
       origin_of(in, cp, cr);
@@ -304,6 +305,7 @@ Model load_urdf(const std::string& path_or_xml) {
     if (is_child[c->get("link")]) throw std::runtime_error("URDF: link '" + c->get("link") + "' has two parents (kinematic loops are unsupported)");
     is_child[c->get("link")] = true;
     bd.kids_of[p->get("link")].push_back(j);
+    if (const XmlNode* ch = j->child("child")) bd.joint_of_link[ch->get("link")] = j->get("name");
   }
   std::string root_link;
   for (const XmlNode* l : root->children("link"))

@@ -12,7 +12,8 @@ enum JointType { JT_FIXED = 0, JT_REVOLUTE = 1, JT_PRISMATIC = 2, JT_FLOATING = 
 enum CollType { CT_SPHERE = 0, CT_BOX = 1, CT_CAPSULE = 2, CT_CYLINDER = 3 };
 
 struct Frame {
-  std::string name;
+  std::string name;    // link name
+  std::string joint;   // name of the joint attaching the link (upstream names frames after joints); empty for the root
   int body;
   std::array<double, 3> pos;
   std::array<double, 9> rot;

@@ -63,7 +63,8 @@ struct BlobHeader {
   // dof tree (floating base = chain of 6 dofs) for the branch-sparse factorisation
   int nbase, maxdd, dlp, nent;
   int off_ddepth, off_dsub, off_danc, off_dbody, off_bdof, off_lvl, off_lvldofs, off_entstart, off_ent, off_lcad;
-  int words, flags;    // flags bit0: every joint origin has identity rotation (rpy = 0 in the URDF)
+  int words, flags;    // flags bit0: every joint origin has identity rotation (rpy = 0 in the URDF); bits 8..15: largest
+                       // non-root subtree size - 1 (loop bound of stage A's subtree accumulation)
 };
 static_assert(sizeof(BlobHeader) == 128, "header is 32 words");
 constexpr int HEADER_WORDS = 32;
@@ -167,6 +168,7 @@ struct StepArgs {
   float *dbg_M, *dbg_h, *dbg_R, *dbg_p;   // optional (integrate1 / getters)
   float* obs;          // optional [N][ob_dim]: RaisimGym observation row of the final state, written by this kernel
   int ob_dim;
+  unsigned* prof;      // optional [num_envs][4 sub-steps][8] SM-clock stamps at the stage boundaries (tools/balance_probe.py)
   int phase_mask;      // bit0: stop after stage C (integrate1: no state update)
   int substep_barrier; // 1: re-align the CTA's warps at every sub-step (instruction-cache locality experiment)
 };
@@ -358,7 +360,7 @@ __device__ __forceinline__ bool terrain_query(const TerrainDesc& t, f3 P, float&
 
 // getters of integrate1(): full symmetric M rebuilt from the compact rows, h, body poses (cold path)
 __device__ __noinline__ void write_debug(const StepArgs& args, int env, int lane, int nv, int nb, int nvp, int DLP, const float* s_L,
-                                         const float* s_h, const int* ddepth, const int* danc, bool bvalid, const float* R, f3 p) {
+                                         const float* s_h, const int* ddepth, const int* danc, bool bvalid, const float* s_pose, int nbp) {
   float* gM = args.dbg_M + (size_t)env * nv * nv;
   for (int i = lane; i < nv * nv; i += 32) {
     int r = i / nv, c = i % nv;
@@ -371,8 +373,8 @@ __device__ __noinline__ void write_debug(const StepArgs& args, int env, int lane
   if (bvalid) {
     float* gR = args.dbg_R + ((size_t)env * nb + lane) * 9;
     float* gp = args.dbg_p + ((size_t)env * nb + lane) * 3;
-    for (int k = 0; k < 9; k++) gR[k] = R[k];
-    gp[0] = p.x; gp[1] = p.y; gp[2] = p.z;
+    for (int k = 0; k < 9; k++) gR[k] = s_pose[(PF_R + k) * nbp + lane];   // poses were published to shared memory by stage A
+    for (int k = 0; k < 3; k++) gp[k] = s_pose[(PF_P + k) * nbp + lane];
   }
 }
 
@@ -406,8 +408,9 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
 
   const BlobHeader& H = *reinterpret_cast<const BlobHeader*>(blob_s);
 #define HO(f) (ST ? HS.f : H.f)
-  const int nb = HO(nb), nq = HO(nq), nv = HO(nv), npts = H.npts, floating = HO(floating), maxdepth = HO(maxdepth);
-  const int nbp = HO(nbp), nptp = H.nptp, nvp = HO(nvp);
+  const int nb = HO(nb), nq = HO(nq), nv = HO(nv), floating = HO(floating), maxdepth = HO(maxdepth);
+  const int nbp = HO(nbp), nvp = HO(nvp);
+
   const float* bodyf = reinterpret_cast<const float*>(blob_s + HO(off_body));
   const int* bodyi = reinterpret_cast<const int*>(blob_s + HO(off_body));
   const int* anc = reinterpret_cast<const int*>(blob_s + HO(off_anc));
@@ -419,7 +422,6 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
   const float* sec_c = reinterpret_cast<const float*>(blob_s + HO(off_sec));
   const float* sec_s = sec_c + NROUNDS * SEC_STRIDE;
   const int nbase = HO(nbase), maxdd = HO(maxdd), DLP = HO(dlp);
-  const bool jrot_identity = (H.flags & 1) != 0;
   const int* ddepth = reinterpret_cast<const int*>(blob_s + HO(off_ddepth));
   const int* dsub = reinterpret_cast<const int*>(blob_s + HO(off_dsub));
   const int* danc = reinterpret_cast<const int*>(blob_s + HO(off_danc));
@@ -438,25 +440,24 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
   float* s_h = ws + WSO(o_h); float* s_b = ws + WSO(o_b); float* s_pose = ws + WSO(o_pose); float* s_G = ws + WSO(o_G);
 #undef WSO
 #undef HO
-  const float dt = args.prm.dt;
-  const float mu = args.prm.mu;
-  const f3 grav = mk(args.prm.gravity[0], args.prm.gravity[1], args.prm.gravity[2]);
+  // Long-lived per-thread values are kept to a minimum: at 72 registers (28 warps x 32 lanes per SM) everything cached
+  // here is spilled, and 28 warps' spill slots do not fit the L1 next to the terrain gathers -- every reload was an L2
+  // round trip on the critical path.  Kernel parameters are read in place (constant bank), model constants from the
+  // shared-memory blob at the point of use.
 
   // body constants of this lane (lane == body)
   const int b = lane;
   const bool bvalid = b < nb;
   const int bb = bvalid ? b : 0;
-  const int my_parent = bodyi[BF_PARENT * nbp + bb], my_jtype = bodyi[BF_JTYPE * nbp + bb];
-  const int my_vidx = bodyi[BF_VIDX * nbp + bb], my_depth = bodyi[BF_DEPTH * nbp + bb], my_sub = bodyi[BF_SUBTREE * nbp + bb];
-  int er = 0, ec = 0;   // (row, col) of the base 6x6 lower triangle owned by lanes 0..20
-  for (int r = 0, e = 0; r < 6; r++) for (int c = 0; c <= r; c++, e++) if (e == lane) { er = r; ec = c; }
-  int max_inner = 0;   // largest non-root subtree size - 1 (loop bound of the subtree accumulation)
-  {
-    int v = (bvalid && b > 0) ? my_sub - 1 : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
-    max_inner = v;
+#define MYB(f) (bodyi[(f) * nbp + bb])
+  // (row, col) of the base 6x6 lower triangle owned by lanes 0..20, packed row | col << 3: one table per CTA
+  __shared__ uint8_t s_tri[32];
+  if (threadIdx.x < 32) {
+    int pr = 0;
+    for (int r = 0, e = 0; r < 6; r++) for (int c = 0; c <= r; c++, e++) if (e == (int)threadIdx.x) pr = r | (c << 3);
+    s_tri[threadIdx.x] = (uint8_t)pr;
   }
+  __syncthreads();
 
   const int warps_total = gridDim.x * WPC;
 #pragma unroll 1
@@ -488,6 +489,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       // owns exactly one environment, so all of them reach the barrier the same number of times.
       const int bar_threads = min(WPC, args.num_envs - (int)blockIdx.x * WPC) * 32;
       if (args.substep_barrier >= 1) asm volatile("bar.sync 1, %0;" ::"r"(bar_threads));
+      if (args.prof && lane == 0) args.prof[((size_t)env * 4 + (sub & 3)) * 8 + 0] = (unsigned)clock64();
       // =========================== stage A: FK + RNEA + CRBA =====================================
       float R[9]; f3 p, w, v, wd, vd, ax;
       if (floating) {
@@ -506,10 +508,11 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         v = mk(0.f, 0.f, 0.f); w = mk(0.f, 0.f, 0.f);
       }
       const f3 O = p;                      // base origin: centre of the world-aligned CRBA frame
-      wd = mk(0.f, 0.f, 0.f); vd = mk(-grav.x, -grav.y, -grav.z); ax = mk(0.f, 0.f, 0.f);
+      const bool jrot_identity = (H.flags & 1) != 0;
+      wd = mk(0.f, 0.f, 0.f); vd = mk(-args.prm.gravity[0], -args.prm.gravity[1], -args.prm.gravity[2]); ax = mk(0.f, 0.f, 0.f);
 #pragma unroll 1
       for (int d = 1; d <= maxdepth; d++) {
-        int j = (bvalid && d <= my_depth) ? anc[(d - 1) * nbp + b] : -1;
+        int j = (bvalid && d <= MYB(BF_DEPTH)) ? anc[(d - 1) * nbp + b] : -1;
         if (j >= 0) {
           f3 jp = mk(bodyf[(BF_JPOS + 0) * nbp + j], bodyf[(BF_JPOS + 1) * nbp + j], bodyf[(BF_JPOS + 2) * nbp + j]);
           float Jr[9], Rj[9];
@@ -592,6 +595,8 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       float A[16];
 #pragma unroll
       for (int k = 0; k < 16; k++) A[k] = X[k];
+      const int my_sub = MYB(BF_SUBTREE);
+      const int max_inner = (H.flags >> 8) & 0xff;   // largest non-root subtree size - 1
 #pragma unroll 1
       for (int s = 1; s <= max_inner; s++) {
         bool take = (b > 0) && (s < my_sub);
@@ -617,14 +622,15 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       }
       // bias force h and CRBA columns (row i of M stored compactly: column index = ancestor depth)
       f3 rO = p - O;
-      const bool rev = my_jtype == 1;
+      const bool rev = MYB(BF_JTYPE) == 1;
       f3 Sw = rev ? ax : mk(0.f, 0.f, 0.f);
       f3 Sv = rev ? cross(rO, ax) : ax;
       f3 Fc = mk(A[0], A[1], A[2]), Nc = mk(A[3], A[4], A[5]);
       f3 hh = mk(A[7], A[8], A[9]);
       f3 ff = A[6] * Sv + cross(Sw, hh);
       f3 nn = mk(A[10] * Sw.x + A[11] * Sw.y + A[12] * Sw.z, A[11] * Sw.x + A[13] * Sw.y + A[14] * Sw.z, A[12] * Sw.x + A[14] * Sw.y + A[15] * Sw.z) + cross(hh, Sv);
-      const int my_dd = nbase + my_depth - 1;          // depth of this body's dof in the dof tree
+      const int my_vidx = MYB(BF_VIDX);
+      const int my_dd = nbase + MYB(BF_DEPTH) - 1;          // depth of this body's dof in the dof tree
       if (bvalid && b > 0) {
         float* row = s_L + my_vidx * DLP;
         s_h[my_vidx] = dot(Sw, Nc) + dot(Sv, Fc);      // S^T [N_O; F]  (moment about O)
@@ -643,7 +649,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         s_L[4 * DLP + 4] = A[13]; s_L[5 * DLP + 4] = A[14]; s_L[5 * DLP + 5] = A[15];
       }
       {   // M[vi][vj] for proper ancestors j (excluding the root): column = depth of j's dof
-        int j = (bvalid && b > 0) ? my_parent : 0;
+        int j = (bvalid && b > 0) ? MYB(BF_PARENT) : 0;
         int tj = my_dd - 1;
 #pragma unroll 1
         for (int d = 2; d <= maxdepth; d++) {
@@ -657,8 +663,9 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         }
       }
       __syncwarp();
+      if (args.prof && lane == 0) args.prof[((size_t)env * 4 + (sub & 3)) * 8 + 1] = (unsigned)clock64();
       if (args.dbg_M)   // getters (integrate1): cold path, kept out of line to spare the instruction cache
-        write_debug(args, env, lane, nv, nb, nvp, DLP, s_L, s_h, ddepth, danc, bvalid, R, p);
+        write_debug(args, env, lane, nv, nb, nvp, DLP, s_L, s_h, ddepth, danc, bvalid, s_pose, nbp);
 
       // =========================== stage B: narrow phase ========================================
       float c_depth[SLOTS]; f3 c_pos[SLOTS], c_n[SLOTS]; int c_pair[SLOTS], c_body[SLOTS];
@@ -667,10 +674,10 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       for (int s = 0; s < SLOTS; s++) {
         int k = lane + 32 * s;
         c_hit[s] = false; c_depth[s] = 0.f; c_pair[s] = 0; c_body[s] = 0; c_pos[s] = mk(0, 0, 0); c_n[s] = mk(0, 0, 1);
-        if (k < npts) {
-          int pb = ptsi[0 * nptp + k];
-          f3 pl = mk(ptsf[1 * nptp + k], ptsf[2 * nptp + k], ptsf[3 * nptp + k]);
-          float rad = ptsf[4 * nptp + k];
+        if (k < H.npts) {
+          int pb = ptsi[0 * H.nptp + k];
+          f3 pl = mk(ptsf[1 * H.nptp + k], ptsf[2 * H.nptp + k], ptsf[3 * H.nptp + k]);
+          float rad = ptsf[4 * H.nptp + k];
           float Rb[9];
 #pragma unroll
           for (int q = 0; q < 9; q++) Rb[q] = s_pose[(PF_R + q) * nbp + pb];
@@ -727,6 +734,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         }
       }
       const int C = 3 * K;
+      if (args.prof && lane == 0) args.prof[((size_t)env * 4 + (sub & 3)) * 8 + 2] = (unsigned)clock64();
       if (args.phase_mask & 1) { __syncwarp(); break; }   // integrate1(): kinematics, collision, M, h only
 
       if (args.substep_barrier >= 2) asm volatile("bar.sync 1, %0;" ::"r"(bar_threads));
@@ -740,7 +748,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         const unsigned lm_mask = __ballot_sync(FULL, act);
         const int slot = __popc(lm_mask & ((1u << lane) - 1u));
         if (act && slot < LMAX) {
-          s_lim[4 * slot + 0] = __int_as_float(my_vidx);
+          s_lim[4 * slot + 0] = __int_as_float(MYB(BF_VIDX));
           s_lim[4 * slot + 1] = q < lo ? 1.f : -1.f;
           s_lim[4 * slot + 2] = q < lo ? lo - q : q - hi;
         }
@@ -755,8 +763,8 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
           float kpi = kp[i], kdi = kd[i];
           if (kpi != 0.f || kdi != 0.f) {
             int qi = dofq[i];
-            bi += kpi * (s_pt[qi] - s_gc[qi] - dt * s_gv[i]) + kdi * (s_vt[i] - s_gv[i]);
-            s_L[i * DLP + ddepth[i]] += dt * kdi + dt * dt * kpi;
+            bi += kpi * (s_pt[qi] - s_gc[qi] - args.prm.dt * s_gv[i]) + kdi * (s_vt[i] - s_gv[i]);
+            s_L[i * DLP + ddepth[i]] += args.prm.dt * kdi + args.prm.dt * args.prm.dt * kpi;
           }
         }
         s_b[i] = bi;
@@ -793,6 +801,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         __syncwarp();
       }
       if (floating) {   // base 6x6 block: every other dof is a descendant of every base dof
+        const int er = s_tri[lane] & 7, ec = s_tri[lane] >> 3;
         float val = 0.f;
         if (lane < 21) {
           val = s_L[er * DLP + ec];
@@ -913,10 +922,10 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
             for (int t = 0; t < sI; t++) s_Y[t * CP + c] -= s_L[a_s * DLP + t] * y;
           }
         }
-        u_c = jv + dt * yz;
-        if (is_lim) u_c -= args.prm.erp * lm[2] / dt;
+        u_c = jv + args.prm.dt * yz;
+        if (is_lim) u_c -= args.prm.erp * lm[2] / args.prm.dt;
         else if (d == 2) {
-          float target = args.prm.erp * ct[CF_DEPTH] / dt;
+          float target = args.prm.erp * ct[CF_DEPTH] / args.prm.dt;
           if (args.prm.restitution > 0.f && jv < -args.prm.rest_threshold) target += -args.prm.restitution * jv;
           u_c -= target;
         }
@@ -955,13 +964,14 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
           float id = 1.0f / (a * c00 + bq * c01 + cc * c02);
           float* o = s_Gii + 13 * lane;
           {
-            const float pm = ptsf[5 * nptp + __float_as_int(s_ct[lane * CT_WORDS + CF_PT])];
-            o[12] = pm >= 0.f ? pm : mu;     // per-collision-body friction (World::setMaterialPairProp analogue)
+            const float pm = ptsf[5 * H.nptp + __float_as_int(s_ct[lane * CT_WORDS + CF_PT])];
+            o[12] = pm >= 0.f ? pm : args.prm.mu;     // per-collision-body friction (World::setMaterialPairProp analogue)
           }
           o[0] = a; o[1] = bq; o[2] = cc; o[3] = d; o[4] = e; o[5] = f;
           o[6] = c00 * id; o[7] = c01 * id; o[8] = c02 * id; o[9] = c11 * id; o[10] = c12 * id; o[11] = c22 * id;
         }
         __syncwarp();
+        if (args.prof && lane == 0) args.prof[((size_t)env * 4 + (sub & 3)) * 8 + 3] = (unsigned)clock64();
         // =========================== stage D: per-contact Gauss-Seidel ===========================
         float alpha = args.prm.alpha_init;
         float sd_c = 1.f, sd_s = 0.f; int sd_v = 0;
@@ -1010,11 +1020,12 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         __syncwarp();
       }
       __syncwarp();
+      if (args.prof && lane == 0) args.prof[((size_t)env * 4 + (sub & 3)) * 8 + 4] = (unsigned)clock64();
       if (args.substep_barrier >= 3) asm volatile("bar.sync 1, %0;" ::"r"(bar_threads));
       // =========================== stage E: v+ = v + L^-1 (dt z + Y lam), integration ============
 #pragma unroll 1
       for (int i = lane; i < nv; i += 32) {   // w = dt z + Y lam, gathered per dof over the contacts whose chain holds it
-        float sacc = dt * s_z[i];
+        float sacc = args.prm.dt * s_z[i];
         const int di = ddepth[i];
 #pragma unroll 1
         for (int k = 0; k < K; k++) {
@@ -1063,18 +1074,18 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         float ta = s_tau[i];
         if (args.use_pd) {
           const float kpi = kp[i], kdi = kd[i];
-          if (kpi != 0.f || kdi != 0.f) { const int qi = dofq[i]; ta += kpi * (s_pt[qi] - s_gc[qi] - dt * vp) + kdi * (s_vt[i] - vp); }
+          if (kpi != 0.f || kdi != 0.f) { const int qi = dofq[i]; ta += kpi * (s_pt[qi] - s_gc[qi] - args.prm.dt * vp) + kdi * (s_vt[i] - vp); }
         }
         s_b[i] = ta;
       }
       __syncwarp();
       if (floating) {
-        if (lane < 3) s_gc[lane] += dt * s_gv[lane];
+        if (lane < 3) s_gc[lane] += args.prm.dt * s_gv[lane];
         f3 wn = mk(s_gv[3], s_gv[4], s_gv[5]);
-        float wnorm = sqrtf(dot(wn, wn)), ang = wnorm * dt;
+        float wnorm = sqrtf(dot(wn, wn)), ang = wnorm * args.prm.dt;
         float qw, qx, qy, qz;
         if (ang > 1e-10f) { float sh, ch; sincosf(0.5f * ang, &sh, &ch); float s = sh / wnorm; qw = ch; qx = s * wn.x; qy = s * wn.y; qz = s * wn.z; }
-        else { qw = 1.f; qx = 0.5f * dt * wn.x; qy = 0.5f * dt * wn.y; qz = 0.5f * dt * wn.z; }
+        else { qw = 1.f; qx = 0.5f * args.prm.dt * wn.x; qy = 0.5f * args.prm.dt * wn.y; qz = 0.5f * args.prm.dt * wn.z; }
         float pw = s_gc[3], px = s_gc[4], py = s_gc[5], pz = s_gc[6];
         float nw = qw * pw - qx * px - qy * py - qz * pz;
         float nx = qw * px + qx * pw + qy * pz - qz * py;
@@ -1087,9 +1098,10 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
 #pragma unroll 1
       for (int i = lane; i < nv; i += 32) {
         int qi = dofq[i];
-        if (qi >= (floating ? 7 : 0)) s_gc[qi] += dt * s_gv[i];
+        if (qi >= (floating ? 7 : 0)) s_gc[qi] += args.prm.dt * s_gv[i];
       }
       __syncwarp();
+      if (args.prof && lane == 0) args.prof[((size_t)env * 4 + (sub & 3)) * 8 + 5] = (unsigned)clock64();
     }   // substeps
 
     // ---- store state rows and contact records -----------------------------------------------------
@@ -1105,16 +1117,17 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       float qw = s_gc[3], qx = s_gc[4], qy = s_gc[5], qz = s_gc[6];
       const float inv = 1.0f / sqrtf(qw * qw + qx * qx + qy * qy + qz * qz);
       qw *= inv; qx *= inv; qy *= inv; qz *= inv;
-      const float Ro[9] = {1.f - 2.f * (qy * qy + qz * qz), 2.f * (qx * qy - qw * qz), 2.f * (qx * qz + qw * qy),
-                           2.f * (qx * qy + qw * qz), 1.f - 2.f * (qx * qx + qz * qz), 2.f * (qy * qz - qw * qx),
-                           2.f * (qx * qz - qw * qy), 2.f * (qy * qz + qw * qx), 1.f - 2.f * (qx * qx + qy * qy)};
+      // column `lane` of the base rotation (lanes 0..2), selected without a lane-indexed local array
+      const float c0 = lane == 0 ? 1.f - 2.f * (qy * qy + qz * qz) : lane == 1 ? 2.f * (qx * qy - qw * qz) : 2.f * (qx * qz + qw * qy);
+      const float c1 = lane == 0 ? 2.f * (qx * qy + qw * qz) : lane == 1 ? 1.f - 2.f * (qx * qx + qz * qz) : 2.f * (qy * qz - qw * qx);
+      const float c2 = lane == 0 ? 2.f * (qx * qz - qw * qy) : lane == 1 ? 2.f * (qy * qz + qw * qx) : 1.f - 2.f * (qx * qx + qy * qy);
       float* o = args.obs + (size_t)env * args.ob_dim;
       const int nj = nq - 7;
       if (lane == 0) o[0] = s_gc[2];
       if (lane < 3) {
-        o[1 + lane] = Ro[6 + lane];
-        o[4 + nj + lane] = Ro[0 + lane] * s_gv[0] + Ro[3 + lane] * s_gv[1] + Ro[6 + lane] * s_gv[2];
-        o[7 + nj + lane] = Ro[0 + lane] * s_gv[3] + Ro[3 + lane] * s_gv[4] + Ro[6 + lane] * s_gv[5];
+        o[1 + lane] = c2;
+        o[4 + nj + lane] = c0 * s_gv[0] + c1 * s_gv[1] + c2 * s_gv[2];
+        o[7 + nj + lane] = c0 * s_gv[3] + c1 * s_gv[4] + c2 * s_gv[5];
       }
 #pragma unroll 1
       for (int i = lane; i < nj; i += 32) { o[4 + i] = s_gc[7 + i]; o[10 + nj + i] = s_gv[6 + i]; }

@@ -365,6 +365,18 @@ def test_cpp_facade_example_program(capi):
     assert "contacts=4" in out.stdout
 
 
+def test_cpp_kinematic_getters_example():
+    """facade getters (frame pose / velocity / Jacobians) against finite differences, from C++"""
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "examples", "kinematics_check")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")])
+    out = subprocess.run([exe, os.path.join(RSC, "anymal_c_like.urdf")], capture_output=True, text=True, timeout=120)
+    print(out.stdout)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+
 def test_stagnation_exit_matches_oracle(capi):
     """Default solver parameters (stall_window = 8): same exit decisions as the oracle, short tail."""
     n = 1024
