@@ -9,6 +9,7 @@
 
 namespace rsb {
 
+// obs_rot_column / obs_dot3: see step_kernel.cuh (shared with the fused observation write)
 __global__ void rsb_observe_kernel(const float* __restrict__ gc, const float* __restrict__ gv, int gc_stride, int gv_stride, int nq, int nv,
                                    int floating, int num_envs, float* __restrict__ obs, int ob_dim) {
   const int lane = threadIdx.x & 31;
@@ -25,15 +26,14 @@ __global__ void rsb_observe_kernel(const float* __restrict__ gc, const float* __
   float qw = q[3], qx = q[4], qy = q[5], qz = q[6];
   float inv = 1.0f / sqrtf(qw * qw + qx * qx + qy * qy + qz * qz);
   qw *= inv; qx *= inv; qy *= inv; qz *= inv;
-  float R[9] = {1.f - 2.f * (qy * qy + qz * qz), 2.f * (qx * qy - qw * qz), 2.f * (qx * qz + qw * qy),
-                2.f * (qx * qy + qw * qz), 1.f - 2.f * (qx * qx + qz * qz), 2.f * (qy * qz - qw * qx),
-                2.f * (qx * qz - qw * qy), 2.f * (qy * qz + qw * qx), 1.f - 2.f * (qx * qx + qy * qy)};
   const int nj = nq - 7;
   if (lane == 0) o[0] = q[2];
   if (lane < 3) {
-    o[1 + lane] = R[6 + lane];
-    o[4 + nj + lane] = R[0 + lane] * v[0] + R[3 + lane] * v[1] + R[6 + lane] * v[2];
-    o[7 + nj + lane] = R[0 + lane] * v[3] + R[3 + lane] * v[4] + R[6 + lane] * v[5];
+    float c0, c1, c2;
+    obs_rot_column(qw, qx, qy, qz, lane, c0, c1, c2);
+    o[1 + lane] = c2;
+    o[4 + nj + lane] = obs_dot3(c0, c1, c2, v[0], v[1], v[2]);
+    o[7 + nj + lane] = obs_dot3(c0, c1, c2, v[3], v[4], v[5]);
   }
   for (int i = lane; i < nj; i += 32) { o[4 + i] = q[7 + i]; o[10 + nj + i] = v[6 + i]; }
 }

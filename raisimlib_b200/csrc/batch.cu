@@ -38,6 +38,9 @@ struct rsb_batch {
   bool pd_set = false;
   const float* pt_bound = nullptr;   // caller-owned device buffer read in place of the internal PD-target rows
   int pt_bound_stride = 0;
+  const float* vt_bound = nullptr;   // same for the velocity targets
+  int vt_bound_stride = 0;
+  bool bound_once = false;           // zero-copy control step: the kernel copies the rows it read into pt / vt, then the binding ends
   unsigned* prof = nullptr;          // rsb_internal_set_profile
   // device buffers
   float *gc = nullptr, *gv = nullptr, *tau = nullptr, *pt = nullptr, *vt = nullptr, *tau_applied = nullptr;
@@ -227,7 +230,10 @@ static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug, flo
   a.gc_stride = b->gc_stride; a.gv_stride = b->gv_stride;
   a.gc = b->gc; a.gv = b->gv; a.tau = b->tau;
   a.use_pd = (b->control_mode == RSB_PD_PLUS_FEEDFORWARD_TORQUE && b->pd_set) ? 1 : 0;
-  a.ptarget = b->pt_bound ? b->pt_bound : b->pt; a.pt_stride = b->pt_bound ? b->pt_bound_stride : b->gc_stride; a.vtarget = b->vt;
+  a.ptarget = b->pt_bound ? b->pt_bound : b->pt; a.pt_stride = b->pt_bound ? b->pt_bound_stride : b->gc_stride;
+  a.vtarget = b->vt_bound ? b->vt_bound : b->vt; a.vt_stride = b->vt_bound ? b->vt_bound_stride : b->gv_stride;
+  a.pt_store = (b->bound_once && b->pt_bound) ? b->pt : nullptr;
+  a.vt_store = (b->bound_once && b->vt_bound) ? b->vt : nullptr;
   a.prm = b->prm; a.ter = b->ter; a.ws = b->ws;
   a.blob_words = (int)b->blob_host.size(); a.blob = b->blob;
   a.tau_applied = b->tau_applied;
@@ -262,6 +268,13 @@ static int ensure_staging(rsb_batch* b, size_t words) {
   CK(cudaMalloc((void**)&b->staging, words * 4));
   b->staging_words = words;
   return RSB_OK;
+}
+// device-side alias of a pinned, mapped host allocation (cudaHostAlloc / cudaHostRegister / torch pin_memory); null otherwise
+static const float* mapped_alias(const void* host) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (at.type == cudaMemoryTypeHost && at.devicePointer) return static_cast<const float*>(at.devicePointer);
+  return nullptr;
 }
 static int copy_rows_in(rsb_batch* b, float* dst, int stride, const float* src, int w, int env_begin, int n, int where) {
   if (!src || n == 0) return RSB_OK;
@@ -670,17 +683,37 @@ int rsb_batch_observe(rsb_batch* b, float* obs, int env_begin, int env_count, in
 int rsb_batch_control_step(rsb_batch* b, const float* ptarget, const float* vtarget, int where_in, int substeps, float* obs, int where_out) {
   if (!b || substeps < 1) return fail(RSB_ERR_INVALID, "bad arguments to rsb_batch_control_step");
   CK(cudaSetDevice(b->device));
-  if (ptarget) b->pt_bound = nullptr;
-  int rc = copy_rows_in(b, b->pt, b->gc_stride, ptarget, b->nq, 0, b->N, where_in); if (rc) return rc;
-  rc = copy_rows_in(b, b->vt, b->gv_stride, vtarget, b->nv, 0, b->N, where_in); if (rc) return rc;
+  // Host buffers in pinned (page-locked, mapped) memory are read and written IN PLACE by the step kernel over PCIe:
+  // no staging copy, no separate H2D / D2H operations on the stream.  Pageable buffers take the staged path.
+  int rc = RSB_OK;
+  const float* pt_alias = (ptarget && where_in == RSB_HOST) ? mapped_alias(ptarget) : nullptr;
+  const float* vt_alias = (vtarget && where_in == RSB_HOST) ? mapped_alias(vtarget) : nullptr;
+  const bool pd_mode = b->control_mode == RSB_PD_PLUS_FEEDFORWARD_TORQUE && b->pd_set;
+  struct Unbind { rsb_batch* b; ~Unbind() { if (b->bound_once) { b->pt_bound = nullptr; b->vt_bound = nullptr; b->bound_once = false; } } } unbind{b};
+  if (ptarget) {
+    b->pt_bound = nullptr;
+    if (pt_alias && pd_mode) { b->pt_bound = pt_alias; b->pt_bound_stride = b->nq; b->bound_once = true; }
+    else { rc = copy_rows_in(b, b->pt, b->gc_stride, ptarget, b->nq, 0, b->N, where_in); if (rc) return rc; }
+  }
+  if (vtarget) {
+    if (vt_alias && pd_mode) { b->vt_bound = vt_alias; b->vt_bound_stride = b->nv; b->bound_once = true; }
+    else { rc = copy_rows_in(b, b->vt, b->gv_stride, vtarget, b->nv, 0, b->N, where_in); if (rc) return rc; }
+  }
   if (!obs || !b->model->md.floating) {
     rc = do_launch(b, substeps, 0, false); if (rc) return rc;
-    if (obs) return observe_impl(b, obs, 0, b->N, where_out, true);
-    return RSB_OK;
+    if (obs) rc = observe_impl(b, obs, 0, b->N, where_out, true);
+    if (b->bound_once) CK(cudaStreamSynchronize(b->stream));   // the caller may reuse its pinned target buffer on return
+    return rc;
   }
   // observation rows are written by the step kernel itself (no separate observe launch)
   float* dst = obs;
   const int od = rsb_batch_ob_dim(b);
+  float* obs_alias = where_out == RSB_HOST ? const_cast<float*>(mapped_alias(obs)) : nullptr;
+  if (obs_alias) {   // observation rows go straight to the caller's pinned buffer as each environment finishes
+    rc = do_launch(b, substeps, 0, false, obs_alias); if (rc) return rc;
+    CK(cudaStreamSynchronize(b->stream));
+    return RSB_OK;
+  }
   if (where_out == RSB_HOST) {
     size_t need = (size_t)b->N * od;
     if (b->obs_staging_words < need) {
@@ -695,7 +728,7 @@ int rsb_batch_control_step(rsb_batch* b, const float* ptarget, const float* vtar
   if (where_out == RSB_HOST) {
     CK(cudaMemcpyAsync(obs, dst, (size_t)b->N * od * 4, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
-  }
+  } else if (b->bound_once) CK(cudaStreamSynchronize(b->stream));
   return RSB_OK;
 }
 
@@ -748,10 +781,14 @@ int rsb_batch_gym_step(rsb_batch* b, const float* action, int where_in, int subs
   CK(cudaSetDevice(b->device));
   const int nj = b->nq - 7, od = rsb_batch_ob_dim(b);
   b->pt_bound = nullptr;              // the task writes its own PD-target rows
+  // pinned host buffers are read / written in place by the task kernels (see rsb_batch_control_step)
   const float* act = action;
   if (where_in == RSB_HOST) {
-    CK(cudaMemcpyAsync(b->gym_action, action, (size_t)b->N * nj * 4, cudaMemcpyHostToDevice, b->stream));
-    act = b->gym_action;
+    act = mapped_alias(action);
+    if (!act) {
+      CK(cudaMemcpyAsync(b->gym_action, action, (size_t)b->N * nj * 4, cudaMemcpyHostToDevice, b->stream));
+      act = b->gym_action;
+    }
   }
   {
     int threads = 256, blocks = (b->N * nj + threads - 1) / threads;
@@ -760,9 +797,13 @@ int rsb_batch_gym_step(rsb_batch* b, const float* action, int where_in, int subs
     b->launches++;
   }
   int rc = do_launch(b, substeps, 0, false); if (rc) return rc;
-  float* d_obs = (where_out == RSB_HOST || !obs) ? b->gym_obs : obs;
-  float* d_rew = (where_out == RSB_HOST || !reward) ? b->gym_reward : reward;
-  unsigned char* d_done = (where_out == RSB_HOST || !done) ? b->gym_done : done;
+  const bool host_out = where_out == RSB_HOST;
+  float* a_obs = (host_out && obs) ? const_cast<float*>(mapped_alias(obs)) : nullptr;
+  float* a_rew = (host_out && reward) ? const_cast<float*>(mapped_alias(reward)) : nullptr;
+  unsigned char* a_done = (host_out && done) ? reinterpret_cast<unsigned char*>(const_cast<float*>(mapped_alias(done))) : nullptr;
+  float* d_obs = a_obs ? a_obs : (host_out || !obs) ? b->gym_obs : obs;
+  float* d_rew = a_rew ? a_rew : (host_out || !reward) ? b->gym_reward : reward;
+  unsigned char* d_done = a_done ? a_done : (host_out || !done) ? b->gym_done : done;
   {
     int threads = 128, blocks = (b->N * 32 + threads - 1) / threads;
     rsb_gym_post_kernel<<<blocks, threads, 0, b->stream>>>(b->gc, b->gv, b->tau_applied, b->pt, b->ncontacts, b->contacts, b->gym, b->gc_stride, b->gv_stride,
@@ -771,9 +812,9 @@ int rsb_batch_gym_step(rsb_batch* b, const float* action, int where_in, int subs
     b->launches++;
   }
   if (where_out == RSB_HOST) {
-    if (obs) CK(cudaMemcpyAsync(obs, d_obs, (size_t)b->N * od * 4, cudaMemcpyDeviceToHost, b->stream));
-    if (reward) CK(cudaMemcpyAsync(reward, d_rew, (size_t)b->N * 4, cudaMemcpyDeviceToHost, b->stream));
-    if (done) CK(cudaMemcpyAsync(done, d_done, (size_t)b->N, cudaMemcpyDeviceToHost, b->stream));
+    if (obs && !a_obs) CK(cudaMemcpyAsync(obs, d_obs, (size_t)b->N * od * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (reward && !a_rew) CK(cudaMemcpyAsync(reward, d_rew, (size_t)b->N * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (done && !a_done) CK(cudaMemcpyAsync(done, d_done, (size_t)b->N, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
   }
   return RSB_OK;

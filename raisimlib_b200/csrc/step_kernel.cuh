@@ -149,10 +149,12 @@ struct TerrainDesc {
 
 struct StepArgs {
   int num_envs, substeps;
-  int gc_stride, gv_stride, pt_stride;   // pt_stride: row stride of ptarget (own padded buffer or a bound caller buffer)
+  int gc_stride, gv_stride, pt_stride, vt_stride;   // vt_stride likewise for vtarget; pt_stride: row stride of ptarget (own padded buffer or a bound caller buffer)
   float *gc, *gv;
   const float *tau, *ptarget, *vtarget;
   int use_pd;
+  float* pt_store;     // when the targets are read in place from a caller buffer (zero-copy, possibly pinned host memory):
+  float* vt_store;     // keep a copy in the batch's own rows, so that setPdTarget semantics (targets persist) hold
   rsb_params prm;
   TerrainDesc ter;
   WsLayout ws;
@@ -220,10 +222,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); spin++)
     if (spin > (1u << 26)) __trap();
 }
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src_gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+// Observation arithmetic shared by rsb_observe_kernel and the fused write in rsb_step_kernel: explicit
+// round-to-nearest intrinsics, so that both produce bit-identical rows whatever the compiler contracts elsewhere.
+// c = column `col` (0..2) of the base rotation matrix of the unit quaternion (qw, qx, qy, qz).
+__device__ __forceinline__ void obs_rot_column(float qw, float qx, float qy, float qz, int col, float& c0, float& c1, float& c2) {
+  const float xx = __fmul_rn(qx, qx), yy = __fmul_rn(qy, qy), zz = __fmul_rn(qz, qz);
+  const float xy = __fmul_rn(qx, qy), xz = __fmul_rn(qx, qz), yz = __fmul_rn(qy, qz);
+  const float wx = __fmul_rn(qw, qx), wy = __fmul_rn(qw, qy), wz = __fmul_rn(qw, qz);
+  const float r00 = __fsub_rn(1.f, __fmul_rn(2.f, __fadd_rn(yy, zz))), r01 = __fmul_rn(2.f, __fsub_rn(xy, wz)), r02 = __fmul_rn(2.f, __fadd_rn(xz, wy));
+  const float r10 = __fmul_rn(2.f, __fadd_rn(xy, wz)), r11 = __fsub_rn(1.f, __fmul_rn(2.f, __fadd_rn(xx, zz))), r12 = __fmul_rn(2.f, __fsub_rn(yz, wx));
+  const float r20 = __fmul_rn(2.f, __fsub_rn(xz, wy)), r21 = __fmul_rn(2.f, __fadd_rn(yz, wx)), r22 = __fsub_rn(1.f, __fmul_rn(2.f, __fadd_rn(xx, yy)));
+  c0 = col == 0 ? r00 : col == 1 ? r01 : r02;
+  c1 = col == 0 ? r10 : col == 1 ? r11 : r12;
+  c2 = col == 0 ? r20 : col == 1 ? r21 : r22;
+}
+__device__ __forceinline__ float obs_dot3(float c0, float c1, float c2, float x, float y, float z) {
+  return __fmaf_rn(c2, z, __fmaf_rn(c1, y, __fmul_rn(c0, x)));
 }
 
 // ------------------------------------------------------------------ slip search ----------------
@@ -473,10 +496,13 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
 #pragma unroll 1
       for (int i = lane; i < nv; i += 32) s_tau[i] = args.tau ? args.tau[(size_t)env * args.gv_stride + i] : 0.f;
       if (args.use_pd) {
+        // PD targets are first needed in stage C: fetch them asynchronously (cp.async, global -> shared) so that a
+        // caller buffer in pinned host memory (zero-copy control step) is read over PCIe behind stages A and B
 #pragma unroll 1
-        for (int i = lane; i < nq; i += 32) s_pt[i] = args.ptarget[(size_t)env * args.pt_stride + i];
+        for (int i = lane; i < nq; i += 32) cp_async4(&s_pt[i], &args.ptarget[(size_t)env * args.pt_stride + i]);
 #pragma unroll 1
-        for (int i = lane; i < nv; i += 32) s_vt[i] = args.vtarget[(size_t)env * args.gv_stride + i];
+        for (int i = lane; i < nv; i += 32) cp_async4(&s_vt[i], &args.vtarget[(size_t)env * args.vt_stride + i]);
+        asm volatile("cp.async.commit_group;" ::: "memory");
       }
     }
     __syncwarp();
@@ -735,7 +761,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       }
       const int C = 3 * K;
       if (args.prof && lane == 0) args.prof[((size_t)env * 4 + (sub & 3)) * 8 + 2] = (unsigned)clock64();
-      if (args.phase_mask & 1) { __syncwarp(); break; }   // integrate1(): kinematics, collision, M, h only
+      if (args.phase_mask & 1) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncwarp(); break; }   // integrate1(): kinematics, collision, M, h only
 
       if (args.substep_barrier >= 2) asm volatile("bar.sync 1, %0;" ::"r"(bar_threads));
       // =========================== stage C: b, Mhat = L^T L, z, Y, G ==============================
@@ -756,6 +782,18 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         __syncwarp();
       }
       const int C3 = C, CR = C3 + Lm;   // contact rows, all constraint rows
+      if (sub == 0 && args.use_pd) {     // the asynchronous target fetch of the prologue lands here
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        if (args.pt_store) {
+#pragma unroll 1
+          for (int i = lane; i < nq; i += 32) args.pt_store[(size_t)env * args.gc_stride + i] = s_pt[i];
+        }
+        if (args.vt_store) {
+#pragma unroll 1
+          for (int i = lane; i < nv; i += 32) args.vt_store[(size_t)env * args.gv_stride + i] = s_vt[i];
+        }
+      }
 #pragma unroll 1
       for (int i = lane; i < nv; i += 32) {
         float bi = s_tau[i] - s_h[i];
@@ -1117,17 +1155,15 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       float qw = s_gc[3], qx = s_gc[4], qy = s_gc[5], qz = s_gc[6];
       const float inv = 1.0f / sqrtf(qw * qw + qx * qx + qy * qy + qz * qz);
       qw *= inv; qx *= inv; qy *= inv; qz *= inv;
-      // column `lane` of the base rotation (lanes 0..2), selected without a lane-indexed local array
-      const float c0 = lane == 0 ? 1.f - 2.f * (qy * qy + qz * qz) : lane == 1 ? 2.f * (qx * qy - qw * qz) : 2.f * (qx * qz + qw * qy);
-      const float c1 = lane == 0 ? 2.f * (qx * qy + qw * qz) : lane == 1 ? 1.f - 2.f * (qx * qx + qz * qz) : 2.f * (qy * qz - qw * qx);
-      const float c2 = lane == 0 ? 2.f * (qx * qz - qw * qy) : lane == 1 ? 2.f * (qy * qz + qw * qx) : 1.f - 2.f * (qx * qx + qy * qy);
       float* o = args.obs + (size_t)env * args.ob_dim;
       const int nj = nq - 7;
       if (lane == 0) o[0] = s_gc[2];
-      if (lane < 3) {
+      if (lane < 3) {   // same arithmetic as rsb_observe_kernel (aux_kernels.cuh)
+        float c0, c1, c2;
+        obs_rot_column(qw, qx, qy, qz, lane, c0, c1, c2);
         o[1 + lane] = c2;
-        o[4 + nj + lane] = c0 * s_gv[0] + c1 * s_gv[1] + c2 * s_gv[2];
-        o[7 + nj + lane] = c0 * s_gv[3] + c1 * s_gv[4] + c2 * s_gv[5];
+        o[4 + nj + lane] = obs_dot3(c0, c1, c2, s_gv[0], s_gv[1], s_gv[2]);
+        o[7 + nj + lane] = obs_dot3(c0, c1, c2, s_gv[3], s_gv[4], s_gv[5]);
       }
 #pragma unroll 1
       for (int i = lane; i < nj; i += 32) { o[4 + i] = s_gc[7 + i]; o[10 + nj + i] = s_gv[6 + i]; }

@@ -427,6 +427,23 @@ def test_control_step_equals_separate_calls(capi):
     bt.bind_pd_target(None)
     assert np.array_equal(g_ref, g3) and np.array_equal(v_ref, v3)
     assert np.array_equal(ref_obs, pin_o.numpy())          # observation rows written by the step kernel == observe kernel
+    # pageable host buffers take the staged-copy path: same result
+    bt.set_state(gc.astype(np.float32), gv.astype(np.float32))
+    o_np = np.empty((n, 34), np.float32)
+    bt.control_step(target.copy(), 4, o_np)
+    g4, v4 = bt.get_state()
+    assert np.array_equal(g_ref, g4) and np.array_equal(v_ref, v4) and np.array_equal(ref_obs, o_np)
+    # targets read in place from pinned host memory persist like setPdTarget(): the caller may reuse its buffer
+    bt.integrate(4)
+    g_ref8, v_ref8 = bt.get_state()
+    bt.set_pd_target(np.zeros((n, 19), np.float32), None)           # clobber the stored targets
+    bt.set_state(gc.astype(np.float32), gv.astype(np.float32))
+    scratch = pin_t.clone().pin_memory()
+    bt.control_step(scratch, 4, pin_o)
+    scratch.zero_()
+    bt.integrate(4)
+    g8, v8 = bt.get_state()
+    assert np.array_equal(g_ref8, g8) and np.array_equal(v_ref8, v8)
 
 
 @pytest.mark.parametrize("n", [1, 5, 4097, 9000])
@@ -545,6 +562,19 @@ def test_gym_task_matches_numpy_restatement(capi):
     g, v = bt.get_state()
     tau = bt.generalized_force()
     assert np.isfinite(g).all() and np.isfinite(tau).all()
+    # pinned host buffers are read / written in place by the task kernels: identical to the staged-copy path
+    import torch
+    act = (base + rng.normal(0, 0.3, (n, 12))).astype(np.float32)
+    bt.gym_step(act, substeps, obs, rew, done)
+    g1, v1 = bt.get_state()
+    bt.set_state(g, v)
+    p_act = torch.from_numpy(act).pin_memory()
+    p_obs = torch.empty((n, 34), dtype=torch.float32).pin_memory(); p_rew = torch.empty(n, dtype=torch.float32).pin_memory()
+    p_done = torch.empty(n, dtype=torch.uint8).pin_memory()
+    bt.gym_step(p_act, substeps, p_obs, p_rew, p_done)
+    g2, v2 = bt.get_state()
+    assert np.array_equal(g1, g2) and np.array_equal(v1, v2)
+    assert np.array_equal(obs, p_obs.numpy()) and np.array_equal(rew, p_rew.numpy()) and np.array_equal(done, p_done.numpy())
 
 
 def test_cpp_vectorized_environment_example(capi):
