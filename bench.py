@@ -228,21 +228,22 @@ def main():
     bt.set_pd_target(tg_dev[0], vt_dev)
     obs = torch.empty((n, od), dtype=torch.float32, device="cuda")
     obs_all = torch.empty((world * n, od), dtype=torch.float32, device="cuda") if world > 1 else obs
-    obs_host = torch.empty((world * n, od), dtype=torch.float32).pin_memory()
+    obs_host = torch.empty((n, od), dtype=torch.float32).pin_memory() if world == 1 else None
+    shared = None
+    if world > 1:
+        # e2e arm at N > 1: the host-side consumer reads one [world*n, obDim] array in shared, page-locked memory; every
+        # rank's step kernel writes its own rows in place over its own PCIe link (no NVLink hop, no D2H funnel on rank 0)
+        from raisimlib_b200.sharding import SharedHostRows
+        shared = SharedHostRows(f"bench_{os.environ.get('MASTER_PORT', '0')}", world, rank, n, od)
+        sync_flag = torch.zeros(1, dtype=torch.float32, device="cuda")
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device="cuda")
 
     def control_step(k, host_io):
-        if host_io:
-            bt.set_pd_target(tg_pin[k % RING], None)        # pinned H2D inside the timed region
-        else:
-            bt.bind_pd_target(tg_dev[k % RING])             # resident targets read in place (zero-copy)
+        assert not host_io
+        bt.bind_pd_target(tg_dev[k % RING])                  # resident targets read in place (zero-copy)
         bt.control_step(None, SUBSTEPS, obs)                 # ONE fused launch: 4 x World::integrate() + observation rows
         if world > 1:
             allgather_observations(obs, obs_all)             # the only collective of the path
-        if host_io:
-            if rank == 0:
-                obs_host.copy_(obs_all, non_blocking=True)   # D2H of the step's result
-            stream.synchronize()
 
     def barrier():
         if world > 1:
@@ -264,19 +265,22 @@ def main():
                 ev[k][1].record(stream)
                 continue
             if host_io:
-                bt.set_pd_target(tg_pin[(step0 + k) % RING], None)
-            else:
-                bt.bind_pd_target(tg_dev[(step0 + k) % RING])    # resident targets read in place (zero-copy)
+                # N > 1: same call per rank, observation rows land in the shared host array; one tiny all-reduce is the
+                # barrier after which the trainer's rank may read every row
+                kev[k][0].record(stream)
+                bt.control_step(tg_pin[(step0 + k) % RING], SUBSTEPS, shared.local)
+                kev[k][1].record(stream)
+                dist.all_reduce(sync_flag)
+                ev[k][1].record(stream)
+                stream.synchronize()                         # the caller reads the observation before acting
+                continue
+            bt.bind_pd_target(tg_dev[(step0 + k) % RING])    # resident targets read in place (zero-copy)
             kev[k][0].record(stream)
             bt.control_step(None, SUBSTEPS, obs)             # ONE launch: 4 fused sub-steps + observation rows
             kev[k][1].record(stream)
             if world > 1:
                 allgather_observations(obs, obs_all)
-            if host_io and rank == 0:
-                obs_host.copy_(obs_all, non_blocking=True)   # the gathered rows go back to the host once, on the trainer's rank
             ev[k][1].record(stream)
-            if host_io:
-                stream.synchronize()                         # the caller reads the observation before acting
         barrier()
         ms = sum(a.elapsed_time(b) for a, b in ev)
         kms = sum(a.elapsed_time(b) for a, b in kev)
@@ -332,7 +336,9 @@ def main():
                        "envs_per_gpu": n, "substeps_per_step": SUBSTEPS, "l2": "flushed between timed iterations (256 MiB write)",
                        "mean_contacts_per_env": kbar, "mean_solver_iters": float(stats[1]), "max_solver_iters": float(stats[2]),
                        "standing_fraction": float(stats[3]), "parallelism": f"env-shard x{world}" + (", NCCL obs all-gather" if world > 1 else "")},
-            "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": int(n * 19 * 4), "d2h_bytes_per_step": int(world * n * od * 4)},
+            "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": int(world * n * 19 * 4), "d2h_bytes_per_step": int(world * n * od * 4),
+                    "path": "pinned host targets and observation rows read / written in place by the step kernel (zero-copy over PCIe)"
+                            + ("; rows of all ranks land in one shared page-locked array, one all-reduce as barrier" if world > 1 else "")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "rsb_step_kernel (fused FK+CRBA+RNEA+narrow-phase+contact solver+integrate)",
@@ -343,6 +349,8 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(n, 400)
         print(json.dumps(line), flush=True)
+    if shared is not None:
+        shared.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -30,3 +30,50 @@ def allgather_observations(obs_local, out=None):
         out = torch.empty((world * obs_local.shape[0], obs_local.shape[1]), dtype=obs_local.dtype, device=obs_local.device)
     dist.all_gather_into_tensor(out, obs_local.contiguous())
     return out
+
+
+class SharedHostRows:
+    """A [world * rows_per_rank, width] float32 array in POSIX shared memory that every rank maps and page-locks.
+
+    Host-side consumers (a trainer process on rank 0 reading observation rows) do not need the NVLink all-gather:
+    each rank's step kernel writes its own block of rows IN PLACE over its own PCIe link (the C-ABI recognises the
+    page-locked buffer and binds it zero-copy), all links in parallel; one barrier later every row is visible to
+    every process.  `local` is this rank's block (a numpy view to hand to Batch.control_step), `all` the whole array.
+    """
+
+    def __init__(self, tag, world, rank, rows_per_rank, width, register=True, barrier=None):
+        import os
+        import numpy as np
+        self.path = f"/dev/shm/rsb_{tag}"
+        self.rank, self.registered = rank, False
+        shape = (world * rows_per_rank, width)
+        nbytes = shape[0] * shape[1] * 4
+        barrier = barrier or (dist.barrier if (dist.is_available() and dist.is_initialized()) else (lambda: None))
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(nbytes)
+        barrier()
+        self.all = np.memmap(self.path, dtype=np.float32, mode="r+", shape=shape)
+        self.local = self.all[rank * rows_per_rank:(rank + 1) * rows_per_rank]
+        self._ptr, self._nbytes = self.all.ctypes.data, nbytes
+        if register:
+            rc = torch.cuda.cudart().cudaHostRegister(self._ptr, nbytes, 1 | 2)      # portable | mapped
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister failed with {rc}")
+            self.registered = True
+        barrier()
+
+    def close(self, barrier=None):
+        import os
+        if self.registered:
+            torch.cuda.cudart().cudaHostUnregister(self._ptr)
+            self.registered = False
+        barrier = barrier or (dist.barrier if (dist.is_available() and dist.is_initialized()) else (lambda: None))
+        barrier()
+        self.local = None
+        self.all = None
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass

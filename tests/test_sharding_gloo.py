@@ -33,7 +33,14 @@ def _worker(rank, world, port, total, q):
     lo, hi = shard_range(total, world, rank)
     local = torch.from_numpy(_obs_rows(gc[lo:hi], gv[lo:hi]))
     full = allgather_observations(local)
-    q.put((rank, lo, hi, full.numpy().copy()))
+    # host-side consumers: every rank writes its own block of a shared, mapped array; one barrier makes all rows visible
+    from raisimlib_b200.sharding import SharedHostRows
+    sh = SharedHostRows(f"test_{port}", world, rank, hi - lo, 34, register=False)
+    sh.local[:] = local.numpy()
+    dist.barrier()
+    shared_copy = np.array(sh.all)
+    sh.close()
+    q.put((rank, lo, hi, full.numpy().copy(), shared_copy))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -64,10 +71,11 @@ def test_allgather_two_ranks_gloo():
     t = load_tables(os.path.join(ROOT, "raisimlib_b200", "rsc", "anymal_c_like.urdf"))
     gc, gv = random_state(t, np.random.default_rng(5), total)
     ref = _obs_rows(gc, gv)
-    for rank, lo, hi, full in got:
+    for rank, lo, hi, full, shared_copy in got:
         assert (lo, hi) == (rank * 8, rank * 8 + 8)
         assert full.shape == (total, 34)
         assert np.array_equal(full, ref)          # every rank holds all rows, in rank order
+        assert np.array_equal(shared_copy, ref)   # the shared host array holds the same rows on every rank
 
 
 def test_allgather_single_process_is_identity():
