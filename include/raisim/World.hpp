@@ -197,6 +197,27 @@ class ArticulatedSystem {
     for (size_t i = 0; i < t.size(); i++) r[i] = t[i];
     return r;
   }
+  // upstream: setExternalForce(localIdx, force) acts at the body COM, setExternalForce(localIdx, pos_in_body, force) at a
+  // point fixed in the body, setExternalTorque(localIdx, torque); world frame, valid for the next integrate() only.
+  // One wrench (force + torque on the same body) per environment.
+  void setExternalForce(size_t localIdx, const Vec<3>& force) {
+    rsb_model_tables t; rsbCheck(rsb_model_get_tables(w_->model(), &t), "getTables");
+    Vec<3> c{t.com[localIdx * 3], t.com[localIdx * 3 + 1], t.com[localIdx * 3 + 2]};
+    setExternalForce(localIdx, c, force);
+  }
+  void setExternalForce(size_t localIdx, const Vec<3>& posInBody, const Vec<3>& force) {
+    if (extBody_ >= 0 && extBody_ != int(localIdx)) throw std::runtime_error("setExternalForce: one external wrench per environment (force and torque must act on the same body)");
+    extBody_ = int(localIdx); extHasForce_ = true;
+    for (int k = 0; k < 3; k++) { extF_[k] = float(force[k]); extP_[k] = float(posInBody[k]); }
+    pushWrench();
+  }
+  void setExternalTorque(size_t localIdx, const Vec<3>& torque) {
+    if (extBody_ >= 0 && extBody_ != int(localIdx)) throw std::runtime_error("setExternalTorque: one external wrench per environment (force and torque must act on the same body)");
+    extBody_ = int(localIdx);
+    for (int k = 0; k < 3; k++) extT_[k] = float(torque[k]);
+    pushWrench();
+  }
+  void clearExternalWrench() { extBody_ = -1; extHasForce_ = false; for (int k = 0; k < 3; k++) extF_[k] = extT_[k] = extP_[k] = 0.f; }   // called by World::integrate()
   // friction of one collision body against the terrain (upstream: getCollisionBody(name).setMaterial + setMaterialPairProp)
   void setCollisionBodyFriction(size_t collisionBodyIdx, double mu) {
     rsbCheck(rsb_batch_set_collision_friction(w_->batch(), int(collisionBodyIdx), float(mu)), "setCollisionBodyFriction");
@@ -257,6 +278,11 @@ class ArticulatedSystem {
   }
   int env() const { return env_; }
  private:
+  void pushWrench() {
+    rsbCheck(rsb_batch_set_external_wrench(w_->batch(), extBody_, extF_, extT_, extP_, env_, 1, RSB_HOST), "setExternalForce");
+  }
+  int extBody_ = -1; bool extHasForce_ = false;
+  float extF_[3] = {0, 0, 0}, extT_[3] = {0, 0, 0}, extP_[3] = {0, 0, 0};
   struct Poses { std::vector<float> R, p; };
   struct FrameW { int body; Vec<3> pos; Mat<3, 3> rot; };
   Poses poses() const {
@@ -366,9 +392,9 @@ class World {
   }
   // one World::integrate() of THIS environment's batch.  Views of a shared batch must not call this
   // per environment -- the vectorized wrapper steps the whole batch once (see VectorizedEnvironment.hpp).
-  void integrate() { need(); w_->integrate(1); }
+  void integrate() { need(); w_->integrate(1); if (robot_) robot_->clearExternalWrench(); }
   void integrate1() { need(); w_->integrate1(); }
-  void integrate2() { need(); w_->integrate2(); }
+  void integrate2() { need(); w_->integrate2(); if (robot_) robot_->clearExternalWrench(); }
   double getWorldTime() const { return w_ ? w_->worldTime() : 0.0; }
   ArticulatedSystem* getRobot() { return robot_.get(); }
   BatchedWorld* batched() { return w_; }

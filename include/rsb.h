@@ -139,6 +139,12 @@ int rsb_batch_set_pd_target(rsb_batch* b, const float* ptarget, const float* vta
 int rsb_batch_bind_pd_target(rsb_batch* b, const float* ptarget_device, int row_stride);
 int rsb_batch_set_generalized_force(rsb_batch* b, const float* tau, int env_begin, int env_count, int where);
 int rsb_batch_set_control_mode(rsb_batch* b, int mode);
+/* ArticulatedSystem::setExternalForce(bodyIdx, pos, force) / setExternalTorque(bodyIdx, torque): one wrench per
+ * environment on `body`, applied at point_body[3] (body frame, host pointer; NULL = body origin); force / torque are
+ * [env_count][3] world-frame rows (NULL = zero).  Like upstream it acts during the next integrate() call only (all fused
+ * sub-steps of that call) and is cleared afterwards. */
+int rsb_batch_set_external_wrench(rsb_batch* b, int body, const float* force, const float* torque, const float* point_body,
+                                  int env_begin, int env_count, int where);
 /* ArticulatedSystem::getGeneralizedForce(): feed-forward + PD force applied over the last integrate() */
 int rsb_batch_get_generalized_force(rsb_batch* b, float* tau, int env_begin, int env_count, int where);
 

@@ -35,8 +35,10 @@ class _ModelDesc(C.Structure):
 
 
 class _Debug(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("M", "h", "R", "p", "ncontacts", "c_pt", "c_body", "c_pair", "c_pos",
-                                          "c_normal", "c_depth", "c_lambda", "iters", "G", "u0", "warm_pt", "warm_imp", "tau_applied", "nlimits", "lim_dof", "lim_lambda")]
+    _fields_ = ([(n, C.c_void_p) for n in ("M", "h", "R", "p", "ncontacts", "c_pt", "c_body", "c_pair", "c_pos",
+                                           "c_normal", "c_depth", "c_lambda", "iters", "G", "u0")]
+                + [("ext_body", C.c_int), ("ext_force", C.c_void_p), ("ext_torque", C.c_void_p), ("ext_point", C.c_double * 3)]
+                + [(n, C.c_void_p) for n in ("warm_pt", "warm_imp", "tau_applied", "nlimits", "lim_dof", "lim_lambda")])
 
 
 _lib = None
@@ -111,8 +113,10 @@ class Oracle:
         self._pt_mu[np.asarray(self.t["pt_coll"]) == collision_body] = mu
         lib().orc_set_point_mu(self.h, _p(self._pt_mu))
 
-    def step(self, gc, gv, n_steps=1, tau_ff=None, ptarget=None, vtarget=None, kp=None, kd=None, nthreads=0, debug=False):
-        """gc [n,nq], gv [n,nv] float64 C-contiguous, updated IN PLACE.  Returns debug dict or None."""
+    def step(self, gc, gv, n_steps=1, tau_ff=None, ptarget=None, vtarget=None, kp=None, kd=None, nthreads=0, debug=False, ext=None):
+        """gc [n,nq], gv [n,nv] float64 C-contiguous, updated IN PLACE.  Returns debug dict or None.
+        ext = (body, force [n,3] world | None, torque [n,3] world | None, point in body frame (3) | None): external wrench
+        acting during this call (ArticulatedSystem::setExternalForce / setExternalTorque)."""
         assert gc.dtype == np.float64 and gv.dtype == np.float64 and gc.flags.c_contiguous and gv.flags.c_contiguous
         n = gc.shape[0]
         assert gc.shape == (n, self.nq) and gv.shape == (n, self.nv)
@@ -134,6 +138,15 @@ class Oracle:
         ptrs = {k: v.ctypes.data for k, v in out.items()}
         ptrs["warm_pt"], ptrs["warm_imp"] = self.warm_pt.ctypes.data, self.warm_imp.ctypes.data
         dbg = _Debug(**ptrs)
+        dbg.ext_body = -1
+        if ext is not None:
+            eb, ef, et, ep = ext
+            ef = None if ef is None else np.ascontiguousarray(np.broadcast_to(np.asarray(ef, np.float64), (n, 3)))
+            et = None if et is None else np.ascontiguousarray(np.broadcast_to(np.asarray(et, np.float64), (n, 3)))
+            dbg.ext_body = int(eb)
+            dbg.ext_force = None if ef is None else ef.ctypes.data
+            dbg.ext_torque = None if et is None else et.ctypes.data
+            dbg.ext_point = (C.c_double * 3)(*(np.zeros(3) if ep is None else np.asarray(ep, np.float64)))
         lib().orc_step(self.h, n, n_steps, _p(gc), _p(gv), _p(tau_ff), _p(ptarget), _p(vtarget), _p(kp), _p(kd),
                        int(nthreads), C.byref(dbg))
         return out if debug else None

@@ -24,6 +24,10 @@ struct OrcDebug {       // every pointer optional; sized for n_envs; filled from
   int* iters;           // [n]
   double* G;            // [n][(3*KMAX)^2]  Delassus matrix of the kept contacts (row stride 3*KMAX)
   double* u0;           // [n][3*KMAX]      free contact velocity minus target
+  int ext_body;         // IN external wrench for this call (all sub-steps): body index, < 0 = none
+  const double* ext_force;   // [n][3] world, nullable
+  const double* ext_torque;  // [n][3] world, nullable
+  double ext_point[3];  // application point in the body frame
   int* warm_pt;         // [n][KMAX]   IN/OUT contact cache (candidate-point ids, -1 = empty); null = cold start
   double* warm_imp;     // [n][KMAX*3] IN/OUT world-frame impulses of the cache
   double* tau_applied;  // [n][nv]     generalized force applied over the last step
@@ -37,6 +41,9 @@ struct Handle {
   std::unique_ptr<Sim<double>> d;
   std::unique_ptr<Sim<float>> f;
 };
+
+long long g_counts[4] = {0, 0, 0, 0};   // per-contact rule outcomes summed over all run() calls (statistics for tools/, tests)
+extern "C" void orc_get_counts(long long* out, int reset) { for (int k = 0; k < 4; k++) { out[k] = g_counts[k]; if (reset) g_counts[k] = 0; } }
 
 template <typename T>
 static void run(Sim<T>& sim, int n_envs, int n_steps, double* gc, double* gv, const double* tau, const double* pt, const double* vt,
@@ -60,6 +67,13 @@ static void run(Sim<T>& sim, int n_envs, int n_steps, double* gc, double* gv, co
       for (int k = 0; k < KMAX; k++) {
         ws.prev_pt[k] = (dbg && dbg->warm_pt) ? dbg->warm_pt[(size_t)e * KMAX + k] : -1;
         if (dbg && dbg->warm_imp) ws.prev_imp[k] = {T(dbg->warm_imp[((size_t)e * KMAX + k) * 3]), T(dbg->warm_imp[((size_t)e * KMAX + k) * 3 + 1]), T(dbg->warm_imp[((size_t)e * KMAX + k) * 3 + 2])};
+      }
+      ws.ext_body = -1;
+      if (dbg && dbg->ext_body >= 0) {
+        ws.ext_body = dbg->ext_body;
+        ws.ext_f = dbg->ext_force ? V3<T>{T(dbg->ext_force[3 * (size_t)e]), T(dbg->ext_force[3 * (size_t)e + 1]), T(dbg->ext_force[3 * (size_t)e + 2])} : V3<T>{0, 0, 0};
+        ws.ext_t = dbg->ext_torque ? V3<T>{T(dbg->ext_torque[3 * (size_t)e]), T(dbg->ext_torque[3 * (size_t)e + 1]), T(dbg->ext_torque[3 * (size_t)e + 2])} : V3<T>{0, 0, 0};
+        ws.ext_pos = {T(dbg->ext_point[0]), T(dbg->ext_point[1]), T(dbg->ext_point[2])};
       }
       for (int s = 0; s < n_steps; s++)
         sim.step(q.data(), v.data(), tau ? tf.data() : nullptr, pt ? ptt.data() : nullptr, vt ? vtt.data() : nullptr,
@@ -97,6 +111,8 @@ static void run(Sim<T>& sim, int n_envs, int n_steps, double* gc, double* gv, co
         }
       }
     }
+#pragma omp critical
+    for (int k = 0; k < 4; k++) g_counts[k] += ws.counts[k];
   }
 }
 

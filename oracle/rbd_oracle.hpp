@@ -123,6 +123,9 @@ template <typename T> struct Limit { int dof; T sign, viol, lam; };   // joint-l
 
 template <typename T> struct Workspace {
   int nb, nv;
+  // external wrench of this step (ArticulatedSystem::setExternalForce / setExternalTorque): body < 0 = none
+  int ext_body = -1; V3<T> ext_f{0, 0, 0}, ext_t{0, 0, 0}, ext_pos{0, 0, 0};
+  long long counts[4] = {0, 0, 0, 0};   // per-contact rule outcomes: opening, stick, slip, slip found by the local fan (statistics only)
   std::vector<M3<T>> R;
   std::vector<V3<T>> p, a, w, v, wd, vd, F, N;
   std::vector<T> Ic;             // 10 per body: m, h(3), I_O(6: xx xy xz yy yz zz)
@@ -455,9 +458,9 @@ template <typename T> class Sim {
   // ---- a8: per-contact solve (Hwangbo et al. 2018, section IV) ------------------------------------
   // G: 3x3 (rows/cols t1,t2,n) block G_ii; c: contact velocity without this contact's own impulse
   // (already shifted by the ERP / restitution target).  Returns the new impulse.
-  void solve_one(const T* G, V3<T> c, T mu, V3<T>& lam, SlipDir<T>* sd = nullptr) const {
+  void solve_one(const T* G, V3<T> c, T mu, V3<T>& lam, SlipDir<T>* sd = nullptr, long long* counts = nullptr) const {
     SlipDir<T> prev; if (sd) { prev = *sd; sd->valid = false; }
-    if (c.z > T(0)) { lam = {0, 0, 0}; return; }                 // opening
+    if (c.z > T(0)) { lam = {0, 0, 0}; if (counts) counts[0]++; return; }                 // opening
     // stick candidate: lam = -G^-1 c
     T a = G[0], b = G[1], cc = G[2], d = G[4], e = G[5], f = G[8];
     T c00 = d * f - e * e, c01 = cc * e - b * f, c02 = b * e - cc * d;
@@ -465,7 +468,8 @@ template <typename T> class Sim {
     T det = a * c00 + b * c01 + cc * c02;
     T id = T(1) / det;
     V3<T> ls = {-(c00 * c.x + c01 * c.y + c02 * c.z) * id, -(c01 * c.x + c11 * c.y + c12 * c.z) * id, -(c02 * c.x + c12 * c.y + c22 * c.z) * id};
-    if (ls.z >= T(0) && ls.x * ls.x + ls.y * ls.y <= mu * mu * ls.z * ls.z) { lam = ls; return; }   // stick
+    if (ls.z >= T(0) && ls.x * ls.x + ls.y * ls.y <= mu * mu * ls.z * ls.z) { lam = ls; if (counts) counts[1]++; return; }   // stick
+    if (counts) counts[2]++;
     // slip: lam(theta) = lz(theta) * (mu cos, mu sin, 1),  lz = -c_z / (G_zz + mu (G_zx cos + G_zy sin))
     // minimise f = c.lam + 1/2 lam^T G lam on that curve: find the - to + sign change of
     //   g(theta) = (v_t . u_perp) D - mu (G_zt . u_perp)(v_t . u),    v_t = tangential part of c + G lam
@@ -505,6 +509,7 @@ template <typename T> class Sim {
         lo_c = dc[pick]; lo_s = ds[pick]; hi_c = dc[pick + 1]; hi_s = ds[pick + 1]; glo = gk[pick]; ghi = gk[pick + 1];
         base_c = lo_c; base_s = lo_s; have = true; best = lk[pick];
         r_start = 2;
+        if (counts) counts[3]++;
       }
     }
     for (int r = r_start; r < (prm.slip_bisect ? 1 : NROUNDS); r++) {
@@ -570,6 +575,18 @@ template <typename T> class Sim {
     // a5: generalized force with implicit PD (ArticulatedSystem::setPdGains / setPdTarget):
     //   b = tau_ff + Kp (q* - q - dt v) + Kd (v* - v) - h ;   Mhat = M + dt Kd + dt^2 Kp
     for (int i = 0; i < nv; i++) ws.b[i] = (tau_ff ? tau_ff[i] : T(0)) - ws.h[i];
+    if (ws.ext_body >= 0) {   // b += J_p^T F + J_r^T T for a world-frame wrench at a point fixed in the body
+      const int eb = ws.ext_body;
+      const V3<T> P = ws.p[eb] + ws.R[eb] * ws.ext_pos;
+      if (floating) {
+        const V3<T> m = cross(P - ws.p[0], ws.ext_f) + ws.ext_t;
+        ws.b[0] += ws.ext_f.x; ws.b[1] += ws.ext_f.y; ws.b[2] += ws.ext_f.z; ws.b[3] += m.x; ws.b[4] += m.y; ws.b[5] += m.z;
+      }
+      for (int j = eb; parent[j] >= 0; j = parent[j]) {
+        if (jtype[j] == JT_REVOLUTE) ws.b[vidx[j]] += dot(cross(ws.a[j], P - ws.p[j]), ws.ext_f) + dot(ws.a[j], ws.ext_t);
+        else if (jtype[j] == JT_PRISMATIC) ws.b[vidx[j]] += dot(ws.a[j], ws.ext_f);
+      }
+    }
     ws.Mh = ws.M;
     std::vector<T>& Mh = ws.Mh;
     for (int i = 1; i < nb; i++) {
@@ -651,7 +668,7 @@ template <typename T> class Sim {
                       ws.u[3 * i + 1] - (Gii[3] * l0.x + Gii[4] * l0.y + Gii[5] * l0.z),
                       ws.u[3 * i + 2] - (Gii[6] * l0.x + Gii[7] * l0.y + Gii[8] * l0.z)};
           V3<T> ln;
-          solve_one(Gii, c0, pt_mu[ct.pt] >= T(0) ? pt_mu[ct.pt] : mu, ln, &ct.sdir);
+          solve_one(Gii, c0, pt_mu[ct.pt] >= T(0) ? pt_mu[ct.pt] : mu, ln, &ct.sdir, ws.counts);
           V3<T> dl = alpha * (ln - l0);
           ct.lam = l0 + dl;
           for (int a = 0; a < C; a++) ws.u[a] += ws.G[a * C + 3 * i] * dl.x + ws.G[a * C + 3 * i + 1] * dl.y + ws.G[a * C + 3 * i + 2] * dl.z;

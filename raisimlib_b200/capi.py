@@ -74,7 +74,7 @@ EXPORTED = [
     "rsb_batch_set_ground", "rsb_batch_set_heightmap", "rsb_batch_clear_terrain", "rsb_batch_set_params", "rsb_batch_get_params",
     "rsb_batch_set_collision_friction",
     "rsb_batch_set_state", "rsb_batch_get_state", "rsb_batch_set_pd_gains", "rsb_batch_set_pd_target",
-    "rsb_batch_set_generalized_force", "rsb_batch_set_control_mode", "rsb_batch_get_generalized_force", "rsb_batch_bind_pd_target",
+    "rsb_batch_set_generalized_force", "rsb_batch_set_external_wrench", "rsb_batch_set_control_mode", "rsb_batch_get_generalized_force", "rsb_batch_bind_pd_target",
     "rsb_batch_integrate1", "rsb_batch_integrate2", "rsb_batch_integrate",
     "rsb_batch_get_mass_matrix", "rsb_batch_get_nonlinearities", "rsb_batch_get_body_poses", "rsb_batch_get_contacts",
     "rsb_batch_get_contact_points", "rsb_batch_get_solver_iterations", "rsb_batch_get_diverged", "rsb_batch_device_ptrs", "rsb_batch_launch_count",
@@ -127,6 +127,7 @@ def lib():
         L.rsb_batch_set_pd_gains.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.rsb_batch_set_generalized_force.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.rsb_batch_set_control_mode.argtypes = [C.c_void_p, C.c_int]
+        L.rsb_batch_set_external_wrench.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.rsb_batch_bind_pd_target.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.rsb_batch_get_generalized_force.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.rsb_batch_integrate1.argtypes = [C.c_void_p]
@@ -391,6 +392,18 @@ class Batch:
 
     def ob_dim(self):
         return lib().rsb_batch_ob_dim(self.h)
+
+    def set_external_wrench(self, body, force=None, torque=None, point_body=None, env_begin=0, env_count=None):
+        """setExternalForce / setExternalTorque: world-frame force / torque rows [n, 3] on `body`, applied at point_body (body
+        frame, default = body origin) during the next integrate() / control_step() call only."""
+        n = self.n - env_begin if env_count is None else env_count
+        conv = lambda a: a if (a is None or hasattr(a, "data_ptr")) else np.ascontiguousarray(np.broadcast_to(np.asarray(a, np.float32), (n, 3)))
+        force, torque = conv(force), conv(torque)
+        pf, w1 = _ptr(force); pt_, w2 = _ptr(torque)
+        where = w1 if force is not None else w2
+        assert force is None or torque is None or w1 == w2
+        pp = None if point_body is None else np.ascontiguousarray(point_body, np.float32).ctypes.data_as(C.c_void_p)
+        _ck(lib().rsb_batch_set_external_wrench(self.h, int(body), pf, pt_, pp, env_begin, n, where))
 
     def control_step(self, ptarget, substeps, obs_out, vtarget=None):
         """one RaisimGym control step for the whole batch: targets in, fused sub-steps, observations out"""

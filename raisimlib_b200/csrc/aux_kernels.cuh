@@ -38,6 +38,17 @@ __global__ void rsb_observe_kernel(const float* __restrict__ gc, const float* __
   for (int i = lane; i < nj; i += 32) { o[4 + i] = q[7 + i]; o[10 + nj + i] = v[6 + i]; }
 }
 
+// external wrench rows for rsb_step_kernel (StepArgs::ext): [body | F(3) | T(3) | point in body frame(3) | pad(2)]
+__global__ void rsb_ext_pack_kernel(float* rows, int body, const float* __restrict__ force, const float* __restrict__ torque, float px, float py, float pz,
+                                    int count) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= count) return;
+  float* r = rows + (size_t)e * EXT_WORDS;
+  r[0] = __int_as_float(body);
+  for (int k = 0; k < 3; k++) { r[1 + k] = force ? force[(size_t)e * 3 + k] : 0.f; r[4 + k] = torque ? torque[(size_t)e * 3 + k] : 0.f; }
+  r[7] = px; r[8] = py; r[9] = pz; r[10] = 0.f; r[11] = 0.f;
+}
+
 }  // namespace rsb
 
 // ---- RaisimGym ANYmal locomotion task on the device ([RECALL] raisimGymTorch

@@ -42,6 +42,8 @@ struct rsb_batch {
   int vt_bound_stride = 0;
   bool bound_once = false;           // zero-copy control step: the kernel copies the rows it read into pt / vt, then the binding ends
   unsigned* prof = nullptr;          // rsb_internal_set_profile
+  float* ext = nullptr;              // [N][EXT_WORDS] external wrench rows; ext_active: rows hold a wrench for the next launch
+  bool ext_active = false;
   // device buffers
   float *gc = nullptr, *gv = nullptr, *tau = nullptr, *pt = nullptr, *vt = nullptr, *tau_applied = nullptr;
   int *ncontacts = nullptr, *contact_pt = nullptr, *iters = nullptr, *diverged = nullptr;
@@ -240,6 +242,7 @@ static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug, flo
   a.ncontacts = b->ncontacts; a.contacts = b->contacts; a.contact_pt = b->contact_pt; a.iters = b->iters; a.diverged = b->diverged;
   if (debug) { a.dbg_M = b->dbg_M; a.dbg_h = b->dbg_h; a.dbg_R = b->dbg_R; a.dbg_p = b->dbg_p; }
   a.phase_mask = phase_mask; a.prof = b->prof;
+  a.ext = b->ext_active ? b->ext : nullptr;
   a.obs = obs_dev; a.ob_dim = rsb_batch_ob_dim(b);
   {
     const char* e = getenv("RSB_SUBSTEP_BARRIER");
@@ -257,6 +260,7 @@ static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug, flo
   }
   if (e != cudaSuccess) return fail(RSB_ERR_CUDA, std::string("step kernel launch: ") + cudaGetErrorString(e));
   b->launches++;
+  if (phase_mask == 0 || (phase_mask & 2)) b->ext_active = false;   // an external wrench lasts for one integrate() call (upstream semantics)
   return RSB_OK;
 }
 
@@ -430,7 +434,7 @@ void rsb_batch_destroy(rsb_batch* b) {
   if (b->stream) cudaStreamSynchronize(b->stream);
   for (void* p : {(void*)b->diverged, (void*)b->tau_applied, (void*)b->gc, (void*)b->gv, (void*)b->tau, (void*)b->pt, (void*)b->vt, (void*)b->ncontacts, (void*)b->contact_pt, (void*)b->iters,
                   (void*)b->contacts, (void*)b->dbg_M, (void*)b->dbg_h, (void*)b->dbg_R, (void*)b->dbg_p, (void*)b->hmap, (void*)b->staging, (void*)b->obs_staging, (void*)b->blob, (void*)b->gym_const, (void*)b->gym_action,
-                  (void*)b->gym_obs, (void*)b->gym_reward, (void*)b->gym_done})
+                  (void*)b->gym_obs, (void*)b->gym_reward, (void*)b->gym_done, (void*)b->ext})
     if (p) cudaFree(p);
   if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
   delete b;
@@ -546,6 +550,33 @@ int rsb_batch_get_generalized_force(rsb_batch* b, float* tau, int env_begin, int
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
   rc = copy_rows_out(b, tau, b->tau_applied, b->gv_stride, b->nv, env_begin, env_count, where); if (rc) return rc;
   if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
+  return RSB_OK;
+}
+// ArticulatedSystem::setExternalForce / setExternalTorque for a range of environments: one wrench per environment,
+// acting on `body` at `point_body` (body frame; null = body origin), world-frame force / torque rows (null = zero).
+// It acts during the next integrate() / control-step call (all of its fused sub-steps) and is cleared afterwards.
+int rsb_batch_set_external_wrench(rsb_batch* b, int body, const float* force, const float* torque, const float* point_body, int env_begin, int env_count, int where) {
+  int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  if (body < 0 || body >= b->nb) return fail(RSB_ERR_INVALID, "external wrench: body index out of range");
+  CK(cudaSetDevice(b->device));
+  if (!b->ext) CK(cudaMalloc((void**)&b->ext, (size_t)b->N * EXT_WORDS * 4));
+  if (!b->ext_active) {   // rows of an earlier call are stale: body = -1 everywhere
+    CK(cudaMemsetAsync(b->ext, 0xff, (size_t)b->N * EXT_WORDS * 4, b->stream));
+    b->ext_active = true;
+  }
+  const float *df = force, *dtq = torque;
+  if (where == RSB_HOST && (force || torque)) {
+    rc = ensure_staging(b, (size_t)b->N * 64 + 64); if (rc) return rc;
+    float* st = b->staging + b->staging_cursor;
+    b->staging_cursor = (b->staging_cursor + (size_t)env_count * 6 + 31) / 32 * 32;
+    if (b->staging_cursor + (size_t)b->N * 40 > b->staging_words) b->staging_cursor = 0;
+    if (force) { CK(cudaMemcpyAsync(st, force, (size_t)env_count * 12, cudaMemcpyHostToDevice, b->stream)); df = st; }
+    if (torque) { CK(cudaMemcpyAsync(st + (size_t)env_count * 3, torque, (size_t)env_count * 12, cudaMemcpyHostToDevice, b->stream)); dtq = st + (size_t)env_count * 3; }
+  }
+  const float px = point_body ? point_body[0] : 0.f, py = point_body ? point_body[1] : 0.f, pz = point_body ? point_body[2] : 0.f;
+  const int threads = 128, blocks = (env_count + threads - 1) / threads;
+  rsb_ext_pack_kernel<<<blocks, threads, 0, b->stream>>>(b->ext + (size_t)env_begin * EXT_WORDS, body, df, dtq, px, py, pz, env_count);
+  CK(cudaGetLastError());
   return RSB_OK;
 }
 int rsb_batch_set_control_mode(rsb_batch* b, int mode) {

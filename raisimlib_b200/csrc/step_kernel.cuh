@@ -39,6 +39,7 @@ constexpr int NSEC = 32;
 constexpr int NROUNDS = 3;         // 32-section rounds: bracket 2*pi/32^(r+1); the closing secant step is then exact to float32
 constexpr int SEC_STRIDE = 36;      // (NSEC+1) padded
 constexpr int CT_WORDS = 16;        // per-contact shared record
+constexpr int EXT_WORDS = 12;       // external wrench row: body (int bits), force(3), torque(3), point in the body frame(3), 2 pad
 constexpr int MAX_PT_SLOTS = 2;     // candidate points per lane (npts <= 64)
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -170,6 +171,7 @@ struct StepArgs {
   float *dbg_M, *dbg_h, *dbg_R, *dbg_p;   // optional (integrate1 / getters)
   float* obs;          // optional [N][ob_dim]: RaisimGym observation row of the final state, written by this kernel
   int ob_dim;
+  const float* ext;    // optional [num_envs][EXT_WORDS] external wrench rows (body, F world, T world, point in body frame); null = none
   unsigned* prof;      // optional [num_envs][4 sub-steps][8] SM-clock stamps at the stage boundaries (tools/balance_probe.py)
   int phase_mask;      // bit0: stop after stage C (integrate1: no state update)
   int substep_barrier; // 1: re-align the CTA's warps at every sub-step (instruction-cache locality experiment)
@@ -616,6 +618,15 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         X[6] = m; X[7] = m * cO.x; X[8] = m * cO.y; X[9] = m * cO.z;
         X[10] = W0 + m * (cc - cO.x * cO.x); X[11] = W1 - m * cO.x * cO.y; X[12] = W2 - m * cO.x * cO.z;
         X[13] = W3 + m * (cc - cO.y * cO.y); X[14] = W4 - m * cO.y * cO.z; X[15] = W5 + m * (cc - cO.z * cO.z);
+      }
+      if (args.ext) {   // ArticulatedSystem::setExternalForce / setExternalTorque: h -= J^T wrench, through the RNEA force terms
+        const float* e = args.ext + (size_t)env * EXT_WORDS;
+        if (bvalid && __float_as_int(e[0]) == b) {
+          const f3 Fe = mk(e[1], e[2], e[3]), Te = mk(e[4], e[5], e[6]);
+          const f3 re = (p - O) + mulR(R, mk(e[7], e[8], e[9]));
+          const f3 Me = cross(re, Fe) + Te;
+          X[0] -= Fe.x; X[1] -= Fe.y; X[2] -= Fe.z; X[3] -= Me.x; X[4] -= Me.y; X[5] -= Me.z;
+        }
       }
       // subtree sums: bodies are in DFS pre-order, so subtree(b) = lanes [b, b + size)
       float A[16];

@@ -707,3 +707,45 @@ def test_per_body_friction_matches_oracle(capi):
         bb.integrate(100)
         out[mu] = bb.get_state()[1][0, 0]
     assert abs(out[-1.0]) < 1e-4 and 0.3 < out[0.2] < 0.45
+
+
+def test_external_wrench_matches_oracle(capi):
+    """ArticulatedSystem::setExternalForce / setExternalTorque (SURVEY 8b): a per-environment world-frame wrench on a distal
+    link acts during ONE integrate() call (both fused sub-steps here) and is gone afterwards."""
+    n = 512
+    t, bt, o64, o32, gc, gv, tau = _setup(capi, "anymal_c_like.urdf", n, seed=211, base_z=0.75, vel=0.3, tau_scale=5.0)   # airborne: no contacts
+    rng = np.random.default_rng(212)
+    body = 6                                            # RF_SHANK
+    F = rng.uniform(-30, 30, (n, 3)).astype(np.float32); T = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    pb = np.array([0.02, -0.01, -0.2], np.float32)
+    bt.integrate(2)                                     # baseline without the wrench
+    g0, v0 = bt.get_state()
+    bt.set_state(gc.astype(np.float32), gv.astype(np.float32))
+    bt.set_external_wrench(body, F, T, pb)
+    bt.integrate(2)
+    g1, v1 = bt.get_state()
+    a, b = gc.copy(), gv.copy()
+    o64.step(a, b, n_steps=2, tau_ff=tau, ext=(body, F.astype(np.float64), T.astype(np.float64), pb.astype(np.float64)))
+    assert np.abs(v1 - v0).max() > 1e-2                 # the wrench did something
+    ev = np.abs(v1 - b); scale = 1.0 + np.abs(b)
+    c32, d32 = gc.copy(), gv.copy()
+    o32.step(c32, d32, n_steps=2, tau_ff=tau, ext=(body, F.astype(np.float64), T.astype(np.float64), pb.astype(np.float64)))
+    e32 = np.abs(d32 - b)
+    print(f"external wrench: gv err max {ev.max():.2e} median {np.median(ev.max(1)):.2e}; float32 oracle {e32.max():.2e}")
+    assert np.median(ev.max(1)) < max(2e-5, 3 * np.median(e32.max(1)))
+    assert np.max(ev / scale) < max(1e-3, 3 * np.max(e32 / scale))
+    # cleared after the call: the next step equals the oracle's step without a wrench
+    bt.integrate(1)
+    g2, v2 = bt.get_state()
+    o64.step(a, b, n_steps=1, tau_ff=tau)
+    assert np.median(np.abs(v2 - b).max(1)) < 5e-5
+    # torque only / force only on a sub-range of environments, device-resident rows
+    import torch
+    bt.set_state(gc.astype(np.float32), gv.astype(np.float32))
+    bt.set_external_wrench(0, torch.from_numpy(F[100:200]).cuda(), None, None, env_begin=100, env_count=100)
+    bt.integrate(1)
+    g3, v3 = bt.get_state()
+    a, b = gc.copy(), gv.copy()
+    Fz = np.zeros((n, 3)); Fz[100:200] = F[100:200]
+    o64.step(a, b, n_steps=1, tau_ff=tau, ext=(0, Fz, None, None))
+    assert np.median(np.abs(v3 - b).max(1)) < 5e-5 and np.abs(v3 - b).max() < 5e-3
