@@ -59,6 +59,8 @@ def lib():
         _lib.orc_step.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p]
         _lib.orc_solve_one.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         _lib.orc_set_point_mu.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.orc_get_flops.argtypes = [C.c_void_p, C.c_int]
+        _lib.orc_get_counts.argtypes = [C.c_void_p, C.c_int]
     return _lib
 
 
@@ -79,7 +81,7 @@ class Oracle:
         for k, a in self._keep.items():
             setattr(d, k, a.ctypes.data)
         self.precision = precision
-        self.h = lib().orc_create(C.byref(d), 0 if precision == "f64" else 1)
+        self.h = lib().orc_create(C.byref(d), {"f64": 0, "f32": 1, "count": 2}[precision])
         self.kmax = lib().orc_kmax()
         self.params = dict(DEFAULT_PARAMS)
         self.set_params(**(params or {}))
@@ -162,3 +164,17 @@ class Oracle:
         lam = np.zeros(3)
         lib().orc_solve_one(self.h, _p(G), _p(c), float(mu), _p(lam))
         return lam
+
+
+def flop_counters(reset=True):
+    """counters of the FLOP-counting build (Oracle(..., precision="count")): dict add/mul/div/sqrt/trig/cmp"""
+    c = (C.c_longlong * 6)()
+    lib().orc_get_flops(c, 1 if reset else 0)
+    return dict(zip(("add", "mul", "div", "sqrt", "trig", "cmp"), [int(x) for x in c]))
+
+
+def solver_outcome_counters(reset=True):
+    """per-contact rule outcomes summed over all step() calls: opening, stick, slip, slip found by the local fan"""
+    c = (C.c_longlong * 4)()
+    lib().orc_get_counts(c, 1 if reset else 0)
+    return dict(zip(("open", "stick", "slip", "slip_local"), [int(x) for x in c]))

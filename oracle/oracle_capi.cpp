@@ -2,6 +2,7 @@
 // Builds liboracle.so: a double and a float instance of the restated World::integrate(),
 // OpenMP over environments the way RaisimGym's VectorizedEnvironment does
 // (`#pragma omp parallel for` over envs, SURVEY.md 3.1 [RECALL]).
+#include "counting_scalar.hpp"
 #include "rbd_oracle.hpp"
 #include <omp.h>
 #include <memory>
@@ -40,9 +41,16 @@ struct Handle {
   int precision;
   std::unique_ptr<Sim<double>> d;
   std::unique_ptr<Sim<float>> f;
+  std::unique_ptr<Sim<Cnt>> c;      // precision 2: FLOP-counting build (single-threaded use)
 };
 
 long long g_counts[4] = {0, 0, 0, 0};   // per-contact rule outcomes summed over all run() calls (statistics for tools/, tests)
+// counters of the FLOP-counting build (precision 2): add, mul, div, sqrt, trig, cmp
+extern "C" void orc_get_flops(long long* out, int reset) {
+  orc::FlopCounters& c = orc::flop_counters();
+  out[0] = c.add; out[1] = c.mul; out[2] = c.div; out[3] = c.sqrt; out[4] = c.trig; out[5] = c.cmp;
+  if (reset) c = orc::FlopCounters();
+}
 extern "C" void orc_get_counts(long long* out, int reset) { for (int k = 0; k < 4; k++) { out[k] = g_counts[k]; if (reset) g_counts[k] = 0; } }
 
 template <typename T>
@@ -89,7 +97,7 @@ static void run(Sim<T>& sim, int n_envs, int n_steps, double* gc, double* gv, co
         if (dbg->h) for (int i = 0; i < nv; i++) dbg->h[(size_t)e * nv + i] = double(ws.h[i]);
         if (dbg->tau_applied) for (int i = 0; i < nv; i++) dbg->tau_applied[(size_t)e * nv + i] = double(ws.tau_applied[i]);
         if (dbg->R) for (int i = 0; i < nb; i++) for (int k = 0; k < 9; k++) dbg->R[((size_t)e * nb + i) * 9 + k] = double(ws.R[i].m[k]);
-        if (dbg->p) for (int i = 0; i < nb; i++) { dbg->p[((size_t)e * nb + i) * 3] = ws.p[i].x; dbg->p[((size_t)e * nb + i) * 3 + 1] = ws.p[i].y; dbg->p[((size_t)e * nb + i) * 3 + 2] = ws.p[i].z; }
+        if (dbg->p) for (int i = 0; i < nb; i++) { dbg->p[((size_t)e * nb + i) * 3] = double(ws.p[i].x); dbg->p[((size_t)e * nb + i) * 3 + 1] = double(ws.p[i].y); dbg->p[((size_t)e * nb + i) * 3 + 2] = double(ws.p[i].z); }
         int K = int(ws.contacts.size());
         if (dbg->ncontacts) dbg->ncontacts[e] = K;
         if (dbg->iters) dbg->iters[e] = ws.iters;
@@ -105,9 +113,9 @@ static void run(Sim<T>& sim, int n_envs, int n_steps, double* gc, double* gv, co
           if (dbg->c_body) dbg->c_body[o] = on ? ws.contacts[k].body : -1;
           if (dbg->c_pair) dbg->c_pair[o] = on ? ws.contacts[k].pair : -1;
           if (dbg->c_depth) dbg->c_depth[o] = on ? double(ws.contacts[k].depth) : 0.0;
-          if (dbg->c_pos) { dbg->c_pos[3 * o] = on ? ws.contacts[k].pos.x : 0; dbg->c_pos[3 * o + 1] = on ? ws.contacts[k].pos.y : 0; dbg->c_pos[3 * o + 2] = on ? ws.contacts[k].pos.z : 0; }
-          if (dbg->c_normal) { dbg->c_normal[3 * o] = on ? ws.contacts[k].n.x : 0; dbg->c_normal[3 * o + 1] = on ? ws.contacts[k].n.y : 0; dbg->c_normal[3 * o + 2] = on ? ws.contacts[k].n.z : 0; }
-          if (dbg->c_lambda) { dbg->c_lambda[3 * o] = on ? ws.contacts[k].lam.x : 0; dbg->c_lambda[3 * o + 1] = on ? ws.contacts[k].lam.y : 0; dbg->c_lambda[3 * o + 2] = on ? ws.contacts[k].lam.z : 0; }
+          if (dbg->c_pos) { dbg->c_pos[3 * o] = on ? double(ws.contacts[k].pos.x) : 0; dbg->c_pos[3 * o + 1] = on ? double(ws.contacts[k].pos.y) : 0; dbg->c_pos[3 * o + 2] = on ? double(ws.contacts[k].pos.z) : 0; }
+          if (dbg->c_normal) { dbg->c_normal[3 * o] = on ? double(ws.contacts[k].n.x) : 0; dbg->c_normal[3 * o + 1] = on ? double(ws.contacts[k].n.y) : 0; dbg->c_normal[3 * o + 2] = on ? double(ws.contacts[k].n.z) : 0; }
+          if (dbg->c_lambda) { dbg->c_lambda[3 * o] = on ? double(ws.contacts[k].lam.x) : 0; dbg->c_lambda[3 * o + 1] = on ? double(ws.contacts[k].lam.y) : 0; dbg->c_lambda[3 * o + 2] = on ? double(ws.contacts[k].lam.z) : 0; }
         }
       }
     }
@@ -121,7 +129,7 @@ extern "C" {
 void* orc_create(const ModelDesc* d, int precision) {
   Handle* h = new Handle;
   h->precision = precision;
-  if (precision == 0) h->d.reset(new Sim<double>(*d)); else h->f.reset(new Sim<float>(*d));
+  if (precision == 0) h->d.reset(new Sim<double>(*d)); else if (precision == 1) h->f.reset(new Sim<float>(*d)); else h->c.reset(new Sim<Cnt>(*d));
   return h;
 }
 void orc_destroy(void* hv) { delete static_cast<Handle*>(hv); }
@@ -135,26 +143,26 @@ void orc_set_params(void* hv, const double* p) {
   prm.dt = p[0]; prm.gravity[0] = p[1]; prm.gravity[1] = p[2]; prm.gravity[2] = p[3]; prm.erp = p[4];
   prm.alpha_init = p[5]; prm.alpha_min = p[6]; prm.alpha_decay = p[7]; prm.max_iter = int(p[8]); prm.threshold = p[9];
   prm.mu = p[10]; prm.restitution = p[11]; prm.rest_threshold = p[12]; prm.stall_window = int(p[13]); prm.stall_ratio = p[14]; prm.warm_start = int(p[15]); prm.slip_bisect = int(p[16]); prm.joint_limits = int(p[17]); prm.slip_local = int(p[18]);
-  if (h->d) h->d->prm = prm; else h->f->prm = prm;
+  if (h->d) h->d->prm = prm; else if (h->f) h->f->prm = prm; else h->c->prm = prm;
 }
 
 void orc_set_ground(void* hv, double z) {
   Handle* h = static_cast<Handle*>(hv);
   Terrain t; t.type = 1; t.ground_z = z;
-  if (h->d) h->d->set_terrain(t); else h->f->set_terrain(t);
+  if (h->d) h->d->set_terrain(t); else if (h->f) h->f->set_terrain(t); else h->c->set_terrain(t);
 }
 
 void orc_set_heightmap(void* hv, int xs, int ys, double x_size, double y_size, double cx, double cy, const double* heights) {
   Handle* h = static_cast<Handle*>(hv);
   Terrain t; t.type = 2; t.xs = xs; t.ys = ys; t.x_size = x_size; t.y_size = y_size; t.cx = cx; t.cy = cy;
   t.h.assign(heights, heights + (size_t)xs * ys);
-  if (h->d) h->d->set_terrain(t); else h->f->set_terrain(t);
+  if (h->d) h->d->set_terrain(t); else if (h->f) h->f->set_terrain(t); else h->c->set_terrain(t);
 }
 
 void orc_clear_terrain(void* hv) {
   Handle* h = static_cast<Handle*>(hv);
   Terrain t;
-  if (h->d) h->d->set_terrain(t); else h->f->set_terrain(t);
+  if (h->d) h->d->set_terrain(t); else if (h->f) h->f->set_terrain(t); else h->c->set_terrain(t);
 }
 
 // n_steps of World::integrate() for n_envs environments; gc [n][nq], gv [n][nv] updated in place.
@@ -163,6 +171,7 @@ int orc_step(void* hv, int n_envs, int n_steps, double* gc, double* gv, const do
              const double* vtarget, const double* kp, const double* kd, int nthreads, OrcDebug* dbg) {
   Handle* h = static_cast<Handle*>(hv);
   if (h->d) run(*h->d, n_envs, n_steps, gc, gv, tau_ff, ptarget, vtarget, kp, kd, nthreads, dbg);
+  else if (h->c) run(*h->c, n_envs, n_steps, gc, gv, tau_ff, ptarget, vtarget, kp, kd, 1, dbg);
   else run(*h->f, n_envs, n_steps, gc, gv, tau_ff, ptarget, vtarget, kp, kd, nthreads, dbg);
   return 0;
 }

@@ -576,3 +576,29 @@ def test_external_torque_on_pendulum_closed_form():
     gc, gv = np.array([[0.0]]), np.array([[0.0]])
     o.step(gc, gv)                                                            # the wrench does not persist
     assert gv[0, 0] == 0.0
+
+
+def test_flop_counting_build_matches_f64_and_reports_algorithmic_flops(anymal_tables):
+    """ALGORITHMIC FLOPs per env-step counted with an instrumented scalar (Sim<Cnt>); the counting build is
+    the float64 restatement operation for operation, so its results are bit-identical."""
+    from oracle.oracle import flop_counters
+    t = anymal_tables
+    n = 32
+    rng = np.random.default_rng(77)
+    gc = np.tile(ANYMAL_GC0, (n, 1)); gc[:, 2] = 0.58; gc[:, 7:] += rng.uniform(-0.1, 0.1, (n, 12))
+    gv = np.zeros((n, 18))
+    kp = np.r_[np.zeros(6), 300.0 * np.ones(12)]; kd = np.r_[np.zeros(6), 8.0 * np.ones(12)]
+    tgt = np.tile(ANYMAL_GC0, (n, 1))
+    o = Oracle(t, params=dict(threshold=1e-6)); oc = Oracle(t, precision="count", params=dict(threshold=1e-6))
+    for x in (o, oc):
+        x.set_ground(0.0)
+    o.step(gc, gv, n_steps=200, ptarget=tgt, vtarget=np.zeros((n, 18)), kp=kp, kd=kd)       # settle on the ground
+    a, b = gc.copy(), gv.copy()
+    flop_counters()
+    d = oc.step(a, b, n_steps=4, ptarget=tgt, vtarget=np.zeros((n, 18)), kp=kp, kd=kd, debug=True)
+    c = flop_counters()
+    o.step(gc, gv, n_steps=4, ptarget=tgt, vtarget=np.zeros((n, 18)), kp=kp, kd=kd)
+    assert np.array_equal(a, gc) and np.array_equal(b, gv)
+    flops = (c["add"] + c["mul"] + c["div"] + c["sqrt"]) / (4 * n)
+    print(f"algorithmic FLOPs per env-step (dense restatement, K mean {d['ncontacts'].mean():.2f}): {flops:.0f}  {c}")
+    assert d["ncontacts"].mean() > 3.5 and 20e3 < flops < 80e3           # SURVEY 8(d) estimated 30-60 k for ANYmal with K = 4
