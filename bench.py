@@ -235,7 +235,7 @@ def main():
         # rank's step kernel writes its own rows in place over its own PCIe link (no NVLink hop, no D2H funnel on rank 0)
         from raisimlib_b200.sharding import SharedHostRows
         shared = SharedHostRows(f"bench_{os.environ.get('MASTER_PORT', '0')}", world, rank, n, od)
-        sync_flag = torch.zeros(1, dtype=torch.float32, device="cuda")
+        e2e_step = [0]
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device="cuda")
 
     def control_step(k, host_io):
@@ -265,14 +265,14 @@ def main():
                 ev[k][1].record(stream)
                 continue
             if host_io:
-                # N > 1: same call per rank, observation rows land in the shared host array; one tiny all-reduce is the
-                # barrier after which the trainer's rank may read every row
+                # N > 1: same call per rank (it returns when this rank's rows are in host memory); shared-memory flags are
+                # the barrier after which the trainer's rank may read every row
                 kev[k][0].record(stream)
                 bt.control_step(tg_pin[(step0 + k) % RING], SUBSTEPS, shared.local)
                 kev[k][1].record(stream)
-                dist.all_reduce(sync_flag)
+                e2e_step[0] += 1
+                shared.publish_and_wait(e2e_step[0])         # host-side barrier: every rank's rows are in the shared array
                 ev[k][1].record(stream)
-                stream.synchronize()                         # the caller reads the observation before acting
                 continue
             bt.bind_pd_target(tg_dev[(step0 + k) % RING])    # resident targets read in place (zero-copy)
             kev[k][0].record(stream)
@@ -338,7 +338,7 @@ def main():
                        "standing_fraction": float(stats[3]), "parallelism": f"env-shard x{world}" + (", NCCL obs all-gather" if world > 1 else "")},
             "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": int(world * n * 19 * 4), "d2h_bytes_per_step": int(world * n * od * 4),
                     "path": "pinned host targets and observation rows read / written in place by the step kernel (zero-copy over PCIe)"
-                            + ("; rows of all ranks land in one shared page-locked array, one all-reduce as barrier" if world > 1 else "")},
+                            + ("; rows of all ranks land in one shared page-locked array, shared-memory flags as barrier" if world > 1 else "")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "rsb_step_kernel (fused FK+CRBA+RNEA+narrow-phase+contact solver+integrate)",

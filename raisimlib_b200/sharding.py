@@ -38,7 +38,8 @@ class SharedHostRows:
     Host-side consumers (a trainer process on rank 0 reading observation rows) do not need the NVLink all-gather:
     each rank's step kernel writes its own block of rows IN PLACE over its own PCIe link (the C-ABI recognises the
     page-locked buffer and binds it zero-copy), all links in parallel; one barrier later every row is visible to
-    every process.  `local` is this rank's block (a numpy view to hand to Batch.control_step), `all` the whole array.
+    every process (`publish_and_wait`, shared-memory flags).  `local` is this rank's block (a numpy view to hand to
+    Batch.control_step), `all` the whole array.
     """
 
     def __init__(self, tag, world, rank, rows_per_rank, width, register=True, barrier=None):
@@ -47,21 +48,40 @@ class SharedHostRows:
         self.path = f"/dev/shm/rsb_{tag}"
         self.rank, self.registered = rank, False
         shape = (world * rows_per_rank, width)
-        nbytes = shape[0] * shape[1] * 4
+        row_bytes = shape[0] * shape[1] * 4
+        flag_off = (row_bytes + 4095) // 4096 * 4096          # one cache line of flags per rank, behind the rows
+        nbytes = flag_off + world * 64
+        self.world = world
         barrier = barrier or (dist.barrier if (dist.is_available() and dist.is_initialized()) else (lambda: None))
         if rank == 0:
             with open(self.path, "wb") as f:
                 f.truncate(nbytes)
         barrier()
         self.all = np.memmap(self.path, dtype=np.float32, mode="r+", shape=shape)
+        self._flags = np.memmap(self.path, dtype=np.int64, mode="r+", offset=flag_off, shape=(world, 8))
         self.local = self.all[rank * rows_per_rank:(rank + 1) * rows_per_rank]
-        self._ptr, self._nbytes = self.all.ctypes.data, nbytes
+        self._ptr, self._nbytes = self.all.ctypes.data, row_bytes
         if register:
-            rc = torch.cuda.cudart().cudaHostRegister(self._ptr, nbytes, 1 | 2)      # portable | mapped
+            rc = torch.cuda.cudart().cudaHostRegister(self._ptr, row_bytes, 1 | 2)   # portable | mapped
             if int(rc) != 0:
                 raise RuntimeError(f"cudaHostRegister failed with {rc}")
             self.registered = True
         barrier()
+
+    def publish_and_wait(self, step_id, timeout_s=60.0):
+        """Host-side barrier for the rows of control step `step_id` (> 0, increasing): call after this rank's step call
+        returned (its rows are then in host memory), returns when every rank has published the same step.  Plain
+        shared-memory flags (x86 store order: rows before flag) -- no GPU work, no NCCL on the host-bound path."""
+        import time
+        self._flags[self.rank, 0] = step_id
+        f = self._flags[:, 0]
+        spins, t0 = 0, None
+        while int(f.min()) < step_id:
+            spins += 1
+            if spins % 4096 == 0:                      # a dead peer must not hang the job
+                t0 = t0 or time.monotonic()
+                if time.monotonic() - t0 > timeout_s:
+                    raise RuntimeError(f"SharedHostRows: rank(s) {[int(r) for r in (f < step_id).nonzero()[0]]} did not publish step {step_id} within {timeout_s} s")
 
     def close(self, barrier=None):
         import os
@@ -72,6 +92,7 @@ class SharedHostRows:
         barrier()
         self.local = None
         self.all = None
+        self._flags = None
         if self.rank == 0:
             try:
                 os.unlink(self.path)

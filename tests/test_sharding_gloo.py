@@ -37,7 +37,7 @@ def _worker(rank, world, port, total, q):
     from raisimlib_b200.sharding import SharedHostRows
     sh = SharedHostRows(f"test_{port}", world, rank, hi - lo, 34, register=False)
     sh.local[:] = local.numpy()
-    dist.barrier()
+    sh.publish_and_wait(1)                       # shared-memory flag barrier (no collective)
     shared_copy = np.array(sh.all)
     sh.close()
     q.put((rank, lo, hi, full.numpy().copy(), shared_copy))
