@@ -60,6 +60,35 @@ int main(int argc, char** argv) {
     }
     pPrev = p; RPrev = R; JpPrev = Jf; JrPrev = Jr;
   }
+  // setExternalForce against the facade's own M^-1 and Jacobian: from rest in zero gravity v+ = dt M^-1 J^T F
+  double worst_f = 0;
+  {
+    world.setGravity({0.0, 0.0, 0.0});
+    raisim::VecDyn rest(nv);
+    robot->setGeneralizedVelocity(rest);
+    world.integrate1();
+    raisim::MatDyn Minv = robot->getInverseMassMatrix();
+    raisim::Vec<3> pFoot; robot->getFramePosition(foot, pFoot);
+    raisim::MatDyn Jf; robot->getDenseFrameJacobian(foot, Jf);
+    const raisim::Vec<3> F{4.0, -3.0, 6.0};
+    raisim::Vec<3> pShank; robot->getBodyPosition(shank, pShank);
+    raisim::Mat<3, 3> RShank; robot->getBodyOrientation(shank, RShank);
+    raisim::Vec<3> posInBody;      // foot frame origin expressed in the shank body frame
+    for (int r = 0; r < 3; r++) posInBody[r] = RShank(0, r) * (pFoot[0] - pShank[0]) + RShank(1, r) * (pFoot[1] - pShank[1]) + RShank(2, r) * (pFoot[2] - pShank[2]);
+    robot->setExternalForce(shank, posInBody, F);
+    world.integrate();
+    raisim::VecDyn v1 = robot->getGeneralizedVelocity();
+    for (size_t i = 0; i < nv; i++) {
+      double s = 0;
+      for (size_t c = 0; c < nv; c++) { double jtF = Jf(0, c) * F[0] + Jf(1, c) * F[1] + Jf(2, c) * F[2]; s += Minv(i, c) * jtF; }
+      worst_f = std::fmax(worst_f, std::fabs(v1[i] - dt * s));
+    }
+    world.integrate();              // the wrench is gone: velocity stays (zero gravity, no contact), up to the O(dt |v|^2) bias
+    raisim::VecDyn v2 = robot->getGeneralizedVelocity();
+    for (size_t i = 0; i < nv; i++) worst_f = std::fmax(worst_f, std::fabs(v2[i] - v1[i]) * 0.1);
+  }
+  std::printf("external force vs dt M^-1 J^T F: %.3e\n", worst_f);
+  if (!(worst_f < 5e-5)) return 1;
   std::printf("frame velocity vs finite difference: %.3e m/s   angular: %.3e rad/s   orthonormality: %.2e   body-vs-frame API: %.2e\n",
               worst_v, worst_w, worst_orth, worst_j);
   // float32 poses differenced over dt = 1e-3: ~1e-7 / 1e-3 = 1e-4 rounding + O(dt |a|) truncation
