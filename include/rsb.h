@@ -187,6 +187,12 @@ typedef struct rsb_terrain_properties {
 } rsb_terrain_properties;
 int rsb_terrain_generate(const rsb_terrain_properties* p, float* heights_out /* [y_samples][x_samples] */);
 
+/* height-map files: World::addHeightMap(raisimHeightMapFileName, centerX, centerY) -- text, header "xSamples ySamples xSize
+ * ySize" then the heights, x fastest -- and World::addHeightMap(pngFileName, centerX, centerY, xSize, ySize, heightScale,
+ * heightOffset) -- 8/16-bit PNG, height = pixel * scale + offset.  heights == NULL only reports the sample counts. */
+int rsb_heightmap_read_text(const char* path, int* x_samples, int* y_samples, double* x_size, double* y_size, float* heights, int capacity);
+int rsb_heightmap_read_png(const char* path, double height_scale, double height_offset, int* x_samples, int* y_samples, float* heights, int capacity);
+
 /* ---- multi-GPU inside one process: one rsb_batch per GPU, NCCL all-gather of the observation rows ----
  *      (NCCL is bound at run time; bench.py uses torch.distributed for the same collective, one process per GPU) */
 typedef struct rsb_comm rsb_comm;

@@ -120,3 +120,43 @@ def test_terrain_generator_properties():
     assert np.allclose(st / 0.05, np.round(st / 0.05), atol=1e-4)
     off = capi.generate_terrain(seed=7, height_offset=1.5)
     assert np.allclose(off - a, 1.5, atol=1e-6)
+
+
+def test_heightmap_text_and_png_loaders(tmp_path):
+    """N3: World::addHeightMap(file ...) front ends -- host code, no GPU needed"""
+    from PIL import Image
+    rng = np.random.default_rng(9)
+    xs, ys = 37, 23
+    H = rng.uniform(-0.3, 0.4, (ys, xs)).astype(np.float32)
+    txt = tmp_path / "hm.txt"
+    with open(txt, "w") as f:
+        f.write(f"{xs} {ys} 7.4 4.6\n")
+        for row in H:
+            f.write(" ".join(f"{v:.9g}" for v in row) + "\n")
+    got, sx, sy = capi.read_heightmap_text(str(txt))
+    assert got.shape == (ys, xs) and (sx, sy) == (7.4, 4.6) and np.array_equal(got, H)
+    # 16-bit grey, 8-bit grey, RGB and RGBA (first channel), with a smooth image so that PNG's adaptive filters are all used
+    yy, xx = np.mgrid[0:ys, 0:xs]
+    smooth = (np.sin(xx / 5.0) * np.cos(yy / 3.0) * 0.5 + 0.5)
+    img16 = (smooth * 60000 + rng.integers(0, 300, (ys, xs))).astype(np.uint16)
+    p16 = tmp_path / "hm16.png"; Image.fromarray(img16).save(p16)
+    got = capi.read_heightmap_png(str(p16), 1e-4, -2.0)
+    assert got.shape == (ys, xs) and np.allclose(got, img16.astype(np.float64) * 1e-4 - 2.0, atol=1e-6)
+    img8 = (smooth * 250).astype(np.uint8)
+    p8 = tmp_path / "hm8.png"; Image.fromarray(img8).save(p8)
+    assert np.array_equal(capi.read_heightmap_png(str(p8)), img8.astype(np.float32))
+    rgb = np.stack([img8, 255 - img8, img8 // 2], -1)
+    prgb = tmp_path / "hmrgb.png"; Image.fromarray(rgb).save(prgb)
+    assert np.array_equal(capi.read_heightmap_png(str(prgb), 0.5, 1.0), img8.astype(np.float32) * 0.5 + 1.0)
+    rgba = np.concatenate([rgb, np.full((ys, xs, 1), 200, np.uint8)], -1)
+    prgba = tmp_path / "hmrgba.png"; Image.fromarray(rgba).save(prgba)
+    assert np.array_equal(capi.read_heightmap_png(str(prgba)), img8.astype(np.float32))
+    # errors are reported, not thrown
+    bad = tmp_path / "bad.png"; bad.write_bytes(b"not a png at all, just text that is long enough to pass the size check....")
+    with pytest.raises(RuntimeError, match="not a PNG"):
+        capi.read_heightmap_png(str(bad))
+    short = tmp_path / "short.txt"; short.write_text("4 4 1.0 1.0\n0 0 0\n")
+    with pytest.raises(RuntimeError, match="heights found"):
+        capi.read_heightmap_text(str(short))
+    with pytest.raises(RuntimeError, match="cannot open"):
+        capi.read_heightmap_text(str(tmp_path / "missing.txt"))
