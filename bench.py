@@ -154,6 +154,11 @@ def cpu_baseline(sample_envs, max_steps, budget_s=12.0):
             "sample": f"{sample_envs} envs x {done} sub-steps of the same workload (float64 oracle, bisection slip search, OpenMP over envs, after the same settling phase as the GPU arm)"}
 
 
+def workload_string(n):
+    return (f"{n} ANYmal-C-like envs per GPU on 513x513 rough height field (+-0.10 m), PD stance kp={KP} kd={KD}, dt=0.0025, "
+            f"{SUBSTEPS} sub-steps fused per step")
+
+
 def run_reference(args):
     """--impl reference: the CPU path on this box's host cores; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -178,7 +183,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "env-steps/s", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{n} ANYmal-C-like envs on 513x513 rough height field, PD stance, {SUBSTEPS} sub-steps per step (CPU oracle port, {cores} threads)"},
+            "config": {"workload": workload_string(n), "envs_per_gpu": n, "substeps_per_step": SUBSTEPS,
+                       "arm": f"CPU oracle port (a restatement, not RaiSim's binary), float64, OpenMP over envs, {cores} threads; each step = the full per-GPU workload"},
             "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": cores, "kind": "port",
                              "sample": f"{n} envs x {SUBSTEPS * args.steps} sub-steps (the full per-GPU workload), float64, OpenMP over envs"},
             "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -332,7 +338,7 @@ def main():
             "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{n} ANYmal-C-like envs per GPU on 513x513 rough height field (+-0.10 m), PD stance kp={KP} kd={KD}, dt=0.0025, {SUBSTEPS} sub-steps fused per step",
+            "config": {"workload": workload_string(n),
                        "envs_per_gpu": n, "substeps_per_step": SUBSTEPS, "l2": "flushed between timed iterations (256 MiB write)",
                        "mean_contacts_per_env": kbar, "mean_solver_iters": float(stats[1]), "max_solver_iters": float(stats[2]),
                        "standing_fraction": float(stats[3]), "parallelism": f"env-shard x{world}" + (", NCCL obs all-gather" if world > 1 else "")},
