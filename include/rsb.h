@@ -121,6 +121,10 @@ int rsb_batch_set_ground(rsb_batch* b, float z);                                
 int rsb_batch_set_heightmap(rsb_batch* b, int x_samples, int y_samples, float x_size, float y_size,
                             float center_x, float center_y, const float* heights_host); /* World::addHeightMap */
 int rsb_batch_clear_terrain(rsb_batch* b);
+/* terrain atlas: upstream gives every environment its own World, hence possibly its own HeightMap; here `count` same-sized
+ * maps ([count][y_samples][x_samples], host) share one batch and map_of_env[num_envs] (host) picks one per environment */
+int rsb_batch_set_heightmaps(rsb_batch* b, int count, int x_samples, int y_samples, float x_size, float y_size,
+                             float center_x, float center_y, const float* heights_host, const int32_t* map_of_env);
 int rsb_batch_set_params(rsb_batch* b, const rsb_params* p);
 int rsb_batch_get_params(const rsb_batch* b, rsb_params* p);
 int rsb_params_default(rsb_params* p);

@@ -105,6 +105,15 @@ class Oracle:
         assert hh.size == xs * ys
         lib().orc_set_heightmap(self.h, xs, ys, x_size, y_size, cx, cy, _p(hh))
 
+    def set_heightmaps(self, x_size, y_size, cx, cy, heights, env_map):
+        """terrain atlas: heights [count, ys, xs], env_map [n] -> every environment collides with its own map"""
+        hh = np.ascontiguousarray(heights, dtype=np.float64)
+        count, ys, xs = hh.shape
+        em = np.ascontiguousarray(env_map, dtype=np.int32)
+        assert em.min() >= 0 and em.max() < count
+        lib().orc_set_heightmaps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int]
+        lib().orc_set_heightmaps(self.h, count, xs, ys, x_size, y_size, cx, cy, _p(hh), em.ctypes.data, len(em))
+
     def clear_terrain(self):
         lib().orc_clear_terrain(self.h)
 

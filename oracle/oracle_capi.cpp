@@ -76,6 +76,7 @@ static void run(Sim<T>& sim, int n_envs, int n_steps, double* gc, double* gv, co
         ws.prev_pt[k] = (dbg && dbg->warm_pt) ? dbg->warm_pt[(size_t)e * KMAX + k] : -1;
         if (dbg && dbg->warm_imp) ws.prev_imp[k] = {T(dbg->warm_imp[((size_t)e * KMAX + k) * 3]), T(dbg->warm_imp[((size_t)e * KMAX + k) * 3 + 1]), T(dbg->warm_imp[((size_t)e * KMAX + k) * 3 + 2])};
       }
+      ws.hm_offset = (sim.ter.type == 2 && !sim.ter.env_map.empty()) ? sim.ter.env_map[(size_t)e % sim.ter.env_map.size()] * sim.ter.xs * sim.ter.ys : 0;
       ws.ext_body = -1;
       if (dbg && dbg->ext_body >= 0) {
         ws.ext_body = dbg->ext_body;
@@ -156,6 +157,16 @@ void orc_set_heightmap(void* hv, int xs, int ys, double x_size, double y_size, d
   Handle* h = static_cast<Handle*>(hv);
   Terrain t; t.type = 2; t.xs = xs; t.ys = ys; t.x_size = x_size; t.y_size = y_size; t.cx = cx; t.cy = cy;
   t.h.assign(heights, heights + (size_t)xs * ys);
+  if (h->d) h->d->set_terrain(t); else if (h->f) h->f->set_terrain(t); else h->c->set_terrain(t);
+}
+
+// terrain atlas: `count` same-sized height maps back to back, env_map[n_envs] picks one per environment
+void orc_set_heightmaps(void* hv, int count, int xs, int ys, double x_size, double y_size, double cx, double cy, const double* heights,
+                        const int* env_map, int n_envs) {
+  Handle* h = static_cast<Handle*>(hv);
+  Terrain t; t.type = 2; t.xs = xs; t.ys = ys; t.x_size = x_size; t.y_size = y_size; t.cx = cx; t.cy = cy; t.count = count;
+  t.h.assign(heights, heights + (size_t)count * xs * ys);
+  t.env_map.assign(env_map, env_map + n_envs);
   if (h->d) h->d->set_terrain(t); else if (h->f) h->f->set_terrain(t); else h->c->set_terrain(t);
 }
 

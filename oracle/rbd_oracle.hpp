@@ -103,7 +103,9 @@ struct Terrain {
   double ground_z = 0.0;
   int xs = 0, ys = 0;
   double x_size = 0, y_size = 0, cx = 0, cy = 0;
-  std::vector<double> h;        // h[iy * xs + ix]
+  std::vector<double> h;        // h[iy * xs + ix]; `count` maps back to back for a terrain atlas
+  int count = 1;                // terrain atlas: number of same-sized height maps
+  std::vector<int> env_map;     // terrain atlas: map index of every environment (empty = everyone on map 0)
 };
 
 template <typename T> struct SlipDir { bool valid = false; T cs = 1, sn = 0; };   // last slip direction of a contact (per step)
@@ -125,6 +127,7 @@ template <typename T> struct Workspace {
   int nb, nv;
   // external wrench of this step (ArticulatedSystem::setExternalForce / setExternalTorque): body < 0 = none
   int ext_body = -1; V3<T> ext_f{0, 0, 0}, ext_t{0, 0, 0}, ext_pos{0, 0, 0};
+  int hm_offset = 0;              // terrain atlas: offset of this environment's height map inside Sim::hmap
   long long counts[4] = {0, 0, 0, 0};   // per-contact rule outcomes: opening, stick, slip, slip found by the local fan (statistics only)
   std::vector<M3<T>> R;
   std::vector<V3<T>> p, a, w, v, wd, vd, F, N;
@@ -344,7 +347,7 @@ template <typename T> class Sim {
   }
 
   // ---- a6: narrow phase (Ground / HeightMap vs collision bodies expanded to candidate points) ----
-  bool terrain_query(V3<T> P, T& dist, V3<T>& n, int& pair) const {
+  bool terrain_query(V3<T> P, T& dist, V3<T>& n, int& pair, int hm_offset = 0) const {
     if (ter.type == 1) { dist = P.z - T(ter.ground_z); n = {0, 0, 1}; pair = 0; return true; }
     if (ter.type != 2) return false;
     T dx = T(ter.x_size) / T(ter.xs - 1), dy = T(ter.y_size) / T(ter.ys - 1);
@@ -353,7 +356,7 @@ template <typename T> class Sim {
     if (!(gx >= T(0)) || !(gy >= T(0)) || !(gx < T(ter.xs - 1)) || !(gy < T(ter.ys - 1))) return false;
     int ix = int(gx), iy = int(gy);
     T fx = gx - T(ix), fy = gy - T(iy);
-    const T* H = hmap.data();
+    const T* H = hmap.data() + hm_offset;
     T h00 = H[iy * ter.xs + ix], h10 = H[iy * ter.xs + ix + 1], h01 = H[(iy + 1) * ter.xs + ix], h11 = H[(iy + 1) * ter.xs + ix + 1];
     T sx, sy; int tri;
     if (fx >= fy) { sx = (h10 - h00); sy = (h11 - h10); tri = 0; }
@@ -376,7 +379,7 @@ template <typename T> class Sim {
       if (b == 0 && !floating) continue;               // a body welded to the world cannot collide
       V3<T> P = ws.p[b] + ws.R[b] * pt_pos[k];
       T dist; V3<T> n; int pair;
-      if (!terrain_query(P, dist, n, pair)) continue;
+      if (!terrain_query(P, dist, n, pair, ws.hm_offset)) continue;
       T depth = pt_rad[k] - dist;
       if (!(depth > T(0))) continue;
       Contact<T> c;

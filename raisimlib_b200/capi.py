@@ -93,7 +93,7 @@ EXPORTED = [
     "rsb_model_create_from_urdf", "rsb_model_destroy", "rsb_model_dims", "rsb_model_get_tables", "rsb_model_body_index",
     "rsb_model_body_name", "rsb_model_joint_name", "rsb_model_frame_index", "rsb_model_frame",
     "rsb_batch_create", "rsb_batch_destroy", "rsb_batch_set_stream", "rsb_batch_sync", "rsb_batch_num_envs",
-    "rsb_batch_set_ground", "rsb_batch_set_heightmap", "rsb_batch_clear_terrain", "rsb_batch_set_params", "rsb_batch_get_params",
+    "rsb_batch_set_ground", "rsb_batch_set_heightmap", "rsb_batch_set_heightmaps", "rsb_batch_clear_terrain", "rsb_batch_set_params", "rsb_batch_get_params",
     "rsb_batch_set_collision_friction",
     "rsb_batch_set_state", "rsb_batch_get_state", "rsb_batch_set_pd_gains", "rsb_batch_set_pd_target",
     "rsb_batch_set_generalized_force", "rsb_batch_set_external_wrench", "rsb_batch_set_control_mode", "rsb_batch_get_generalized_force", "rsb_batch_bind_pd_target",
@@ -266,6 +266,16 @@ class Batch:
         hh = np.ascontiguousarray(heights, dtype=np.float32).reshape(-1)
         assert hh.size == xs * ys
         _ck(lib().rsb_batch_set_heightmap(self.h, xs, ys, x_size, y_size, cx, cy, hh.ctypes.data_as(C.c_void_p)))
+
+    def set_heightmaps(self, x_size, y_size, cx, cy, heights, map_of_env):
+        """terrain atlas: heights [count, ys, xs] float32, map_of_env [n] int32 -> one height map per environment"""
+        h = np.ascontiguousarray(heights, np.float32)
+        count, ys, xs = h.shape
+        m = np.ascontiguousarray(map_of_env, np.int32)
+        assert m.shape == (self.n,)
+        L = lib()
+        L.rsb_batch_set_heightmaps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        _ck(L.rsb_batch_set_heightmaps(self.h, count, xs, ys, x_size, y_size, cx, cy, h.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p)))
 
     def clear_terrain(self):
         _ck(lib().rsb_batch_clear_terrain(self.h))

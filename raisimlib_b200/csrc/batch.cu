@@ -42,6 +42,7 @@ struct rsb_batch {
   int vt_bound_stride = 0;
   bool bound_once = false;           // zero-copy control step: the kernel copies the rows it read into pt / vt, then the binding ends
   unsigned* prof = nullptr;          // rsb_internal_set_profile
+  int* hmap_index = nullptr;         // terrain atlas: map index per environment
   float* ext = nullptr;              // [N][EXT_WORDS] external wrench rows; ext_active: rows hold a wrench for the next launch
   bool ext_active = false;
   // device buffers
@@ -434,7 +435,7 @@ void rsb_batch_destroy(rsb_batch* b) {
   if (b->stream) cudaStreamSynchronize(b->stream);
   for (void* p : {(void*)b->diverged, (void*)b->tau_applied, (void*)b->gc, (void*)b->gv, (void*)b->tau, (void*)b->pt, (void*)b->vt, (void*)b->ncontacts, (void*)b->contact_pt, (void*)b->iters,
                   (void*)b->contacts, (void*)b->dbg_M, (void*)b->dbg_h, (void*)b->dbg_R, (void*)b->dbg_p, (void*)b->hmap, (void*)b->staging, (void*)b->obs_staging, (void*)b->blob, (void*)b->gym_const, (void*)b->gym_action,
-                  (void*)b->gym_obs, (void*)b->gym_reward, (void*)b->gym_done, (void*)b->ext})
+                  (void*)b->gym_obs, (void*)b->gym_reward, (void*)b->gym_done, (void*)b->ext, (void*)b->hmap_index})
     if (p) cudaFree(p);
   if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
   delete b;
@@ -477,6 +478,31 @@ int rsb_batch_set_heightmap(rsb_batch* b, int xs, int ys, float x_size, float y_
   t.x0 = cx - 0.5f * x_size; t.y0 = cy - 0.5f * y_size;
   t.xmax = (float)(xs - 1); t.ymax = (float)(ys - 1);
   t.h = b->hmap;
+  b->ter = t;
+  return RSB_OK;
+}
+// terrain atlas (SURVEY 8f N3 "per-env distinct terrains"): `count` same-sized height maps back to back and one map
+// index per environment; every environment collides with its own map, everything else is as rsb_batch_set_heightmap
+int rsb_batch_set_heightmaps(rsb_batch* b, int count, int xs, int ys, float x_size, float y_size, float cx, float cy, const float* h,
+                             const int32_t* map_of_env) {
+  if (!b || !h || !map_of_env || count < 1 || xs < 2 || ys < 2 || !(x_size > 0) || !(y_size > 0)) return fail(RSB_ERR_INVALID, "bad height-map atlas");
+  if ((size_t)count * xs * ys > ((size_t)1 << 30)) return fail(RSB_ERR_INVALID, "height-map atlas too large");
+  for (int e = 0; e < b->N; e++) if (map_of_env[e] < 0 || map_of_env[e] >= count) return fail(RSB_ERR_INVALID, "height-map index out of range");
+  CK(cudaSetDevice(b->device));
+  CK(cudaStreamSynchronize(b->stream));
+  if (b->hmap) { cudaFree(b->hmap); b->hmap = nullptr; }
+  if (b->hmap_index) { cudaFree(b->hmap_index); b->hmap_index = nullptr; }
+  const size_t words = (size_t)count * xs * ys;
+  CK(cudaMalloc((void**)&b->hmap, words * 4));
+  CK(cudaMemcpy(b->hmap, h, words * 4, cudaMemcpyHostToDevice));
+  CK(cudaMalloc((void**)&b->hmap_index, (size_t)b->N * 4));
+  CK(cudaMemcpy(b->hmap_index, map_of_env, (size_t)b->N * 4, cudaMemcpyHostToDevice));
+  TerrainDesc t{};
+  t.type = 2; t.xs = xs; t.ys = ys;
+  t.dx = x_size / (float)(xs - 1); t.dy = y_size / (float)(ys - 1);
+  t.x0 = cx - 0.5f * x_size; t.y0 = cy - 0.5f * y_size;
+  t.xmax = (float)(xs - 1); t.ymax = (float)(ys - 1);
+  t.h = b->hmap; t.env_map = b->hmap_index; t.map_words = xs * ys;
   b->ter = t;
   return RSB_OK;
 }

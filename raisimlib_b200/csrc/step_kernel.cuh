@@ -146,6 +146,8 @@ struct TerrainDesc {
   int xs, ys;
   float x0, y0, dx, dy, xmax, ymax;   // grid origin, pitch, index bounds (xs-1, ys-1 as float)
   const float* h;
+  const int* env_map;  // terrain atlas: height-map index of every environment (null: one shared map)
+  int map_words;       // xs * ys
 };
 
 struct StepArgs {
@@ -362,14 +364,14 @@ __device__ __forceinline__ f3 solve_contact(const float* Gs, const float* Gi, f3
 }
 
 // ------------------------------------------------------------------ terrain --------------------
-__device__ __forceinline__ bool terrain_query(const TerrainDesc& t, f3 P, float& dist, f3& n, int& pair) {
+__device__ __forceinline__ bool terrain_query(const TerrainDesc& t, int hm_offset, f3 P, float& dist, f3& n, int& pair) {
   if (t.type == 1) { dist = P.z - t.ground_z; n = mk(0.f, 0.f, 1.f); pair = 0; return true; }
   if (t.type != 2) return false;
   float gx = (P.x - t.x0) / t.dx, gy = (P.y - t.y0) / t.dy;
   if (!(gx >= 0.f) || !(gy >= 0.f) || !(gx < t.xmax) || !(gy < t.ymax)) return false;
   int ix = (int)gx, iy = (int)gy;
   float fx = gx - (float)ix, fy = gy - (float)iy;
-  const float* H = t.h + iy * t.xs + ix;
+  const float* H = t.h + hm_offset + iy * t.xs + ix;
   float h00 = __ldg(H), h10 = __ldg(H + 1), h01 = __ldg(H + t.xs), h11 = __ldg(H + t.xs + 1);
   float sx, sy; int tri;
   if (fx >= fy) { sx = h10 - h00; sy = h11 - h10; tri = 0; }
@@ -709,6 +711,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       // =========================== stage B: narrow phase ========================================
       float c_depth[SLOTS]; f3 c_pos[SLOTS], c_n[SLOTS]; int c_pair[SLOTS], c_body[SLOTS];
       bool c_hit[SLOTS];
+      const int hm_offset = args.ter.env_map ? __ldg(args.ter.env_map + env) * args.ter.map_words : 0;   // terrain atlas
 #pragma unroll
       for (int s = 0; s < SLOTS; s++) {
         int k = lane + 32 * s;
@@ -722,7 +725,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
           for (int q = 0; q < 9; q++) Rb[q] = s_pose[(PF_R + q) * nbp + pb];
           f3 P = mk(s_pose[(PF_P + 0) * nbp + pb], s_pose[(PF_P + 1) * nbp + pb], s_pose[(PF_P + 2) * nbp + pb]) + mulR(Rb, pl);
           float dist; f3 n; int pair;
-          if (bdof[pb] >= 0 && terrain_query(args.ter, P, dist, n, pair)) {   // bodies welded to the world cannot collide
+          if (bdof[pb] >= 0 && terrain_query(args.ter, hm_offset, P, dist, n, pair)) {   // bodies welded to the world cannot collide
             float depth = rad - dist;
             if (depth > 0.f) { c_hit[s] = true; c_depth[s] = depth; c_pair[s] = pair; c_body[s] = pb; c_n[s] = n; c_pos[s] = P - rad * n; }
           }

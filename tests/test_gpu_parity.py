@@ -749,3 +749,47 @@ def test_external_wrench_matches_oracle(capi):
     Fz = np.zeros((n, 3)); Fz[100:200] = F[100:200]
     o64.step(a, b, n_steps=1, tau_ff=tau, ext=(0, Fz, None, None))
     assert np.median(np.abs(v3 - b).max(1)) < 5e-5 and np.abs(v3 - b).max() < 5e-3
+
+
+def test_terrain_atlas_matches_oracle(capi):
+    """N3 per-environment terrains: three height maps in one batch, environments assigned round robin; contact indices
+    bit-exact vs the float32 oracle, one step vs the float64 oracle; a single-map atlas equals rsb_batch_set_heightmap."""
+    n = 384
+    t, bt, o64, o32, gc, gv, tau = _setup(capi, "anymal_c_like.urdf", n, seed=231, terrain="none", base_z=0.42)
+    rng = np.random.default_rng(232)
+    xs, ys = 65, 49
+    H = (0.1 * rng.uniform(-1, 1, (3, ys, xs))).astype(np.float32)
+    H[1] += 0.05; H[2] -= 0.04
+    env_map = (np.arange(n) % 3).astype(np.int32)
+    bt.set_heightmaps(12.8, 9.6, 0.1, -0.2, H, env_map)
+    for o in (o64, o32):
+        o.set_heightmaps(12.8, 9.6, 0.1, -0.2, H.astype(np.float64), env_map)
+    bt.integrate(1)
+    g1, v1 = bt.get_state()
+    pts = bt.contact_points(); ct, cnt = bt.contacts()
+    a, b = gc.copy(), gv.copy()
+    d32 = o32.step(a, b, tau_ff=tau, debug=True)
+    shallow = ((np.abs(d32["c_depth"]) < MARGIN) & (d32["c_pt"] >= 0)).any(1)
+    assert cnt.sum() > n                                      # contacts exist
+    assert ((pts != d32["c_pt"]).any(1) & ~shallow).sum() == 0
+    a, b = gc.copy(), gv.copy()
+    d = o64.step(a, b, tau_ff=tau, debug=True)
+    it = bt.solver_iterations()
+    conv = (pts == d["c_pt"]).all(1) & (it < 150) & (d["iters"] < 150)
+    assert conv.mean() > 0.9
+    assert np.median(np.abs(v1 - b)[conv].max(1)) < 5e-5
+    # the maps really differ: the same state on a different map gives a different contact set somewhere
+    bt.set_state(gc.astype(np.float32), gv.astype(np.float32))
+    bt.set_heightmaps(12.8, 9.6, 0.1, -0.2, H, ((np.arange(n) + 1) % 3).astype(np.int32))
+    bt.integrate1()
+    assert (bt.contact_points() != pts).any()
+    # atlas of one map == the plain height-map call
+    bt.set_state(gc.astype(np.float32), gv.astype(np.float32))
+    bt.set_heightmaps(12.8, 9.6, 0.1, -0.2, H[:1], np.zeros(n, np.int32))
+    bt.integrate(2)
+    ga, va = bt.get_state()
+    bt.set_state(gc.astype(np.float32), gv.astype(np.float32))
+    bt.set_heightmap(xs, ys, 12.8, 9.6, 0.1, -0.2, H[0])
+    bt.integrate(2)
+    gb, vb = bt.get_state()
+    assert np.array_equal(ga, gb) and np.array_equal(va, vb)

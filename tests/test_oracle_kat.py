@@ -602,3 +602,28 @@ def test_flop_counting_build_matches_f64_and_reports_algorithmic_flops(anymal_ta
     flops = (c["add"] + c["mul"] + c["div"] + c["sqrt"]) / (4 * n)
     print(f"algorithmic FLOPs per env-step (dense restatement, K mean {d['ncontacts'].mean():.2f}): {flops:.0f}  {c}")
     assert d["ncontacts"].mean() > 3.5 and 20e3 < flops < 80e3           # SURVEY 8(d) estimated 30-60 k for ANYmal with K = 4
+
+
+def test_terrain_atlas_gives_every_environment_its_own_map():
+    """N3: per-environment height maps.  Flat maps at different heights: a resting sphere ends up on ITS map."""
+    t = load_tables(SPHERE_URDF)
+    o = Oracle(t, params=dict(dt=0.002))
+    n, xs, ys = 6, 9, 7
+    levels = np.array([0.0, 0.25, -0.1])
+    H = np.tile(levels[:, None, None], (1, ys, xs))
+    env_map = np.array([0, 1, 2, 2, 1, 0], np.int32)
+    o.set_heightmaps(4.0, 3.0, 0.0, 0.0, H, env_map)
+    gc = np.zeros((n, 7)); gc[:, 3] = 1.0; gc[:, 2] = levels[env_map] + 0.1 + 0.05      # sphere radius 0.1: 5 cm above its own map
+    gv = np.zeros((n, 6))
+    o.step(gc, gv, n_steps=400)
+    assert np.allclose(gc[:, 2], levels[env_map] + 0.1, atol=2e-3)
+    # identical maps in the atlas == the single-map call
+    rng = np.random.default_rng(2)
+    Hr = 0.05 * rng.uniform(-1, 1, (ys, xs))
+    a, b = np.zeros((n, 7)), np.zeros((n, 6)); a[:, 3] = 1.0; a[:, 2] = 0.12; a[:, 0] = np.linspace(-1, 1, n)
+    c, d = a.copy(), b.copy()
+    o.set_heightmaps(4.0, 3.0, 0.0, 0.0, np.stack([Hr, Hr]), np.array([0, 1, 0, 1, 1, 0], np.int32))
+    o.step(a, b, n_steps=50)
+    o.set_heightmap(xs, ys, 4.0, 3.0, 0.0, 0.0, Hr)
+    o.step(c, d, n_steps=50)
+    assert np.array_equal(a, c) and np.array_equal(b, d)
