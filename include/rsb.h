@@ -101,6 +101,9 @@ int rsb_version(void);
 /* ---- model: World::addArticulatedSystem(urdf) parsing half ---------------------- */
 int rsb_model_create_from_urdf(const char* path_or_xml, rsb_model** out);
 void rsb_model_destroy(rsb_model* m);
+/* binary cache of the compiled model tables: skips XML parsing for fleets of workers; same-architecture file */
+int rsb_model_save(const rsb_model* m, const char* path);
+int rsb_model_load(const char* path, rsb_model** out);
 int rsb_model_dims(const rsb_model* m, int* nq, int* nv, int* nb, int* ncoll, int* npts);
 int rsb_model_get_tables(const rsb_model* m, rsb_model_tables* out);
 int rsb_model_body_index(const rsb_model* m, const char* name);    /* ArticulatedSystem::getBodyIdx   */

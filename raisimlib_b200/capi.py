@@ -90,7 +90,7 @@ class DeviceView(C.Structure):
 
 EXPORTED = [
     "rsb_last_error", "rsb_version", "rsb_params_default",
-    "rsb_model_create_from_urdf", "rsb_model_destroy", "rsb_model_dims", "rsb_model_get_tables", "rsb_model_body_index",
+    "rsb_model_create_from_urdf", "rsb_model_destroy", "rsb_model_save", "rsb_model_load", "rsb_model_dims", "rsb_model_get_tables", "rsb_model_body_index",
     "rsb_model_body_name", "rsb_model_joint_name", "rsb_model_frame_index", "rsb_model_frame",
     "rsb_batch_create", "rsb_batch_destroy", "rsb_batch_set_stream", "rsb_batch_sync", "rsb_batch_num_envs",
     "rsb_batch_set_ground", "rsb_batch_set_heightmap", "rsb_batch_set_heightmaps", "rsb_batch_clear_terrain", "rsb_batch_set_params", "rsb_batch_get_params",
@@ -198,13 +198,22 @@ def _ptr(a):
 
 
 class Model:
-    def __init__(self, path_or_xml):
+    def __init__(self, path_or_xml, cache=False):
+        """URDF path / XML text, or (cache=True) a binary model cache written by Model.save()"""
         h = C.c_void_p()
-        _ck(lib().rsb_model_create_from_urdf(path_or_xml.encode(), C.byref(h)))
+        if cache:
+            lib().rsb_model_load.argtypes = [C.c_char_p, C.c_void_p]
+            _ck(lib().rsb_model_load(path_or_xml.encode(), C.byref(h)))
+        else:
+            _ck(lib().rsb_model_create_from_urdf(path_or_xml.encode(), C.byref(h)))
         self.h = h
         d = [C.c_int() for _ in range(5)]
         _ck(lib().rsb_model_dims(h, *[C.byref(x) for x in d]))
         self.nq, self.nv, self.nb, self.ncoll, self.npts = [x.value for x in d]
+
+    def save(self, path):
+        lib().rsb_model_save.argtypes = [C.c_void_p, C.c_char_p]
+        _ck(lib().rsb_model_save(self.h, path.encode()))
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -341,6 +341,21 @@ int rsb_model_create_from_urdf(const char* path_or_xml, rsb_model** out) {
     return RSB_OK;
   } catch (const std::exception& e) { return fail(RSB_ERR_PARSE, e.what()); }
 }
+int rsb_model_save(const rsb_model* m, const char* path) {
+  if (!m || !path) return fail(RSB_ERR_INVALID, "null argument");
+  try { save_model(m->md, path); return RSB_OK; } catch (const std::exception& e) { return fail(RSB_ERR_PARSE, e.what()); }
+}
+int rsb_model_load(const char* path, rsb_model** out) {
+  if (!path || !out) return fail(RSB_ERR_INVALID, "null argument");
+  try {
+    rsb_model* m = new rsb_model;
+    m->md = load_model(path);
+    if (m->md.nb > 32) { delete m; return fail(RSB_ERR_UNSUPPORTED, "more than 32 movable bodies (one lane per body)"); }
+    if (m->md.npts() > 32 * MAX_PT_SLOTS) { delete m; return fail(RSB_ERR_UNSUPPORTED, "more than 64 candidate contact points"); }
+    *out = m;
+    return RSB_OK;
+  } catch (const std::exception& e) { return fail(RSB_ERR_PARSE, e.what()); }
+}
 void rsb_model_destroy(rsb_model* m) { delete m; }
 int rsb_model_dims(const rsb_model* m, int* nq, int* nv, int* nb, int* ncoll, int* npts) {
   if (!m) return fail(RSB_ERR_INVALID, "null model");

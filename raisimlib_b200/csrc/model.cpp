@@ -339,4 +339,71 @@ Model load_urdf(const std::string& path_or_xml) {
   return md;
 }
 
+// ---- binary model cache: the compiled tables of a description, so that large fleets of workers need not
+//      re-parse XML.  Layout: magic "RSBM", version, then every field of Model in declaration order; vectors and strings
+//      carry a 64-bit length.  Little-endian, same-architecture cache (not an interchange format).
+namespace {
+constexpr uint32_t kCacheMagic = 0x4d425352u, kCacheVersion = 2u;
+struct Writer {
+  std::ofstream f;
+  template <class T> void pod(const T& v) { f.write(reinterpret_cast<const char*>(&v), sizeof(T)); }
+  template <class T> void vec(const std::vector<T>& v) { pod<uint64_t>(v.size()); if (!v.empty()) f.write(reinterpret_cast<const char*>(v.data()), sizeof(T) * v.size()); }
+  void str(const std::string& s) { pod<uint64_t>(s.size()); f.write(s.data(), (std::streamsize)s.size()); }
+  void strs(const std::vector<std::string>& v) { pod<uint64_t>(v.size()); for (const auto& s : v) str(s); }
+};
+struct Reader {
+  std::ifstream f;
+  template <class T> void pod(T& v) { f.read(reinterpret_cast<char*>(&v), sizeof(T)); if (!f) throw std::runtime_error("model cache: truncated file"); }
+  uint64_t len() { uint64_t n; pod(n); if (n > (1u << 24)) throw std::runtime_error("model cache: corrupt length"); return n; }
+  template <class T> void vec(std::vector<T>& v) { v.resize(len()); if (!v.empty()) { f.read(reinterpret_cast<char*>(v.data()), sizeof(T) * v.size()); if (!f) throw std::runtime_error("model cache: truncated file"); } }
+  void str(std::string& s) { s.resize(len()); if (!s.empty()) { f.read(&s[0], (std::streamsize)s.size()); if (!f) throw std::runtime_error("model cache: truncated file"); } }
+  void strs(std::vector<std::string>& v) { v.resize(len()); for (auto& s : v) str(s); }
+};
+template <class IO, class M> void model_fields(IO& io, M& md) {
+  io.pod(md.nb); io.pod(md.nq); io.pod(md.nv); io.pod(md.floating); io.pod(md.maxdepth); io.pod(md.skipped_collisions);
+  io.vec(md.parent); io.vec(md.jtype); io.vec(md.qidx); io.vec(md.vidx); io.vec(md.depth); io.vec(md.subtree);
+  io.vec(md.jpos); io.vec(md.jrot); io.vec(md.axis); io.vec(md.mass); io.vec(md.com); io.vec(md.inertia); io.vec(md.jlimit);
+  io.strs(md.body_names); io.strs(md.joint_names);
+  io.vec(md.cbody); io.vec(md.ctype); io.vec(md.csize); io.vec(md.cpos); io.vec(md.crot); io.strs(md.coll_names);
+  io.vec(md.pt_body); io.vec(md.pt_coll); io.vec(md.pt_feat); io.vec(md.pt_pos); io.vec(md.pt_rad);
+}
+}  // namespace
+
+void save_model(const Model& md, const std::string& path) {
+  Writer w; w.f.open(path, std::ios::binary | std::ios::trunc);
+  if (!w.f) throw std::runtime_error("model cache: cannot write '" + path + "'");
+  w.pod(kCacheMagic); w.pod(kCacheVersion);
+  model_fields(w, const_cast<Model&>(md));
+  w.pod<uint64_t>(md.frames.size());
+  for (const Frame& fr : md.frames) { w.str(fr.name); w.str(fr.joint); w.pod(fr.body); w.pod(fr.pos); w.pod(fr.rot); }
+  w.f.flush();
+  if (!w.f) throw std::runtime_error("model cache: write to '" + path + "' failed");
+}
+
+Model load_model(const std::string& path) {
+  Reader r; r.f.open(path, std::ios::binary);
+  if (!r.f) throw std::runtime_error("model cache: cannot open '" + path + "'");
+  uint32_t magic = 0, version = 0;
+  r.pod(magic); r.pod(version);
+  if (magic != kCacheMagic) throw std::runtime_error("model cache: '" + path + "' is not a model cache");
+  if (version != kCacheVersion) throw std::runtime_error("model cache: '" + path + "' has version " + std::to_string(version) + ", this library reads " + std::to_string(kCacheVersion));
+  Model md;
+  model_fields(r, md);
+  md.frames.resize(r.len());
+  for (Frame& fr : md.frames) { r.str(fr.name); r.str(fr.joint); r.pod(fr.body); r.pod(fr.pos); r.pod(fr.rot); }
+  // structural sanity: a cache is trusted input only as far as the sizes agree
+  const size_t nb = (size_t)md.nb;
+  if (md.nb < 1 || md.parent.size() != nb || md.jtype.size() != nb || md.qidx.size() != nb || md.vidx.size() != nb || md.depth.size() != nb ||
+      md.subtree.size() != nb || md.jpos.size() != 3 * nb || md.jrot.size() != 9 * nb || md.axis.size() != 3 * nb || md.mass.size() != nb ||
+      md.com.size() != 3 * nb || md.inertia.size() != 6 * nb || md.jlimit.size() != 2 * nb || md.body_names.size() != nb || md.joint_names.size() != nb ||
+      md.ctype.size() != md.cbody.size() || md.csize.size() != 3 * md.cbody.size() || md.cpos.size() != 3 * md.cbody.size() || md.crot.size() != 9 * md.cbody.size() ||
+      md.pt_coll.size() != md.pt_body.size() || md.pt_feat.size() != md.pt_body.size() || md.pt_pos.size() != 3 * md.pt_body.size() || md.pt_rad.size() != md.pt_body.size())
+    throw std::runtime_error("model cache: '" + path + "' is inconsistent");
+  for (size_t i = 0; i < nb; i++) if (md.parent[i] >= (int)i || (i > 0 && md.parent[i] < 0)) throw std::runtime_error("model cache: '" + path + "' is inconsistent (parents)");
+  for (int b : md.cbody) if (b < 0 || b >= md.nb) throw std::runtime_error("model cache: '" + path + "' is inconsistent (collision bodies)");
+  for (int b : md.pt_body) if (b < 0 || b >= md.nb) throw std::runtime_error("model cache: '" + path + "' is inconsistent (points)");
+  for (const Frame& fr : md.frames) if (fr.body < 0 || fr.body >= md.nb) throw std::runtime_error("model cache: '" + path + "' is inconsistent (frames)");
+  return md;
+}
+
 }  // namespace rsb

@@ -40,4 +40,8 @@ struct Model {
 // Throws std::runtime_error with a readable message on malformed input.
 Model load_urdf(const std::string& path_or_xml);
 
+// binary cache of the compiled tables (same-architecture; throws std::runtime_error on I/O or format errors)
+void save_model(const Model& md, const std::string& path);
+Model load_model(const std::string& path);
+
 }  // namespace rsb

@@ -160,3 +160,28 @@ def test_heightmap_text_and_png_loaders(tmp_path):
         capi.read_heightmap_text(str(short))
     with pytest.raises(RuntimeError, match="cannot open"):
         capi.read_heightmap_text(str(tmp_path / "missing.txt"))
+
+
+@pytest.mark.parametrize("src", ["anymal_c_like.urdf", "atlas_like.urdf"])
+def test_binary_model_cache_round_trip(src, tmp_path):
+    """N2: rsb_model_save / rsb_model_load reproduce every table bit for bit; damaged files are reported"""
+    m = capi.Model(os.path.join(RSC, src))
+    path = str(tmp_path / "model.rsbm")
+    m.save(path)
+    m2 = capi.Model(path, cache=True)
+    a, b = m.tables(), m2.tables()
+    assert a.keys() == b.keys()
+    for k in a:
+        assert (np.array_equal(a[k], b[k]) if isinstance(a[k], np.ndarray) else a[k] == b[k]), k
+    assert (m.nq, m.nv, m.nb, m.ncoll, m.npts) == (m2.nq, m2.nv, m2.nb, m2.ncoll, m2.npts)
+    foot = "LF_FOOT" if "anymal" in src else m.tables()["body_names"][-1]
+    assert m.body_index(foot) == m2.body_index(foot)
+    blob = open(path, "rb").read()
+    bad = tmp_path / "trunc.rsbm"; bad.write_bytes(blob[: len(blob) // 2])
+    with pytest.raises(capi.RsbError, match="truncated|corrupt|inconsistent"):
+        capi.Model(str(bad), cache=True)
+    bad2 = tmp_path / "magic.rsbm"; bad2.write_bytes(b"XXXX" + blob[4:])
+    with pytest.raises(capi.RsbError, match="not a model cache"):
+        capi.Model(str(bad2), cache=True)
+    with pytest.raises(capi.RsbError, match="cannot open"):
+        capi.Model(str(tmp_path / "missing.rsbm"), cache=True)
