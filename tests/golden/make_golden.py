@@ -5,7 +5,7 @@ and give the GPU tests a reference that does not need the oracle at run time.
 Re-run only when a convention in DESIGN.md section 2 changes on purpose."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle.oracle import Oracle
 from oracle.urdf_tables import load_tables

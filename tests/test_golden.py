@@ -1,4 +1,4 @@
-"""Golden fixtures (tests/golden/*.npz, made by tools/make_golden.py from the float64 oracle).
+"""Golden fixtures (tests/golden/*.npz, made by tests/golden/make_golden.py from the float64 oracle).
 CPU: the oracle still reproduces them.  GPU: the kernel matches them without running the oracle."""
 import os
 import numpy as np

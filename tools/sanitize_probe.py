@@ -6,12 +6,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from raisimlib_b200 import capi, RSC_DIR
 from helpers import ANYMAL_GC0, PENDULUM_URDF, random_state
-from oracle.urdf_tables import load_tables
 
 for urdf, n, z in (("anymal_c_like.urdf", 40, 0.4), ("atlas_like.urdf", 20, 0.6), (PENDULUM_URDF, 10, 0.0)):
     path = os.path.join(RSC_DIR, urdf) if urdf.endswith(".urdf") else urdf
-    t = load_tables(path)
     m = capi.Model(path)
+    t = m.tables()          # same keys as the Python restatement's tables; no oracle import outside tests/
     b = capi.Batch(m, n)
     rng = np.random.default_rng(0)
     gc, gv = random_state(t, rng, n, vel_scale=0.5, base_z=z)
