@@ -137,13 +137,13 @@ void orc_destroy(void* hv) { delete static_cast<Handle*>(hv); }
 
 int orc_kmax() { return KMAX; }
 
-// p = {dt, gx, gy, gz, erp, alpha_init, alpha_min, alpha_decay, max_iter, threshold, mu, restitution, rest_threshold, stall_window, stall_ratio, warm_start, slip_bisect, joint_limits, slip_local}
+// p = {dt, gx, gy, gz, erp, alpha_init, alpha_min, alpha_decay, max_iter, threshold, mu, restitution, rest_threshold, stall_window, stall_ratio, warm_start, slip_bisect, joint_limits, slip_local, accel_m, accel_start}
 void orc_set_params(void* hv, const double* p) {
   Handle* h = static_cast<Handle*>(hv);
   Params prm;
   prm.dt = p[0]; prm.gravity[0] = p[1]; prm.gravity[1] = p[2]; prm.gravity[2] = p[3]; prm.erp = p[4];
   prm.alpha_init = p[5]; prm.alpha_min = p[6]; prm.alpha_decay = p[7]; prm.max_iter = int(p[8]); prm.threshold = p[9];
-  prm.mu = p[10]; prm.restitution = p[11]; prm.rest_threshold = p[12]; prm.stall_window = int(p[13]); prm.stall_ratio = p[14]; prm.warm_start = int(p[15]); prm.slip_bisect = int(p[16]); prm.joint_limits = int(p[17]); prm.slip_local = int(p[18]);
+  prm.mu = p[10]; prm.restitution = p[11]; prm.rest_threshold = p[12]; prm.stall_window = int(p[13]); prm.stall_ratio = p[14]; prm.warm_start = int(p[15]); prm.slip_bisect = int(p[16]); prm.joint_limits = int(p[17]); prm.slip_local = int(p[18]); prm.accel_m = int(p[19]); prm.accel_start = int(p[20]);
   if (h->d) h->d->prm = prm; else if (h->f) h->f->prm = prm; else h->c->prm = prm;
 }
 

@@ -90,6 +90,8 @@ struct Params {
   int slip_bisect = 0;          // 1: after the first 32-probe round, refine the bracket by plain bisection (what a CPU
                                 // implementation of the published method does); 0: 32-section rounds, probe-for-probe the
                                 // kernel's search.  Both end in the same bracket width; results agree to ~1e-7.
+  int accel_m = 0;              // EXPERIMENT, oracle only (round-2 candidate): Anderson acceleration of the
+  int accel_start = 6;          // Gauss-Seidel sweep map with a history of accel_m (<= 3) differences, allowed from sweep accel_start on
   int slip_local = 1;           // from the 2nd Gauss-Seidel iteration on, a contact that slipped searches a 2*pi/32 fan centred on
                                 // its previous slip direction first (31 sections) and falls back to the full circle if no
                                 // sign change is inside; saves one 32-probe round per slip update
@@ -660,8 +662,17 @@ template <typename T> class Sim {
       T alpha = T(prm.alpha_init), mu = T(prm.mu);
       T err_ckpt = T(3.0e38);
       int next_ckpt = prm.stall_window;
+      // Anderson acceleration state: sweep outputs g_k and residuals f_k = g_k - x_k of the last accel_m + 1 sweeps
+      const int AM = std::min(std::max(prm.accel_m, 0), 3);
+      std::vector<T> hx, hg, hf;          // current x, and history rows [slot][C]
+      int hcount = 0;
+      if (AM > 0) { hx.assign(C, T(0)); hg.assign((size_t)(AM + 1) * C, T(0)); hf.assign((size_t)(AM + 1) * C, T(0)); }
       for (int it = 0; it < prm.max_iter; it++) {
         T err = 0;
+        if (AM > 0) {
+          for (int i = 0; i < K; i++) { hx[3 * i] = ws.contacts[i].lam.x; hx[3 * i + 1] = ws.contacts[i].lam.y; hx[3 * i + 2] = ws.contacts[i].lam.z; }
+          for (int l = 0; l < Lm; l++) hx[C3 + l] = ws.limits[l].lam;
+        }
         for (int i = 0; i < K; i++) {
           Contact<T>& ct = ws.contacts[i];
           T Gii[9];
@@ -691,6 +702,67 @@ template <typename T> class Sim {
         ws.iters = it + 1;
         alpha = std::max(T(prm.alpha_min), alpha * T(prm.alpha_decay));
         if (err < T(prm.threshold)) break;
+        if (AM > 0) {
+          // push (g, f) of this sweep; slots are a shift register, newest last
+          if (hcount == AM + 1) {
+            for (int sl = 0; sl < AM; sl++) for (int a = 0; a < C; a++) { hg[(size_t)sl * C + a] = hg[(size_t)(sl + 1) * C + a]; hf[(size_t)sl * C + a] = hf[(size_t)(sl + 1) * C + a]; }
+            hcount = AM;
+          }
+          T* g = &hg[(size_t)hcount * C]; T* f = &hf[(size_t)hcount * C];
+          for (int i = 0; i < K; i++) { g[3 * i] = ws.contacts[i].lam.x; g[3 * i + 1] = ws.contacts[i].lam.y; g[3 * i + 2] = ws.contacts[i].lam.z; }
+          for (int l = 0; l < Lm; l++) g[C3 + l] = ws.limits[l].lam;
+          T fn = 0, fp = 0;
+          for (int a = 0; a < C; a++) { f[a] = g[a] - hx[a]; fn += f[a] * f[a]; }
+          if (hcount > 0) for (int a = 0; a < C; a++) fp += hf[(size_t)(hcount - 1) * C + a] * hf[(size_t)(hcount - 1) * C + a];
+          hcount++;
+          if (hcount > 1 && fn > T(4) * fp) {          // residual doubled: drop the history, continue from the plain sweep output
+            for (int a = 0; a < C; a++) { hg[a] = g[a]; hf[a] = f[a]; }
+            hcount = 1;
+          } else if (hcount > 1 && it + 1 >= prm.accel_start) {
+            const int md = hcount - 1;                 // differences available
+            T A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, rhs[3] = {0, 0, 0}, gam[3] = {0, 0, 0};
+            for (int p2 = 0; p2 < md; p2++) {
+              for (int q2 = 0; q2 < md; q2++) {
+                T sacc = 0;
+                for (int a = 0; a < C; a++) sacc += (hf[(size_t)(p2 + 1) * C + a] - hf[(size_t)p2 * C + a]) * (hf[(size_t)(q2 + 1) * C + a] - hf[(size_t)q2 * C + a]);
+                A[3 * p2 + q2] = sacc;
+              }
+              T sacc = 0;
+              for (int a = 0; a < C; a++) sacc += (hf[(size_t)(p2 + 1) * C + a] - hf[(size_t)p2 * C + a]) * f[a];
+              rhs[p2] = sacc;
+            }
+            T tr = 0; for (int p2 = 0; p2 < md; p2++) tr += A[3 * p2 + p2];
+            for (int p2 = 0; p2 < md; p2++) A[3 * p2 + p2] += T(1e-10) * tr + T(1e-30);
+            // Gaussian elimination without pivoting (SPD + ridge)
+            bool ok = true;
+            for (int p2 = 0; p2 < md && ok; p2++) {
+              T piv = A[3 * p2 + p2];
+              if (!(piv > T(0))) { ok = false; break; }
+              for (int r2 = p2 + 1; r2 < md; r2++) {
+                T m2 = A[3 * r2 + p2] / piv;
+                for (int c2 = p2; c2 < md; c2++) A[3 * r2 + c2] -= m2 * A[3 * p2 + c2];
+                rhs[r2] -= m2 * rhs[p2];
+              }
+            }
+            if (ok) {
+              for (int p2 = md - 1; p2 >= 0; p2--) {
+                T sacc = rhs[p2];
+                for (int c2 = p2 + 1; c2 < md; c2++) sacc -= A[3 * p2 + c2] * gam[c2];
+                gam[p2] = sacc / A[3 * p2 + p2];
+              }
+              // x_next = g - sum_j gamma_j (g_{j+1} - g_j); then rebuild the contact velocities u = u0 + G x_next
+              std::vector<T> xn(g, g + C);
+              for (int p2 = 0; p2 < md; p2++) for (int a = 0; a < C; a++) xn[a] -= gam[p2] * (hg[(size_t)(p2 + 1) * C + a] - hg[(size_t)p2 * C + a]);
+              for (int i = 0; i < K; i++) ws.contacts[i].lam = {xn[3 * i], xn[3 * i + 1], xn[3 * i + 2]};
+              for (int l = 0; l < Lm; l++) ws.limits[l].lam = xn[C3 + l];
+              for (int a = 0; a < C; a++) {
+                T sacc = ws.u0[a];
+                for (int b2 = 0; b2 < C; b2++) sacc += ws.G[a * C + b2] * xn[b2];
+                ws.u[a] = sacc;
+              }
+            }
+          }
+        }
         if (it + 1 == next_ckpt) {
           if (it + 1 >= 2 * prm.stall_window && err > T(prm.stall_ratio) * err_ckpt) break;
           err_ckpt = err; next_ckpt += prm.stall_window;

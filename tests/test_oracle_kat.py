@@ -627,3 +627,34 @@ def test_terrain_atlas_gives_every_environment_its_own_map():
     o.set_heightmap(xs, ys, 4.0, 3.0, 0.0, 0.0, Hr)
     o.step(c, d, n_steps=50)
     assert np.array_equal(a, c) and np.array_equal(b, d)
+
+
+def test_anderson_accelerated_gauss_seidel_same_fixed_point_fewer_sweeps(atlas_tables):
+    """Round-2 candidate (oracle only, accel_m = 0 by default): Anderson acceleration of the Gauss-Seidel
+    sweep map.  Redundant box-corner contacts of the standing humanoid: same solution, a third of the sweeps."""
+    t = atlas_tables
+    n = 64
+    rng = np.random.default_rng(3)
+    gc = np.zeros((n, 37)); gc[:, 2] = 0.95; gc[:, 3] = 1.0; gc[:, 7:] += rng.uniform(-0.05, 0.05, (n, 30))
+    gv = np.zeros((n, 36))
+    kp = np.r_[np.zeros(6), 400 * np.ones(30)]; kd = np.r_[np.zeros(6), 10 * np.ones(30)]
+    tgt = gc.copy()
+    plain = Oracle(t, params=dict(threshold=1e-7, stall_window=0)); plain.set_ground(0.0)
+    plain.step(gc, gv, n_steps=60, ptarget=tgt, vtarget=np.zeros((n, 36)), kp=kp, kd=kd)          # settle onto the feet
+    acc = Oracle(t, params=dict(threshold=1e-7, stall_window=0, accel_m=2)); acc.set_ground(0.0)
+    a, b = gc.copy(), gv.copy(); c, d = gc.copy(), gv.copy()
+    dp = plain.step(a, b, ptarget=tgt, vtarget=np.zeros((n, 36)), kp=kp, kd=kd, debug=True)
+    da = acc.step(c, d, ptarget=tgt, vtarget=np.zeros((n, 36)), kp=kp, kd=kd, debug=True)
+    both = (dp["iters"] < 150) & (da["iters"] < 150)
+    assert both.mean() > 0.9 and (dp["ncontacts"] >= 6).mean() > 0.9
+    print(f"sweeps plain {dp['iters'][both].mean():.1f} accelerated {da['iters'][both].mean():.1f}; |dgv| {np.abs(b - d)[both].max():.2e}")
+    assert da["iters"][both].mean() < 0.5 * dp["iters"][both].mean()
+    assert np.abs(b - d)[both].max() < 2e-5          # same fixed point (velocity level), to the solver threshold
+    # default parameters leave quickly converging problems untouched (acceleration starts at sweep 6)
+    t2 = load_tables(SPHERE_URDF)
+    o1, o2 = Oracle(t2), Oracle(t2, params=dict(accel_m=2))
+    for o in (o1, o2):
+        o.set_ground(0.0)
+    g1 = np.array([[0, 0, 0.1, 1, 0, 0, 0.0]]); v1 = np.array([[0.5, 0, -0.2, 0, 0, 0.0]]); g2, v2 = g1.copy(), v1.copy()
+    o1.step(g1, v1, n_steps=20); o2.step(g2, v2, n_steps=20)
+    assert np.array_equal(g1, g2) and np.array_equal(v1, v2)
