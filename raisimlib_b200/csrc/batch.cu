@@ -485,6 +485,7 @@ int rsb_batch_set_heightmap(rsb_batch* b, int xs, int ys, float x_size, float y_
   CK(cudaSetDevice(b->device));
   CK(cudaStreamSynchronize(b->stream));
   if (b->hmap) { cudaFree(b->hmap); b->hmap = nullptr; }
+  b->ter = TerrainDesc{};               // nothing may point at the freed map if an allocation below fails
   CK(cudaMalloc((void**)&b->hmap, (size_t)xs * ys * 4));
   CK(cudaMemcpy(b->hmap, h, (size_t)xs * ys * 4, cudaMemcpyHostToDevice));
   TerrainDesc t{};
@@ -507,6 +508,7 @@ int rsb_batch_set_heightmaps(rsb_batch* b, int count, int xs, int ys, float x_si
   CK(cudaStreamSynchronize(b->stream));
   if (b->hmap) { cudaFree(b->hmap); b->hmap = nullptr; }
   if (b->hmap_index) { cudaFree(b->hmap_index); b->hmap_index = nullptr; }
+  b->ter = TerrainDesc{};               // nothing may point at the freed maps if an allocation below fails
   const size_t words = (size_t)count * xs * ys;
   CK(cudaMalloc((void**)&b->hmap, words * 4));
   CK(cudaMemcpy(b->hmap, h, words * 4, cudaMemcpyHostToDevice));
