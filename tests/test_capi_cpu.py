@@ -185,3 +185,18 @@ def test_binary_model_cache_round_trip(src, tmp_path):
         capi.Model(str(bad2), cache=True)
     with pytest.raises(capi.RsbError, match="cannot open"):
         capi.Model(str(tmp_path / "missing.rsbm"), cache=True)
+
+
+def test_product_never_touches_the_oracle():
+    """the oracle is test infrastructure: nothing under raisimlib_b200/, include/, examples/ or tools/ may import, link or call it"""
+    import re
+    bad = []
+    for top in ("raisimlib_b200", "include", "examples", "tools"):
+        for root, _dirs, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if not f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", "Makefile")):
+                    continue
+                txt = open(os.path.join(root, f), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|liboracle|-loracle|#\s*include[^\n]*oracle|orc_[a-z_]+\(", txt, re.M):
+                    bad.append(os.path.relpath(os.path.join(root, f), ROOT))
+    assert not bad, bad
