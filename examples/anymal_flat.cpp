@@ -21,7 +21,11 @@ int main(int argc, char** argv) {
   anymal->setControlMode(raisim::ControlMode::PD_PLUS_FEEDFORWARD_TORQUE);
   anymal->setPdGains(kp, kd);
   anymal->setPdTarget(gc, gv);
+  // named materials, upstream style: one foot gets a grippier sole
+  anymal->getCollisionBody("LF_FOOT/0").setMaterial("rubber");
+  world.setMaterialPairProp("rubber", "default", 0.95, 0.0, 0.0);
   for (int k = 0; k < steps; k++) world.integrate();
+  std::printf("contact solver sweeps in the last step: %d\n", world.getContactSolver().getLoopCounter());
   anymal->getState(gc, gv);
   auto& contacts = anymal->getContacts();
   std::printf("t=%.4f s  base z=%.4f  contacts=%zu\n", world.getWorldTime(), gc[2], contacts.size());

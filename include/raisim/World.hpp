@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -218,6 +219,24 @@ class ArticulatedSystem {
     pushWrench();
   }
   void clearExternalWrench() { extBody_ = -1; extHasForce_ = false; for (int k = 0; k < 3; k++) extF_[k] = extT_[k] = extP_[k] = 0.f; }   // called by World::integrate()
+  // upstream: robot->getCollisionBody("LF_FOOT/0").setMaterial("rubber"); world.setMaterialPairProp("rubber", "default", mu, ...)
+  class CollisionBodyRef {
+   public:
+    CollisionBodyRef(ArticulatedSystem* a, size_t idx) : a_(a), idx_(idx) {}
+    void setMaterial(const std::string& name) { a_->collisionMaterial_[idx_] = name; a_->materialsDirty_ = true; }
+    const std::string& getMaterial() const { static const std::string d = "default"; auto it = a_->collisionMaterial_.find(idx_); return it == a_->collisionMaterial_.end() ? d : it->second; }
+    size_t index() const { return idx_; }
+   private:
+    ArticulatedSystem* a_; size_t idx_;
+  };
+  CollisionBodyRef getCollisionBody(const std::string& name) {
+    int i = rsb_model_collision_index(w_->model(), name.c_str());
+    rsbCheck(i, "getCollisionBody");
+    return CollisionBodyRef(this, size_t(i));
+  }
+  const std::map<size_t, std::string>& collisionMaterials() const { return collisionMaterial_; }
+  bool materialsDirty() const { return materialsDirty_; }
+  void materialsApplied() { materialsDirty_ = false; }
   // friction of one collision body against the terrain (upstream: getCollisionBody(name).setMaterial + setMaterialPairProp)
   void setCollisionBodyFriction(size_t collisionBodyIdx, double mu) {
     rsbCheck(rsb_batch_set_collision_friction(w_->batch(), int(collisionBodyIdx), float(mu)), "setCollisionBodyFriction");
@@ -281,6 +300,8 @@ class ArticulatedSystem {
   void pushWrench() {
     rsbCheck(rsb_batch_set_external_wrench(w_->batch(), extBody_, extF_, extT_, extP_, env_, 1, RSB_HOST), "setExternalForce");
   }
+  std::map<size_t, std::string> collisionMaterial_;   // collision body -> material name (absent = "default")
+  bool materialsDirty_ = false;
   int extBody_ = -1; bool extHasForce_ = false;
   float extF_[3] = {0, 0, 0}, extT_[3] = {0, 0, 0}, extP_[3] = {0, 0, 0};
   struct Poses { std::vector<float> R, p; };
@@ -356,8 +377,9 @@ class World {
     robot_.reset(new ArticulatedSystem(w_, 0));
     return robot_.get();
   }
-  Ground* addGround(double zHeight = 0.0, const std::string& = "default", CollisionGroup = CollisionGroup(-1)) {
-    haveGround_ = true; groundZ_ = zHeight;
+  Ground* addGround(double zHeight = 0.0, const std::string& material = "default", CollisionGroup = CollisionGroup(-1)) {
+    haveGround_ = true; groundZ_ = zHeight; terrainMaterial_ = material;
+    if (robot_) applyMaterials(true);
     if (w_) rsbCheck(rsb_batch_set_ground(w_->batch(), float(zHeight)), "addGround");
     return &ground_;
   }
@@ -411,16 +433,40 @@ class World {
   void setDefaultMaterial(double friction, double restitution, double resThreshold) {
     need(); rsb_params p = w_->params(); p.mu = float(friction); p.restitution = float(restitution); p.rest_threshold = float(resThreshold); w_->setParams(p);
   }
+  // named material pairs: friction of (collision-body material, terrain material); restitution is global (setDefaultMaterial)
+  void setMaterialPairProp(const std::string& m1, const std::string& m2, double friction, double /*restitution*/ = 0, double /*resThreshold*/ = 0) {
+    pairFriction_[m1 < m2 ? std::make_pair(m1, m2) : std::make_pair(m2, m1)] = friction;
+    if (robot_) applyMaterials(true);
+  }
+  struct ContactSolverView {            // World::getContactSolver().getLoopCounter()
+    const World* w;
+    int getLoopCounter() const { int32_t it = 0; rsbCheck(rsb_batch_get_solver_iterations(w->w_->batch(), &it, w->env_, 1, RSB_HOST), "getLoopCounter"); return it; }
+  };
+  ContactSolverView getContactSolver() const { need(); return ContactSolverView{this}; }
+  ArticulatedSystem* getObject(const std::string& name) { return (robot_ && robot_->getName() == name) ? robot_.get() : nullptr; }
+  // object-object and self collisions are not part of this path (robot vs terrain only): nothing to ignore
+  void ignoreCollisionBetween(size_t, size_t, size_t, size_t) {}
   // one World::integrate() of THIS environment's batch.  Views of a shared batch must not call this
   // per environment -- the vectorized wrapper steps the whole batch once (see VectorizedEnvironment.hpp).
-  void integrate() { need(); w_->integrate(1); if (robot_) robot_->clearExternalWrench(); }
-  void integrate1() { need(); w_->integrate1(); }
+  void integrate() { need(); applyMaterials(false); w_->integrate(1); if (robot_) robot_->clearExternalWrench(); }
+  void integrate1() { need(); applyMaterials(false); w_->integrate1(); }
   void integrate2() { need(); w_->integrate2(); if (robot_) robot_->clearExternalWrench(); }
   double getWorldTime() const { return w_ ? w_->worldTime() : 0.0; }
   ArticulatedSystem* getRobot() { return robot_.get(); }
   BatchedWorld* batched() { return w_; }
  private:
   void need() const { if (!w_) throw std::runtime_error("World: call addArticulatedSystem() first (the batch is created with the robot)"); }
+  void applyMaterials(bool force) {
+    if (!robot_ || (!force && !robot_->materialsDirty())) return;
+    for (const auto& kv : robot_->collisionMaterials()) {
+      const std::string& a = kv.second; const std::string& b = terrainMaterial_;
+      auto it = pairFriction_.find(a < b ? std::make_pair(a, b) : std::make_pair(b, a));
+      robot_->setCollisionBodyFriction(kv.first, it == pairFriction_.end() ? -1.0 : it->second);   // < 0: default material
+    }
+    robot_->materialsApplied();
+  }
+  std::map<std::pair<std::string, std::string>, double> pairFriction_;
+  std::string terrainMaterial_ = "default";
   std::unique_ptr<BatchedWorld> owned_;
   BatchedWorld* w_ = nullptr;
   int env_ = 0;

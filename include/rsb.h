@@ -108,6 +108,7 @@ int rsb_model_dims(const rsb_model* m, int* nq, int* nv, int* nb, int* ncoll, in
 int rsb_model_get_tables(const rsb_model* m, rsb_model_tables* out);
 int rsb_model_body_index(const rsb_model* m, const char* name);    /* ArticulatedSystem::getBodyIdx   */
 const char* rsb_model_body_name(const rsb_model* m, int body);
+int rsb_model_collision_index(const rsb_model* m, const char* name); /* getCollisionBody("LINK/k"): k-th collision body of a link */
 const char* rsb_model_joint_name(const rsb_model* m, int body);
 int rsb_model_frame_index(const rsb_model* m, const char* name);   /* getFrameIdxByName (link frames) */
 int rsb_model_frame(const rsb_model* m, int frame, int* body, double pos[3], double rot[9]);

@@ -91,7 +91,7 @@ class DeviceView(C.Structure):
 EXPORTED = [
     "rsb_last_error", "rsb_version", "rsb_params_default",
     "rsb_model_create_from_urdf", "rsb_model_destroy", "rsb_model_save", "rsb_model_load", "rsb_model_dims", "rsb_model_get_tables", "rsb_model_body_index",
-    "rsb_model_body_name", "rsb_model_joint_name", "rsb_model_frame_index", "rsb_model_frame",
+    "rsb_model_body_name", "rsb_model_collision_index", "rsb_model_joint_name", "rsb_model_frame_index", "rsb_model_frame",
     "rsb_batch_create", "rsb_batch_destroy", "rsb_batch_set_stream", "rsb_batch_sync", "rsb_batch_num_envs",
     "rsb_batch_set_ground", "rsb_batch_set_heightmap", "rsb_batch_set_heightmaps", "rsb_batch_clear_terrain", "rsb_batch_set_params", "rsb_batch_get_params",
     "rsb_batch_set_collision_friction",
@@ -210,6 +210,10 @@ class Model:
         d = [C.c_int() for _ in range(5)]
         _ck(lib().rsb_model_dims(h, *[C.byref(x) for x in d]))
         self.nq, self.nv, self.nb, self.ncoll, self.npts = [x.value for x in d]
+
+    def collision_index(self, name):
+        lib().rsb_model_collision_index.argtypes = [C.c_void_p, C.c_char_p]
+        return _ck(lib().rsb_model_collision_index(self.h, name.encode()))
 
     def save(self, path):
         lib().rsb_model_save.argtypes = [C.c_void_p, C.c_char_p]

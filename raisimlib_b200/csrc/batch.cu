@@ -379,6 +379,16 @@ int rsb_model_body_index(const rsb_model* m, const char* name) {
   for (const Frame& f : m->md.frames) if (f.name == name) return f.body;   // a link merged through a fixed joint
   return fail(RSB_ERR_INVALID, std::string("no body named '") + name + "'");
 }
+// collision bodies are named after the link that carries them, upstream style "LINK/k" for the k-th one ("LINK" = "LINK/0")
+int rsb_model_collision_index(const rsb_model* m, const char* name) {
+  if (!m || !name) return fail(RSB_ERR_INVALID, "null argument");
+  std::string link = name; int which = 0;
+  const size_t slash = link.rfind('/');
+  if (slash != std::string::npos) { which = std::atoi(link.c_str() + slash + 1); link.resize(slash); }
+  int seen = 0;
+  for (int c = 0; c < m->md.ncoll(); c++) if (m->md.coll_names[c] == link) { if (seen == which) return c; seen++; }
+  return fail(RSB_ERR_INVALID, std::string("no collision body named '") + name + "'");
+}
 const char* rsb_model_body_name(const rsb_model* m, int body) { return (m && body >= 0 && body < m->md.nb) ? m->md.body_names[body].c_str() : nullptr; }
 const char* rsb_model_joint_name(const rsb_model* m, int body) { return (m && body >= 0 && body < m->md.nb) ? m->md.joint_names[body].c_str() : nullptr; }
 int rsb_model_frame_index(const rsb_model* m, const char* name) {
