@@ -156,7 +156,7 @@ class ArticulatedSystem {
   }
   void setControlMode(ControlMode::Type m) { rsbCheck(rsb_batch_set_control_mode(w_->batch(), int(m)), "setControlMode"); }
 
-  // lazy getters: valid after integrate1() (or integrate1()+integrate2())
+  // lazy getters: always describe the current state (the C-ABI refreshes M, h and the poses when the state changed)
   MatDyn getMassMatrix() const {
     const int nv = w_->nv();
     std::vector<float> m(size_t(nv) * nv);
@@ -308,7 +308,8 @@ class ArticulatedSystem {
   struct FrameW { int body; Vec<3> pos; Mat<3, 3> rot; };
   Poses poses() const {
     Poses P; P.R.resize(size_t(w_->nb()) * 9); P.p.resize(size_t(w_->nb()) * 3);
-    w_->integrate1();   // kinematics pass at the CURRENT state (idempotent; no state change): upstream's updateKinematics()
+    // the C-ABI getter is lazy: it runs a kinematics-only pass when the state changed (upstream's updateKinematics()); the contact
+    // records and impulses of the last integrate() stay valid across kinematic getters, as upstream's getContacts() does
     rsbCheck(rsb_batch_get_body_poses(w_->batch(), env_, 1, P.R.data(), P.p.data(), RSB_HOST), "getBodyPoses");
     return P;
   }

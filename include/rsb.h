@@ -59,11 +59,19 @@ typedef struct rsb_params {
   float rest_threshold; /* restitution threshold velocity               (0.01)           */
   /* Stagnation exit of the Gauss-Seidel loop (NOT in the reference; stall_window = 0 restores the
    * plain maxIter behaviour): every stall_window iterations, stop if the largest impulse update has
-   * not dropped below stall_ratio x its value one window earlier.  Rank-deficient Delassus blocks
-   * (two contacts on one body) make the published per-contact rule cycle; see DESIGN.md section 5. */
-  int stall_window;     /*                                               (8)              */
+   * not dropped below stall_ratio x its value one window earlier.  A safety net for the rare contact
+   * sets on which the published per-contact rule enters a limit cycle (< 0.2 % of the problems of
+   * fallen robots with the accelerated sweeps; never on standing ones); see DESIGN.md section 5. */
+  int stall_window;     /*                                               (16)             */
   float stall_ratio;    /*                                               (0.5)            */
   int joint_limits;     /* enforce URDF <limit lower upper> as unilateral rows of the same solve (1) */
+  /* Anderson acceleration of the Gauss-Seidel sweep map (NOT in the reference; accel_m = 0 restores the plain sweeps of the
+   * published method): from sweep accel_start on, the next iterate is extrapolated from the last accel_m + 1 sweep
+   * outputs g_k and residuals f_k = g_k - x_k (least squares over the residual differences; history dropped when the
+   * residual doubles).  Same fixed point; redundant contact sets (box feet, knee + foot on one shank) converge in a
+   * third of the sweeps and quickly converging problems never reach accel_start.  DESIGN.md section 5. */
+  int accel_m;          /* 0 = off, 2 = on                               (2)              */
+  int accel_start;      /* first extrapolation after this sweep          (6)              */
 } rsb_params;
 
 /* raisim::Contact as returned by ArticulatedSystem::getContacts(): 12 words */
@@ -161,7 +169,7 @@ int rsb_batch_integrate1(rsb_batch* b);               /* kinematics, collision, 
 int rsb_batch_integrate2(rsb_batch* b);               /* contact solve + state integration               */
 int rsb_batch_integrate(rsb_batch* b, int substeps);  /* substeps x integrate(), one fused launch        */
 
-/* ---- read-backs (lazy getters of the reference); valid after integrate1/integrate --- */
+/* ---- read-backs (lazy getters of the reference): M, h and poses always describe the current state ---- */
 int rsb_batch_get_mass_matrix(rsb_batch* b, int env_begin, int env_count, float* out, int where);     /* [n][nv*nv] getMassMatrix     */
 int rsb_batch_get_nonlinearities(rsb_batch* b, int env_begin, int env_count, float* out, int where);  /* [n][nv]    getNonlinearities */
 int rsb_batch_get_body_poses(rsb_batch* b, int env_begin, int env_count, float* rot, float* pos, int where); /* [n][nb*9],[n][nb*3] */
@@ -169,6 +177,11 @@ int rsb_batch_get_contacts(rsb_batch* b, rsb_contact* out, int32_t* counts, int 
 int rsb_batch_get_contact_points(rsb_batch* b, int32_t* pt_index, int env_begin, int env_count, int where);          /* [n][RSB_KMAX] candidate-point ids */
 int rsb_batch_get_solver_iterations(rsb_batch* b, int32_t* iters, int env_begin, int env_count, int where);          /* getContactSolver().getLoopCounter() */
 int rsb_batch_get_diverged(rsb_batch* b, int32_t* flags, int env_begin, int env_count, int where);                   /* 1 = state went non-finite in the last step: reset it */
+int rsb_batch_get_solver_residual(rsb_batch* b, float* resid, int env_begin, int env_count, int where);              /* largest impulse update of the last sweep (< threshold: converged) */
+/* FK, M and h of the CURRENT state for the getters above, without touching the contact records of the last integrate()
+ * (upstream's getters are lazy the same way).  The getters call it themselves when the state changed through this API;
+ * call it explicitly after writing the state through rsb_batch_device_ptrs() views. */
+int rsb_batch_update_kinematics(rsb_batch* b);
 int rsb_batch_device_ptrs(rsb_batch* b, rsb_device_view* view);
 int64_t rsb_batch_launch_count(const rsb_batch* b);   /* kernels launched by this batch so far */
 

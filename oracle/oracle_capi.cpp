@@ -23,8 +23,8 @@ struct OrcDebug {       // every pointer optional; sized for n_envs; filled from
   double* c_depth;      // [n][KMAX]
   double* c_lambda;     // [n][KMAX*3]  contact-frame impulse (t1,t2,n)
   int* iters;           // [n]
-  double* G;            // [n][(3*KMAX)^2]  Delassus matrix of the kept contacts (row stride 3*KMAX)
-  double* u0;           // [n][3*KMAX]      free contact velocity minus target
+  double* G;            // [n][RMAX^2]  Delassus matrix of the constraint rows: contacts, then joint limits (row stride RMAX)
+  double* u0;           // [n][RMAX]    free constraint velocity minus target
   int ext_body;         // IN external wrench for this call (all sub-steps): body index, < 0 = none
   const double* ext_force;   // [n][3] world, nullable
   const double* ext_torque;  // [n][3] world, nullable
@@ -35,6 +35,7 @@ struct OrcDebug {       // every pointer optional; sized for n_envs; filled from
   int* nlimits;         // [n]         active joint-limit rows
   int* lim_dof;         // [n][LMAX]   their dofs (-1 = none)
   double* lim_lambda;   // [n][LMAX]   their impulses
+  double* resid;        // [n]         largest impulse update of the last sweep (solver residual at exit)
 };
 
 struct Handle {
@@ -102,9 +103,10 @@ static void run(Sim<T>& sim, int n_envs, int n_steps, double* gc, double* gv, co
         int K = int(ws.contacts.size());
         if (dbg->ncontacts) dbg->ncontacts[e] = K;
         if (dbg->iters) dbg->iters[e] = ws.iters;
+        if (dbg->resid) dbg->resid[e] = double(ws.resid);
         const int Crows = 3 * K + int(ws.limits.size());
-        if (dbg->G) for (int a = 0; a < 3 * K; a++) for (int b2 = 0; b2 < 3 * K; b2++) dbg->G[(size_t)e * 9 * KMAX * KMAX + a * 3 * KMAX + b2] = double(ws.G[a * Crows + b2]);
-        if (dbg->u0) for (int a = 0; a < 3 * K; a++) dbg->u0[(size_t)e * 3 * KMAX + a] = double(ws.u0[a]);
+        if (dbg->G) for (int a = 0; a < Crows; a++) for (int b2 = 0; b2 < Crows; b2++) dbg->G[(size_t)e * RMAX * RMAX + a * RMAX + b2] = double(ws.G[a * Crows + b2]);
+        if (dbg->u0) for (int a = 0; a < Crows; a++) dbg->u0[(size_t)e * RMAX + a] = double(ws.u0[a]);
         if (dbg->nlimits) dbg->nlimits[e] = int(ws.limits.size());
         if (dbg->lim_dof) for (int l = 0; l < LMAX; l++) { dbg->lim_dof[(size_t)e * LMAX + l] = l < (int)ws.limits.size() ? ws.limits[l].dof : -1; if (dbg->lim_lambda) dbg->lim_lambda[(size_t)e * LMAX + l] = l < (int)ws.limits.size() ? double(ws.limits[l].lam) : 0.0; }
         for (int k = 0; k < KMAX; k++) {

@@ -85,13 +85,13 @@ struct Params {
   double mu = 0.8;              // World::setDefaultMaterial friction
   double restitution = 0.0, rest_threshold = 0.01;
   int joint_limits = 1;         // enforce the URDF <limit lower upper> of revolute/prismatic joints (unilateral rows in the solver)
-  int stall_window = 8;         // stagnation exit of the Gauss-Seidel loop (0 = off), see include/rsb.h
+  int stall_window = 16;        // stagnation exit of the Gauss-Seidel loop (0 = off), see include/rsb.h
   double stall_ratio = 0.5;
   int slip_bisect = 0;          // 1: after the first 32-probe round, refine the bracket by plain bisection (what a CPU
                                 // implementation of the published method does); 0: 32-section rounds, probe-for-probe the
                                 // kernel's search.  Both end in the same bracket width; results agree to ~1e-7.
-  int accel_m = 0;              // EXPERIMENT, oracle only (round-2 candidate): Anderson acceleration of the
-  int accel_start = 6;          // Gauss-Seidel sweep map with a history of accel_m (<= 3) differences, allowed from sweep accel_start on
+  int accel_m = 2;              // Anderson acceleration of the Gauss-Seidel sweep map (rsb_params.accel_m): history of
+  int accel_start = 6;          // accel_m (<= 3; the kernel implements 0 and 2) differences, first extrapolation after sweep accel_start
   int slip_local = 1;           // from the 2nd Gauss-Seidel iteration on, a contact that slipped searches a 2*pi/32 fan centred on
                                 // its previous slip direction first (31 sections) and falls back to the full circle if no
                                 // sign change is inside; saves one 32-probe round per slip update
@@ -139,6 +139,7 @@ template <typename T> struct Workspace {
   std::vector<Contact<T>> contacts, all;
   std::vector<Limit<T>> limits;
   int iters = 0;
+  T resid = 0;                    // largest impulse update of the last Gauss-Seidel sweep (< threshold: converged)
   // warm-start cache: candidate-point id and WORLD-frame impulse of the previous step's contacts
   int prev_pt[KMAX]; V3<T> prev_imp[KMAX];
   Workspace() { for (int k = 0; k < KMAX; k++) { prev_pt[k] = -1; prev_imp[k] = {0, 0, 0}; } }
@@ -617,7 +618,7 @@ template <typename T> class Sim {
       }
     const int Lm = int(ws.limits.size()), C3 = 3 * K, C = C3 + Lm;
     for (int i = 0; i < nv; i++) ws.rhs[i] = dt * ws.z[i];
-    ws.iters = 0;
+    ws.iters = 0; ws.resid = T(0);
     if (C > 0) {
       jacobians(ws);
       // Y = L^-1 J^T (nv x C);  G = Y^T Y;  u0 = J v + dt Y^T z - target
@@ -699,10 +700,10 @@ template <typename T> class Sim {
           for (int a = 0; a < C; a++) ws.u[a] += ws.G[a * C + r] * dl;
           err = std::max(err, std::fabs(dl));
         }
-        ws.iters = it + 1;
+        ws.iters = it + 1; ws.resid = err;
         alpha = std::max(T(prm.alpha_min), alpha * T(prm.alpha_decay));
         if (err < T(prm.threshold)) break;
-        if (AM > 0) {
+        if (AM > 0 && it + 1 >= prm.accel_start - AM) {   // the history starts AM sweeps before the first extrapolation: nothing is kept (or paid for) on quickly converging problems
           // push (g, f) of this sweep; slots are a shift register, newest last
           if (hcount == AM + 1) {
             for (int sl = 0; sl < AM; sl++) for (int a = 0; a < C; a++) { hg[(size_t)sl * C + a] = hg[(size_t)(sl + 1) * C + a]; hf[(size_t)sl * C + a] = hf[(size_t)(sl + 1) * C + a]; }

@@ -40,7 +40,8 @@ struct rsb_batch {
   int pt_bound_stride = 0;
   const float* vt_bound = nullptr;   // same for the velocity targets
   int vt_bound_stride = 0;
-  bool bound_once = false;           // zero-copy control step: the kernel copies the rows it read into pt / vt, then the binding ends
+  bool pt_once = false, vt_once = false;   // zero-copy control step: the kernel copies the rows it read into pt / vt, then THAT binding ends
+  bool kin_dirty = true;             // the getters' buffers (M, h, poses) do not describe the current state
   unsigned* prof = nullptr;          // rsb_internal_set_profile
   int* hmap_index = nullptr;         // terrain atlas: map index per environment
   float* ext = nullptr;              // [N][EXT_WORDS] external wrench rows; ext_active: rows hold a wrench for the next launch
@@ -48,6 +49,7 @@ struct rsb_batch {
   // device buffers
   float *gc = nullptr, *gv = nullptr, *tau = nullptr, *pt = nullptr, *vt = nullptr, *tau_applied = nullptr;
   int *ncontacts = nullptr, *contact_pt = nullptr, *iters = nullptr, *diverged = nullptr;
+  float* resid = nullptr;
   rsb_contact* contacts = nullptr;
   float *dbg_M = nullptr, *dbg_h = nullptr, *dbg_R = nullptr, *dbg_p = nullptr;
   float* hmap = nullptr;
@@ -235,12 +237,12 @@ static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug, flo
   a.use_pd = (b->control_mode == RSB_PD_PLUS_FEEDFORWARD_TORQUE && b->pd_set) ? 1 : 0;
   a.ptarget = b->pt_bound ? b->pt_bound : b->pt; a.pt_stride = b->pt_bound ? b->pt_bound_stride : b->gc_stride;
   a.vtarget = b->vt_bound ? b->vt_bound : b->vt; a.vt_stride = b->vt_bound ? b->vt_bound_stride : b->gv_stride;
-  a.pt_store = (b->bound_once && b->pt_bound) ? b->pt : nullptr;
-  a.vt_store = (b->bound_once && b->vt_bound) ? b->vt : nullptr;
+  a.pt_store = (b->pt_once && b->pt_bound) ? b->pt : nullptr;
+  a.vt_store = (b->vt_once && b->vt_bound) ? b->vt : nullptr;
   a.prm = b->prm; a.ter = b->ter; a.ws = b->ws;
   a.blob_words = (int)b->blob_host.size(); a.blob = b->blob;
   a.tau_applied = b->tau_applied;
-  a.ncontacts = b->ncontacts; a.contacts = b->contacts; a.contact_pt = b->contact_pt; a.iters = b->iters; a.diverged = b->diverged;
+  a.ncontacts = b->ncontacts; a.contacts = b->contacts; a.contact_pt = b->contact_pt; a.iters = b->iters; a.diverged = b->diverged; a.resid = b->resid;
   if (debug) { a.dbg_M = b->dbg_M; a.dbg_h = b->dbg_h; a.dbg_R = b->dbg_R; a.dbg_p = b->dbg_p; }
   a.phase_mask = phase_mask; a.prof = b->prof;
   a.ext = b->ext_active ? b->ext : nullptr;
@@ -261,6 +263,8 @@ static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug, flo
   }
   if (e != cudaSuccess) return fail(RSB_ERR_CUDA, std::string("step kernel launch: ") + cudaGetErrorString(e));
   b->launches++;
+  if (!(phase_mask & 1)) b->kin_dirty = !debug;   // the state advanced: M, h and poses are stale unless this launch refreshed them
+  else if (debug) b->kin_dirty = false;
   if (phase_mask == 0 || (phase_mask & 2)) b->ext_active = false;   // an external wrench lasts for one integrate() call (upstream semantics)
   return RSB_OK;
 }
@@ -325,7 +329,8 @@ int rsb_params_default(rsb_params* p) {
   if (!p) return fail(RSB_ERR_INVALID, "null params");
   p->dt = 0.0025f; p->gravity[0] = 0.f; p->gravity[1] = 0.f; p->gravity[2] = -9.81f; p->erp = 0.f;
   p->alpha_init = 1.f; p->alpha_min = 1.f; p->alpha_decay = 1.f; p->max_iter = 150; p->threshold = 1e-6f;
-  p->mu = 0.8f; p->restitution = 0.f; p->rest_threshold = 0.01f; p->stall_window = 8; p->stall_ratio = 0.5f; p->joint_limits = 1;
+  p->mu = 0.8f; p->restitution = 0.f; p->rest_threshold = 0.01f; p->stall_window = 16; p->stall_ratio = 0.5f; p->joint_limits = 1;
+  p->accel_m = 2; p->accel_start = 6;
   return RSB_OK;
 }
 
@@ -438,6 +443,7 @@ int rsb_batch_create(const rsb_model* m, int num_envs, int device, rsb_batch** o
   if (e == cudaSuccess) e = alloc((void**)&b->contact_pt, N * KMAX * 4);
   if (e == cudaSuccess) e = alloc((void**)&b->iters, N * 4);
   if (e == cudaSuccess) e = alloc((void**)&b->diverged, N * 4);
+  if (e == cudaSuccess) e = alloc((void**)&b->resid, N * 4);
   if (e == cudaSuccess) e = alloc((void**)&b->contacts, N * KMAX * sizeof(rsb_contact));
   if (e == cudaSuccess) e = alloc((void**)&b->blob, b->blob_host.size() * 4);
   if (e == cudaSuccess) e = cudaMemcpy(b->blob, b->blob_host.data(), b->blob_host.size() * 4, cudaMemcpyHostToDevice);
@@ -458,7 +464,7 @@ void rsb_batch_destroy(rsb_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
-  for (void* p : {(void*)b->diverged, (void*)b->tau_applied, (void*)b->gc, (void*)b->gv, (void*)b->tau, (void*)b->pt, (void*)b->vt, (void*)b->ncontacts, (void*)b->contact_pt, (void*)b->iters,
+  for (void* p : {(void*)b->resid, (void*)b->diverged, (void*)b->tau_applied, (void*)b->gc, (void*)b->gv, (void*)b->tau, (void*)b->pt, (void*)b->vt, (void*)b->ncontacts, (void*)b->contact_pt, (void*)b->iters,
                   (void*)b->contacts, (void*)b->dbg_M, (void*)b->dbg_h, (void*)b->dbg_R, (void*)b->dbg_p, (void*)b->hmap, (void*)b->staging, (void*)b->obs_staging, (void*)b->blob, (void*)b->gym_const, (void*)b->gym_action,
                   (void*)b->gym_obs, (void*)b->gym_reward, (void*)b->gym_done, (void*)b->ext, (void*)b->hmap_index})
     if (p) cudaFree(p);
@@ -536,6 +542,8 @@ int rsb_batch_set_heightmaps(rsb_batch* b, int count, int xs, int ys, float x_si
 int rsb_batch_set_params(rsb_batch* b, const rsb_params* p) {
   if (!b || !p) return fail(RSB_ERR_INVALID, "null argument");
   if (!(p->dt > 0) || p->max_iter < 1 || !(p->mu >= 0)) return fail(RSB_ERR_INVALID, "invalid params");
+  if (p->accel_m != 0 && p->accel_m != 2) return fail(RSB_ERR_INVALID, "accel_m must be 0 (plain sweeps) or 2");
+  if (p->accel_m == 2 && p->accel_start < 3) return fail(RSB_ERR_INVALID, "accel_start must be at least 3");
   b->prm = *p;
   return RSB_OK;
 }
@@ -547,6 +555,7 @@ int rsb_batch_get_params(const rsb_batch* b, rsb_params* p) {
 
 int rsb_batch_set_state(rsb_batch* b, const float* gc, const float* gv, int env_begin, int env_count, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  b->kin_dirty = true;
   rc = copy_rows_in(b, b->gc, b->gc_stride, gc, b->nq, env_begin, env_count, where); if (rc) return rc;
   return copy_rows_in(b, b->gv, b->gv_stride, gv, b->nv, env_begin, env_count, where);
 }
@@ -611,6 +620,7 @@ int rsb_batch_get_generalized_force(rsb_batch* b, float* tau, int env_begin, int
 int rsb_batch_set_external_wrench(rsb_batch* b, int body, const float* force, const float* torque, const float* point_body, int env_begin, int env_count, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
   if (body < 0 || body >= b->nb) return fail(RSB_ERR_INVALID, "external wrench: body index out of range");
+  if (env_count == 0) return RSB_OK;
   CK(cudaSetDevice(b->device));
   if (!b->ext) CK(cudaMalloc((void**)&b->ext, (size_t)b->N * EXT_WORDS * 4));
   if (!b->ext_active) {   // rows of an earlier call are stale: body = -1 everywhere
@@ -654,6 +664,17 @@ int rsb_batch_integrate1(rsb_batch* b) {
   int rc = ensure_debug(b); if (rc) return rc;
   return do_launch(b, 1, 1, true);
 }
+int rsb_batch_update_kinematics(rsb_batch* b) {
+  if (!b) return fail(RSB_ERR_INVALID, "null batch");
+  CK(cudaSetDevice(b->device));
+  int rc = ensure_debug(b); if (rc) return rc;
+  return do_launch(b, 1, 1 | 4, true);      // stage A + the getters' buffers; contact records of the last integrate() untouched
+}
+// lazy getters: refresh M, h and the poses when the state changed through this API since they were last computed
+static int ensure_kinematics(rsb_batch* b) {
+  if (b->dbg_M && !b->kin_dirty) return RSB_OK;
+  return rsb_batch_update_kinematics(b);
+}
 int rsb_batch_integrate2(rsb_batch* b) {
   if (!b) return fail(RSB_ERR_INVALID, "null batch");
   CK(cudaSetDevice(b->device));
@@ -669,7 +690,8 @@ int rsb_batch_integrate(rsb_batch* b, int substeps) {
 
 int rsb_batch_get_mass_matrix(rsb_batch* b, int env_begin, int env_count, float* out, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
-  if (!b->dbg_M) return fail(RSB_ERR_INVALID, "call rsb_batch_integrate1() first");
+  if (env_count == 0) return RSB_OK;
+  rc = ensure_kinematics(b); if (rc) return rc;
   size_t w = (size_t)b->nv * b->nv;
   CK(cudaMemcpyAsync(out, b->dbg_M + env_begin * w, env_count * w * 4, where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
   if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
@@ -677,14 +699,16 @@ int rsb_batch_get_mass_matrix(rsb_batch* b, int env_begin, int env_count, float*
 }
 int rsb_batch_get_nonlinearities(rsb_batch* b, int env_begin, int env_count, float* out, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
-  if (!b->dbg_h) return fail(RSB_ERR_INVALID, "call rsb_batch_integrate1() first");
+  if (env_count == 0) return RSB_OK;
+  rc = ensure_kinematics(b); if (rc) return rc;
   CK(cudaMemcpyAsync(out, b->dbg_h + (size_t)env_begin * b->nv, (size_t)env_count * b->nv * 4, where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
   if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
   return RSB_OK;
 }
 int rsb_batch_get_body_poses(rsb_batch* b, int env_begin, int env_count, float* rot, float* pos, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
-  if (!b->dbg_R) return fail(RSB_ERR_INVALID, "call rsb_batch_integrate1() first");
+  if (env_count == 0) return RSB_OK;
+  rc = ensure_kinematics(b); if (rc) return rc;
   cudaMemcpyKind kind = where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   if (rot) CK(cudaMemcpyAsync(rot, b->dbg_R + (size_t)env_begin * b->nb * 9, (size_t)env_count * b->nb * 9 * 4, kind, b->stream));
   if (pos) CK(cudaMemcpyAsync(pos, b->dbg_p + (size_t)env_begin * b->nb * 3, (size_t)env_count * b->nb * 3 * 4, kind, b->stream));
@@ -708,6 +732,12 @@ int rsb_batch_get_contact_points(rsb_batch* b, int32_t* pt, int env_begin, int e
 int rsb_batch_get_solver_iterations(rsb_batch* b, int32_t* it, int env_begin, int env_count, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
   CK(cudaMemcpyAsync(it, b->iters + env_begin, (size_t)env_count * 4, where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
+  if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
+  return RSB_OK;
+}
+int rsb_batch_get_solver_residual(rsb_batch* b, float* resid, int env_begin, int env_count, int where) {
+  int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  CK(cudaMemcpyAsync(resid, b->resid + env_begin, (size_t)env_count * 4, where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
   if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
   return RSB_OK;
 }
@@ -757,6 +787,7 @@ static int observe_impl(rsb_batch* b, float* obs, int env_begin, int env_count, 
 int rsb_batch_observe(rsb_batch* b, float* obs, int env_begin, int env_count, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
   if (!obs) return fail(RSB_ERR_INVALID, "null obs");
+  if (env_count == 0) return RSB_OK;
   CK(cudaSetDevice(b->device));
   return observe_impl(b, obs, env_begin, env_count, where, true);
 }
@@ -773,20 +804,23 @@ int rsb_batch_control_step(rsb_batch* b, const float* ptarget, const float* vtar
   const float* pt_alias = (ptarget && where_in == RSB_HOST) ? mapped_alias(ptarget) : nullptr;
   const float* vt_alias = (vtarget && where_in == RSB_HOST) ? mapped_alias(vtarget) : nullptr;
   const bool pd_mode = b->control_mode == RSB_PD_PLUS_FEEDFORWARD_TORQUE && b->pd_set;
-  struct Unbind { rsb_batch* b; ~Unbind() { if (b->bound_once) { b->pt_bound = nullptr; b->vt_bound = nullptr; b->bound_once = false; } } } unbind{b};
+  // one-shot bindings end with this call; a persistent rsb_batch_bind_pd_target() binding the call did not replace survives it
+  struct Unbind { rsb_batch* b; ~Unbind() { if (b->pt_once) { b->pt_bound = nullptr; b->pt_once = false; } if (b->vt_once) { b->vt_bound = nullptr; b->vt_once = false; } } } unbind{b};
   if (ptarget) {
     b->pt_bound = nullptr;
-    if (pt_alias && pd_mode) { b->pt_bound = pt_alias; b->pt_bound_stride = b->nq; b->bound_once = true; }
+    if (pt_alias && pd_mode) { b->pt_bound = pt_alias; b->pt_bound_stride = b->nq; b->pt_once = true; }
     else { rc = copy_rows_in(b, b->pt, b->gc_stride, ptarget, b->nq, 0, b->N, where_in); if (rc) return rc; }
   }
   if (vtarget) {
-    if (vt_alias && pd_mode) { b->vt_bound = vt_alias; b->vt_bound_stride = b->nv; b->bound_once = true; }
+    b->vt_bound = nullptr;
+    if (vt_alias && pd_mode) { b->vt_bound = vt_alias; b->vt_bound_stride = b->nv; b->vt_once = true; }
     else { rc = copy_rows_in(b, b->vt, b->gv_stride, vtarget, b->nv, 0, b->N, where_in); if (rc) return rc; }
   }
+  const bool bound_once = b->pt_once || b->vt_once;
   if (!obs || !b->model->md.floating) {
     rc = do_launch(b, substeps, 0, false); if (rc) return rc;
     if (obs) rc = observe_impl(b, obs, 0, b->N, where_out, true);
-    if (b->bound_once) CK(cudaStreamSynchronize(b->stream));   // the caller may reuse its pinned target buffer on return
+    if (bound_once) CK(cudaStreamSynchronize(b->stream));   // the caller may reuse its pinned target buffer on return
     return rc;
   }
   // observation rows are written by the step kernel itself (no separate observe launch)
@@ -812,7 +846,7 @@ int rsb_batch_control_step(rsb_batch* b, const float* ptarget, const float* vtar
   if (where_out == RSB_HOST) {
     CK(cudaMemcpyAsync(obs, dst, (size_t)b->N * od * 4, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
-  } else if (b->bound_once) CK(cudaStreamSynchronize(b->stream));
+  } else if (bound_once) CK(cudaStreamSynchronize(b->stream));
   return RSB_OK;
 }
 
@@ -826,13 +860,12 @@ int rsb_batch_gym_configure(rsb_batch* b, const float* gc_init, const float* gv_
   std::vector<float> h((size_t)nq + nv + 2 * nj);
   std::memcpy(h.data(), gc_init, nq * 4); std::memcpy(h.data() + nq, gv_init, nv * 4);
   std::memcpy(h.data() + nq + nv, action_mean, nj * 4); std::memcpy(h.data() + nq + nv + nj, action_std, nj * 4);
-  if (!b->gym_const) {
-    CK(cudaMalloc((void**)&b->gym_const, h.size() * 4));
-    CK(cudaMalloc((void**)&b->gym_action, (size_t)b->N * nj * 4));
-    CK(cudaMalloc((void**)&b->gym_obs, (size_t)b->N * rsb_batch_ob_dim(b) * 4));
-    CK(cudaMalloc((void**)&b->gym_reward, (size_t)b->N * 4));
-    CK(cudaMalloc((void**)&b->gym_done, (size_t)b->N));
-  }
+  // every buffer under its own check: a retry after a failed allocation finishes the set instead of skipping it
+  if (!b->gym_const) CK(cudaMalloc((void**)&b->gym_const, h.size() * 4));
+  if (!b->gym_action) CK(cudaMalloc((void**)&b->gym_action, (size_t)b->N * nj * 4));
+  if (!b->gym_obs) CK(cudaMalloc((void**)&b->gym_obs, (size_t)b->N * rsb_batch_ob_dim(b) * 4));
+  if (!b->gym_reward) CK(cudaMalloc((void**)&b->gym_reward, (size_t)b->N * 4));
+  if (!b->gym_done) CK(cudaMalloc((void**)&b->gym_done, (size_t)b->N));
   CK(cudaMemcpyAsync(b->gym_const, h.data(), h.size() * 4, cudaMemcpyHostToDevice, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   b->gym.gc_init = b->gym_const; b->gym.gv_init = b->gym_const + nq; b->gym.action_mean = b->gym_const + nq + nv; b->gym.action_std = b->gym_const + nq + nv + nj;
@@ -853,6 +886,7 @@ int rsb_batch_gym_reset(rsb_batch* b) {
   int threads = 128, blocks = (b->N * 32 + threads - 1) / threads;
   rsb_gym_reset_kernel<<<blocks, threads, 0, b->stream>>>(b->gc, b->gv, b->pt, b->vt, b->gym, b->gc_stride, b->gv_stride, b->nq, b->nv, b->N);
   CK(cudaGetLastError());
+  b->kin_dirty = true;
   b->launches++;
   return RSB_OK;
 }
@@ -900,6 +934,8 @@ int rsb_batch_gym_step(rsb_batch* b, const float* action, int where_in, int subs
     if (reward && !a_rew) CK(cudaMemcpyAsync(reward, d_rew, (size_t)b->N * 4, cudaMemcpyDeviceToHost, b->stream));
     if (done && !a_done) CK(cudaMemcpyAsync(done, d_done, (size_t)b->N, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
+  } else if (where_in == RSB_HOST && act != b->gym_action) {
+    CK(cudaStreamSynchronize(b->stream));   // the action rows were read in place from pinned host memory: the caller may reuse them on return
   }
   return RSB_OK;
 }

@@ -41,6 +41,7 @@ constexpr int SEC_STRIDE = 36;      // (NSEC+1) padded
 constexpr int CT_WORDS = 16;        // per-contact shared record
 constexpr int EXT_WORDS = 12;       // external wrench row: body (int bits), force(3), torque(3), point in the body frame(3), 2 pad
 constexpr int MAX_PT_SLOTS = 2;     // candidate points per lane (npts <= 64)
+constexpr int HIST_WORDS = 6 * 32;  // Anderson history of the Gauss-Seidel sweep map (stage D)
 constexpr unsigned FULL = 0xffffffffu;
 
 enum BodyField {
@@ -104,7 +105,7 @@ __host__ __device__ constexpr BlobHeader make_blob_header(Dims d, int npts, int 
 
 // per-warp workspace layout (word offsets)
 struct WsLayout {
-  int o_gc, o_gv, o_tau, o_pt, o_vt, o_L, o_invd, o_rhs, o_z, o_ct, o_Y, o_lam, o_u, o_lim;   // persistent
+  int o_gc, o_gv, o_tau, o_pt, o_vt, o_L, o_invd, o_rhs, o_z, o_ct, o_Y, o_lam, o_u, o_lim, o_hist;   // persistent
   int o_h, o_b, o_pose;                                                                  // union A
   int o_G;                                                                               // union B
   int words;
@@ -128,6 +129,7 @@ __host__ __device__ constexpr WsLayout make_ws_layout(Dims d) {
   L.o_lam = o; o += 32;
   L.o_u = o; o += 13 * KMAX;                                      // per contact: G_ii (6), its inverse (6), friction
   L.o_lim = o; o += 4 * LMAX;                                     // joint-limit rows: dof, sign, violation
+  L.o_hist = o; o += HIST_WORDS;                                  // Anderson acceleration: u0, x, g, f, dG, dF (one value per constraint row each)
   // union: {h, b, poses} (stages A-C) overlaid by G (stages C-D)
   int ua = 0;
   L.o_h = o + ua; ua += nvp;
@@ -169,13 +171,15 @@ struct StepArgs {
   int* contact_pt;     // [N][KMAX]
   int* iters;          // [N]
   int* diverged;       // [N] 1 when the stored state holds a non-finite value (caller resets those environments)
+  float* resid;        // [N] largest impulse update of the last Gauss-Seidel sweep (< threshold: the solve converged)
   float* tau_applied;  // [N][gv_stride] generalized force actually applied in the last sub-step (getGeneralizedForce)
   float *dbg_M, *dbg_h, *dbg_R, *dbg_p;   // optional (integrate1 / getters)
   float* obs;          // optional [N][ob_dim]: RaisimGym observation row of the final state, written by this kernel
   int ob_dim;
   const float* ext;    // optional [num_envs][EXT_WORDS] external wrench rows (body, F world, T world, point in body frame); null = none
   unsigned* prof;      // optional [num_envs][4 sub-steps][8] SM-clock stamps at the stage boundaries (tools/balance_probe.py)
-  int phase_mask;      // bit0: stop after stage C (integrate1: no state update)
+  int phase_mask;      // bit0: stop after stage B (integrate1: no state update); bit2: kinematics only (stage A + getters' buffers,
+                       // the contact records of the last integrate() stay as they are)
   int substep_barrier; // 1: re-align the CTA's warps at every sub-step (instruction-cache locality experiment)
 };
 
@@ -363,6 +367,66 @@ __device__ __forceinline__ f3 solve_contact(const float* Gs, const float* Gi, f3
   return mk(p.lx, p.ly, p.lz);
 }
 
+
+// ------------------------------------------------------------------ Anderson acceleration ------
+// One step of Anderson acceleration (history of two differences) on the Gauss-Seidel sweep map, oracle step() "accel_m".
+// hist = [u0 | x | g1 | f1 | dG | dF] x 32 lanes: u0 = constraint velocities at lambda = 0, x = impulses at the start of this
+// sweep, (g1, f1) = output and residual of the previous sweep, (dG, dF) = the difference before that.  lam = this sweep's
+// output g; f = g - x.  hc = number of earlier sweeps in the history (0..2), fp = |f|^2 of the previous sweep.
+// Cold path (only problems that need more than accel_start - 2 sweeps get here): out of line.
+struct AAState { float lam, u, fp; int hc; };
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __noinline__ AAState anderson_step(float* hist, const float* s_G, int lane, int CR, float lam_c, float u_c, int hc, float fp, int extrapolate) {
+  float* h_u0 = hist; float* h_x = hist + 32; float* h_g1 = hist + 64; float* h_f1 = hist + 96; float* h_dg = hist + 128; float* h_df = hist + 160;
+  const bool on = lane < CR;
+  const float g = on ? lam_c : 0.f;
+  const float f = on ? g - h_x[lane] : 0.f;
+  const float fn = warp_sum(f * f);
+  const float g1 = on ? h_g1[lane] : 0.f, f1 = on ? h_f1[lane] : 0.f;
+  AAState o; o.lam = lam_c; o.u = u_c;
+  if (hc >= 1 && fn > 4.f * fp) hc = 0;            // residual doubled: drop the history, go on from the plain sweep output
+  else if (hc >= 1 && extrapolate) {
+    const float dFb = (hc >= 1) ? f - f1 : 0.f, dGb = g - g1;
+    const float dFa = (hc == 2 && on) ? h_df[lane] : 0.f, dGa = (hc == 2 && on) ? h_dg[lane] : 0.f;
+    const float a00 = warp_sum(dFa * dFa), a01 = warp_sum(dFa * dFb), r0 = warp_sum(dFa * f);
+    const float a11 = warp_sum(dFb * dFb), r1 = warp_sum(dFb * f);
+    const float ridge = 1e-10f * (a00 + a11) + 1e-30f;
+    float gam0 = 0.f, gam1 = 0.f; bool ok;
+    if (hc == 2) {   // 2 x 2 normal equations, elimination without pivoting (SPD + ridge)
+      const float p0 = a00 + ridge;
+      ok = p0 > 0.f;
+      const float m = a01 / p0;
+      const float p1 = (a11 + ridge) - m * a01, q1 = r1 - m * r0;
+      ok = ok && p1 > 0.f;
+      gam1 = q1 / p1; gam0 = (r0 - a01 * gam1) / p0;
+    } else {
+      const float p1 = a11 + ridge;
+      ok = p1 > 0.f;
+      gam1 = r1 / p1;
+    }
+    if (ok) {
+      const float xn = g - gam0 * dGa - gam1 * dGb;
+      float acc = on ? h_u0[lane] : 0.f;      // u = u0 + G x_next
+#pragma unroll 1
+      for (int b2 = 0; b2 < CR; b2++) {
+        const float xb = __shfl_sync(FULL, xn, b2);
+        if (on) acc += s_G[lane * GP + b2] * xb;
+      }
+      o.lam = on ? xn : lam_c; o.u = on ? acc : u_c;
+    }
+  }
+  if (on) {
+    if (hc >= 1) { h_dg[lane] = g - g1; h_df[lane] = f - f1; }
+    h_g1[lane] = g; h_f1[lane] = f;
+  }
+  o.hc = min(hc + 1, 2); o.fp = fn;
+  return o;
+}
+
 // ------------------------------------------------------------------ terrain --------------------
 __device__ __forceinline__ bool terrain_query(const TerrainDesc& t, int hm_offset, f3 P, float& dist, f3& n, int& pair) {
   if (t.type == 1) { dist = P.z - t.ground_z; n = mk(0.f, 0.f, 1.f); pair = 0; return true; }
@@ -465,7 +529,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
   float* const ws = reinterpret_cast<float*>(smem) + warp * WSO(words);
   float* s_gc = ws + WSO(o_gc); float* s_gv = ws + WSO(o_gv); float* s_tau = ws + WSO(o_tau); float* s_pt = ws + WSO(o_pt); float* s_vt = ws + WSO(o_vt);
   float* s_L = ws + WSO(o_L); float* s_invd = ws + WSO(o_invd); float* s_rhs = ws + WSO(o_rhs); float* s_z = ws + WSO(o_z); float* s_ct = ws + WSO(o_ct);
-  float* s_Y = ws + WSO(o_Y); float* s_lam = ws + WSO(o_lam); float* s_u = ws + WSO(o_u); float* s_lim = ws + WSO(o_lim);
+  float* s_Y = ws + WSO(o_Y); float* s_lam = ws + WSO(o_lam); float* s_u = ws + WSO(o_u); float* s_lim = ws + WSO(o_lim); float* s_hist = ws + WSO(o_hist);
   float* s_h = ws + WSO(o_h); float* s_b = ws + WSO(o_b); float* s_pose = ws + WSO(o_pose); float* s_G = ws + WSO(o_G);
 #undef WSO
 #undef HO
@@ -513,6 +577,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
     }
     __syncwarp();
     int K = 0, iters = 0;
+    float resid = 0.f;
 
 #pragma unroll 1
     for (int sub = 0; sub < args.substeps; sub++) {
@@ -707,6 +772,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       if (args.prof && lane == 0) args.prof[((size_t)env * 4 + (sub & 3)) * 8 + 1] = (unsigned)clock64();
       if (args.dbg_M)   // getters (integrate1): cold path, kept out of line to spare the instruction cache
         write_debug(args, env, lane, nv, nb, nvp, DLP, s_L, s_h, ddepth, danc, bvalid, s_pose, nbp);
+      if (args.phase_mask & 4) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncwarp(); break; }   // kinematics for the getters only
 
       // =========================== stage B: narrow phase ========================================
       float c_depth[SLOTS]; f3 c_pos[SLOTS], c_n[SLOTS]; int c_pair[SLOTS], c_body[SLOTS];
@@ -984,7 +1050,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
           u_c -= target;
         }
       }
-      iters = 0;
+      iters = 0; resid = 0.f;
       float lam_c = 0.f;
       if (CR > 0) {
         __syncwarp();      // h / b / poses are dead from here: G overlays them
@@ -1031,9 +1097,13 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         float sd_c = 1.f, sd_s = 0.f; int sd_v = 0;
         float err_ckpt = 3.0e38f;
         int next_ckpt = args.prm.stall_window;
+        int aa_hc = 0; float aa_fp = 0.f;          // Anderson history: entries kept, |f|^2 of the previous sweep
+        if (args.prm.accel_m > 0) s_hist[lane] = u_c;   // u0
 #pragma unroll 1
         for (int it = 0; it < args.prm.max_iter; it++) {
           float err = 0.f;
+          const bool aa_rec = args.prm.accel_m > 0 && it + 1 >= args.prm.accel_start - 2;   // the history starts two sweeps before the first extrapolation
+          if (aa_rec) s_hist[32 + lane] = lam_c;
 #pragma unroll 1
           for (int i = 0; i < K; i++) {
             const int i3 = 3 * i;
@@ -1062,9 +1132,14 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
             if (lane == r) lam_c = lr + dl;
             err = fmaxf(err, fabsf(dl));
           }
-          iters = it + 1;
+          iters = it + 1; resid = err;
           alpha = fmaxf(args.prm.alpha_min, alpha * args.prm.alpha_decay);
           if (err < args.prm.threshold) break;
+          if (aa_rec) {
+            __syncwarp();
+            const AAState st = anderson_step(s_hist, s_G, lane, CR, lam_c, u_c, aa_hc, aa_fp, it + 1 >= args.prm.accel_start ? 1 : 0);
+            lam_c = st.lam; u_c = st.u; aa_hc = st.hc; aa_fp = st.fp;
+          }
           if (it + 1 == next_ckpt) {      // stagnation exit (see rsb_params.stall_window)
             if (it + 1 >= 2 * args.prm.stall_window && err > args.prm.stall_ratio * err_ckpt) break;
             err_ckpt = err; next_ckpt += args.prm.stall_window;
@@ -1184,6 +1259,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
 #pragma unroll 1
       for (int i = lane; i < nj; i += 32) { o[4 + i] = s_gc[7 + i]; o[10 + nj + i] = s_gv[6 + i]; }
     }
+    if (args.phase_mask & 4) { __syncwarp(); continue; }   // kinematics only: contact records, iteration counts and flags of the last integrate() stay
     {   // failure detection: a non-finite coordinate or velocity marks the environment as diverged
       bool bad = false;
 #pragma unroll 1
@@ -1193,7 +1269,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       const bool any_bad = __any_sync(FULL, bad);
       if (lane == 0) args.diverged[env] = any_bad ? 1 : 0;
     }
-    if (lane == 0) { args.ncontacts[env] = K; args.iters[env] = iters; }
+    if (lane == 0) { args.ncontacts[env] = K; args.iters[env] = iters; args.resid[env] = resid; }
     if (lane < KMAX) {
       rsb_contact rc;
       int pt = -1;

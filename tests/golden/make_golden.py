@@ -12,7 +12,7 @@ from oracle.urdf_tables import load_tables
 from helpers import random_state
 
 OUT = os.path.join(ROOT, "tests", "golden")
-PRM = dict(threshold=1e-6, stall_window=0)
+PRM = dict(threshold=1e-6, stall_window=0, accel_m=0)     # the published method as is: plain sweeps, maxIter semantics
 
 
 def make(name, urdf, n, seed, terrain, base_z, tau_scale, steps):

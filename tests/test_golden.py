@@ -22,7 +22,7 @@ def _terrain(obj, g):
 @pytest.mark.parametrize("name,urdf", CASES)
 def test_oracle_reproduces_golden(name, urdf):
     g = np.load(os.path.join(GOLD, name + ".npz"))
-    o = Oracle(load_tables(os.path.join(RSC, urdf)), params=dict(threshold=1e-6, stall_window=0))
+    o = Oracle(load_tables(os.path.join(RSC, urdf)), params=dict(threshold=1e-6, stall_window=0, accel_m=0))
     _terrain(o, g)
     a, b = g["gc0"].copy(), g["gv0"].copy()
     d = o.step(a, b, tau_ff=g["tau"], debug=True)
@@ -41,7 +41,7 @@ def test_kernel_matches_golden(name, urdf):
     g = np.load(os.path.join(GOLD, name + ".npz"))
     n = g["gc0"].shape[0]
     bt = capi.Batch(capi.Model(os.path.join(RSC, urdf)), n)
-    bt.set_params(threshold=1e-6, stall_window=0)
+    bt.set_params(threshold=1e-6, stall_window=0, accel_m=0)
     _terrain(bt, g)
     bt.set_control_mode(capi.FORCE_AND_TORQUE)
     bt.set_state(g["gc0"].astype(np.float32), g["gv0"].astype(np.float32))

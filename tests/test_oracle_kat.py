@@ -630,8 +630,8 @@ def test_terrain_atlas_gives_every_environment_its_own_map():
 
 
 def test_anderson_accelerated_gauss_seidel_same_fixed_point_fewer_sweeps(atlas_tables):
-    """Round-2 candidate (oracle only, accel_m = 0 by default): Anderson acceleration of the Gauss-Seidel
-    sweep map.  Redundant box-corner contacts of the standing humanoid: same solution, a third of the sweeps."""
+    """Anderson acceleration of the Gauss-Seidel sweep map (accel_m = 2 by default in oracle and kernel).
+    Redundant box-corner contacts of the standing humanoid: same solution, a third of the sweeps."""
     t = atlas_tables
     n = 64
     rng = np.random.default_rng(3)
@@ -639,7 +639,7 @@ def test_anderson_accelerated_gauss_seidel_same_fixed_point_fewer_sweeps(atlas_t
     gv = np.zeros((n, 36))
     kp = np.r_[np.zeros(6), 400 * np.ones(30)]; kd = np.r_[np.zeros(6), 10 * np.ones(30)]
     tgt = gc.copy()
-    plain = Oracle(t, params=dict(threshold=1e-7, stall_window=0)); plain.set_ground(0.0)
+    plain = Oracle(t, params=dict(threshold=1e-7, stall_window=0, accel_m=0)); plain.set_ground(0.0)
     plain.step(gc, gv, n_steps=60, ptarget=tgt, vtarget=np.zeros((n, 36)), kp=kp, kd=kd)          # settle onto the feet
     acc = Oracle(t, params=dict(threshold=1e-7, stall_window=0, accel_m=2)); acc.set_ground(0.0)
     a, b = gc.copy(), gv.copy(); c, d = gc.copy(), gv.copy()
@@ -652,7 +652,7 @@ def test_anderson_accelerated_gauss_seidel_same_fixed_point_fewer_sweeps(atlas_t
     assert np.abs(b - d)[both].max() < 2e-5          # same fixed point (velocity level), to the solver threshold
     # default parameters leave quickly converging problems untouched (acceleration starts at sweep 6)
     t2 = load_tables(SPHERE_URDF)
-    o1, o2 = Oracle(t2), Oracle(t2, params=dict(accel_m=2))
+    o1, o2 = Oracle(t2, params=dict(accel_m=0)), Oracle(t2, params=dict(accel_m=2))
     for o in (o1, o2):
         o.set_ground(0.0)
     g1 = np.array([[0, 0, 0.1, 1, 0, 0, 0.0]]); v1 = np.array([[0.5, 0, -0.2, 0, 0, 0.0]]); g2, v2 = g1.copy(), v1.copy()
