@@ -221,6 +221,20 @@ int rsb_comm_init(rsb_batch** batches, int ndev, rsb_comm** out);             /*
 int rsb_comm_allgather_obs(rsb_comm* c, float* const* obs_all_per_device);     /* observe + ncclAllGather on every device     */
 void rsb_comm_destroy(rsb_comm* c);
 
+/* ---- multi-GPU, one process per GPU: the observation all-gather FUSED into the step kernel over NVLink peer memory ----
+ * Every rank allocates two gathered-rows buffers [world * num_envs][ob_dim] and one counter row unsigned[world]
+ * (rsb_peer_buffer_create: cudaMalloc + CUDA IPC handle), ships the 64-byte handles to its peers over any host channel
+ * (torch.distributed / MPI / a pipe), maps theirs (rsb_peer_buffer_open) and hands all pointers to its batch.  From then on
+ * a control step that returns observation rows on the device also stores every finished row straight into every rank's
+ * buffer (parity = control step & 1) while the kernel is still running, and bumps a counter on every rank as each CTA ends;
+ * rsb_batch_wait_observation_peers() enqueues the wait for all ranks' rows of the last step.  No NCCL call on the data path. */
+int rsb_peer_buffer_create(int device, size_t bytes, void** dev_ptr, unsigned char* handle64 /* may be NULL */);
+int rsb_peer_buffer_open(int device, const unsigned char* handle64, void** dev_ptr);
+int rsb_peer_buffer_close(void* dev_ptr);
+int rsb_peer_buffer_destroy(void* dev_ptr);
+int rsb_batch_set_observation_peers(rsb_batch* b, int world, int rank, void* const* obs_all /* [2 * world] */, void* const* flags /* [world] */);
+int rsb_batch_wait_observation_peers(rsb_batch* b, int* buffer_parity /* may be NULL */);
+
 /* ---- RaisimGym task on the device (raisimGymTorch VectorizedEnvironment.hpp / envs/rsg_anymal/Environment.hpp,
  *      [RECALL]): pTarget = action * std + mean; reward = torque_coeff * |tau|^2 + forward_vel_coeff * min(4, v_body_x);
  *      an episode terminates on any contact whose local body is not in foot_bodies (reward += terminal_reward, state reset) -- */

@@ -41,27 +41,46 @@ class _Debug(C.Structure):
                 + [(n, C.c_void_p) for n in ("warm_pt", "warm_imp", "tau_applied", "nlimits", "lim_dof", "lim_lambda", "resid")])
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        build()
-        _lib = C.CDLL(_LIB_PATH)
-        _lib.orc_create.restype = C.c_void_p
-        _lib.orc_create.argtypes = [C.POINTER(_ModelDesc), C.c_int]
-        _lib.orc_destroy.argtypes = [C.c_void_p]
-        _lib.orc_set_params.argtypes = [C.c_void_p, C.c_void_p]
-        _lib.orc_set_ground.argtypes = [C.c_void_p, C.c_double]
-        _lib.orc_set_heightmap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
-        _lib.orc_clear_terrain.argtypes = [C.c_void_p]
-        _lib.orc_step.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p]
-        _lib.orc_solve_one.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
-        _lib.orc_set_point_mu.argtypes = [C.c_void_p, C.c_void_p]
-        _lib.orc_get_flops.argtypes = [C.c_void_p, C.c_int]
-        _lib.orc_get_counts.argtypes = [C.c_void_p, C.c_int]
-    return _lib
+def _declare(L):
+    L.orc_create.restype = C.c_void_p
+    L.orc_create.argtypes = [C.POINTER(_ModelDesc), C.c_int]
+    L.orc_destroy.argtypes = [C.c_void_p]
+    L.orc_set_params.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_set_ground.argtypes = [C.c_void_p, C.c_double]
+    L.orc_set_heightmap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    L.orc_set_heightmaps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_clear_terrain.argtypes = [C.c_void_p]
+    L.orc_step.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p]
+    L.orc_solve_one.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    L.orc_set_point_mu.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_get_flops.argtypes = [C.c_void_p, C.c_int]
+    L.orc_get_counts.argtypes = [C.c_void_p, C.c_int]
+    return L
+
+
+def lib(which="parity"):
+    """parity: liboracle.so, the checker (-ffp-contract=off, portable ISA: bit-stable predicates).
+    native: liboracle_native.so, the TIMING build of the same source for bench.py's CPU arm (-O3 -march=native, FMA
+    contraction on), compiled on the machine it is timed on; falls back to the parity build if that fails."""
+    if which not in _libs:
+        if which == "native":
+            path = os.path.join(_HERE, "liboracle_native.so")
+            try:
+                subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "liboracle_native.so"])
+                _libs[which] = _declare(C.CDLL(path))
+            except Exception:
+                _libs[which] = lib("parity")
+        else:
+            build()
+            _libs[which] = _declare(C.CDLL(_LIB_PATH))
+    return _libs[which]
+
+
+def native_build_available():
+    return lib("native") is not lib("parity")
 
 
 def _p(a):
@@ -71,7 +90,8 @@ def _p(a):
 class Oracle:
     """CPU restatement of raisim::World::integrate() for a batch of independent environments."""
 
-    def __init__(self, tables, precision="f64", params=None):
+    def __init__(self, tables, precision="f64", params=None, build="parity"):
+        self.L = lib(build)
         self.t = tables
         self.nb, self.nq, self.nv = tables["nb"], tables["nq"], tables["nv"]
         self._keep = {k: np.ascontiguousarray(tables[k], dtype=(np.int32 if tables[k].dtype.kind == "i" else np.float64))
@@ -81,29 +101,29 @@ class Oracle:
         for k, a in self._keep.items():
             setattr(d, k, a.ctypes.data)
         self.precision = precision
-        self.h = lib().orc_create(C.byref(d), {"f64": 0, "f32": 1, "count": 2}[precision])
-        self.kmax = lib().orc_kmax()
+        self.h = self.L.orc_create(C.byref(d), {"f64": 0, "f32": 1, "count": 2}[precision])
+        self.kmax = self.L.orc_kmax()
         self.params = dict(DEFAULT_PARAMS)
         self.set_params(**(params or {}))
         self.warm_pt = self.warm_imp = None      # contact cache carried across step() calls (per environment)
 
     def __del__(self):
         if getattr(self, "h", None):
-            lib().orc_destroy(self.h)
+            self.L.orc_destroy(self.h)
             self.h = None
 
     def set_params(self, **kw):
         self.params.update(kw)
         arr = np.array([float(self.params[k]) for k in PARAM_ORDER], dtype=np.float64)
-        lib().orc_set_params(self.h, _p(arr))
+        self.L.orc_set_params(self.h, _p(arr))
 
     def set_ground(self, z=0.0):
-        lib().orc_set_ground(self.h, float(z))
+        self.L.orc_set_ground(self.h, float(z))
 
     def set_heightmap(self, xs, ys, x_size, y_size, cx, cy, heights):
         hh = np.ascontiguousarray(heights, dtype=np.float64).reshape(-1)
         assert hh.size == xs * ys
-        lib().orc_set_heightmap(self.h, xs, ys, x_size, y_size, cx, cy, _p(hh))
+        self.L.orc_set_heightmap(self.h, xs, ys, x_size, y_size, cx, cy, _p(hh))
 
     def set_heightmaps(self, x_size, y_size, cx, cy, heights, env_map):
         """terrain atlas: heights [count, ys, xs], env_map [n] -> every environment collides with its own map"""
@@ -111,18 +131,17 @@ class Oracle:
         count, ys, xs = hh.shape
         em = np.ascontiguousarray(env_map, dtype=np.int32)
         assert em.min() >= 0 and em.max() < count
-        lib().orc_set_heightmaps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int]
-        lib().orc_set_heightmaps(self.h, count, xs, ys, x_size, y_size, cx, cy, _p(hh), em.ctypes.data, len(em))
+        self.L.orc_set_heightmaps(self.h, count, xs, ys, x_size, y_size, cx, cy, _p(hh), em.ctypes.data, len(em))
 
     def clear_terrain(self):
-        lib().orc_clear_terrain(self.h)
+        self.L.orc_clear_terrain(self.h)
 
     def set_collision_friction(self, collision_body, mu):
         """friction of every candidate point of one collision body (mu < 0: default material)"""
         if not hasattr(self, "_pt_mu"):
             self._pt_mu = np.full(self.t["npts"], -1.0)
         self._pt_mu[np.asarray(self.t["pt_coll"]) == collision_body] = mu
-        lib().orc_set_point_mu(self.h, _p(self._pt_mu))
+        self.L.orc_set_point_mu(self.h, _p(self._pt_mu))
 
     def step(self, gc, gv, n_steps=1, tau_ff=None, ptarget=None, vtarget=None, kp=None, kd=None, nthreads=0, debug=False, ext=None):
         """gc [n,nq], gv [n,nv] float64 C-contiguous, updated IN PLACE.  Returns debug dict or None.
@@ -158,7 +177,7 @@ class Oracle:
             dbg.ext_force = None if ef is None else ef.ctypes.data
             dbg.ext_torque = None if et is None else et.ctypes.data
             dbg.ext_point = (C.c_double * 3)(*(np.zeros(3) if ep is None else np.asarray(ep, np.float64)))
-        lib().orc_step(self.h, n, n_steps, _p(gc), _p(gv), _p(tau_ff), _p(ptarget), _p(vtarget), _p(kp), _p(kd),
+        self.L.orc_step(self.h, n, n_steps, _p(gc), _p(gv), _p(tau_ff), _p(ptarget), _p(vtarget), _p(kp), _p(kd),
                        int(nthreads), C.byref(dbg))
         return out if debug else None
 
@@ -171,7 +190,7 @@ class Oracle:
     def solve_one(self, G, c, mu):
         G = np.ascontiguousarray(G, np.float64); c = np.ascontiguousarray(c, np.float64)
         lam = np.zeros(3)
-        lib().orc_solve_one(self.h, _p(G), _p(c), float(mu), _p(lam))
+        self.L.orc_solve_one(self.h, _p(G), _p(c), float(mu), _p(lam))
         return lam
 
 

@@ -103,6 +103,7 @@ EXPORTED = [
     "rsb_batch_get_contact_points", "rsb_batch_get_solver_iterations", "rsb_batch_get_diverged", "rsb_batch_get_solver_residual", "rsb_batch_update_kinematics", "rsb_batch_device_ptrs", "rsb_batch_launch_count",
     "rsb_batch_ob_dim", "rsb_batch_observe", "rsb_batch_control_step",
     "rsb_batch_gym_configure", "rsb_batch_gym_reset", "rsb_batch_gym_step",
+    "rsb_peer_buffer_create", "rsb_peer_buffer_open", "rsb_peer_buffer_close", "rsb_peer_buffer_destroy", "rsb_batch_set_observation_peers", "rsb_batch_wait_observation_peers",
     "rsb_comm_init", "rsb_comm_allgather_obs", "rsb_comm_destroy", "rsb_terrain_generate", "rsb_heightmap_read_text", "rsb_heightmap_read_png",
 ]
 
@@ -177,6 +178,12 @@ def lib():
         L.rsb_comm_allgather_obs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.rsb_comm_destroy.argtypes = [C.c_void_p]
         L.rsb_terrain_generate.argtypes = [C.POINTER(TerrainProperties), C.c_void_p]
+        L.rsb_peer_buffer_create.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]
+        L.rsb_peer_buffer_open.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.rsb_peer_buffer_close.argtypes = [C.c_void_p]
+        L.rsb_peer_buffer_destroy.argtypes = [C.c_void_p]
+        L.rsb_batch_set_observation_peers.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.rsb_batch_wait_observation_peers.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
@@ -482,6 +489,20 @@ class Batch:
     def gym_step(self, action, substeps, obs, reward, done):
         pa, w1 = _ptr(action); po, w2 = _ptr(obs); pr, _ = _ptr(reward); pd, _ = _ptr(done)
         _ck(lib().rsb_batch_gym_step(self.h, pa, w1, substeps, po, pr, pd, w2))
+
+    def set_observation_peers(self, world, rank, obs_ptrs, flag_ptrs):
+        """fused observation all-gather: obs_ptrs [2 * world] / flag_ptrs [world] raw device pointers valid in this process"""
+        if world == 0:
+            _ck(lib().rsb_batch_set_observation_peers(self.h, 0, 0, None, None)); return
+        a = (C.c_void_p * (2 * world))(*[C.c_void_p(int(x)) for x in obs_ptrs])
+        f = (C.c_void_p * world)(*[C.c_void_p(int(x)) for x in flag_ptrs])
+        _ck(lib().rsb_batch_set_observation_peers(self.h, world, rank, a, f))
+
+    def wait_observation_peers(self):
+        """enqueue the wait for every rank's rows of the last control step; returns the buffer parity that holds them"""
+        par = C.c_int()
+        _ck(lib().rsb_batch_wait_observation_peers(self.h, C.byref(par)))
+        return par.value
 
     def observe(self, out=None, env_begin=0, env_count=None):
         n = self.n - env_begin if env_count is None else env_count

@@ -41,6 +41,11 @@ struct rsb_batch {
   const float* vt_bound = nullptr;   // same for the velocity targets
   int vt_bound_stride = 0;
   bool pt_once = false, vt_once = false;   // zero-copy control step: the kernel copies the rows it read into pt / vt, then THAT binding ends
+  // fused observation all-gather over NVLink peer memory (rsb_batch_set_observation_peers)
+  int peer_world = 0, peer_rank = 0;
+  float* peer_obs[MAX_PEERS][2] = {};     // [peer][buffer parity]: gathered-rows buffers, double-buffered by control step
+  unsigned* peer_flag[MAX_PEERS] = {};    // [peer]: arrival counters [world]
+  unsigned peer_epoch = 0;                // control steps signalled so far
   bool kin_dirty = true;             // the getters' buffers (M, h, poses) do not describe the current state
   unsigned* prof = nullptr;          // rsb_internal_set_profile
   int* hmap_index = nullptr;         // terrain atlas: map index per environment
@@ -229,7 +234,7 @@ static cudaError_t dispatch_spec(const rsb_batch* b, const StepArgs& a) {
   return launch_step<WPC, 2, 0, 0, 0, 0, 0, 0>(a, b->grid, b->smem_bytes, b->stream);
 }
 
-static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug, float* obs_dev = nullptr) {
+static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug, float* obs_dev = nullptr, bool peers = false) {
   StepArgs a{};
   a.num_envs = b->N; a.substeps = substeps;
   a.gc_stride = b->gc_stride; a.gv_stride = b->gv_stride;
@@ -247,6 +252,11 @@ static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug, flo
   a.phase_mask = phase_mask; a.prof = b->prof;
   a.ext = b->ext_active ? b->ext : nullptr;
   a.obs = obs_dev; a.ob_dim = rsb_batch_ob_dim(b);
+  if (peers && b->peer_world > 0 && obs_dev && phase_mask == 0) {
+    a.peer_world = b->peer_world; a.peer_rank = b->peer_rank;
+    for (int p = 0; p < b->peer_world; p++) { a.peer_obs[p] = b->peer_obs[p][b->peer_epoch & 1]; a.peer_flag[p] = b->peer_flag[p]; }
+    b->peer_epoch++;
+  }
   {
     const char* e = getenv("RSB_SUBSTEP_BARRIER");
     const int level = e ? atoi(e) : 1;
@@ -842,7 +852,7 @@ int rsb_batch_control_step(rsb_batch* b, const float* ptarget, const float* vtar
     }
     dst = b->obs_staging;
   }
-  rc = do_launch(b, substeps, 0, false, dst); if (rc) return rc;
+  rc = do_launch(b, substeps, 0, false, dst, where_out == RSB_DEVICE); if (rc) return rc;
   if (where_out == RSB_HOST) {
     CK(cudaMemcpyAsync(obs, dst, (size_t)b->N * od * 4, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
@@ -937,6 +947,65 @@ int rsb_batch_gym_step(rsb_batch* b, const float* action, int where_in, int subs
   } else if (where_in == RSB_HOST && act != b->gym_action) {
     CK(cudaStreamSynchronize(b->stream));   // the action rows were read in place from pinned host memory: the caller may reuse them on return
   }
+  return RSB_OK;
+}
+
+// ---- fused observation all-gather over NVLink peer memory (one process per GPU or one process for all) ----
+// Buffers that other processes map: plain cudaMalloc memory + a CUDA IPC handle (64 bytes) to ship over any host channel.
+int rsb_peer_buffer_create(int device, size_t bytes, void** dev_ptr, unsigned char* handle64) {
+  if (!dev_ptr || bytes == 0) return fail(RSB_ERR_INVALID, "bad arguments to rsb_peer_buffer_create");
+  CK(cudaSetDevice(device));
+  void* p = nullptr;
+  CK(cudaMalloc(&p, bytes));
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess && handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e == cudaSuccess) std::memcpy(handle64, &h, 64);
+  }
+  if (e != cudaSuccess) { cudaFree(p); return fail(RSB_ERR_CUDA, std::string("rsb_peer_buffer_create: ") + cudaGetErrorString(e)); }
+  *dev_ptr = p;
+  return RSB_OK;
+}
+int rsb_peer_buffer_open(int device, const unsigned char* handle64, void** dev_ptr) {
+  if (!dev_ptr || !handle64) return fail(RSB_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  CK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return RSB_OK;
+}
+int rsb_peer_buffer_close(void* dev_ptr) { if (dev_ptr) CK(cudaIpcCloseMemHandle(dev_ptr)); return RSB_OK; }
+int rsb_peer_buffer_destroy(void* dev_ptr) { if (dev_ptr) CK(cudaFree(dev_ptr)); return RSB_OK; }
+
+// obs_all[2 * world]: for every rank r, its two gathered-rows buffers (parity 0, 1), each [world * num_envs][ob_dim] float32, as
+// device pointers valid in THIS process (own allocations, IPC mappings, or peer-enabled pointers of other devices of this process);
+// flags[world]: rank r's arrival counters, unsigned[world], zero-initialised.  From now on every control step that returns
+// observation rows on the device also stores them into the buffer (step parity) of every rank and bumps flags[r][rank] once
+// per finished CTA.  world = 0 switches the fused gather off.  Every rank must run the same num_envs.
+int rsb_batch_set_observation_peers(rsb_batch* b, int world, int rank, void* const* obs_all, void* const* flags) {
+  if (!b) return fail(RSB_ERR_INVALID, "null batch");
+  if (world == 0) { b->peer_world = 0; return RSB_OK; }
+  if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || !obs_all || !flags) return fail(RSB_ERR_INVALID, "bad arguments to rsb_batch_set_observation_peers");
+  if (!b->model->md.floating) return fail(RSB_ERR_UNSUPPORTED, "fused observation rows need a floating-base robot");
+  for (int p = 0; p < world; p++) if (!obs_all[2 * p] || !obs_all[2 * p + 1] || !flags[p]) return fail(RSB_ERR_INVALID, "null peer buffer");
+  CK(cudaSetDevice(b->device));
+  CK(cudaStreamSynchronize(b->stream));
+  for (int p = 0; p < world; p++) { b->peer_obs[p][0] = (float*)obs_all[2 * p]; b->peer_obs[p][1] = (float*)obs_all[2 * p + 1]; b->peer_flag[p] = (unsigned*)flags[p]; }
+  b->peer_world = world; b->peer_rank = rank; b->peer_epoch = 0;
+  return RSB_OK;
+}
+// Enqueue (on the batch's stream) the wait for the rows of the LAST control step of every rank to have landed in this rank's
+// buffer; *buffer_parity (optional) = which of this rank's two buffers holds them.
+int rsb_batch_wait_observation_peers(rsb_batch* b, int* buffer_parity) {
+  if (!b || b->peer_world <= 0 || b->peer_epoch == 0) return fail(RSB_ERR_INVALID, "no fused observation gather in flight");
+  CK(cudaSetDevice(b->device));
+  const unsigned expected = b->peer_epoch * (unsigned)b->grid;
+  rsb_peer_wait_kernel<<<1, 32, 0, b->stream>>>(b->peer_flag[b->peer_rank], b->peer_world, expected, 20000000000ll /* ~10 s of SM clocks */);
+  CK(cudaGetLastError());
+  b->launches++;
+  if (buffer_parity) *buffer_parity = (int)((b->peer_epoch - 1) & 1);
   return RSB_OK;
 }
 

@@ -42,6 +42,7 @@ constexpr int CT_WORDS = 16;        // per-contact shared record
 constexpr int EXT_WORDS = 12;       // external wrench row: body (int bits), force(3), torque(3), point in the body frame(3), 2 pad
 constexpr int MAX_PT_SLOTS = 2;     // candidate points per lane (npts <= 64)
 constexpr int HIST_WORDS = 6 * 32;  // Anderson history of the Gauss-Seidel sweep map (stage D)
+constexpr int MAX_PEERS = 8;        // GPUs of one NVSwitch domain that receive this GPU's observation rows (fused all-gather)
 constexpr unsigned FULL = 0xffffffffu;
 
 enum BodyField {
@@ -178,6 +179,11 @@ struct StepArgs {
   int ob_dim;
   const float* ext;    // optional [num_envs][EXT_WORDS] external wrench rows (body, F world, T world, point in body frame); null = none
   unsigned* prof;      // optional [num_envs][4 sub-steps][8] SM-clock stamps at the stage boundaries (tools/balance_probe.py)
+  // fused observation all-gather: every rank's kernel stores its observation rows straight into every peer's
+  // [world * num_envs][ob_dim] buffer over NVLink (peer memory mapped into this process), then signals one counter per peer
+  float* peer_obs[MAX_PEERS];      // peer p's gathered-rows buffer of this step (null = not in use)
+  unsigned* peer_flag[MAX_PEERS];  // peer p's arrival counters [world]: += 1 per finished CTA of this rank
+  int peer_world, peer_rank;
   int phase_mask;      // bit0: stop after stage B (integrate1: no state update); bit2: kinematics only (stage A + getters' buffers,
                        // the contact records of the last integrate() stay as they are)
   int substep_barrier; // 1: re-align the CTA's warps at every sub-step (instruction-cache locality experiment)
@@ -1258,6 +1264,16 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       }
 #pragma unroll 1
       for (int i = lane; i < nj; i += 32) { o[4 + i] = s_gc[7 + i]; o[10 + nj + i] = s_gv[6 + i]; }
+      if (args.peer_world > 0) {   // fused all-gather: the finished row goes to every GPU of the job (this one included) over NVLink
+        __syncwarp();
+        const size_t row = ((size_t)args.peer_rank * args.num_envs + env) * args.ob_dim;
+#pragma unroll 1
+        for (int pr = 0; pr < args.peer_world; pr++) {
+          float* dst = args.peer_obs[pr] + row;
+#pragma unroll 1
+          for (int i = lane; i < args.ob_dim; i += 32) dst[i] = o[i];   // re-read of this warp's own row: L1/L2 hit
+        }
+      }
     }
     if (args.phase_mask & 4) { __syncwarp(); continue; }   // kinematics only: contact records, iteration counts and flags of the last integrate() stay
     {   // failure detection: a non-finite coordinate or velocity marks the environment as diverged
@@ -1294,6 +1310,26 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       args.contact_pt[(size_t)env * KMAX + lane] = pt;
     }
     __syncwarp();
+  }
+  if (args.peer_world > 0 && args.obs) {
+    // every row this CTA stored must be visible on the peers before they see the arrival count (release at system scope)
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < args.peer_world) atomicAdd_system(args.peer_flag[threadIdx.x] + args.peer_rank, 1u);
+  }
+}
+
+// Arrival wait of the fused observation all-gather: lane r returns when rank r's `expected` CTAs have signalled, i.e. when every
+// row of that rank's step has landed in THIS GPU's gathered buffer.  Bounded: a dead peer traps instead of hanging the GPU.
+__global__ void rsb_peer_wait_kernel(const unsigned* flags, int world, unsigned expected, long long max_cycles) {
+  if ((int)threadIdx.x >= world) return;
+  const volatile unsigned* f = flags + threadIdx.x;
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if ((int)(v - expected) >= 0) break;
+    if (clock64() - t0 > max_cycles) __trap();
   }
 }
 

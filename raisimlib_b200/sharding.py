@@ -32,6 +32,90 @@ def allgather_observations(obs_local, out=None):
     return out
 
 
+class ObservationGather:
+    """The path's one collective, one process per GPU.
+
+    mode "peer" (default on NVLink boxes): the all-gather is FUSED into the step kernel.  Every rank owns two gathered-rows
+    buffers [world * n, ob_dim] (double-buffered by control step) and a row of arrival counters, all plain device memory exported
+    through CUDA IPC; `torch.distributed` only ships the 64-byte handles once, at set-up.  During a control step each finished
+    observation row is stored straight into every rank's buffer over NVLink while the kernel is still running; `wait()` enqueues
+    a tiny kernel that returns when every rank's rows of that step have landed.  No NCCL call on the data path.
+    mode "nccl": `all_gather_into_tensor` after the step (the baseline this replaces; also what the gloo CPU test drives)."""
+
+    def __init__(self, batch, world, rank, n, ob_dim, mode="peer", device=None):
+        self.batch, self.world, self.rank, self.n, self.od, self.mode = batch, world, rank, n, ob_dim, mode
+        self.steps = 0
+        self._opened, self._own = [], []
+        if mode == "peer":
+            from . import capi
+            import ctypes as C
+            L = capi.lib()
+            dev = torch.cuda.current_device() if device is None else device
+            mine = []                                        # (pointer, handle bytes): two row buffers + the counter row
+            for nbytes in (world * n * ob_dim * 4, world * n * ob_dim * 4, 256):
+                ptr, h = C.c_void_p(), (C.c_ubyte * 64)()
+                capi._ck(L.rsb_peer_buffer_create(dev, nbytes, C.byref(ptr), h))
+                mine.append((ptr.value, bytes(h)))
+                self._own.append(ptr.value)
+            everyone = [None] * world
+            dist.all_gather_object(everyone, [h for _, h in mine])
+            obs_ptrs, flag_ptrs = [], []
+            for r in range(world):
+                ptrs = []
+                for k in range(3):
+                    if r == rank:
+                        ptrs.append(mine[k][0])
+                    else:
+                        q = C.c_void_p()
+                        hb = (C.c_ubyte * 64).from_buffer_copy(everyone[r][k])
+                        capi._ck(L.rsb_peer_buffer_open(dev, hb, C.byref(q)))
+                        self._opened.append(q.value)
+                        ptrs.append(q.value)
+                obs_ptrs += ptrs[:2]; flag_ptrs.append(ptrs[2])
+            batch.set_observation_peers(world, rank, obs_ptrs, flag_ptrs)
+            self.rows = [self._view(mine[0][0]), self._view(mine[1][0])]
+            dist.barrier()
+        else:
+            self.rows = [torch.empty((world * n, ob_dim), dtype=torch.float32, device="cuda" if torch.cuda.is_available() else "cpu") for _ in range(2)]
+
+    def _view(self, ptr):
+        class _Raw:
+            def __init__(s, p, shape):
+                s.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (int(p), False), "version": 2}
+        return torch.as_tensor(_Raw(ptr, (self.world * self.n, self.od)), device="cuda")
+
+    def gather(self, obs_local):
+        """call right after the control step that produced obs_local; returns the [world * n, ob_dim] rows of that step (valid
+        in stream order on the batch's stream)"""
+        self.steps += 1
+        if self.mode == "peer":
+            return self.rows[self.batch.wait_observation_peers()]
+        out = self.rows[self.steps & 1]
+        allgather_observations(obs_local, out)
+        return out
+
+    def report(self):
+        return {"mode": self.mode, "collective": ("observation rows stored into every rank's buffer by the step kernel over NVLink peer memory (CUDA IPC), "
+                                                  "arrival counters + one wait kernel per step; no NCCL call on the data path") if self.mode == "peer"
+                else "torch.distributed all_gather_into_tensor (NCCL) after the step, on the launching stream",
+                "bytes_per_step_per_rank": int(self.n * self.od * 4 * self.world)}
+
+    def close(self):
+        if self.mode == "peer":
+            from . import capi
+            torch.cuda.synchronize()
+            dist.barrier()
+            self.batch.set_observation_peers(0, 0, None, None)
+            self.rows = None
+            L = capi.lib()
+            for q in self._opened:
+                L.rsb_peer_buffer_close(q)
+            dist.barrier()
+            for q in self._own:
+                L.rsb_peer_buffer_destroy(q)
+            self._opened, self._own = [], []
+
+
 class SharedHostRows:
     """A [world * rows_per_rank, width] float32 array in POSIX shared memory that every rank maps and page-locks.
 

@@ -142,9 +142,14 @@ def test_one_step_state_and_impulses(capi, urdf, terrain, base_z, tau_scale):
     assert np.isfinite(g1).all() and np.isfinite(v1).all()
     # compare where both solvers converged on the same contact set; cycling Gauss-Seidel cases
     # (both sides hit max_iter; see DESIGN.md "solver convergence") have no unique answer
-    conv = (pts == d["c_pt"]).all(1) & (it < 150) & (d["iters"] < 150)
-    print(f"converged+same-contact envs: {conv.sum()}/{n}; K mean {cnt.mean():.2f}; iters gpu {it.mean():.1f} oracle {d['iters'].mean():.1f}")
-    assert conv.mean() > 0.9
+    res = bt.solver_residual()
+    same = (pts == d["c_pt"]).all(1)
+    conv = same & (res < THRESH) & (d["resid"] < THRESH)
+    print(f"same-contact envs {same.sum()}/{n}, of those converged on both sides {conv.sum()}; non-converged gpu {100 * (res >= THRESH).mean():.2f}% oracle "
+          f"{100 * (d['resid'] >= THRESH).mean():.2f}%; K mean {cnt.mean():.2f}; sweeps gpu {it.mean():.1f} oracle {d['iters'].mean():.1f}")
+    # accelerated sweeps: random drops (knee + foot on one shank, box feet) converge too -- round 1 excluded up to 10 % here
+    assert (res >= THRESH).mean() < 0.01 and (d["resid"] >= THRESH).mean() < 0.01
+    assert conv.mean() > 0.98
     ev = np.abs(v1 - b)[conv]; eq = np.abs(g1 - a)[conv]
     scale_v = 1.0 + np.abs(b[conv])
     print(f"one-step errors: gv max {ev.max():.2e} (rel {np.max(ev / scale_v):.2e}) median {np.median(ev.max(1)):.2e}; gc max {eq.max():.2e}")
@@ -185,8 +190,11 @@ def test_trajectory_50_steps(capi):
     e = np.abs(gN - a).max(1); e32 = np.abs(c - a).max(1)
     print(f"50-step gc error vs f64 oracle: median {np.median(e):.2e} p90 {np.quantile(e, .9):.2e} max {e.max():.2e} | f32 oracle: median {np.median(e32):.2e} p90 {np.quantile(e32, .9):.2e}")
     assert np.isfinite(gN).all()
+    print(f"   p99 {np.quantile(e, .99):.2e} | f32 oracle p99 {np.quantile(e32, .99):.2e}")
     assert np.median(e) < 2e-5          # stated tolerance: 2e-5 (m, rad) median after 50 steps
-    assert np.quantile(e, 0.9) < 5e-4
+    assert np.quantile(e, 0.9) < 1e-4
+    # the tail is contact-set chaos (a foot that lands one step earlier): bounded against the float32 build of the oracle itself
+    assert np.quantile(e, 0.99) < max(5e-3, 5 * np.quantile(e32, 0.99))
     assert np.median(e) < 5 * np.median(e32) + 1e-6   # no worse than float32 arithmetic itself
 
 
@@ -377,27 +385,223 @@ def test_cpp_kinematic_getters_example():
     assert out.returncode == 0, out.stdout + out.stderr
 
 
-def test_stagnation_exit_matches_oracle(capi):
-    """Default solver parameters (stall_window = 8): same exit decisions as the oracle, short tail."""
+def test_default_solver_matches_oracle_on_random_drops(capi):
+    """Library defaults (Anderson-accelerated sweeps from sweep 6, stagnation window 16, threshold 1e-6) on a brutal random-drop
+    batch (knee + foot contacts on one shank, bodies on the ground): same sweep counts as the oracle, < 1 % non-converged."""
     n = 1024
-    t, bt, o64, o32, gc, gv, tau = _setup(capi, "anymal_c_like.urdf", n, seed=111, base_z=0.35, params=dict(stall_window=8, stall_ratio=0.5))
+    t, bt, o64, o32, gc, gv, tau = _setup(capi, "anymal_c_like.urdf", n, seed=111, base_z=0.35, params=dict(stall_window=16, stall_ratio=0.5, accel_m=2, accel_start=6))
     bt.integrate(1)
-    it = bt.solver_iterations()
+    it = bt.solver_iterations(); res = bt.solver_residual()
     g1, v1 = bt.get_state()
     a, b = gc.copy(), gv.copy()
     d = o64.step(a, b, tau_ff=tau, debug=True)
     pts = bt.contact_points()
     same = (pts == d["c_pt"]).all(1)
-    # the 150-iteration tail is gone on both sides (a slowly but steadily converging problem may still run long)
-    assert (it > 48).mean() < 0.04 and (d["iters"] > 48).mean() < 0.04 and (it >= 150).mean() < 0.005
     agree = (it == d["iters"])[same].mean()
-    print(f"stagnation exit: max iters gpu {it.max()} oracle {d['iters'].max()}; identical iteration counts in {100 * agree:.1f}% of envs")
-    # cycling / slowly converging problems are chaotic: float32 vs float64 may leave at a different window
-    assert agree > 0.85
-    quick = same & (d["iters"] <= 12)
-    assert (np.abs(it - d["iters"])[quick] <= 1).mean() > 0.95
-    ok = same & (it == d["iters"]) & (it < 16)                  # converged before any stall check could fire
-    assert np.abs(v1 - b)[ok].max() < 5e-3
+    print(f"default solver: sweeps gpu mean {it.mean():.2f} max {it.max()} | oracle mean {d['iters'].mean():.2f} max {d['iters'].max()}; identical counts in "
+          f"{100 * agree:.1f}% of envs; non-converged gpu {100 * (res >= THRESH).mean():.2f}% oracle {100 * (d['resid'] >= THRESH).mean():.2f}%")
+    assert (res >= THRESH).mean() < 0.01 and (d["resid"] >= THRESH).mean() < 0.01
+    assert it.max() < 150 and it.mean() < 1.15 * d["iters"].mean() + 0.5
+    assert agree > 0.85                                   # float32 vs float64 leave the loop one sweep apart now and then
+    assert (np.abs(it - d["iters"])[same] <= 2).mean() > 0.97
+    ok = same & (res < THRESH) & (d["resid"] < THRESH)
+    ev = np.abs(v1 - b)[ok].max(1)
+    print(f"   one-step gv error on converged envs: median {np.median(ev):.2e} p99 {np.quantile(ev, .99):.2e} max {ev.max():.2e}")
+    assert np.median(ev) < 2e-5 and np.quantile(ev, 0.99) < 2e-3
+    # plain sweeps (accel_m = 0) reach the same fixed point: the acceleration changes the path, not the answer
+    bt.set_params(accel_m=0, stall_window=0)
+    bt.set_state(gc.astype(np.float32), gv.astype(np.float32))
+    bt.integrate(1)
+    it0 = bt.solver_iterations(); res0 = bt.solver_residual(); v0 = bt.get_state()[1]
+    both = (res < THRESH) & (res0 < THRESH)
+    print(f"   plain sweeps: mean {it0.mean():.2f} max {it0.max()}, non-converged {100 * (res0 >= THRESH).mean():.2f}%; |dv| accelerated vs plain max {np.abs(v1 - v0)[both].max():.2e}")
+    assert it.mean() < 0.8 * it0.mean()
+    assert np.quantile(np.abs(v1 - v0)[both].max(1), 0.99) < 1e-4
+
+
+def test_atlas_standing_trajectory_and_heightmap(capi):
+    """Config 4 regime, library defaults: the Atlas-like humanoid standing on box feet (8 redundant corner contacts, the case that
+    needed 55 plain sweeps per step) for 50 steps, and dropped onto a height map; gc / gv against the float64 oracle."""
+    n = 256
+    path = os.path.join(RSC, "atlas_like.urdf")
+    t = load_tables(path)
+    rng = np.random.default_rng(301)
+    gc0 = np.zeros(37); gc0[2] = 0.95; gc0[3] = 1.0
+    gc = np.tile(gc0, (n, 1)); gc[:, 7:] += rng.uniform(-0.05, 0.05, (n, 30)); gv = np.zeros((n, 36))
+    kp = np.r_[np.zeros(6), 400.0 * np.ones(30)]; kd = np.r_[np.zeros(6), 10.0 * np.ones(30)]
+    tgt = gc.copy()
+    prm = dict(threshold=THRESH)
+    o = Oracle(t, params=prm); o.set_ground(0.0)
+    o.step(gc, gv, n_steps=60, ptarget=tgt, vtarget=np.zeros((n, 36)), kp=kp, kd=kd)        # settle onto the feet (CPU)
+    gc32, gv32 = gc.astype(np.float32), gv.astype(np.float32)
+    bt = capi.Batch(capi.Model(path), n)
+    bt.set_ground(0.0); bt.set_params(**prm)
+    bt.set_pd_gains(kp, kd); bt.set_pd_target(tgt.astype(np.float32), np.zeros((n, 36), np.float32))
+    bt.set_state(gc32, gv32)
+    a, b = gc32.astype(np.float64), gv32.astype(np.float64)
+    o32 = Oracle(t, precision="f32", params=prm); o32.set_ground(0.0)
+    c, d = a.copy(), b.copy()
+    sweeps, ncv = [], []
+    for k in range(10):
+        bt.integrate(5)
+        sweeps.append(bt.solver_iterations()); ncv.append(bt.solver_residual() >= THRESH)
+        dbg = o.step(a, b, n_steps=5, ptarget=tgt.astype(np.float32).astype(np.float64), vtarget=np.zeros((n, 36)), kp=kp, kd=kd, debug=True)
+    o32.step(c, d, n_steps=50, ptarget=tgt.astype(np.float32).astype(np.float64), vtarget=np.zeros((n, 36)), kp=kp, kd=kd)
+    g, v = bt.get_state()
+    _, cnt = bt.contacts()
+    sweeps = np.array(sweeps); ncv = np.array(ncv)
+    e = np.abs(g - a).max(1); e32 = np.abs(c - a).max(1); ev = np.abs(v - b).max(1)
+    print(f"atlas standing 50 steps: K {cnt.mean():.2f}, sweeps mean {sweeps.mean():.1f} p99 {np.quantile(sweeps, .99):.0f} max {sweeps.max()} (oracle last {dbg['iters'].mean():.1f}), "
+          f"non-converged {100 * ncv.mean():.2f}%; gc err median {np.median(e):.2e} p99 {np.quantile(e, .99):.2e} max {e.max():.2e} | f32 oracle median {np.median(e32):.2e} "
+          f"p99 {np.quantile(e32, .99):.2e}; gv err median {np.median(ev):.2e} p99 {np.quantile(ev, .99):.2e}")
+    assert cnt.mean() > 6                                   # standing on the box corners
+    assert sweeps.mean() <= 15 and ncv.mean() < 0.01         # VERDICT r1 item 1: <= 15 mean sweeps, < 1 % non-converged
+    assert np.median(e) < 2e-5 and np.quantile(e, 0.99) < max(1e-3, 5 * np.quantile(e32, 0.99))
+    # on a height map: random drops, 20 steps
+    t2, bt2, o64, o32b, gc2, gv2, tau2 = _setup(capi, "atlas_like.urdf", n, seed=302, terrain="hm", base_z=0.95, tau_scale=2.0, vel=0.3, joint_scale=0.2,
+                                                params=dict(stall_window=16, accel_m=2, accel_start=6))
+    # upright-ish: small random tilt instead of a random quaternion, so that the feet (not the head) meet the terrain
+    q = np.c_[np.ones(n), 0.1 * rng.standard_normal((n, 3))]; q /= np.linalg.norm(q, axis=1, keepdims=True)
+    gc2[:, 3:7] = q.astype(np.float32)
+    bt2.set_state(gc2.astype(np.float32), gv2.astype(np.float32))
+    a, b = gc2.astype(np.float32).astype(np.float64), gv2.copy()
+    c, d = a.copy(), b.copy()
+    bt2.integrate(20)
+    g, v = bt2.get_state()
+    dbg = o64.step(a, b, n_steps=20, tau_ff=tau2, debug=True)
+    o32b.step(c, d, n_steps=20, tau_ff=tau2)
+    _, cnt = bt2.contacts()
+    res = bt2.solver_residual()
+    e = np.abs(g - a).max(1); e32 = np.abs(c - a).max(1)
+    print(f"atlas on a height map, 20 steps: K {cnt.mean():.2f} (oracle {dbg['ncontacts'].mean():.2f}), sweeps {bt2.solver_iterations().mean():.1f}, non-converged {100 * (res >= THRESH).mean():.2f}%; "
+          f"gc err median {np.median(e):.2e} p90 {np.quantile(e, .9):.2e} p99 {np.quantile(e, .99):.2e} | f32 oracle median {np.median(e32):.2e} p99 {np.quantile(e32, .99):.2e}")
+    assert cnt.sum() > n                                     # contact-rich
+    assert (res >= THRESH).mean() < 0.01
+    assert np.median(e) < 2e-5 and np.quantile(e, 0.99) < max(2e-3, 5 * np.quantile(e32, 0.99))
+
+
+def test_bench_workload_parity(capi):
+    """What bench.py measures is what is tested: the exact headline workload (4096 environments, 513 x 513 height field, PD stance
+    with target jitter, library-default solver), settled on the GPU, then 1 and 20 control steps (4 fused sub-steps each) against
+    the oracle from the same state: contact lists, gc, gv."""
+    import bench
+    n = 4096
+    wl = bench.Workload("c3", 0, n)
+    hm = bench.HM
+    path = os.path.join(RSC, wl.urdf)
+    bt = capi.Batch(capi.Model(path), n)
+    bt.set_params(**bench.SOLVER)
+    bt.set_heightmap(hm["xs"], hm["ys"], hm["size"], hm["size"], 0.0, 0.0, wl.H)
+    bt.set_pd_gains(wl.kp, wl.kd)
+    bt.set_state(wl.gc.astype(np.float32), wl.gv.astype(np.float32))
+    vt = np.zeros((n, 18), np.float32)
+    ring32 = wl.ring.astype(np.float32)
+    for k in range(wl.settle + 5):
+        bt.set_pd_target(ring32[k % bench.RING], vt)
+        bt.integrate(bench.SUBSTEPS)
+    g0, v0 = bt.get_state()
+    t = load_tables(path)
+    o64 = Oracle(t, params=bench.SOLVER); o32 = Oracle(t, precision="f32", params=bench.SOLVER)
+    for o in (o64, o32):
+        o.set_heightmap(hm["xs"], hm["ys"], hm["size"], hm["size"], 0.0, 0.0, wl.H.astype(np.float64))
+    k0 = wl.settle + 5
+    # ---- one control step ----
+    tg = ring32[k0 % bench.RING]
+    bt.set_pd_target(tg, vt); bt.integrate(bench.SUBSTEPS)
+    g1, v1 = bt.get_state(); pts = bt.contact_points(); ct, cnt = bt.contacts(); it = bt.solver_iterations(); res = bt.solver_residual()
+    a, b = g0.astype(np.float64), v0.astype(np.float64)
+    d = o64.step(a, b, n_steps=bench.SUBSTEPS, ptarget=tg.astype(np.float64), vtarget=vt.astype(np.float64), kp=wl.kp, kd=wl.kd, debug=True)
+    c, e_ = g0.astype(np.float64), v0.astype(np.float64)
+    d32 = o32.step(c, e_, n_steps=bench.SUBSTEPS, ptarget=tg.astype(np.float64), vtarget=vt.astype(np.float64), kp=wl.kp, kd=wl.kd, debug=True)
+    same = (pts == d["c_pt"]).all(1) & (cnt == d["ncontacts"])
+    same32 = (pts == d32["c_pt"]).all(1)
+    eq = np.abs(g1 - a).max(1); ev = np.abs(v1 - b).max(1); eq32 = np.abs(c - a).max(1); ev32 = np.abs(e_ - b).max(1)
+    print(f"bench workload, 1 control step: K {cnt.mean():.2f} hist {np.bincount(cnt, minlength=9).tolist()}, sweeps gpu {it.mean():.2f} max {it.max()} oracle {d['iters'].mean():.2f}; "
+          f"non-converged {100 * (res >= 1e-6).mean():.2f}%; identical contact lists (4th sub-step) vs f64 oracle {100 * same.mean():.2f}% vs f32 oracle {100 * same32.mean():.2f}%")
+    print(f"   gc err median {np.median(eq):.2e} p99 {np.quantile(eq, .99):.2e} max {eq.max():.2e} (f32 oracle: {np.median(eq32):.2e} / {np.quantile(eq32, .99):.2e} / {eq32.max():.2e}); "
+          f"gv err median {np.median(ev):.2e} p99 {np.quantile(ev, .99):.2e} max {ev.max():.2e} (f32 oracle: {np.median(ev32):.2e} / {np.quantile(ev32, .99):.2e} / {ev32.max():.2e})")
+    assert (res >= 1e-6).mean() < 0.01 and it.max() <= 150
+    assert same.mean() > 0.99                                # the few that differ have a foot within float32 rounding of touching down
+    assert np.median(eq) < 2e-6 and np.quantile(eq, 0.99) < max(2e-5, 5 * np.quantile(eq32, 0.99))
+    assert np.median(ev) < 5e-5 and np.quantile(ev, 0.99) < max(5e-3, 5 * np.quantile(ev32, 0.99))
+    # impulses of the last sub-step where the lists agree
+    live = same[:, None] & (d["c_pt"] >= 0)
+    ln_gpu = np.einsum("ekj,ekj->ek", ct["impulse"], ct["normal"])
+    en = np.abs(ln_gpu - d["c_lambda"][:, :, 2])[live]
+    assert np.quantile(en, 0.99) < 2e-3 * max(1.0, np.abs(d["c_lambda"][:, :, 2][live]).max())
+    # ---- 20 control steps ----
+    for k in range(1, 20):
+        tg = ring32[(k0 + k) % bench.RING]
+        bt.set_pd_target(tg, vt); bt.integrate(bench.SUBSTEPS)
+        o64.step(a, b, n_steps=bench.SUBSTEPS, ptarget=tg.astype(np.float64), vtarget=vt.astype(np.float64), kp=wl.kp, kd=wl.kd)
+        o32.step(c, e_, n_steps=bench.SUBSTEPS, ptarget=tg.astype(np.float64), vtarget=vt.astype(np.float64), kp=wl.kp, kd=wl.kd)
+    g20, v20 = bt.get_state()
+    eq = np.abs(g20 - a).max(1); eq32 = np.abs(c - a).max(1)
+    print(f"   20 control steps (80 sub-steps): gc err median {np.median(eq):.2e} p90 {np.quantile(eq, .9):.2e} p99 {np.quantile(eq, .99):.2e} | f32 oracle median {np.median(eq32):.2e} "
+          f"p90 {np.quantile(eq32, .9):.2e} p99 {np.quantile(eq32, .99):.2e}")
+    assert np.isfinite(g20).all()
+    assert np.median(eq) < 2e-5                              # the stated tolerance (DESIGN.md section 5)
+    assert np.quantile(eq, 0.9) < max(1e-3, 5 * np.quantile(eq32, 0.9))
+    assert np.quantile(eq, 0.99) < max(2e-2, 5 * np.quantile(eq32, 0.99))   # contact-set chaos: bounded by float32 arithmetic itself
+
+
+def test_fallen_quadrupeds_default_solver(capi):
+    """Config 2 regime: quadrupeds lying on flat ground under random joint torques (bodies, knees and feet in contact, joints at
+    their stops); state prepared by the oracle, one control step with fresh torques on both sides."""
+    import bench
+    n = 1024
+    wl = bench.Workload("c2", 0, n)
+    path = os.path.join(RSC, wl.urdf)
+    t = load_tables(path)
+    o = Oracle(t, params=bench.SOLVER); o.set_ground(0.0)
+    a, b = wl.gc.copy(), wl.gv.copy()
+    for k in range(wl.settle):
+        o.step(a, b, n_steps=bench.SUBSTEPS, tau_ff=wl.ring[k % bench.RING])
+    g0, v0 = a.astype(np.float32), b.astype(np.float32)
+    bt = capi.Batch(capi.Model(path), n)
+    bt.set_ground(0.0); bt.set_params(**bench.SOLVER)
+    bt.set_control_mode(capi.FORCE_AND_TORQUE)
+    bt.set_state(g0, v0)
+    tau = wl.ring[wl.settle % bench.RING].astype(np.float32)
+    bt.set_generalized_force(tau)
+    bt.integrate(1)
+    g1, v1 = bt.get_state(); pts = bt.contact_points(); _, cnt = bt.contacts(); it = bt.solver_iterations(); res = bt.solver_residual()
+    a, b = g0.astype(np.float64), v0.astype(np.float64)
+    d = o.step(a, b, n_steps=1, tau_ff=tau.astype(np.float64), debug=True)
+    same = (pts == d["c_pt"]).all(1)
+    conv = same & (res < 1e-6) & (d["resid"] < 1e-6)
+    ev = np.abs(v1 - b)[conv].max(1)
+    print(f"fallen quadrupeds: base z median {np.median(g0[:, 2]):.3f}, K {cnt.mean():.2f} hist {np.bincount(cnt, minlength=9).tolist()}, sweeps gpu {it.mean():.2f} (p99 {np.quantile(it, .99):.0f}, max {it.max()}) "
+          f"oracle {d['iters'].mean():.2f}; non-converged gpu {100 * (res >= 1e-6).mean():.2f}% oracle {100 * (d['resid'] >= 1e-6).mean():.2f}%; same lists {100 * same.mean():.2f}%; "
+          f"gv err median {np.median(ev):.2e} p99 {np.quantile(ev, .99):.2e}")
+    assert np.median(g0[:, 2]) < 0.2 and cnt.mean() > 3
+    assert (res >= 1e-6).mean() < 0.01 and (d["resid"] >= 1e-6).mean() < 0.01
+    assert same.mean() > 0.98 and conv.mean() > 0.97
+    assert np.median(ev) < 5e-5 and np.quantile(ev, 0.99) < 5e-3
+
+
+def test_kinematic_getters_keep_contact_records(capi):
+    """kinematic getters after integrate() must not replace the last step's contacts, impulses and sweep
+    count (upstream's getContacts() stays valid across getFramePosition() etc.), and the lazy getters follow the state."""
+    n = 64
+    t, bt, o64, o32, gc, gv, tau = _setup(capi, "anymal_c_like.urdf", n, seed=401, base_z=0.5, joint_scale=0.2)
+    bt.integrate(3)
+    ct0, cnt0 = bt.contacts(); it0 = bt.solver_iterations(); res0 = bt.solver_residual()
+    assert cnt0.sum() > 0 and np.abs(ct0["impulse"]).max() > 0
+    M = bt.mass_matrix(); h = bt.nonlinearities(); R, p = bt.body_poses()      # lazy: a kinematics-only pass at the CURRENT state
+    ct1, cnt1 = bt.contacts()
+    assert np.array_equal(cnt0, cnt1) and np.array_equal(ct0["impulse"], ct1["impulse"]) and np.array_equal(ct0["position"], ct1["position"])
+    assert np.array_equal(it0, bt.solver_iterations()) and np.array_equal(res0, bt.solver_residual())
+    g, v = bt.get_state()
+    bt2 = capi.Batch(bt.model, n)
+    bt2.set_ground(0.0); bt2.set_state(g, v)
+    bt2.integrate1()
+    assert np.array_equal(M, bt2.mass_matrix()) and np.array_equal(p, bt2.body_poses()[1]) and np.allclose(h, bt2.nonlinearities(), atol=1e-4)
+    l0 = bt.launch_count()
+    bt.mass_matrix(); bt.body_poses()
+    assert bt.launch_count() == l0                           # nothing changed since: no relaunch
+    bt.integrate(1)
+    assert not np.array_equal(bt.body_poses()[1], p)         # ... and after a step the getters describe the new state
 
 
 def test_control_step_equals_separate_calls(capi):
@@ -484,10 +688,19 @@ def test_contact_cap_parity_atlas(capi):
     a, b = gc32.astype(np.float64), np.zeros((n, 36))
     d = o32.step(a, b, debug=True)
     assert (cnt == 8).sum() > n // 2                       # the cap is actually exercised
-    shallow = ((np.abs(d["c_depth"]) < MARGIN) & (d["c_pt"] >= 0)).any(1)
-    mism = (pts != d["c_pt"]).any(1) & ~shallow
-    # near-equal depths at the cap boundary can legitimately swap under float32 rounding: allow a few
-    assert mism.mean() < 0.05, f"{mism.sum()} of {n} capped contact lists differ"
+    # Every list must be the 8 deepest candidates.  The only legitimate difference: candidates whose depth equals the cut-off (the
+    # 8th deepest) to float32 rounding may swap -- checked candidate by candidate against depths recomputed from the oracle's poses.
+    P = d["p"][:, t["pt_body"]] + np.einsum("ebij,bj->ebi", d["R"][:, t["pt_body"]], t["pt_pos"])
+    depth = t["pt_rad"][None, :] - P[:, :, 2]                # plane z = 0
+    n_bad = 0
+    for e in range(n):
+        if (pts[e] == d["c_pt"][e]).all():
+            continue
+        cut = np.sort(depth[e][depth[e] > 0])[::-1][7]
+        diff = set(pts[e][pts[e] >= 0]) ^ set(d["c_pt"][e][d["c_pt"][e] >= 0])
+        if any(abs(depth[e][k] - cut) > MARGIN for k in diff):
+            n_bad += 1
+    assert n_bad == 0, f"{n_bad} capped contact lists differ beyond depth ties at the cut-off"
     assert (np.diff(np.where(pts >= 0, pts, 10**6), axis=1) > 0).all()   # candidate order
 
 
@@ -793,3 +1006,57 @@ def test_terrain_atlas_matches_oracle(capi):
     bt.integrate(2)
     gb, vb = bt.get_state()
     assert np.array_equal(ga, gb) and np.array_equal(va, vb)
+
+
+def _peer_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import torch, torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)      # host channel for the 64-byte IPC handles only
+    from raisimlib_b200 import capi as c
+    from raisimlib_b200.sharding import ObservationGather
+    n = 300                                                            # not a multiple of the CTA size
+    m = c.Model(os.path.join(RSC, "anymal_c_like.urdf"))
+    bt = c.Batch(m, n, device=rank)
+    bt.set_ground(0.0)
+    rng = np.random.default_rng(500 + rank)
+    gc = np.tile(ANYMAL_GC0, (n, 1)); gc[:, 2] = rng.uniform(0.5, 0.7, n); gc[:, 7:] += rng.uniform(-0.2, 0.2, (n, 12))
+    bt.set_state(gc.astype(np.float32), (0.3 * rng.standard_normal((n, 18))).astype(np.float32))
+    og = ObservationGather(bt, world, rank, n, bt.ob_dim(), mode="peer", device=rank)
+    obs = torch.empty((n, bt.ob_dim()), dtype=torch.float32, device=f"cuda:{rank}")
+    out = []
+    for k in range(3):                                                 # three steps: both buffer parities, counters accumulate
+        bt.control_step(None, 2, obs)
+        rows = og.gather(obs)
+        bt.sync()
+        out.append((obs.cpu().numpy().copy(), rows.cpu().numpy().copy()))
+        dist.barrier()                                                 # nobody overwrites a buffer a peer is still copying out
+    og.close()
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fused_peer_observation_gather_two_gpus(capi):
+    """SURVEY 8e without NCCL on the data path: every rank's step kernel stores its observation rows into every rank's buffer over
+    NVLink peer memory (CUDA IPC), counters + a wait kernel close the exchange; rows must equal each rank's own rows, in rank order."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world = 2
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, 29733, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for k in range(3):
+        ref = np.concatenate([got[r][k][0] for r in range(world)])     # every rank's own rows of step k, in rank order
+        for r in range(world):
+            assert np.array_equal(got[r][k][1], ref), (k, r)

@@ -33,6 +33,12 @@ def _worker(rank, world, port, total, q):
     lo, hi = shard_range(total, world, rank)
     local = torch.from_numpy(_obs_rows(gc[lo:hi], gv[lo:hi]))
     full = allgather_observations(local)
+    # the gather object bench.py drives: "nccl" mode = the collective after the step (gloo here), two alternating row buffers
+    from raisimlib_b200.sharding import ObservationGather
+    og = ObservationGather(None, world, rank, hi - lo, 34, mode="nccl")
+    r1 = og.gather(local).clone(); r2 = og.gather(2 * local)
+    assert torch.equal(r1, full) and torch.equal(r2, 2 * full) and r1.data_ptr() != r2.data_ptr()
+    assert og.report()["mode"] == "nccl"
     # host-side consumers: every rank writes its own block of a shared, mapped array; one barrier makes all rows visible
     from raisimlib_b200.sharding import SharedHostRows
     sh = SharedHostRows(f"test_{port}", world, rank, hi - lo, 34, register=False)
