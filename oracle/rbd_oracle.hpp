@@ -31,7 +31,9 @@ constexpr int KMAX = 8;            // contacts kept per environment (deepest KMA
 constexpr int LMAX = 4;            // joint-limit constraints kept per environment (first LMAX violated joints) == RSB_LMAX
 constexpr int RMAX = 3 * KMAX + LMAX;   // constraint rows
 constexpr int NSEC = 32;           // sections per refinement round of the slip search
-constexpr int NROUNDS = 3;         // rounds: bracket 2*pi/32^(r+1), then one secant step (error ~ bracket^2 = 4e-8 rad)
+constexpr int NROUNDS = 2;         // 32-section rounds: bracket 2*pi/32^(r+1) = 6e-3 rad after both (or after the local fan alone)
+constexpr int ACCEL_MAX_RESETS = 2; // Anderson acceleration is switched off for the rest of a solve after this many history drops
+constexpr int NREF = 2;            // then NREF regula-falsi steps (Illinois variant): direction exact to float32 rounding (< 1e-6 rad)
 
 template <typename T> struct V3 { T x, y, z; };
 template <typename T> inline V3<T> operator+(V3<T> a, V3<T> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
@@ -514,7 +516,7 @@ template <typename T> class Sim {
       if (pick >= 0) {
         lo_c = dc[pick]; lo_s = ds[pick]; hi_c = dc[pick + 1]; hi_s = ds[pick + 1]; glo = gk[pick]; ghi = gk[pick + 1];
         base_c = lo_c; base_s = lo_s; have = true; best = lk[pick];
-        r_start = 2;
+        r_start = NROUNDS;
         if (counts) counts[3]++;
       }
     }
@@ -550,8 +552,28 @@ template <typename T> class Sim {
       lo_c = cs0; lo_s = sn0; hi_c = cs1; hi_s = sn1; glo = gk[pick]; ghi = gk[pick + 1];
       base_c = cs0; base_s = sn0; have = true; best = lk[pick];
     }
-    if (prm.slip_bisect) {   // 5 * (NROUNDS - 1) halvings: same final bracket width as the 32-section rounds
-      for (int it = 0; it < 5 * (NROUNDS - 1); it++) {
+    if (!prm.slip_bisect && have) {
+      // regula falsi inside the final bracket, Illinois variant (an end kept twice has its value halved): every step is ONE
+      // probe, the direction is the normalised chord point.  2 steps from a 6e-3 rad bracket: exact to float32 rounding.
+      T wlo = glo, whi = ghi; int side = 0;
+      T cs = lo_c, sn = lo_s; V3<T> l = best;
+      for (int st = 0; st < NREF; st++) {
+        T tt = wlo / (wlo - whi);
+        T c2 = lo_c + tt * (hi_c - lo_c), s2 = lo_s + tt * (hi_s - lo_s);
+        T inv = T(1) / std::sqrt(c2 * c2 + s2 * s2);
+        c2 *= inv; s2 *= inv;
+        T g2, f2; V3<T> l2;
+        if (!eval(c2, s2, g2, f2, l2)) break;
+        cs = c2; sn = s2; l = l2;
+        if (g2 < T(0)) { lo_c = c2; lo_s = s2; wlo = g2; if (side == -1) whi *= T(0.5); side = -1; }
+        else { hi_c = c2; hi_s = s2; whi = g2; if (side == 1) wlo *= T(0.5); side = 1; }
+      }
+      lam = l;
+      if (sd) { sd->valid = true; sd->cs = cs; sd->sn = sn; }
+      return;
+    }
+    if (prm.slip_bisect) {   // CPU-tuned variant: 10 halvings of the round-0 bracket (2*pi/32768), then the secant step below
+      for (int it = 0; it < 10; it++) {
         T mc = lo_c + hi_c, ms = lo_s + hi_s;
         T inv = T(1) / std::sqrt(mc * mc + ms * ms);
         mc *= inv; ms *= inv;
@@ -666,7 +688,7 @@ template <typename T> class Sim {
       // Anderson acceleration state: sweep outputs g_k and residuals f_k = g_k - x_k of the last accel_m + 1 sweeps
       const int AM = std::min(std::max(prm.accel_m, 0), 3);
       std::vector<T> hx, hg, hf;          // current x, and history rows [slot][C]
-      int hcount = 0;
+      int hcount = 0, resets = 0;
       if (AM > 0) { hx.assign(C, T(0)); hg.assign((size_t)(AM + 1) * C, T(0)); hf.assign((size_t)(AM + 1) * C, T(0)); }
       for (int it = 0; it < prm.max_iter; it++) {
         T err = 0;
@@ -703,7 +725,7 @@ template <typename T> class Sim {
         ws.iters = it + 1; ws.resid = err;
         alpha = std::max(T(prm.alpha_min), alpha * T(prm.alpha_decay));
         if (err < T(prm.threshold)) break;
-        if (AM > 0 && it + 1 >= prm.accel_start - AM) {   // the history starts AM sweeps before the first extrapolation: nothing is kept (or paid for) on quickly converging problems
+        if (AM > 0 && it + 1 >= prm.accel_start - AM && resets < ACCEL_MAX_RESETS) {   // the history starts AM sweeps before the first extrapolation: nothing is kept (or paid for) on quickly converging problems
           // push (g, f) of this sweep; slots are a shift register, newest last
           if (hcount == AM + 1) {
             for (int sl = 0; sl < AM; sl++) for (int a = 0; a < C; a++) { hg[(size_t)sl * C + a] = hg[(size_t)(sl + 1) * C + a]; hf[(size_t)sl * C + a] = hf[(size_t)(sl + 1) * C + a]; }
@@ -718,7 +740,8 @@ template <typename T> class Sim {
           hcount++;
           if (hcount > 1 && fn > T(4) * fp) {          // residual doubled: drop the history, continue from the plain sweep output
             for (int a = 0; a < C; a++) { hg[a] = g[a]; hf[a] = f[a]; }
-            hcount = 1;
+            hcount = 1; resets++;      // after ACCEL_MAX_RESETS such failures the plain sweeps finish the solve (rank-deficient
+                                       // contact sets have a continuum of fixed points along which an extrapolation can run away)
           } else if (hcount > 1 && it + 1 >= prm.accel_start) {
             const int md = hcount - 1;                 // differences available
             T A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, rhs[3] = {0, 0, 0}, gam[3] = {0, 0, 0};

