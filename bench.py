@@ -40,7 +40,7 @@ RING = 8            # distinct PD-target / torque sets cycled through (synthetic
 SETTLE = 40         # untimed control steps run while BUILDING the workload: robots are dropped from 0.75 m and must stand
                     # on the terrain before warm-up starts, whatever --warmup the caller passes
 L2_FLUSH_BYTES = 256 << 20
-SOLVER = dict(threshold=1e-6)   # everything else at the library defaults (rsb_params_default): accel_m=2, accel_start=6, stall_window=16
+SOLVER = dict(threshold=1e-6)   # everything else at the library defaults (rsb_params_default): accel_m=2, accel_start=6, stall_window=8, stall_reg=0.02
 
 
 def value_noise(rng, n, size_cells):
@@ -507,7 +507,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_string(n),
                        "envs_per_gpu": n, "substeps_per_step": SUBSTEPS, "l2": "flushed between timed iterations (256 MiB write)",
-                       "solver": "library defaults: Anderson-accelerated per-contact Gauss-Seidel (accel_m=2 from sweep 6), threshold 1e-6, maxIter 150, stagnation exit window 16",
+                       "solver": "library defaults: Anderson-accelerated per-contact Gauss-Seidel (accel_m=2 from sweep 6), threshold 1e-6, maxIter 150, stagnation window 8 with compliant fallback (stall_reg 0.02)",
                        "mean_contacts_per_env": kbar, "contacts_histogram_rank0": st["contacts_histogram"],
                        "mean_solver_sweeps": float(stats[1]), "max_solver_sweeps": float(stats[4]), "sweeps_histogram_rank0": st["sweeps_histogram"],
                        "non_converged_fraction": float(stats[2]), "standing_fraction": float(stats[3]),

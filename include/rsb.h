@@ -59,10 +59,10 @@ typedef struct rsb_params {
   float rest_threshold; /* restitution threshold velocity               (0.01)           */
   /* Stagnation exit of the Gauss-Seidel loop (NOT in the reference; stall_window = 0 restores the
    * plain maxIter behaviour): every stall_window iterations, stop if the largest impulse update has
-   * not dropped below stall_ratio x its value one window earlier.  A safety net for the rare contact
-   * sets on which the published per-contact rule enters a limit cycle (< 0.2 % of the problems of
-   * fallen robots with the accelerated sweeps; never on standing ones); see DESIGN.md section 5. */
-  int stall_window;     /*                                               (16)             */
+   * not dropped below stall_ratio x its value one window earlier (then see stall_reg below).  A safety
+   * net for the contact sets on which the published per-contact rule enters a limit cycle (~1 % of the
+   * problems of fallen robots even with the accelerated sweeps; none of standing ones); DESIGN.md 5. */
+  int stall_window;     /*                                               (8)              */
   float stall_ratio;    /*                                               (0.5)            */
   int joint_limits;     /* enforce URDF <limit lower upper> as unilateral rows of the same solve (1) */
   /* Anderson acceleration of the Gauss-Seidel sweep map (NOT in the reference; accel_m = 0 restores the plain sweeps of the
@@ -72,6 +72,11 @@ typedef struct rsb_params {
    * third of the sweeps and quickly converging problems never reach accel_start.  DESIGN.md section 5. */
   int accel_m;          /* 0 = off, 2 = on                               (2)              */
   int accel_start;      /* first extrapolation after this sweep          (6)              */
+  /* What the FIRST failed stagnation check does: with stall_reg > 0 the solve goes on with the Delassus matrix
+   * G + stall_reg * mean(diag G) * I -- a slightly compliant contact set (constraint-force mixing) on which the sweeps do
+   * converge -- and only a second failed check ends it; stall_reg = 0 ends it at once.  Fires on ~1 % of the steps of
+   * fallen robots whose joint stops fight sticking contacts, never on standing ones. */
+  float stall_reg;      /*                                               (0.02)           */
 } rsb_params;
 
 /* raisim::Contact as returned by ArticulatedSystem::getContacts(): 12 words */
@@ -177,6 +182,12 @@ int rsb_batch_get_contacts(rsb_batch* b, rsb_contact* out, int32_t* counts, int 
 int rsb_batch_get_contact_points(rsb_batch* b, int32_t* pt_index, int env_begin, int env_count, int where);          /* [n][RSB_KMAX] candidate-point ids */
 int rsb_batch_get_solver_iterations(rsb_batch* b, int32_t* iters, int env_begin, int env_count, int where);          /* getContactSolver().getLoopCounter() */
 int rsb_batch_get_diverged(rsb_batch* b, int32_t* flags, int env_begin, int env_count, int where);                   /* 1 = state went non-finite in the last step: reset it */
+/* how the last contact solve of every environment ended */
+#define RSB_SOLVER_CONVERGED 0           /* largest impulse update < threshold                                         */
+#define RSB_SOLVER_CONVERGED_COMPLIANT 1 /* ... on the compliant contact set entered after a failed stagnation check   */
+#define RSB_SOLVER_STALLED 2             /* ended by a failed stagnation check (second one when stall_reg > 0)          */
+#define RSB_SOLVER_MAXITER 3             /* max_iter sweeps without reaching the threshold                              */
+int rsb_batch_get_solver_status(rsb_batch* b, int32_t* status, int env_begin, int env_count, int where);
 int rsb_batch_get_solver_residual(rsb_batch* b, float* resid, int env_begin, int env_count, int where);              /* largest impulse update of the last sweep (< threshold: converged) */
 /* FK, M and h of the CURRENT state for the getters above, without touching the contact records of the last integrate()
  * (upstream's getters are lazy the same way).  The getters call it themselves when the state changed through this API;

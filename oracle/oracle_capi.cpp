@@ -36,6 +36,7 @@ struct OrcDebug {       // every pointer optional; sized for n_envs; filled from
   int* lim_dof;         // [n][LMAX]   their dofs (-1 = none)
   double* lim_lambda;   // [n][LMAX]   their impulses
   double* resid;        // [n]         largest impulse update of the last sweep (solver residual at exit)
+  int* status;          // [n]         how the solve ended (RSB_SOLVER_*)
 };
 
 struct Handle {
@@ -104,6 +105,7 @@ static void run(Sim<T>& sim, int n_envs, int n_steps, double* gc, double* gv, co
         if (dbg->ncontacts) dbg->ncontacts[e] = K;
         if (dbg->iters) dbg->iters[e] = ws.iters;
         if (dbg->resid) dbg->resid[e] = double(ws.resid);
+        if (dbg->status) dbg->status[e] = ws.status;
         const int Crows = 3 * K + int(ws.limits.size());
         if (dbg->G) for (int a = 0; a < Crows; a++) for (int b2 = 0; b2 < Crows; b2++) dbg->G[(size_t)e * RMAX * RMAX + a * RMAX + b2] = double(ws.G[a * Crows + b2]);
         if (dbg->u0) for (int a = 0; a < Crows; a++) dbg->u0[(size_t)e * RMAX + a] = double(ws.u0[a]);
@@ -139,13 +141,13 @@ void orc_destroy(void* hv) { delete static_cast<Handle*>(hv); }
 
 int orc_kmax() { return KMAX; }
 
-// p = {dt, gx, gy, gz, erp, alpha_init, alpha_min, alpha_decay, max_iter, threshold, mu, restitution, rest_threshold, stall_window, stall_ratio, warm_start, slip_bisect, joint_limits, slip_local, accel_m, accel_start}
+// p = {dt, gx, gy, gz, erp, alpha_init, alpha_min, alpha_decay, max_iter, threshold, mu, restitution, rest_threshold, stall_window, stall_ratio, warm_start, slip_bisect, joint_limits, slip_local, accel_m, accel_start, stall_reg}
 void orc_set_params(void* hv, const double* p) {
   Handle* h = static_cast<Handle*>(hv);
   Params prm;
   prm.dt = p[0]; prm.gravity[0] = p[1]; prm.gravity[1] = p[2]; prm.gravity[2] = p[3]; prm.erp = p[4];
   prm.alpha_init = p[5]; prm.alpha_min = p[6]; prm.alpha_decay = p[7]; prm.max_iter = int(p[8]); prm.threshold = p[9];
-  prm.mu = p[10]; prm.restitution = p[11]; prm.rest_threshold = p[12]; prm.stall_window = int(p[13]); prm.stall_ratio = p[14]; prm.warm_start = int(p[15]); prm.slip_bisect = int(p[16]); prm.joint_limits = int(p[17]); prm.slip_local = int(p[18]); prm.accel_m = int(p[19]); prm.accel_start = int(p[20]);
+  prm.mu = p[10]; prm.restitution = p[11]; prm.rest_threshold = p[12]; prm.stall_window = int(p[13]); prm.stall_ratio = p[14]; prm.warm_start = int(p[15]); prm.slip_bisect = int(p[16]); prm.joint_limits = int(p[17]); prm.slip_local = int(p[18]); prm.accel_m = int(p[19]); prm.accel_start = int(p[20]); prm.stall_reg = p[21];
   if (h->d) h->d->prm = prm; else if (h->f) h->f->prm = prm; else h->c->prm = prm;
 }
 

@@ -87,8 +87,9 @@ struct Params {
   double mu = 0.8;              // World::setDefaultMaterial friction
   double restitution = 0.0, rest_threshold = 0.01;
   int joint_limits = 1;         // enforce the URDF <limit lower upper> of revolute/prismatic joints (unilateral rows in the solver)
-  int stall_window = 16;        // stagnation exit of the Gauss-Seidel loop (0 = off), see include/rsb.h
+  int stall_window = 8;         // stagnation check of the Gauss-Seidel loop (0 = off), see include/rsb.h
   double stall_ratio = 0.5;
+  double stall_reg = 0.02;      // first stall: go on with G + stall_reg * mean(diag G) * I (a compliant contact set); second stall: exit.  0 = exit at once
   int slip_bisect = 0;          // 1: after the first 32-probe round, refine the bracket by plain bisection (what a CPU
                                 // implementation of the published method does); 0: 32-section rounds, probe-for-probe the
                                 // kernel's search.  Both end in the same bracket width; results agree to ~1e-7.
@@ -142,6 +143,7 @@ template <typename T> struct Workspace {
   std::vector<Limit<T>> limits;
   int iters = 0;
   T resid = 0;                    // largest impulse update of the last Gauss-Seidel sweep (< threshold: converged)
+  int status = 0;                 // 0 converged, 1 converged on the compliant contact set (stall_reg), 2 stalled, 3 max_iter == RSB_SOLVER_*
   // warm-start cache: candidate-point id and WORLD-frame impulse of the previous step's contacts
   int prev_pt[KMAX]; V3<T> prev_imp[KMAX];
   Workspace() { for (int k = 0; k < KMAX; k++) { prev_pt[k] = -1; prev_imp[k] = {0, 0, 0}; } }
@@ -640,7 +642,7 @@ template <typename T> class Sim {
       }
     const int Lm = int(ws.limits.size()), C3 = 3 * K, C = C3 + Lm;
     for (int i = 0; i < nv; i++) ws.rhs[i] = dt * ws.z[i];
-    ws.iters = 0; ws.resid = T(0);
+    ws.iters = 0; ws.resid = T(0); ws.status = 0;
     if (C > 0) {
       jacobians(ws);
       // Y = L^-1 J^T (nv x C);  G = Y^T Y;  u0 = J v + dt Y^T z - target
@@ -689,6 +691,8 @@ template <typename T> class Sim {
       const int AM = std::min(std::max(prm.accel_m, 0), 3);
       std::vector<T> hx, hg, hf;          // current x, and history rows [slot][C]
       int hcount = 0, resets = 0;
+      bool regularised = false;
+      ws.status = 3;
       if (AM > 0) { hx.assign(C, T(0)); hg.assign((size_t)(AM + 1) * C, T(0)); hf.assign((size_t)(AM + 1) * C, T(0)); }
       for (int it = 0; it < prm.max_iter; it++) {
         T err = 0;
@@ -724,7 +728,7 @@ template <typename T> class Sim {
         }
         ws.iters = it + 1; ws.resid = err;
         alpha = std::max(T(prm.alpha_min), alpha * T(prm.alpha_decay));
-        if (err < T(prm.threshold)) break;
+        if (err < T(prm.threshold)) { ws.status = regularised ? 1 : 0; break; }
         if (AM > 0 && it + 1 >= prm.accel_start - AM && resets < ACCEL_MAX_RESETS) {   // the history starts AM sweeps before the first extrapolation: nothing is kept (or paid for) on quickly converging problems
           // push (g, f) of this sweep; slots are a shift register, newest last
           if (hcount == AM + 1) {
@@ -788,7 +792,20 @@ template <typename T> class Sim {
           }
         }
         if (it + 1 == next_ckpt) {
-          if (it + 1 >= 2 * prm.stall_window && err > T(prm.stall_ratio) * err_ckpt) break;
+          if (it + 1 >= 2 * prm.stall_window && err > T(prm.stall_ratio) * err_ckpt) {
+            if (regularised || !(prm.stall_reg > 0)) { ws.status = 2; break; }
+            // The per-contact rule is cycling on this contact set (typically a joint stop fighting a sticking contact of the same leg).
+            // Go on with a slightly compliant set: G + eps I, eps = stall_reg * mean(diag G)  (constraint-force mixing, only here).
+            T tr = 0;
+            for (int a = 0; a < C; a++) tr += ws.G[a * C + a];
+            const T eps = T(prm.stall_reg) * tr / T(C);
+            for (int a = 0; a < C; a++) ws.G[a * C + a] += eps;
+            for (int i = 0; i < K; i++) { const V3<T>& l = ws.contacts[i].lam; ws.u[3 * i] += eps * l.x; ws.u[3 * i + 1] += eps * l.y; ws.u[3 * i + 2] += eps * l.z; }
+            for (int l = 0; l < Lm; l++) ws.u[C3 + l] += eps * ws.limits[l].lam;
+            regularised = true; hcount = 0; resets = 0;
+            err_ckpt = T(3.0e38); next_ckpt = it + 1 + prm.stall_window;
+            continue;
+          }
           err_ckpt = err; next_ckpt += prm.stall_window;
         }
       }

@@ -23,7 +23,7 @@ class Params(C.Structure):
                 ("alpha_min", C.c_float), ("alpha_decay", C.c_float), ("max_iter", C.c_int), ("threshold", C.c_float),
                 ("mu", C.c_float), ("restitution", C.c_float), ("rest_threshold", C.c_float),
                 ("stall_window", C.c_int), ("stall_ratio", C.c_float), ("joint_limits", C.c_int),
-                ("accel_m", C.c_int), ("accel_start", C.c_int)]
+                ("accel_m", C.c_int), ("accel_start", C.c_int), ("stall_reg", C.c_float)]
 
 
 class Contact(C.Structure):
@@ -100,7 +100,7 @@ EXPORTED = [
     "rsb_batch_set_generalized_force", "rsb_batch_set_external_wrench", "rsb_batch_set_control_mode", "rsb_batch_get_generalized_force", "rsb_batch_bind_pd_target",
     "rsb_batch_integrate1", "rsb_batch_integrate2", "rsb_batch_integrate",
     "rsb_batch_get_mass_matrix", "rsb_batch_get_nonlinearities", "rsb_batch_get_body_poses", "rsb_batch_get_contacts",
-    "rsb_batch_get_contact_points", "rsb_batch_get_solver_iterations", "rsb_batch_get_diverged", "rsb_batch_get_solver_residual", "rsb_batch_update_kinematics", "rsb_batch_device_ptrs", "rsb_batch_launch_count",
+    "rsb_batch_get_contact_points", "rsb_batch_get_solver_iterations", "rsb_batch_get_diverged", "rsb_batch_get_solver_residual", "rsb_batch_get_solver_status", "rsb_batch_update_kinematics", "rsb_batch_device_ptrs", "rsb_batch_launch_count",
     "rsb_batch_ob_dim", "rsb_batch_observe", "rsb_batch_control_step",
     "rsb_batch_gym_configure", "rsb_batch_gym_reset", "rsb_batch_gym_step",
     "rsb_peer_buffer_create", "rsb_peer_buffer_open", "rsb_peer_buffer_close", "rsb_peer_buffer_destroy", "rsb_batch_set_observation_peers", "rsb_batch_wait_observation_peers",
@@ -165,6 +165,7 @@ def lib():
         L.rsb_batch_get_solver_iterations.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.rsb_batch_get_diverged.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.rsb_batch_get_solver_residual.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.rsb_batch_get_solver_status.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.rsb_batch_update_kinematics.argtypes = [C.c_void_p]
         L.rsb_batch_device_ptrs.argtypes = [C.c_void_p, C.POINTER(DeviceView)]
         L.rsb_batch_launch_count.argtypes = [C.c_void_p]
@@ -422,6 +423,13 @@ class Batch:
         n = self.n - env_begin if env_count is None else env_count
         out = np.empty(n, np.float32)
         _ck(lib().rsb_batch_get_solver_residual(self.h, out.ctypes.data_as(C.c_void_p), env_begin, n, HOST))
+        return out
+
+    def solver_status(self, env_begin=0, env_count=None):
+        """0 converged, 1 converged on the compliant contact set (stall_reg), 2 stalled, 3 max_iter -- of the last solve"""
+        n = self.n - env_begin if env_count is None else env_count
+        out = np.empty(n, np.int32)
+        _ck(lib().rsb_batch_get_solver_status(self.h, out.ctypes.data_as(C.c_void_p), env_begin, n, HOST))
         return out
 
     def update_kinematics(self):

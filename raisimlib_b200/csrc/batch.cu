@@ -55,6 +55,7 @@ struct rsb_batch {
   float *gc = nullptr, *gv = nullptr, *tau = nullptr, *pt = nullptr, *vt = nullptr, *tau_applied = nullptr;
   int *ncontacts = nullptr, *contact_pt = nullptr, *iters = nullptr, *diverged = nullptr;
   float* resid = nullptr;
+  int* solver_status = nullptr;
   rsb_contact* contacts = nullptr;
   float *dbg_M = nullptr, *dbg_h = nullptr, *dbg_R = nullptr, *dbg_p = nullptr;
   float* hmap = nullptr;
@@ -247,7 +248,7 @@ static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug, flo
   a.prm = b->prm; a.ter = b->ter; a.ws = b->ws;
   a.blob_words = (int)b->blob_host.size(); a.blob = b->blob;
   a.tau_applied = b->tau_applied;
-  a.ncontacts = b->ncontacts; a.contacts = b->contacts; a.contact_pt = b->contact_pt; a.iters = b->iters; a.diverged = b->diverged; a.resid = b->resid;
+  a.ncontacts = b->ncontacts; a.contacts = b->contacts; a.contact_pt = b->contact_pt; a.iters = b->iters; a.diverged = b->diverged; a.resid = b->resid; a.solver_status = b->solver_status;
   if (debug) { a.dbg_M = b->dbg_M; a.dbg_h = b->dbg_h; a.dbg_R = b->dbg_R; a.dbg_p = b->dbg_p; }
   a.phase_mask = phase_mask; a.prof = b->prof;
   a.ext = b->ext_active ? b->ext : nullptr;
@@ -339,8 +340,8 @@ int rsb_params_default(rsb_params* p) {
   if (!p) return fail(RSB_ERR_INVALID, "null params");
   p->dt = 0.0025f; p->gravity[0] = 0.f; p->gravity[1] = 0.f; p->gravity[2] = -9.81f; p->erp = 0.f;
   p->alpha_init = 1.f; p->alpha_min = 1.f; p->alpha_decay = 1.f; p->max_iter = 150; p->threshold = 1e-6f;
-  p->mu = 0.8f; p->restitution = 0.f; p->rest_threshold = 0.01f; p->stall_window = 16; p->stall_ratio = 0.5f; p->joint_limits = 1;
-  p->accel_m = 2; p->accel_start = 6;
+  p->mu = 0.8f; p->restitution = 0.f; p->rest_threshold = 0.01f; p->stall_window = 8; p->stall_ratio = 0.5f; p->joint_limits = 1;
+  p->accel_m = 2; p->accel_start = 6; p->stall_reg = 0.02f;
   return RSB_OK;
 }
 
@@ -454,6 +455,7 @@ int rsb_batch_create(const rsb_model* m, int num_envs, int device, rsb_batch** o
   if (e == cudaSuccess) e = alloc((void**)&b->iters, N * 4);
   if (e == cudaSuccess) e = alloc((void**)&b->diverged, N * 4);
   if (e == cudaSuccess) e = alloc((void**)&b->resid, N * 4);
+  if (e == cudaSuccess) e = alloc((void**)&b->solver_status, N * 4);
   if (e == cudaSuccess) e = alloc((void**)&b->contacts, N * KMAX * sizeof(rsb_contact));
   if (e == cudaSuccess) e = alloc((void**)&b->blob, b->blob_host.size() * 4);
   if (e == cudaSuccess) e = cudaMemcpy(b->blob, b->blob_host.data(), b->blob_host.size() * 4, cudaMemcpyHostToDevice);
@@ -474,7 +476,7 @@ void rsb_batch_destroy(rsb_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
-  for (void* p : {(void*)b->resid, (void*)b->diverged, (void*)b->tau_applied, (void*)b->gc, (void*)b->gv, (void*)b->tau, (void*)b->pt, (void*)b->vt, (void*)b->ncontacts, (void*)b->contact_pt, (void*)b->iters,
+  for (void* p : {(void*)b->solver_status, (void*)b->resid, (void*)b->diverged, (void*)b->tau_applied, (void*)b->gc, (void*)b->gv, (void*)b->tau, (void*)b->pt, (void*)b->vt, (void*)b->ncontacts, (void*)b->contact_pt, (void*)b->iters,
                   (void*)b->contacts, (void*)b->dbg_M, (void*)b->dbg_h, (void*)b->dbg_R, (void*)b->dbg_p, (void*)b->hmap, (void*)b->staging, (void*)b->obs_staging, (void*)b->blob, (void*)b->gym_const, (void*)b->gym_action,
                   (void*)b->gym_obs, (void*)b->gym_reward, (void*)b->gym_done, (void*)b->ext, (void*)b->hmap_index})
     if (p) cudaFree(p);
@@ -554,6 +556,7 @@ int rsb_batch_set_params(rsb_batch* b, const rsb_params* p) {
   if (!(p->dt > 0) || p->max_iter < 1 || !(p->mu >= 0)) return fail(RSB_ERR_INVALID, "invalid params");
   if (p->accel_m != 0 && p->accel_m != 2) return fail(RSB_ERR_INVALID, "accel_m must be 0 (plain sweeps) or 2");
   if (p->accel_m == 2 && p->accel_start < 3) return fail(RSB_ERR_INVALID, "accel_start must be at least 3");
+  if (!(p->stall_reg >= 0.f)) return fail(RSB_ERR_INVALID, "stall_reg must be >= 0");
   b->prm = *p;
   return RSB_OK;
 }
@@ -742,6 +745,12 @@ int rsb_batch_get_contact_points(rsb_batch* b, int32_t* pt, int env_begin, int e
 int rsb_batch_get_solver_iterations(rsb_batch* b, int32_t* it, int env_begin, int env_count, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
   CK(cudaMemcpyAsync(it, b->iters + env_begin, (size_t)env_count * 4, where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
+  if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
+  return RSB_OK;
+}
+int rsb_batch_get_solver_status(rsb_batch* b, int32_t* status, int env_begin, int env_count, int where) {
+  int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  CK(cudaMemcpyAsync(status, b->solver_status + env_begin, (size_t)env_count * 4, where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
   if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
   return RSB_OK;
 }

@@ -20,7 +20,7 @@ constexpr int CB_WORDS = 16;
 constexpr int NREF = 2;              // regula-falsi (Illinois) steps after the 32-section rounds, oracle NREF
 constexpr int ACCEL_MAX_RESETS = 2;  // oracle ACCEL_MAX_RESETS
 
-struct GsResult { float lam, resid; int iters; };
+struct GsResult { float lam, resid; int iters, status; };   // status: RSB_SOLVER_* (rsb.h)
 
 // a / b for b > 1e-12 (or a NaN-producing b whose result is discarded): one MUFU.RCP and one multiply, no denormal scaling
 __device__ __forceinline__ float fast_div(float a, float b) {
@@ -198,10 +198,30 @@ __device__ __noinline__ AAState anderson_step(float* hist, const float* s_G, int
   return o;
 }
 
+// The per-contact rule is cycling on this contact set (typically a joint stop fighting a sticking contact of the same leg):
+// continue on G + eps I, eps = stall_reg * mean(diag G) -- constraint-force mixing, only for these problems (oracle step()).
+// Updates the Delassus diagonal, the per-contact blocks and their inverses; returns this lane's constraint velocity.
+__device__ __noinline__ float regularise(float stall_reg, float* s_G, int g_stride, float* s_cb, int lane, int K, int CR, float lam_c, float u_c) {
+  const bool on = lane < CR;
+  const float eps = stall_reg * warp_sum(on ? s_G[lane * g_stride + lane] : 0.f) / (float)CR;
+  if (on) s_G[lane * g_stride + lane] += eps;
+  if (lane < K) {
+    float* o = s_cb + CB_WORDS * lane;
+    const float a = o[0] + eps, bq = o[1], cc = o[2], d = o[3] + eps, e = o[4], f = o[5] + eps;
+    const float c00 = d * f - e * e, c01 = cc * e - bq * f, c02 = bq * e - cc * d;
+    const float c11 = a * f - cc * cc, c12 = bq * cc - a * e, c22 = a * d - bq * bq;
+    const float id = 1.0f / (a * c00 + bq * c01 + cc * c02);
+    o[0] = a; o[3] = d; o[5] = f;
+    o[8] = c00 * id; o[9] = c01 * id; o[10] = c02 * id; o[11] = c11 * id; o[12] = c12 * id; o[13] = c22 * id;
+  }
+  __syncwarp();
+  return on ? u_c + eps * lam_c : u_c;
+}
+
 // ------------------------------------------------------------------ the solve ------------------
 // s_G: Delassus matrix, row stride g_stride (odd: lane-strided row reads are conflict-free); s_cb: per-contact constant blocks;
 // u_c: this lane's constraint velocity at lambda = 0 (rows 3K .. 3K+Lm-1 are joint-limit rows).  Returns this lane's impulse.
-__device__ __noinline__ GsResult gs_solve(const rsb_params& prm, const float* s_G, int g_stride, const float* s_cb, float* s_hist, const float* sec, int sec_stride,
+__device__ __noinline__ GsResult gs_solve(const rsb_params& prm, float* s_G, int g_stride, float* s_cb, float* s_hist, const float* sec, int sec_stride,
                                           int lane, int K, int Lm, float u_c) {
   constexpr unsigned FULLM = 0xffffffffu;
   const int C3 = 3 * K, CR = C3 + Lm;
@@ -213,9 +233,10 @@ __device__ __noinline__ GsResult gs_solve(const rsb_params& prm, const float* s_
   float err_ckpt = 3.0e38f;
   int next_ckpt = prm.stall_window;
   int aa_hc = 0, aa_resets = 0; float aa_fp = 0.f;
+  bool regularised = false;
   const int aa_first = prm.accel_m > 0 ? prm.accel_start - 2 : 0x7fffffff;   // the history starts two sweeps before the first extrapolation
   if (prm.accel_m > 0) s_hist[lane] = u_c;   // u0
-  GsResult res; res.iters = 0; res.resid = 0.f;
+  GsResult res; res.iters = 0; res.resid = 0.f; res.status = RSB_SOLVER_MAXITER;
 #pragma unroll 1
   for (int it = 0; it < prm.max_iter; it++) {
     float err = 0.f;
@@ -264,14 +285,20 @@ __device__ __noinline__ GsResult gs_solve(const rsb_params& prm, const float* s_
     }
     res.iters = it + 1; res.resid = err;
     alpha = fmaxf(prm.alpha_min, alpha * prm.alpha_decay);
-    if (err < prm.threshold) break;
+    if (err < prm.threshold) { res.status = regularised ? RSB_SOLVER_CONVERGED_COMPLIANT : RSB_SOLVER_CONVERGED; break; }
     if (aa_rec) {
       __syncwarp();
       const AAState st = anderson_step(s_hist, s_G, g_stride, lane, CR, lam_c, u_c, aa_hc, aa_fp, it + 1 >= prm.accel_start ? 1 : 0);
       lam_c = st.lam; u_c = st.u; aa_hc = st.hc; aa_fp = st.fp; aa_resets += st.dropped;
     }
-    if (it + 1 == next_ckpt) {      // stagnation exit (see rsb_params.stall_window)
-      if (it + 1 >= 2 * prm.stall_window && err > prm.stall_ratio * err_ckpt) break;
+    if (it + 1 == next_ckpt) {      // stagnation check (see rsb_params.stall_window)
+      if (it + 1 >= 2 * prm.stall_window && err > prm.stall_ratio * err_ckpt) {
+        if (regularised || !(prm.stall_reg > 0.f)) { res.status = RSB_SOLVER_STALLED; break; }
+        u_c = regularise(prm.stall_reg, s_G, g_stride, s_cb, lane, K, CR, lam_c, u_c);   // first stall: go on with a slightly compliant contact set
+        regularised = true; aa_hc = 0; aa_resets = 0;
+        err_ckpt = 3.0e38f; next_ckpt = it + 1 + prm.stall_window;
+        continue;
+      }
       err_ckpt = err; next_ckpt += prm.stall_window;
     }
   }

@@ -174,6 +174,7 @@ struct StepArgs {
   int* iters;          // [N]
   int* diverged;       // [N] 1 when the stored state holds a non-finite value (caller resets those environments)
   float* resid;        // [N] largest impulse update of the last Gauss-Seidel sweep (< threshold: the solve converged)
+  int* solver_status;  // [N] RSB_SOLVER_* of the last sub-step's solve
   float* tau_applied;  // [N][gv_stride] generalized force actually applied in the last sub-step (getGeneralizedForce)
   float *dbg_M, *dbg_h, *dbg_R, *dbg_p;   // optional (integrate1 / getters)
   float* obs;          // optional [N][ob_dim]: RaisimGym observation row of the final state, written by this kernel
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
     }
     __syncwarp();
     int K = 0, iters = 0;
-    float resid = 0.f;
+    float resid = 0.f; int gs_status = RSB_SOLVER_CONVERGED;
 
 #pragma unroll 1
     for (int sub = 0; sub < args.substeps; sub++) {
@@ -886,7 +887,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
           u_c -= target;
         }
       }
-      iters = 0; resid = 0.f;
+      iters = 0; resid = 0.f; gs_status = RSB_SOLVER_CONVERGED;
       if (CR > 0) {
         __syncwarp();      // h / b / poses are dead from here: G overlays them
         // G = Y^T Y; rows a, b share ancestors exactly up to the depth of their bodies' LCA
@@ -926,7 +927,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         if (args.prof && lane == 0) args.prof[((size_t)env * 4 + (sub & 3)) * 8 + 3] = (unsigned)clock64();
         // =========================== stage D: per-contact Gauss-Seidel ===========================
         const GsResult gs = gs_solve(args.prm, s_G, GP, s_u, s_hist, sec_c, SEC_STRIDE, lane, K, Lm, u_c);
-        iters = gs.iters; resid = gs.resid;
+        iters = gs.iters; resid = gs.resid; gs_status = gs.status;
         if (lane < CR) s_lam[lane] = gs.lam;
         __syncwarp();
       }
@@ -1061,7 +1062,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       const bool any_bad = __any_sync(FULL, bad);
       if (lane == 0) args.diverged[env] = any_bad ? 1 : 0;
     }
-    if (lane == 0) { args.ncontacts[env] = K; args.iters[env] = iters; args.resid[env] = resid; }
+    if (lane == 0) { args.ncontacts[env] = K; args.iters[env] = iters; args.resid[env] = resid; args.solver_status[env] = gs_status; }
     if (lane < KMAX) {
       rsb_contact rc;
       int pt = -1;

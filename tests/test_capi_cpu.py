@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(capi.Contact) == 48       # 12 words, SURVEY 8d algorithmic-bytes formula
-    assert ctypes.sizeof(capi.Params) == 4 * 18      # rsb_params: 16 words of round 1 + accel_m, accel_start
+    assert ctypes.sizeof(capi.Params) == 4 * 19      # rsb_params: 16 words of round 1 + accel_m, accel_start, stall_reg
 
 
 @pytest.mark.parametrize("src", ["anymal_c_like.urdf", "atlas_like.urdf", PENDULUM_URDF, BOX_URDF, REALISTIC_URDF])
@@ -88,7 +88,7 @@ def test_argument_validation_without_gpu():
     assert L.rsb_model_body_index(None, b"x") < 0
     p = capi.Params()
     assert L.rsb_params_default(C.byref(p)) == 0
-    assert abs(p.dt - 0.0025) < 1e-9 and p.max_iter == 150 and p.stall_window == 16 and abs(p.mu - 0.8) < 1e-7 and p.accel_m == 2 and p.accel_start == 6
+    assert abs(p.dt - 0.0025) < 1e-9 and p.max_iter == 150 and p.stall_window == 8 and abs(p.mu - 0.8) < 1e-7 and p.accel_m == 2 and p.accel_start == 6 and abs(p.stall_reg - 0.02) < 1e-8
 
 
 def test_too_many_bodies_is_reported():

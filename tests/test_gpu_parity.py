@@ -42,7 +42,8 @@ def _setup(capi, urdf, n, seed, terrain="ground", base_z=0.45, vel=0.5, tau_scal
     tau = rng.uniform(-tau_scale, tau_scale, (n, t["nv"]))
     if t["floating"]:
         tau[:, :6] = 0
-    prm = dict(threshold=THRESH, stall_window=0)     # plain maxIter semantics unless a test asks for the stagnation exit
+    prm = dict(threshold=THRESH)     # everything else at the library defaults = what bench.py runs (accelerated sweeps, stagnation
+                                     # window 8 with the compliant fallback); tests of the plain published method pass accel_m=0, stall_window=0
     prm.update(params or {})
     o64, o32 = Oracle(t, params=prm), Oracle(t, precision="f32", params=prm)
     bt.set_params(**{k: v for k, v in prm.items() if k not in ("gx", "gy", "gz")})
@@ -142,14 +143,16 @@ def test_one_step_state_and_impulses(capi, urdf, terrain, base_z, tau_scale):
     assert np.isfinite(g1).all() and np.isfinite(v1).all()
     # compare where both solvers converged on the same contact set; cycling Gauss-Seidel cases
     # (both sides hit max_iter; see DESIGN.md "solver convergence") have no unique answer
-    res = bt.solver_residual()
+    st = bt.solver_status()
     same = (pts == d["c_pt"]).all(1)
-    conv = same & (res < THRESH) & (d["resid"] < THRESH)
-    print(f"same-contact envs {same.sum()}/{n}, of those converged on both sides {conv.sum()}; non-converged gpu {100 * (res >= THRESH).mean():.2f}% oracle "
-          f"{100 * (d['resid'] >= THRESH).mean():.2f}%; K mean {cnt.mean():.2f}; sweeps gpu {it.mean():.1f} oracle {d['iters'].mean():.1f}")
-    # accelerated sweeps: random drops (knee + foot on one shank, box feet) converge too -- round 1 excluded up to 10 % here
-    assert (res >= THRESH).mean() < 0.01 and (d["resid"] >= THRESH).mean() < 0.01
-    assert conv.mean() > 0.98
+    conv = same & (st == 0) & (d["status"] == 0)
+    print(f"same-contact envs {same.sum()}/{n}, of those converged on both sides {conv.sum()}; solver status gpu {np.bincount(st, minlength=4).tolist()} oracle "
+          f"{np.bincount(d['status'], minlength=4).tolist()} (converged / on the compliant set / stalled / max_iter); K mean {cnt.mean():.2f}; sweeps gpu {it.mean():.1f} oracle {d['iters'].mean():.1f}")
+    # Random orientations half inside the ground (a whole leg under the surface): the per-contact rule cycles on a few % of these
+    # unphysical states; they finish on the compliant contact set (status 1) and are compared separately.  Round 1 excluded up
+    # to 10 % here; the physical regimes (standing, fallen, humanoid on box feet) have their own tests below.
+    assert (st >= 2).mean() < 0.01 and (d["status"] >= 2).mean() < 0.01        # < 1 % end without converging
+    assert conv.mean() > 0.95
     ev = np.abs(v1 - b)[conv]; eq = np.abs(g1 - a)[conv]
     scale_v = 1.0 + np.abs(b[conv])
     print(f"one-step errors: gv max {ev.max():.2e} (rel {np.max(ev / scale_v):.2e}) median {np.median(ev.max(1)):.2e}; gc max {eq.max():.2e}")
@@ -386,12 +389,13 @@ def test_cpp_kinematic_getters_example():
 
 
 def test_default_solver_matches_oracle_on_random_drops(capi):
-    """Library defaults (Anderson-accelerated sweeps from sweep 6, stagnation window 16, threshold 1e-6) on a brutal random-drop
-    batch (knee + foot contacts on one shank, bodies on the ground): same sweep counts as the oracle, < 1 % non-converged."""
+    """Library defaults (Anderson-accelerated sweeps from sweep 6, stagnation window 8 with the compliant fallback, threshold 1e-6)
+    on a brutal random-drop batch (knee + foot contacts on one shank, bodies on the ground): same sweep counts and the same
+    endings as the oracle, < 1 % of the environments end without converging."""
     n = 1024
-    t, bt, o64, o32, gc, gv, tau = _setup(capi, "anymal_c_like.urdf", n, seed=111, base_z=0.35, params=dict(stall_window=16, stall_ratio=0.5, accel_m=2, accel_start=6))
+    t, bt, o64, o32, gc, gv, tau = _setup(capi, "anymal_c_like.urdf", n, seed=111, base_z=0.35)
     bt.integrate(1)
-    it = bt.solver_iterations(); res = bt.solver_residual()
+    it = bt.solver_iterations(); st = bt.solver_status()
     g1, v1 = bt.get_state()
     a, b = gc.copy(), gv.copy()
     d = o64.step(a, b, tau_ff=tau, debug=True)
@@ -399,22 +403,28 @@ def test_default_solver_matches_oracle_on_random_drops(capi):
     same = (pts == d["c_pt"]).all(1)
     agree = (it == d["iters"])[same].mean()
     print(f"default solver: sweeps gpu mean {it.mean():.2f} max {it.max()} | oracle mean {d['iters'].mean():.2f} max {d['iters'].max()}; identical counts in "
-          f"{100 * agree:.1f}% of envs; non-converged gpu {100 * (res >= THRESH).mean():.2f}% oracle {100 * (d['resid'] >= THRESH).mean():.2f}%")
-    assert (res >= THRESH).mean() < 0.01 and (d["resid"] >= THRESH).mean() < 0.01
+          f"{100 * agree:.1f}% of envs; status gpu {np.bincount(st, minlength=4).tolist()} oracle {np.bincount(d['status'], minlength=4).tolist()}")
+    assert (st >= 2).mean() < 0.01 and (d["status"] >= 2).mean() < 0.01
     assert it.max() < 150 and it.mean() < 1.15 * d["iters"].mean() + 0.5
     assert agree > 0.85                                   # float32 vs float64 leave the loop one sweep apart now and then
-    assert (np.abs(it - d["iters"])[same] <= 2).mean() > 0.97
-    ok = same & (res < THRESH) & (d["resid"] < THRESH)
+    assert (np.abs(it - d["iters"])[same] <= 2).mean() > 0.95
+    assert ((st == 1) == (d["status"] == 1))[same].mean() > 0.97      # the same problems take the compliant fallback
+    ok = same & (st == 0) & (d["status"] == 0)
     ev = np.abs(v1 - b)[ok].max(1)
     print(f"   one-step gv error on converged envs: median {np.median(ev):.2e} p99 {np.quantile(ev, .99):.2e} max {ev.max():.2e}")
     assert np.median(ev) < 2e-5 and np.quantile(ev, 0.99) < 2e-3
-    # plain sweeps (accel_m = 0) reach the same fixed point: the acceleration changes the path, not the answer
+    both1 = same & (st == 1) & (d["status"] == 1)
+    if both1.sum() > 5:
+        e1 = np.abs(v1 - b)[both1].max(1)
+        print(f"   on the compliant set ({both1.sum()} envs): gv error median {np.median(e1):.2e} max {e1.max():.2e}")
+        assert np.median(e1) < 5e-3
+    # plain sweeps (the published method: accel_m = 0, no stagnation check) reach the same fixed point where both converge
     bt.set_params(accel_m=0, stall_window=0)
     bt.set_state(gc.astype(np.float32), gv.astype(np.float32))
     bt.integrate(1)
-    it0 = bt.solver_iterations(); res0 = bt.solver_residual(); v0 = bt.get_state()[1]
-    both = (res < THRESH) & (res0 < THRESH)
-    print(f"   plain sweeps: mean {it0.mean():.2f} max {it0.max()}, non-converged {100 * (res0 >= THRESH).mean():.2f}%; |dv| accelerated vs plain max {np.abs(v1 - v0)[both].max():.2e}")
+    it0 = bt.solver_iterations(); st0 = bt.solver_status(); v0 = bt.get_state()[1]
+    both = (st == 0) & (st0 == 0)
+    print(f"   plain sweeps: mean {it0.mean():.2f} max {it0.max()}, max_iter reached in {100 * (st0 == 3).mean():.2f}%; |dv| accelerated vs plain p99 {np.quantile(np.abs(v1 - v0)[both].max(1), .99):.2e}")
     assert it.mean() < 0.8 * it0.mean()
     assert np.quantile(np.abs(v1 - v0)[both].max(1), 0.99) < 1e-4
 
@@ -444,7 +454,7 @@ def test_atlas_standing_trajectory_and_heightmap(capi):
     sweeps, ncv = [], []
     for k in range(10):
         bt.integrate(5)
-        sweeps.append(bt.solver_iterations()); ncv.append(bt.solver_residual() >= THRESH)
+        sweeps.append(bt.solver_iterations()); ncv.append(bt.solver_status() >= 1)
         dbg = o.step(a, b, n_steps=5, ptarget=tgt.astype(np.float32).astype(np.float64), vtarget=np.zeros((n, 36)), kp=kp, kd=kd, debug=True)
     o32.step(c, d, n_steps=50, ptarget=tgt.astype(np.float32).astype(np.float64), vtarget=np.zeros((n, 36)), kp=kp, kd=kd)
     g, v = bt.get_state()
@@ -452,14 +462,13 @@ def test_atlas_standing_trajectory_and_heightmap(capi):
     sweeps = np.array(sweeps); ncv = np.array(ncv)
     e = np.abs(g - a).max(1); e32 = np.abs(c - a).max(1); ev = np.abs(v - b).max(1)
     print(f"atlas standing 50 steps: K {cnt.mean():.2f}, sweeps mean {sweeps.mean():.1f} p99 {np.quantile(sweeps, .99):.0f} max {sweeps.max()} (oracle last {dbg['iters'].mean():.1f}), "
-          f"non-converged {100 * ncv.mean():.2f}%; gc err median {np.median(e):.2e} p99 {np.quantile(e, .99):.2e} max {e.max():.2e} | f32 oracle median {np.median(e32):.2e} "
+          f"not converged on the exact contact set {100 * ncv.mean():.2f}%; gc err median {np.median(e):.2e} p99 {np.quantile(e, .99):.2e} max {e.max():.2e} | f32 oracle median {np.median(e32):.2e} "
           f"p99 {np.quantile(e32, .99):.2e}; gv err median {np.median(ev):.2e} p99 {np.quantile(ev, .99):.2e}")
     assert cnt.mean() > 6                                   # standing on the box corners
     assert sweeps.mean() <= 15 and ncv.mean() < 0.01         # <= 15 mean sweeps, < 1 % non-converged
     assert np.median(e) < 2e-5 and np.quantile(e, 0.99) < max(1e-3, 5 * np.quantile(e32, 0.99))
     # on a height map: random drops, 20 steps
-    t2, bt2, o64, o32b, gc2, gv2, tau2 = _setup(capi, "atlas_like.urdf", n, seed=302, terrain="hm", base_z=0.95, tau_scale=2.0, vel=0.3, joint_scale=0.2,
-                                                params=dict(stall_window=16, accel_m=2, accel_start=6))
+    t2, bt2, o64, o32b, gc2, gv2, tau2 = _setup(capi, "atlas_like.urdf", n, seed=302, terrain="hm", base_z=0.95, tau_scale=2.0, vel=0.3, joint_scale=0.2)
     # upright-ish: small random tilt instead of a random quaternion, so that the feet (not the head) meet the terrain
     q = np.c_[np.ones(n), 0.1 * rng.standard_normal((n, 3))]; q /= np.linalg.norm(q, axis=1, keepdims=True)
     gc2[:, 3:7] = q.astype(np.float32)
@@ -471,12 +480,12 @@ def test_atlas_standing_trajectory_and_heightmap(capi):
     dbg = o64.step(a, b, n_steps=20, tau_ff=tau2, debug=True)
     o32b.step(c, d, n_steps=20, tau_ff=tau2)
     _, cnt = bt2.contacts()
-    res = bt2.solver_residual()
+    st2 = bt2.solver_status()
     e = np.abs(g - a).max(1); e32 = np.abs(c - a).max(1)
-    print(f"atlas on a height map, 20 steps: K {cnt.mean():.2f} (oracle {dbg['ncontacts'].mean():.2f}), sweeps {bt2.solver_iterations().mean():.1f}, non-converged {100 * (res >= THRESH).mean():.2f}%; "
+    print(f"atlas on a height map, 20 steps: K {cnt.mean():.2f} (oracle {dbg['ncontacts'].mean():.2f}), sweeps {bt2.solver_iterations().mean():.1f}, status {np.bincount(st2, minlength=4).tolist()}; "
           f"gc err median {np.median(e):.2e} p90 {np.quantile(e, .9):.2e} p99 {np.quantile(e, .99):.2e} | f32 oracle median {np.median(e32):.2e} p99 {np.quantile(e32, .99):.2e}")
     assert cnt.sum() > n                                     # contact-rich
-    assert (res >= THRESH).mean() < 0.01
+    assert (st2 >= 2).mean() < 0.01
     assert np.median(e) < 2e-5 and np.quantile(e, 0.99) < max(2e-3, 5 * np.quantile(e32, 0.99))
 
 
@@ -508,7 +517,7 @@ def test_bench_workload_parity(capi):
     # ---- one control step ----
     tg = ring32[k0 % bench.RING]
     bt.set_pd_target(tg, vt); bt.integrate(bench.SUBSTEPS)
-    g1, v1 = bt.get_state(); pts = bt.contact_points(); ct, cnt = bt.contacts(); it = bt.solver_iterations(); res = bt.solver_residual()
+    g1, v1 = bt.get_state(); pts = bt.contact_points(); ct, cnt = bt.contacts(); it = bt.solver_iterations(); st = bt.solver_status()
     a, b = g0.astype(np.float64), v0.astype(np.float64)
     d = o64.step(a, b, n_steps=bench.SUBSTEPS, ptarget=tg.astype(np.float64), vtarget=vt.astype(np.float64), kp=wl.kp, kd=wl.kd, debug=True)
     c, e_ = g0.astype(np.float64), v0.astype(np.float64)
@@ -517,11 +526,11 @@ def test_bench_workload_parity(capi):
     same32 = (pts == d32["c_pt"]).all(1)
     eq = np.abs(g1 - a).max(1); ev = np.abs(v1 - b).max(1); eq32 = np.abs(c - a).max(1); ev32 = np.abs(e_ - b).max(1)
     print(f"bench workload, 1 control step: K {cnt.mean():.2f} hist {np.bincount(cnt, minlength=9).tolist()}, sweeps gpu {it.mean():.2f} max {it.max()} oracle {d['iters'].mean():.2f}; "
-          f"non-converged {100 * (res >= 1e-6).mean():.2f}%; identical contact lists (4th sub-step) vs f64 oracle {100 * same.mean():.2f}% vs f32 oracle {100 * same32.mean():.2f}%")
+          f"status {np.bincount(st, minlength=4).tolist()}; identical contact lists (4th sub-step) vs f64 oracle {100 * same.mean():.2f}% vs f32 oracle {100 * same32.mean():.2f}%")
     print(f"   gc err median {np.median(eq):.2e} p99 {np.quantile(eq, .99):.2e} max {eq.max():.2e} (f32 oracle: {np.median(eq32):.2e} / {np.quantile(eq32, .99):.2e} / {eq32.max():.2e}); "
           f"gv err median {np.median(ev):.2e} p99 {np.quantile(ev, .99):.2e} max {ev.max():.2e} (f32 oracle: {np.median(ev32):.2e} / {np.quantile(ev32, .99):.2e} / {ev32.max():.2e})")
-    assert (res >= 1e-6).mean() < 0.01 and it.max() <= 150
-    assert same.mean() > 0.99                                # the few that differ have a foot within float32 rounding of touching down
+    assert (st == 0).all()                                   # every environment of the benchmarked workload converges, on the exact contact set
+    assert same.mean() > 0.995                                # the few that differ have a foot within float32 rounding of touching down
     assert np.median(eq) < 2e-6 and np.quantile(eq, 0.99) < max(2e-5, 5 * np.quantile(eq32, 0.99))
     assert np.median(ev) < 5e-5 and np.quantile(ev, 0.99) < max(5e-3, 5 * np.quantile(ev32, 0.99))
     # impulses of the last sub-step where the lists agree
@@ -565,18 +574,18 @@ def test_fallen_quadrupeds_default_solver(capi):
     tau = wl.ring[wl.settle % bench.RING].astype(np.float32)
     bt.set_generalized_force(tau)
     bt.integrate(1)
-    g1, v1 = bt.get_state(); pts = bt.contact_points(); _, cnt = bt.contacts(); it = bt.solver_iterations(); res = bt.solver_residual()
+    g1, v1 = bt.get_state(); pts = bt.contact_points(); _, cnt = bt.contacts(); it = bt.solver_iterations(); st = bt.solver_status()
     a, b = g0.astype(np.float64), v0.astype(np.float64)
     d = o.step(a, b, n_steps=1, tau_ff=tau.astype(np.float64), debug=True)
     same = (pts == d["c_pt"]).all(1)
-    conv = same & (res < 1e-6) & (d["resid"] < 1e-6)
+    conv = same & (st == 0) & (d["status"] == 0)
     ev = np.abs(v1 - b)[conv].max(1)
     print(f"fallen quadrupeds: base z median {np.median(g0[:, 2]):.3f}, K {cnt.mean():.2f} hist {np.bincount(cnt, minlength=9).tolist()}, sweeps gpu {it.mean():.2f} (p99 {np.quantile(it, .99):.0f}, max {it.max()}) "
-          f"oracle {d['iters'].mean():.2f}; non-converged gpu {100 * (res >= 1e-6).mean():.2f}% oracle {100 * (d['resid'] >= 1e-6).mean():.2f}%; same lists {100 * same.mean():.2f}%; "
+          f"oracle {d['iters'].mean():.2f}; status gpu {np.bincount(st, minlength=4).tolist()} oracle {np.bincount(d['status'], minlength=4).tolist()}; same lists {100 * same.mean():.2f}%; "
           f"gv err median {np.median(ev):.2e} p99 {np.quantile(ev, .99):.2e}")
     assert np.median(g0[:, 2]) < 0.2 and cnt.mean() > 3
-    assert (res >= 1e-6).mean() < 0.01 and (d["resid"] >= 1e-6).mean() < 0.01
-    assert same.mean() > 0.98 and conv.mean() > 0.97
+    assert (st >= 2).mean() < 0.01 and (d["status"] >= 2).mean() < 0.01      # < 1 % non-converged
+    assert same.mean() > 0.98 and conv.mean() > 0.95
     assert np.median(ev) < 5e-5 and np.quantile(ev, 0.99) < 5e-3
 
 
