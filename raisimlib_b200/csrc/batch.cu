@@ -208,7 +208,18 @@ static int pick_config(rsb_batch* b) {
   const size_t per_warp = (size_t)b->ws.words * 4;
   const int sms = prop.multiProcessorCount;
   b->slots = b->model->md.npts() > 32 ? 2 : 1;
-  b->spec = same_dims(b->dims, kQuad12) && b->slots == 1 ? 1 : (same_dims(b->dims, kHumanoid30) ? 2 : 0);
+  // the quadruped instance has the topology compiled in (floating base + 4 serial chains of 3 joints in DFS order): check it
+  bool quad_topology = same_dims(b->dims, kQuad12) && b->slots == 1;
+  if (quad_topology) {
+    const Model& md = b->model->md;
+    for (int leg = 0; leg < 4; leg++)
+      for (int j = 0; j < 3; j++) {
+        const int body = 1 + 3 * leg + j;
+        if (md.parent[body] != (j == 0 ? 0 : body - 1) || md.vidx[body] != 5 + body || md.qidx[body] != 6 + body) quad_topology = false;
+        if (md.jtype[body] != 1 && md.jtype[body] != 2) quad_topology = false;
+      }
+  }
+  b->spec = quad_topology ? 1 : (same_dims(b->dims, kHumanoid30) ? 2 : 0);
   if (const char* e = getenv("RSB_FORCE_GENERIC")) if (atoi(e)) b->spec = 0;
   // one persistent CTA per SM; as many warps (= resident environments) as shared memory allows
   static const int options[] = {28, 16, 8, 4, 1};   // 14 = two 14-warp CTAs per SM (experiment: RSB_FORCE_WPC=14)

@@ -307,6 +307,49 @@ __device__ __noinline__ void write_debug(const StepArgs& args, int env, int lane
   }
 }
 
+
+// 1/sqrt(x) and sqrt(x) for x > 0: MUFU.RSQ + one Newton step (relative error < 2e-7, the level of a float32 rounding);
+// the IEEE sqrtf / division pair of the generic path costs ~27 instructions per pivot.
+__device__ __forceinline__ float rsqrt_nr(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * (1.5f - 0.5f * x * r * r);
+}
+
+// ---- compile-time topology: floating base + four serial chains of three joints (every 12-joint quadruped) -------------
+// dof 0..5 = base, dof 6 + 3 leg + j = joint j of that leg (j = 0 hip abduction, 1 hip flexion, 2 knee); body b >= 1 carries
+// dof 5 + b.  The compact row of dof (leg, j) holds its 6 base couplings at t = 0..5 and its chain entries at t = 6..6+j.
+// Lane (leg = lane >> 3, t = lane & 7) keeps column t of its leg's three rows in registers: the leg blocks factorise with
+// four shuffles per level and no table look-ups (the generic path walks entry lists, subtree ranges and level tables).
+constexpr int QDLP = 9;   // compact row stride of the quadruped (maxdd + 1 = 9)
+struct QuadLeg { float k, h, a, i8, i7, i6, k7, k6, h6; };   // column t of the knee / hip-flexion / hip-abduction rows; inverse pivots; couplings
+
+__device__ __forceinline__ QuadLeg quad_factor_legs(float* s_L, float* s_invd, int lane) {
+  const int leg = lane >> 3, t = lane & 7, l0 = lane & 24;
+  const int rA = 6 + 3 * leg, rH = rA + 1, rK = rA + 2;
+  QuadLeg q;
+  q.k = s_L[rK * QDLP + t];
+  q.h = s_L[rH * QDLP + t];
+  q.a = t < 7 ? s_L[rA * QDLP + t] : 0.f;
+  const float k8 = s_L[rK * QDLP + 8];
+  q.i8 = rsqrt_nr(k8);
+  q.k *= q.i8;                                          // level 8: the knee row has no descendants
+  q.k7 = __shfl_sync(FULL, q.k, l0 + 7);
+  q.h -= q.k7 * q.k;                                    // level 7: hip flexion, descendant = knee
+  const float h7 = __shfl_sync(FULL, q.h, l0 + 7);
+  q.i7 = rsqrt_nr(h7);
+  q.h = (t == 7) ? h7 * q.i7 : q.h * q.i7;
+  q.k6 = __shfl_sync(FULL, q.k, l0 + 6); q.h6 = __shfl_sync(FULL, q.h, l0 + 6);
+  q.a -= q.k6 * q.k + q.h6 * q.h;                       // level 6: hip abduction, descendants = flexion, knee
+  const float a6 = __shfl_sync(FULL, q.a, l0 + 6);
+  q.i6 = rsqrt_nr(a6);
+  q.a = (t == 6) ? a6 * q.i6 : q.a * q.i6;
+  s_L[rK * QDLP + t] = q.k; s_L[rH * QDLP + t] = q.h;
+  if (t < 7) s_L[rA * QDLP + t] = q.a;
+  if (t == 0) { s_L[rK * QDLP + 8] = k8 * q.i8; s_invd[rK] = q.i8; s_invd[rH] = q.i7; s_invd[rA] = q.i6; }
+  return q;
+}
+
 // ------------------------------------------------------------------ the kernel -----------------
 // SNB > 0: compiled for the model dimensions (SNB, SNQ, SNV, SFL, SMAXDEPTH, SMAXDD) -- every table and
 // workspace offset is an immediate.  SNB == 0: generic, dimensions read from the blob header.
@@ -318,6 +361,8 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
   // the shuffle marks the warp index as warp-uniform for the compiler: the workspace base then lives in a uniform register
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   constexpr bool ST = SNB > 0;
+  // every 12-joint quadruped: the host selects this instance only when the parent table is base + 4 chains of 3 (pick_config)
+  constexpr bool QUAD = SNB == 13 && SNQ == 19 && SNV == 18 && SFL == 1 && SMAXDEPTH == 3 && SMAXDD == 8;
   constexpr Dims SD{SNB, SNQ, SNV, SFL, SMAXDEPTH, SMAXDD};
   constexpr WsLayout LS = make_ws_layout(SD);
   constexpr BlobHeader HS = make_blob_header(SD, 0, 0);
@@ -727,184 +772,316 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         s_b[i] = bi;
       }
       __syncwarp();
-      // ---- branch-sparse factorisation Mhat = L^T L, "pull" form, one dof-tree level at a time (deepest first):
-      //      L[i][t] = (M[i][t] - sum_{k in subtree(i), k != i} L[k][depth i] L[k][t]) / L[i][i]
-#pragma unroll 1
-      for (int lev = maxdd; lev >= nbase; lev--) {
-        const int e0 = entstart[lev], ne = entstart[lev + 1] - e0;
-#pragma unroll 1
-        for (int e = lane; e < ne; e += 32) {
-          const int pk = ent[e0 + e], i = pk & 255, t = pk >> 8;
-          float acc = s_L[i * DLP + t];
-          const int kend = i + dsub[i];
-#pragma unroll 1
-          for (int k = i + 1; k < kend; k++) acc -= s_L[k * DLP + lev] * s_L[k * DLP + t];
-          s_L[i * DLP + t] = acc;
-        }
+      if constexpr (QUAD) {
+        // ---- Mhat = L^T L with the topology compiled in: leg blocks in registers (quad_factor_legs), base block by 21 lanes
+        static_assert(!QUAD || make_blob_header(SD, 0, 0).dlp == QDLP, "compact row stride");
+        const QuadLeg ql = quad_factor_legs(s_L, s_invd, lane);
         __syncwarp();
-        const int d0 = lvl[lev], nd = lvl[lev + 1] - d0;
-        if (lane < nd) {
-          const int i = lvldofs[d0 + lane];
-          float d = sqrtf(s_L[i * DLP + lev]);
-          s_L[i * DLP + lev] = d;
-          s_invd[i] = 1.0f / d;
-        }
-        __syncwarp();
-#pragma unroll 1
-        for (int e = lane; e < ne; e += 32) {
-          const int pk = ent[e0 + e], i = pk & 255, t = pk >> 8;
-          if (t < lev) s_L[i * DLP + t] *= s_invd[i];
-        }
-        __syncwarp();
-      }
-      if (floating) {   // base 6x6 block: every other dof is a descendant of every base dof
         const int er = s_tri[lane] & 7, ec = s_tri[lane] >> 3;
         float val = 0.f;
         if (lane < 21) {
-          val = s_L[er * DLP + ec];
-#pragma unroll 4
-          for (int k = 6; k < nv; k++) val -= s_L[k * DLP + er] * s_L[k * DLP + ec];
+          val = s_L[er * QDLP + ec];
+#pragma unroll
+          for (int k = 6; k < 18; k++) val -= s_L[k * QDLP + er] * s_L[k * QDLP + ec];
         }
-#pragma unroll 1
+#pragma unroll
         for (int i = 5; i >= 0; i--) {
           const int ti = i * (i + 1) / 2;
-          float d = sqrtf(__shfl_sync(FULL, val, ti + i));
-          float inv = 1.0f / d;
-          if (er == i) val = (ec == i) ? d : val * inv;
-          float lir = __shfl_sync(FULL, val, ti + min(er, i));
-          float lic = __shfl_sync(FULL, val, ti + min(ec, i));
+          const float dd = __shfl_sync(FULL, val, ti + i);
+          const float inv = rsqrt_nr(dd);
+          if (er == i) val = (ec == i) ? dd * inv : val * inv;
+          const float lir = __shfl_sync(FULL, val, ti + min(er, i));
+          const float lic = __shfl_sync(FULL, val, ti + min(ec, i));
           if (lane < 21 && er < i) val -= lir * lic;
           if (lane == 0) s_invd[i] = inv;
         }
-        if (lane < 21) s_L[er * DLP + ec] = val;
-        __syncwarp();
-      }
-      // ---- z = L^-T b  (leaves to root)
-#pragma unroll 1
-      for (int lev = maxdd; lev >= nbase; lev--) {
-        const int d0 = lvl[lev], nd = lvl[lev + 1] - d0;
-        if (lane < nd) {
-          const int i = lvldofs[d0 + lane];
-          float acc = s_b[i];
-          const int kend = i + dsub[i];
-#pragma unroll 1
-          for (int k = i + 1; k < kend; k++) acc -= s_L[k * DLP + lev] * s_z[k];
-          s_z[i] = acc * s_invd[i];
-        }
-        __syncwarp();
-      }
-      if (floating) {
-        float acc = 0.f;
-        if (lane < 6) {
-          acc = s_b[lane];
-#pragma unroll 4
-          for (int k = 6; k < nv; k++) acc -= s_L[k * DLP + lane] * s_z[k];
-        }
-#pragma unroll 1
+        if (lane < 21) s_L[er * QDLP + ec] = val;
+        // ---- z = L^-T b: the three chain dofs of a leg in registers, then the base against every leg
+        const int leg = lane >> 3, t = lane & 7, rA = 6 + 3 * leg;
+        const float zK = s_b[rA + 2] * ql.i8;
+        const float zH = (s_b[rA + 1] - ql.k7 * zK) * ql.i7;
+        const float zA = (s_b[rA] - ql.h6 * zH - ql.k6 * zK) * ql.i6;
+        if (t == 0) { s_z[rA] = zA; s_z[rA + 1] = zH; s_z[rA + 2] = zK; }
+        float part = t < 6 ? ql.k * zK + ql.h * zH + ql.a * zA : 0.f;     // this leg's share of sum_k L[k][t] z_k
+        part += __shfl_xor_sync(FULL, part, 8);
+        part += __shfl_xor_sync(FULL, part, 16);
+        __syncwarp();          // the base block and invd[0..5] written above are read below
+        float acc = lane < 6 ? s_b[lane] - part : 0.f;
+#pragma unroll
         for (int i = 5; i >= 0; i--) {
-          float zi = __shfl_sync(FULL, acc, i) * s_invd[i];
-          if (lane < i) acc -= s_L[i * DLP + lane] * zi;
+          const float zi = __shfl_sync(FULL, acc, i) * s_invd[i];
+          if (lane < i) acc -= s_L[i * QDLP + lane] * zi;
           if (lane == i) s_z[i] = zi;
         }
         __syncwarp();
+      } else {
+        // ---- branch-sparse factorisation Mhat = L^T L, "pull" form, one dof-tree level at a time (deepest first):
+        //      L[i][t] = (M[i][t] - sum_{k in subtree(i), k != i} L[k][depth i] L[k][t]) / L[i][i]
+  #pragma unroll 1
+        for (int lev = maxdd; lev >= nbase; lev--) {
+          const int e0 = entstart[lev], ne = entstart[lev + 1] - e0;
+  #pragma unroll 1
+          for (int e = lane; e < ne; e += 32) {
+            const int pk = ent[e0 + e], i = pk & 255, t = pk >> 8;
+            float acc = s_L[i * DLP + t];
+            const int kend = i + dsub[i];
+  #pragma unroll 1
+            for (int k = i + 1; k < kend; k++) acc -= s_L[k * DLP + lev] * s_L[k * DLP + t];
+            s_L[i * DLP + t] = acc;
+          }
+          __syncwarp();
+          const int d0 = lvl[lev], nd = lvl[lev + 1] - d0;
+          if (lane < nd) {
+            const int i = lvldofs[d0 + lane];
+            float d = sqrtf(s_L[i * DLP + lev]);
+            s_L[i * DLP + lev] = d;
+            s_invd[i] = 1.0f / d;
+          }
+          __syncwarp();
+  #pragma unroll 1
+          for (int e = lane; e < ne; e += 32) {
+            const int pk = ent[e0 + e], i = pk & 255, t = pk >> 8;
+            if (t < lev) s_L[i * DLP + t] *= s_invd[i];
+          }
+          __syncwarp();
+        }
+        if (floating) {   // base 6x6 block: every other dof is a descendant of every base dof
+          const int er = s_tri[lane] & 7, ec = s_tri[lane] >> 3;
+          float val = 0.f;
+          if (lane < 21) {
+            val = s_L[er * DLP + ec];
+  #pragma unroll 4
+            for (int k = 6; k < nv; k++) val -= s_L[k * DLP + er] * s_L[k * DLP + ec];
+          }
+  #pragma unroll 1
+          for (int i = 5; i >= 0; i--) {
+            const int ti = i * (i + 1) / 2;
+            float d = sqrtf(__shfl_sync(FULL, val, ti + i));
+            float inv = 1.0f / d;
+            if (er == i) val = (ec == i) ? d : val * inv;
+            float lir = __shfl_sync(FULL, val, ti + min(er, i));
+            float lic = __shfl_sync(FULL, val, ti + min(ec, i));
+            if (lane < 21 && er < i) val -= lir * lic;
+            if (lane == 0) s_invd[i] = inv;
+          }
+          if (lane < 21) s_L[er * DLP + ec] = val;
+          __syncwarp();
+        }
+        // ---- z = L^-T b  (leaves to root)
+  #pragma unroll 1
+        for (int lev = maxdd; lev >= nbase; lev--) {
+          const int d0 = lvl[lev], nd = lvl[lev + 1] - d0;
+          if (lane < nd) {
+            const int i = lvldofs[d0 + lane];
+            float acc = s_b[i];
+            const int kend = i + dsub[i];
+  #pragma unroll 1
+            for (int k = i + 1; k < kend; k++) acc -= s_L[k * DLP + lev] * s_z[k];
+            s_z[i] = acc * s_invd[i];
+          }
+          __syncwarp();
+        }
+        if (floating) {
+          float acc = 0.f;
+          if (lane < 6) {
+            acc = s_b[lane];
+  #pragma unroll 4
+            for (int k = 6; k < nv; k++) acc -= s_L[k * DLP + lane] * s_z[k];
+          }
+  #pragma unroll 1
+          for (int i = 5; i >= 0; i--) {
+            float zi = __shfl_sync(FULL, acc, i) * s_invd[i];
+            if (lane < i) acc -= s_L[i * DLP + lane] * zi;
+            if (lane == i) s_z[i] = zi;
+          }
+          __syncwarp();
+        }
       }
       // ---- Y = L^-T J^T, one constraint row per lane, only along the row's own ancestor chain
       float u_c = 0.f;
-      if (lane < CR) {
-        const int c = lane;
-        const bool is_lim = c >= C3;
-        const float* ct = s_ct + (is_lim ? 0 : c / 3) * CT_WORDS;
-        const float* lm = s_lim + 4 * (is_lim ? c - C3 : 0);
-        const int d = c % 3;
-        const int fo = (d == 0) ? CF_T1 : (d == 1 ? CF_T2 : CF_N);
-        const f3 axd = mk(ct[fo], ct[fo + 1], ct[fo + 2]);
-        const f3 pos = mk(ct[CF_POS], ct[CF_POS + 1], ct[CF_POS + 2]);
-        const int i0 = is_lim ? __float_as_int(lm[0]) : bdof[__float_as_int(ct[CF_BODY])];
-        const int m = i0 >= 0 ? ddepth[i0] : -1;
-        float jv = 0.f;
-        if (is_lim) {   // J = sign * e_dof
-#pragma unroll 1
-          for (int t = 0; t < m; t++) s_Y[t * CP + c] = 0.f;
-          s_Y[m * CP + c] = lm[1];
-          jv = lm[1] * s_gv[i0];
-        } else {
-          if (floating) {
-            f3 rc = cross(pos - O, axd);
-            s_Y[0 * CP + c] = axd.x; s_Y[1 * CP + c] = axd.y; s_Y[2 * CP + c] = axd.z;
-            s_Y[3 * CP + c] = rc.x; s_Y[4 * CP + c] = rc.y; s_Y[5 * CP + c] = rc.z;
+      int row_lm = 5;          // QUAD: (leg << 4) | depth of this lane's row (chain = base dofs 0..5, then 3 leg + t for t = 6..depth)
+      if constexpr (QUAD) {
+        if (lane < CR) {
+          const int c = lane;
+          const bool is_lim = c >= C3;
+          const float* ct = s_ct + (is_lim ? 0 : c / 3) * CT_WORDS;
+          const float* lm = s_lim + 4 * (is_lim ? c - C3 : 0);
+          const int d = c % 3;
+          const int fo = (d == 0) ? CF_T1 : (d == 1 ? CF_T2 : CF_N);
+          const f3 axd = mk(ct[fo], ct[fo + 1], ct[fo + 2]);
+          const f3 pos = mk(ct[CF_POS], ct[CF_POS + 1], ct[CF_POS + 2]);
+          const int i0 = is_lim ? __float_as_int(lm[0]) : 5 + __float_as_int(ct[CF_BODY]);   // body b >= 1 carries dof 5 + b; the base "dof" is 5
+          const int leg = i0 >= 6 ? (i0 - 6) / 3 : 0;
+          const int m = i0 >= 6 ? i0 - 3 * leg : 5;                                           // depth of that dof in the dof tree
+          row_lm = (leg << 4) | m;
+          float y[9];
+          float jv;
+          if (is_lim) {   // J = sign * e_dof
+#pragma unroll
+            for (int t = 0; t < 9; t++) y[t] = (t == m) ? lm[1] : 0.f;
+            jv = lm[1] * s_gv[i0];
+          } else {
+            const f3 rc = cross(pos - O, axd);
+            y[0] = axd.x; y[1] = axd.y; y[2] = axd.z; y[3] = rc.x; y[4] = rc.y; y[5] = rc.z;
             jv = axd.x * s_gv[0] + axd.y * s_gv[1] + axd.z * s_gv[2] + rc.x * s_gv[3] + rc.y * s_gv[4] + rc.z * s_gv[5];
-          }
-#pragma unroll 1
-          for (int t = nbase; t <= m; t++) {
-            const int a_t = danc[t * nvp + i0], j = dbody[a_t];
-            f3 aj = mk(s_pose[(PF_A + 0) * nbp + j], s_pose[(PF_A + 1) * nbp + j], s_pose[(PF_A + 2) * nbp + j]);
-            f3 col = aj;
-            if (bodyi[BF_JTYPE * nbp + j] == 1) {
-              f3 pj = mk(s_pose[(PF_P + 0) * nbp + j], s_pose[(PF_P + 1) * nbp + j], s_pose[(PF_P + 2) * nbp + j]);
-              col = cross(aj, pos - pj);
+#pragma unroll
+            for (int t = 6; t < 9; t++) {
+              y[t] = 0.f;
+              if (t <= m) {
+                const int j = 3 * leg + t - 5;         // body of chain dof 3 leg + t
+                const f3 aj = mk(s_pose[(PF_A + 0) * nbp + j], s_pose[(PF_A + 1) * nbp + j], s_pose[(PF_A + 2) * nbp + j]);
+                f3 col = aj;
+                if (bodyi[BF_JTYPE * nbp + j] == 1) {
+                  const f3 pj = mk(s_pose[(PF_P + 0) * nbp + j], s_pose[(PF_P + 1) * nbp + j], s_pose[(PF_P + 2) * nbp + j]);
+                  col = cross(aj, pos - pj);
+                }
+                y[t] = dot(col, axd);
+                jv += y[t] * s_gv[3 * leg + t];
+              }
             }
-            float val = dot(col, axd);
-            s_Y[t * CP + c] = val;
-            jv += val * s_gv[a_t];
           }
-        }
-        float yz = 0.f;
-        if constexpr (ST && SMAXDD + 1 <= 9) {
-          // whole chain in registers (compile-time indices): 2 instructions per multiply-add instead of 4
-          constexpr int DLc = SMAXDD + 1;
-          float y[DLc];
+          float yz = 0.f;
 #pragma unroll
-          for (int t = 0; t < DLc; t++) y[t] = (t <= m) ? s_Y[t * CP + c] : 0.f;
-#pragma unroll
-          for (int sI = DLc - 1; sI >= 0; sI--) {
+          for (int sI = 8; sI >= 0; sI--) {
             if (sI <= m) {
-              const int a_s = danc[sI * nvp + i0];
+              const int a_s = sI < 6 ? sI : 3 * leg + sI;
               const float ys = y[sI] * s_invd[a_s];
               y[sI] = ys;
               yz += ys * s_z[a_s];
 #pragma unroll
-              for (int t = 0; t < sI; t++) y[t] -= s_L[a_s * DLP + t] * ys;
+              for (int t = 0; t < sI; t++) y[t] -= s_L[a_s * QDLP + t] * ys;
             }
           }
 #pragma unroll
-          for (int t = 0; t < DLc; t++) if (t <= m) s_Y[t * CP + c] = y[t];
-        } else {
-#pragma unroll 1
-          for (int sI = m; sI >= 0; sI--) {
-            const int a_s = danc[sI * nvp + i0];
-            float y = s_Y[sI * CP + c] * s_invd[a_s];
-            s_Y[sI * CP + c] = y;
-            yz += y * s_z[a_s];
-#pragma unroll 1
-            for (int t = 0; t < sI; t++) s_Y[t * CP + c] -= s_L[a_s * DLP + t] * y;
+          for (int t = 0; t < 9; t++) if (t <= m) s_Y[t * CP + c] = y[t];
+          u_c = jv + args.prm.dt * yz;
+          if (is_lim) u_c -= args.prm.erp * lm[2] / args.prm.dt;
+          else if (d == 2) {
+            float target = args.prm.erp * ct[CF_DEPTH] / args.prm.dt;
+            if (args.prm.restitution > 0.f && jv < -args.prm.rest_threshold) target += -args.prm.restitution * jv;
+            u_c -= target;
           }
         }
-        u_c = jv + args.prm.dt * yz;
-        if (is_lim) u_c -= args.prm.erp * lm[2] / args.prm.dt;
-        else if (d == 2) {
-          float target = args.prm.erp * ct[CF_DEPTH] / args.prm.dt;
-          if (args.prm.restitution > 0.f && jv < -args.prm.rest_threshold) target += -args.prm.restitution * jv;
-          u_c -= target;
+      } else {
+        if (lane < CR) {
+          const int c = lane;
+          const bool is_lim = c >= C3;
+          const float* ct = s_ct + (is_lim ? 0 : c / 3) * CT_WORDS;
+          const float* lm = s_lim + 4 * (is_lim ? c - C3 : 0);
+          const int d = c % 3;
+          const int fo = (d == 0) ? CF_T1 : (d == 1 ? CF_T2 : CF_N);
+          const f3 axd = mk(ct[fo], ct[fo + 1], ct[fo + 2]);
+          const f3 pos = mk(ct[CF_POS], ct[CF_POS + 1], ct[CF_POS + 2]);
+          const int i0 = is_lim ? __float_as_int(lm[0]) : bdof[__float_as_int(ct[CF_BODY])];
+          const int m = i0 >= 0 ? ddepth[i0] : -1;
+          float jv = 0.f;
+          if (is_lim) {   // J = sign * e_dof
+  #pragma unroll 1
+            for (int t = 0; t < m; t++) s_Y[t * CP + c] = 0.f;
+            s_Y[m * CP + c] = lm[1];
+            jv = lm[1] * s_gv[i0];
+          } else {
+            if (floating) {
+              f3 rc = cross(pos - O, axd);
+              s_Y[0 * CP + c] = axd.x; s_Y[1 * CP + c] = axd.y; s_Y[2 * CP + c] = axd.z;
+              s_Y[3 * CP + c] = rc.x; s_Y[4 * CP + c] = rc.y; s_Y[5 * CP + c] = rc.z;
+              jv = axd.x * s_gv[0] + axd.y * s_gv[1] + axd.z * s_gv[2] + rc.x * s_gv[3] + rc.y * s_gv[4] + rc.z * s_gv[5];
+            }
+  #pragma unroll 1
+            for (int t = nbase; t <= m; t++) {
+              const int a_t = danc[t * nvp + i0], j = dbody[a_t];
+              f3 aj = mk(s_pose[(PF_A + 0) * nbp + j], s_pose[(PF_A + 1) * nbp + j], s_pose[(PF_A + 2) * nbp + j]);
+              f3 col = aj;
+              if (bodyi[BF_JTYPE * nbp + j] == 1) {
+                f3 pj = mk(s_pose[(PF_P + 0) * nbp + j], s_pose[(PF_P + 1) * nbp + j], s_pose[(PF_P + 2) * nbp + j]);
+                col = cross(aj, pos - pj);
+              }
+              float val = dot(col, axd);
+              s_Y[t * CP + c] = val;
+              jv += val * s_gv[a_t];
+            }
+          }
+          float yz = 0.f;
+          if constexpr (ST && SMAXDD + 1 <= 9) {
+            // whole chain in registers (compile-time indices): 2 instructions per multiply-add instead of 4
+            constexpr int DLc = SMAXDD + 1;
+            float y[DLc];
+  #pragma unroll
+            for (int t = 0; t < DLc; t++) y[t] = (t <= m) ? s_Y[t * CP + c] : 0.f;
+  #pragma unroll
+            for (int sI = DLc - 1; sI >= 0; sI--) {
+              if (sI <= m) {
+                const int a_s = danc[sI * nvp + i0];
+                const float ys = y[sI] * s_invd[a_s];
+                y[sI] = ys;
+                yz += ys * s_z[a_s];
+  #pragma unroll
+                for (int t = 0; t < sI; t++) y[t] -= s_L[a_s * DLP + t] * ys;
+              }
+            }
+  #pragma unroll
+            for (int t = 0; t < DLc; t++) if (t <= m) s_Y[t * CP + c] = y[t];
+          } else {
+  #pragma unroll 1
+            for (int sI = m; sI >= 0; sI--) {
+              const int a_s = danc[sI * nvp + i0];
+              float y = s_Y[sI * CP + c] * s_invd[a_s];
+              s_Y[sI * CP + c] = y;
+              yz += y * s_z[a_s];
+  #pragma unroll 1
+              for (int t = 0; t < sI; t++) s_Y[t * CP + c] -= s_L[a_s * DLP + t] * y;
+            }
+          }
+          u_c = jv + args.prm.dt * yz;
+          if (is_lim) u_c -= args.prm.erp * lm[2] / args.prm.dt;
+          else if (d == 2) {
+            float target = args.prm.erp * ct[CF_DEPTH] / args.prm.dt;
+            if (args.prm.restitution > 0.f && jv < -args.prm.rest_threshold) target += -args.prm.restitution * jv;
+            u_c -= target;
+          }
         }
       }
       iters = 0; resid = 0.f; gs_status = RSB_SOLVER_CONVERGED;
       if (CR > 0) {
         __syncwarp();      // h / b / poses are dead from here: G overlays them
         // G = Y^T Y; rows a, b share ancestors exactly up to the depth of their bodies' LCA
-        {
-          const int ng = 32 / CR;                   // CR <= 28 -> ng >= 1
+        if constexpr (QUAD) {
+          const int ng = 32 / CR;
           const int a = lane % CR, g = lane / CR;
-          if (g < ng) {
-            const int ba = a < C3 ? __float_as_int(s_ct[(a / 3) * CT_WORDS + CF_BODY]) : dbody[__float_as_int(s_lim[4 * (a - C3)])];
+          const int pa = __shfl_sync(FULL, row_lm, a);
+          const int nit = (CR / 2 + ng) / ng;              // ceil((CR / 2 + 1) / ng): every lane runs the same trip count (warp-wide shuffle inside)
 #pragma unroll 1
-            for (int dd = g; dd <= CR / 2; dd += ng) {
-              int bcol = a + dd; if (bcol >= CR) bcol -= CR;
-              const int bbody = bcol < C3 ? __float_as_int(s_ct[(bcol / 3) * CT_WORDS + CF_BODY]) : dbody[__float_as_int(s_lim[4 * (bcol - C3)])];
-              const int tmax = lcad[ba * nbp + bbody];
+          for (int itr = 0; itr < nit; itr++) {
+            const int dd = g + itr * ng;
+            const bool active = g < ng && dd <= CR / 2;
+            int bcol = a + dd; if (bcol >= CR) bcol -= CR;
+            if (!active) bcol = 0;
+            const int pb = __shfl_sync(FULL, row_lm, bcol);
+            // same leg: the chains agree down to the shallower of the two; different legs (or a base row): the six base dofs only
+            const int tmax = ((pa ^ pb) >> 4) == 0 ? min(pa & 15, pb & 15) : 5;
+            if (active) {
               float sacc = 0.f;
-#pragma unroll 1
-              for (int t = 0; t <= tmax; t++) sacc += s_Y[t * CP + a] * s_Y[t * CP + bcol];
+#pragma unroll
+              for (int t = 0; t < 9; t++) if (t <= tmax) sacc += s_Y[t * CP + a] * s_Y[t * CP + bcol];
               s_G[a * GP + bcol] = sacc; s_G[bcol * GP + a] = sacc;
+            }
+          }
+        } else {
+          {
+            const int ng = 32 / CR;                   // CR <= 28 -> ng >= 1
+            const int a = lane % CR, g = lane / CR;
+            if (g < ng) {
+              const int ba = a < C3 ? __float_as_int(s_ct[(a / 3) * CT_WORDS + CF_BODY]) : dbody[__float_as_int(s_lim[4 * (a - C3)])];
+  #pragma unroll 1
+              for (int dd = g; dd <= CR / 2; dd += ng) {
+                int bcol = a + dd; if (bcol >= CR) bcol -= CR;
+                const int bbody = bcol < C3 ? __float_as_int(s_ct[(bcol / 3) * CT_WORDS + CF_BODY]) : dbody[__float_as_int(s_lim[4 * (bcol - C3)])];
+                const int tmax = lcad[ba * nbp + bbody];
+                float sacc = 0.f;
+  #pragma unroll 1
+                for (int t = 0; t <= tmax; t++) sacc += s_Y[t * CP + a] * s_Y[t * CP + bcol];
+                s_G[a * GP + bcol] = sacc; s_G[bcol * GP + a] = sacc;
+              }
             }
           }
         }
@@ -935,48 +1112,87 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       if (args.prof && lane == 0) args.prof[((size_t)env * 4 + (sub & 3)) * 8 + 4] = (unsigned)clock64();
       if (args.substep_barrier >= 3) asm volatile("bar.sync 1, %0;" ::"r"(bar_threads));
       // =========================== stage E: v+ = v + L^-1 (dt z + Y lam), integration ============
-#pragma unroll 1
-      for (int i = lane; i < nv; i += 32) {   // w = dt z + Y lam, gathered per dof over the contacts whose chain holds it
+      if constexpr (QUAD) {
+        // w_i = dt z_i + sum over the rows whose chain holds dof i of Y[depth i][row] lam_row, lane = dof
+        const int i = min(lane, 17);
+        const int legi = i >= 6 ? (i - 6) / 3 : 0, di = i >= 6 ? i - 3 * legi : i;
         float sacc = args.prm.dt * s_z[i];
-        const int di = ddepth[i];
 #pragma unroll 1
         for (int k = 0; k < K; k++) {
-          const int i0 = bdof[__float_as_int(s_ct[k * CT_WORDS + CF_BODY])];
-          if (i0 >= 0 && ddepth[i0] >= di && danc[di * nvp + i0] == i)
+          const int pr = __shfl_sync(FULL, row_lm, 3 * k);
+          if (i < 6 || ((pr >> 4) == legi && (pr & 15) >= di))
             sacc += s_Y[di * CP + 3 * k] * s_lam[3 * k] + s_Y[di * CP + 3 * k + 1] * s_lam[3 * k + 1] + s_Y[di * CP + 3 * k + 2] * s_lam[3 * k + 2];
         }
 #pragma unroll 1
         for (int l = 0; l < Lm; l++) {
-          const int i0 = __float_as_int(s_lim[4 * l]);
-          if (ddepth[i0] >= di && danc[di * nvp + i0] == i) sacc += s_Y[di * CP + C3 + l] * s_lam[C3 + l];
+          const int pr = __shfl_sync(FULL, row_lm, C3 + l);
+          if (i < 6 || ((pr >> 4) == legi && (pr & 15) >= di)) sacc += s_Y[di * CP + C3 + l] * s_lam[C3 + l];
         }
-        s_rhs[i] = sacc;
-      }
-      __syncwarp();
-      if (floating) {   // x = L^-1 w, root to leaves: base chain by shuffles, then one tree level at a time
-        float acc = lane < 6 ? s_rhs[lane] : 0.f;
-#pragma unroll 1
-        for (int t = 0; t < 6; t++) {
-          float xt = __shfl_sync(FULL, acc, t) * s_invd[t];
-          if (lane > t && lane < 6) acc -= s_L[lane * DLP + t] * xt;
-          if (lane == t) s_rhs[t] = xt;
-        }
-        __syncwarp();
-      }
-#pragma unroll 1
-      for (int lev = nbase; lev <= maxdd; lev++) {
-        const int d0 = lvl[lev], nd = lvl[lev + 1] - d0;
-        if (lane < nd) {
-          const int i = lvldofs[d0 + lane];
-          float acc = s_rhs[i];
-          // base dofs are ancestors of every other dof and are their own index: no ancestor lookup
+        // x = L^-1 w, root to leaves: the base chain by shuffles, then the three joints of every leg by shuffles from the parent lanes
+        float acc = lane < 6 ? sacc : 0.f;
 #pragma unroll
-          for (int t = 0; t < 6; t++) if (t < nbase) acc -= s_L[i * DLP + t] * s_rhs[t];
-#pragma unroll 1
-          for (int t = nbase; t < lev; t++) acc -= s_L[i * DLP + t] * s_rhs[danc[t * nvp + i]];
-          s_rhs[i] = acc * s_invd[i];
+        for (int t = 0; t < 6; t++) {
+          const float xt = __shfl_sync(FULL, acc, t) * s_invd[t];
+          if (lane > t && lane < 6) acc -= s_L[lane * QDLP + t] * xt;
+          if (lane == t) acc = xt;
+        }
+        // acc (lanes 0..5) = x of the base dofs
+        float legacc = sacc;
+#pragma unroll
+        for (int t = 0; t < 6; t++) legacc -= s_L[i * QDLP + t] * __shfl_sync(FULL, acc, t);
+        const int j = i >= 6 ? di - 6 : 0;
+        const float inv = s_invd[i];
+        const float x0 = legacc * inv;                                            // joint 0 of a leg
+        const float xa1 = __shfl_up_sync(FULL, x0, 1);
+        const float x1 = (legacc - s_L[i * QDLP + 6] * xa1) * inv;               // joint 1: parent = joint 0
+        const float xa2 = __shfl_up_sync(FULL, x0, 2), xh2 = __shfl_up_sync(FULL, x1, 1);
+        const float x2 = (legacc - s_L[i * QDLP + 6] * xa2 - s_L[i * QDLP + 7] * xh2) * inv;   // joint 2: ancestors = joints 0, 1
+        if (lane < 18) s_rhs[lane] = lane < 6 ? acc : (j == 0 ? x0 : (j == 1 ? x1 : x2));
+        __syncwarp();
+      } else {
+  #pragma unroll 1
+        for (int i = lane; i < nv; i += 32) {   // w = dt z + Y lam, gathered per dof over the contacts whose chain holds it
+          float sacc = args.prm.dt * s_z[i];
+          const int di = ddepth[i];
+  #pragma unroll 1
+          for (int k = 0; k < K; k++) {
+            const int i0 = bdof[__float_as_int(s_ct[k * CT_WORDS + CF_BODY])];
+            if (i0 >= 0 && ddepth[i0] >= di && danc[di * nvp + i0] == i)
+              sacc += s_Y[di * CP + 3 * k] * s_lam[3 * k] + s_Y[di * CP + 3 * k + 1] * s_lam[3 * k + 1] + s_Y[di * CP + 3 * k + 2] * s_lam[3 * k + 2];
+          }
+  #pragma unroll 1
+          for (int l = 0; l < Lm; l++) {
+            const int i0 = __float_as_int(s_lim[4 * l]);
+            if (ddepth[i0] >= di && danc[di * nvp + i0] == i) sacc += s_Y[di * CP + C3 + l] * s_lam[C3 + l];
+          }
+          s_rhs[i] = sacc;
         }
         __syncwarp();
+        if (floating) {   // x = L^-1 w, root to leaves: base chain by shuffles, then one tree level at a time
+          float acc = lane < 6 ? s_rhs[lane] : 0.f;
+  #pragma unroll 1
+          for (int t = 0; t < 6; t++) {
+            float xt = __shfl_sync(FULL, acc, t) * s_invd[t];
+            if (lane > t && lane < 6) acc -= s_L[lane * DLP + t] * xt;
+            if (lane == t) s_rhs[t] = xt;
+          }
+          __syncwarp();
+        }
+  #pragma unroll 1
+        for (int lev = nbase; lev <= maxdd; lev++) {
+          const int d0 = lvl[lev], nd = lvl[lev + 1] - d0;
+          if (lane < nd) {
+            const int i = lvldofs[d0 + lane];
+            float acc = s_rhs[i];
+            // base dofs are ancestors of every other dof and are their own index: no ancestor lookup
+  #pragma unroll
+            for (int t = 0; t < 6; t++) if (t < nbase) acc -= s_L[i * DLP + t] * s_rhs[t];
+  #pragma unroll 1
+            for (int t = nbase; t < lev; t++) acc -= s_L[i * DLP + t] * s_rhs[danc[t * nvp + i]];
+            s_rhs[i] = acc * s_invd[i];
+          }
+          __syncwarp();
+        }
       }
 #pragma unroll 1
       for (int i = lane; i < nv; i += 32) {
