@@ -98,6 +98,11 @@ typedef struct rsb_model_tables {
   const double *csize, *cpos, *crot;
   const int *pt_body, *pt_coll, *pt_feat;
   const double *pt_pos, *pt_rad;
+  /* contact candidates are typed: 0 = sphere of radius pt_rad at pt_pos (radius 0: box corner / cylinder rim sample), 1 = the
+   * segment pt_pos .. pt_pos2 swept by pt_rad (capsule / cylinder side), 2 = the box of collision body pt_coll against terrain
+   * vertices; types 1 and 2 come after the points and act on height maps only */
+  const int* pt_type;
+  const double* pt_pos2;
 } rsb_model_tables;
 
 /* zero-copy device view (rows are padded: element (env, i) of X lives at X[env * X_stride + i]) */

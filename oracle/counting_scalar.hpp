@@ -54,4 +54,5 @@ inline orc::Cnt cos(orc::Cnt a) { orc::flop_counters().trig++; return orc::Cnt(s
 inline orc::Cnt fabs(orc::Cnt a) { return orc::Cnt(std::fabs(a.v)); }
 inline orc::Cnt pow(orc::Cnt a, orc::Cnt b) { orc::flop_counters().trig++; return orc::Cnt(std::pow(a.v, b.v)); }
 inline bool isfinite(orc::Cnt a) { return std::isfinite(a.v); }
+inline orc::Cnt floor(orc::Cnt a) { return orc::Cnt(std::floor(a.v)); }
 }  // namespace std

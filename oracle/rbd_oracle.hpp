@@ -75,6 +75,11 @@ struct ModelDesc {   // plain-C description handed over the oracle's C API (all 
   int npts;
   const int *pt_body;
   const double *pt_pos, *pt_rad;
+  // typed candidates (model.hpp FeatType): 0 point / sphere, 1 segment pt_pos .. pt_pos2 swept by pt_rad, 2 box of collision body pt_coll
+  const int *pt_type, *pt_coll;      // may be null: every candidate is a point
+  const double* pt_pos2;
+  int ncoll;
+  const double *coll_size, *coll_pos, *coll_rot;   // [ncoll][3], [ncoll][3], [ncoll][9]: half extents and body-frame pose of the collision bodies
 };
 
 struct Params {
@@ -152,8 +157,9 @@ template <typename T> struct Workspace {
 template <typename T> class Sim {
  public:
   int nb, nq, nv, floating, npts;
-  std::vector<int> parent, jtype, qidx, vidx, pt_body;
-  std::vector<V3<T>> jpos, axis, com, pt_pos;
+  std::vector<int> parent, jtype, qidx, vidx, pt_body, pt_type, pt_coll;
+  std::vector<V3<T>> jpos, axis, com, pt_pos, pt_pos2, coll_size, coll_pos;
+  std::vector<M3<T>> coll_rot;
   std::vector<M3<T>> jrot;
   std::vector<T> mass, inertia, pt_rad, jlo, jhi, pt_mu;   // pt_mu < 0: default material friction
   Params prm;
@@ -180,6 +186,17 @@ template <typename T> class Sim {
     for (int i = 0; i < npts; i++) {
       pt_pos[i] = {T(d.pt_pos[3 * i]), T(d.pt_pos[3 * i + 1]), T(d.pt_pos[3 * i + 2])};
       pt_rad[i] = T(d.pt_rad[i]);
+    }
+    pt_type.assign(npts, 0); pt_coll.assign(npts, 0); pt_pos2 = pt_pos;
+    if (d.pt_type) {
+      pt_type.assign(d.pt_type, d.pt_type + npts); pt_coll.assign(d.pt_coll, d.pt_coll + npts);
+      for (int i = 0; i < npts; i++) pt_pos2[i] = {T(d.pt_pos2[3 * i]), T(d.pt_pos2[3 * i + 1]), T(d.pt_pos2[3 * i + 2])};
+      coll_size.resize(d.ncoll); coll_pos.resize(d.ncoll); coll_rot.resize(d.ncoll);
+      for (int c = 0; c < d.ncoll; c++) {
+        coll_size[c] = {T(d.coll_size[3 * c]), T(d.coll_size[3 * c + 1]), T(d.coll_size[3 * c + 2])};
+        coll_pos[c] = {T(d.coll_pos[3 * c]), T(d.coll_pos[3 * c + 1]), T(d.coll_pos[3 * c + 2])};
+        for (int k = 0; k < 9; k++) coll_rot[c].m[k] = T(d.coll_rot[9 * c + k]);
+      }
     }
     // direction tables of the slip search: round r covers a bracket of width 2*pi/32^r in 32 sections
     for (int r = 0; r < NROUNDS; r++) {
@@ -377,26 +394,207 @@ template <typename T> class Sim {
     return true;
   }
 
+  // ---- height-map geometry (shape against every triangle under the shape's AABB) -------------------
+  // Cell (ix, iy) holds two triangles split along the diagonal P00-P11: tri 0 = (P00, P10, P11), tri 1 = (P00, P11, P01).
+  struct HmGrid { T x0, y0, dx, dy; int xs, ys; const T* H; };
+  HmGrid grid(int hm_offset) const {
+    return {T(ter.cx) - T(0.5) * T(ter.x_size), T(ter.cy) - T(0.5) * T(ter.y_size), T(ter.x_size) / T(ter.xs - 1), T(ter.y_size) / T(ter.ys - 1), ter.xs, ter.ys,
+            hmap.data() + hm_offset};
+  }
+  static V3<T> vertex(const HmGrid& g, int ix, int iy) { return {g.x0 + T(ix) * g.dx, g.y0 + T(iy) * g.dy, g.H[iy * g.xs + ix]}; }
+  // closest point of triangle (a, b, c) to p (Ericson, Real-Time Collision Detection 5.1.5: Voronoi regions of the triangle)
+  static V3<T> closest_on_triangle(V3<T> p, V3<T> a, V3<T> b, V3<T> c) {
+    const V3<T> ab = b - a, ac = c - a, ap = p - a;
+    const T d1 = dot(ab, ap), d2 = dot(ac, ap);
+    if (d1 <= T(0) && d2 <= T(0)) return a;
+    const V3<T> bp = p - b;
+    const T d3 = dot(ab, bp), d4 = dot(ac, bp);
+    if (d3 >= T(0) && d4 <= d3) return b;
+    const T vc = d1 * d4 - d3 * d2;
+    if (vc <= T(0) && d1 >= T(0) && d3 <= T(0)) return a + (d1 / (d1 - d3)) * ab;
+    const V3<T> cp = p - c;
+    const T d5 = dot(ab, cp), d6 = dot(ac, cp);
+    if (d6 >= T(0) && d5 <= d6) return c;
+    const T vb = d5 * d2 - d1 * d6;
+    if (vb <= T(0) && d2 >= T(0) && d6 <= T(0)) return a + (d2 / (d2 - d6)) * ac;
+    const T va = d3 * d6 - d5 * d4;
+    if (va <= T(0) && (d4 - d3) >= T(0) && (d5 - d6) >= T(0)) return b + ((d4 - d3) / ((d4 - d3) + (d5 - d6))) * (c - b);
+    const T den = T(1) / (va + vb + vc);
+    return a + (vb * den) * ab + (vc * den) * ac;
+  }
+  // closest points of segments p1 + s d1 and p2 + t d2, s, t in [0, 1] (Ericson 5.1.9)
+  static void closest_segments(V3<T> p1, V3<T> d1, V3<T> p2, V3<T> d2, T& s, T& t) {
+    const V3<T> r = p1 - p2;
+    const T a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r), eps = T(1e-12);
+    if (a <= eps && e <= eps) { s = t = T(0); return; }
+    if (a <= eps) { s = T(0); t = std::min(std::max(f / e, T(0)), T(1)); return; }
+    const T c = dot(d1, r);
+    if (e <= eps) { t = T(0); s = std::min(std::max(-c / a, T(0)), T(1)); return; }
+    const T b = dot(d1, d2), den = a * e - b * b;
+    s = den > eps * a * e ? std::min(std::max((b * f - c * e) / den, T(0)), T(1)) : T(0);
+    t = (b * s + f) / e;
+    if (t < T(0)) { t = T(0); s = std::min(std::max(-c / a, T(0)), T(1)); }
+    else if (t > T(1)) { t = T(1); s = std::min(std::max((b - c) / a, T(0)), T(1)); }
+  }
+  // One candidate of a feature loop: keeps the deepest contact; a later triangle must be deeper by more than TIE to replace an
+  // earlier one (two triangles that share the touched edge give the same depth to rounding: the lower pair index wins everywhere).
+  struct Best { bool hit = false; T depth = 0; V3<T> n{0, 0, 1}, pos{0, 0, 0}; int pair = 0; };
+  static void offer(Best& b, T depth, V3<T> n, V3<T> pos, int pair) {
+    if (!(depth > T(0))) return;
+    if (!b.hit || depth > b.depth + T(1e-6)) { b.hit = true; b.depth = depth; b.n = n; b.pos = pos; b.pair = pair; }
+  }
+  static V3<T> tri_normal(V3<T> a, V3<T> b, V3<T> c) {
+    V3<T> n = cross(b - a, c - a);
+    T inv = T(1) / std::sqrt(dot(n, n));
+    if (n.z < T(0)) inv = -inv;
+    return inv * n;
+  }
+  // cells [ix0, ix1] x [iy0, iy1] under the axis-aligned box [lo, hi], at most 3 x 3 around the cell of the centre
+  static bool cell_range(const HmGrid& g, T lox, T hix, T loy, T hiy, T cxp, T cyp, int& ix0, int& ix1, int& iy0, int& iy1) {
+    const T gx = (cxp - g.x0) / g.dx, gy = (cyp - g.y0) / g.dy;
+    if (!(gx >= T(0)) || !(gy >= T(0)) || !(gx < T(g.xs - 1)) || !(gy < T(g.ys - 1))) return false;
+    const int cx = int(gx), cy = int(gy);
+    ix0 = std::max(std::max(int(std::floor((lox - g.x0) / g.dx)), cx - 1), 0); ix1 = std::min(std::min(int(std::floor((hix - g.x0) / g.dx)), cx + 1), g.xs - 2);
+    iy0 = std::max(std::max(int(std::floor((loy - g.y0) / g.dy)), cy - 1), 0); iy1 = std::min(std::min(int(std::floor((hiy - g.y0) / g.dy)), cy + 1), g.ys - 2);
+    return true;
+  }
+  // sphere (centre C, radius r > 0) against the triangles under its AABB: the terrain point closest to the centre decides.
+  // Centre above the surface (the usual case): depth = r - distance, pushed out along the line to that point (face, edge or vertex);
+  // centre under the surface (deep penetration): depth = r + distance, pushed out along that triangle's normal.
+  void sphere_vs_heightmap(const HmGrid& g, V3<T> C, T r, Best& best) const {
+    int ix0, ix1, iy0, iy1;
+    if (!cell_range(g, C.x - r, C.x + r, C.y - r, C.y + r, C.x, C.y, ix0, ix1, iy0, iy1)) return;
+    bool have = false, inside = false; T dmin = 0; V3<T> qn{0, 0, 1}, qv{0, 0, 0}; int qpair = 0;
+    const int ccx = int((C.x - g.x0) / g.dx), ccy = int((C.y - g.y0) / g.dy);
+    for (int iy = iy0; iy <= iy1; iy++) for (int ix = ix0; ix <= ix1; ix++) {
+      const V3<T> p00 = vertex(g, ix, iy), p10 = vertex(g, ix + 1, iy), p01 = vertex(g, ix, iy + 1), p11 = vertex(g, ix + 1, iy + 1);
+      for (int tri = 0; tri < 2; tri++) {
+        const V3<T> a = p00, b = tri == 0 ? p10 : p11, c = tri == 0 ? p11 : p01;
+        const V3<T> nt = tri_normal(a, b, c);
+        const T side = dot(C - a, nt);
+        if (ix == ccx && iy == ccy) {                          // the triangle directly beneath the centre tells inside from outside
+          const T fx = (C.x - p00.x) / g.dx, fy = (C.y - p00.y) / g.dy;
+          if ((fx >= fy) == (tri == 0)) inside = side < T(0);
+        }
+        if (side - r > T(0)) continue;                         // the whole sphere is above this triangle's plane
+        const V3<T> Q = closest_on_triangle(C, a, b, c);
+        const V3<T> v = C - Q;
+        const T dist = std::sqrt(dot(v, v));
+        // a later triangle must be closer by more than 1e-6 m to replace an earlier one (shared edges: the lower pair index wins)
+        if (!have || dist < dmin - T(1e-6)) { have = true; dmin = dist; qn = nt; qv = v; qpair = 2 * (iy * (g.xs - 1) + ix) + tri; }
+      }
+    }
+    if (!have) return;
+    const V3<T> n = (!inside && dmin > T(1e-9)) ? (T(1) / dmin) * qv : qn;
+    offer(best, inside ? r + dmin : r - dmin, n, C - r * n, qpair);
+  }
+  // interior of segment A-B swept by radius r against the terrain edges under its AABB (the end spheres are candidates of their own)
+  void segment_vs_heightmap(const HmGrid& g, V3<T> A, V3<T> B, T r, Best& best) const {
+    int ix0, ix1, iy0, iy1;
+    const V3<T> M = T(0.5) * (A + B);
+    if (!cell_range(g, std::min(A.x, B.x) - r, std::max(A.x, B.x) + r, std::min(A.y, B.y) - r, std::max(A.y, B.y) + r, M.x, M.y, ix0, ix1, iy0, iy1)) return;
+    const V3<T> d1 = B - A;
+    for (int iy = iy0; iy <= iy1; iy++) for (int ix = ix0; ix <= ix1; ix++) {
+      const V3<T> p00 = vertex(g, ix, iy), p10 = vertex(g, ix + 1, iy), p01 = vertex(g, ix, iy + 1), p11 = vertex(g, ix + 1, iy + 1);
+      const V3<T> n0 = tri_normal(p00, p10, p11), n1 = tri_normal(p00, p11, p01);
+      // the five edges of the cell: bottom, right (tri 0), diagonal (both), top, left (tri 1); o0 / o1 = the third vertex of the
+      // cell's triangle(s) on that edge
+      const V3<T> e0[5] = {p00, p10, p00, p01, p00}, e1[5] = {p10, p11, p11, p11, p01};
+      const V3<T> o0[5] = {p11, p00, p10, p00, p11}, o1[5] = {p11, p00, p01, p00, p11};
+      for (int k = 0; k < 5; k++) {
+        T sgm, tt;
+        closest_segments(A, d1, e0[k], e1[k] - e0[k], sgm, tt);
+        if (!(sgm > T(1e-3)) || !(sgm < T(1) - T(1e-3))) continue;      // an end of the segment: the end sphere's business
+        const V3<T> Ps = A + sgm * d1, Pe = e0[k] + tt * (e1[k] - e0[k]);
+        const V3<T> v = Ps - Pe;
+        const T dist = std::sqrt(dot(v, v));
+        const int tri = k < 3 ? 0 : 1;
+        const V3<T> nt = tri == 0 ? n0 : n1;
+        // a true edge contact: the segment point lies beyond the edge as seen from the triangle(s) of this cell on it (v . m < 0, m = the
+        // in-plane direction from the edge into the triangle).  Over a face (or a flat / concave edge) the segment interior is never the
+        // first thing to touch -- the end spheres are -- so a flat height map gives exactly the contacts of a ground plane.
+        const V3<T> ed = e1[k] - e0[k];
+        const T ee = dot(ed, ed);
+        bool convex = true;
+        for (int q = 0; q < 2; q++) {
+          const V3<T> w = (q == 0 ? o0[k] : o1[k]) - e0[k];
+          const V3<T> m = w - (dot(w, ed) / ee) * ed;
+          if (!(dot(v, m) < T(-1e-6) * dist * std::sqrt(dot(m, m)))) convex = false;
+        }
+        if (!convex) continue;
+        if (!(dot(v, nt) > T(0)) || !(dist < r) || !(dist > T(1e-9))) continue;   // from above only: a segment under the surface is the end spheres' business
+        const V3<T> n = (T(1) / dist) * v;
+        offer(best, r - dist, n, Ps - r * n, 2 * (iy * (g.xs - 1) + ix) + tri);
+      }
+    }
+  }
+  // terrain vertices inside the box (centre c, rotation R, half extents h): the vertex deepest inside, pushed out through its nearest face
+  void box_vs_heightmap(const HmGrid& g, V3<T> c, const M3<T>& R, V3<T> h, Best& best) const {
+    const T ex = std::fabs(R.m[0]) * h.x + std::fabs(R.m[1]) * h.y + std::fabs(R.m[2]) * h.z, ey = std::fabs(R.m[3]) * h.x + std::fabs(R.m[4]) * h.y + std::fabs(R.m[5]) * h.z;
+    int ix0, ix1, iy0, iy1;
+    if (!cell_range(g, c.x - ex, c.x + ex, c.y - ey, c.y + ey, c.x, c.y, ix0, ix1, iy0, iy1)) return;
+    for (int iy = iy0; iy <= iy1 + 1; iy++) for (int ix = ix0; ix <= ix1 + 1; ix++) {
+      const V3<T> V = vertex(g, ix, iy);
+      // only a vertex that stands proud of its four neighbours (a peak, a ridge point) can reach a face before the box's own corners
+      // reach the terrain: on a flat or evenly sloping map this candidate adds nothing to the corners (flat height map == ground plane)
+      const T hn = T(0.25) * (g.H[iy * g.xs + std::max(ix - 1, 0)] + g.H[iy * g.xs + std::min(ix + 1, g.xs - 1)] + g.H[std::max(iy - 1, 0) * g.xs + ix] + g.H[std::min(iy + 1, g.ys - 1) * g.xs + ix]);
+      if (!(V.z - hn > T(1e-6))) continue;
+      const V3<T> q = R.tmul(V - c);
+      const T px = h.x - std::fabs(q.x), py = h.y - std::fabs(q.y), pz = h.z - std::fabs(q.z);
+      if (!(px > T(0)) || !(py > T(0)) || !(pz > T(0))) continue;
+      // nearest face; its outward normal is the way the terrain vertex leaves the box, the contact normal (terrain -> robot) is its opposite
+      V3<T> nf; T pen;
+      if (px <= py && px <= pz) { pen = px; nf = {q.x >= T(0) ? T(1) : T(-1), 0, 0}; }
+      else if (py <= pz) { pen = py; nf = {0, q.y >= T(0) ? T(1) : T(-1), 0}; }
+      else { pen = pz; nf = {0, 0, q.z >= T(0) ? T(1) : T(-1)}; }
+      const V3<T> n = T(-1) * (R * nf);
+      const int cix = std::min(ix, g.xs - 2), ciy = std::min(iy, g.ys - 2);
+      offer(best, pen, n, V, 2 * (ciy * (g.xs - 1) + cix));
+    }
+  }
+
   void collide(Workspace<T>& ws) const {
     ws.contacts.clear();
     std::vector<Contact<T>>& all = ws.all;
     all.clear();
+    const bool hm = ter.type == 2;
+    const HmGrid g = hm ? grid(ws.hm_offset) : HmGrid{};
     for (int k = 0; k < npts; k++) {
       int b = pt_body[k];
       if (b == 0 && !floating) continue;               // a body welded to the world cannot collide
+      Best best;
       V3<T> P = ws.p[b] + ws.R[b] * pt_pos[k];
-      T dist; V3<T> n; int pair;
-      if (!terrain_query(P, dist, n, pair, ws.hm_offset)) continue;
-      T depth = pt_rad[k] - dist;
-      if (!(depth > T(0))) continue;
+      T rad = pt_rad[k];
+      bool as_point = pt_type[k] == 0 && !(hm && rad > T(0));
+      if (pt_type[k] == 3) {
+        // cylinder cap: the lowest point of its rim circle (centre P, radius rad, axis a) -- the point of the circle furthest along -z
+        V3<T> a = P - (ws.p[b] + ws.R[b] * pt_pos2[k]);
+        a = (T(1) / std::sqrt(dot(a, a))) * a;
+        V3<T> dd = {a.z * a.x, a.z * a.y, a.z * a.z - T(1)};        // -(e_z - (e_z . a) a)
+        const T dn = std::sqrt(dot(dd, dd));
+        if (!(dn > T(1e-6))) continue;                              // cap parallel to the ground: the fixed rim samples carry it
+        P = P + (rad / dn) * dd; rad = T(0); as_point = true;
+      }
+      if (as_point) {
+        // plane, or a zero-radius point on a height map (box corner, cylinder rim point): the triangle directly beneath
+        T dist; V3<T> n; int pair;
+        if (!terrain_query(P, dist, n, pair, ws.hm_offset)) continue;
+        offer(best, rad - dist, n, P - rad * n, pair);
+      } else if (!hm) continue;                        // segment interiors and box faces add nothing on a plane: ends and corners are deeper
+      else if (pt_type[k] == 0) sphere_vs_heightmap(g, P, rad, best);
+      else if (pt_type[k] == 1) segment_vs_heightmap(g, P, ws.p[b] + ws.R[b] * pt_pos2[k], rad, best);
+      else {
+        const int ci = pt_coll[k];
+        box_vs_heightmap(g, ws.p[b] + ws.R[b] * coll_pos[ci], ws.R[b] * coll_rot[ci], coll_size[ci], best);
+      }
+      if (!best.hit) continue;
       Contact<T> c;
-      c.pt = k; c.body = b; c.pair = pair; c.n = n; c.depth = depth;
-      c.pos = P - pt_rad[k] * n;
+      c.pt = k; c.body = b; c.pair = best.pair; c.n = best.n; c.depth = best.depth; c.pos = best.pos;
       // tangent basis: t1 = normalised projection of e_x (or e_y when n is nearly along x)
-      V3<T> e = (std::fabs(n.x) < T(0.9)) ? V3<T>{1, 0, 0} : V3<T>{0, 1, 0};
-      V3<T> t = e - dot(e, n) * n;
+      V3<T> e = (std::fabs(c.n.x) < T(0.9)) ? V3<T>{1, 0, 0} : V3<T>{0, 1, 0};
+      V3<T> t = e - dot(e, c.n) * c.n;
       T inv = T(1) / std::sqrt(dot(t, t));
-      c.t1 = inv * t; c.t2 = cross(n, c.t1);
+      c.t1 = inv * t; c.t2 = cross(c.n, c.t1);
       c.lam = {0, 0, 0};
       c.sdir = SlipDir<T>();
       all.push_back(c);

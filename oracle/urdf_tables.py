@@ -200,11 +200,29 @@ def load_tables(path_or_xml):
                     pts.append((pos + rot @ (sgn * np.array(size)), 0.0))
             for f, (pp, rr) in enumerate(pts):
                 pt_body.append(bi); pt_pos.append(pp); pt_rad.append(rr); pt_coll.append(ci); pt_feat.append(f)
+    pt_type = [0] * len(pt_body); pt_pos2 = [p.copy() for p in pt_pos]
+    # shape features after the points, in collision-body order: one segment (type 1) per capsule / cylinder axis, one box-face
+    # feature (type 2) per box -- what can touch a height map where no end sphere / corner does
+    for ci in range(len(cbody)):
+        ty, size, pos, rot = ctype[ci], csize[ci], cpos[ci], crot[ci].reshape(3, 3)
+        if ty == CT_SPHERE:
+            continue
+        pt_body.append(cbody[ci]); pt_coll.append(ci); pt_feat.append(0)
+        if ty == CT_BOX:
+            pt_type.append(2); pt_pos.append(np.array(pos, float)); pt_pos2.append(np.array(pos, float)); pt_rad.append(0.0)
+        else:
+            ax = rot[:, 2] * size[1]
+            pt_type.append(1); pt_pos.append(np.array(pos, float) - ax); pt_pos2.append(np.array(pos, float) + ax); pt_rad.append(size[0])
+            if ty == CT_CYLINDER:      # two rim features (type 3): the lowest point of each cap's rim circle
+                for cap, sg in enumerate((-1.0, 1.0)):
+                    pt_body.append(cbody[ci]); pt_coll.append(ci); pt_feat.append(cap); pt_type.append(3)
+                    pt_pos.append(np.array(pos, float) + sg * ax); pt_pos2.append(np.array(pos, float) - sg * ax); pt_rad.append(size[0])
     t.update(
         ncoll=len(cbody), cbody=np.array(cbody, np.int32), ctype=np.array(ctype, np.int32),
         csize=np.array(csize, np.float64).reshape(-1, 3), cpos=np.array(cpos, np.float64).reshape(-1, 3),
         crot=np.array(crot, np.float64).reshape(-1, 9), coll_names=cname,
         npts=len(pt_body), pt_body=np.array(pt_body, np.int32), pt_pos=np.array(pt_pos, np.float64).reshape(-1, 3),
         pt_rad=np.array(pt_rad, np.float64), pt_coll=np.array(pt_coll, np.int32), pt_feat=np.array(pt_feat, np.int32),
+        pt_type=np.array(pt_type, np.int32), pt_pos2=np.array(pt_pos2, np.float64).reshape(-1, 3),
     )
     return t

@@ -110,7 +110,7 @@ static void build_blob(rsb_batch* b) {
   }
   lvl[DL] = (int)lvldofs.size(); entstart[DL] = (int)ent.size();
   b->dims = Dims{md.nb, md.nq, md.nv, md.floating, md.maxdepth, maxdd};
-  H = make_blob_header(b->dims, md.npts(), (int)ent.size());
+  H = make_blob_header(b->dims, md.npts(), (int)ent.size(), md.ncoll());
   {
     bool ident = true;
     for (int i = 1; i < md.nb; i++) for (int k = 0; k < 9; k++) if (std::fabs(md.jrot[9 * i + k] - ((k % 4 == 0) ? 1.0 : 0.0)) > 0.0) ident = false;
@@ -144,6 +144,13 @@ static void build_blob(rsb_batch* b) {
     for (int q = 0; q < 3; q++) F(H.off_pts + (1 + q) * H.nptp + k, (float)md.pt_pos[3 * k + q]);
     F(H.off_pts + 4 * H.nptp + k, (float)md.pt_rad[k]);
     F(H.off_pts + 5 * H.nptp + k, -1.0f);
+    I(H.off_pts + 6 * H.nptp + k, md.pt_type[k]);
+    for (int q = 0; q < 3; q++) F(H.off_pts + (7 + q) * H.nptp + k, (float)md.pt_pos2[3 * k + q]);
+    I(H.off_pts + 10 * H.nptp + k, md.pt_coll[k]);
+  }
+  for (int c = 0; c < md.ncoll(); c++) {   // collision-body table (box features): half extents, body-frame position and rotation
+    for (int q = 0; q < 3; q++) { F(H.off_coll + COLL_WORDS * c + q, (float)md.csize[3 * c + q]); F(H.off_coll + COLL_WORDS * c + 3 + q, (float)md.cpos[3 * c + q]); }
+    for (int q = 0; q < 9; q++) F(H.off_coll + COLL_WORDS * c + 6 + q, (float)md.crot[9 * c + q]);
   }
   for (int i = 0; i < md.nv; i++) {
     F(H.off_gain + i, b->kp[i]); F(H.off_gain + H.nvp + i, b->kd[i]);
@@ -209,7 +216,7 @@ static int pick_config(rsb_batch* b) {
   const int sms = prop.multiProcessorCount;
   b->slots = b->model->md.npts() > 32 ? 2 : 1;
   // the quadruped instance has the topology compiled in (floating base + 4 serial chains of 3 joints in DFS order): check it
-  bool quad_topology = same_dims(b->dims, kQuad12) && b->slots == 1;
+  bool quad_topology = same_dims(b->dims, kQuad12);
   if (quad_topology) {
     const Model& md = b->model->md;
     for (int leg = 0; leg < 4; leg++)
@@ -240,7 +247,8 @@ static int pick_config(rsb_batch* b) {
 
 template <int WPC>
 static cudaError_t dispatch_spec(const rsb_batch* b, const StepArgs& a) {
-  if (b->spec == 1) return launch_step<WPC, 1, 13, 19, 18, 1, 3, 8>(a, b->grid, b->smem_bytes, b->stream);
+  if (b->spec == 1 && b->slots == 1) return launch_step<WPC, 1, 13, 19, 18, 1, 3, 8>(a, b->grid, b->smem_bytes, b->stream);
+  if (b->spec == 1) return launch_step<WPC, 2, 13, 19, 18, 1, 3, 8>(a, b->grid, b->smem_bytes, b->stream);
   if (b->spec == 2) return launch_step<WPC, 2, 31, 37, 36, 1, 10, 15>(a, b->grid, b->smem_bytes, b->stream);
   if (b->slots == 1) return launch_step<WPC, 1, 0, 0, 0, 0, 0, 0>(a, b->grid, b->smem_bytes, b->stream);
   return launch_step<WPC, 2, 0, 0, 0, 0, 0, 0>(a, b->grid, b->smem_bytes, b->stream);
@@ -398,6 +406,7 @@ int rsb_model_get_tables(const rsb_model* m, rsb_model_tables* t) {
   t->inertia = d.inertia.data(); t->jlimit = d.jlimit.data();
   t->cbody = d.cbody.data(); t->ctype = d.ctype.data(); t->csize = d.csize.data(); t->cpos = d.cpos.data(); t->crot = d.crot.data();
   t->pt_body = d.pt_body.data(); t->pt_coll = d.pt_coll.data(); t->pt_feat = d.pt_feat.data(); t->pt_pos = d.pt_pos.data(); t->pt_rad = d.pt_rad.data();
+  t->pt_type = d.pt_type.data(); t->pt_pos2 = d.pt_pos2.data();
   return RSB_OK;
 }
 int rsb_model_body_index(const rsb_model* m, const char* name) {
@@ -533,6 +542,8 @@ int rsb_batch_set_heightmap(rsb_batch* b, int xs, int ys, float x_size, float y_
   t.x0 = cx - 0.5f * x_size; t.y0 = cy - 0.5f * y_size;
   t.xmax = (float)(xs - 1); t.ymax = (float)(ys - 1);
   t.h = b->hmap;
+  t.hmax = h[0];
+  for (size_t i = 1; i < (size_t)xs * ys; i++) t.hmax = std::max(t.hmax, h[i]);
   b->ter = t;
   return RSB_OK;
 }
@@ -559,6 +570,8 @@ int rsb_batch_set_heightmaps(rsb_batch* b, int count, int xs, int ys, float x_si
   t.x0 = cx - 0.5f * x_size; t.y0 = cy - 0.5f * y_size;
   t.xmax = (float)(xs - 1); t.ymax = (float)(ys - 1);
   t.h = b->hmap; t.env_map = b->hmap_index; t.map_words = xs * ys;
+  t.hmax = h[0];
+  for (size_t i = 1; i < words; i++) t.hmax = std::max(t.hmax, h[i]);
   b->ter = t;
   return RSB_OK;
 }

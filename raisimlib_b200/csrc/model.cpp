@@ -231,8 +231,9 @@ struct Builder {
       md.coll_names.push_back(link_name);
       auto add_pt = [&](const V3& local, double rad, int feat) {
         V3 w = add(p, mul(R, local));
-        md.pt_body.push_back(b); md.pt_coll.push_back(ci); md.pt_feat.push_back(feat);
+        md.pt_body.push_back(b); md.pt_coll.push_back(ci); md.pt_feat.push_back(feat); md.pt_type.push_back(FT_POINT);
         md.pt_pos.insert(md.pt_pos.end(), w.begin(), w.end());
+        md.pt_pos2.insert(md.pt_pos2.end(), w.begin(), w.end());
         md.pt_rad.push_back(rad);
       };
       if (type == CT_SPHERE) add_pt({0, 0, 0}, size[0], 0);
@@ -277,6 +278,34 @@ struct Builder {
 };
 
 }  // namespace
+
+// One FT_SEGMENT per capsule / cylinder (its axis, swept by the radius) and one FT_BOXFACE per box, appended after the point
+// candidates in collision-body order: the parts of a shape that can touch a height map where no end sphere / corner does
+// (a capsule lying across a ridge, a box resting on a peak).  Positions in the body frame.
+static void append_shape_features(Model& md) {
+  for (int ci = 0; ci < md.ncoll(); ci++) {
+    const int type = md.ctype[ci];
+    if (type == CT_SPHERE) continue;
+    const double* cp = &md.cpos[3 * ci]; const double* R = &md.crot[9 * ci]; const double* sz = &md.csize[3 * ci];
+    md.pt_body.push_back(md.cbody[ci]); md.pt_coll.push_back(ci); md.pt_feat.push_back(0);
+    if (type == CT_BOX) {
+      md.pt_type.push_back(FT_BOXFACE);
+      for (int k = 0; k < 3; k++) { md.pt_pos.push_back(cp[k]); md.pt_pos2.push_back(cp[k]); }
+      md.pt_rad.push_back(0.0);
+    } else {   // capsule, cylinder: axis = local z of the collision frame, half length sz[1]
+      md.pt_type.push_back(FT_SEGMENT);
+      for (int k = 0; k < 3; k++) { md.pt_pos.push_back(cp[k] - R[3 * k + 2] * sz[1]); md.pt_pos2.push_back(cp[k] + R[3 * k + 2] * sz[1]); }
+      md.pt_rad.push_back(sz[0]);
+      if (type == CT_CYLINDER)   // the lowest rim point of each cap moves round the rim as the cylinder rolls: no fixed sample can stand in for it
+        for (int cap = 0; cap < 2; cap++) {
+          const double sg = cap ? 1.0 : -1.0;
+          md.pt_body.push_back(md.cbody[ci]); md.pt_coll.push_back(ci); md.pt_feat.push_back(cap); md.pt_type.push_back(FT_RIM);
+          for (int k = 0; k < 3; k++) { md.pt_pos.push_back(cp[k] + sg * R[3 * k + 2] * sz[1]); md.pt_pos2.push_back(cp[k] - sg * R[3 * k + 2] * sz[1]); }
+          md.pt_rad.push_back(sz[0]);
+        }
+    }
+  }
+}
 
 Model load_urdf(const std::string& path_or_xml) {
   std::string text;
@@ -336,6 +365,7 @@ Model load_urdf(const std::string& path_or_xml) {
     md.inertia[6 * i + 3] = a.I[4]; md.inertia[6 * i + 4] = a.I[5]; md.inertia[6 * i + 5] = a.I[8];
     if (i > 0 && !(a.m > 0)) throw std::runtime_error("URDF: movable body '" + md.body_names[i] + "' has no mass");
   }
+  append_shape_features(md);
   return md;
 }
 
@@ -343,7 +373,7 @@ Model load_urdf(const std::string& path_or_xml) {
 //      re-parse XML.  Layout: magic "RSBM", version, then every field of Model in declaration order; vectors and strings
 //      carry a 64-bit length.  Little-endian, same-architecture cache (not an interchange format).
 namespace {
-constexpr uint32_t kCacheMagic = 0x4d425352u, kCacheVersion = 2u;
+constexpr uint32_t kCacheMagic = 0x4d425352u, kCacheVersion = 3u;
 struct Writer {
   std::ofstream f;
   template <class T> void pod(const T& v) { f.write(reinterpret_cast<const char*>(&v), sizeof(T)); }
@@ -365,7 +395,7 @@ template <class IO, class M> void model_fields(IO& io, M& md) {
   io.vec(md.jpos); io.vec(md.jrot); io.vec(md.axis); io.vec(md.mass); io.vec(md.com); io.vec(md.inertia); io.vec(md.jlimit);
   io.strs(md.body_names); io.strs(md.joint_names);
   io.vec(md.cbody); io.vec(md.ctype); io.vec(md.csize); io.vec(md.cpos); io.vec(md.crot); io.strs(md.coll_names);
-  io.vec(md.pt_body); io.vec(md.pt_coll); io.vec(md.pt_feat); io.vec(md.pt_pos); io.vec(md.pt_rad);
+  io.vec(md.pt_body); io.vec(md.pt_coll); io.vec(md.pt_feat); io.vec(md.pt_type); io.vec(md.pt_pos); io.vec(md.pt_pos2); io.vec(md.pt_rad);
 }
 }  // namespace
 
@@ -397,8 +427,27 @@ Model load_model(const std::string& path) {
       md.subtree.size() != nb || md.jpos.size() != 3 * nb || md.jrot.size() != 9 * nb || md.axis.size() != 3 * nb || md.mass.size() != nb ||
       md.com.size() != 3 * nb || md.inertia.size() != 6 * nb || md.jlimit.size() != 2 * nb || md.body_names.size() != nb || md.joint_names.size() != nb ||
       md.ctype.size() != md.cbody.size() || md.csize.size() != 3 * md.cbody.size() || md.cpos.size() != 3 * md.cbody.size() || md.crot.size() != 9 * md.cbody.size() ||
-      md.pt_coll.size() != md.pt_body.size() || md.pt_feat.size() != md.pt_body.size() || md.pt_pos.size() != 3 * md.pt_body.size() || md.pt_rad.size() != md.pt_body.size())
+      md.pt_coll.size() != md.pt_body.size() || md.pt_feat.size() != md.pt_body.size() || md.pt_pos.size() != 3 * md.pt_body.size() || md.pt_rad.size() != md.pt_body.size() ||
+      md.pt_type.size() != md.pt_body.size() || md.pt_pos2.size() != 3 * md.pt_body.size() || md.coll_names.size() != md.cbody.size())
     throw std::runtime_error("model cache: '" + path + "' is inconsistent");
+  // derived index tables are recomputed, not trusted (a truncated or edited cache must give a parse error, never an out-of-bounds access)
+  {
+    int nq = md.floating ? 7 : 0, nv = md.floating ? 6 : 0, maxdepth = 0;
+    if (md.floating != 0 && md.floating != 1) throw std::runtime_error("model cache: '" + path + "' is inconsistent (base)");
+    std::vector<int> sub(nb, 1);
+    for (size_t i = 1; i < nb; i++) {
+      if (md.jtype[i] != JT_REVOLUTE && md.jtype[i] != JT_PRISMATIC) throw std::runtime_error("model cache: '" + path + "' is inconsistent (joint types)");
+      if (md.qidx[i] != nq++ || md.vidx[i] != nv++ || md.depth[i] != md.depth[md.parent[i]] + 1) throw std::runtime_error("model cache: '" + path + "' is inconsistent (indices)");
+      maxdepth = std::max(maxdepth, md.depth[i]);
+    }
+    for (size_t i = nb - 1; i > 0; i--) sub[md.parent[i]] += sub[i];
+    if (md.jtype[0] != (md.floating ? JT_FLOATING : JT_FIXED) || md.depth[0] != 0 || nq != md.nq || nv != md.nv || maxdepth != md.maxdepth || sub != md.subtree)
+      throw std::runtime_error("model cache: '" + path + "' is inconsistent (tree)");
+  }
+  for (size_t k = 0; k < md.pt_body.size(); k++)
+    if (md.pt_coll[k] < 0 || md.pt_coll[k] >= md.ncoll() || md.pt_type[k] < FT_POINT || md.pt_type[k] > FT_RIM || md.cbody[md.pt_coll[k]] != md.pt_body[k])
+      throw std::runtime_error("model cache: '" + path + "' is inconsistent (candidates)");
+  for (int ty : md.ctype) if (ty < CT_SPHERE || ty > CT_CYLINDER) throw std::runtime_error("model cache: '" + path + "' is inconsistent (shapes)");
   for (size_t i = 0; i < nb; i++) if (md.parent[i] >= (int)i || (i > 0 && md.parent[i] < 0)) throw std::runtime_error("model cache: '" + path + "' is inconsistent (parents)");
   for (int b : md.cbody) if (b < 0 || b >= md.nb) throw std::runtime_error("model cache: '" + path + "' is inconsistent (collision bodies)");
   for (int b : md.pt_body) if (b < 0 || b >= md.nb) throw std::runtime_error("model cache: '" + path + "' is inconsistent (points)");

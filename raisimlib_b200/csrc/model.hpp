@@ -10,6 +10,11 @@ namespace rsb {
 
 enum JointType { JT_FIXED = 0, JT_REVOLUTE = 1, JT_PRISMATIC = 2, JT_FLOATING = 3 };
 enum CollType { CT_SPHERE = 0, CT_BOX = 1, CT_CAPSULE = 2, CT_CYLINDER = 3 };
+// contact candidates ("features") of a collision body against the terrain, one contact at most each
+enum FeatType { FT_POINT = 0,     // sphere of radius pt_rad at pt_pos (radius 0: a box corner / cylinder rim sample)
+                FT_SEGMENT = 1,   // interior of the segment pt_pos .. pt_pos2 swept by radius pt_rad (capsule / cylinder side) against terrain edges
+                FT_BOXFACE = 2,   // terrain vertices inside the box of collision body pt_coll (a box resting on a peak)
+                FT_RIM = 3 };     // lowest point of the rim circle of a cylinder cap: centre pt_pos, radius pt_rad, axis towards pt_pos2 (side rolling)
 
 struct Frame {
   std::string name;    // link name
@@ -28,9 +33,11 @@ struct Model {
   std::vector<int> cbody, ctype;
   std::vector<double> csize, cpos, crot;                               // 3,3,9 per collision body
   std::vector<std::string> coll_names;
-  // candidate contact points (sphere -> 1, capsule -> 2 end spheres, box -> 8 corners, cylinder -> 2 x 4 rim points)
-  std::vector<int> pt_body, pt_coll, pt_feat;
-  std::vector<double> pt_pos, pt_rad;
+  // contact candidates: points first (sphere -> 1, capsule -> 2 end spheres, box -> 8 corners, cylinder -> 2 x 4 rim points), then, in
+  // collision-body order, one FT_SEGMENT per capsule / cylinder and one FT_BOXFACE per box (height-map terrain only) and two FT_RIM
+  // per cylinder (any terrain)
+  std::vector<int> pt_body, pt_coll, pt_feat, pt_type;
+  std::vector<double> pt_pos, pt_rad, pt_pos2;
   std::vector<Frame> frames;                                            // one per URDF link
   int skipped_collisions = 0;                                           // <mesh> collision bodies ignored by the loader
   int ncoll() const { return (int)cbody.size(); }

@@ -67,15 +67,18 @@ struct BlobHeader {
   // dof tree (floating base = chain of 6 dofs) for the branch-sparse factorisation
   int nbase, maxdd, dlp, nent;
   int off_ddepth, off_dsub, off_danc, off_dbody, off_bdof, off_lvl, off_lvldofs, off_entstart, off_ent, off_lcad;
+  int off_coll, ncoll; // collision-body table (box features): [ncoll][COLL_WORDS] = half extents, body-frame position, rotation
   int words, flags;    // flags bit0: every joint origin has identity rotation (rpy = 0 in the URDF); bits 8..15: largest
                        // non-root subtree size - 1 (loop bound of stage A's subtree accumulation)
 };
-static_assert(sizeof(BlobHeader) == 128, "header is 32 words");
-constexpr int HEADER_WORDS = 32;
+static_assert(sizeof(BlobHeader) == 136, "header is 34 words");
+constexpr int HEADER_WORDS = 36;      // padded to a 16-byte multiple
+constexpr int PT_ROWS = 11;           // candidate table rows: body, pos(3), radius, friction override, type, pos2(3), collision body
+constexpr int COLL_WORDS = 16;
 
 // Every offset except off_ent / words depends on Dims only: the two variable-size tables
 // (candidate points, factorisation entry list) sit at the end.
-__host__ __device__ constexpr BlobHeader make_blob_header(Dims d, int npts, int nent) {
+__host__ __device__ constexpr BlobHeader make_blob_header(Dims d, int npts, int nent, int ncoll = 0) {
   BlobHeader H{};
   H.nb = d.nb; H.nq = d.nq; H.nv = d.nv; H.npts = npts; H.floating = d.floating; H.maxdepth = d.maxdepth;
   H.nbp = d.nb | 1;                       // odd stride: field-major reads by body index stay conflict-free
@@ -99,7 +102,8 @@ __host__ __device__ constexpr BlobHeader make_blob_header(Dims d, int npts, int 
   H.off_lvldofs = off; off += H.nvp;
   H.off_entstart = off; off += DL + 1;
   H.off_lcad = off; off += (d.nb * H.nbp + 3) / 4;
-  H.off_pts = off; off += 6 * H.nptp;                 // body, pos(3), radius, friction override (< 0: default material)
+  H.off_pts = off; off += PT_ROWS * H.nptp;           // body, pos(3), radius, friction override (< 0: default material), type, pos2(3), collision body
+  H.ncoll = ncoll; H.off_coll = off; off += COLL_WORDS * ncoll;
   H.off_ent = off; off += max_c(1, nent);
   H.words = round_up_c(off, 4);
   return H;
@@ -152,6 +156,7 @@ struct TerrainDesc {
   const float* h;
   const int* env_map;  // terrain atlas: height-map index of every environment (null: one shared map)
   int map_words;       // xs * ys
+  float hmax;          // largest height of the map(s): a candidate whose lowest point is above it cannot touch (stage B cull)
 };
 
 struct StepArgs {
@@ -286,6 +291,8 @@ __device__ __forceinline__ bool terrain_query(const TerrainDesc& t, int hm_offse
   pair = 2 * (iy * (t.xs - 1) + ix) + tri;
   return true;
 }
+
+#include "narrow_phase.cuh"
 
 // getters of integrate1(): full symmetric M rebuilt from the compact rows, h, body poses (cold path)
 __device__ __noinline__ void write_debug(const StepArgs& args, int env, int lane, int nv, int nb, int nvp, int DLP, const float* s_L,
@@ -665,17 +672,54 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         int k = lane + 32 * s;
         c_hit[s] = false; c_depth[s] = 0.f; c_pair[s] = 0; c_body[s] = 0; c_pos[s] = mk(0, 0, 0); c_n[s] = mk(0, 0, 1);
         if (k < H.npts) {
-          int pb = ptsi[0 * H.nptp + k];
-          f3 pl = mk(ptsf[1 * H.nptp + k], ptsf[2 * H.nptp + k], ptsf[3 * H.nptp + k]);
-          float rad = ptsf[4 * H.nptp + k];
+          const int pb = ptsi[0 * H.nptp + k];
+          const f3 pl = mk(ptsf[1 * H.nptp + k], ptsf[2 * H.nptp + k], ptsf[3 * H.nptp + k]);
+          const float rad = ptsf[4 * H.nptp + k];
+          const int ptype = ptsi[6 * H.nptp + k];
           float Rb[9];
 #pragma unroll
           for (int q = 0; q < 9; q++) Rb[q] = s_pose[(PF_R + q) * nbp + pb];
-          f3 P = mk(s_pose[(PF_P + 0) * nbp + pb], s_pose[(PF_P + 1) * nbp + pb], s_pose[(PF_P + 2) * nbp + pb]) + mulR(Rb, pl);
-          float dist; f3 n; int pair;
-          if (bdof[pb] >= 0 && terrain_query(args.ter, hm_offset, P, dist, n, pair)) {   // bodies welded to the world cannot collide
-            float depth = rad - dist;
-            if (depth > 0.f) { c_hit[s] = true; c_depth[s] = depth; c_pair[s] = pair; c_body[s] = pb; c_n[s] = n; c_pos[s] = P - rad * n; }
+          const f3 pb_pos = mk(s_pose[(PF_P + 0) * nbp + pb], s_pose[(PF_P + 1) * nbp + pb], s_pose[(PF_P + 2) * nbp + pb]);
+          f3 P = pb_pos + mulR(Rb, pl);
+          float prad = rad;
+          const bool on_hm = args.ter.type == 2;
+          bool as_point = ptype == 0 && !(on_hm && rad > 0.f), live = bdof[pb] >= 0;   // a body welded to the world cannot collide
+          if (ptype == 3) {
+            // cylinder cap: the lowest point of its rim circle (centre P, radius rad, axis a), the point of the circle furthest along -z
+            f3 a = P - (pb_pos + mulR(Rb, mk(ptsf[7 * H.nptp + k], ptsf[8 * H.nptp + k], ptsf[9 * H.nptp + k])));
+            a = (1.0f / sqrtf(dot(a, a))) * a;
+            const f3 dd = mk(a.z * a.x, a.z * a.y, a.z * a.z - 1.f);
+            const float dn = sqrtf(dot(dd, dd));
+            if (dn > 1e-6f) { P = P + (rad / dn) * dd; prad = 0.f; as_point = true; }
+            else live = false;                                  // cap parallel to the ground: the fixed rim samples carry it
+          }
+          if (!live) {
+          } else if (as_point) {
+            // Ground plane, or a zero-radius point on a HeightMap (box corner, cylinder rim point): the triangle directly beneath
+            float dist; f3 n; int pair;
+            if (terrain_query(args.ter, hm_offset, P, dist, n, pair)) {
+              float depth = prad - dist;
+              if (depth > 0.f) { c_hit[s] = true; c_depth[s] = depth; c_pair[s] = pair; c_body[s] = pb; c_n[s] = n; c_pos[s] = P - prad * n; }
+            }
+          } else if (on_hm) {
+            // HeightMap: the shape against every triangle under its bounding box (narrow_phase.cuh); first a conservative cull against
+            // the highest point of the terrain, which removes every candidate of an upright robot except its feet
+            HmBest hb; hb.hit = false;
+            if (ptype == 0) {
+              if (P.z - rad <= args.ter.hmax) hb = sphere_vs_heightmap(args.ter, hm_offset, P, rad);
+            } else if (ptype == 1) {
+              const f3 P2 = pb_pos + mulR(Rb, mk(ptsf[7 * H.nptp + k], ptsf[8 * H.nptp + k], ptsf[9 * H.nptp + k]));
+              if (fminf(P.z, P2.z) - rad <= args.ter.hmax) hb = segment_vs_heightmap(args.ter, hm_offset, P, P2, rad);
+            } else {
+              const float* cb = reinterpret_cast<const float*>(blob_s + H.off_coll) + COLL_WORDS * ptsi[10 * H.nptp + k];
+              const f3 hsz = mk(cb[0], cb[1], cb[2]);
+              float Rw[9];
+              matmul3(Rb, cb + 6, Rw);
+              const f3 cw = pb_pos + mulR(Rb, mk(cb[3], cb[4], cb[5]));
+              const float ez = fabsf(Rw[6]) * hsz.x + fabsf(Rw[7]) * hsz.y + fabsf(Rw[8]) * hsz.z;
+              if (cw.z - ez <= args.ter.hmax) hb = box_vs_heightmap(args.ter, hm_offset, cw, Rw, hsz);
+            }
+            if (hb.hit) { c_hit[s] = true; c_depth[s] = hb.depth; c_pair[s] = hb.pair; c_body[s] = pb; c_n[s] = hb.n; c_pos[s] = hb.pos; }
           }
         }
       }

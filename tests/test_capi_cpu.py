@@ -39,9 +39,9 @@ def test_model_tables_match_python_restatement(src):
     b = load_tables(path)
     for k in ("nb", "nq", "nv", "floating", "ncoll", "npts"):
         assert a[k] == b[k], k
-    for k in ("parent", "jtype", "qidx", "vidx", "depth", "cbody", "ctype", "pt_body", "pt_coll", "pt_feat"):
+    for k in ("parent", "jtype", "qidx", "vidx", "depth", "cbody", "ctype", "pt_body", "pt_coll", "pt_feat", "pt_type"):
         assert (a[k] == b[k]).all(), k
-    for k in ("jpos", "jrot", "axis", "mass", "com", "inertia", "jlimit", "csize", "cpos", "crot", "pt_pos", "pt_rad"):
+    for k in ("jpos", "jrot", "axis", "mass", "com", "inertia", "jlimit", "csize", "cpos", "crot", "pt_pos", "pt_rad", "pt_pos2"):
         assert np.allclose(a[k], b[k], rtol=1e-13, atol=1e-15), k
     assert a["body_names"] == b["body_names"] and a["joint_names"] == b["joint_names"]
 
@@ -103,8 +103,9 @@ def test_realistic_description_features():
     t = capi.Model(REALISTIC_URDF).tables()
     assert (t["nb"], t["nq"], t["nv"]) == (2, 8, 7)
     assert t["ncoll"] == 2 and list(t["ctype"]) == [1, 3]          # box + cylinder; the mesh collision body is skipped
-    assert t["npts"] == 16
-    rim = t["pt_pos"][8:]
+    assert t["npts"] == 16 + 1 + 3                                  # 8 box corners + 8 rim samples, then the box-face feature and the cylinder's axis segment + 2 rim features
+    assert list(t["pt_type"]) == [0] * 16 + [2, 1, 3, 3]
+    rim = t["pt_pos"][8:16]
     assert np.allclose(np.hypot(rim[:, 0], rim[:, 1]), 0.025) and np.allclose(sorted(set(np.round(rim[:, 2], 6))), [-0.3, 0.0])
     assert t["jlimit"][1, 0] < -1e29                               # continuous joint: no limits
 

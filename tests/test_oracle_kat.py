@@ -351,15 +351,15 @@ def test_heightmap_tilted_plane_normal_and_depth():
     H = 0.3 * gx[None, :] + 0.1 * gy[:, None]          # z = 0.3 x + 0.1 y, h[iy*xs+ix]
     o.set_heightmap(xs, ys, X, Y, 0.0, 0.0, H)
     n = np.array([-0.3, -0.1, 1.0]); n /= np.linalg.norm(n)
-    P = np.array([1.23, -0.77, 0.0]); P[2] = 0.3 * P[0] + 0.1 * P[1]
+    P = np.array([1.23, -0.57, 0.0]); P[2] = 0.3 * P[0] + 0.1 * P[1]
     centre = P + n * (0.1 - 0.002)                      # sphere r=0.1 penetrating 2 mm along the normal
     gc = np.array([[*centre, 1, 0, 0, 0.0]]); gv = np.zeros((1, 6))
     d = o.step(gc, gv, n_steps=1, debug=True)
     assert d["ncontacts"][0] == 1
     assert np.allclose(d["c_normal"][0, 0], n, atol=1e-12)
     assert abs(d["c_depth"][0, 0] - 0.002) < 1e-12
-    ix, iy = int((centre[0] + 5) / 1.0), int((centre[1] + 5) / 1.0)
-    fx, fy = (centre[0] + 5) - ix, (centre[1] + 5) - iy
+    ix, iy = int((P[0] + 5) / 1.0), int((P[1] + 5) / 1.0)        # the triangle that holds the touched point
+    fx, fy = (P[0] + 5) - ix, (P[1] + 5) - iy
     assert d["c_pair"][0, 0] == 2 * (iy * (xs - 1) + ix) + (0 if fx >= fy else 1)
     # outside the map: no contact
     gc = np.array([[7.0, 0, -3.0, 1, 0, 0, 0.0]])
@@ -664,3 +664,110 @@ def test_anderson_accelerated_gauss_seidel_same_fixed_point_fewer_sweeps(atlas_t
     g1 = np.array([[0, 0, 0.1, 1, 0, 0, 0.0]]); v1 = np.array([[0.5, 0, -0.2, 0, 0, 0.0]]); g2, v2 = g1.copy(), v1.copy()
     o1.step(g1, v1, n_steps=20); o2.step(g2, v2, n_steps=20)
     assert np.array_equal(g1, g2) and np.array_equal(v1, v2)
+
+
+# ---- a6 narrow phase against a HeightMap: shape vs every triangle under its bounding box ----------------------
+def _single_shape_urdf(geometry, rpy="0 0 0"):
+    return f"""<robot name="one"><link name="b"><inertial><origin xyz="0 0 0"/><mass value="2.0"/><inertia ixx="0.02" ixy="0" ixz="0" iyy="0.02" iyz="0" izz="0.02"/></inertial>
+  <collision><origin xyz="0 0 0" rpy="{rpy}"/><geometry>{geometry}</geometry></collision></link></robot>"""
+
+
+CAPSULE_X_URDF = _single_shape_urdf('<capsule radius="0.05" length="1.0"/>', rpy="0 1.5707963267948966 0")    # axis along world x
+CYLINDER_Y_URDF = _single_shape_urdf('<cylinder radius="0.1" length="0.4"/>', rpy="1.5707963267948966 0 0")   # axis along world y
+SPHERE5_URDF = _single_shape_urdf('<sphere radius="0.05"/>')
+
+
+def ridge_map(n=21, pitch=0.1, top=0.3, slope=0.5):
+    """a ridge along y at x = 0 (on a grid line): h = top - slope |x|"""
+    x = (np.arange(n) - n // 2) * pitch
+    return np.tile(top - slope * np.abs(x), (n, 1)), (n - 1) * pitch
+
+
+def peak_map(n=21, pitch=0.1, h=0.2):
+    H = np.zeros((n, n)); H[n // 2, n // 2] = h
+    return H, (n - 1) * pitch
+
+
+def _contacts_of(o, gc):
+    gc = np.array([gc], float); gv = np.zeros((1, 6))
+    d = o.step(gc, gv, debug=True)
+    K = d["ncontacts"][0]
+    return K, d["c_pt"][0][:K], d["c_pos"][0][:K], d["c_normal"][0][:K], d["c_depth"][0][:K], d["c_pair"][0][:K]
+
+
+def test_capsule_lying_across_a_ridge_touches_with_its_side():
+    """round 1 saw nothing here (two end spheres hanging in the air); the segment feature meets the ridge edge"""
+    t = load_tables(CAPSULE_X_URDF)
+    assert list(t["pt_type"]) == [0, 0, 1]
+    H, size = ridge_map()
+    o = Oracle(t); o.set_heightmap(21, 21, size, size, 0.0, 0.0, H)
+    for cy, delta in ((0.03, 0.004), (0.27, 0.011), (-0.448, 0.002)):
+        K, pt, pos, nrm, dep, pair = _contacts_of(o, [0.013, cy, 0.3 + 0.05 - delta, 1, 0, 0, 0])
+        assert K == 1 and pt[0] == 2                                  # the segment candidate, not an end sphere
+        assert abs(dep[0] - delta) < 1e-9 and np.allclose(nrm[0], [0, 0, 1], atol=1e-9)
+        assert np.allclose(pos[0], [0.0, cy, 0.3 - delta], atol=1e-9)  # the capsule's surface point above the ridge line (contact positions are on the robot)
+    # lifted clear of the ridge: nothing; tilted so that one end sphere digs into the slope: that end, not the side
+    assert _contacts_of(o, [0.0, 0.0, 0.3 + 0.05 + 1e-4, 1, 0, 0, 0])[0] == 0
+    K, pt, *_ = _contacts_of(o, [0.3, 0.0, 0.26, np.cos(0.35), 0, np.sin(0.35), 0])    # pitched: +x end down
+    assert K >= 1 and (pt < 2).any()
+
+
+def test_box_resting_on_a_peak_touches_with_its_face():
+    t = load_tables(BOX_URDF)
+    assert list(t["pt_type"]) == [0] * 8 + [2]
+    H, size = peak_map()
+    o = Oracle(t); o.set_heightmap(21, 21, size, size, 0.0, 0.0, H)
+    delta = 0.007
+    K, pt, pos, nrm, dep, pair = _contacts_of(o, [0.02, -0.01, 0.2 + 0.1 - delta, 1, 0, 0, 0])
+    assert K == 1 and pt[0] == 8                                       # the eight corners hang over flat ground 0.2 m below
+    assert abs(dep[0] - delta) < 1e-12 and np.allclose(nrm[0], [0, 0, 1]) and np.allclose(pos[0], [0, 0, 0.2])
+    assert pair[0] == 2 * (10 * 20 + 10)                               # the cell whose lower-left vertex is the peak
+    # rolled by 30 degrees about x: still the bottom face, the normal follows the box
+    a = np.deg2rad(30.0)
+    K, pt, pos, nrm, dep, pair = _contacts_of(o, [0.0, 0.0, 0.2 + (0.1 - delta) / np.cos(a), np.cos(a / 2), np.sin(a / 2), 0, 0])
+    assert K == 1 and pt[0] == 8 and np.allclose(nrm[0], [0, -np.sin(a), np.cos(a)], atol=1e-9) and abs(dep[0] - delta) < 1e-9   # depth along the face normal
+
+
+def test_sphere_on_a_ridge_and_in_a_valley_uses_the_closest_feature():
+    """convex edge: the contact is on the edge and the depth is measured to it, not to the plane of the triangle beneath;
+    concave edge: a sphere beside the valley line still meets the far slope when that is closer"""
+    t = load_tables(SPHERE5_URDF)
+    H, size = ridge_map()
+    o = Oracle(t); o.set_heightmap(21, 21, size, size, 0.0, 0.0, H)
+    delta = 0.003
+    K, pt, pos, nrm, dep, pair = _contacts_of(o, [0.0, 0.033, 0.3 + 0.05 - delta, 1, 0, 0, 0])
+    assert K == 1 and abs(dep[0] - delta) < 1e-9 and np.allclose(nrm[0], [0, 0, 1], atol=1e-9) and np.allclose(pos[0], [0, 0.033, 0.3 - delta], atol=1e-9)
+    # beside the ridge line, above the slope: the ridge edge is still the closest feature while the foot of the perpendicular leaves the slope
+    K, pt, pos, nrm, dep, pair = _contacts_of(o, [0.01, 0.033, 0.3 + 0.048, 1, 0, 0, 0])
+    d_edge = np.hypot(0.01, 0.048)
+    assert K == 1 and abs(dep[0] - (0.05 - d_edge)) < 1e-9 and np.allclose(nrm[0], [0.01 / d_edge, 0, 0.048 / d_edge], atol=1e-9)
+    # valley: h = 0.5 |x|; the sphere centre sits 1 cm to the right of the valley line, lower than both slopes allow
+    Hv = 0.5 * np.abs((np.arange(21) - 10) * 0.1); Hv = np.tile(Hv, (21, 1))
+    o.set_heightmap(21, 21, size, size, 0.0, 0.0, Hv)
+    c = np.array([0.01, 0.0, 0.05])
+    K, pt, pos, nrm, dep, pair = _contacts_of(o, [*c, 1, 0, 0, 0])
+    n_r, n_l = np.array([-0.5, 0, 1]) / np.hypot(0.5, 1), np.array([0.5, 0, 1]) / np.hypot(0.5, 1)
+    d_r, d_l = c @ n_r, c @ n_l                                        # both slopes pass through the origin
+    assert K == 1 and abs(dep[0] - (0.05 - min(d_r, d_l))) < 1e-9 and np.allclose(nrm[0], n_r if d_r < d_l else n_l, atol=1e-9)
+
+
+def test_cylinder_rolls_on_its_side_without_bobbing():
+    """the lowest point of each cap's rim circle is a candidate of its own: depth independent of the roll angle, and a rolling
+    cylinder keeps its axis at one radius above the ground (4 fixed rim samples alone let it sink by up to 29 % of the radius)"""
+    t = load_tables(CYLINDER_Y_URDF)
+    assert list(t["pt_type"]) == [0] * 8 + [1, 3, 3]
+    o = Oracle(t); o.set_ground(0.0)
+    delta = 0.002
+    for phi in (0.0, 0.3, 0.7, 1.234):
+        q = [np.cos(phi / 2), 0, np.sin(phi / 2), 0]                   # rolled about its own axis (world y)
+        K, pt, pos, nrm, dep, pair = _contacts_of(o, [0, 0, 0.1 - delta, *q])
+        rim = pt >= 9
+        assert rim.sum() == 2 and np.allclose(dep[rim], delta, atol=1e-12)
+        assert np.allclose(np.sort(pos[rim][:, 1]), [-0.2, 0.2]) and np.allclose(pos[rim][:, 0], 0.0, atol=1e-12) and np.allclose(pos[rim][:, 2], -delta, atol=1e-12)   # the rim point itself, delta under the ground
+    # rolling without slipping: v = omega R; 400 steps = 1.4 revolutions
+    gc = np.array([[0, 0, 0.1, 1, 0, 0, 0.0]]); gv = np.array([[0.35, 0, 0, 0, 3.5, 0.0]])
+    z = []
+    for k in range(400):
+        o.step(gc, gv)
+        z.append(gc[0, 2])
+    assert max(z) - min(z) < 2e-4 and abs(gv[0, 0] - 0.35) < 5e-3 and gc[0, 0] > 0.33
