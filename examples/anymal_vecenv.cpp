@@ -8,7 +8,7 @@ int main(int argc, char** argv) {
   std::string urdf = argc > 1 ? argv[1] : "raisimlib_b200/rsc/anymal_c_like.urdf";
   raisim::AnymalTaskConfig cfg;
   cfg.num_envs = argc > 2 ? std::atoi(argv[2]) : 512;
-  raisim::VectorizedEnvironment env(urdf, cfg);
+  raisim::VectorizedAnymalTask env(urdf, cfg);
   env.init();
   const int N = env.getNumOfEnvs(), A = env.getActionDim(), O = env.getObDim();
   std::vector<float> action(size_t(N) * A), ob(size_t(N) * O), reward(N);

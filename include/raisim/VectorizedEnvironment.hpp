@@ -1,19 +1,131 @@
-// raisim::VectorizedEnvironment for the ANYmal locomotion task -- batched drop-in for RaisimGym's
-// `VectorizedEnvironment<ENVIRONMENT>` (upstream raisimGymTorch/raisimGymTorch/env/VectorizedEnvironment.hpp
-// with envs/rsg_anymal/Environment.hpp, [RECALL]; not in the reference snapshot -- SURVEY.md 8f row N1).
+// RaisimGym's `VectorizedEnvironment` (upstream raisimGymTorch/raisimGymTorch/env/VectorizedEnvironment.hpp with
+// envs/rsg_anymal/Environment.hpp, [RECALL]; not in the reference snapshot -- SURVEY.md 8f row N1), two ways:
 //
-// Upstream runs `#pragma omp parallel for` over N ENVIRONMENT objects, each calling world_->integrate()
-// control_dt/simulation_dt times.  Here step() is ONE C-ABI call (rsb_batch_gym_step): action rows in,
-// one fused launch for every environment and sub-step, reward / done / observation rows out.
-// Method names and argument meaning follow upstream; matrices are plain row-major float buffers
-// (upstream: Eigen::Ref<EigenRowMajorMat>; Eigen overloads are provided when Eigen is available).
+//  * VectorizedEnvironment<ENVIRONMENT> -- the generic drop-in.  N unmodified ENVIRONMENT objects (any observation, reward and
+//    termination code written against raisim::World / ArticulatedSystem) run in LOCK STEP on one batch: each environment's step()
+//    executes on its own fiber; World::integrate() only counts, and the first access that needs the result parks the fiber until all
+//    N have arrived; then one upload per dirty array, ONE fused launch for every environment and every counted sub-step, and the
+//    fibers go on (World.hpp `LockStep`).  Upstream runs `#pragma omp parallel for` over the environments instead, each integrating
+//    its own World.  The host-side reward / observation code still runs on the CPU, so this is the compatible path, not the fast one.
+//  * VectorizedAnymalTask -- the rsg_anymal task moved onto the device: step() is ONE C-ABI call (rsb_batch_gym_step): action rows in,
+//    one fused launch, reward / done / observation rows out, nothing per environment on the host.
+//
+// Method names and argument meaning follow upstream; matrices are plain row-major float buffers (upstream: Eigen::Ref<EigenRowMajorMat>).
 #pragma once
+#include <ucontext.h>
+
+#include <exception>
 #include <string>
 #include <vector>
 
+#include "RaisimGymEnv.hpp"
 #include "World.hpp"
 
 namespace raisim {
+
+template <class ChildEnvironment>
+class VectorizedEnvironment {
+ public:
+  // upstream: VectorizedEnvironment(std::string resourceDir, std::string cfg); here the configuration object is handed through as is
+  template <class Cfg>
+  VectorizedEnvironment(std::string resourceDir, const Cfg& cfg, int numEnvs, int device = 0, size_t fiberStackBytes = 256 * 1024)
+      : resourceDir_(std::move(resourceDir)), stackBytes_(fiberStackBytes) {
+    ctx_.numEnvs = numEnvs; ctx_.device = device;
+    BatchContext::current() = &ctx_;
+    try {
+      for (int i = 0; i < numEnvs; i++) { ctx_.envIndex = i; environments_.emplace_back(new ChildEnvironment(resourceDir_, cfg, false)); }
+    } catch (...) { BatchContext::current() = nullptr; throw; }
+    BatchContext::current() = nullptr;
+    if (!ctx_.batch) throw std::runtime_error("VectorizedEnvironment: the environments created no robot");
+    ls_ = ctx_.batch->lockStep();
+    fibers_.resize(numEnvs);
+    for (Fiber& f : fibers_) f.stack.resize(stackBytes_);
+    ls_->suspend = [this](int env) { park(env); };
+  }
+  ~VectorizedEnvironment() { if (ls_) ls_->suspend = nullptr; }
+  VectorizedEnvironment(const VectorizedEnvironment&) = delete;
+  VectorizedEnvironment& operator=(const VectorizedEnvironment&) = delete;
+
+  void init() {
+    for (auto& e : environments_) e->init();
+    obDim_ = environments_[0]->getObDim(); actionDim_ = environments_[0]->getActionDim();
+    ls_->pushWrites();
+  }
+  void reset() { for (auto& e : environments_) e->reset(); ls_->pushWrites(); }
+  // ob [num_envs][obDim] row-major
+  void observe(float* ob) { for (int i = 0; i < getNumOfEnvs(); i++) environments_[i]->observe(RowRef{ob + size_t(i) * obDim_, obDim_}); }
+  // action [num_envs][actionDim], reward [num_envs], done [num_envs] -- upstream perAgentStep() for every environment, in lock step
+  void step(const float* action, float* reward, bool* done) {
+    action_ = action; reward_ = reward; done_ = done;
+    runAll();
+  }
+  int getObDim() const { return obDim_; }
+  int getActionDim() const { return actionDim_; }
+  int getNumOfEnvs() const { return int(environments_.size()); }
+  void setSimulationTimeStep(double dt) { for (auto& e : environments_) e->setSimulationTimeStep(dt); }
+  void setControlTimeStep(double dt) { for (auto& e : environments_) e->setControlTimeStep(dt); }
+  void setSeed(int seed) { int k = seed; for (auto& e : environments_) e->setSeed(k++); }
+  void curriculumUpdate() { for (auto& e : environments_) e->curriculumUpdate(); }
+  void close() { for (auto& e : environments_) e->close(); }
+  ChildEnvironment& environment(int i) { return *environments_[i]; }
+  BatchedWorld& world() { return *ctx_.batch; }
+  long launches() const { return ls_->launches; }          // batched launches issued so far (one per control step for the usual step())
+
+ private:
+  struct Fiber { ucontext_t ctx; std::vector<char> stack; bool done = true; std::exception_ptr error; };
+
+  void perAgentStep(int i) {
+    float r = environments_[i]->step(RowRef{const_cast<float*>(action_) + size_t(i) * actionDim_, actionDim_});
+    float terminalReward = 0.f;
+    done_[i] = environments_[i]->isTerminalState(terminalReward);
+    if (done_[i]) { environments_[i]->reset(); r += terminalReward; }
+    reward_[i] = r;
+  }
+  static void trampoline(unsigned lo, unsigned hi, unsigned idx) {
+    auto* self = reinterpret_cast<VectorizedEnvironment*>((uintptr_t(hi) << 32) | uintptr_t(lo));
+    Fiber& f = self->fibers_[idx];
+    try { self->perAgentStep(int(idx)); } catch (...) { f.error = std::current_exception(); }
+    f.done = true;
+    swapcontext(&f.ctx, &self->main_);      // never returns
+  }
+  void park(int env) { swapcontext(&fibers_[env].ctx, &main_); }      // called on environment env's fiber: back to the scheduler
+  void runAll() {
+    const int n = getNumOfEnvs();
+    const uintptr_t self = reinterpret_cast<uintptr_t>(this);
+    for (int i = 0; i < n; i++) {
+      Fiber& f = fibers_[i];
+      getcontext(&f.ctx);
+      f.ctx.uc_stack.ss_sp = f.stack.data(); f.ctx.uc_stack.ss_size = f.stack.size(); f.ctx.uc_link = nullptr;
+      f.done = false; f.error = nullptr;
+      makecontext(&f.ctx, reinterpret_cast<void (*)()>(&VectorizedEnvironment::trampoline), 3, unsigned(self & 0xffffffffu), unsigned(self >> 32), unsigned(i));
+    }
+    for (;;) {
+      int live = 0;
+      for (int i = 0; i < n; i++) {
+        Fiber& f = fibers_[i];
+        if (f.done) continue;
+        swapcontext(&main_, &f.ctx);                  // runs until the environment finishes or needs the batch to catch up
+        if (f.error) { for (int& p : ls_->pending) p = 0; std::rethrow_exception(f.error); }
+        if (!f.done) live++;
+      }
+      if (live == 0) break;
+      if (live != n) throw std::runtime_error("VectorizedEnvironment: some environments finished step() while others wait for World::integrate()");
+      ls_->flush();                                   // every environment waits at the same point: one upload, ONE launch
+    }
+    ls_->flush();                                     // integrate() calls nobody read back yet
+    ls_->pushWrites();                                // resets written by terminated environments
+  }
+
+  std::string resourceDir_;
+  size_t stackBytes_;
+  BatchContext ctx_;
+  LockStep* ls_ = nullptr;
+  std::vector<std::unique_ptr<ChildEnvironment>> environments_;
+  std::vector<Fiber> fibers_;
+  ucontext_t main_;
+  const float* action_ = nullptr; float* reward_ = nullptr; bool* done_ = nullptr;
+  int obDim_ = 0, actionDim_ = 0;
+};
 
 struct AnymalTaskConfig {            // the fields of upstream's cfg.yaml that the environment reads
   int num_envs = 100;
@@ -25,9 +137,9 @@ struct AnymalTaskConfig {            // the fields of upstream's cfg.yaml that t
   std::vector<std::string> foot_links = {"LF_FOOT", "RF_FOOT", "LH_FOOT", "RH_FOOT"};   // upstream: LF/RF/LH/RH_SHANK bodies
 };
 
-class VectorizedEnvironment {
+class VectorizedAnymalTask {
  public:
-  VectorizedEnvironment(const std::string& urdf, const AnymalTaskConfig& cfg, int device = 0) : cfg_(cfg), world_(urdf, cfg.num_envs, device) {}
+  VectorizedAnymalTask(const std::string& urdf, const AnymalTaskConfig& cfg, int device = 0) : cfg_(cfg), world_(urdf, cfg.num_envs, device) {}
 
   void init() {
     rsb_params p = world_.params();

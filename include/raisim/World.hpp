@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -61,6 +62,76 @@ class Contact {
   rsb_contact c_;
 };
 
+// Lock-step execution of N unmodified per-environment programs on one batch (VectorizedEnvironment<ENVIRONMENT>).
+// Every environment holds World / ArticulatedSystem VIEWS of the same BatchedWorld.  Their setters and getters work on host
+// mirrors of the batch rows, and World::integrate() only counts: the first access that needs the result (getState, getContacts,
+// setPdTarget after an integrate ...) suspends that environment until every environment has reached the same point; then the
+// dirty rows go up in one copy each, ONE launch integrates the counted sub-steps of every environment (the usual RaisimGym loop
+// `for (i < control_dt / simulation_dt) world_->integrate();` becomes a single fused launch), and the mirrors are refilled lazily,
+// one copy per array and control step.
+struct LockStep {
+  rsb_batch* batch = nullptr;
+  int n = 0, nq = 0, nv = 0;
+  std::vector<float> gc, gv, pt, vt, tau, tauApplied;
+  std::vector<rsb_contact> contacts;
+  std::vector<int32_t> ncontacts;
+  std::vector<int> pending;                 // World::integrate() calls not executed yet, per environment
+  bool stateValid = false, stateDirty = false, ptDirty = false, vtDirty = false, tauDirty = false, tauAppliedValid = false, contactsValid = false;
+  long launches = 0;
+  std::function<void(int)> suspend;         // installed by the scheduler: park the calling environment until the batch was flushed
+
+  void init(rsb_batch* b, int n_, int nq_, int nv_) {
+    batch = b; n = n_; nq = nq_; nv = nv_;
+    gc.assign(size_t(n) * nq, 0.f); gv.assign(size_t(n) * nv, 0.f); pt.assign(size_t(n) * nq, 0.f); vt.assign(size_t(n) * nv, 0.f);
+    tau.assign(size_t(n) * nv, 0.f); tauApplied.assign(size_t(n) * nv, 0.f); contacts.resize(size_t(n) * RSB_KMAX); ncontacts.assign(n, 0);
+    pending.assign(n, 0);
+  }
+  // an environment is about to read or write the world: whatever it integrated before must have happened
+  void sync(int env) {
+    if (pending[env] == 0) return;
+    if (!suspend) throw std::runtime_error("World: state access with integrate() calls pending outside VectorizedEnvironment::step()");
+    suspend(env);
+  }
+  void needState() {
+    if (stateValid) return;
+    rsbCheck(rsb_batch_get_state(batch, gc.data(), gv.data(), 0, n, RSB_HOST), "getState");
+    stateValid = true;
+  }
+  void needTauApplied() {
+    if (tauAppliedValid) return;
+    rsbCheck(rsb_batch_get_generalized_force(batch, tauApplied.data(), 0, n, RSB_HOST), "getGeneralizedForce");
+    tauAppliedValid = true;
+  }
+  void needContacts() {
+    if (contactsValid) return;
+    rsbCheck(rsb_batch_get_contacts(batch, contacts.data(), ncontacts.data(), 0, n, RSB_HOST), "getContacts");
+    contactsValid = true;
+  }
+  // every environment is parked (or finished) with the same number of integrate() calls pending: upload, one launch, invalidate
+  void flush() {
+    int k = 0;
+    for (int e = 0; e < n; e++) k = pending[e] > k ? pending[e] : k;
+    if (k == 0) return;
+    for (int e = 0; e < n; e++)
+      if (pending[e] != k) throw std::runtime_error("VectorizedEnvironment: environments disagree on the number of World::integrate() calls between two state accesses");
+    if (stateDirty) rsbCheck(rsb_batch_set_state(batch, gc.data(), gv.data(), 0, n, RSB_HOST), "setState");
+    if (ptDirty || vtDirty) rsbCheck(rsb_batch_set_pd_target(batch, ptDirty ? pt.data() : nullptr, vtDirty ? vt.data() : nullptr, 0, n, RSB_HOST), "setPdTarget");
+    if (tauDirty) rsbCheck(rsb_batch_set_generalized_force(batch, tau.data(), 0, n, RSB_HOST), "setGeneralizedForce");
+    stateDirty = ptDirty = vtDirty = tauDirty = false;
+    rsbCheck(rsb_batch_integrate(batch, k), "integrate");
+    launches++;
+    for (int& p : pending) p = 0;
+    stateValid = tauAppliedValid = contactsValid = false;
+  }
+  // rows written outside a step (reset(), init()): push them before anything else reads the device
+  void pushWrites() {
+    if (stateDirty) rsbCheck(rsb_batch_set_state(batch, gc.data(), gv.data(), 0, n, RSB_HOST), "setState");
+    if (ptDirty || vtDirty) rsbCheck(rsb_batch_set_pd_target(batch, ptDirty ? pt.data() : nullptr, vtDirty ? vt.data() : nullptr, 0, n, RSB_HOST), "setPdTarget");
+    if (tauDirty) rsbCheck(rsb_batch_set_generalized_force(batch, tau.data(), 0, n, RSB_HOST), "setGeneralizedForce");
+    stateDirty = ptDirty = vtDirty = tauDirty = false;
+  }
+};
+
 // One GPU batch of N identical worlds (new; the reference has no equivalent -- its batching is the
 // OpenMP loop of VectorizedEnvironment).
 class BatchedWorld {
@@ -86,7 +157,15 @@ class BatchedWorld {
   void integrate1() { rsbCheck(rsb_batch_integrate1(batch_), "integrate1"); }
   void integrate2() { rsbCheck(rsb_batch_integrate2(batch_), "integrate2"); worldTime_ += params().dt; }
   double worldTime() const { return worldTime_; }
+  void advanceTime(double t) { worldTime_ += t; }
+  // lock-step mode (VectorizedEnvironment<ENVIRONMENT>): per-environment views work on host mirrors, integrate() is deferred
+  LockStep* lockStep() { return ls_.get(); }
+  void enableLockStep() { if (!ls_) { ls_.reset(new LockStep); ls_->init(batch_, n_, nq_, nv_); } }
+  const std::string& urdf() const { return urdf_; }
+  void rememberUrdf(const std::string& u) { urdf_ = u; }
  private:
+  std::unique_ptr<LockStep> ls_;
+  std::string urdf_;
   rsb_model* model_ = nullptr;
   rsb_batch* batch_ = nullptr;
   int n_ = 0, nq_ = 0, nv_ = 0, nb_ = 0;
@@ -113,6 +192,13 @@ class ArticulatedSystem {
   const std::string& getName() const { return name_; }
 
   void getState(VecDyn& gc, VecDyn& gv) const {
+    if (LockStep* ls = w_->lockStep()) {
+      ls->sync(env_); ls->needState();
+      gc.resize(size_t(ls->nq)); gv.resize(size_t(ls->nv));
+      for (int i = 0; i < ls->nq; i++) gc[i] = ls->gc[size_t(env_) * ls->nq + i];
+      for (int i = 0; i < ls->nv; i++) gv[i] = ls->gv[size_t(env_) * ls->nv + i];
+      return;
+    }
     std::vector<float> q(w_->nq()), v(w_->nv());
     rsbCheck(rsb_batch_get_state(w_->batch(), q.data(), v.data(), env_, 1, RSB_HOST), "getState");
     gc.resize(q.size()); gv.resize(v.size());
@@ -122,22 +208,47 @@ class ArticulatedSystem {
   VecDyn getGeneralizedCoordinate() const { VecDyn q, v; getState(q, v); return q; }
   VecDyn getGeneralizedVelocity() const { VecDyn q, v; getState(q, v); return v; }
   template <class VQ, class VV> void setState(const VQ& gc, const VV& gv) {
+    if (LockStep* ls = w_->lockStep()) {
+      ls->sync(env_); ls->needState();           // the other environments' rows of the mirror must be current before the whole array goes up
+      for (int i = 0; i < ls->nq; i++) ls->gc[size_t(env_) * ls->nq + i] = float(gc[i]);
+      for (int i = 0; i < ls->nv; i++) ls->gv[size_t(env_) * ls->nv + i] = float(gv[i]);
+      ls->stateDirty = true;
+      return;
+    }
     std::vector<float> q(w_->nq()), v(w_->nv());
     for (size_t i = 0; i < q.size(); i++) q[i] = float(gc[i]);
     for (size_t i = 0; i < v.size(); i++) v[i] = float(gv[i]);
     rsbCheck(rsb_batch_set_state(w_->batch(), q.data(), v.data(), env_, 1, RSB_HOST), "setState");
   }
   template <class VQ> void setGeneralizedCoordinate(const VQ& gc) {
+    if (LockStep* ls = w_->lockStep()) {
+      ls->sync(env_); ls->needState();
+      for (int i = 0; i < ls->nq; i++) ls->gc[size_t(env_) * ls->nq + i] = float(gc[i]);
+      ls->stateDirty = true;
+      return;
+    }
     std::vector<float> q(w_->nq());
     for (size_t i = 0; i < q.size(); i++) q[i] = float(gc[i]);
     rsbCheck(rsb_batch_set_state(w_->batch(), q.data(), nullptr, env_, 1, RSB_HOST), "setGeneralizedCoordinate");
   }
   template <class VV> void setGeneralizedVelocity(const VV& gv) {
+    if (LockStep* ls = w_->lockStep()) {
+      ls->sync(env_); ls->needState();
+      for (int i = 0; i < ls->nv; i++) ls->gv[size_t(env_) * ls->nv + i] = float(gv[i]);
+      ls->stateDirty = true;
+      return;
+    }
     std::vector<float> v(w_->nv());
     for (size_t i = 0; i < v.size(); i++) v[i] = float(gv[i]);
     rsbCheck(rsb_batch_set_state(w_->batch(), nullptr, v.data(), env_, 1, RSB_HOST), "setGeneralizedVelocity");
   }
   template <class VV> void setGeneralizedForce(const VV& tau) {
+    if (LockStep* ls = w_->lockStep()) {
+      ls->sync(env_);
+      for (int i = 0; i < ls->nv; i++) ls->tau[size_t(env_) * ls->nv + i] = float(tau[i]);
+      ls->tauDirty = true;
+      return;
+    }
     std::vector<float> t(w_->nv());
     for (size_t i = 0; i < t.size(); i++) t[i] = float(tau[i]);
     rsbCheck(rsb_batch_set_generalized_force(w_->batch(), t.data(), env_, 1, RSB_HOST), "setGeneralizedForce");
@@ -149,6 +260,13 @@ class ArticulatedSystem {
     rsbCheck(rsb_batch_set_pd_gains(w_->batch(), kp.data(), kd.data()), "setPdGains");
   }
   template <class VQ, class VV> void setPdTarget(const VQ& posTarget, const VV& velTarget) {
+    if (LockStep* ls = w_->lockStep()) {
+      ls->sync(env_);
+      for (int i = 0; i < ls->nq; i++) ls->pt[size_t(env_) * ls->nq + i] = float(posTarget[i]);
+      for (int i = 0; i < ls->nv; i++) ls->vt[size_t(env_) * ls->nv + i] = float(velTarget[i]);
+      ls->ptDirty = ls->vtDirty = true;
+      return;
+    }
     std::vector<float> q(w_->nq()), v(w_->nv());
     for (size_t i = 0; i < q.size(); i++) q[i] = float(posTarget[i]);
     for (size_t i = 0; i < v.size(); i++) v[i] = float(velTarget[i]);
@@ -192,6 +310,12 @@ class ArticulatedSystem {
     return Minv;
   }
   VecDyn getGeneralizedForce() const {
+    if (LockStep* ls = w_->lockStep()) {
+      ls->sync(env_); ls->needTauApplied();
+      VecDyn r(size_t(ls->nv));
+      for (int i = 0; i < ls->nv; i++) r[i] = ls->tauApplied[size_t(env_) * ls->nv + i];
+      return r;
+    }
     std::vector<float> t(w_->nv());
     rsbCheck(rsb_batch_get_generalized_force(w_->batch(), t.data(), env_, 1, RSB_HOST), "getGeneralizedForce");
     VecDyn r(t.size());
@@ -289,6 +413,12 @@ class ArticulatedSystem {
   void getFrameAngularVelocity(size_t frameIdx, Vec<3>& out) const { MatDyn J; getDenseFrameRotationalJacobian(frameIdx, J); mulGv(J, out); }
 
   std::vector<Contact>& getContacts() {
+    if (LockStep* ls = w_->lockStep()) {
+      ls->sync(env_); ls->needContacts();
+      contacts_.clear();
+      for (int i = 0; i < ls->ncontacts[env_]; i++) contacts_.emplace_back(ls->contacts[size_t(env_) * RSB_KMAX + i]);
+      return contacts_;
+    }
     rsb_contact c[RSB_KMAX]; int32_t n = 0;
     rsbCheck(rsb_batch_get_contacts(w_->batch(), c, &n, env_, 1, RSB_HOST), "getContacts");
     contacts_.clear();
@@ -308,6 +438,7 @@ class ArticulatedSystem {
   struct FrameW { int body; Vec<3> pos; Mat<3, 3> rot; };
   Poses poses() const {
     Poses P; P.R.resize(size_t(w_->nb()) * 9); P.p.resize(size_t(w_->nb()) * 3);
+    if (LockStep* ls = w_->lockStep()) { ls->sync(env_); ls->pushWrites(); }
     // the C-ABI getter is lazy: it runs a kinematics-only pass when the state changed (upstream's updateKinematics()); the contact
     // records and impulses of the last integrate() stay valid across kinematic getters, as upstream's getContacts() does
     rsbCheck(rsb_batch_get_body_poses(w_->batch(), env_, 1, P.R.data(), P.p.data(), RSB_HOST), "getBodyPoses");
@@ -360,15 +491,38 @@ class ArticulatedSystem {
 };
 
 // raisim::World -- standalone it owns a batch of one environment; as a view it forwards to a shared batch
+// While a VectorizedEnvironment<ENVIRONMENT> constructs its environments, every `raisim::World` they create becomes a view of
+// ONE shared batch instead of a batch of one: environment i's World is view i; the first addArticulatedSystem() creates the
+// batch (num_envs environments of that URDF, lock-step mode), the others attach to it.
+struct BatchContext {
+  int numEnvs = 0, device = 0, envIndex = 0;
+  std::unique_ptr<BatchedWorld> batch;
+  static BatchContext*& current() { static thread_local BatchContext* c = nullptr; return c; }
+};
+
 class World {
  public:
-  World() = default;
+  World() { if (BatchContext* c = BatchContext::current()) { ctx_ = c; env_ = c->envIndex; } }
   World(BatchedWorld* shared, int env) : w_(shared), env_(env) { robot_.reset(new ArticulatedSystem(w_, env_)); }
   static void setActivationKey(const std::string&) {}          // licence check of the reference: not a capability
 
   ArticulatedSystem* addArticulatedSystem(const std::string& urdfPathOrXml, const std::string& = "", const std::vector<std::string>& = {},
                                           CollisionGroup = 1, CollisionGroup = CollisionGroup(-1)) {
     if (w_) throw std::runtime_error("addArticulatedSystem: this World is a view of a BatchedWorld (one robot per environment)");
+    if (ctx_) {   // environment of a VectorizedEnvironment: attach to (or create) the shared batch
+      if (!ctx_->batch) {
+        ctx_->batch.reset(new BatchedWorld(urdfPathOrXml, ctx_->numEnvs, ctx_->device));
+        ctx_->batch->rememberUrdf(urdfPathOrXml);
+        ctx_->batch->enableLockStep();
+      } else if (ctx_->batch->urdf() != urdfPathOrXml) throw std::runtime_error("VectorizedEnvironment: every environment must load the same robot description");
+      w_ = ctx_->batch.get();
+      rsb_params p = w_->params();
+      p.dt = float(dt_); p.gravity[0] = float(g_[0]); p.gravity[1] = float(g_[1]); p.gravity[2] = float(g_[2]);
+      w_->setParams(p);
+      if (haveGround_) rsbCheck(rsb_batch_set_ground(w_->batch(), float(groundZ_)), "addGround");
+      robot_.reset(new ArticulatedSystem(w_, env_));
+      return robot_.get();
+    }
     owned_.reset(new BatchedWorld(urdfPathOrXml, 1));
     w_ = owned_.get(); env_ = 0;
     rsb_params p = w_->params();
@@ -449,7 +603,15 @@ class World {
   void ignoreCollisionBetween(size_t, size_t, size_t, size_t) {}
   // one World::integrate() of THIS environment's batch.  Views of a shared batch must not call this
   // per environment -- the vectorized wrapper steps the whole batch once (see VectorizedEnvironment.hpp).
-  void integrate() { need(); applyMaterials(false); w_->integrate(1); if (robot_) robot_->clearExternalWrench(); }
+  void integrate() {
+    need();
+    if (LockStep* ls = w_->lockStep()) {   // deferred: counted now, executed for every environment at once when the result is first needed
+      ls->pending[env_]++;
+      if (env_ == 0) w_->advanceTime(w_->params().dt);
+      return;
+    }
+    applyMaterials(false); w_->integrate(1); if (robot_) robot_->clearExternalWrench();
+  }
   void integrate1() { need(); applyMaterials(false); w_->integrate1(); }
   void integrate2() { need(); w_->integrate2(); if (robot_) robot_->clearExternalWrench(); }
   double getWorldTime() const { return w_ ? w_->worldTime() : 0.0; }
@@ -470,6 +632,7 @@ class World {
   std::string terrainMaterial_ = "default";
   std::unique_ptr<BatchedWorld> owned_;
   BatchedWorld* w_ = nullptr;
+  BatchContext* ctx_ = nullptr;
   int env_ = 0;
   std::unique_ptr<ArticulatedSystem> robot_;
   Ground ground_; HeightMap hm_;

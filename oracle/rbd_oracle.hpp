@@ -458,35 +458,43 @@ template <typename T> class Sim {
     iy0 = std::max(std::max(int(std::floor((loy - g.y0) / g.dy)), cy - 1), 0); iy1 = std::min(std::min(int(std::floor((hiy - g.y0) / g.dy)), cy + 1), g.ys - 2);
     return true;
   }
-  // sphere (centre C, radius r > 0) against the triangles under its AABB: the terrain point closest to the centre decides.
-  // Centre above the surface (the usual case): depth = r - distance, pushed out along the line to that point (face, edge or vertex);
-  // centre under the surface (deep penetration): depth = r + distance, pushed out along that triangle's normal.
+  // sphere (centre C, radius r > 0) against the eight triangles of the 2 x 2 block of cells nearest to its centre (everything
+  // within half a cell of the centre horizontally: exact for radii up to half the grid pitch): the terrain point closest to
+  // the centre decides.  Centre above the surface (the usual case): depth = r - distance, pushed out along the line to that point
+  // (face, edge or vertex); centre under the surface (deep penetration): depth = r + distance, along that triangle's normal.
+  // Of several triangles within 1e-6 m of the smallest distance (they share the touched edge or vertex) the lowest pair index wins.
   void sphere_vs_heightmap(const HmGrid& g, V3<T> C, T r, Best& best) const {
-    int ix0, ix1, iy0, iy1;
-    if (!cell_range(g, C.x - r, C.x + r, C.y - r, C.y + r, C.x, C.y, ix0, ix1, iy0, iy1)) return;
-    bool have = false, inside = false; T dmin = 0; V3<T> qn{0, 0, 1}, qv{0, 0, 0}; int qpair = 0;
-    const int ccx = int((C.x - g.x0) / g.dx), ccy = int((C.y - g.y0) / g.dy);
-    for (int iy = iy0; iy <= iy1; iy++) for (int ix = ix0; ix <= ix1; ix++) {
-      const V3<T> p00 = vertex(g, ix, iy), p10 = vertex(g, ix + 1, iy), p01 = vertex(g, ix, iy + 1), p11 = vertex(g, ix + 1, iy + 1);
-      for (int tri = 0; tri < 2; tri++) {
-        const V3<T> a = p00, b = tri == 0 ? p10 : p11, c = tri == 0 ? p11 : p01;
-        const V3<T> nt = tri_normal(a, b, c);
-        const T side = dot(C - a, nt);
-        if (ix == ccx && iy == ccy) {                          // the triangle directly beneath the centre tells inside from outside
-          const T fx = (C.x - p00.x) / g.dx, fy = (C.y - p00.y) / g.dy;
-          if ((fx >= fy) == (tri == 0)) inside = side < T(0);
-        }
-        if (side - r > T(0)) continue;                         // the whole sphere is above this triangle's plane
-        const V3<T> Q = closest_on_triangle(C, a, b, c);
-        const V3<T> v = C - Q;
-        const T dist = std::sqrt(dot(v, v));
-        // a later triangle must be closer by more than 1e-6 m to replace an earlier one (shared edges: the lower pair index wins)
-        if (!have || dist < dmin - T(1e-6)) { have = true; dmin = dist; qn = nt; qv = v; qpair = 2 * (iy * (g.xs - 1) + ix) + tri; }
+    const T gx = (C.x - g.x0) / g.dx, gy = (C.y - g.y0) / g.dy;
+    if (!(gx >= T(0)) || !(gy >= T(0)) || !(gx < T(g.xs - 1)) || !(gy < T(g.ys - 1))) return;
+    const int ccx = int(gx), ccy = int(gy);
+    const int bx = std::min(std::max(int(std::floor(gx - T(0.5))), 0), std::max(g.xs - 3, 0)), by = std::min(std::max(int(std::floor(gy - T(0.5))), 0), std::max(g.ys - 3, 0));
+    T dist[8]; V3<T> vv[8], nn[8]; int pr[8]; bool ok[8];
+    bool inside = false; T dmin = T(3.0e38);
+    for (int k = 0; k < 8; k++) {
+      const int ix = bx + ((k >> 1) & 1), iy = by + (k >> 2), tri = k & 1;
+      ok[k] = false;
+      if (ix > g.xs - 2 || iy > g.ys - 2) continue;
+      const V3<T> a = vertex(g, ix, iy), b = tri == 0 ? vertex(g, ix + 1, iy) : vertex(g, ix + 1, iy + 1), c = tri == 0 ? vertex(g, ix + 1, iy + 1) : vertex(g, ix, iy + 1);
+      const V3<T> nt = tri_normal(a, b, c);
+      const T side = dot(C - a, nt);
+      if (ix == ccx && iy == ccy) {                            // the triangle directly beneath the centre tells inside from outside
+        const T fx = gx - T(ccx), fy = gy - T(ccy);
+        if ((fx >= fy) == (tri == 0)) inside = side < T(0);
       }
+      if (side - r > T(0)) continue;                           // the whole sphere is above this triangle's plane
+      const V3<T> Q = closest_on_triangle(C, a, b, c);
+      vv[k] = C - Q; nn[k] = nt;
+      dist[k] = std::sqrt(dot(vv[k], vv[k]));
+      pr[k] = 2 * (iy * (g.xs - 1) + ix) + tri;
+      ok[k] = true;
+      dmin = std::min(dmin, dist[k]);
     }
-    if (!have) return;
-    const V3<T> n = (!inside && dmin > T(1e-9)) ? (T(1) / dmin) * qv : qn;
-    offer(best, inside ? r + dmin : r - dmin, n, C - r * n, qpair);
+    int win = -1;
+    for (int k = 0; k < 8; k++) if (ok[k] && dist[k] <= dmin + T(1e-6) && (win < 0 || pr[k] < pr[win])) win = k;
+    if (win < 0) return;
+    const T d = dist[win];
+    const V3<T> n = (!inside && d > T(1e-9)) ? (T(1) / d) * vv[win] : nn[win];
+    offer(best, inside ? r + d : r - d, n, C - r * n, pr[win]);
   }
   // interior of segment A-B swept by radius r against the terrain edges under its AABB (the end spheres are candidates of their own)
   void segment_vs_heightmap(const HmGrid& g, V3<T> A, V3<T> B, T r, Best& best) const {

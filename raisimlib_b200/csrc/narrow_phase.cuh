@@ -67,41 +67,51 @@ __device__ __forceinline__ void closest_segments(f3 p1, f3 d1, f3 p2, f3 d2, flo
   else if (t > 1.f) { t = 1.f; s = fminf(fmaxf((b - c) / a, 0.f), 1.f); }
 }
 
-// sphere (centre C, radius r > 0) against the triangles under its AABB: the terrain point closest to the centre decides.
-// Centre above the surface (the usual case): depth = r - distance, pushed out along the line to that point (face, edge or vertex);
-// centre under the surface (deep penetration): depth = r + distance, pushed out along that triangle's normal.
-__device__ __forceinline__ HmBest sphere_vs_heightmap(const TerrainDesc& t, int hm_offset, f3 C, float r) {
+// Sphere (centre C, radius r > 0) against the eight triangles of the 2 x 2 block of cells nearest to its centre (oracle
+// sphere_vs_heightmap).  EIGHT LANES share one sphere, one triangle each (sub = lane & 7: cell (sub >> 1) & 1, sub >> 2 of the block,
+// triangle sub & 1); the group reduces to the closest terrain point with xor shuffles inside its aligned 8-lane segment.  Of several
+// triangles within 1e-6 m of the smallest distance (they share the touched edge or vertex) the lowest pair index wins.  Every lane of
+// the group returns the same result; `valid` = this group holds a sphere at all.
+__device__ __forceinline__ HmBest sphere_vs_heightmap_group(const TerrainDesc& t, int hm_offset, f3 C, float r, bool valid, int lane) {
   HmBest best; best.hit = false; best.depth = 0.f; best.n = mk(0.f, 0.f, 1.f); best.pos = C; best.pair = 0;
-  int ix0, ix1, iy0, iy1;
-  if (!hm_cell_range(t, C.x - r, C.x + r, C.y - r, C.y + r, C.x, C.y, ix0, ix1, iy0, iy1)) return best;
-  const float* H = t.h + hm_offset;
-  bool have = false, inside = false; float dmin = 0.f; f3 qn = mk(0.f, 0.f, 1.f), qv = mk(0.f, 0.f, 0.f); int qpair = 0;
-  const int ccx = (int)((C.x - t.x0) / t.dx), ccy = (int)((C.y - t.y0) / t.dy);
-#pragma unroll 1
-  for (int iy = iy0; iy <= iy1; iy++)
-#pragma unroll 1
-    for (int ix = ix0; ix <= ix1; ix++) {
-      const f3 p00 = hm_vertex(t, H, ix, iy), p10 = hm_vertex(t, H, ix + 1, iy), p01 = hm_vertex(t, H, ix, iy + 1), p11 = hm_vertex(t, H, ix + 1, iy + 1);
-#pragma unroll 1
-      for (int tri = 0; tri < 2; tri++) {
-        const f3 a = p00, b = tri == 0 ? p10 : p11, c = tri == 0 ? p11 : p01;
-        const f3 nt = hm_tri_normal(a, b, c);
-        const float side = dot(C - a, nt);
-        if (ix == ccx && iy == ccy) {                           // the triangle directly beneath the centre tells inside from outside
-          const float fx = (C.x - p00.x) / t.dx, fy = (C.y - p00.y) / t.dy;
-          if ((fx >= fy) == (tri == 0)) inside = side < 0.f;
-        }
-        if (side - r > 0.f) continue;                           // the whole sphere is above this triangle's plane
-        const f3 Q = closest_on_triangle(C, a, b, c);
-        const f3 v = C - Q;
-        const float dist = sqrtf(dot(v, v));
-        // a later triangle must be closer by more than 1e-6 m to replace an earlier one (shared edges: the lower pair index wins)
-        if (!have || dist < dmin - 1e-6f) { have = true; dmin = dist; qn = nt; qv = v; qpair = 2 * (iy * (t.xs - 1) + ix) + tri; }
-      }
+  const float gx = (C.x - t.x0) / t.dx, gy = (C.y - t.y0) / t.dy;
+  const bool in_map = valid && gx >= 0.f && gy >= 0.f && gx < t.xmax && gy < t.ymax;
+  const int ccx = (int)gx, ccy = (int)gy;
+  const int bx = min(max((int)floorf(gx - 0.5f), 0), max(t.xs - 3, 0)), by = min(max((int)floorf(gy - 0.5f), 0), max(t.ys - 3, 0));
+  const int sub = lane & 7, tri = sub & 1;
+  const int ix = bx + ((sub >> 1) & 1), iy = by + (sub >> 2);
+  float dist = 3.0e38f; f3 v = mk(0.f, 0.f, 0.f), nt = mk(0.f, 0.f, 1.f); int pair = 0x7fffffff; bool beneath_inside = false;
+  if (in_map && ix <= t.xs - 2 && iy <= t.ys - 2) {
+    const float* H = t.h + hm_offset;
+    const f3 a = hm_vertex(t, H, ix, iy), b = tri == 0 ? hm_vertex(t, H, ix + 1, iy) : hm_vertex(t, H, ix + 1, iy + 1), c = tri == 0 ? hm_vertex(t, H, ix + 1, iy + 1) : hm_vertex(t, H, ix, iy + 1);
+    nt = hm_tri_normal(a, b, c);
+    const float side = dot(C - a, nt);
+    if (ix == ccx && iy == ccy) {                               // the triangle directly beneath the centre tells inside from outside
+      const float fx = gx - (float)ccx, fy = gy - (float)ccy;
+      if ((fx >= fy) == (tri == 0)) beneath_inside = side < 0.f;
     }
-  if (!have) return best;
-  const f3 n = (!inside && dmin > 1e-9f) ? (1.0f / dmin) * qv : qn;
-  hm_offer(best, inside ? r + dmin : r - dmin, n, C - r * n, qpair);
+    if (!(side - r > 0.f)) {                                    // else: the whole sphere is above this triangle's plane
+      const f3 Q = closest_on_triangle(C, a, b, c);
+      v = C - Q;
+      dist = sqrtf(dot(v, v));
+      pair = 2 * (iy * (t.xs - 1) + ix) + tri;
+    }
+  }
+  const unsigned seg = 0xffu << (lane & 24);
+  const bool inside = (__ballot_sync(FULL, beneath_inside) & seg) != 0u;
+  float dmin = dist;
+  dmin = fminf(dmin, __shfl_xor_sync(FULL, dmin, 1)); dmin = fminf(dmin, __shfl_xor_sync(FULL, dmin, 2)); dmin = fminf(dmin, __shfl_xor_sync(FULL, dmin, 4));
+  int key = (dist < 3.0e38f && dist <= dmin + 1e-6f) ? pair : 0x7fffffff;
+  int kmin = key;
+  kmin = min(kmin, __shfl_xor_sync(FULL, kmin, 1)); kmin = min(kmin, __shfl_xor_sync(FULL, kmin, 2)); kmin = min(kmin, __shfl_xor_sync(FULL, kmin, 4));
+  const unsigned wm = __ballot_sync(FULL, key == kmin && kmin != 0x7fffffff) & seg;
+  const int wl = wm ? __ffs(wm) - 1 : lane;
+  const float wd = __shfl_sync(FULL, dist, wl);
+  const f3 wv = shfl3(v, wl), wn = shfl3(nt, wl);
+  if (wm) {
+    const f3 n = (!inside && wd > 1e-9f) ? (1.0f / wd) * wv : wn;
+    hm_offer(best, inside ? r + wd : r - wd, n, C - r * n, kmin);
+  }
   return best;
 }
 

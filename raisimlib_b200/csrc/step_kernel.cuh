@@ -665,12 +665,12 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
 
       // =========================== stage B: narrow phase ========================================
       float c_depth[SLOTS]; f3 c_pos[SLOTS], c_n[SLOTS]; int c_pair[SLOTS], c_body[SLOTS];
-      bool c_hit[SLOTS];
+      bool c_hit[SLOTS], c_sph[SLOTS];      // c_sph: a sphere candidate on a HeightMap, evaluated below by a group of eight lanes
       const int hm_offset = args.ter.env_map ? __ldg(args.ter.env_map + env) * args.ter.map_words : 0;   // terrain atlas
 #pragma unroll
       for (int s = 0; s < SLOTS; s++) {
         int k = lane + 32 * s;
-        c_hit[s] = false; c_depth[s] = 0.f; c_pair[s] = 0; c_body[s] = 0; c_pos[s] = mk(0, 0, 0); c_n[s] = mk(0, 0, 1);
+        c_hit[s] = false; c_sph[s] = false; c_depth[s] = 0.f; c_pair[s] = 0; c_body[s] = 0; c_pos[s] = mk(0, 0, 0); c_n[s] = mk(0, 0, 1);
         if (k < H.npts) {
           const int pb = ptsi[0 * H.nptp + k];
           const f3 pl = mk(ptsf[1 * H.nptp + k], ptsf[2 * H.nptp + k], ptsf[3 * H.nptp + k]);
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
             // the highest point of the terrain, which removes every candidate of an upright robot except its feet
             HmBest hb; hb.hit = false;
             if (ptype == 0) {
-              if (P.z - rad <= args.ter.hmax) hb = sphere_vs_heightmap(args.ter, hm_offset, P, rad);
+              if (P.z - rad <= args.ter.hmax) { c_sph[s] = true; c_pos[s] = P; c_depth[s] = rad; c_body[s] = pb; }   // parked: eight lanes take it below
             } else if (ptype == 1) {
               const f3 P2 = pb_pos + mulR(Rb, mk(ptsf[7 * H.nptp + k], ptsf[8 * H.nptp + k], ptsf[9 * H.nptp + k]));
               if (fminf(P.z, P2.z) - rad <= args.ter.hmax) hb = segment_vs_heightmap(args.ter, hm_offset, P, P2, rad);
@@ -722,6 +722,43 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
             if (hb.hit) { c_hit[s] = true; c_depth[s] = hb.depth; c_pair[s] = hb.pair; c_body[s] = pb; c_n[s] = hb.n; c_pos[s] = hb.pos; }
           }
         }
+      }
+      {   // sphere candidates on a HeightMap: four at a time, eight lanes (= the eight triangles of the 2 x 2 cell block under it) each
+        unsigned sm[SLOTS]; int nsph = 0;
+#pragma unroll
+        for (int s = 0; s < SLOTS; s++) { sm[s] = __ballot_sync(FULL, c_sph[s]); nsph += __popc(sm[s]); }
+        float* scr = s_hist;          // 4 x 12 words of scratch: the Anderson history is not in use during stage B
+#pragma unroll 1
+        for (int base = 0; base < nsph; base += 4) {
+          const int rk = base + (lane >> 3);
+          int rr = rk, oslot = 0;
+          if (SLOTS > 1 && rr >= __popc(sm[0])) { oslot = 1; rr -= __popc(sm[0]); }
+          const bool gvalid = rk < nsph;
+          const int olane = gvalid ? __fns(sm[SLOTS > 1 ? oslot : 0], 0, rr + 1) : 0;
+          f3 C = shfl3(c_pos[0], olane); float rad = __shfl_sync(FULL, c_depth[0], olane);
+          if (SLOTS > 1) {
+            const f3 C1 = shfl3(c_pos[SLOTS - 1], olane); const float r1 = __shfl_sync(FULL, c_depth[SLOTS - 1], olane);
+            if (oslot == 1) { C = C1; rad = r1; }
+          }
+          const HmBest hb = sphere_vs_heightmap_group(args.ter, hm_offset, C, rad, gvalid, lane);
+          __syncwarp();
+          if ((lane & 7) == 0 && gvalid) {
+            float* o = scr + 12 * (lane >> 3);
+            o[0] = hb.hit ? 1.f : 0.f; o[1] = hb.depth; o[2] = hb.n.x; o[3] = hb.n.y; o[4] = hb.n.z; o[5] = hb.pos.x; o[6] = hb.pos.y; o[7] = hb.pos.z; o[8] = __int_as_float(hb.pair);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int s = 0; s < SLOTS; s++) {
+            const int myrank = __popc(sm[s] & ((1u << lane) - 1u)) + (s > 0 ? __popc(sm[0]) : 0);
+            if (c_sph[s] && myrank >= base && myrank < base + 4) {
+              const float* o = scr + 12 * (myrank - base);
+              c_depth[s] = 0.f;
+              if (o[0] != 0.f) { c_hit[s] = true; c_depth[s] = o[1]; c_n[s] = mk(o[2], o[3], o[4]); c_pos[s] = mk(o[5], o[6], o[7]); c_pair[s] = __float_as_int(o[8]); }
+            }
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < SLOTS; s++) if (c_sph[s] && !c_hit[s]) { c_depth[s] = 0.f; c_pos[s] = mk(0, 0, 0); }
       }
       unsigned hm[SLOTS];
       int total = 0;

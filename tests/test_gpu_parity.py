@@ -1135,3 +1135,18 @@ def test_heightmap_narrow_phase_matches_oracle_on_rough_terrain(capi):
         assert pair_same > 0.995                                                                   # same reason: which of two triangles sharing an edge
         ok = live & (ct["pair_index"] == d["c_pair"])
         assert np.abs(ct["depth"] - d["c_depth"])[ok].max() < 5e-6 and np.abs(ct["normal"] - d["c_normal"])[ok].max() < 2e-4
+
+
+def test_cpp_generic_vectorized_environment_example(capi):
+    """VectorizedEnvironment<ENVIRONMENT> runs N objects of an upstream-shaped environment class (own observation,
+    reward, termination on the host; examples/rsg_custom/Environment.hpp) in lock step on one batch: ONE launch per control step although
+    every environment calls world_->integrate() four times, and environment 0 reproduces the same class run standalone bit for bit."""
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "examples", "custom_vecenv")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")])
+    out = subprocess.run([exe, os.path.join(RSC, "anymal_c_like.urdf"), "256"], capture_output=True, text=True, timeout=300)
+    print(out.stdout, out.stderr[-500:])
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "1.00 per control step" in out.stdout and "max |difference| over observations and rewards 0" in out.stdout
