@@ -103,6 +103,7 @@ typedef struct rsb_model_tables {
    * vertices; types 1 and 2 come after the points and act on height maps only */
   const int* pt_type;
   const double* pt_pos2;
+  const double* jeffort; /* [nb] URDF <limit effort> of the joint that carries the body (1e30 = none): the commanded torque saturates there */
 } rsb_model_tables;
 
 /* zero-copy device view (rows are padded: element (env, i) of X lives at X[env * X_stride + i]) */

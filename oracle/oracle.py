@@ -30,7 +30,7 @@ class _ModelDesc(C.Structure):
     _fields_ = [("nb", C.c_int), ("nq", C.c_int), ("nv", C.c_int), ("floating", C.c_int),
                 ("parent", C.c_void_p), ("jtype", C.c_void_p), ("qidx", C.c_void_p), ("vidx", C.c_void_p),
                 ("jpos", C.c_void_p), ("jrot", C.c_void_p), ("axis", C.c_void_p), ("mass", C.c_void_p),
-                ("com", C.c_void_p), ("inertia", C.c_void_p), ("jlimit", C.c_void_p),
+                ("com", C.c_void_p), ("inertia", C.c_void_p), ("jlimit", C.c_void_p), ("jeffort", C.c_void_p),
                 ("npts", C.c_int), ("pt_body", C.c_void_p), ("pt_pos", C.c_void_p), ("pt_rad", C.c_void_p),
                 ("pt_type", C.c_void_p), ("pt_coll", C.c_void_p), ("pt_pos2", C.c_void_p),
                 ("ncoll", C.c_int), ("coll_size", C.c_void_p), ("coll_pos", C.c_void_p), ("coll_rot", C.c_void_p)]
@@ -97,7 +97,7 @@ class Oracle:
         self.t = tables
         self.nb, self.nq, self.nv = tables["nb"], tables["nq"], tables["nv"]
         self._keep = {k: np.ascontiguousarray(tables[k], dtype=(np.int32 if tables[k].dtype.kind == "i" else np.float64))
-                      for k in ("parent", "jtype", "qidx", "vidx", "jpos", "jrot", "axis", "mass", "com", "inertia", "jlimit",
+                      for k in ("parent", "jtype", "qidx", "vidx", "jpos", "jrot", "axis", "mass", "com", "inertia", "jlimit", "jeffort",
                                 "pt_body", "pt_pos", "pt_rad", "pt_type", "pt_coll", "pt_pos2")}
         for src, dst in (("csize", "coll_size"), ("cpos", "coll_pos"), ("crot", "coll_rot")):
             self._keep[dst] = np.ascontiguousarray(tables[src], dtype=np.float64)

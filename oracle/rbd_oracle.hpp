@@ -72,6 +72,7 @@ struct ModelDesc {   // plain-C description handed over the oracle's C API (all 
   const int *parent, *jtype, *qidx, *vidx;
   const double *jpos, *jrot, *axis, *mass, *com, *inertia;
   const double* jlimit;   // [nb][2] lower/upper (|.| >= 1e29 = none); may be null
+  const double* jeffort;  // [nb] actuator effort limit of the joint (>= 1e29 = none); may be null
   int npts;
   const int *pt_body;
   const double *pt_pos, *pt_rad;
@@ -143,7 +144,8 @@ template <typename T> struct Workspace {
   std::vector<V3<T>> p, a, w, v, wd, vd, F, N;
   std::vector<T> Ic;             // 10 per body: m, h(3), I_O(6: xx xy xz yy yz zz)
   std::vector<T> S;              // 6 per body: [ang(3); lin_at_O(3)]
-  std::vector<T> M, Mh, L, h, b, z, Jt, Y, G, u, u0, rhs, tau_applied;
+  std::vector<T> M, Mh, L, h, b, z, Jt, Y, G, u, u0, rhs, tau_applied, b_sat;
+  std::vector<char> sat;          // dof driven at its effort limit in this step
   std::vector<Contact<T>> contacts, all;
   std::vector<Limit<T>> limits;
   int iters = 0;
@@ -161,7 +163,7 @@ template <typename T> class Sim {
   std::vector<V3<T>> jpos, axis, com, pt_pos, pt_pos2, coll_size, coll_pos;
   std::vector<M3<T>> coll_rot;
   std::vector<M3<T>> jrot;
-  std::vector<T> mass, inertia, pt_rad, jlo, jhi, pt_mu;   // pt_mu < 0: default material friction
+  std::vector<T> mass, inertia, pt_rad, jlo, jhi, jeff, pt_mu;   // pt_mu < 0: default material friction; jeff: effort limit per body
   Params prm;
   Terrain ter;
   std::vector<T> hmap;
@@ -182,6 +184,8 @@ template <typename T> class Sim {
     }
     jlo.assign(nb, T(-1e30)); jhi.assign(nb, T(1e30));
     if (d.jlimit) for (int i = 0; i < nb; i++) { jlo[i] = T(d.jlimit[2 * i]); jhi[i] = T(d.jlimit[2 * i + 1]); }
+    jeff.assign(nb, T(1e30));
+    if (d.jeffort) for (int i = 0; i < nb; i++) jeff[i] = T(std::min(d.jeffort[i], 1e30));
     pt_body.assign(d.pt_body, d.pt_body + npts); pt_pos.resize(npts); pt_rad.resize(npts); pt_mu.assign(npts, T(-1));
     for (int i = 0; i < npts; i++) {
       pt_pos[i] = {T(d.pt_pos[3 * i]), T(d.pt_pos[3 * i + 1]), T(d.pt_pos[3 * i + 2])};
@@ -218,7 +222,7 @@ template <typename T> class Sim {
     ws.nb = nb; ws.nv = nv;
     ws.R.resize(nb); ws.p.resize(nb); ws.a.resize(nb); ws.w.resize(nb); ws.v.resize(nb); ws.wd.resize(nb); ws.vd.resize(nb);
     ws.F.resize(nb); ws.N.resize(nb); ws.Ic.resize(10 * nb); ws.S.resize(6 * nb);
-    ws.M.resize(nv * nv); ws.Mh.resize(nv * nv); ws.L.resize(nv * nv); ws.h.resize(nv); ws.tau_applied.resize(nv); ws.b.resize(nv); ws.z.resize(nv); ws.rhs.resize(nv);
+    ws.M.resize(nv * nv); ws.Mh.resize(nv * nv); ws.L.resize(nv * nv); ws.h.resize(nv); ws.tau_applied.resize(nv); ws.b.resize(nv); ws.z.resize(nv); ws.rhs.resize(nv); ws.b_sat.assign(nv, T(0)); ws.sat.assign(nv, 0);
     ws.Jt.resize(nv * RMAX); ws.Y.resize(nv * RMAX); ws.G.resize(RMAX * RMAX); ws.u.resize(RMAX); ws.u0.resize(RMAX);
   }
 
@@ -828,6 +832,15 @@ template <typename T> class Sim {
     for (int i = 1; i < nb; i++) {
       int vi = vidx[i], qi = qidx[i];
       T kpi = kp ? kp[vi] : T(0), kdi = kd ? kd[vi] : T(0);
+      // actuator effort limit (URDF <limit effort>; upstream setActuationLimits): when the commanded torque -- feed-forward plus the PD
+      // law at the current state -- exceeds it, the joint is driven by the constant limit torque over this step (no implicit PD terms)
+      const T tff = tau_ff ? tau_ff[vi] : T(0);
+      T te = tff;
+      if (kpi != T(0) || kdi != T(0)) te += kpi * ((ptarget ? ptarget[qi] : T(0)) - gc[qi]) + kdi * ((vtarget ? vtarget[vi] : T(0)) - gv[vi]);
+      // ... judged on the torque the implicit law would really apply: for a stiff loop (dt^2 kp >> inertia) that is the explicit value
+      // divided by 1 + (dt kd + dt^2 kp) / M_dd, so a stiff controller sitting near its target is not mistaken for a saturated one
+      ws.sat[vi] = std::fabs(te) > jeff[i] * (T(1) + (dt * kdi + dt * dt * kpi) / ws.M[vi * nv + vi]);
+      if (ws.sat[vi]) { ws.b_sat[vi] = te > T(0) ? jeff[i] : -jeff[i]; ws.b[vi] += ws.b_sat[vi] - tff; continue; }
       if (kpi != T(0) || kdi != T(0)) {
         T qt = ptarget ? ptarget[qi] : T(0), vt = vtarget ? vtarget[vi] : T(0);
         ws.b[vi] += kpi * (qt - gc[qi] - dt * gv[vi]) + kdi * (vt - gv[vi]);
@@ -1040,6 +1053,7 @@ template <typename T> class Sim {
     for (int i = 1; i < nb; i++) {
       int vi = vidx[i], qi = qidx[i];
       T kpi = kp ? kp[vi] : T(0), kdi = kd ? kd[vi] : T(0);
+      if (ws.sat[vi]) { ws.tau_applied[vi] = ws.tau_applied[vi] + (ws.b_sat[vi] - ws.tau_applied[vi]); continue; }
       if (kpi != T(0) || kdi != T(0)) {
         T qt = ptarget ? ptarget[qi] : T(0), vt = vtarget ? vtarget[vi] : T(0);
         ws.tau_applied[vi] += kpi * (qt - gc[qi] - dt * gv[vi]) + kdi * (vt - gv[vi]);

@@ -97,6 +97,7 @@ def load_tables(path_or_xml):
         children.setdefault(j.find("parent").get("link"), []).append(j)
 
     bodies, parent, jtype, jpos, jrot, axis, jname, jlimit = [], [], [], [], [], [], [], []
+    jeffort = []
 
     def absorb(body, link_name, T_pos, T_rot):
         """merge link `link_name` (frame at T in body coords) into body, then recurse."""
@@ -149,6 +150,8 @@ def load_tables(path_or_xml):
                 lim = j.find("limit")
                 jlimit.append([float(lim.get("lower", "-1e30")), float(lim.get("upper", "1e30"))]
                               if (lim is not None and t != "continuous") else [-1e30, 1e30])
+                eff = float(lim.get("effort", "0")) if lim is not None else 0.0
+                jeffort.append(eff if eff > 0 else 1e30)          # <limit effort>: 0 or absent = unlimited
                 absorb(nb, child, np.zeros(3), np.eye(3))
             else:
                 raise ValueError("unsupported joint type " + t)
@@ -159,7 +162,7 @@ def load_tables(path_or_xml):
     parent.append(-1)
     jtype.append(JT_FLOATING if floating else JT_FIXED)
     jpos.append(np.zeros(3)); jrot.append(np.eye(3)); axis.append(np.array([0.0, 0, 1])); jname.append("root")
-    jlimit.append([-1e30, 1e30])
+    jlimit.append([-1e30, 1e30]); jeffort.append(1e30)
     absorb(b0, root_name, np.zeros(3), np.eye(3))
 
     nb = len(bodies)
@@ -176,7 +179,7 @@ def load_tables(path_or_xml):
         parent=np.array(parent, np.int32), jtype=np.array(jtype, np.int32), qidx=qidx, vidx=vidx, depth=depth,
         jpos=np.array(jpos), jrot=np.array([r.reshape(9) for r in jrot]), axis=np.array(axis),
         mass=np.array([b.mass for b in bodies]), com=np.array([b.com for b in bodies]), inertia=I6,
-        jlimit=np.array(jlimit),
+        jlimit=np.array(jlimit), jeffort=np.array(jeffort, np.float64),
         body_names=[b.name for b in bodies], joint_names=jname,
     )
     # collision bodies and their candidate points

@@ -44,7 +44,7 @@ class ModelTables(C.Structure):
                 [(n, C.POINTER(C.c_double)) for n in ("csize", "cpos", "crot")] +
                 [(n, C.POINTER(C.c_int)) for n in ("pt_body", "pt_coll", "pt_feat")] +
                 [(n, C.POINTER(C.c_double)) for n in ("pt_pos", "pt_rad")] +
-                [("pt_type", C.POINTER(C.c_int)), ("pt_pos2", C.POINTER(C.c_double))])
+                [("pt_type", C.POINTER(C.c_int)), ("pt_pos2", C.POINTER(C.c_double)), ("jeffort", C.POINTER(C.c_double))])
 
 
 class TerrainProperties(C.Structure):
@@ -257,6 +257,7 @@ class Model:
         out["pt_rad"] = arr(t.pt_rad, npt, np.float64)
         out["pt_type"] = arr(t.pt_type, npt, np.int32)
         out["pt_pos2"] = arr(t.pt_pos2, npt * 3, np.float64).reshape(npt, 3)
+        out["jeffort"] = arr(t.jeffort, nb, np.float64)
         out["body_names"] = [lib().rsb_model_body_name(self.h, i).decode() for i in range(nb)]
         out["joint_names"] = [lib().rsb_model_joint_name(self.h, i).decode() for i in range(nb)]
         return out

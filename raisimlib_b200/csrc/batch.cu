@@ -153,9 +153,10 @@ static void build_blob(rsb_batch* b) {
     for (int q = 0; q < 9; q++) F(H.off_coll + COLL_WORDS * c + 6 + q, (float)md.crot[9 * c + q]);
   }
   for (int i = 0; i < md.nv; i++) {
-    F(H.off_gain + i, b->kp[i]); F(H.off_gain + H.nvp + i, b->kd[i]);
+    F(H.off_gain + i, b->kp[i]); F(H.off_gain + H.nvp + i, b->kd[i]); F(H.off_gain + 2 * H.nvp + i, 3.0e38f);
     I(H.off_dofq + i, -1);
   }
+  for (int i = 1; i < md.nb; i++) F(H.off_gain + 2 * H.nvp + md.vidx[i], (float)std::min(md.jeffort[i], 3.0e38));   // actuator effort limit per dof
   for (int i = 1; i < md.nb; i++) I(H.off_dofq + md.vidx[i], md.qidx[i]);
   for (int i = 0; i < nv; i++) {
     I(H.off_ddepth + i, ddepth[i]); I(H.off_dsub + i, dsub[i]); I(H.off_dbody + i, dbody[i]);
@@ -406,7 +407,7 @@ int rsb_model_get_tables(const rsb_model* m, rsb_model_tables* t) {
   t->inertia = d.inertia.data(); t->jlimit = d.jlimit.data();
   t->cbody = d.cbody.data(); t->ctype = d.ctype.data(); t->csize = d.csize.data(); t->cpos = d.cpos.data(); t->crot = d.crot.data();
   t->pt_body = d.pt_body.data(); t->pt_coll = d.pt_coll.data(); t->pt_feat = d.pt_feat.data(); t->pt_pos = d.pt_pos.data(); t->pt_rad = d.pt_rad.data();
-  t->pt_type = d.pt_type.data(); t->pt_pos2 = d.pt_pos2.data();
+  t->pt_type = d.pt_type.data(); t->pt_pos2 = d.pt_pos2.data(); t->jeffort = d.jeffort.data();
   return RSB_OK;
 }
 int rsb_model_body_index(const rsb_model* m, const char* name) {

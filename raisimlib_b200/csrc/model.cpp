@@ -3,8 +3,13 @@
 #include "model.hpp"
 
 #include <cmath>
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
+#include <iterator>
 #include <map>
 #include <memory>
 #include <sstream>
@@ -171,6 +176,48 @@ struct Accum {
   }
 };
 
+// Axis-aligned bounds of a mesh file (binary or ASCII STL, Wavefront OBJ), scaled.  `filename` may be absolute, file://, relative to
+// the URDF's directory, or package://pkg/rest (tried as <dir>/rest, <dir>/../rest and <dir>/../../rest, the usual package layouts).
+static bool mesh_bounds(const std::string& dir, std::string filename, const V3& scale, V3& lo, V3& hi) {
+  std::vector<std::string> tries;
+  if (filename.rfind("file://", 0) == 0) filename = filename.substr(7);
+  if (filename.rfind("package://", 0) == 0) {
+    std::string rest = filename.substr(10);
+    size_t slash = rest.find('/');
+    std::string tail = slash == std::string::npos ? rest : rest.substr(slash + 1);
+    for (const char* up : {"", "../", "../../"}) { tries.push_back(dir + "/" + up + tail); tries.push_back(dir + "/" + up + rest); }
+  } else {
+    tries.push_back(filename);
+    if (!dir.empty()) tries.push_back(dir + "/" + filename);
+  }
+  for (const std::string& path : tries) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) continue;
+    std::string data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    bool any = false;
+    auto take = [&](double x, double y, double z) {
+      const double v[3] = {x * scale[0], y * scale[1], z * scale[2]};
+      for (int k = 0; k < 3; k++) { lo[k] = any ? std::min(lo[k], v[k]) : v[k]; hi[k] = any ? std::max(hi[k], v[k]) : v[k]; }
+      any = true;
+    };
+    const bool obj = path.size() > 4 && (path.substr(path.size() - 4) == ".obj" || path.substr(path.size() - 4) == ".OBJ");
+    if (obj) {
+      std::istringstream ss(data); std::string line;
+      while (std::getline(ss, line)) if (line.size() > 2 && line[0] == 'v' && line[1] == ' ') { double x, y, z; if (std::sscanf(line.c_str() + 2, "%lf %lf %lf", &x, &y, &z) == 3) take(x, y, z); }
+    } else if (data.size() >= 84) {
+      uint32_t ntri = 0; std::memcpy(&ntri, data.data() + 80, 4);
+      if (data.size() == 84 + size_t(ntri) * 50) {           // binary STL: 80-byte header, count, 50 bytes per triangle
+        for (uint32_t t = 0; t < ntri; t++) for (int v = 0; v < 3; v++) { float c[3]; std::memcpy(c, data.data() + 84 + size_t(t) * 50 + 12 + 12 * v, 12); take(c[0], c[1], c[2]); }
+      } else {                                                 // ASCII STL: "vertex x y z"
+        size_t pos = 0;
+        while ((pos = data.find("vertex", pos)) != std::string::npos) { double x, y, z; if (std::sscanf(data.c_str() + pos + 6, "%lf %lf %lf", &x, &y, &z) == 3) take(x, y, z); pos += 6; }
+      }
+    }
+    if (any) return true;
+  }
+  return false;
+}
+
 struct Builder {
   Model md;
   std::map<std::string, const XmlNode*> links;
@@ -178,7 +225,8 @@ struct Builder {
   std::vector<Accum> acc;
   std::map<std::string, std::string> joint_of_link;              // child link -> name of the joint that carries it
 
-  int new_body(const std::string& name, int parent, int jt, const V3& jp, const M3& jr, const V3& ax, const std::string& jname, double lo, double hi) {
+  int new_body(const std::string& name, int parent, int jt, const V3& jp, const M3& jr, const V3& ax, const std::string& jname, double lo, double hi,
+               double effort = 1e30, double velocity = 1e30) {
     int i = md.nb++;
     md.parent.push_back(parent); md.jtype.push_back(jt);
     md.jpos.insert(md.jpos.end(), jp.begin(), jp.end());
@@ -186,6 +234,7 @@ struct Builder {
     md.axis.insert(md.axis.end(), ax.begin(), ax.end());
     md.body_names.push_back(name); md.joint_names.push_back(jname);
     md.jlimit.push_back(lo); md.jlimit.push_back(hi);
+    md.jeffort.push_back(effort); md.jvelocity.push_back(velocity);
     acc.emplace_back();
     return i;
   }
@@ -221,7 +270,17 @@ struct Builder {
       else if (const XmlNode* bx = g->child("box")) { type = CT_BOX; V3 sz = parse_v3(bx->get("size"), {0, 0, 0}); size = {0.5 * sz[0], 0.5 * sz[1], 0.5 * sz[2]}; }
       else if (const XmlNode* cp2 = g->child("capsule")) { type = CT_CAPSULE; size[0] = parse_d(cp2->get("radius"), "capsule radius"); size[1] = 0.5 * parse_d(cp2->get("length"), "capsule length"); }
       else if (const XmlNode* cy = g->child("cylinder")) { type = CT_CYLINDER; size[0] = parse_d(cy->get("radius"), "cylinder radius"); size[1] = 0.5 * parse_d(cy->get("length"), "cylinder length"); }
-      else if (g->child("mesh")) { md.skipped_collisions++; continue; }   // mesh collision bodies are not part of this path
+      else if (const XmlNode* me = g->child("mesh")) {
+        // mesh collision bodies are not part of this path: a mesh whose file can be read is replaced by its
+        // bounding box (centre and half extents in the collision frame, <mesh scale> applied); an unreadable one is skipped and counted
+        V3 lo3, hi3;
+        if (!mesh_bounds(md.source_dir, me->get("filename"), parse_v3(me->get("scale", "1 1 1"), {1, 1, 1}), lo3, hi3)) { md.skipped_collisions++; continue; }
+        type = CT_BOX;
+        V3 ctr = {0.5 * (lo3[0] + hi3[0]), 0.5 * (lo3[1] + hi3[1]), 0.5 * (lo3[2] + hi3[2])};
+        size = {0.5 * (hi3[0] - lo3[0]), 0.5 * (hi3[1] - lo3[1]), 0.5 * (hi3[2] - lo3[2])};
+        p = add(p, mul(R, ctr));
+        md.mesh_boxes++;
+      }
       else throw std::runtime_error("URDF: unsupported collision geometry in link '" + link_name + "' (sphere, box, capsule, cylinder are supported)");
       int ci = md.ncoll();
       md.cbody.push_back(b); md.ctype.push_back(type);
@@ -271,7 +330,12 @@ struct Builder {
         if (lim->has("lower")) lo = parse_d(lim->get("lower"), "limit lower");
         if (lim->has("upper")) hi = parse_d(lim->get("upper"), "limit upper");
       }
-      int nb = new_body(child, b, jt, jp, jr, ax, j->get("name"), lo, hi);
+      double effort = 1e30, velocity = 1e30;       // <limit effort velocity>: 0 or absent = unlimited (URDFs often carry effort="0" placeholders)
+      if (lim) {
+        if (lim->has("effort")) { double e = parse_d(lim->get("effort"), "limit effort"); if (e > 0) effort = e; }
+        if (lim->has("velocity")) { double v = parse_d(lim->get("velocity"), "limit velocity"); if (v > 0) velocity = v; }
+      }
+      int nb = new_body(child, b, jt, jp, jr, ax, j->get("name"), lo, hi, effort, velocity);
       absorb(nb, child, {0, 0, 0}, kEye);
     }
   }
@@ -321,6 +385,10 @@ Model load_urdf(const std::string& path_or_xml) {
   std::unique_ptr<XmlNode> root = parser.parse();
   if (root->tag != "robot") throw std::runtime_error("URDF: root element must be <robot>");
   Builder bd;
+  if (!(first != std::string::npos && path_or_xml[first] == '<')) {
+    size_t sl = path_or_xml.find_last_of('/');
+    bd.md.source_dir = sl == std::string::npos ? std::string(".") : path_or_xml.substr(0, sl);
+  }
   std::map<std::string, bool> is_child;
   for (const XmlNode* l : root->children("link")) {
     std::string n = l->get("name");
@@ -373,7 +441,7 @@ Model load_urdf(const std::string& path_or_xml) {
 //      re-parse XML.  Layout: magic "RSBM", version, then every field of Model in declaration order; vectors and strings
 //      carry a 64-bit length.  Little-endian, same-architecture cache (not an interchange format).
 namespace {
-constexpr uint32_t kCacheMagic = 0x4d425352u, kCacheVersion = 3u;
+constexpr uint32_t kCacheMagic = 0x4d425352u, kCacheVersion = 4u;
 struct Writer {
   std::ofstream f;
   template <class T> void pod(const T& v) { f.write(reinterpret_cast<const char*>(&v), sizeof(T)); }
@@ -393,6 +461,7 @@ template <class IO, class M> void model_fields(IO& io, M& md) {
   io.pod(md.nb); io.pod(md.nq); io.pod(md.nv); io.pod(md.floating); io.pod(md.maxdepth); io.pod(md.skipped_collisions);
   io.vec(md.parent); io.vec(md.jtype); io.vec(md.qidx); io.vec(md.vidx); io.vec(md.depth); io.vec(md.subtree);
   io.vec(md.jpos); io.vec(md.jrot); io.vec(md.axis); io.vec(md.mass); io.vec(md.com); io.vec(md.inertia); io.vec(md.jlimit);
+  io.vec(md.jeffort); io.vec(md.jvelocity); io.pod(md.mesh_boxes);
   io.strs(md.body_names); io.strs(md.joint_names);
   io.vec(md.cbody); io.vec(md.ctype); io.vec(md.csize); io.vec(md.cpos); io.vec(md.crot); io.strs(md.coll_names);
   io.vec(md.pt_body); io.vec(md.pt_coll); io.vec(md.pt_feat); io.vec(md.pt_type); io.vec(md.pt_pos); io.vec(md.pt_pos2); io.vec(md.pt_rad);
@@ -425,7 +494,7 @@ Model load_model(const std::string& path) {
   const size_t nb = (size_t)md.nb;
   if (md.nb < 1 || md.parent.size() != nb || md.jtype.size() != nb || md.qidx.size() != nb || md.vidx.size() != nb || md.depth.size() != nb ||
       md.subtree.size() != nb || md.jpos.size() != 3 * nb || md.jrot.size() != 9 * nb || md.axis.size() != 3 * nb || md.mass.size() != nb ||
-      md.com.size() != 3 * nb || md.inertia.size() != 6 * nb || md.jlimit.size() != 2 * nb || md.body_names.size() != nb || md.joint_names.size() != nb ||
+      md.com.size() != 3 * nb || md.inertia.size() != 6 * nb || md.jlimit.size() != 2 * nb || md.jeffort.size() != nb || md.jvelocity.size() != nb || md.body_names.size() != nb || md.joint_names.size() != nb ||
       md.ctype.size() != md.cbody.size() || md.csize.size() != 3 * md.cbody.size() || md.cpos.size() != 3 * md.cbody.size() || md.crot.size() != 9 * md.cbody.size() ||
       md.pt_coll.size() != md.pt_body.size() || md.pt_feat.size() != md.pt_body.size() || md.pt_pos.size() != 3 * md.pt_body.size() || md.pt_rad.size() != md.pt_body.size() ||
       md.pt_type.size() != md.pt_body.size() || md.pt_pos2.size() != 3 * md.pt_body.size() || md.coll_names.size() != md.cbody.size())

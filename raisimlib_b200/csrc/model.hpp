@@ -28,6 +28,7 @@ struct Model {
   int nb = 0, nq = 0, nv = 0, floating = 0, maxdepth = 0;
   std::vector<int> parent, jtype, qidx, vidx, depth, subtree;
   std::vector<double> jpos, jrot, axis, mass, com, inertia, jlimit;   // 3,9,3,1,3,6,2 per body
+  std::vector<double> jeffort, jvelocity;                              // <limit effort velocity> per body (1e30 = none); velocity is carried, not enforced
   std::vector<std::string> body_names, joint_names;
   // collision bodies
   std::vector<int> cbody, ctype;
@@ -39,7 +40,9 @@ struct Model {
   std::vector<int> pt_body, pt_coll, pt_feat, pt_type;
   std::vector<double> pt_pos, pt_rad, pt_pos2;
   std::vector<Frame> frames;                                            // one per URDF link
-  int skipped_collisions = 0;                                           // <mesh> collision bodies ignored by the loader
+  int skipped_collisions = 0;                                           // <mesh> collision bodies whose file could not be read (ignored)
+  int mesh_boxes = 0;                                                   // <mesh> collision bodies replaced by their bounding box
+  std::string source_dir;                                               // directory of the URDF file (mesh paths resolve against it)
   int ncoll() const { return (int)cbody.size(); }
   int npts() const { return (int)pt_body.size(); }
 };

@@ -9,6 +9,11 @@
 
 struct HmBest { bool hit; float depth; f3 n, pos; int pair; };
 
+// approximate reciprocal / reciprocal square root (MUFU, ~1e-7 relative): distances and normals here feed a 1e-6 m tie rule and a
+// float32 pose, an IEEE division (15 instructions with its slow path) buys nothing
+__device__ __forceinline__ float np_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float np_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 // keeps the deepest contact; a later triangle must be deeper by more than 1e-6 m to replace an earlier one (two triangles sharing the
 // touched edge give the same depth to rounding: the lower pair index wins, in the oracle and here alike)
 __device__ __forceinline__ void hm_offer(HmBest& b, float depth, f3 n, f3 pos, int pair) {
@@ -20,7 +25,7 @@ __device__ __forceinline__ f3 hm_vertex(const TerrainDesc& t, const float* H, in
 }
 __device__ __forceinline__ f3 hm_tri_normal(f3 a, f3 b, f3 c) {
   f3 n = cross(b - a, c - a);
-  float inv = 1.0f / sqrtf(dot(n, n));
+  float inv = np_rsqrt(dot(n, n));
   if (n.z < 0.f) inv = -inv;
   return inv * n;
 }
@@ -41,15 +46,15 @@ __device__ __forceinline__ f3 closest_on_triangle(f3 p, f3 a, f3 b, f3 c) {
   const float d3 = dot(ab, bp), d4 = dot(ac, bp);
   if (d3 >= 0.f && d4 <= d3) return b;
   const float vc = d1 * d4 - d3 * d2;
-  if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) return a + (d1 / (d1 - d3)) * ab;
+  if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) return a + (d1 * np_rcp(d1 - d3)) * ab;
   const f3 cp = p - c;
   const float d5 = dot(ab, cp), d6 = dot(ac, cp);
   if (d6 >= 0.f && d5 <= d6) return c;
   const float vb = d5 * d2 - d1 * d6;
-  if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) return a + (d2 / (d2 - d6)) * ac;
+  if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) return a + (d2 * np_rcp(d2 - d6)) * ac;
   const float va = d3 * d6 - d5 * d4;
-  if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) return b + ((d4 - d3) / ((d4 - d3) + (d5 - d6))) * (c - b);
-  const float den = 1.0f / (va + vb + vc);
+  if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) return b + ((d4 - d3) * np_rcp((d4 - d3) + (d5 - d6))) * (c - b);
+  const float den = np_rcp(va + vb + vc);
   return a + (vb * den) * ab + (vc * den) * ac;
 }
 // closest points of segments p1 + s d1 and p2 + t d2, s, t in [0, 1] (Ericson 5.1.9)
@@ -93,7 +98,8 @@ __device__ __forceinline__ HmBest sphere_vs_heightmap_group(const TerrainDesc& t
     if (!(side - r > 0.f)) {                                    // else: the whole sphere is above this triangle's plane
       const f3 Q = closest_on_triangle(C, a, b, c);
       v = C - Q;
-      dist = sqrtf(dot(v, v));
+      const float d2 = dot(v, v);
+      dist = d2 * np_rsqrt(fmaxf(d2, 1e-30f));
       pair = 2 * (iy * (t.xs - 1) + ix) + tri;
     }
   }
@@ -109,14 +115,14 @@ __device__ __forceinline__ HmBest sphere_vs_heightmap_group(const TerrainDesc& t
   const float wd = __shfl_sync(FULL, dist, wl);
   const f3 wv = shfl3(v, wl), wn = shfl3(nt, wl);
   if (wm) {
-    const f3 n = (!inside && wd > 1e-9f) ? (1.0f / wd) * wv : wn;
+    const f3 n = (!inside && wd > 1e-9f) ? np_rcp(wd) * wv : wn;
     hm_offer(best, inside ? r + wd : r - wd, n, C - r * n, kmin);
   }
   return best;
 }
 
 // interior of segment A-B swept by radius r against the terrain edges under its AABB (the end spheres are candidates of their own)
-__device__ __forceinline__ HmBest segment_vs_heightmap(const TerrainDesc& t, int hm_offset, f3 A, f3 B, float r) {
+__device__ __noinline__ HmBest segment_vs_heightmap(const TerrainDesc& t, int hm_offset, f3 A, f3 B, float r) {
   HmBest best; best.hit = false; best.depth = 0.f; best.n = mk(0.f, 0.f, 1.f); best.pos = A; best.pair = 0;
   int ix0, ix1, iy0, iy1;
   const f3 M = 0.5f * (A + B);
@@ -159,7 +165,7 @@ __device__ __forceinline__ HmBest segment_vs_heightmap(const TerrainDesc& t, int
 }
 
 // terrain vertices inside the box (centre c, rotation Rb row-major, half extents h): the vertex deepest inside, pushed out through its nearest face
-__device__ __forceinline__ HmBest box_vs_heightmap(const TerrainDesc& t, int hm_offset, f3 c, const float* Rb, f3 h) {
+__device__ __noinline__ HmBest box_vs_heightmap(const TerrainDesc& t, int hm_offset, f3 c, const float* Rb, f3 h) {
   HmBest best; best.hit = false; best.depth = 0.f; best.n = mk(0.f, 0.f, 1.f); best.pos = c; best.pair = 0;
   const float ex = fabsf(Rb[0]) * h.x + fabsf(Rb[1]) * h.y + fabsf(Rb[2]) * h.z, ey = fabsf(Rb[3]) * h.x + fabsf(Rb[4]) * h.y + fabsf(Rb[5]) * h.z;
   int ix0, ix1, iy0, iy1;

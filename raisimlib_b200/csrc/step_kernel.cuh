@@ -90,7 +90,7 @@ __host__ __device__ constexpr BlobHeader make_blob_header(Dims d, int npts, int 
   int off = HEADER_WORDS;
   H.off_body = off; off += 33 * H.nbp;
   H.off_anc = off; off += max_c(1, d.maxdepth) * H.nbp;
-  H.off_gain = off; off += 2 * H.nvp;
+  H.off_gain = off; off += 3 * H.nvp;                 // kp, kd, actuator effort limit per dof
   H.off_dofq = off; off += H.nvp;
   H.off_sec = off; off += 2 * NROUNDS * SEC_STRIDE;
   H.off_ddepth = off; off += H.nvp;
@@ -111,7 +111,7 @@ __host__ __device__ constexpr BlobHeader make_blob_header(Dims d, int npts, int 
 
 // per-warp workspace layout (word offsets)
 struct WsLayout {
-  int o_gc, o_gv, o_tau, o_pt, o_vt, o_L, o_invd, o_rhs, o_z, o_ct, o_Y, o_lam, o_u, o_lim, o_hist;   // persistent
+  int o_gc, o_gv, o_tau, o_pt, o_vt, o_L, o_invd, o_rhs, o_z, o_ct, o_Y, o_lam, o_u, o_lim, o_hist, o_sat;   // persistent
   int o_h, o_b, o_pose;                                                                  // union A
   int o_G;                                                                               // union B
   int words;
@@ -135,6 +135,7 @@ __host__ __device__ constexpr WsLayout make_ws_layout(Dims d) {
   L.o_lam = o; o += 32;
   L.o_u = o; o += CB_WORDS * KMAX;                                // per contact: G_ii (6), friction, its inverse (6): contact_solver.cuh
   L.o_lim = o; o += 4 * LMAX;                                     // joint-limit rows: dof, sign, violation
+  L.o_sat = o; o += nvp;                                          // dof driven at its actuator effort limit in this sub-step (stage C -> E)
   L.o_hist = o; o += HIST_WORDS;                                  // Anderson acceleration: u0, x, g, f, dG, dF (one value per constraint row each)
   // union: {h, b, poses} (stages A-C) overlaid by G (stages C-D)
   int ua = 0;
@@ -401,6 +402,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
   const int* ptsi = reinterpret_cast<const int*>(blob_s + HO(off_pts));
   const float* kp = reinterpret_cast<const float*>(blob_s + HO(off_gain));
   const float* kd = kp + nvp;
+  const float* emax = kp + 2 * nvp;     // actuator effort limit per dof (URDF <limit effort>, 3e38 = none)
   const int* dofq = reinterpret_cast<const int*>(blob_s + HO(off_dofq));
   const float* sec_c = reinterpret_cast<const float*>(blob_s + HO(off_sec));
   const int nbase = HO(nbase), maxdd = HO(maxdd), DLP = HO(dlp);
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
   float* const ws = reinterpret_cast<float*>(smem) + warp * WSO(words);
   float* s_gc = ws + WSO(o_gc); float* s_gv = ws + WSO(o_gv); float* s_tau = ws + WSO(o_tau); float* s_pt = ws + WSO(o_pt); float* s_vt = ws + WSO(o_vt);
   float* s_L = ws + WSO(o_L); float* s_invd = ws + WSO(o_invd); float* s_rhs = ws + WSO(o_rhs); float* s_z = ws + WSO(o_z); float* s_ct = ws + WSO(o_ct);
-  float* s_Y = ws + WSO(o_Y); float* s_lam = ws + WSO(o_lam); float* s_u = ws + WSO(o_u); float* s_lim = ws + WSO(o_lim); float* s_hist = ws + WSO(o_hist);
+  float* s_Y = ws + WSO(o_Y); float* s_lam = ws + WSO(o_lam); float* s_u = ws + WSO(o_u); float* s_lim = ws + WSO(o_lim); float* s_hist = ws + WSO(o_hist); float* s_sat = ws + WSO(o_sat);
   float* s_h = ws + WSO(o_h); float* s_b = ws + WSO(o_b); float* s_pose = ws + WSO(o_pose); float* s_G = ws + WSO(o_G);
 #undef WSO
 #undef HO
@@ -842,13 +844,21 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
 #pragma unroll 1
       for (int i = lane; i < nv; i += 32) {
         float bi = s_tau[i] - s_h[i];
-        if (args.use_pd) {
-          float kpi = kp[i], kdi = kd[i];
-          if (kpi != 0.f || kdi != 0.f) {
-            int qi = dofq[i];
-            bi += kpi * (s_pt[qi] - s_gc[qi] - args.prm.dt * s_gv[i]) + kdi * (s_vt[i] - s_gv[i]);
-            s_L[i * DLP + ddepth[i]] += args.prm.dt * kdi + args.prm.dt * args.prm.dt * kpi;
-          }
+        // actuator effort limit (oracle step()): when feed-forward + PD law at the current state exceed it, the joint is driven by the
+        // constant limit torque over this step and gets no implicit PD terms
+        float te = s_tau[i];
+        const float kpi = args.use_pd ? kp[i] : 0.f, kdi = args.use_pd ? kd[i] : 0.f;
+        const bool pd = kpi != 0.f || kdi != 0.f;
+        const int qi = pd ? dofq[i] : 0;
+        if (pd) te += kpi * (s_pt[qi] - s_gc[qi]) + kdi * (s_vt[i] - s_gv[i]);
+        // ... judged on the torque the implicit law would really apply (the explicit value over 1 + (dt kd + dt^2 kp) / M_dd)
+        const float soft = args.prm.dt * kdi + args.prm.dt * args.prm.dt * kpi;
+        const bool sat = fabsf(te) > emax[i] * (1.f + soft / s_L[i * DLP + ddepth[i]]);
+        s_sat[i] = sat ? 1.f : 0.f;          // remembered for stage E (generalized force applied)
+        if (sat) bi += copysignf(emax[i], te) - s_tau[i];
+        else if (pd) {
+          bi += kpi * (s_pt[qi] - s_gc[qi] - args.prm.dt * s_gv[i]) + kdi * (s_vt[i] - s_gv[i]);
+          s_L[i * DLP + ddepth[i]] += args.prm.dt * kdi + args.prm.dt * args.prm.dt * kpi;
         }
         s_b[i] = bi;
       }
@@ -1277,14 +1287,17 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       }
 #pragma unroll 1
       for (int i = lane; i < nv; i += 32) {
-        const float vp = s_gv[i] + s_rhs[i];
+        const float v0 = s_gv[i], vp = v0 + s_rhs[i];
         s_gv[i] = vp;
-        // generalized force applied over this step (implicit PD evaluated at q + dt v+, v+): getGeneralizedForce()
+        // generalized force applied over this step (implicit PD evaluated at q + dt v+, v+; the effort limit where it was hit): getGeneralizedForce()
         float ta = s_tau[i];
-        if (args.use_pd) {
-          const float kpi = kp[i], kdi = kd[i];
-          if (kpi != 0.f || kdi != 0.f) { const int qi = dofq[i]; ta += kpi * (s_pt[qi] - s_gc[qi] - args.prm.dt * vp) + kdi * (s_vt[i] - vp); }
-        }
+        const float kpi = args.use_pd ? kp[i] : 0.f, kdi = args.use_pd ? kd[i] : 0.f;
+        const bool pd = kpi != 0.f || kdi != 0.f;
+        const int qi = pd ? dofq[i] : 0;
+        float te = ta;
+        if (pd) te += kpi * (s_pt[qi] - s_gc[qi]) + kdi * (s_vt[i] - v0);
+        if (s_sat[i] != 0.f) ta = copysignf(emax[i], te);
+        else if (pd) ta += kpi * (s_pt[qi] - s_gc[qi] - args.prm.dt * vp) + kdi * (s_vt[i] - vp);
         s_b[i] = ta;
       }
       __syncwarp();

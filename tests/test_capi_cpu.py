@@ -41,7 +41,7 @@ def test_model_tables_match_python_restatement(src):
         assert a[k] == b[k], k
     for k in ("parent", "jtype", "qidx", "vidx", "depth", "cbody", "ctype", "pt_body", "pt_coll", "pt_feat", "pt_type"):
         assert (a[k] == b[k]).all(), k
-    for k in ("jpos", "jrot", "axis", "mass", "com", "inertia", "jlimit", "csize", "cpos", "crot", "pt_pos", "pt_rad", "pt_pos2"):
+    for k in ("jpos", "jrot", "axis", "mass", "com", "inertia", "jlimit", "csize", "cpos", "crot", "pt_pos", "pt_rad", "pt_pos2", "jeffort"):
         assert np.allclose(a[k], b[k], rtol=1e-13, atol=1e-15), k
     assert a["body_names"] == b["body_names"] and a["joint_names"] == b["joint_names"]
 
@@ -201,3 +201,16 @@ def test_product_never_touches_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|liboracle|-loracle|#\s*include[^\n]*oracle|orc_[a-z_]+\(", txt, re.M):
                     bad.append(os.path.relpath(os.path.join(root, f), ROOT))
     assert not bad, bad
+
+
+def test_pybind_module_loads_and_fails_loudly_without_gpu():
+    """N4: the pybind11 + DLPack module (raisimlib_b200/_rsb_py) imports on a CPU-only machine, parses a model, and refuses to
+    create a batch without a GPU (no CPU fallback)"""
+    import torch
+    from raisimlib_b200 import _rsb_py
+    m = _rsb_py.Model(os.path.join(RSC, "anymal_c_like.urdf"))
+    with pytest.raises(RuntimeError, match="cannot open"):
+        _rsb_py.Model("/nonexistent.urdf")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            _rsb_py.Batch(m, 4, 0)

@@ -117,9 +117,12 @@ def test_contact_indices_bit_exact(capi, terrain):
     assert (ct["local_body"][same] == d32["c_body"][same]).all()
     assert (ct["pair_index"][same] == d32["c_pair"][same]).all()
     live = same[:, None] & (d32["c_pt"] >= 0)
-    assert np.abs(ct["depth"] - d32["c_depth"])[live].max() < 1e-6
-    assert np.abs(ct["normal"] - d32["c_normal"])[live].max() < 1e-6
-    assert np.abs(ct["position"] - d32["c_pos"])[live].max() < 5e-6
+    assert np.abs(ct["depth"] - d32["c_depth"])[live].max() < 2e-6
+    # a sphere's normal is (centre - closest terrain point) / distance: rounding of the pose (1e-7 m) over a distance of r - depth
+    rad = np.where(d32["c_pt"] >= 0, t["pt_rad"][np.maximum(d32["c_pt"], 0)], 0.0)
+    tol_n = 2e-6 + 4e-7 / np.maximum(rad - d32["c_depth"], 1e-4)
+    assert (np.abs(ct["normal"] - d32["c_normal"]).max(2)[live] < tol_n[live]).all()
+    assert (np.abs(ct["position"] - d32["c_pos"]).max(2)[live] < 5e-6 + rad[live] * tol_n[live]).all()
     if terrain == "hm":
         assert len(np.unique(ct["pair_index"][live])) > 100   # many different cells / both triangles
 
@@ -1134,7 +1137,9 @@ def test_heightmap_narrow_phase_matches_oracle_on_rough_terrain(capi):
         pair_same = (ct["pair_index"] == d["c_pair"])[live].mean()
         assert pair_same > 0.995                                                                   # same reason: which of two triangles sharing an edge
         ok = live & (ct["pair_index"] == d["c_pair"])
-        assert np.abs(ct["depth"] - d["c_depth"])[ok].max() < 5e-6 and np.abs(ct["normal"] - d["c_normal"])[ok].max() < 2e-4
+        rad = np.where(d["c_pt"] >= 0, t["pt_rad"][np.maximum(d["c_pt"], 0)], 0.0)
+        tol_n = 2e-6 + 4e-7 / np.maximum(rad - d["c_depth"], 1e-4)         # normal = (centre - closest point) / distance
+        assert np.abs(ct["depth"] - d["c_depth"])[ok].max() < 5e-6 and (np.abs(ct["normal"] - d["c_normal"]).max(2)[ok] < tol_n[ok]).all()
 
 
 def test_cpp_generic_vectorized_environment_example(capi):
@@ -1150,3 +1155,36 @@ def test_cpp_generic_vectorized_environment_example(capi):
     print(out.stdout, out.stderr[-500:])
     assert out.returncode == 0, out.stdout + out.stderr
     assert "1.00 per control step" in out.stdout and "max |difference| over observations and rewards 0" in out.stdout
+
+
+def test_pybind_dlpack_zero_copy_views(capi):
+    """N4: the pybind11 module hands out the batch rows as DLPack capsules; torch.from_dlpack() gives strided CUDA tensors that alias
+    the memory the step kernel works on (writes are seen by the next integrate(), results appear in the tensors), and a control step
+    driven entirely through device tensors equals the ctypes path bit for bit."""
+    import torch
+    from raisimlib_b200 import _rsb_py
+    n = 96
+    t, bt, o64, o32, gc, gv, tau = _setup(capi, "anymal_c_like.urdf", n, seed=601, base_z=0.55, joint_scale=0.2)
+    pm = _rsb_py.Model(os.path.join(RSC, "anymal_c_like.urdf"))
+    pb = _rsb_py.Batch(pm, n, 0)
+    pb.set_ground(0.0)
+    tg, tv = torch.from_dlpack(pb.gc()), torch.from_dlpack(pb.gv())
+    assert tg.is_cuda and tg.shape == (n, 19) and tv.shape == (n, 18) and tg.stride(0) >= 19 and tg.dtype == torch.float32
+    tg.copy_(torch.from_numpy(gc.astype(np.float32)).cuda()); tv.copy_(torch.from_numpy(gv.astype(np.float32)).cuda())     # write through the views
+    kp = [0.0] * 6 + [120.0] * 12; kd = [0.0] * 6 + [3.0] * 12
+    pb.set_pd_gains(kp, kd)
+    target = torch.from_numpy(np.tile(ANYMAL_GC0, (n, 1)).astype(np.float32)).cuda().contiguous()
+    obs = torch.empty((n, pb.ob_dim), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    pb.control_step(target.data_ptr(), 4, obs.data_ptr())
+    pb.sync()
+    # the ctypes path from the same state
+    bt.set_control_mode(capi.PD_PLUS_FEEDFORWARD_TORQUE)
+    bt.set_pd_gains(np.array(kp), np.array(kd))
+    bt.set_pd_target(target.cpu().numpy(), np.zeros((n, 18), np.float32))
+    bt.integrate(4)
+    g_ref, v_ref = bt.get_state()
+    assert np.array_equal(tg.cpu().numpy(), g_ref) and np.array_equal(tv.cpu().numpy(), v_ref)          # the tensors ARE the state
+    assert np.array_equal(obs.cpu().numpy(), bt.observe())
+    del pb                                                             # the tensors keep the batch alive
+    assert torch.isfinite(tg).all()

@@ -771,3 +771,26 @@ def test_cylinder_rolls_on_its_side_without_bobbing():
         o.step(gc, gv)
         z.append(gc[0, 2])
     assert max(z) - min(z) < 2e-4 and abs(gv[0, 0] - 0.35) < 5e-3 and gc[0, 0] > 0.33
+
+
+EFFORT_PENDULUM = LIMIT_PENDULUM.replace('<limit lower="-0.5" upper="0.5" effort="10" velocity="10"/>', '<limit lower="-3" upper="3" effort="1.5" velocity="10"/>')
+
+
+def test_actuator_effort_limit_saturates_the_commanded_torque():
+    """N2: URDF <limit effort>: a PD law that asks for more than the actuator can give drives the joint with the limit torque
+    (alpha = tau_max / I exactly, whatever the gains); below the limit the implicit PD law is untouched"""
+    t = load_tables(EFFORT_PENDULUM)
+    assert np.isclose(t["jeffort"][1], 1.5) and t["jeffort"][0] >= 1e29
+    o = Oracle(t, params=dict(gz=0.0))                       # no gravity: the only torque is the actuator's
+    I = 0.1 + 2.0 * 0.5 ** 2                                 # inertia about the joint axis (iyy + m c^2)
+    for kp, target, expect in ((4000.0, 1.0, 1.5), (4000.0, -1.0, -1.5), (1.0, 1.0, None)):
+        gc = np.zeros((1, 1)); gv = np.zeros((1, 1))
+        d = o.step(gc, gv, ptarget=np.array([[target]]), vtarget=np.zeros((1, 1)), kp=np.array([kp]), kd=np.array([0.0]), debug=True)
+        if expect is not None:
+            assert abs(gv[0, 0] - expect / I * 0.0025) < 1e-12 and abs(d["tau_applied"][0, 0] - expect) < 1e-12
+        else:                                                # 1 N m asked, 1.5 available: implicit PD, v+ = dt kp (q* - q) / (I + dt^2 kp)
+            assert abs(gv[0, 0] - 0.0025 * 1.0 / (I + 0.0025 ** 2 * 1.0)) < 1e-12
+    # feed-forward torque alone is limited too
+    gc = np.zeros((1, 1)); gv = np.zeros((1, 1))
+    o.step(gc, gv, tau_ff=np.array([[7.0]]))
+    assert abs(gv[0, 0] - 1.5 / I * 0.0025) < 1e-12
