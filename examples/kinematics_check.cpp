@@ -89,6 +89,36 @@ int main(int argc, char** argv) {
   }
   std::printf("external force vs dt M^-1 J^T F: %.3e\n", worst_f);
   if (!(worst_f < 5e-5)) return 1;
+  // jointOrder (upstream addArticulatedSystem(urdf, resDir, jointOrder)): the same robot with its legs listed hind-first gives the same
+  // motion, seen through the caller's ordering of gc / gv / targets
+  {
+    const char* legs[4] = {"LF", "RF", "LH", "RH"};
+    const char* joints[3] = {"HAA", "HFE", "KFE"};
+    std::vector<std::string> order;
+    for (int l = 3; l >= 0; l--) for (int j = 0; j < 3; j++) order.push_back(std::string(legs[l]) + "_" + joints[j]);
+    raisim::World wa, wb;
+    for (raisim::World* w : {&wa, &wb}) { w->setTimeStep(0.0025); w->addGround(0.0); }
+    auto* ra = wa.addArticulatedSystem(urdf);
+    auto* rb = wb.addArticulatedSystem(urdf, "", order);
+    raisim::VecDyn qa(nq), va(nv), qb(nq), vb(nv), kp(nv), kd(nv);
+    const double stance[19] = {0, 0, 0.57, 1, 0, 0, 0, 0.03, 0.4, -0.8, -0.03, 0.4, -0.8, 0.03, -0.4, 0.8, -0.03, -0.4, 0.8};
+    for (int i = 0; i < 19; i++) qa[i] = stance[i];
+    for (int i = 0; i < 7; i++) qb[i] = qa[i];
+    for (int l = 0; l < 4; l++) for (int j = 0; j < 3; j++) qb[7 + 3 * l + j] = qa[7 + 3 * (3 - l) + j];      // caller's order: RH, LH, RF, LF
+    for (size_t i = 6; i < nv; i++) { kp[i] = 120.0 + double(i); kd[i] = 2.0 + 0.1 * double(i); }              // gains differ per joint: the permutation must carry them
+    raisim::VecDyn kpb(nv), kdb(nv);
+    for (int l = 0; l < 4; l++) for (int j = 0; j < 3; j++) { kpb[6 + 3 * l + j] = kp[6 + 3 * (3 - l) + j]; kdb[6 + 3 * l + j] = kd[6 + 3 * (3 - l) + j]; }
+    ra->setState(qa, va); rb->setState(qb, vb);
+    ra->setPdGains(kp, kd); rb->setPdGains(kpb, kdb);
+    ra->setPdTarget(qa, va); rb->setPdTarget(qb, vb);
+    for (int k = 0; k < 200; k++) { wa.integrate(); wb.integrate(); }
+    ra->getState(qa, va); rb->getState(qb, vb);
+    double worst_o = 0;
+    for (int i = 0; i < 7; i++) worst_o = std::fmax(worst_o, std::fabs(qa[i] - qb[i]));
+    for (int l = 0; l < 4; l++) for (int j = 0; j < 3; j++) worst_o = std::fmax(worst_o, std::fabs(qb[7 + 3 * l + j] - qa[7 + 3 * (3 - l) + j]) + std::fabs(vb[6 + 3 * l + j] - va[6 + 3 * (3 - l) + j]));
+    std::printf("jointOrder: same motion through the caller's joint order, max difference %.3g\n", worst_o);
+    if (worst_o != 0.0) return 1;
+  }
   std::printf("frame velocity vs finite difference: %.3e m/s   angular: %.3e rad/s   orthonormality: %.2e   body-vs-frame API: %.2e\n",
               worst_v, worst_w, worst_orth, worst_j);
   // float32 poses differenced over dt = 1e-3: ~1e-7 / 1e-3 = 1e-4 rounding + O(dt |a|) truncation

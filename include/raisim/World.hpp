@@ -186,6 +186,26 @@ struct TerrainProperties {
 class ArticulatedSystem {
  public:
   ArticulatedSystem(BatchedWorld* w, int env) : w_(w), env_(env) {}
+  // upstream addArticulatedSystem(urdf, resDir, jointOrder): the order of the joints in gc / gv as the caller wants it.  The batch keeps
+  // its depth-first order; this view permutes on the way in and out (base coordinates first, as always).
+  void setJointOrder(const std::vector<std::string>& jointOrder) {
+    qmap_.clear(); vmap_.clear();
+    if (jointOrder.empty()) return;
+    rsb_model_tables t; rsbCheck(rsb_model_get_tables(w_->model(), &t), "getTables");
+    const int nj = t.nb - 1, q0 = t.floating ? 7 : 0, v0 = t.floating ? 6 : 0;
+    if (int(jointOrder.size()) != nj) throw std::runtime_error("addArticulatedSystem: jointOrder must name every movable joint exactly once");
+    qmap_.resize(size_t(t.nq)); vmap_.resize(size_t(t.nv));
+    for (int i = 0; i < q0; i++) qmap_[i] = i;
+    for (int i = 0; i < v0; i++) vmap_[i] = i;
+    std::vector<bool> seen(size_t(t.nb), false);
+    for (int k = 0; k < nj; k++) {
+      int body = -1;
+      for (int b = 1; b < t.nb; b++) if (jointOrder[k] == rsb_model_joint_name(w_->model(), b)) body = b;
+      if (body < 0 || seen[body]) throw std::runtime_error("addArticulatedSystem: jointOrder names an unknown joint or one joint twice: '" + jointOrder[k] + "'");
+      seen[body] = true;
+      qmap_[q0 + k] = t.qidx[body]; vmap_[v0 + k] = t.vidx[body];
+    }
+  }
   size_t getGeneralizedCoordinateDim() const { return size_t(w_->nq()); }
   size_t getDOF() const { return size_t(w_->nv()); }
   void setName(const std::string& n) { name_ = n; }
@@ -195,81 +215,81 @@ class ArticulatedSystem {
     if (LockStep* ls = w_->lockStep()) {
       ls->sync(env_); ls->needState();
       gc.resize(size_t(ls->nq)); gv.resize(size_t(ls->nv));
-      for (int i = 0; i < ls->nq; i++) gc[i] = ls->gc[size_t(env_) * ls->nq + i];
-      for (int i = 0; i < ls->nv; i++) gv[i] = ls->gv[size_t(env_) * ls->nv + i];
+      for (int i = 0; i < ls->nq; i++) gc[i] = ls->gc[size_t(env_) * ls->nq + qi(i)];
+      for (int i = 0; i < ls->nv; i++) gv[i] = ls->gv[size_t(env_) * ls->nv + vi(i)];
       return;
     }
     std::vector<float> q(w_->nq()), v(w_->nv());
     rsbCheck(rsb_batch_get_state(w_->batch(), q.data(), v.data(), env_, 1, RSB_HOST), "getState");
     gc.resize(q.size()); gv.resize(v.size());
-    for (size_t i = 0; i < q.size(); i++) gc[i] = q[i];
-    for (size_t i = 0; i < v.size(); i++) gv[i] = v[i];
+    for (size_t i = 0; i < q.size(); i++) gc[i] = q[qi(i)];
+    for (size_t i = 0; i < v.size(); i++) gv[i] = v[vi(i)];
   }
   VecDyn getGeneralizedCoordinate() const { VecDyn q, v; getState(q, v); return q; }
   VecDyn getGeneralizedVelocity() const { VecDyn q, v; getState(q, v); return v; }
   template <class VQ, class VV> void setState(const VQ& gc, const VV& gv) {
     if (LockStep* ls = w_->lockStep()) {
       ls->sync(env_); ls->needState();           // the other environments' rows of the mirror must be current before the whole array goes up
-      for (int i = 0; i < ls->nq; i++) ls->gc[size_t(env_) * ls->nq + i] = float(gc[i]);
-      for (int i = 0; i < ls->nv; i++) ls->gv[size_t(env_) * ls->nv + i] = float(gv[i]);
+      for (int i = 0; i < ls->nq; i++) ls->gc[size_t(env_) * ls->nq + qi(i)] = float(gc[i]);
+      for (int i = 0; i < ls->nv; i++) ls->gv[size_t(env_) * ls->nv + vi(i)] = float(gv[i]);
       ls->stateDirty = true;
       return;
     }
     std::vector<float> q(w_->nq()), v(w_->nv());
-    for (size_t i = 0; i < q.size(); i++) q[i] = float(gc[i]);
-    for (size_t i = 0; i < v.size(); i++) v[i] = float(gv[i]);
+    for (size_t i = 0; i < q.size(); i++) q[qi(i)] = float(gc[i]);
+    for (size_t i = 0; i < v.size(); i++) v[vi(i)] = float(gv[i]);
     rsbCheck(rsb_batch_set_state(w_->batch(), q.data(), v.data(), env_, 1, RSB_HOST), "setState");
   }
   template <class VQ> void setGeneralizedCoordinate(const VQ& gc) {
     if (LockStep* ls = w_->lockStep()) {
       ls->sync(env_); ls->needState();
-      for (int i = 0; i < ls->nq; i++) ls->gc[size_t(env_) * ls->nq + i] = float(gc[i]);
+      for (int i = 0; i < ls->nq; i++) ls->gc[size_t(env_) * ls->nq + qi(i)] = float(gc[i]);
       ls->stateDirty = true;
       return;
     }
     std::vector<float> q(w_->nq());
-    for (size_t i = 0; i < q.size(); i++) q[i] = float(gc[i]);
+    for (size_t i = 0; i < q.size(); i++) q[qi(i)] = float(gc[i]);
     rsbCheck(rsb_batch_set_state(w_->batch(), q.data(), nullptr, env_, 1, RSB_HOST), "setGeneralizedCoordinate");
   }
   template <class VV> void setGeneralizedVelocity(const VV& gv) {
     if (LockStep* ls = w_->lockStep()) {
       ls->sync(env_); ls->needState();
-      for (int i = 0; i < ls->nv; i++) ls->gv[size_t(env_) * ls->nv + i] = float(gv[i]);
+      for (int i = 0; i < ls->nv; i++) ls->gv[size_t(env_) * ls->nv + vi(i)] = float(gv[i]);
       ls->stateDirty = true;
       return;
     }
     std::vector<float> v(w_->nv());
-    for (size_t i = 0; i < v.size(); i++) v[i] = float(gv[i]);
+    for (size_t i = 0; i < v.size(); i++) v[vi(i)] = float(gv[i]);
     rsbCheck(rsb_batch_set_state(w_->batch(), nullptr, v.data(), env_, 1, RSB_HOST), "setGeneralizedVelocity");
   }
   template <class VV> void setGeneralizedForce(const VV& tau) {
     if (LockStep* ls = w_->lockStep()) {
       ls->sync(env_);
-      for (int i = 0; i < ls->nv; i++) ls->tau[size_t(env_) * ls->nv + i] = float(tau[i]);
+      for (int i = 0; i < ls->nv; i++) ls->tau[size_t(env_) * ls->nv + vi(i)] = float(tau[i]);
       ls->tauDirty = true;
       return;
     }
     std::vector<float> t(w_->nv());
-    for (size_t i = 0; i < t.size(); i++) t[i] = float(tau[i]);
+    for (size_t i = 0; i < t.size(); i++) t[vi(i)] = float(tau[i]);
     rsbCheck(rsb_batch_set_generalized_force(w_->batch(), t.data(), env_, 1, RSB_HOST), "setGeneralizedForce");
   }
   // gains are shared by every environment of the batch (they are per-robot-model constants in RaisimGym)
   template <class VV> void setPdGains(const VV& p, const VV& d) {
     std::vector<float> kp(w_->nv()), kd(w_->nv());
-    for (size_t i = 0; i < kp.size(); i++) { kp[i] = float(p[i]); kd[i] = float(d[i]); }
+    for (size_t i = 0; i < kp.size(); i++) { kp[vi(i)] = float(p[i]); kd[vi(i)] = float(d[i]); }
     rsbCheck(rsb_batch_set_pd_gains(w_->batch(), kp.data(), kd.data()), "setPdGains");
   }
   template <class VQ, class VV> void setPdTarget(const VQ& posTarget, const VV& velTarget) {
     if (LockStep* ls = w_->lockStep()) {
       ls->sync(env_);
-      for (int i = 0; i < ls->nq; i++) ls->pt[size_t(env_) * ls->nq + i] = float(posTarget[i]);
-      for (int i = 0; i < ls->nv; i++) ls->vt[size_t(env_) * ls->nv + i] = float(velTarget[i]);
+      for (int i = 0; i < ls->nq; i++) ls->pt[size_t(env_) * ls->nq + qi(i)] = float(posTarget[i]);
+      for (int i = 0; i < ls->nv; i++) ls->vt[size_t(env_) * ls->nv + vi(i)] = float(velTarget[i]);
       ls->ptDirty = ls->vtDirty = true;
       return;
     }
     std::vector<float> q(w_->nq()), v(w_->nv());
-    for (size_t i = 0; i < q.size(); i++) q[i] = float(posTarget[i]);
-    for (size_t i = 0; i < v.size(); i++) v[i] = float(velTarget[i]);
+    for (size_t i = 0; i < q.size(); i++) q[qi(i)] = float(posTarget[i]);
+    for (size_t i = 0; i < v.size(); i++) v[vi(i)] = float(velTarget[i]);
     rsbCheck(rsb_batch_set_pd_target(w_->batch(), q.data(), v.data(), env_, 1, RSB_HOST), "setPdTarget");
   }
   void setControlMode(ControlMode::Type m) { rsbCheck(rsb_batch_set_control_mode(w_->batch(), int(m)), "setControlMode"); }
@@ -313,13 +333,13 @@ class ArticulatedSystem {
     if (LockStep* ls = w_->lockStep()) {
       ls->sync(env_); ls->needTauApplied();
       VecDyn r(size_t(ls->nv));
-      for (int i = 0; i < ls->nv; i++) r[i] = ls->tauApplied[size_t(env_) * ls->nv + i];
+      for (int i = 0; i < ls->nv; i++) r[i] = ls->tauApplied[size_t(env_) * ls->nv + vi(i)];
       return r;
     }
     std::vector<float> t(w_->nv());
     rsbCheck(rsb_batch_get_generalized_force(w_->batch(), t.data(), env_, 1, RSB_HOST), "getGeneralizedForce");
     VecDyn r(t.size());
-    for (size_t i = 0; i < t.size(); i++) r[i] = t[i];
+    for (size_t i = 0; i < t.size(); i++) r[i] = t[vi(i)];
     return r;
   }
   // upstream: setExternalForce(localIdx, force) acts at the body COM, setExternalForce(localIdx, pos_in_body, force) at a
@@ -484,6 +504,9 @@ class ArticulatedSystem {
     VecDyn gv = getGeneralizedVelocity();
     for (int r = 0; r < 3; r++) { double s = 0; for (size_t c = 0; c < J.cols(); c++) s += J(r, c) * gv[c]; out[r] = s; }
   }
+  size_t qi(size_t i) const { return qmap_.empty() ? i : size_t(qmap_[i]); }     // caller's coordinate index -> the batch's
+  size_t vi(size_t i) const { return vmap_.empty() ? i : size_t(vmap_[i]); }
+  std::vector<int> qmap_, vmap_;
   BatchedWorld* w_;
   int env_;
   std::string name_;
@@ -506,7 +529,7 @@ class World {
   World(BatchedWorld* shared, int env) : w_(shared), env_(env) { robot_.reset(new ArticulatedSystem(w_, env_)); }
   static void setActivationKey(const std::string&) {}          // licence check of the reference: not a capability
 
-  ArticulatedSystem* addArticulatedSystem(const std::string& urdfPathOrXml, const std::string& = "", const std::vector<std::string>& = {},
+  ArticulatedSystem* addArticulatedSystem(const std::string& urdfPathOrXml, const std::string& = "", const std::vector<std::string>& jointOrder = {},
                                           CollisionGroup = 1, CollisionGroup = CollisionGroup(-1)) {
     if (w_) throw std::runtime_error("addArticulatedSystem: this World is a view of a BatchedWorld (one robot per environment)");
     if (ctx_) {   // environment of a VectorizedEnvironment: attach to (or create) the shared batch
@@ -521,6 +544,7 @@ class World {
       w_->setParams(p);
       if (haveGround_) rsbCheck(rsb_batch_set_ground(w_->batch(), float(groundZ_)), "addGround");
       robot_.reset(new ArticulatedSystem(w_, env_));
+      robot_->setJointOrder(jointOrder);
       return robot_.get();
     }
     owned_.reset(new BatchedWorld(urdfPathOrXml, 1));
@@ -530,6 +554,7 @@ class World {
     w_->setParams(p);
     if (haveGround_) rsbCheck(rsb_batch_set_ground(w_->batch(), float(groundZ_)), "addGround");
     robot_.reset(new ArticulatedSystem(w_, 0));
+    robot_->setJointOrder(jointOrder);
     return robot_.get();
   }
   Ground* addGround(double zHeight = 0.0, const std::string& material = "default", CollisionGroup = CollisionGroup(-1)) {

@@ -539,7 +539,7 @@ int rsb_batch_set_heightmap(rsb_batch* b, int xs, int ys, float x_size, float y_
   CK(cudaMemcpy(b->hmap, h, (size_t)xs * ys * 4, cudaMemcpyHostToDevice));
   TerrainDesc t{};
   t.type = 2; t.xs = xs; t.ys = ys;
-  t.dx = x_size / (float)(xs - 1); t.dy = y_size / (float)(ys - 1);
+  t.dx = x_size / (float)(xs - 1); t.dy = y_size / (float)(ys - 1); t.inv_dx = 1.0f / t.dx; t.inv_dy = 1.0f / t.dy;
   t.x0 = cx - 0.5f * x_size; t.y0 = cy - 0.5f * y_size;
   t.xmax = (float)(xs - 1); t.ymax = (float)(ys - 1);
   t.h = b->hmap;
@@ -567,7 +567,7 @@ int rsb_batch_set_heightmaps(rsb_batch* b, int count, int xs, int ys, float x_si
   CK(cudaMemcpy(b->hmap_index, map_of_env, (size_t)b->N * 4, cudaMemcpyHostToDevice));
   TerrainDesc t{};
   t.type = 2; t.xs = xs; t.ys = ys;
-  t.dx = x_size / (float)(xs - 1); t.dy = y_size / (float)(ys - 1);
+  t.dx = x_size / (float)(xs - 1); t.dy = y_size / (float)(ys - 1); t.inv_dx = 1.0f / t.dx; t.inv_dy = 1.0f / t.dy;
   t.x0 = cx - 0.5f * x_size; t.y0 = cy - 0.5f * y_size;
   t.xmax = (float)(xs - 1); t.ymax = (float)(ys - 1);
   t.h = b->hmap; t.env_map = b->hmap_index; t.map_words = xs * ys;

@@ -79,7 +79,7 @@ __device__ __forceinline__ void closest_segments(f3 p1, f3 d1, f3 p2, f3 d2, flo
 // the group returns the same result; `valid` = this group holds a sphere at all.
 __device__ __forceinline__ HmBest sphere_vs_heightmap_group(const TerrainDesc& t, int hm_offset, f3 C, float r, bool valid, int lane) {
   HmBest best; best.hit = false; best.depth = 0.f; best.n = mk(0.f, 0.f, 1.f); best.pos = C; best.pair = 0;
-  const float gx = (C.x - t.x0) / t.dx, gy = (C.y - t.y0) / t.dy;
+  const float gx = (C.x - t.x0) * t.inv_dx, gy = (C.y - t.y0) * t.inv_dy;
   const bool in_map = valid && gx >= 0.f && gy >= 0.f && gx < t.xmax && gy < t.ymax;
   const int ccx = (int)gx, ccy = (int)gy;
   const int bx = min(max((int)floorf(gx - 0.5f), 0), max(t.xs - 3, 0)), by = min(max((int)floorf(gy - 0.5f), 0), max(t.ys - 3, 0));

@@ -214,3 +214,30 @@ def test_pybind_module_loads_and_fails_loudly_without_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             _rsb_py.Batch(m, 4, 0)
+
+
+def test_mesh_collision_becomes_its_bounding_box(tmp_path):
+    """N2 mesh -> primitive fallback: a <mesh> collision whose file can be read (binary / ASCII STL, OBJ; package:// or relative path,
+    <mesh scale>) is replaced by its axis-aligned bounding box in the collision frame; an unreadable one is skipped as before"""
+    import struct
+    tris = [((0, 0, 0), (0.4, 0, 0), (0, 0.2, 0)), ((0.4, 0.2, 0.1), (0.4, 0, 0), (0, 0.2, 0)), ((-0.1, 0, 0.05), (0, 0, 0), (0, 0.2, 0.1))]
+    (tmp_path / "meshes").mkdir()
+    with open(tmp_path / "meshes" / "part.stl", "wb") as f:
+        f.write(b"binary stl".ljust(80, b" ")); f.write(struct.pack("<I", len(tris)))
+        for t3 in tris:
+            f.write(struct.pack("<3f", 0, 0, 1))
+            for v in t3:
+                f.write(struct.pack("<3f", *v))
+            f.write(struct.pack("<H", 0))
+    with open(tmp_path / "meshes" / "part.obj", "w") as f:
+        f.write("# obj\n" + "".join(f"v {x} {y} {z}\n" for t3 in tris for (x, y, z) in t3) + "f 1 2 3\n")
+    urdf = tmp_path / "robot.urdf"
+    urdf.write_text(f"""<robot name="m"><link name="b"><inertial><mass value="1"/><inertia ixx="0.01" iyy="0.01" izz="0.01"/></inertial>
+      <collision><origin xyz="0 0 0.5"/><geometry><mesh filename="package://some_pkg/meshes/part.stl" scale="2 1 1"/></geometry></collision>
+      <collision><geometry><mesh filename="meshes/part.obj"/></geometry></collision>
+      <collision><geometry><mesh filename="package://some_pkg/meshes/missing.dae"/></geometry></collision></link></robot>""")
+    t = capi.Model(str(urdf)).tables()
+    assert t["ncoll"] == 2 and list(t["ctype"]) == [1, 1]                                       # two boxes, the unreadable mesh skipped
+    assert np.allclose(t["csize"][0], [0.5, 0.1, 0.05]) and np.allclose(t["cpos"][0], [0.3, 0.1, 0.55])   # x scaled by 2: [-0.2, 0.8] x [0, 0.2] x [0, 0.1]
+    assert np.allclose(t["csize"][1], [0.25, 0.1, 0.05]) and np.allclose(t["cpos"][1], [0.15, 0.1, 0.05])
+    assert t["npts"] == 2 * 8 + 2                                                                # corners + one box-face candidate each
