@@ -948,7 +948,26 @@ template <typename T> class Sim {
         ws.iters = it + 1; ws.resid = err;
         alpha = std::max(T(prm.alpha_min), alpha * T(prm.alpha_decay));
         if (err < T(prm.threshold)) { ws.status = regularised ? 1 : 0; break; }
-        if (AM > 0 && it + 1 >= prm.accel_start - AM && resets < ACCEL_MAX_RESETS) {   // the history starts AM sweeps before the first extrapolation: nothing is kept (or paid for) on quickly converging problems
+        // the stagnation check comes before the extrapolation, and the last sweep is not extrapolated: whatever ends the loop, the impulses
+        // returned are the output of a projected sweep (inside their friction cones, normal parts >= 0)
+        if (it + 1 == next_ckpt) {
+          if (it + 1 >= 2 * prm.stall_window && err > T(prm.stall_ratio) * err_ckpt) {
+            if (regularised || !(prm.stall_reg > 0)) { ws.status = 2; break; }
+            // The per-contact rule is cycling on this contact set (typically a joint stop fighting a sticking contact of the same leg).
+            // Go on with a slightly compliant set: G + eps I, eps = stall_reg * mean(diag G)  (constraint-force mixing, only here).
+            T tr = 0;
+            for (int a = 0; a < C; a++) tr += ws.G[a * C + a];
+            const T eps = T(prm.stall_reg) * tr / T(C);
+            for (int a = 0; a < C; a++) ws.G[a * C + a] += eps;
+            for (int i = 0; i < K; i++) { const V3<T>& l = ws.contacts[i].lam; ws.u[3 * i] += eps * l.x; ws.u[3 * i + 1] += eps * l.y; ws.u[3 * i + 2] += eps * l.z; }
+            for (int l = 0; l < Lm; l++) ws.u[C3 + l] += eps * ws.limits[l].lam;
+            regularised = true; hcount = 0; resets = 0;
+            err_ckpt = T(3.0e38); next_ckpt = it + 1 + prm.stall_window;
+            continue;
+          }
+          err_ckpt = err; next_ckpt += prm.stall_window;
+        }
+        if (AM > 0 && it + 1 >= prm.accel_start - AM && resets < ACCEL_MAX_RESETS && it + 1 < prm.max_iter) {   // the history starts AM sweeps before the first extrapolation: nothing is kept (or paid for) on quickly converging problems
           // push (g, f) of this sweep; slots are a shift register, newest last
           if (hcount == AM + 1) {
             for (int sl = 0; sl < AM; sl++) for (int a = 0; a < C; a++) { hg[(size_t)sl * C + a] = hg[(size_t)(sl + 1) * C + a]; hf[(size_t)sl * C + a] = hf[(size_t)(sl + 1) * C + a]; }
@@ -1009,23 +1028,6 @@ template <typename T> class Sim {
               }
             }
           }
-        }
-        if (it + 1 == next_ckpt) {
-          if (it + 1 >= 2 * prm.stall_window && err > T(prm.stall_ratio) * err_ckpt) {
-            if (regularised || !(prm.stall_reg > 0)) { ws.status = 2; break; }
-            // The per-contact rule is cycling on this contact set (typically a joint stop fighting a sticking contact of the same leg).
-            // Go on with a slightly compliant set: G + eps I, eps = stall_reg * mean(diag G)  (constraint-force mixing, only here).
-            T tr = 0;
-            for (int a = 0; a < C; a++) tr += ws.G[a * C + a];
-            const T eps = T(prm.stall_reg) * tr / T(C);
-            for (int a = 0; a < C; a++) ws.G[a * C + a] += eps;
-            for (int i = 0; i < K; i++) { const V3<T>& l = ws.contacts[i].lam; ws.u[3 * i] += eps * l.x; ws.u[3 * i + 1] += eps * l.y; ws.u[3 * i + 2] += eps * l.z; }
-            for (int l = 0; l < Lm; l++) ws.u[C3 + l] += eps * ws.limits[l].lam;
-            regularised = true; hcount = 0; resets = 0;
-            err_ckpt = T(3.0e38); next_ckpt = it + 1 + prm.stall_window;
-            continue;
-          }
-          err_ckpt = err; next_ckpt += prm.stall_window;
         }
       }
       for (int r = 0; r < nv; r++) {

@@ -286,11 +286,6 @@ __device__ __noinline__ GsResult gs_solve(const rsb_params& prm, float* s_G, int
     res.iters = it + 1; res.resid = err;
     alpha = fmaxf(prm.alpha_min, alpha * prm.alpha_decay);
     if (err < prm.threshold) { res.status = regularised ? RSB_SOLVER_CONVERGED_COMPLIANT : RSB_SOLVER_CONVERGED; break; }
-    if (aa_rec) {
-      __syncwarp();
-      const AAState st = anderson_step(s_hist, s_G, g_stride, lane, CR, lam_c, u_c, aa_hc, aa_fp, it + 1 >= prm.accel_start ? 1 : 0);
-      lam_c = st.lam; u_c = st.u; aa_hc = st.hc; aa_fp = st.fp; aa_resets += st.dropped;
-    }
     if (it + 1 == next_ckpt) {      // stagnation check (see rsb_params.stall_window)
       if (it + 1 >= 2 * prm.stall_window && err > prm.stall_ratio * err_ckpt) {
         if (regularised || !(prm.stall_reg > 0.f)) { res.status = RSB_SOLVER_STALLED; break; }
@@ -300,6 +295,11 @@ __device__ __noinline__ GsResult gs_solve(const rsb_params& prm, float* s_G, int
         continue;
       }
       err_ckpt = err; next_ckpt += prm.stall_window;
+    }
+    if (aa_rec && it + 1 < prm.max_iter) {   // after the stagnation check, never on the last sweep: the loop always ends on a projected sweep's impulses
+      __syncwarp();
+      const AAState st = anderson_step(s_hist, s_G, g_stride, lane, CR, lam_c, u_c, aa_hc, aa_fp, it + 1 >= prm.accel_start ? 1 : 0);
+      lam_c = st.lam; u_c = st.u; aa_hc = st.hc; aa_fp = st.fp; aa_resets += st.dropped;
     }
   }
   res.lam = lam_c;

@@ -75,10 +75,12 @@ __device__ __forceinline__ void closest_segments(f3 p1, f3 d1, f3 p2, f3 d2, flo
 // Sphere (centre C, radius r > 0) against the eight triangles of the 2 x 2 block of cells nearest to its centre (oracle
 // sphere_vs_heightmap).  EIGHT LANES share one sphere, one triangle each (sub = lane & 7: cell (sub >> 1) & 1, sub >> 2 of the block,
 // triangle sub & 1); the group reduces to the closest terrain point with xor shuffles inside its aligned 8-lane segment.  Of several
-// triangles within 1e-6 m of the smallest distance (they share the touched edge or vertex) the lowest pair index wins.  Every lane of
-// the group returns the same result; `valid` = this group holds a sphere at all.
-__device__ __forceinline__ HmBest sphere_vs_heightmap_group(const TerrainDesc& t, int hm_offset, f3 C, float r, bool valid, int lane) {
-  HmBest best; best.hit = false; best.depth = 0.f; best.n = mk(0.f, 0.f, 1.f); best.pos = C; best.pair = 0;
+// triangles within 1e-6 m of the smallest distance (they share the touched edge or vertex) the lowest pair index wins.
+// Every lane returns the contact ITS triangle would give (depth, normal, pair) and the lane of its group whose triangle won
+// (winner, the same in all eight lanes; -1 = no contact): the lane that owns the sphere fetches the winner's answer with shuffles.
+// `valid` = this group holds a sphere at all.
+struct SphereTri { int winner; float depth; f3 n; int pair; };
+__device__ __forceinline__ SphereTri sphere_vs_heightmap_group(const TerrainDesc& t, int hm_offset, f3 C, float r, bool valid, int lane) {
   const float gx = (C.x - t.x0) * t.inv_dx, gy = (C.y - t.y0) * t.inv_dy;
   const bool in_map = valid && gx >= 0.f && gy >= 0.f && gx < t.xmax && gy < t.ymax;
   const int ccx = (int)gx, ccy = (int)gy;
@@ -87,8 +89,11 @@ __device__ __forceinline__ HmBest sphere_vs_heightmap_group(const TerrainDesc& t
   const int ix = bx + ((sub >> 1) & 1), iy = by + (sub >> 2);
   float dist = 3.0e38f; f3 v = mk(0.f, 0.f, 0.f), nt = mk(0.f, 0.f, 1.f); int pair = 0x7fffffff; bool beneath_inside = false;
   if (in_map && ix <= t.xs - 2 && iy <= t.ys - 2) {
-    const float* H = t.h + hm_offset;
-    const f3 a = hm_vertex(t, H, ix, iy), b = tri == 0 ? hm_vertex(t, H, ix + 1, iy) : hm_vertex(t, H, ix + 1, iy + 1), c = tri == 0 ? hm_vertex(t, H, ix + 1, iy + 1) : hm_vertex(t, H, ix, iy + 1);
+    const float* H = t.h + hm_offset + iy * t.xs + ix;
+    const float h00 = __ldg(H), h11 = __ldg(H + t.xs + 1), h3 = __ldg(tri == 0 ? H + 1 : H + t.xs);
+    const float X0 = t.x0 + (float)ix * t.dx, X1 = t.x0 + (float)(ix + 1) * t.dx, Y0 = t.y0 + (float)iy * t.dy, Y1 = t.y0 + (float)(iy + 1) * t.dy;
+    const f3 a = mk(X0, Y0, h00), p11 = mk(X1, Y1, h11), p3 = tri == 0 ? mk(X1, Y0, h3) : mk(X0, Y1, h3);
+    const f3 b = tri == 0 ? p3 : p11, c = tri == 0 ? p11 : p3;      // tri 0 = (P00, P10, P11), tri 1 = (P00, P11, P01)
     nt = hm_tri_normal(a, b, c);
     const float side = dot(C - a, nt);
     if (ix == ccx && iy == ccy) {                               // the triangle directly beneath the centre tells inside from outside
@@ -104,21 +109,19 @@ __device__ __forceinline__ HmBest sphere_vs_heightmap_group(const TerrainDesc& t
     }
   }
   const unsigned seg = 0xffu << (lane & 24);
-  const bool inside = (__ballot_sync(FULL, beneath_inside) & seg) != 0u;
+  const bool inside = (__ballot_sync(0xffffffffu, beneath_inside) & seg) != 0u;
   float dmin = dist;
-  dmin = fminf(dmin, __shfl_xor_sync(FULL, dmin, 1)); dmin = fminf(dmin, __shfl_xor_sync(FULL, dmin, 2)); dmin = fminf(dmin, __shfl_xor_sync(FULL, dmin, 4));
-  int key = (dist < 3.0e38f && dist <= dmin + 1e-6f) ? pair : 0x7fffffff;
+  dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, 1)); dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, 2)); dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, 4));
+  const int key = (dist < 3.0e38f && dist <= dmin + 1e-6f) ? pair : 0x7fffffff;
   int kmin = key;
-  kmin = min(kmin, __shfl_xor_sync(FULL, kmin, 1)); kmin = min(kmin, __shfl_xor_sync(FULL, kmin, 2)); kmin = min(kmin, __shfl_xor_sync(FULL, kmin, 4));
-  const unsigned wm = __ballot_sync(FULL, key == kmin && kmin != 0x7fffffff) & seg;
-  const int wl = wm ? __ffs(wm) - 1 : lane;
-  const float wd = __shfl_sync(FULL, dist, wl);
-  const f3 wv = shfl3(v, wl), wn = shfl3(nt, wl);
-  if (wm) {
-    const f3 n = (!inside && wd > 1e-9f) ? np_rcp(wd) * wv : wn;
-    hm_offer(best, inside ? r + wd : r - wd, n, C - r * n, kmin);
-  }
-  return best;
+  kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, 1)); kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, 2)); kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, 4));
+  SphereTri st;
+  st.depth = inside ? r + dist : r - dist;
+  st.n = (!inside && dist > 1e-9f) ? np_rcp(dist) * v : nt;
+  st.pair = pair;
+  const unsigned wm = __ballot_sync(0xffffffffu, key == kmin && kmin != 0x7fffffff && st.depth > 0.f) & seg;
+  st.winner = wm ? __ffs(wm) - 1 : -1;
+  return st;
 }
 
 // interior of segment A-B swept by radius r against the terrain edges under its AABB (the end spheres are candidates of their own)

@@ -365,7 +365,7 @@ __device__ __forceinline__ QuadLeg quad_factor_legs(float* s_L, float* s_invd, i
 // RSB_KMAX deepest kept.  Out of line (one call per sub-step) so that the candidate registers of both slots get an allocation of
 // their own instead of being spilled around the rest of the 72-register kernel body.  Returns the number of contacts written to s_ct.
 template <int SLOTS>
-__device__ __noinline__ int stage_b_narrow_phase(const StepArgs& args, const uint32_t* blob_s, const float* s_pose, float* s_ct, float* s_hist, int env, int lane, int nbp) {
+__device__ __noinline__ int stage_b_narrow_phase(const StepArgs& args, const uint32_t* blob_s, const float* s_pose, float* s_ct, float* s_hist, int env, int lane, int nbp, int sub) {
   const BlobHeader& H = *reinterpret_cast<const BlobHeader*>(blob_s);
   const float* ptsf = reinterpret_cast<const float*>(blob_s + H.off_pts);
   const int* ptsi = reinterpret_cast<const int*>(blob_s + H.off_pts);
@@ -373,23 +373,37 @@ __device__ __noinline__ int stage_b_narrow_phase(const StepArgs& args, const uin
   float c_depth[SLOTS]; f3 c_pos[SLOTS], c_n[SLOTS]; int c_pair[SLOTS], c_body[SLOTS];
   bool c_hit[SLOTS], c_sph[SLOTS];      // c_sph: a sphere candidate on a HeightMap, evaluated below by a group of eight lanes
   const int hm_offset = args.ter.env_map ? __ldg(args.ter.env_map + env) * args.ter.map_words : 0;   // terrain atlas
+  const bool on_hm = args.ter.type == 2;
+  // nothing whose lowest point is above the highest point of the terrain (the plane itself for a Ground) can touch it
+  const float zcull = on_hm ? args.ter.hmax : args.ter.ground_z;
 #pragma unroll
   for (int s = 0; s < SLOTS; s++) {
-    int k = lane + 32 * s;
+    const int k = lane + 32 * s;
     c_hit[s] = false; c_sph[s] = false; c_depth[s] = 0.f; c_pair[s] = 0; c_body[s] = 0; c_pos[s] = mk(0, 0, 0); c_n[s] = mk(0, 0, 1);
-    if (k < H.npts) {
-      const int pb = ptsi[0 * H.nptp + k];
-      const f3 pl = mk(ptsf[1 * H.nptp + k], ptsf[2 * H.nptp + k], ptsf[3 * H.nptp + k]);
-      const float rad = ptsf[4 * H.nptp + k];
-      const int ptype = ptsi[6 * H.nptp + k];
+    // ---- cull on the height alone: third row of the body rotation, one dot product per feature.  An upright robot keeps its feet.
+    bool alive = false;
+    int pb = 0, ptype = 0; float rad = 0.f; f3 pl = mk(0, 0, 0);
+    if (k < H.npts && args.ter.type != 0) {
+      pb = ptsi[0 * H.nptp + k]; ptype = ptsi[6 * H.nptp + k]; rad = ptsf[4 * H.nptp + k];
+      pl = mk(ptsf[1 * H.nptp + k], ptsf[2 * H.nptp + k], ptsf[3 * H.nptp + k]);
+      const float r6 = s_pose[(PF_R + 6) * nbp + pb], r7 = s_pose[(PF_R + 7) * nbp + pb], r8 = s_pose[(PF_R + 8) * nbp + pb], pz = s_pose[(PF_P + 2) * nbp + pb];
+      float zlow = pz + r6 * pl.x + r7 * pl.y + r8 * pl.z, ext = rad;
+      if (ptype == 1) zlow = fminf(zlow, pz + r6 * ptsf[7 * H.nptp + k] + r7 * ptsf[8 * H.nptp + k] + r8 * ptsf[9 * H.nptp + k]);
+      if (ptype == 2) {
+        const float* cb = reinterpret_cast<const float*>(blob_s + H.off_coll) + COLL_WORDS * ptsi[10 * H.nptp + k];
+        zlow = pz + r6 * cb[3] + r7 * cb[4] + r8 * cb[5]; ext = cb[0] + cb[1] + cb[2];     // box centre, a bound on its vertical half extent
+      }
+      alive = bdof[pb] >= 0 && zlow - ext <= zcull;       // (a body welded to the world cannot collide)
+    }
+    if (!__any_sync(FULL, alive)) continue;
+    if (alive) {
       float Rb[9];
 #pragma unroll
       for (int q = 0; q < 9; q++) Rb[q] = s_pose[(PF_R + q) * nbp + pb];
       const f3 pb_pos = mk(s_pose[(PF_P + 0) * nbp + pb], s_pose[(PF_P + 1) * nbp + pb], s_pose[(PF_P + 2) * nbp + pb]);
       f3 P = pb_pos + mulR(Rb, pl);
       float prad = rad;
-      const bool on_hm = args.ter.type == 2;
-      bool as_point = ptype == 0 && !(on_hm && rad > 0.f), live = bdof[pb] >= 0;   // a body welded to the world cannot collide
+      bool as_point = ptype == 0 && !(on_hm && rad > 0.f), live = true;
       if (ptype == 3) {
         // cylinder cap: the lowest point of its rim circle (centre P, radius rad, axis a), the point of the circle furthest along -z
         f3 a = P - (pb_pos + mulR(Rb, mk(ptsf[7 * H.nptp + k], ptsf[8 * H.nptp + k], ptsf[9 * H.nptp + k])));
@@ -399,7 +413,7 @@ __device__ __noinline__ int stage_b_narrow_phase(const StepArgs& args, const uin
         if (dn > 1e-6f) { P = P + (rad / dn) * dd; prad = 0.f; as_point = true; }
         else live = false;                                  // cap parallel to the ground: the fixed rim samples carry it
       }
-      if (on_hm && as_point && P.z - prad > args.ter.hmax) live = false;   // above the highest point of the terrain: cannot touch
+      if (on_hm && as_point && P.z - prad > args.ter.hmax) live = false;
       if (!live) {
       } else if (as_point) {
         // Ground plane, or a zero-radius point on a HeightMap (box corner, cylinder rim point): the triangle directly beneath
@@ -409,14 +423,13 @@ __device__ __noinline__ int stage_b_narrow_phase(const StepArgs& args, const uin
           if (depth > 0.f) { c_hit[s] = true; c_depth[s] = depth; c_pair[s] = pair; c_body[s] = pb; c_n[s] = n; c_pos[s] = P - prad * n; }
         }
       } else if (on_hm) {
-        // HeightMap: the shape against every triangle under its bounding box (narrow_phase.cuh); first a conservative cull against
-        // the highest point of the terrain, which removes every candidate of an upright robot except its feet
+        // HeightMap: the shape against every triangle under its bounding box (narrow_phase.cuh)
         HmBest hb; hb.hit = false;
         if (ptype == 0) {
-          if (P.z - rad <= args.ter.hmax) { c_sph[s] = true; c_pos[s] = P; c_depth[s] = rad; c_body[s] = pb; }   // parked: eight lanes take it below
+          c_sph[s] = true; c_pos[s] = P; c_depth[s] = rad; c_body[s] = pb;     // parked: eight lanes take it below
         } else if (ptype == 1) {
           const f3 P2 = pb_pos + mulR(Rb, mk(ptsf[7 * H.nptp + k], ptsf[8 * H.nptp + k], ptsf[9 * H.nptp + k]));
-          if (fminf(P.z, P2.z) - rad <= args.ter.hmax) hb = segment_vs_heightmap(args.ter, hm_offset, P, P2, rad);
+          hb = segment_vs_heightmap(args.ter, hm_offset, P, P2, rad);
         } else {
           const float* cb = reinterpret_cast<const float*>(blob_s + H.off_coll) + COLL_WORDS * ptsi[10 * H.nptp + k];
           const f3 hsz = mk(cb[0], cb[1], cb[2]);
@@ -430,42 +443,44 @@ __device__ __noinline__ int stage_b_narrow_phase(const StepArgs& args, const uin
       }
     }
   }
+  if (args.prof && lane == 0) args.prof[((size_t)env * 4 + (sub & 3)) * 8 + 6] = (unsigned)clock64();
   {   // sphere candidates on a HeightMap: four at a time, eight lanes (= the eight triangles of the 2 x 2 cell block under it) each
     unsigned sm[SLOTS]; int nsph = 0;
 #pragma unroll
     for (int s = 0; s < SLOTS; s++) { sm[s] = __ballot_sync(FULL, c_sph[s]); nsph += __popc(sm[s]); }
-    float* scr = s_hist;          // 4 x 12 words of scratch: the Anderson history is not in use during stage B
+    if (args.prof && lane == 0) args.prof[((size_t)env * 4 + (sub & 3)) * 8 + 7] = (unsigned)nsph;
 #pragma unroll 1
     for (int base = 0; base < nsph; base += 4) {
       const int rk = base + (lane >> 3);
       int rr = rk, oslot = 0;
       if (SLOTS > 1 && rr >= __popc(sm[0])) { oslot = 1; rr -= __popc(sm[0]); }
       const bool gvalid = rk < nsph;
-      const int olane = gvalid ? __fns(sm[SLOTS > 1 ? oslot : 0], 0, rr + 1) : 0;
+      const int olane = gvalid ? __fns(SLOTS > 1 && oslot == 1 ? sm[SLOTS - 1] : sm[0], 0, rr + 1) : 0;
       f3 C = shfl3(c_pos[0], olane); float rad = __shfl_sync(FULL, c_depth[0], olane);
-      if (SLOTS > 1) {
+      if (SLOTS > 1 && sm[SLOTS - 1] != 0u) {
         const f3 C1 = shfl3(c_pos[SLOTS - 1], olane); const float r1 = __shfl_sync(FULL, c_depth[SLOTS - 1], olane);
         if (oslot == 1) { C = C1; rad = r1; }
       }
-      const HmBest hb = sphere_vs_heightmap_group(args.ter, hm_offset, C, rad, gvalid, lane);
-      __syncwarp();
-      if ((lane & 7) == 0 && gvalid) {
-        float* o = scr + 12 * (lane >> 3);
-        o[0] = hb.hit ? 1.f : 0.f; o[1] = hb.depth; o[2] = hb.n.x; o[3] = hb.n.y; o[4] = hb.n.z; o[5] = hb.pos.x; o[6] = hb.pos.y; o[7] = hb.pos.z; o[8] = __int_as_float(hb.pair);
-      }
-      __syncwarp();
+      // every lane: its triangle's answer, and the lane of its group that holds the winning triangle (-1: no contact)
+      const SphereTri st = sphere_vs_heightmap_group(args.ter, hm_offset, C, rad, gvalid, lane);
+      // the owner of each sphere fetches the winner's answer: contact position = centre - r n
 #pragma unroll
       for (int s = 0; s < SLOTS; s++) {
+        if (s > 0 && sm[s] == 0u) continue;
         const int myrank = __popc(sm[s] & ((1u << lane) - 1u)) + (s > 0 ? __popc(sm[0]) : 0);
-        if (c_sph[s] && myrank >= base && myrank < base + 4) {
-          const float* o = scr + 12 * (myrank - base);
-          c_depth[s] = 0.f;
-          if (o[0] != 0.f) { c_hit[s] = true; c_depth[s] = o[1]; c_n[s] = mk(o[2], o[3], o[4]); c_pos[s] = mk(o[5], o[6], o[7]); c_pair[s] = __float_as_int(o[8]); }
+        const bool mine = c_sph[s] && myrank >= base && myrank < base + 4;
+        const int wl = __shfl_sync(FULL, st.winner, mine ? 8 * (myrank - base) : lane);
+        const int src = (mine && wl >= 0) ? wl : lane;
+        const float wd = __shfl_sync(FULL, st.depth, src);
+        const f3 wn = shfl3(st.n, src);
+        const int wp = __shfl_sync(FULL, st.pair, src);
+        if (mine) {
+          const f3 Cs = c_pos[s]; const float rs = c_depth[s];
+          c_depth[s] = 0.f; c_pos[s] = mk(0, 0, 0);
+          if (wl >= 0) { c_hit[s] = true; c_depth[s] = wd; c_n[s] = wn; c_pos[s] = Cs - rs * wn; c_pair[s] = wp; }
         }
       }
     }
-#pragma unroll
-    for (int s = 0; s < SLOTS; s++) if (c_sph[s] && !c_hit[s]) { c_depth[s] = 0.f; c_pos[s] = mk(0, 0, 0); }
   }
   unsigned hm[SLOTS];
   int total = 0;
@@ -499,7 +514,7 @@ __device__ __noinline__ int stage_b_narrow_phase(const StepArgs& args, const uin
         f3 n = c_n[s];
         f3 e = (fabsf(n.x) < 0.9f) ? mk(1.f, 0.f, 0.f) : mk(0.f, 1.f, 0.f);
         f3 t = e - dot(e, n) * n;
-        float inv = 1.0f / sqrtf(dot(t, t));
+        float inv = rsqrt_nr(dot(t, t));
         f3 t1 = inv * t, t2 = cross(n, t1);
         ct[CF_POS] = c_pos[s].x; ct[CF_POS + 1] = c_pos[s].y; ct[CF_POS + 2] = c_pos[s].z;
         ct[CF_N] = n.x; ct[CF_N + 1] = n.y; ct[CF_N + 2] = n.z;
@@ -822,7 +837,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       if (args.phase_mask & 4) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncwarp(); break; }   // kinematics for the getters only
 
       // =========================== stage B: narrow phase ========================================
-      K = stage_b_narrow_phase<SLOTS>(args, blob_s, s_pose, s_ct, s_hist, env, lane, nbp);
+      K = stage_b_narrow_phase<SLOTS>(args, blob_s, s_pose, s_ct, s_hist, env, lane, nbp, sub);
       const int C = 3 * K;
       if (args.prof && lane == 0) args.prof[((size_t)env * 4 + (sub & 3)) * 8 + 2] = (unsigned)clock64();
       if (args.phase_mask & 1) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncwarp(); break; }   // integrate1(): kinematics, collision, M, h only

@@ -1138,8 +1138,12 @@ def test_heightmap_narrow_phase_matches_oracle_on_rough_terrain(capi):
         assert pair_same > 0.995                                                                   # same reason: which of two triangles sharing an edge
         ok = live & (ct["pair_index"] == d["c_pair"])
         rad = np.where(d["c_pt"] >= 0, t["pt_rad"][np.maximum(d["c_pt"], 0)], 0.0)
-        tol_n = 2e-6 + 4e-7 / np.maximum(rad - d["c_depth"], 1e-4)         # normal = (centre - closest point) / distance
-        assert np.abs(ct["depth"] - d["c_depth"])[ok].max() < 5e-6 and (np.abs(ct["normal"] - d["c_normal"]).max(2)[ok] < tol_n[ok]).all()
+        # normal = (centre - closest point) / distance: both points carry float32 rounding of coordinates up to 12.8 m (ulp 9.5e-7), the
+        # closest point a few operations' worth, so the normal is conditioned like 3e-6 / distance
+        tol_n = 2e-6 + 3e-6 / np.maximum(rad - d["c_depth"], 1e-4)
+        en = np.abs(ct["normal"] - d["c_normal"]).max(2)
+        print(f"   worst normal error / tolerance {np.max(en[ok] / tol_n[ok]):.2f}, worst depth error {np.abs(ct['depth'] - d['c_depth'])[ok].max():.2e}")
+        assert np.abs(ct["depth"] - d["c_depth"])[ok].max() < 5e-6 and (en[ok] < tol_n[ok]).all()
 
 
 def test_cpp_generic_vectorized_environment_example(capi):
@@ -1178,7 +1182,10 @@ def test_pybind_dlpack_zero_copy_views(capi):
     torch.cuda.synchronize()
     pb.control_step(target.data_ptr(), 4, obs.data_ptr())
     pb.sync()
-    # the ctypes path from the same state
+    # the ctypes path from the same state: a fresh batch at the library defaults, like the pybind one
+    bt = capi.Batch(capi.Model(os.path.join(RSC, "anymal_c_like.urdf")), n)
+    bt.set_ground(0.0)
+    bt.set_state(gc.astype(np.float32), gv.astype(np.float32))
     bt.set_control_mode(capi.PD_PLUS_FEEDFORWARD_TORQUE)
     bt.set_pd_gains(np.array(kp), np.array(kd))
     bt.set_pd_target(target.cpu().numpy(), np.zeros((n, 18), np.float32))
