@@ -59,7 +59,7 @@ def main():
     for name, a in (("A", tA), ("B", tB), ("C", tC), ("D", tD), ("E", tE), ("total", tot)):
         print("     %-5s p10 %.0f  p50 %.0f  p90 %.0f  p99 %.0f  max %.0f" % (name, np.quantile(a, .1), np.median(a), np.quantile(a, .9), np.quantile(a, .99), a.max()))
     if (P[:, :, 6] != 0).any():      # inner stamps of stage B: candidate loop | sphere groups + compaction
-        print("  stage B split: candidate loop %.0f  sphere groups + compaction %.0f  | sphere candidates that reach the groups: mean %.2f max %d" % (d(1, 6).mean(), d(6, 2).mean(), P[:, :, 7].mean(), P[:, :, 7].max()))
+        print("  stage B split: candidates + sphere groups %.0f  selection + contact records %.0f  | penetrating candidates: mean %.2f max %d" % (d(1, 6).mean(), d(6, 2).mean(), P[:, :, 7].mean(), P[:, :, 7].max()))
     it = sim.bt.solver_iterations(); _, cnt = sim.bt.contacts()
     upd = np.maximum(1, it * cnt)
     print("  D cycles per contact update (last sub-step): median %.0f" % np.median(tD[:, 3] / upd))
