@@ -147,6 +147,19 @@ static void build_blob(rsb_batch* b) {
     I(H.off_pts + 6 * H.nptp + k, md.pt_type[k]);
     for (int q = 0; q < 3; q++) F(H.off_pts + (7 + q) * H.nptp + k, (float)md.pt_pos2[3 * k + q]);
     I(H.off_pts + 10 * H.nptp + k, md.pt_coll[k]);
+    // bounding sphere of the candidate for the height cull of stage B: the sphere itself / the rim circle, the whole capsule, the whole box
+    double cc[3] = {md.pt_pos[3 * k], md.pt_pos[3 * k + 1], md.pt_pos[3 * k + 2]}, cr = md.pt_rad[k];
+    if (md.pt_type[k] == FT_SEGMENT) {
+      double hl = 0;
+      for (int q = 0; q < 3; q++) { cc[q] = 0.5 * (md.pt_pos[3 * k + q] + md.pt_pos2[3 * k + q]); const double d = md.pt_pos2[3 * k + q] - md.pt_pos[3 * k + q]; hl += d * d; }
+      cr = md.pt_rad[k] + 0.5 * std::sqrt(hl);
+    } else if (md.pt_type[k] == FT_BOXFACE) {
+      const double* sz = &md.csize[3 * md.pt_coll[k]];
+      cr = std::sqrt(sz[0] * sz[0] + sz[1] * sz[1] + sz[2] * sz[2]);
+    }
+    if (bdof[md.pt_body[k]] < 0) cr = -3.0e38;         // welded to the world: cannot collide
+    for (int q = 0; q < 3; q++) F(H.off_pts + (11 + q) * H.nptp + k, (float)cc[q]);
+    F(H.off_pts + 14 * H.nptp + k, (float)(cr * 1.0001 + 1e-6));   // float32 rounding of the product must never cull a touching candidate
   }
   for (int c = 0; c < md.ncoll(); c++) {   // collision-body table (box features): half extents, body-frame position and rotation
     for (int q = 0; q < 3; q++) { F(H.off_coll + COLL_WORDS * c + q, (float)md.csize[3 * c + q]); F(H.off_coll + COLL_WORDS * c + 3 + q, (float)md.cpos[3 * c + q]); }

@@ -73,7 +73,7 @@ struct BlobHeader {
 };
 static_assert(sizeof(BlobHeader) == 136, "header is 34 words");
 constexpr int HEADER_WORDS = 36;      // padded to a 16-byte multiple
-constexpr int PT_ROWS = 11;           // candidate table rows: body, pos(3), radius, friction override, type, pos2(3), collision body
+constexpr int PT_ROWS = 15;           // candidate table rows: body, pos(3), radius, friction override, type, pos2(3), collision body, cull point(3), cull radius
 constexpr int COLL_WORDS = 16;
 
 // Every offset except off_ent / words depends on Dims only: the two variable-size tables
@@ -102,7 +102,7 @@ __host__ __device__ constexpr BlobHeader make_blob_header(Dims d, int npts, int 
   H.off_lvldofs = off; off += H.nvp;
   H.off_entstart = off; off += DL + 1;
   H.off_lcad = off; off += (d.nb * H.nbp + 3) / 4;
-  H.off_pts = off; off += PT_ROWS * H.nptp;           // body, pos(3), radius, friction override (< 0: default material), type, pos2(3), collision body
+  H.off_pts = off; off += PT_ROWS * H.nptp;           // body, pos(3), radius, friction override (< 0: default material), type, pos2(3), collision body, cull point(3) + radius
   H.ncoll = ncoll; H.off_coll = off; off += COLL_WORDS * ncoll;
   H.off_ent = off; off += max_c(1, nent);
   H.words = round_up_c(off, 4);
@@ -377,7 +377,6 @@ __device__ __noinline__ int stage_b_narrow_phase(const TerrainDesc& ter, const u
   const BlobHeader& H = *reinterpret_cast<const BlobHeader*>(blob_s);
   const float* ptsf = reinterpret_cast<const float*>(blob_s + H.off_pts);
   const int* ptsi = reinterpret_cast<const int*>(blob_s + H.off_pts);
-  const int* bdof = reinterpret_cast<const int*>(blob_s + H.off_bdof);
   const int hm_offset = ter.env_map ? __ldg(ter.env_map + env) * ter.map_words : 0;   // terrain atlas
   const bool on_hm = ter.type == 2;
   // nothing whose lowest point is above the highest point of the terrain (the plane itself for a Ground) can touch it
@@ -387,24 +386,22 @@ __device__ __noinline__ int stage_b_narrow_phase(const TerrainDesc& ter, const u
 #pragma unroll 1
   for (int s = 0; s < SLOTS; s++) {
     const int k = lane + 32 * s;
-    // ---- cull on the height alone: third row of the body rotation, one dot product per feature.  An upright robot keeps its feet.
+    // ---- cull on the height alone: every candidate carries a bounding sphere (rows 11-14: centre in the body frame, radius; a body
+    // welded to the world has radius -3e38 and never passes); third row of the body rotation, one dot product.  An upright robot
+    // keeps its feet.
     bool alive = false;
-    int pb = 0, ptype = 0; float rad = 0.f; f3 pl = mk(0, 0, 0);
+    int pb = 0;
     if (k < H.npts && ter.type != 0) {
-      pb = ptsi[0 * H.nptp + k]; ptype = ptsi[6 * H.nptp + k]; rad = ptsf[4 * H.nptp + k];
-      pl = mk(ptsf[1 * H.nptp + k], ptsf[2 * H.nptp + k], ptsf[3 * H.nptp + k]);
-      const float r6 = s_pose[(PF_R + 6) * nbp + pb], r7 = s_pose[(PF_R + 7) * nbp + pb], r8 = s_pose[(PF_R + 8) * nbp + pb], pz = s_pose[(PF_P + 2) * nbp + pb];
-      float zlow = pz + r6 * pl.x + r7 * pl.y + r8 * pl.z, ext = rad;
-      if (ptype == 1) zlow = fminf(zlow, pz + r6 * ptsf[7 * H.nptp + k] + r7 * ptsf[8 * H.nptp + k] + r8 * ptsf[9 * H.nptp + k]);
-      if (ptype == 2) {
-        const float* cb = reinterpret_cast<const float*>(blob_s + H.off_coll) + COLL_WORDS * ptsi[10 * H.nptp + k];
-        zlow = pz + r6 * cb[3] + r7 * cb[4] + r8 * cb[5]; ext = cb[0] + cb[1] + cb[2];     // box centre, a bound on its vertical half extent
-      }
-      alive = bdof[pb] >= 0 && zlow - ext <= zcull;       // (a body welded to the world cannot collide)
+      pb = ptsi[0 * H.nptp + k];
+      const float zc = s_pose[(PF_P + 2) * nbp + pb] + s_pose[(PF_R + 6) * nbp + pb] * ptsf[11 * H.nptp + k] + s_pose[(PF_R + 7) * nbp + pb] * ptsf[12 * H.nptp + k] +
+                       s_pose[(PF_R + 8) * nbp + pb] * ptsf[13 * H.nptp + k];
+      alive = zc - ptsf[14 * H.nptp + k] <= zcull;
     }
     if (!__any_sync(FULL, alive)) continue;
     bool hit = false, sph = false; float depth = 0.f; f3 n = mk(0, 0, 1), pos = mk(0, 0, 0); int pair = 0;
     if (alive) {
+      const int ptype = ptsi[6 * H.nptp + k]; const float rad = ptsf[4 * H.nptp + k];
+      const f3 pl = mk(ptsf[1 * H.nptp + k], ptsf[2 * H.nptp + k], ptsf[3 * H.nptp + k]);
       float Rb[9];
 #pragma unroll
       for (int q = 0; q < 9; q++) Rb[q] = s_pose[(PF_R + q) * nbp + pb];
@@ -438,7 +435,7 @@ __device__ __noinline__ int stage_b_narrow_phase(const TerrainDesc& ter, const u
           HmBest hb; hb.hit = false;
           if (ptype == 1) {
             const f3 P2 = pb_pos + mulR(Rb, mk(ptsf[7 * H.nptp + k], ptsf[8 * H.nptp + k], ptsf[9 * H.nptp + k]));
-            hb = segment_vs_heightmap(ter, hm_offset, P, P2, rad);
+            if (fminf(P.z, P2.z) - rad <= ter.hmax) hb = segment_vs_heightmap(ter, hm_offset, P, P2, rad);
           } else {
             const float* cb = reinterpret_cast<const float*>(blob_s + H.off_coll) + COLL_WORDS * ptsi[10 * H.nptp + k];
             const f3 hsz = mk(cb[0], cb[1], cb[2]);

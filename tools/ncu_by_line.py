@@ -23,7 +23,8 @@ for ln in sass.splitlines():
     if m:
         inner = int(m.group(2))
         outer = int(m.group(4)) if m.group(4) else inner
-        cur = (inner, outer)
+        ofile = os.path.basename(m.group(3) if m.group(3) else m.group(1))
+        cur = (inner, (ofile, outer))
         continue
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/", ln)
     if m and in_k and cur:
@@ -46,19 +47,24 @@ for r in rows[hdr_i + 1:]:
         base = a
     ex = int(float(r[ci["Instructions Executed"]] or 0)); sm = int(float(r[ci["# Samples"]] or 0))
     thr = int(float(r[ci["Thread Instructions Executed"]] or 0))
-    inner, outer = addr2line.get(a - base, (0, 0))
+    inner, outer = addr2line.get(a - base, (0, ("?", 0)))
     by_outer[outer] += ex; by_inner[inner] += ex; samp_outer[outer] += sm
     total += ex; tot_s += sm; tot_thr += thr
-src = open(os.path.join(os.path.dirname(os.path.abspath(so)), "csrc", "step_kernel.cuh")).read().splitlines()
+csrc = os.path.join(os.path.dirname(os.path.abspath(so)), "csrc")
+files = {f: open(os.path.join(csrc, f)).read().splitlines() for f in os.listdir(csrc) if f.endswith((".cuh", ".cu", ".hpp"))}
+src = files["step_kernel.cuh"]
 print(f"total warp-instructions {total}  samples {tot_s}  avg active threads {tot_thr / max(total, 1):.1f}")
 # stage boundaries from the marker comments in the kernel
 marks = [(i + 1, l.strip()) for i, l in enumerate(src) if "=====" in l and "stage" in l]
 marks = [(1, "prologue / loads")] + marks + [(len(src) + 1, "end")]
 print("\n-- by stage (outer line) --")
 for (a, name), (b, _) in zip(marks, marks[1:]):
-    ex = sum(v for k, v in by_outer.items() if a <= k < b); sm = sum(v for k, v in samp_outer.items() if a <= k < b)
+    ex = sum(v for k, v in by_outer.items() if k[0] == "step_kernel.cuh" and a <= k[1] < b); sm = sum(v for k, v in samp_outer.items() if k[0] == "step_kernel.cuh" and a <= k[1] < b)
     print(f"  lines {a:4d}-{b - 1:4d}  instr {ex:11d} ({100.0 * ex / total:5.1f}%)  samples {100.0 * sm / max(tot_s, 1):5.1f}%  {name[:70]}")
 print(f"\n-- top {topn} kernel-body lines by executed warp-instructions --")
-for line, ex in by_outer.most_common(topn):
-    text = src[line - 1].strip() if 0 < line <= len(src) else "?"
-    print(f"  {line:4d} {ex:11d} {100.0 * ex / total:5.1f}%  samp {100.0 * samp_outer[line] / max(tot_s, 1):5.1f}%  {text[:110]}")
+for f in sorted(set(k[0] for k in by_outer) - {"step_kernel.cuh"}):
+    ex = sum(v for k, v in by_outer.items() if k[0] == f); sm = sum(v for k, v in samp_outer.items() if k[0] == f)
+    print(f"  {f:28s} instr {ex:11d} ({100.0 * ex / total:5.1f}%)  samples {100.0 * sm / max(tot_s, 1):5.1f}%  (out-of-line functions of this file)")
+for (f, line), ex in by_outer.most_common(topn):
+    text = files[f][line - 1].strip() if f in files and 0 < line <= len(files[f]) else "?"
+    print(f"  {f[:14]:14s}{line:5d} {ex:11d} {100.0 * ex / total:5.1f}%  samp {100.0 * samp_outer[(f, line)] / max(tot_s, 1):5.1f}%  {text[:100]}")
