@@ -371,8 +371,12 @@ __device__ __forceinline__ QuadLeg quad_factor_legs(float* s_L, float* s_invd, i
 constexpr int HL_WORDS = 9;            // depth (<= 0: dropped), normal, position, pair, candidate index; odd stride: conflict-free by lane
 constexpr int HL_CAP = 64;             // two candidate slots per lane at most
 
+#ifndef RSB_STAGE_B_INLINE
+#define RSB_STAGE_B_INLINE __forceinline__
+#endif
+// ter: the kernel parameter itself (constant bank); ter_s: its shared-memory copy, for the out-of-line shape routines
 template <int SLOTS>
-__device__ __noinline__ int stage_b_narrow_phase(const TerrainDesc& ter, const uint32_t* blob_s, const float* s_pose, float* s_ct, float* s_list,
+__device__ RSB_STAGE_B_INLINE int stage_b_narrow_phase(const TerrainDesc& ter, const TerrainDesc& ter_s, const uint32_t* blob_s, const float* s_pose, float* s_ct, float* s_list,
                                                  int env, int lane, int nbp, unsigned* prof) {
   const BlobHeader& H = *reinterpret_cast<const BlobHeader*>(blob_s);
   const float* ptsf = reinterpret_cast<const float*>(blob_s + H.off_pts);
@@ -435,7 +439,7 @@ __device__ __noinline__ int stage_b_narrow_phase(const TerrainDesc& ter, const u
           HmBest hb; hb.hit = false;
           if (ptype == 1) {
             const f3 P2 = pb_pos + mulR(Rb, mk(ptsf[7 * H.nptp + k], ptsf[8 * H.nptp + k], ptsf[9 * H.nptp + k]));
-            if (fminf(P.z, P2.z) - rad <= ter.hmax) hb = segment_vs_heightmap(ter, hm_offset, P, P2, rad);
+            if (fminf(P.z, P2.z) - rad <= ter.hmax) hb = segment_vs_heightmap(ter_s, hm_offset, P, P2, rad);
           } else {
             const float* cb = reinterpret_cast<const float*>(blob_s + H.off_coll) + COLL_WORDS * ptsi[10 * H.nptp + k];
             const f3 hsz = mk(cb[0], cb[1], cb[2]);
@@ -443,78 +447,82 @@ __device__ __noinline__ int stage_b_narrow_phase(const TerrainDesc& ter, const u
             matmul3(Rb, cb + 6, Rw);
             const f3 cw = pb_pos + mulR(Rb, mk(cb[3], cb[4], cb[5]));
             const float ez = fabsf(Rw[6]) * hsz.x + fabsf(Rw[7]) * hsz.y + fabsf(Rw[8]) * hsz.z;
-            if (cw.z - ez <= ter.hmax) hb = box_vs_heightmap(ter, hm_offset, cw, Rw, hsz);
+            if (cw.z - ez <= ter.hmax) hb = box_vs_heightmap(ter_s, hm_offset, cw, Rw, hsz);
           }
           if (hb.hit) { hit = true; depth = hb.depth; pair = hb.pair; n = hb.n; pos = hb.pos; }
         }
       }
     }
-    // ---- sphere candidates on a HeightMap: four at a time, eight lanes (= the eight triangles of the 2 x 2 cell block under it) each
+    // ---- this slot's direct hits go to the list at once (nothing of them stays in registers across the sphere groups)
+    {
+      const unsigned hmask = __ballot_sync(FULL, hit);
+      if (hit) {
+        float* e = s_list + HL_WORDS * (cnt + __popc(hmask & lt));
+        e[0] = depth; e[1] = n.x; e[2] = n.y; e[3] = n.z; e[4] = pos.x; e[5] = pos.y; e[6] = pos.z; e[7] = __int_as_float(pair); e[8] = __int_as_float(k);
+      }
+      cnt += __popc(hmask);
+    }
+    // ---- sphere candidates on a HeightMap: four at a time, eight lanes (= the eight triangles of the 2 x 2 cell block under it) each;
+    // the lane whose triangle wins appends the contact itself (position = centre - r n)
     const unsigned sm = __ballot_sync(FULL, sph);
     if (sm != 0u) {
-      const int nsph = __popc(sm), myrank = __popc(sm & lt);
+      const int nsph = __popc(sm);
 #pragma unroll 1
       for (int base = 0; base < nsph; base += 4) {
         const int rk = base + (lane >> 3);
         const bool gvalid = rk < nsph;
         const int olane = gvalid ? __fns(sm, 0, rk + 1) : 0;
         const f3 C = shfl3(pos, olane); const float r = __shfl_sync(FULL, depth, olane);
-        // every lane: its triangle's answer, and the lane of its group that holds the winning triangle (-1: no contact)
         const SphereTri st = sphere_vs_heightmap_group(ter, hm_offset, C, r, gvalid, lane);
-        // the owner of each sphere fetches the winner's answer: contact position = centre - r n
-        const bool mine = sph && myrank >= base && myrank < base + 4;
-        const int wl = __shfl_sync(FULL, st.winner, mine ? 8 * (myrank - base) : lane);
-        const int src = (mine && wl >= 0) ? wl : lane;
-        const float wd = __shfl_sync(FULL, st.depth, src);
-        const f3 wn = shfl3(st.n, src);
-        const int wp = __shfl_sync(FULL, st.pair, src);
-        if (mine && wl >= 0) { hit = true; pos = pos - depth * wn; depth = wd; n = wn; pair = wp; }
+        const bool win = gvalid && st.winner == lane;
+        const unsigned wmask = __ballot_sync(FULL, win);
+        if (win) {
+          float* e = s_list + HL_WORDS * (cnt + __popc(wmask & lt));
+          e[0] = st.depth; e[1] = st.n.x; e[2] = st.n.y; e[3] = st.n.z; e[4] = C.x - r * st.n.x; e[5] = C.y - r * st.n.y; e[6] = C.z - r * st.n.z;
+          e[7] = __int_as_float(st.pair); e[8] = __int_as_float(olane + 32 * s);
+        }
+        cnt += __popc(wmask);
       }
     }
-    // ---- append this slot's hits to the list, in candidate order
-    const unsigned hmask = __ballot_sync(FULL, hit);
-    if (hit) {
-      float* e = s_list + HL_WORDS * (cnt + __popc(hmask & lt));
-      e[0] = depth; e[1] = n.x; e[2] = n.y; e[3] = n.z; e[4] = pos.x; e[5] = pos.y; e[6] = pos.z; e[7] = __int_as_float(pair); e[8] = __int_as_float(k);
-    }
-    cnt += __popc(hmask);
   }
   __syncwarp();
   if (prof && lane == 0) { prof[6] = (unsigned)clock64(); prof[7] = (unsigned)cnt; }
   int total = cnt;
 #pragma unroll 1
   while (total > KMAX) {   // drop the shallowest (ties: highest candidate index) until KMAX remain
-    float dmin = 3.0e38f; int imin = -1;
+    float dmin = 3.0e38f; int cmin = -1, imin = 0;     // depth, candidate index, list row of the entry to drop
 #pragma unroll 1
     for (int e = lane; e < cnt; e += 32) {
-      const float d = s_list[HL_WORDS * e];
-      if (d > 0.f && (d < dmin || (d == dmin && e > imin))) { dmin = d; imin = e; }
+      const float d = s_list[HL_WORDS * e]; const int c = __float_as_int(s_list[HL_WORDS * e + 8]);
+      if (d > 0.f && (d < dmin || (d == dmin && c > cmin))) { dmin = d; cmin = c; imin = e; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      const float d2 = __shfl_xor_sync(FULL, dmin, o); const int i2 = __shfl_xor_sync(FULL, imin, o);
-      if (d2 < dmin || (d2 == dmin && i2 > imin)) { dmin = d2; imin = i2; }
+      const float d2 = __shfl_xor_sync(FULL, dmin, o); const int c2 = __shfl_xor_sync(FULL, cmin, o), i2 = __shfl_xor_sync(FULL, imin, o);
+      if (d2 < dmin || (d2 == dmin && c2 > cmin)) { dmin = d2; cmin = c2; imin = i2; }
     }
     if (lane == 0) s_list[HL_WORDS * imin] = 0.f;
     __syncwarp();
     total--;
   }
-  int outbase = 0;
+  // contact records in candidate order (the list holds each slot's direct hits before its sphere hits): rank = live entries with a smaller index
 #pragma unroll 1
   for (int e0 = 0; e0 < cnt; e0 += 32) {
     const int e = e0 + lane;
     const float* le = s_list + HL_WORDS * min(e, cnt - 1);
     const float depth = le[0];
     const bool live = e < cnt && depth > 0.f;
-    const unsigned lm = __ballot_sync(FULL, live);
+    const int cand = __float_as_int(le[8]);
+    int rank = 0;
+#pragma unroll 1
+    for (int j = 0; j < cnt; j++) rank += (s_list[HL_WORDS * j] > 0.f && __float_as_int(s_list[HL_WORDS * j + 8]) < cand) ? 1 : 0;
     if (live) {
-      float* ct = s_ct + (outbase + __popc(lm & lt)) * CT_WORDS;
+      float* ct = s_ct + rank * CT_WORDS;
       const f3 n = mk(le[1], le[2], le[3]);
       const f3 ex = (fabsf(n.x) < 0.9f) ? mk(1.f, 0.f, 0.f) : mk(0.f, 1.f, 0.f);
       const f3 t = ex - dot(ex, n) * n;
       const float inv = rsqrt_nr(dot(t, t));
       const f3 t1 = inv * t, t2 = cross(n, t1);
-      const int cand = __float_as_int(le[8]);
       ct[CF_POS] = le[4]; ct[CF_POS + 1] = le[5]; ct[CF_POS + 2] = le[6];
       ct[CF_N] = n.x; ct[CF_N + 1] = n.y; ct[CF_N + 2] = n.z;
       ct[CF_T1] = t1.x; ct[CF_T1 + 1] = t1.y; ct[CF_T1 + 2] = t1.z;
@@ -522,7 +530,6 @@ __device__ __noinline__ int stage_b_narrow_phase(const TerrainDesc& ter, const u
       ct[CF_DEPTH] = depth;
       ct[CF_PT] = __int_as_float(cand); ct[CF_BODY] = __int_as_float(ptsi[cand]); ct[CF_PAIR] = le[7];
     }
-    outbase += __popc(lm);
   }
   return total;
 }
@@ -840,7 +847,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       if (args.phase_mask & 4) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncwarp(); break; }   // kinematics for the getters only
 
       // =========================== stage B: narrow phase ========================================
-      K = stage_b_narrow_phase<SLOTS>(s_ter, blob_s, s_pose, s_ct, s_Y, env, lane, nbp, args.prof ? args.prof + ((size_t)env * 4 + (sub & 3)) * 8 : nullptr);
+      K = stage_b_narrow_phase<SLOTS>(args.ter, s_ter, blob_s, s_pose, s_ct, s_Y, env, lane, nbp, args.prof ? args.prof + ((size_t)env * 4 + (sub & 3)) * 8 : nullptr);
       const int C = 3 * K;
       if (args.prof && lane == 0) args.prof[((size_t)env * 4 + (sub & 3)) * 8 + 2] = (unsigned)clock64();
       if (args.phase_mask & 1) { asm volatile("cp.async.wait_all;" ::: "memory"); __syncwarp(); break; }   // integrate1(): kinematics, collision, M, h only
