@@ -1397,10 +1397,10 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         __syncwarp();
         const size_t row = ((size_t)args.peer_rank * args.num_envs + env) * args.ob_dim;
 #pragma unroll 1
-        for (int pr = 0; pr < args.peer_world; pr++) {
-          float* dst = args.peer_obs[pr] + row;
+        for (int i = lane; i < args.ob_dim; i += 32) {
+          const float v = o[i];                                          // re-read of this warp's own row (L2 hit), once for all peers
 #pragma unroll 1
-          for (int i = lane; i < args.ob_dim; i += 32) dst[i] = o[i];   // re-read of this warp's own row: L1/L2 hit
+          for (int pr = 0; pr < args.peer_world; pr++) args.peer_obs[pr][row + i] = v;
         }
       }
     }
@@ -1441,10 +1441,12 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
     __syncwarp();
   }
   if (args.peer_world > 0 && args.obs) {
-    // every row this CTA stored must be visible on the peers before they see the arrival count (release at system scope)
-    __threadfence_system();
+    // every row this CTA stored must be visible on the peers before they see the arrival count: the CTA barrier orders the warps'
+    // stores before the signalling threads, whose release at system scope is cumulative over them (one fence per signalling
+    // thread instead of one per thread of the CTA)
     __syncthreads();
-    if ((int)threadIdx.x < args.peer_world) atomicAdd_system(args.peer_flag[threadIdx.x] + args.peer_rank, 1u);
+    if ((int)threadIdx.x < args.peer_world)
+      asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(args.peer_flag[threadIdx.x] + args.peer_rank), "r"(1u) : "memory");
   }
 }
 
