@@ -684,17 +684,18 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         int j = (bvalid && d <= MYB(BF_DEPTH)) ? anc[(d - 1) * nbp + b] : -1;
         if (j >= 0) {
           f3 jp = mk(bodyf[(BF_JPOS + 0) * nbp + j], bodyf[(BF_JPOS + 1) * nbp + j], bodyf[(BF_JPOS + 2) * nbp + j]);
-          float Jr[9], Rj[9];
-          if (!jrot_identity) {
-#pragma unroll
-            for (int k = 0; k < 9; k++) Jr[k] = bodyf[(BF_JROT + k) * nbp + j];
-          }
+          float Rj[9];
           f3 al = mk(bodyf[(BF_AXIS + 0) * nbp + j], bodyf[(BF_AXIS + 1) * nbp + j], bodyf[(BF_AXIS + 2) * nbp + j]);
           f3 r = mulR(R, jp);
           if (jrot_identity) {
 #pragma unroll
             for (int k = 0; k < 9; k++) Rj[k] = R[k];
-          } else matmul3(R, Jr, Rj);
+          } else {
+            float Jr[9];      // scoped here: declared outside the branch it was a maybe-uninitialised value carried (through the stack) round the loop
+#pragma unroll
+            for (int k = 0; k < 9; k++) Jr[k] = bodyf[(BF_JROT + k) * nbp + j];
+            matmul3(R, Jr, Rj);
+          }
           f3 aj = mulR(Rj, al);
           float q = s_gc[bodyi[BF_QIDX * nbp + j]], qd = s_gv[bodyi[BF_VIDX * nbp + j]];
           const bool rev = bodyi[BF_JTYPE * nbp + j] == 1;

@@ -1195,3 +1195,53 @@ def test_pybind_dlpack_zero_copy_views(capi):
     assert np.array_equal(obs.cpu().numpy(), bt.observe())
     del pb                                                             # the tensors keep the batch alive
     assert torch.isfinite(tg).all()
+
+
+def test_actuator_effort_limits_match_oracle(capi):
+    """N2 effort limits on the GPU: (1) the pendulum KAT (alpha = tau_max / I whatever the gains; unsaturated law untouched; feed-forward
+    limited too), generic kernel; (2) the quadruped instance with stiff gains and far targets, where most leg joints saturate at the
+    URDF's 80 N m in the first steps: state parity with the float64 oracle over 20 steps and the same set of saturated joints."""
+    from test_oracle_kat import EFFORT_PENDULUM
+    I = 0.1 + 2.0 * 0.5 ** 2
+    bt = capi.Batch(capi.Model(EFFORT_PENDULUM), 4)
+    bt.set_params(gravity=(0.0, 0.0, 0.0))
+    bt.set_control_mode(capi.PD_PLUS_FEEDFORWARD_TORQUE)
+    bt.set_pd_gains(np.array([4000.0]), np.array([0.0]))
+    bt.set_state(np.zeros((4, 1), np.float32), np.zeros((4, 1), np.float32))
+    bt.set_pd_target(np.array([[1.0], [-1.0], [0.0002], [-0.0002]], np.float32), np.zeros((4, 1), np.float32))
+    bt.integrate(1)
+    _, v = bt.get_state()
+    free = 0.0025 * 4000.0 * 0.0002 / (I + 0.0025 ** 2 * 4000.0)         # 0.8 N m asked, 1.5 available: implicit PD
+    assert np.allclose(v[:, 0], [1.5 / I * 0.0025, -1.5 / I * 0.0025, free, -free], rtol=2e-6, atol=1e-9)
+    bt.set_control_mode(capi.FORCE_AND_TORQUE)
+    bt.set_state(np.zeros((4, 1), np.float32), np.zeros((4, 1), np.float32))
+    bt.set_generalized_force(np.array([[7.0], [-7.0], [1.0], [0.0]], np.float32))
+    bt.integrate(1)
+    _, v = bt.get_state()
+    assert np.allclose(v[:, 0], [1.5 / I * 0.0025, -1.5 / I * 0.0025, 1.0 / I * 0.0025, 0.0], rtol=2e-6, atol=1e-9)
+    # quadruped
+    n = 256
+    t, bt, o64, o32, gc, gv, tau = _setup(capi, "anymal_c_like.urdf", n, seed=777, base_z=0.62, vel=0.2, tau_scale=0.0, joint_scale=0.2)
+    rng = np.random.default_rng(778)
+    kp = np.r_[np.zeros(6), 2000.0 * np.ones(12)]; kd = np.r_[np.zeros(6), 20.0 * np.ones(12)]
+    pt = gc.copy(); pt[:, 7:] += rng.uniform(-0.6, 0.6, (n, 12))          # 2000 N m / rad * 0.3 rad >> 80 N m
+    vt = np.zeros((n, 18))
+    bt.set_control_mode(capi.PD_PLUS_FEEDFORWARD_TORQUE)
+    bt.set_pd_gains(kp, kd)
+    bt.set_pd_target(pt.astype(np.float32), vt.astype(np.float32))
+    a, b = gc.copy(), gv.copy()
+    sat_steps = 0
+    for k in range(20):
+        bt.integrate(1)
+        d = o64.step(a, b, ptarget=pt.astype(np.float32).astype(np.float64), vtarget=vt, kp=kp, kd=kd, debug=True)
+        ta = bt.generalized_force()           # the generalized force applied over the last step (feed-forward + PD, after the limit)
+        if ta is not None and k == 0:
+            sat_ref = np.abs(np.abs(d["tau_applied"][:, 6:]) - 80.0) < 1e-9
+            sat_gpu = np.abs(np.abs(ta[:, 6:]) - 80.0) < 1e-4
+            assert sat_ref.mean() > 0.3 and (sat_ref == sat_gpu).mean() > 0.999
+            sat_steps += 1
+    g, v = bt.get_state()
+    conv = (bt.solver_status() <= 1) & (d["status"] <= 1)
+    eg = np.abs(g - a).max(1)[conv]; ev = np.abs(v - b).max(1)[conv]
+    print(f"effort limits, 20 steps: median |dgc| {np.median(eg):.2e} max {eg.max():.2e}; median |dgv| {np.median(ev):.2e}")
+    assert np.median(eg) < 2e-5 and np.quantile(eg, 0.9) < 2e-4

@@ -42,8 +42,10 @@ clocks = [x["off"] for x in recs if "SR_CLOCKLO" in x["src"]]
 rets = [x["off"] for x in recs if opcode(x["src"]).startswith("RET")]
 main_end = rets[0] + 16
 in_main = [c for c in clocks if c < main_end]
-names = ["prologue (TMA of the model block, state rows in)", "A  FK + RNEA + CRBA (incl. the sub-step barrier)", "B  call site", "C  factorisation, z, Y, G", "D  call site",
+names = ["prologue (TMA of the model block, state rows in)", "A  FK + RNEA + CRBA (incl. the sub-step barrier)", "B  narrow phase", "C  factorisation, z, Y, G", "D  call site",
          "E  v+, integration, records out", "epilogue / cold paths of the kernel body"]
+if len(in_main) == 7:      # stage B compiled in line: its inner stamp splits it
+    names[2:3] = ["B  candidates, sphere groups", "B  selection, contact records"]
 parts = []
 edges = [0] + in_main + [main_end]
 for i, (a, b) in enumerate(zip(edges, edges[1:])):
@@ -52,7 +54,8 @@ for i, (a, b) in enumerate(zip(edges, edges[1:])):
 calls = collections.defaultdict(set)
 for x in recs:
     if opcode(x["src"]).startswith("CALL") and x["off"] < main_end:
-        tgt = int(x["src"].split()[-2 if x["src"].endswith(";") else -1].rstrip(";"), 16)
+        tgt = int([t for t in x["src"].replace(";", " ").split() if t.startswith("0x")][-1], 16)
+        tgt = tgt - base if tgt >= base else tgt
         seg = max(i for i, (a, b, n) in enumerate(parts) if a <= x["off"])
         calls[tgt].add(seg)
 fstart = main_end
@@ -61,7 +64,8 @@ for rr in rets[1:]:
     for tgt, segs in calls.items():
         if fstart <= tgt < rr + 16:
             callers |= segs
-    label = {2: "B  stage_b_narrow_phase()", 4: "D  gs_solve()"}.get(min(callers) if callers else -1, "helper (called from %s)" % ",".join(names[c][:1] for c in sorted(callers)) if callers else "helper")
+    first = names[min(callers)][:1] if callers else ""
+    label = {"B": "B  out-of-line shape routine", "D": "D  gs_solve()"}.get(first, "helper (called from %s)" % ",".join(names[c][:1] for c in sorted(callers)) if callers else "helper")
     parts.append((fstart, rr + 16, label))
     fstart = rr + 16
 print(f"\n{'part':52s} {'instr/env-sub-step':>18s} {'instr %':>8s} {'samples %':>9s}   top stall reasons")
