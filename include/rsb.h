@@ -244,7 +244,9 @@ void rsb_comm_destroy(rsb_comm* c);
  * (torch.distributed / MPI / a pipe), maps theirs (rsb_peer_buffer_open) and hands all pointers to its batch.  From then on
  * a control step that returns observation rows on the device also stores every finished row straight into every rank's
  * buffer (parity = control step & 1) while the kernel is still running, and bumps a counter on every rank as each CTA ends;
- * rsb_batch_wait_observation_peers() enqueues the wait for all ranks' rows of the last step.  No NCCL call on the data path. */
+ * the last CTA of the launch stays until every rank's counter shows its rows of this step, so the launch completes when the
+ * gathered rows are complete (bounded: a dead peer traps).  rsb_batch_wait_observation_peers() tells which of the two buffers
+ * holds the rows of the last step.  No NCCL call on the data path.  Every rank must step the same number of times. */
 int rsb_peer_buffer_create(int device, size_t bytes, void** dev_ptr, unsigned char* handle64 /* may be NULL */);
 int rsb_peer_buffer_open(int device, const unsigned char* handle64, void** dev_ptr);
 int rsb_peer_buffer_close(void* dev_ptr);

@@ -46,6 +46,7 @@ struct rsb_batch {
   float* peer_obs[MAX_PEERS][2] = {};     // [peer][buffer parity]: gathered-rows buffers, double-buffered by control step
   unsigned* peer_flag[MAX_PEERS] = {};    // [peer]: arrival counters [world]
   unsigned peer_epoch = 0;                // control steps signalled so far
+  unsigned* peer_done = nullptr;          // device counter of finished CTAs (in-kernel arrival wait)
   bool kin_dirty = true;             // the getters' buffers (M, h, poses) do not describe the current state
   unsigned* prof = nullptr;          // rsb_internal_set_profile
   int* hmap_index = nullptr;         // terrain atlas: map index per environment
@@ -290,6 +291,7 @@ static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug, flo
     a.peer_world = b->peer_world; a.peer_rank = b->peer_rank;
     for (int p = 0; p < b->peer_world; p++) { a.peer_obs[p] = b->peer_obs[p][b->peer_epoch & 1]; a.peer_flag[p] = b->peer_flag[p]; }
     b->peer_epoch++;
+    a.peer_expected = b->peer_epoch * (unsigned)b->grid; a.peer_done = b->peer_done;
   }
   {
     const char* e = getenv("RSB_SUBSTEP_BARRIER");
@@ -512,7 +514,7 @@ void rsb_batch_destroy(rsb_batch* b) {
   if (b->stream) cudaStreamSynchronize(b->stream);
   for (void* p : {(void*)b->solver_status, (void*)b->resid, (void*)b->diverged, (void*)b->tau_applied, (void*)b->gc, (void*)b->gv, (void*)b->tau, (void*)b->pt, (void*)b->vt, (void*)b->ncontacts, (void*)b->contact_pt, (void*)b->iters,
                   (void*)b->contacts, (void*)b->dbg_M, (void*)b->dbg_h, (void*)b->dbg_R, (void*)b->dbg_p, (void*)b->hmap, (void*)b->staging, (void*)b->obs_staging, (void*)b->blob, (void*)b->gym_const, (void*)b->gym_action,
-                  (void*)b->gym_obs, (void*)b->gym_reward, (void*)b->gym_done, (void*)b->ext, (void*)b->hmap_index})
+                  (void*)b->gym_obs, (void*)b->gym_reward, (void*)b->gym_done, (void*)b->ext, (void*)b->hmap_index, (void*)b->peer_done})
     if (p) cudaFree(p);
   if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
   delete b;
@@ -1041,17 +1043,21 @@ int rsb_batch_set_observation_peers(rsb_batch* b, int world, int rank, void* con
   CK(cudaStreamSynchronize(b->stream));
   for (int p = 0; p < world; p++) { b->peer_obs[p][0] = (float*)obs_all[2 * p]; b->peer_obs[p][1] = (float*)obs_all[2 * p + 1]; b->peer_flag[p] = (unsigned*)flags[p]; }
   b->peer_world = world; b->peer_rank = rank; b->peer_epoch = 0;
+  if (!b->peer_done) CK(cudaMalloc(&b->peer_done, sizeof(unsigned)));
+  CK(cudaMemsetAsync(b->peer_done, 0, sizeof(unsigned), b->stream));
   return RSB_OK;
 }
-// Enqueue (on the batch's stream) the wait for the rows of the LAST control step of every rank to have landed in this rank's
-// buffer; *buffer_parity (optional) = which of this rank's two buffers holds them.
+// *buffer_parity (optional) = which of this rank's two buffers holds the rows of the LAST control step of every rank.  The arrival
+// wait itself is part of that control step's launch (its last CTA stays until every rank's rows have landed), so in stream order
+// after the step the rows are complete and nothing is enqueued here.
 int rsb_batch_wait_observation_peers(rsb_batch* b, int* buffer_parity) {
   if (!b || b->peer_world <= 0 || b->peer_epoch == 0) return fail(RSB_ERR_INVALID, "no fused observation gather in flight");
-  CK(cudaSetDevice(b->device));
-  const unsigned expected = b->peer_epoch * (unsigned)b->grid;
-  rsb_peer_wait_kernel<<<1, 32, 0, b->stream>>>(b->peer_flag[b->peer_rank], b->peer_world, expected, 20000000000ll /* ~10 s of SM clocks */);
-  CK(cudaGetLastError());
-  b->launches++;
+  if (!b->peer_done) {       // (unreachable with rsb_batch_set_observation_peers; kept as the stand-alone form of the wait)
+    CK(cudaSetDevice(b->device));
+    rsb_peer_wait_kernel<<<1, 32, 0, b->stream>>>(b->peer_flag[b->peer_rank], b->peer_world, b->peer_epoch * (unsigned)b->grid, 20000000000ll /* ~10 s of SM clocks */);
+    CK(cudaGetLastError());
+    b->launches++;
+  }
   if (buffer_parity) *buffer_parity = (int)((b->peer_epoch - 1) & 1);
   return RSB_OK;
 }

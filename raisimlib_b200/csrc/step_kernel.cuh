@@ -194,6 +194,8 @@ struct StepArgs {
   float* peer_obs[MAX_PEERS];      // peer p's gathered-rows buffer of this step (null = not in use)
   unsigned* peer_flag[MAX_PEERS];  // peer p's arrival counters [world]: += 1 per finished CTA of this rank
   int peer_world, peer_rank;
+  unsigned peer_expected;          // arrival count every rank's counter reaches when its rows of THIS step have landed (steps so far x CTAs)
+  unsigned* peer_done;             // CTAs of this launch that finished: the last one waits for the peers (null: the caller enqueues rsb_peer_wait_kernel)
   int phase_mask;      // bit0: stop after stage B (integrate1: no state update); bit2: kinematics only (stage A + getters' buffers,
                        // the contact records of the last integrate() stay as they are)
   int substep_barrier; // 1: re-align the CTA's warps at every sub-step (instruction-cache locality experiment)
@@ -1448,6 +1450,28 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
     __syncthreads();
     if ((int)threadIdx.x < args.peer_world)
       asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(args.peer_flag[threadIdx.x] + args.peer_rank), "r"(1u) : "memory");
+    if (args.peer_done) {
+      // the arrival wait folded into the launch: the last CTA to finish stays until every rank's rows of this step have landed in
+      // THIS GPU's buffer, so the launch completes exactly when the gathered rows do (no separate wait kernel, no launch gap).
+      // Bounded: a dead peer traps instead of hanging the GPU.
+      __shared__ int s_last;
+      if (threadIdx.x == 0) {
+        const unsigned d = atomicAdd(args.peer_done, 1u);
+        s_last = d == gridDim.x - 1 ? 1 : 0;
+        if (s_last) *args.peer_done = 0u;           // every CTA has counted itself: ready for the next launch
+      }
+      __syncthreads();
+      if (s_last && (int)threadIdx.x < args.peer_world) {
+        const unsigned* f = args.peer_flag[args.peer_rank] + threadIdx.x;
+        const long long t0 = clock64();
+        for (;;) {
+          unsigned v;
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+          if ((int)(v - args.peer_expected) >= 0) break;
+          if (clock64() - t0 > 20000000000ll) __trap();
+        }
+      }
+    }
   }
 }
 

@@ -38,8 +38,9 @@ class ObservationGather:
     mode "peer" (default on NVLink boxes): the all-gather is FUSED into the step kernel.  Every rank owns two gathered-rows
     buffers [world * n, ob_dim] (double-buffered by control step) and a row of arrival counters, all plain device memory exported
     through CUDA IPC; `torch.distributed` only ships the 64-byte handles once, at set-up.  During a control step each finished
-    observation row is stored straight into every rank's buffer over NVLink while the kernel is still running; `wait()` enqueues
-    a tiny kernel that returns when every rank's rows of that step have landed.  No NCCL call on the data path.
+    observation row is stored straight into every rank's buffer over NVLink while the kernel is still running, and the last CTA
+    of the launch stays until every rank's rows of that step have landed: the control step completes when the gathered rows do.
+    No NCCL call, no extra launch on the data path.
     mode "nccl": `all_gather_into_tensor` after the step (the baseline this replaces; also what the gloo CPU test drives)."""
 
     def __init__(self, batch, world, rank, n, ob_dim, mode="peer", device=None):
@@ -96,7 +97,7 @@ class ObservationGather:
 
     def report(self):
         return {"mode": self.mode, "collective": ("observation rows stored into every rank's buffer by the step kernel over NVLink peer memory (CUDA IPC), "
-                                                  "arrival counters + one wait kernel per step; no NCCL call on the data path") if self.mode == "peer"
+                                                  "arrival counters, the wait folded into the same launch; no NCCL call and no extra launch on the data path") if self.mode == "peer"
                 else "torch.distributed all_gather_into_tensor (NCCL) after the step, on the launching stream",
                 "bytes_per_step_per_rank": int(self.n * self.od * 4 * self.world)}
 
