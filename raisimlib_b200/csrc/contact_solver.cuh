@@ -226,7 +226,6 @@ __device__ __noinline__ GsResult gs_solve(const rsb_params& prm, float* s_G, int
   constexpr unsigned FULLM = 0xffffffffu;
   const int C3 = 3 * K, CR = C3 + Lm;
   const float* Grow = s_G + min(lane, CR - 1) * g_stride;   // lanes past the last row shadow it: branch-free updates, values never used
-  const int my_i = lane / 3, my_d = lane - 3 * my_i;
   float lam_c = 0.f;
   float alpha = prm.alpha_init;
   float sd_c = 1.f, sd_s = 0.f; int sd_v = 0;   // lane i < K: slip direction of contact i in the previous sweep
@@ -269,7 +268,13 @@ __device__ __noinline__ GsResult gs_solve(const rsb_params& prm, float* s_G, int
       if (lane == i) sd_v = slipped ? 1 : 0;
       const float dx = alpha * (nx - lx), dy = alpha * (ny - ly), dz = alpha * (nz - lz);
       u_c += Grow[i3] * dx + Grow[i3 + 1] * dy + Grow[i3 + 2] * dz;
-      if (my_i == i) lam_c = my_d == 0 ? lx + dx : (my_d == 1 ? ly + dy : lz + dz);
+      {   // the three rows of contact i take their new impulse: selects, not a divergent branch (ncu: 6 % of the solve sat on its reconvergence)
+        const float l0 = lx + dx, l1 = ly + dy, l2 = lz + dz;
+        const int rel = lane - i3;
+        lam_c = rel == 0 ? l0 : lam_c;
+        lam_c = rel == 1 ? l1 : lam_c;
+        lam_c = rel == 2 ? l2 : lam_c;
+      }
       err = fmaxf(err, fmaxf(fabsf(dx), fmaxf(fabsf(dy), fabsf(dz))));
     }
 #pragma unroll 1

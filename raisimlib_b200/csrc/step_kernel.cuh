@@ -582,7 +582,6 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
   const int* bodyi = reinterpret_cast<const int*>(blob_s + HO(off_body));
   const int* anc = reinterpret_cast<const int*>(blob_s + HO(off_anc));
   const float* ptsf = reinterpret_cast<const float*>(blob_s + HO(off_pts));
-  const int* ptsi = reinterpret_cast<const int*>(blob_s + HO(off_pts));
   const float* kp = reinterpret_cast<const float*>(blob_s + HO(off_gain));
   const float* kd = kp + nvp;
   const float* emax = kp + 2 * nvp;     // actuator effort limit per dof (URDF <limit effort>, 3e38 = none)
