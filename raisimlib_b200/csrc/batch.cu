@@ -243,14 +243,21 @@ static int pick_config(rsb_batch* b) {
   }
   b->spec = quad_topology ? 1 : (same_dims(b->dims, kHumanoid30) ? 2 : 0);
   if (const char* e = getenv("RSB_FORCE_GENERIC")) if (atoi(e)) b->spec = 0;
-  // one persistent CTA per SM; as many warps (= resident environments) as shared memory allows
-  static const int options[] = {28, 16, 8, 4, 1};   // 14 = two 14-warp CTAs per SM (experiment: RSB_FORCE_WPC=14)
-  int need = (b->N + sms - 1) / sms;    // warps per SM that make every environment resident at once
-  int best = 0;
+  // Warps per CTA (= resident environments per CTA).  A round of w resident warps per SM costs ~ max(13, w): latency-bound up to a
+  // dozen warps (32 k cycles per sub-step), issue-bound beyond (2.5 k cycles per warp; profiles/).  Choose the option with the
+  // smallest rounds x cost, ties to the larger CTA (one sub-step barrier group, one copy of
+  // the model block).  4096 ANYmal-like environments: 28 (one round).  4096 Atlas-like ones, whose 10.9 KB workspaces allow 16 per
+  // SM: 14 (two balanced rounds: 0.98 ms per launch) rather than 16 (a full round and a 73 % one: 1.29 ms).
+  static const int options[] = {28, 16, 14, 8, 4, 1};
+  int best = 0; long best_cost = 0;
   for (int w : options) {
-    if (blob_bytes + (size_t)w * per_warp + 1024 > budget) continue;
-    if (best == 0) best = w;
-    if (w >= need) best = w;            // smallest option that still keeps every environment resident
+    const size_t cta_bytes = blob_bytes + (size_t)w * per_warp + 1024;
+    if (cta_bytes > budget) continue;
+    const int ctas = (w == 14 && 2 * cta_bytes <= (size_t)prop.sharedMemPerMultiprocessor) ? 2 : 1;   // 14-warp CTAs are compiled for two per SM
+    const long resident = (long)sms * w * ctas;
+    const long rounds = (b->N + resident - 1) / resident;
+    const long cost = rounds * std::max(13L, (long)w * ctas);
+    if (best == 0 || cost < best_cost) { best = w; best_cost = cost; }
   }
   if (const char* e = getenv("RSB_FORCE_WPC")) { int w = atoi(e); if (w == 28 || w == 16 || w == 14 || w == 8 || w == 4 || w == 1) if (blob_bytes + (size_t)w * per_warp + 1024 <= budget) best = w; }
   if (best == 0) return fail(RSB_ERR_UNSUPPORTED, "model too large for one warp's shared-memory workspace");

@@ -40,7 +40,8 @@ def main():
     for lvl in ("1", "0"):
         os.environ["RSB_SUBSTEP_BARRIER"] = lvl
         sim.bt.set_state(g, v)
-        print("  barrier %s: launch median %.4f ms (min %.4f max %.4f) -> %.3e env-steps/s" % ((lvl,) + launch_ms(sim, k0) + (n * bench.SUBSTEPS / launch_ms(sim, k0)[0] * 1e3,)))
+        t = launch_ms(sim, k0)
+        print("  barrier %s: launch median %.4f ms (min %.4f max %.4f) -> %.3e env-steps/s" % ((lvl,) + t + (n * bench.SUBSTEPS / t[0] * 1e3,)))
     os.environ.pop("RSB_SUBSTEP_BARRIER")
     lib = capi.lib()
     lib.rsb_internal_set_profile.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
