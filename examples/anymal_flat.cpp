@@ -2,6 +2,7 @@
 // 1000 steps, written against the raisim:: facade exactly as an upstream example program would be
 // (the shape of raisimLib's examples/src/server/anymal.cpp, [RECALL]; compiled by the reference CI
 // with -DRAISIM_EXAMPLE=ON, /root/reference/.travis.yml:11).  Runs on the GPU (batch of one).
+#include <cmath>
 #include <cstdio>
 #include <string>
 #include "raisim/World.hpp"
@@ -29,7 +30,17 @@ int main(int argc, char** argv) {
   anymal->getState(gc, gv);
   auto& contacts = anymal->getContacts();
   std::printf("t=%.4f s  base z=%.4f  contacts=%zu\n", world.getWorldTime(), gc[2], contacts.size());
-  for (auto& c : contacts)
+  bool frames_ok = true;
+  for (auto& c : contacts) {
     std::printf("  body %zu  depth %.5f  impulse_z %.5f\n", c.getlocalBodyIndex(), c.getDepth(), c.getImpulse()[2]);
-  return (gc[2] > 0.3 && contacts.size() == 4) ? 0 : 1;
+    // upstream idiom: world-frame impulse = contactFrame^T * (impulse in the contact frame); normal part >= 0, inside the cone
+    const raisim::Mat<3, 3> F = c.getContactFrame();
+    const raisim::Vec<3> l = c.getImpulseInContactFrame(), w = c.getImpulse();
+    for (int i = 0; i < 3; i++) {
+      const double back = F(0, i) * l[0] + F(1, i) * l[1] + F(2, i) * l[2];
+      if (std::fabs(back - w[i]) > 1e-6) frames_ok = false;
+    }
+    if (l[2] < -1e-9 || std::hypot(l[0], l[1]) > 0.95 * l[2] + 1e-6) frames_ok = false;
+  }
+  return (gc[2] > 0.3 && contacts.size() == 4 && frames_ok) ? 0 : 1;
 }

@@ -56,6 +56,26 @@ class Contact {
   Vec<3> getNormal() const { return {c_.normal[0], c_.normal[1], c_.normal[2]}; }
   Vec<3> getImpulse() const { return {c_.impulse[0], c_.impulse[1], c_.impulse[2]}; }   // world frame, on the robot
   double getDepth() const { return c_.depth; }
+  // Rows t1, t2, n of the contact frame (t1 = normalise(e_x - (e_x . n) n), e_y when |n_x| >= 0.9; t2 = n x t1), so
+  // that frame^T * (impulse in the contact frame) = world-frame impulse, the product user code forms with upstream's frame.
+  Mat<3, 3> getContactFrame() const {
+    const double n[3] = {c_.normal[0], c_.normal[1], c_.normal[2]};
+    const int a = std::fabs(n[0]) < 0.9 ? 0 : 1;
+    double t1[3] = {-n[a] * n[0], -n[a] * n[1], -n[a] * n[2]};
+    t1[a] += 1.0;
+    const double inv = 1.0 / std::sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+    for (double& x : t1) x *= inv;
+    const double t2[3] = {n[1] * t1[2] - n[2] * t1[1], n[2] * t1[0] - n[0] * t1[2], n[0] * t1[1] - n[1] * t1[0]};
+    Mat<3, 3> F;
+    for (int j = 0; j < 3; j++) { F(0, j) = t1[j]; F(1, j) = t2[j]; F(2, j) = n[j]; }
+    return F;
+  }
+  Vec<3> getImpulseInContactFrame() const {       // (tangential 1, tangential 2, normal): what the solver iterates on
+    const Mat<3, 3> F = getContactFrame();
+    Vec<3> l;
+    for (int i = 0; i < 3; i++) l[i] = F(i, 0) * c_.impulse[0] + F(i, 1) * c_.impulse[1] + F(i, 2) * c_.impulse[2];
+    return l;
+  }
   bool isObjectA() const { return true; }
   bool skip() const { return false; }
  private:
