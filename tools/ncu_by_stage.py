@@ -42,6 +42,8 @@ clocks = [x["off"] for x in recs if "SR_CLOCKLO" in x["src"]]
 rets = [x["off"] for x in recs if opcode(x["src"]).startswith("RET")]
 main_end = rets[0] + 16
 in_main = [c for c in clocks if c < main_end]
+if len(in_main) >= 8:      # the in-kernel arrival wait of the fused gather reads the clock twice (bounded spin) at the very end: not stage stamps
+    in_main = in_main[:-2]
 names = ["prologue (TMA of the model block, state rows in)", "A  FK + RNEA + CRBA (incl. the sub-step barrier)", "B  narrow phase", "C  factorisation, z, Y, G", "D  call site",
          "E  v+, integration, records out", "epilogue / cold paths of the kernel body"]
 if len(in_main) == 7:      # stage B compiled in line: its inner stamp splits it
@@ -64,8 +66,11 @@ for rr in rets[1:]:
     for tgt, segs in calls.items():
         if fstart <= tgt < rr + 16:
             callers |= segs
-    first = names[min(callers)][:1] if callers else ""
-    label = {"B": "B  out-of-line shape routine", "D": "D  gs_solve()"}.get(first, "helper (called from %s)" % ",".join(names[c][:1] for c in sorted(callers)) if callers else "helper")
+    nm = lambda c: parts[c][2][:1]
+    first = nm(min(callers)) if callers else ""
+    label = "helper"
+    if callers:
+        label = "D  gs_solve()" if first == "D" else ("B  out-of-line shape routine" if callers == {min(callers)} and first == "B" else "helper (called from %s)" % ",".join(sorted({nm(c) for c in callers})))
     parts.append((fstart, rr + 16, label))
     fstart = rr + 16
 print(f"\n{'part':52s} {'instr/env-sub-step':>18s} {'instr %':>8s} {'samples %':>9s}   top stall reasons")
