@@ -101,8 +101,8 @@ int main(int argc, char** argv) {
     auto* ra = wa.addArticulatedSystem(urdf);
     auto* rb = wb.addArticulatedSystem(urdf, "", order);
     raisim::VecDyn qa(nq), va(nv), qb(nq), vb(nv), kp(nv), kd(nv);
-    const double stance[19] = {0, 0, 0.57, 1, 0, 0, 0, 0.03, 0.4, -0.8, -0.03, 0.4, -0.8, 0.03, -0.4, 0.8, -0.03, -0.4, 0.8};
-    for (int i = 0; i < 19; i++) qa[i] = stance[i];
+    const double level_stance[19] = {0, 0, 0.57, 1, 0, 0, 0, 0.03, 0.4, -0.8, -0.03, 0.4, -0.8, 0.03, -0.4, 0.8, -0.03, -0.4, 0.8};
+    for (int i = 0; i < 19; i++) qa[i] = level_stance[i];
     for (int i = 0; i < 7; i++) qb[i] = qa[i];
     for (int l = 0; l < 4; l++) for (int j = 0; j < 3; j++) qb[7 + 3 * l + j] = qa[7 + 3 * (3 - l) + j];      // caller's order: RH, LH, RF, LF
     for (size_t i = 6; i < nv; i++) { kp[i] = 120.0 + double(i); kd[i] = 2.0 + 0.1 * double(i); }              // gains differ per joint: the permutation must carry them
