@@ -429,16 +429,17 @@ def main():
         torch.cuda.synchronize()
 
     def timed(host_io, steps, step0):
+        # one event pair per step around the whole step (ms_per_step); a second pair around the launch alone only where the step
+        # holds more than the launch (N > 1: the gather / arrival wait) -- two extra event records cost ~5 us of stream time per step
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        inner = gather is not None and not host_io
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)] if inner else ev
         barrier()
         for k in range(steps):
             flush.fill_(float(k))                            # evict L2 between timed iterations (256 MiB > 126 MB L2)
             ev[k][0].record(stream)
             if host_io:
-                kev[k][0].record(stream)
                 sim.step_host(step0 + k, shared.local if world > 1 else None)
-                kev[k][1].record(stream)
                 if world > 1:
                     # N > 1: same call per rank (it returns when this rank's rows are in host memory); shared-memory flags are
                     # the barrier after which the trainer's rank may read every row
@@ -446,10 +447,11 @@ def main():
                     shared.publish_and_wait(e2e_step[0])
                 ev[k][1].record(stream)
                 continue
-            kev[k][0].record(stream)
+            if inner:
+                kev[k][0].record(stream)
             obs = sim.step_resident(step0 + k)               # ONE launch: 4 fused sub-steps + observation rows
-            kev[k][1].record(stream)
-            if gather is not None:
+            if inner:
+                kev[k][1].record(stream)
                 gather.gather(obs)                           # fused: only the arrival wait is left here; nccl mode: the all-gather
             ev[k][1].record(stream)
         barrier()

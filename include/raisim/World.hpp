@@ -13,6 +13,7 @@
 // std::runtime_error with rsb_last_error() (define RAISIM_B200_ABORT_ON_ERROR to abort instead).
 // Units and conventions are the reference's: gc = [xyz | qw qx qy qz | joints], gv = [v | w | joint rates].
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -192,8 +193,58 @@ class BatchedWorld {
   double worldTime_ = 0;
 };
 
-class Ground {};
-class HeightMap {};
+// raisim::Ground / raisim::HeightMap ([RECALL] object/terrain/Ground.hpp, HeightMap.hpp): host-side descriptions of the terrain the
+// batch collides with -- what user code queries when it places a robot (getHeight) or builds height scans
+class Ground {
+ public:
+  double getHeight(double /*x*/ = 0, double /*y*/ = 0) const { return z_; }
+  void setHeight(double z) { z_ = z; }
+ private:
+  double z_ = 0;
+};
+class HeightMap {
+ public:
+  void set(size_t xs, size_t ys, double xSize, double ySize, double cx, double cy, std::vector<double> h) {
+    xs_ = xs; ys_ = ys; xSize_ = xSize; ySize_ = ySize; cx_ = cx; cy_ = cy; h_ = std::move(h);
+  }
+  size_t getXSamples() const { return xs_; }
+  size_t getYSamples() const { return ys_; }
+  double getXSize() const { return xSize_; }
+  double getYSize() const { return ySize_; }
+  double getCenterX() const { return cx_; }
+  double getCenterY() const { return cy_; }
+  const std::vector<double>& getHeightVector() const { return h_; }
+  // height of the collision surface at (x, y): the triangle of the cell beneath the point, two triangles per cell split along the
+  // P00-P11 diagonal exactly as the narrow phase does; outside the map: the nearest border point
+  double getHeight(double x, double y) const {
+    if (xs_ < 2 || ys_ < 2) return 0.0;
+    const double dx = xSize_ / double(xs_ - 1), dy = ySize_ / double(ys_ - 1);
+    double gx = (x - (cx_ - 0.5 * xSize_)) / dx, gy = (y - (cy_ - 0.5 * ySize_)) / dy;
+    gx = std::fmin(std::fmax(gx, 0.0), double(xs_ - 1)); gy = std::fmin(std::fmax(gy, 0.0), double(ys_ - 1));
+    size_t ix = size_t(gx), iy = size_t(gy);
+    if (ix > xs_ - 2) ix = xs_ - 2;
+    if (iy > ys_ - 2) iy = ys_ - 2;
+    const double fx = gx - double(ix), fy = gy - double(iy);
+    const double h00 = h_[iy * xs_ + ix], h10 = h_[iy * xs_ + ix + 1], h01 = h_[(iy + 1) * xs_ + ix], h11 = h_[(iy + 1) * xs_ + ix + 1];
+    return fx >= fy ? h00 + (h10 - h00) * fx + (h11 - h10) * fy : h00 + (h11 - h01) * fx + (h01 - h00) * fy;
+  }
+ private:
+  size_t xs_ = 0, ys_ = 0;
+  double xSize_ = 0, ySize_ = 0, cx_ = 0, cy_ = 0;
+  std::vector<double> h_;
+};
+
+// ArticulatedSystem::getSparseJacobian(): the non-zero columns of a 3 x dof Jacobian (the ancestors' dofs only)
+class SparseJacobian {
+ public:
+  size_t size = 0;             // number of non-zero columns
+  std::vector<size_t> idx;     // their generalized-velocity indices, ascending
+  MatDyn v;                    // 3 x size
+  void resize(size_t cols) { size = cols; idx.assign(cols, 0); v.resize(3, cols); }
+};
+
+// ArticulatedSystem::setIntegrationScheme ([RECALL] ArticulatedSystem.hpp)
+enum class IntegrationScheme : int { TRAPEZOID = 0, SEMI_IMPLICIT, EULER, RUNGE_KUTTA_4 };
 
 // raisim::TerrainProperties ([RECALL] include/raisim/object/terrain/HeightMap.hpp)
 struct TerrainProperties {
@@ -320,7 +371,7 @@ class ArticulatedSystem {
     std::vector<float> m(size_t(nv) * nv);
     rsbCheck(rsb_batch_get_mass_matrix(w_->batch(), env_, 1, m.data(), RSB_HOST), "getMassMatrix");
     MatDyn M; M.resize(nv, nv);
-    for (int i = 0; i < nv; i++) for (int j = 0; j < nv; j++) M(i, j) = m[size_t(i) * nv + j];
+    for (int i = 0; i < nv; i++) for (int j = 0; j < nv; j++) M(i, j) = m[vi(size_t(i)) * size_t(nv) + vi(size_t(j))];   // the caller's dof order (jointOrder)
     return M;
   }
   // M^-1 from the lazy M getter (dense Cholesky on the host: a convenience getter, not the hot path -- the kernel
@@ -409,7 +460,7 @@ class ArticulatedSystem {
     std::vector<float> h(w_->nv());
     rsbCheck(rsb_batch_get_nonlinearities(w_->batch(), env_, 1, h.data(), RSB_HOST), "getNonlinearities");
     VecDyn r(h.size());
-    for (size_t i = 0; i < h.size(); i++) r[i] = h[i];
+    for (size_t i = 0; i < h.size(); i++) r[i] = h[vi(i)];
     return r;
   }
   size_t getBodyIdx(const std::string& name) const {
@@ -451,6 +502,145 @@ class ArticulatedSystem {
   void getAngularVelocity(size_t bodyIdx, Vec<3>& out) const { Poses P = poses(); MatDyn J; jacobian(P, bodyIdx, Vec<3>{0, 0, 0}, nullptr, &J); mulGv(J, out); }
   void getFrameVelocity(size_t frameIdx, Vec<3>& out) const { MatDyn J; getDenseFrameJacobian(frameIdx, J); mulGv(J, out); }
   void getFrameAngularVelocity(size_t frameIdx, Vec<3>& out) const { MatDyn J; getDenseFrameRotationalJacobian(frameIdx, J); mulGv(J, out); }
+
+  // ---- model queries and whole-body quantities (host algebra on the model tables, the poses and M of the current state;
+  //      upstream names, [RECALL] ArticulatedSystem.hpp) --------------------------------------------------------------
+  std::vector<std::string> getBodyNames() const {
+    std::vector<std::string> r;
+    for (int b = 0; b < w_->nb(); b++) r.emplace_back(rsb_model_body_name(w_->model(), b));
+    return r;
+  }
+  // movable joints in the order of the generalized coordinates the caller sees (jointOrder if one was given)
+  std::vector<std::string> getMovableJointNames() const {
+    const rsb_model_tables t = tables();
+    const int q0 = t.floating ? 7 : 0;
+    std::vector<std::string> r(size_t(t.nq - q0));
+    for (int k = 0; k < t.nq - q0; k++)
+      for (int b = 1; b < t.nb; b++) if (t.qidx[b] == int(qi(size_t(q0 + k)))) r[size_t(k)] = rsb_model_joint_name(w_->model(), b);
+    return r;
+  }
+  // [lower, upper] per generalized velocity index (URDF <limit lower upper>; the base dofs and unlimited joints: -/+ 1e30 as parsed)
+  std::vector<Vec<2>> getJointLimits() const {
+    const rsb_model_tables t = tables();
+    std::vector<Vec<2>> r(size_t(t.nv));
+    for (int i = 0; i < t.nv; i++) { r[size_t(i)][0] = -1e30; r[size_t(i)][1] = 1e30; }
+    for (int i = 0; i < t.nv; i++)
+      for (int b = 1; b < t.nb; b++) if (t.vidx[b] == int(vi(size_t(i)))) { r[size_t(i)][0] = t.jlimit[2 * b]; r[size_t(i)][1] = t.jlimit[2 * b + 1]; }
+    return r;
+  }
+  // actuator effort limits per generalized velocity index (URDF <limit effort>; none: 1e30); the step kernel saturates the commanded torque there
+  VecDyn getActuationUpperLimits() const {
+    const rsb_model_tables t = tables();
+    VecDyn r(size_t(t.nv));
+    for (int i = 0; i < t.nv; i++) {
+      r[size_t(i)] = 1e30;
+      for (int b = 1; b < t.nb; b++) if (t.vidx[b] == int(vi(size_t(i)))) r[size_t(i)] = t.jeffort[b];
+    }
+    return r;
+  }
+  VecDyn getActuationLowerLimits() const { VecDyn r = getActuationUpperLimits(); for (size_t i = 0; i < r.size(); i++) r[i] = -r[i]; return r; }
+  double getMass(size_t localIdx) const { return tables().mass[localIdx]; }
+  double getTotalMass() const { const rsb_model_tables t = tables(); double m = 0; for (int b = 0; b < t.nb; b++) m += t.mass[b]; return m; }
+  std::vector<Vec<3>> getBodyCOM_B() const {
+    const rsb_model_tables t = tables();
+    std::vector<Vec<3>> r(size_t(t.nb));
+    for (int b = 0; b < t.nb; b++) for (int k = 0; k < 3; k++) r[size_t(b)][size_t(k)] = t.com[3 * b + k];
+    return r;
+  }
+  std::vector<Vec<3>> getBodyCOM_W() const {
+    const rsb_model_tables t = tables(); const Poses P = poses();
+    std::vector<Vec<3>> r(size_t(t.nb));
+    for (int b = 0; b < t.nb; b++) r[size_t(b)] = comWorld(t, P, b);
+    return r;
+  }
+  Vec<3> getCOM() const {      // centre of mass of the whole robot, world frame
+    const rsb_model_tables t = tables(); const Poses P = poses();
+    Vec<3> c; double m = 0;
+    for (int b = 0; b < t.nb; b++) { const Vec<3> cb = comWorld(t, P, b); for (int k = 0; k < 3; k++) c[size_t(k)] += t.mass[b] * cb[size_t(k)]; m += t.mass[b]; }
+    for (int k = 0; k < 3; k++) c[size_t(k)] /= m;
+    return c;
+  }
+  VecDyn getGeneralizedMomentum() const {      // M gv (M from the kernel's CRBA)
+    const MatDyn M = getMassMatrix(); const VecDyn gv = getGeneralizedVelocity();
+    VecDyn r(size_t(M.rows()));
+    for (size_t i = 0; i < M.rows(); i++) { double s = 0; for (size_t j = 0; j < M.cols(); j++) s += M(i, j) * gv[j]; r[i] = s; }
+    return r;
+  }
+  double getKineticEnergy() const {
+    const MatDyn M = getMassMatrix(); const VecDyn gv = getGeneralizedVelocity();
+    double e = 0;
+    for (size_t i = 0; i < M.rows(); i++) for (size_t j = 0; j < M.cols(); j++) e += 0.5 * gv[i] * M(i, j) * gv[j];
+    return e;
+  }
+  double getPotentialEnergy(const Vec<3>& gravity) const {
+    const rsb_model_tables t = tables(); const Poses P = poses();
+    double e = 0;
+    for (int b = 0; b < t.nb; b++) { const Vec<3> c = comWorld(t, P, b); e -= t.mass[b] * (gravity[0] * c[0] + gravity[1] * c[1] + gravity[2] * c[2]); }
+    return e;
+  }
+  double getEnergy(const Vec<3>& gravity) const { return getKineticEnergy() + getPotentialEnergy(gravity); }
+  Vec<3> getLinearMomentum() const {           // sum of m_b v_com,b through the body Jacobians
+    const rsb_model_tables t = tables(); const Poses P = poses(); const VecDyn gv = getGeneralizedVelocity();
+    Vec<3> p;
+    for (int b = 0; b < t.nb; b++) {
+      MatDyn J; jacobian(P, size_t(b), comWorld(t, P, b), &J, nullptr);
+      for (int r = 0; r < 3; r++) { double s = 0; for (size_t c = 0; c < J.cols(); c++) s += J(size_t(r), c) * gv[c]; p[size_t(r)] += t.mass[b] * s; }
+    }
+    return p;
+  }
+  void getSparseJacobian(size_t bodyIdx, const Vec<3>& point_W, SparseJacobian& J) const {
+    const rsb_model_tables t = tables(); const Poses P = poses();
+    MatDyn D; jacobian(P, bodyIdx, point_W, &D, nullptr);
+    std::vector<size_t> cols;        // dofs of the chain root .. body, in the caller's order
+    for (int i = int(bodyIdx); i >= 0; i = t.parent[i]) {
+      const int nd = t.jtype[i] == 3 ? 6 : (t.jtype[i] == 1 || t.jtype[i] == 2 ? 1 : 0);
+      for (int k = 0; k < nd; k++) cols.push_back(vinv(size_t(t.vidx[i] + k)));
+    }
+    std::sort(cols.begin(), cols.end());
+    J.resize(cols.size());
+    for (size_t k = 0; k < cols.size(); k++) { J.idx[k] = cols[k]; for (size_t r = 0; r < 3; r++) J.v(r, k) = D(r, cols[k]); }
+  }
+  // base pose setters (floating base): the other coordinates stay as they are
+  void setBasePos(const Vec<3>& pos) {
+    VecDyn gc = getGeneralizedCoordinate();
+    if (gc.size() < 7 || !tables().floating) throw std::runtime_error("setBasePos: the robot has a fixed base");
+    for (size_t k = 0; k < 3; k++) gc[k] = pos[k];
+    setGeneralizedCoordinate(gc);
+  }
+  void setBaseOrientation(const Vec<4>& quat) {
+    VecDyn gc = getGeneralizedCoordinate();
+    if (gc.size() < 7 || !tables().floating) throw std::runtime_error("setBaseOrientation: the robot has a fixed base");
+    const double n = std::sqrt(quat[0] * quat[0] + quat[1] * quat[1] + quat[2] * quat[2] + quat[3] * quat[3]);
+    for (size_t k = 0; k < 4; k++) gc[3 + k] = quat[k] / n;
+    setGeneralizedCoordinate(gc);
+  }
+  void setBaseOrientation(const Mat<3, 3>& rot) { Vec<4> q; rotMatToQuat(rot, q); setBaseOrientation(q); }
+  // upstream's separate target / gain setters: the other half keeps its last value
+  template <class VQ> void setPTarget(const VQ& posTarget) {
+    lastP_.resize(size_t(w_->nq())); for (size_t i = 0; i < lastP_.size(); i++) lastP_[i] = posTarget[i];
+    if (lastD_.size() != size_t(w_->nv())) lastD_.resize(size_t(w_->nv()));
+    setPdTarget(lastP_, lastD_);
+  }
+  template <class VV> void setDTarget(const VV& velTarget) {
+    lastD_.resize(size_t(w_->nv())); for (size_t i = 0; i < lastD_.size(); i++) lastD_[i] = velTarget[i];
+    if (lastP_.size() != size_t(w_->nq())) lastP_ = getGeneralizedCoordinate();     // no position target given yet: hold the current pose
+    setPdTarget(lastP_, lastD_);
+  }
+  template <class VV> void setPGains(const VV& p) {
+    kpLast_.resize(size_t(w_->nv())); for (size_t i = 0; i < kpLast_.size(); i++) kpLast_[i] = p[i];
+    if (kdLast_.size() != kpLast_.size()) kdLast_.resize(kpLast_.size());
+    setPdGains(kpLast_, kdLast_);
+  }
+  template <class VV> void setDGains(const VV& d) {
+    kdLast_.resize(size_t(w_->nv())); for (size_t i = 0; i < kdLast_.size(); i++) kdLast_[i] = d[i];
+    if (kpLast_.size() != kdLast_.size()) kpLast_.resize(kdLast_.size());
+    setPdGains(kpLast_, kdLast_);
+  }
+  // The batch integrates semi-implicitly (v+ from the implicit PD / contact solve, then q+ = q (+) dt v+);
+  // asking for another scheme fails loudly instead of silently integrating differently from what the caller expects.
+  void setIntegrationScheme(IntegrationScheme scheme) {
+    if (scheme != IntegrationScheme::SEMI_IMPLICIT) throw std::runtime_error("setIntegrationScheme: only IntegrationScheme::SEMI_IMPLICIT is implemented by the batched step");
+  }
 
   std::vector<Contact>& getContacts() {
     if (LockStep* ls = w_->lockStep()) {
@@ -512,7 +702,7 @@ class ArticulatedSystem {
         const double* ab = &t.axis[size_t(i) * 3];
         double a[3];
         for (int k = 0; k < 3; k++) a[k] = R[3 * k] * ab[0] + R[3 * k + 1] * ab[1] + R[3 * k + 2] * ab[2];
-        const size_t c = size_t(t.vidx[i]);
+        const size_t c = vinv(size_t(t.vidx[i]));      // column in the caller's dof order (jointOrder)
         if (t.jtype[i] == 1) {
           if (Jp) { (*Jp)(0, c) = a[1] * r[2] - a[2] * r[1]; (*Jp)(1, c) = a[2] * r[0] - a[0] * r[2]; (*Jp)(2, c) = a[0] * r[1] - a[1] * r[0]; }
           if (Jr) for (int k = 0; k < 3; k++) (*Jr)(k, c) = a[k];
@@ -526,6 +716,19 @@ class ArticulatedSystem {
   }
   size_t qi(size_t i) const { return qmap_.empty() ? i : size_t(qmap_[i]); }     // caller's coordinate index -> the batch's
   size_t vi(size_t i) const { return vmap_.empty() ? i : size_t(vmap_[i]); }
+  size_t vinv(size_t batchIdx) const {                                            // the batch's velocity index -> the caller's
+    if (vmap_.empty()) return batchIdx;
+    for (size_t i = 0; i < vmap_.size(); i++) if (size_t(vmap_[i]) == batchIdx) return i;
+    return batchIdx;
+  }
+  rsb_model_tables tables() const { rsb_model_tables t; rsbCheck(rsb_model_get_tables(w_->model(), &t), "getTables"); return t; }
+  Vec<3> comWorld(const rsb_model_tables& t, const Poses& P, int b) const {
+    const float* R = &P.R[size_t(b) * 9]; const float* o = &P.p[size_t(b) * 3]; const double* c = &t.com[size_t(b) * 3];
+    Vec<3> r;
+    for (int k = 0; k < 3; k++) r[size_t(k)] = o[k] + R[3 * k] * c[0] + R[3 * k + 1] * c[1] + R[3 * k + 2] * c[2];
+    return r;
+  }
+  VecDyn lastP_, lastD_, kpLast_, kdLast_;
   std::vector<int> qmap_, vmap_;
   BatchedWorld* w_;
   int env_;
@@ -578,7 +781,7 @@ class World {
     return robot_.get();
   }
   Ground* addGround(double zHeight = 0.0, const std::string& material = "default", CollisionGroup = CollisionGroup(-1)) {
-    haveGround_ = true; groundZ_ = zHeight; terrainMaterial_ = material;
+    haveGround_ = true; groundZ_ = zHeight; terrainMaterial_ = material; ground_.setHeight(zHeight);
     if (robot_) applyMaterials(true);
     if (w_) rsbCheck(rsb_batch_set_ground(w_->batch(), float(zHeight)), "addGround");
     return &ground_;
@@ -588,6 +791,7 @@ class World {
     need();
     std::vector<float> h(height.begin(), height.end());
     rsbCheck(rsb_batch_set_heightmap(w_->batch(), int(xSamples), int(ySamples), float(xSize), float(ySize), float(centerX), float(centerY), h.data()), "addHeightMap");
+    hm_.set(xSamples, ySamples, xSize, ySize, centerX, centerY, std::vector<double>(h.begin(), h.end()));   // what the batch collides with (float32 heights)
     return &hm_;
   }
   HeightMap* addHeightMap(double centerX, double centerY, const TerrainProperties& tp, const std::string& = "default", CollisionGroup = 1,
@@ -598,6 +802,7 @@ class World {
     std::vector<float> h(tp.xSamples * tp.ySamples);
     rsbCheck(rsb_terrain_generate(&p, h.data()), "TerrainGenerator");
     rsbCheck(rsb_batch_set_heightmap(w_->batch(), int(tp.xSamples), int(tp.ySamples), float(tp.xSize), float(tp.ySize), float(centerX), float(centerY), h.data()), "addHeightMap");
+    hm_.set(tp.xSamples, tp.ySamples, tp.xSize, tp.ySize, centerX, centerY, std::vector<double>(h.begin(), h.end()));
     return &hm_;
   }
   // height-map files (upstream overloads of the same name; [RECALL] formats, see include/rsb.h)
@@ -609,6 +814,7 @@ class World {
     std::vector<float> h(size_t(xs) * ys);
     rsbCheck(rsb_heightmap_read_text(raisimHeightMapFileName.c_str(), &xs, &ys, &sx, &sy, h.data(), int(h.size())), "addHeightMap");
     rsbCheck(rsb_batch_set_heightmap(w_->batch(), xs, ys, float(sx), float(sy), float(centerX), float(centerY), h.data()), "addHeightMap");
+    hm_.set(size_t(xs), size_t(ys), sx, sy, centerX, centerY, std::vector<double>(h.begin(), h.end()));
     return &hm_;
   }
   HeightMap* addHeightMap(const std::string& pngFileName, double centerX, double centerY, double xSize, double ySize, double heightScale,
@@ -619,6 +825,7 @@ class World {
     std::vector<float> h(size_t(xs) * ys);
     rsbCheck(rsb_heightmap_read_png(pngFileName.c_str(), heightScale, heightOffset, &xs, &ys, h.data(), int(h.size())), "addHeightMap");
     rsbCheck(rsb_batch_set_heightmap(w_->batch(), xs, ys, float(xSize), float(ySize), float(centerX), float(centerY), h.data()), "addHeightMap");
+    hm_.set(size_t(xs), size_t(ys), xSize, ySize, centerX, centerY, std::vector<double>(h.begin(), h.end()));
     return &hm_;
   }
   void setTimeStep(double dt) { dt_ = dt; if (w_) { rsb_params p = w_->params(); p.dt = float(dt); w_->setParams(p); } }

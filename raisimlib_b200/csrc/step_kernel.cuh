@@ -791,8 +791,9 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
 #pragma unroll
         for (int k = 0; k < 16; k++) {
           float t = X[k];
+          // lanes >= nb hold exact zeros (zero mass and inertia): with at most 16 bodies the xor-16 step adds 0 and is skipped
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+          for (int o = (ST && SNB <= 16) ? 8 : 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
           T[k] = t;
         }
         if (b == 0) {

@@ -391,6 +391,20 @@ def test_cpp_kinematic_getters_example():
     assert out.returncode == 0, out.stdout + out.stderr
 
 
+def test_cpp_dynamics_getters_example():
+    """facade whole-body getters (getCOM, getLinearMomentum, getKineticEnergy, getGeneralizedMomentum, getSparseJacobian, getJointLimits,
+    setBasePos / setBaseOrientation, HeightMap::getHeight, jointOrder on M / h / J; SURVEY 8b) against conservation laws and the
+    kernel's own M, poses and contacts, from C++"""
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "examples", "dynamics_getters")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")])
+    out = subprocess.run([exe, os.path.join(RSC, "anymal_c_like.urdf")], capture_output=True, text=True, timeout=180)
+    print(out.stdout)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+
 def test_default_solver_matches_oracle_on_random_drops(capi):
     """Library defaults (Anderson-accelerated sweeps from sweep 6, stagnation window 8 with the compliant fallback, threshold 1e-6)
     on a brutal random-drop batch (knee + foot contacts on one shank, bodies on the ground): same sweep counts and the same
