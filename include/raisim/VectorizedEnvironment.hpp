@@ -180,9 +180,9 @@ class VectorizedAnymalTask {
   int getObDim() const { return rsb_batch_ob_dim(world_.batch()); }
   int getActionDim() const { return world_.nq() - 7; }
   int getNumOfEnvs() const { return world_.numEnvs(); }
-  void setSeed(int) {}
-  void close() {}
-  void curriculumUpdate() {}
+  void setSeed(int) {}            // the device task draws no random numbers (reset() restores gc_init exactly): nothing to seed
+  void close() {}                 // no visualisation server to shut down (out of scope)
+  void curriculumUpdate() {}      // upstream's rsg_anymal has no curriculum either
   BatchedWorld& world() { return world_; }
  private:
   int substeps() const { return int(cfg_.control_dt / cfg_.simulation_dt + 1e-10); }

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -391,11 +392,11 @@ int rsb_params_default(rsb_params* p) {
 int rsb_model_create_from_urdf(const char* path_or_xml, rsb_model** out) {
   if (!path_or_xml || !out) return fail(RSB_ERR_INVALID, "null argument");
   try {
-    rsb_model* m = new rsb_model;
+    std::unique_ptr<rsb_model> m(new rsb_model);      // a parse error thrown below must not leak the half-built model
     m->md = load_urdf(path_or_xml);
-    if (m->md.nb > 32) { delete m; return fail(RSB_ERR_UNSUPPORTED, "more than 32 movable bodies (one lane per body)"); }
-    if (m->md.npts() > 32 * MAX_PT_SLOTS) { delete m; return fail(RSB_ERR_UNSUPPORTED, "more than 64 candidate contact points"); }
-    *out = m;
+    if (m->md.nb > 32) return fail(RSB_ERR_UNSUPPORTED, "more than 32 movable bodies (one lane per body)");
+    if (m->md.npts() > 32 * MAX_PT_SLOTS) return fail(RSB_ERR_UNSUPPORTED, "more than 64 candidate contact points");
+    *out = m.release();
     return RSB_OK;
   } catch (const std::exception& e) { return fail(RSB_ERR_PARSE, e.what()); }
 }
@@ -406,11 +407,11 @@ int rsb_model_save(const rsb_model* m, const char* path) {
 int rsb_model_load(const char* path, rsb_model** out) {
   if (!path || !out) return fail(RSB_ERR_INVALID, "null argument");
   try {
-    rsb_model* m = new rsb_model;
+    std::unique_ptr<rsb_model> m(new rsb_model);
     m->md = load_model(path);
-    if (m->md.nb > 32) { delete m; return fail(RSB_ERR_UNSUPPORTED, "more than 32 movable bodies (one lane per body)"); }
-    if (m->md.npts() > 32 * MAX_PT_SLOTS) { delete m; return fail(RSB_ERR_UNSUPPORTED, "more than 64 candidate contact points"); }
-    *out = m;
+    if (m->md.nb > 32) return fail(RSB_ERR_UNSUPPORTED, "more than 32 movable bodies (one lane per body)");
+    if (m->md.npts() > 32 * MAX_PT_SLOTS) return fail(RSB_ERR_UNSUPPORTED, "more than 64 candidate contact points");
+    *out = m.release();
     return RSB_OK;
   } catch (const std::exception& e) { return fail(RSB_ERR_PARSE, e.what()); }
 }
@@ -750,6 +751,7 @@ int rsb_batch_integrate(rsb_batch* b, int substeps) {
 
 int rsb_batch_get_mass_matrix(rsb_batch* b, int env_begin, int env_count, float* out, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  if (!out) return fail(RSB_ERR_INVALID, "null output buffer");
   if (env_count == 0) return RSB_OK;
   rc = ensure_kinematics(b); if (rc) return rc;
   size_t w = (size_t)b->nv * b->nv;
@@ -759,6 +761,7 @@ int rsb_batch_get_mass_matrix(rsb_batch* b, int env_begin, int env_count, float*
 }
 int rsb_batch_get_nonlinearities(rsb_batch* b, int env_begin, int env_count, float* out, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  if (!out) return fail(RSB_ERR_INVALID, "null output buffer");
   if (env_count == 0) return RSB_OK;
   rc = ensure_kinematics(b); if (rc) return rc;
   CK(cudaMemcpyAsync(out, b->dbg_h + (size_t)env_begin * b->nv, (size_t)env_count * b->nv * 4, where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
@@ -785,30 +788,35 @@ int rsb_batch_get_contacts(rsb_batch* b, rsb_contact* out, int32_t* counts, int 
 }
 int rsb_batch_get_contact_points(rsb_batch* b, int32_t* pt, int env_begin, int env_count, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  if (!pt) return fail(RSB_ERR_INVALID, "null output buffer");
   CK(cudaMemcpyAsync(pt, b->contact_pt + (size_t)env_begin * KMAX, (size_t)env_count * KMAX * 4, where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
   if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
   return RSB_OK;
 }
 int rsb_batch_get_solver_iterations(rsb_batch* b, int32_t* it, int env_begin, int env_count, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  if (!it) return fail(RSB_ERR_INVALID, "null output buffer");
   CK(cudaMemcpyAsync(it, b->iters + env_begin, (size_t)env_count * 4, where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
   if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
   return RSB_OK;
 }
 int rsb_batch_get_solver_status(rsb_batch* b, int32_t* status, int env_begin, int env_count, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  if (!status) return fail(RSB_ERR_INVALID, "null output buffer");
   CK(cudaMemcpyAsync(status, b->solver_status + env_begin, (size_t)env_count * 4, where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
   if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
   return RSB_OK;
 }
 int rsb_batch_get_solver_residual(rsb_batch* b, float* resid, int env_begin, int env_count, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  if (!resid) return fail(RSB_ERR_INVALID, "null output buffer");
   CK(cudaMemcpyAsync(resid, b->resid + env_begin, (size_t)env_count * 4, where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
   if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
   return RSB_OK;
 }
 int rsb_batch_get_diverged(rsb_batch* b, int32_t* flags, int env_begin, int env_count, int where) {
   int rc = check_range(b, env_begin, env_count); if (rc) return rc;
+  if (!flags) return fail(RSB_ERR_INVALID, "null output buffer");
   CK(cudaMemcpyAsync(flags, b->diverged + env_begin, (size_t)env_count * 4, where == RSB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, b->stream));
   if (where == RSB_HOST) CK(cudaStreamSynchronize(b->stream));
   return RSB_OK;

@@ -203,6 +203,7 @@ __device__ __noinline__ AAState anderson_step(float* hist, const float* s_G, int
 // Updates the Delassus diagonal, the per-contact blocks and their inverses; returns this lane's constraint velocity.
 __device__ __noinline__ float regularise(float stall_reg, float* s_G, int g_stride, float* s_cb, int lane, int K, int CR, float lam_c, float u_c) {
   const bool on = lane < CR;
+  __syncwarp();   // the sweep that just ended read the per-contact blocks rewritten below
   const float eps = stall_reg * warp_sum(on ? s_G[lane * g_stride + lane] : 0.f) / (float)CR;
   if (on) s_G[lane * g_stride + lane] += eps;
   if (lane < K) {

@@ -356,6 +356,7 @@ __device__ __forceinline__ QuadLeg quad_factor_legs(float* s_L, float* s_invd, i
   const float a6 = __shfl_sync(FULL, q.a, l0 + 6);
   q.i6 = rsqrt_nr(a6);
   q.a = (t == 6) ? a6 * q.i6 : q.a * q.i6;
+  __syncwarp();   // every lane of the leg has read the knee pivot k8 above; lane t == 0 overwrites it below (racecheck: read / write without a barrier)
   s_L[rK * QDLP + t] = q.k; s_L[rH * QDLP + t] = q.h;
   if (t < 7) s_L[rA * QDLP + t] = q.a;
   if (t == 0) { s_L[rK * QDLP + 8] = k8 * q.i8; s_invd[rK] = q.i8; s_invd[rH] = q.i7; s_invd[rA] = q.i6; }
@@ -503,6 +504,7 @@ __device__ RSB_STAGE_B_INLINE int stage_b_narrow_phase(const TerrainDesc& ter, c
       const float d2 = __shfl_xor_sync(FULL, dmin, o); const int c2 = __shfl_xor_sync(FULL, cmin, o), i2 = __shfl_xor_sync(FULL, imin, o);
       if (d2 < dmin || (d2 == dmin && c2 > cmin)) { dmin = d2; cmin = c2; imin = i2; }
     }
+    __syncwarp();                                       // the scan above read the row that lane 0 now clears
     if (lane == 0) s_list[HL_WORDS * imin] = 0.f;
     __syncwarp();
     total--;

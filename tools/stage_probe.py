@@ -37,12 +37,20 @@ def main():
     st = sim.stats()
     print(key, wl.name)
     print("  K hist", st["contacts_histogram"], "sweeps", st["sweeps_histogram"], "mean %.2f max %d" % (st["mean_solver_sweeps"], st["max_solver_sweeps"]))
-    for lvl in ("1", "0"):
+    ref = None
+    for lvl in os.environ.get("RSB_PROBE_LEVELS", "1,0").split(","):
         os.environ["RSB_SUBSTEP_BARRIER"] = lvl
         sim.bt.set_state(g, v)
         t = launch_ms(sim, k0)
-        print("  barrier %s: launch median %.4f ms (min %.4f max %.4f) -> %.3e env-steps/s" % ((lvl,) + t + (n * bench.SUBSTEPS / t[0] * 1e3,)))
+        ge, ve = sim.bt.get_state()
+        if ref is None:
+            ref = (ge, ve)
+        same = bool((ge == ref[0]).all() and (ve == ref[1]).all())      # the alignment mode must not change a single bit of the result
+        print("  barrier %s: launch median %.4f ms (min %.4f max %.4f) -> %.3e env-steps/s   state identical to the first mode: %s"
+              % ((lvl,) + t + (n * bench.SUBSTEPS / t[0] * 1e3, same)))
     os.environ.pop("RSB_SUBSTEP_BARRIER")
+    if os.environ.get("RSB_PROBE_STAGE_LEVEL"):       # stage timers under this alignment mode instead of the default
+        os.environ["RSB_SUBSTEP_BARRIER"] = os.environ["RSB_PROBE_STAGE_LEVEL"]
     lib = capi.lib()
     lib.rsb_internal_set_profile.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     sim.bt.set_state(g, v)
