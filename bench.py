@@ -430,9 +430,10 @@ def main():
 
     def timed(host_io, steps, step0):
         # one event pair per step around the whole step (ms_per_step); a second pair around the launch alone only where the step
-        # holds more than the launch (N > 1: the gather / arrival wait) -- two extra event records cost ~5 us of stream time per step
+        # holds more than the launch (the NCCL arm's all-gather: with the fused peer gather the arrival wait is part of the launch and
+        # nothing else is enqueued) -- two extra event records cost ~5 us of stream time per step
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        inner = gather is not None and not host_io
+        inner = gather is not None and gather.mode == "nccl" and not host_io
         kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)] if inner else ev
         barrier()
         for k in range(steps):
@@ -452,7 +453,8 @@ def main():
             obs = sim.step_resident(step0 + k)               # ONE launch: 4 fused sub-steps + observation rows
             if inner:
                 kev[k][1].record(stream)
-                gather.gather(obs)                           # fused: only the arrival wait is left here; nccl mode: the all-gather
+            if gather is not None:
+                gather.gather(obs)                           # fused: nothing is enqueued (the launch ends when the rows are complete); nccl mode: the all-gather
             ev[k][1].record(stream)
         barrier()
         ms = sum(a.elapsed_time(b) for a, b in ev)
