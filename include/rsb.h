@@ -260,8 +260,10 @@ int rsb_batch_wait_observation_peers(rsb_batch* b, int* buffer_parity /* may be 
 int rsb_batch_gym_configure(rsb_batch* b, const float* gc_init, const float* gv_init, const float* action_mean, const float* action_std,
                             const int32_t* foot_bodies, int n_foot, float torque_coeff, float forward_vel_coeff, float terminal_reward);
 int rsb_batch_gym_reset(rsb_batch* b);                                             /* VectorizedEnvironment::reset() */
+/* ::step() + ::observe() in ONE launch of the step kernel: action rows -> PD targets, `substeps` x World::integrate(), reward,
+ * isTerminalState(), reset() of the terminated environments, observation rows of the resulting state.  Needs rsb_batch_set_pd_gains(). */
 int rsb_batch_gym_step(rsb_batch* b, const float* action, int where_in, int substeps, float* obs, float* reward, unsigned char* done,
-                       int where_out);                                             /* ::step() + ::observe()          */
+                       int where_out);
 
 #ifdef __cplusplus
 }

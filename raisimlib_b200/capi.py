@@ -232,8 +232,8 @@ class Model:
         _ck(lib().rsb_model_save(self.h, path.encode()))
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().rsb_model_destroy(self.h)
+        if getattr(self, "h", None) and lib is not None and _lib is not None:     # at interpreter shutdown the module globals may be gone already
+            _lib.rsb_model_destroy(self.h)
             self.h = None
 
     def tables(self):
@@ -276,8 +276,8 @@ class Batch:
         self.h, self.n, self.nq, self.nv, self.nb = h, num_envs, model.nq, model.nv, model.nb
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().rsb_batch_destroy(self.h)
+        if getattr(self, "h", None) and lib is not None and _lib is not None:
+            _lib.rsb_batch_destroy(self.h)
             self.h = None
 
     # world set-up

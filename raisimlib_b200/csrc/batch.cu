@@ -277,7 +277,9 @@ static cudaError_t dispatch_spec(const rsb_batch* b, const StepArgs& a) {
   return launch_step<WPC, 2, 0, 0, 0, 0, 0, 0>(a, b->grid, b->smem_bytes, b->stream);
 }
 
-static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug, float* obs_dev = nullptr, bool peers = false) {
+struct GymLaunch { const float* action; float* reward; unsigned char* done; };   // rsb_batch_gym_step: the task fused into the step launch
+
+static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug, float* obs_dev = nullptr, bool peers = false, const GymLaunch* gym = nullptr) {
   StepArgs a{};
   a.num_envs = b->N; a.substeps = substeps;
   a.gc_stride = b->gc_stride; a.gv_stride = b->gv_stride;
@@ -295,6 +297,10 @@ static int do_launch(rsb_batch* b, int substeps, int phase_mask, bool debug, flo
   a.phase_mask = phase_mask; a.prof = b->prof;
   a.ext = b->ext_active ? b->ext : nullptr;
   a.obs = obs_dev; a.ob_dim = rsb_batch_ob_dim(b);
+  if (gym) {       // targets come from the action rows and are kept in the batch's own rows; terminated environments get their reset target there too
+    a.gym_action = gym->action; a.gym = b->gym; a.gym_reward = gym->reward; a.gym_done = gym->done;
+    a.ptarget = b->pt; a.pt_stride = b->gc_stride; a.pt_store = b->pt;
+  }
   if (peers && b->peer_world > 0 && obs_dev && phase_mask == 0) {
     a.peer_world = b->peer_world; a.peer_rank = b->peer_rank;
     for (int p = 0; p < b->peer_world; p++) { a.peer_obs[p] = b->peer_obs[p][b->peer_epoch & 1]; a.peer_flag[p] = b->peer_flag[p]; }
@@ -982,13 +988,6 @@ int rsb_batch_gym_step(rsb_batch* b, const float* action, int where_in, int subs
       act = b->gym_action;
     }
   }
-  {
-    int threads = 256, blocks = (b->N * nj + threads - 1) / threads;
-    rsb_gym_action_kernel<<<blocks, threads, 0, b->stream>>>(act, b->gym, b->nq, b->gc_stride, b->N, b->pt);
-    CK(cudaGetLastError());
-    b->launches++;
-  }
-  int rc = do_launch(b, substeps, 0, false); if (rc) return rc;
   const bool host_out = where_out == RSB_HOST;
   float* a_obs = (host_out && obs) ? const_cast<float*>(mapped_alias(obs)) : nullptr;
   float* a_rew = (host_out && reward) ? const_cast<float*>(mapped_alias(reward)) : nullptr;
@@ -996,13 +995,11 @@ int rsb_batch_gym_step(rsb_batch* b, const float* action, int where_in, int subs
   float* d_obs = a_obs ? a_obs : (host_out || !obs) ? b->gym_obs : obs;
   float* d_rew = a_rew ? a_rew : (host_out || !reward) ? b->gym_reward : reward;
   unsigned char* d_done = a_done ? a_done : (host_out || !done) ? b->gym_done : done;
-  {
-    int threads = 128, blocks = (b->N * 32 + threads - 1) / threads;
-    rsb_gym_post_kernel<<<blocks, threads, 0, b->stream>>>(b->gc, b->gv, b->tau_applied, b->pt, b->ncontacts, b->contacts, b->gym, b->gc_stride, b->gv_stride,
-                                                            b->nq, b->nv, b->N, d_obs, od, d_rew, d_done);
-    CK(cudaGetLastError());
-    b->launches++;
-  }
+  // ONE launch: action rows -> PD targets, `substeps` x World::integrate(), reward, isTerminalState(), reset() of the terminated
+  // environments and the observation rows of the resulting state (the task used to be an action kernel and a post kernel around the step)
+  if (!(b->control_mode == RSB_PD_PLUS_FEEDFORWARD_TORQUE && b->pd_set)) return fail(RSB_ERR_INVALID, "the gym task drives the robot through PD targets: call rsb_batch_set_pd_gains() first");
+  const GymLaunch gl{act, d_rew, d_done};
+  int rc = do_launch(b, substeps, 0, false, d_obs, false, &gl); if (rc) return rc;
   if (where_out == RSB_HOST) {
     if (obs && !a_obs) CK(cudaMemcpyAsync(obs, d_obs, (size_t)b->N * od * 4, cudaMemcpyDeviceToHost, b->stream));
     if (reward && !a_rew) CK(cudaMemcpyAsync(reward, d_rew, (size_t)b->N * 4, cudaMemcpyDeviceToHost, b->stream));

@@ -162,6 +162,17 @@ struct TerrainDesc {
   float inv_dx, inv_dy; // reciprocal pitch (sphere groups: cell of a point without an IEEE division)
 };
 
+// RaisimGym ANYmal locomotion task ([RECALL] raisimGymTorch envs/rsg_anymal/Environment.hpp): constants of
+// ENVIRONMENT::step() / isTerminalState() / reset(), all device pointers
+struct GymConfig {
+  const float* gc_init;      // [nq]
+  const float* gv_init;      // [nv]
+  const float* action_mean;  // [nq - 7]
+  const float* action_std;   // [nq - 7]
+  uint32_t foot_mask;        // bit b set: contacts on body b do not terminate the episode
+  float torque_coeff, forward_vel_coeff, terminal_reward;
+};
+
 struct StepArgs {
   int num_envs, substeps;
   int gc_stride, gv_stride, pt_stride, vt_stride;   // vt_stride likewise for vtarget; pt_stride: row stride of ptarget (own padded buffer or a bound caller buffer)
@@ -196,6 +207,13 @@ struct StepArgs {
   int peer_world, peer_rank;
   unsigned peer_expected;          // arrival count every rank's counter reaches when its rows of THIS step have landed (steps so far x CTAs)
   unsigned* peer_done;             // CTAs of this launch that finished: the last one waits for the peers (null: the caller enqueues rsb_peer_wait_kernel)
+  // RaisimGym task fused into the step (rsb_batch_gym_step): the launch turns the action rows into PD targets before the first
+  // sub-step and, after the last one, computes reward and termination, resets the terminated environments and writes the
+  // observation rows of the (possibly reset) state -- VectorizedEnvironment::step() + observe() in ONE launch
+  const float* gym_action;         // [num_envs][nq - 7] action rows (device memory or mapped pinned host memory); null = no task
+  GymConfig gym;
+  float* gym_reward;               // [num_envs]
+  unsigned char* gym_done;         // [num_envs]
   int phase_mask;      // bit0: stop after stage B (integrate1: no state update); bit2: kinematics only (stage A + getters' buffers,
                        // the contact records of the last integrate() stay as they are)
   int substep_barrier; // 1: re-align the CTA's warps at every sub-step (instruction-cache locality experiment)
@@ -643,11 +661,19 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       if (args.use_pd) {
         // PD targets are first needed in stage C: fetch them asynchronously (cp.async, global -> shared) so that a
         // caller buffer in pinned host memory (zero-copy control step) is read over PCIe behind stages A and B
+        // gym task: the joint part of the position target is action * actionStd + actionMean (ENVIRONMENT::step(), first half); the base
+        // part comes from the batch's own rows like every other target
+        const int nfetch = args.gym_action ? 7 : nq;
 #pragma unroll 1
-        for (int i = lane; i < nq; i += 32) cp_async4(&s_pt[i], &args.ptarget[(size_t)env * args.pt_stride + i]);
+        for (int i = lane; i < nfetch; i += 32) cp_async4(&s_pt[i], &args.ptarget[(size_t)env * args.pt_stride + i]);
 #pragma unroll 1
         for (int i = lane; i < nv; i += 32) cp_async4(&s_vt[i], &args.vtarget[(size_t)env * args.vt_stride + i]);
         asm volatile("cp.async.commit_group;" ::: "memory");
+        if (args.gym_action) {
+          const int nj = nq - 7;
+#pragma unroll 1
+          for (int i = lane; i < nj; i += 32) s_pt[7 + i] = args.gym_action[(size_t)env * nj + i] * args.gym.action_std[i] + args.gym.action_mean[i];
+        }
       }
     }
     __syncwarp();
@@ -1373,6 +1399,34 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
       if (args.prof && lane == 0) args.prof[((size_t)env * 4 + (sub & 3)) * 8 + 5] = (unsigned)clock64();
     }   // substeps
 
+    if (args.gym_action) {
+      // ENVIRONMENT::step() second half + isTerminalState() + reset(), same arithmetic as the stand-alone task kernel it replaces:
+      // reward = torque_coeff |tau|^2 + forward_vel_coeff min(4, body-frame x velocity); any contact on a non-foot body ends the episode
+      float qw = s_gc[3], qx = s_gc[4], qy = s_gc[5], qz = s_gc[6];
+      const float inv = 1.0f / sqrtf(qw * qw + qx * qx + qy * qy + qz * qz);
+      qw *= inv; qx *= inv; qy *= inv; qz *= inv;
+      const float r00 = 1.f - 2.f * (qy * qy + qz * qz), r10 = 2.f * (qx * qy + qw * qz), r20 = 2.f * (qx * qz - qw * qy);
+      const float vbx = r00 * s_gv[0] + r10 * s_gv[1] + r20 * s_gv[2];
+      float t2 = 0.f;
+#pragma unroll 1
+      for (int i = lane; i < nv; i += 32) t2 += s_b[i] * s_b[i];          // s_b: generalized force applied in the last sub-step (stage E)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t2 += __shfl_xor_sync(FULL, t2, o);
+      bool bad = false;
+      if (lane < K) bad = ((args.gym.foot_mask >> __float_as_int(s_ct[lane * CT_WORDS + CF_BODY])) & 1u) == 0u;
+      const bool term = __any_sync(FULL, bad);
+      float r = args.gym.torque_coeff * t2 + args.gym.forward_vel_coeff * fminf(4.0f, vbx);
+      __syncwarp();
+      if (term) {
+        r += args.gym.terminal_reward;
+#pragma unroll 1
+        for (int i = lane; i < nq; i += 32) { const float g0 = args.gym.gc_init[i]; s_gc[i] = g0; if (args.pt_store) args.pt_store[(size_t)env * args.gc_stride + i] = g0; }
+#pragma unroll 1
+        for (int i = lane; i < nv; i += 32) s_gv[i] = args.gym.gv_init[i];
+      }
+      if (lane == 0) { args.gym_reward[env] = r; args.gym_done[env] = term ? 1 : 0; }
+      __syncwarp();
+    }
     // ---- store state rows and contact records -----------------------------------------------------
     if (!(args.phase_mask & 1)) {
       float* g_gc = args.gc + (size_t)env * args.gc_stride;
