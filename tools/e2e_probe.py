@@ -35,6 +35,27 @@ def main():
                     torch.cuda.synchronize()
                     ts.append(e0.elapsed_time(e1))
                 print("targets %-4s  observations %-4s : median %.4f ms  (min %.4f)" % (tin, tout, np.median(ts[10:]), min(ts[10:])))
+        # the same host buffers through the copy engines instead of in-place PCIe access by the kernel: H2D of the targets before the
+        # launch and / or D2H of the observation rows after it, on the launching stream, inside the event window
+        tgt_dev = torch.empty_like(sim.ring_dev[0])
+        for tin in ("zero-copy", "dma"):
+            for tout in ("zero-copy", "dma"):
+                sim.bt.set_state(g, v)
+                ts = []
+                for k in range(60):
+                    flush.fill_(float(k))
+                    src = sim.ring_pin[(k0 + k) % bench.RING]
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    if tin == "dma":
+                        tgt_dev.copy_(src, non_blocking=True)
+                    sim.bt.control_step(tgt_dev if tin == "dma" else src, bench.SUBSTEPS, sim.obs[k & 1] if tout == "dma" else sim.obs_host)
+                    if tout == "dma":
+                        sim.obs_host.copy_(sim.obs[k & 1], non_blocking=True)
+                    e1.record(stream)
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                print("host targets by %-9s  host observations by %-9s : median %.4f ms  (min %.4f)" % (tin, tout, np.median(ts[10:]), min(ts[10:])))
 
 
 if __name__ == "__main__":
