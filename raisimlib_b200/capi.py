@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librsb.so")
+LIB_PATH = os.environ.get("RSB_LIB_PATH") or os.path.join(_HERE, "librsb.so")   # RSB_LIB_PATH: another build of the same library (A/B probes in tools/)
 KMAX = 8
 HOST, DEVICE = 0, 1
 FORCE_AND_TORQUE, PD_PLUS_FEEDFORWARD_TORQUE = 0, 1

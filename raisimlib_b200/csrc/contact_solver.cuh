@@ -182,7 +182,7 @@ __device__ __noinline__ AAState anderson_step(float* hist, const float* s_G, int
     if (ok) {
       const float xn = g - gam0 * dGa - gam1 * dGb;
       float acc = on ? h_u0[lane] : 0.f;      // u = u0 + G x_next
-#pragma unroll 1
+#pragma unroll 4      // independent shuffles and loads in flight; the sum keeps its order
       for (int b2 = 0; b2 < CR; b2++) {
         const float xb = __shfl_sync(0xffffffffu, xn, b2);
         if (on) acc += s_G[lane * g_stride + b2] * xb;

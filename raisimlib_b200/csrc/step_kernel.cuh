@@ -569,6 +569,12 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
   constexpr bool ST = SNB > 0;
   // every 12-joint quadruped: the host selects this instance only when the parent table is base + 4 chains of 3 (pick_config)
   constexpr bool QUAD = SNB == 13 && SNQ == 19 && SNV == 18 && SFL == 1 && SMAXDEPTH == 3 && SMAXDD == 8;
+  // deep trees on few resident warps (the humanoid instance: 14 warps per SM, latency-bound) get their dependent shared-memory loops of
+  // stage C unrolled for memory-level parallelism; everything else keeps them rolled (instruction cache)
+#ifndef RSB_DEEP_UNROLL
+#define RSB_DEEP_UNROLL 4
+#endif
+  constexpr int UNR = (ST && !QUAD && SMAXDD >= 12) ? RSB_DEEP_UNROLL : 1;
   constexpr Dims SD{SNB, SNQ, SNV, SFL, SMAXDEPTH, SMAXDD};
   constexpr WsLayout LS = make_ws_layout(SD);
   constexpr BlobHeader HS = make_blob_header(SD, 0, 0);
@@ -989,7 +995,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
             const int pk = ent[e0 + e], i = pk & 255, t = pk >> 8;
             float acc = s_L[i * DLP + t];
             const int kend = i + dsub[i];
-  #pragma unroll 1
+  #pragma unroll (UNR)
             for (int k = i + 1; k < kend; k++) acc -= s_L[k * DLP + lev] * s_L[k * DLP + t];
             s_L[i * DLP + t] = acc;
           }
@@ -1039,7 +1045,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
             const int i = lvldofs[d0 + lane];
             float acc = s_b[i];
             const int kend = i + dsub[i];
-  #pragma unroll 1
+  #pragma unroll (UNR)
             for (int k = i + 1; k < kend; k++) acc -= s_L[k * DLP + lev] * s_z[k];
             s_z[i] = acc * s_invd[i];
           }
@@ -1192,7 +1198,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
               float y = s_Y[sI * CP + c] * s_invd[a_s];
               s_Y[sI * CP + c] = y;
               yz += y * s_z[a_s];
-  #pragma unroll 1
+  #pragma unroll (UNR)
               for (int t = 0; t < sI; t++) s_Y[t * CP + c] -= s_L[a_s * DLP + t] * y;
             }
           }
@@ -1242,7 +1248,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
                 const int bbody = bcol < C3 ? __float_as_int(s_ct[(bcol / 3) * CT_WORDS + CF_BODY]) : dbody[__float_as_int(s_lim[4 * (bcol - C3)])];
                 const int tmax = lcad[ba * nbp + bbody];
                 float sacc = 0.f;
-  #pragma unroll 1
+  #pragma unroll (UNR)
                 for (int t = 0; t <= tmax; t++) sacc += s_Y[t * CP + a] * s_Y[t * CP + bcol];
                 s_G[a * GP + bcol] = sacc; s_G[bcol * GP + a] = sacc;
               }
