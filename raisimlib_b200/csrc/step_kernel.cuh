@@ -1157,7 +1157,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
               s_Y[3 * CP + c] = rc.x; s_Y[4 * CP + c] = rc.y; s_Y[5 * CP + c] = rc.z;
               jv = axd.x * s_gv[0] + axd.y * s_gv[1] + axd.z * s_gv[2] + rc.x * s_gv[3] + rc.y * s_gv[4] + rc.z * s_gv[5];
             }
-  #pragma unroll 1
+  #pragma unroll (UNR > 1 ? 2 : 1)
             for (int t = nbase; t <= m; t++) {
               const int a_t = danc[t * nvp + i0], j = dbody[a_t];
               f3 aj = mk(s_pose[(PF_A + 0) * nbp + j], s_pose[(PF_A + 1) * nbp + j], s_pose[(PF_A + 2) * nbp + j]);
@@ -1324,7 +1324,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
         for (int i = lane; i < nv; i += 32) {   // w = dt z + Y lam, gathered per dof over the contacts whose chain holds it
           float sacc = args.prm.dt * s_z[i];
           const int di = ddepth[i];
-  #pragma unroll 1
+  #pragma unroll (UNR)
           for (int k = 0; k < K; k++) {
             const int i0 = bdof[__float_as_int(s_ct[k * CT_WORDS + CF_BODY])];
             if (i0 >= 0 && ddepth[i0] >= di && danc[di * nvp + i0] == i)
@@ -1357,7 +1357,7 @@ __global__ void __launch_bounds__(WPC * 32, (WPC == 14 ? 2 : 1)) rsb_step_kernel
             // base dofs are ancestors of every other dof and are their own index: no ancestor lookup
   #pragma unroll
             for (int t = 0; t < 6; t++) if (t < nbase) acc -= s_L[i * DLP + t] * s_rhs[t];
-  #pragma unroll 1
+  #pragma unroll (UNR)
             for (int t = nbase; t < lev; t++) acc -= s_L[i * DLP + t] * s_rhs[danc[t * nvp + i]];
             s_rhs[i] = acc * s_invd[i];
           }
