@@ -241,3 +241,35 @@ def test_mesh_collision_becomes_its_bounding_box(tmp_path):
     assert np.allclose(t["csize"][0], [0.5, 0.1, 0.05]) and np.allclose(t["cpos"][0], [0.3, 0.1, 0.55])   # x scaled by 2: [-0.2, 0.8] x [0, 0.2] x [0, 0.1]
     assert np.allclose(t["csize"][1], [0.25, 0.1, 0.05]) and np.allclose(t["cpos"][1], [0.15, 0.1, 0.05])
     assert t["npts"] == 2 * 8 + 2                                                                # corners + one box-face candidate each
+
+
+def test_facade_host_pieces(tmp_path):
+    """host-only pieces of the C++ facade (no GPU): HeightMap::getHeight against a numpy restatement of the collision surface on a random
+    map (cell interiors, both triangles of a cell, grid nodes), Ground, the math helpers, the contact frame, loud failure without a robot"""
+    import subprocess
+    exe = tmp_path / "facade_host_check"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"), "-o", str(exe), os.path.join(ROOT, "tests", "cpp", "facade_host_check.cpp"),
+                           "-L" + os.path.join(ROOT, "raisimlib_b200"), "-lrsb", "-Wl,-rpath," + os.path.join(ROOT, "raisimlib_b200"), "-Wl,-rpath,/usr/local/cuda/lib64"])
+    rng = np.random.default_rng(77)
+    xs, ys, sx, sy, cx, cy = 9, 7, 4.0, 2.4, 0.3, -0.2
+    H = rng.uniform(-0.2, 0.2, (ys, xs))
+    np.savetxt(tmp_path / "h.txt", H.reshape(-1))
+    dx, dy = sx / (xs - 1), sy / (ys - 1)
+    x0, y0 = cx - sx / 2, cy - sy / 2
+    q = np.c_[rng.uniform(x0, x0 + sx, 400), rng.uniform(y0, y0 + sy, 400)]
+    nodes = np.array([(x0 + i * dx, y0 + j * dy) for j in range(ys) for i in range(xs)])
+    q = np.r_[q, nodes[: len(nodes) - xs][np.arange(len(nodes) - xs) % xs != xs - 1]]          # interior nodes (the oracle has no cell beyond the last row / column)
+    np.savetxt(tmp_path / "q.txt", q)
+    out = subprocess.run([str(exe), str(xs), str(ys), str(sx), str(sy), str(cx), str(cy), str(tmp_path / "h.txt"), str(tmp_path / "q.txt")],
+                         capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.split()
+    got = np.array([float(v) for v in lines[: len(q)]])
+    # numpy restatement of the two-triangles-per-cell surface (DESIGN.md section 2: cell split along P00-P11, tri 0 where fx >= fy)
+    gx, gy = (q[:, 0] - x0) / dx, (q[:, 1] - y0) / dy
+    ix, iy = np.minimum(gx.astype(int), xs - 2), np.minimum(gy.astype(int), ys - 2)
+    fx, fy = gx - ix, gy - iy
+    h00, h10, h01, h11 = H[iy, ix], H[iy, ix + 1], H[iy + 1, ix], H[iy + 1, ix + 1]
+    surf = np.where(fx >= fy, h00 + (h10 - h00) * fx + (h11 - h10) * fy, h00 + (h11 - h01) * fx + (h01 - h00) * fy)
+    assert np.abs(got - surf).max() < 1e-12
+    assert "self-checks ok" in out.stdout
