@@ -665,6 +665,35 @@ def test_control_step_equals_separate_calls(capi):
     bt.control_step(target.copy(), 4, o_np)
     g4, v4 = bt.get_state()
     assert np.array_equal(g_ref, g4) and np.array_equal(v_ref, v4) and np.array_equal(ref_obs, o_np)
+    # row-dependent position AND velocity targets: the CTA-cooperative fetch of pinned rows (16-byte chunks of the CTA's contiguous
+    # rows, staged in shared memory) must hand every environment ITS row -- pinned path == pageable (staged-copy) path, bit for bit
+    rng = np.random.default_rng(5)
+    tq = target.copy(); tq[:, 7:] += rng.uniform(-0.3, 0.3, (n, 12)).astype(np.float32)
+    tv = rng.uniform(-0.5, 0.5, (n, 18)).astype(np.float32); tv[:, :6] = 0
+    bt.set_state(gc.astype(np.float32), gv.astype(np.float32))
+    bt.control_step(tq.copy(), 4, o_np, vtarget=tv.copy())
+    g5, v5 = bt.get_state()
+    bt.set_state(gc.astype(np.float32), gv.astype(np.float32))
+    pq, pv = torch.from_numpy(tq).pin_memory(), torch.from_numpy(tv).pin_memory()
+    bt.control_step(pq, 4, pin_o, vtarget=pv)
+    g6, v6 = bt.get_state()
+    assert np.array_equal(g5, g6) and np.array_equal(v5, v6) and np.array_equal(o_np, pin_o.numpy())
+    assert not np.array_equal(g5, g4)                      # the targets do matter
+    # position targets alone from pinned memory (what bench.py's e2e arm passes), velocity targets kept from the call before
+    bt.set_state(gc.astype(np.float32), gv.astype(np.float32))
+    bt.control_step(pq, 4, pin_o)
+    g7, v7 = bt.get_state()
+    assert np.array_equal(g5, g7) and np.array_equal(v5, v7)
+    # the same rows at a source address that is NOT 16-byte aligned (one row = 76 bytes into a pinned allocation): head / tail words
+    big = torch.empty((n + 1, 19), dtype=torch.float32).pin_memory(); big[1:] = torch.from_numpy(tq)
+    bigv = torch.empty((n + 3, 18), dtype=torch.float32).pin_memory(); bigv[3:] = torch.from_numpy(tv)
+    assert big[1:].data_ptr() % 16 != 0 and bigv[3:].data_ptr() % 16 != 0
+    bt.set_state(gc.astype(np.float32), gv.astype(np.float32))
+    bt.control_step(big[1:], 4, pin_o, vtarget=bigv[3:])
+    g9, v9 = bt.get_state()
+    assert np.array_equal(g5, g9) and np.array_equal(v5, v9)
+    bt.set_pd_target(target, np.zeros((n, 18), np.float32))
+    bt.set_state(g4, v4)
     # targets read in place from pinned host memory persist like setPdTarget(): the caller may reuse its buffer
     bt.integrate(4)
     g_ref8, v_ref8 = bt.get_state()
