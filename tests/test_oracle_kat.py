@@ -794,3 +794,110 @@ def test_actuator_effort_limit_saturates_the_commanded_torque():
     gc = np.zeros((1, 1)); gv = np.zeros((1, 1))
     o.step(gc, gv, tau_ff=np.array([[7.0]]))
     assert abs(gv[0, 0] - 1.5 / I * 0.0025) < 1e-12
+
+
+def _surface_numpy(H, xs, ys, X, Y, cx, cy, x, y):
+    """height and unit normal of the two-triangles-per-cell surface at (x, y): written for this test from DESIGN.md section 2 (cell split
+    along P00-P11, triangle 0 where fx >= fy), independently of the oracle's terrain query"""
+    dx, dy = X / (xs - 1), Y / (ys - 1)
+    gx, gy = (x - (cx - X / 2)) / dx, (y - (cy - Y / 2)) / dy
+    ix, iy = int(gx), int(gy)
+    fx, fy = gx - ix, gy - iy
+    h00, h10, h01, h11 = H[iy, ix], H[iy, ix + 1], H[iy + 1, ix], H[iy + 1, ix + 1]
+    if fx >= fy:
+        sx, sy, tri = h10 - h00, h11 - h10, 0
+    else:
+        sx, sy, tri = h11 - h01, h01 - h00, 1
+    n = np.array([-sx / dx, -sy / dy, 1.0]); n /= np.linalg.norm(n)
+    return h00 + sx * fx + sy * fy, n, 2 * (iy * (xs - 1) + ix) + tri
+
+
+def test_random_heightmap_point_contacts_against_an_independent_surface():
+    """Box corners (zero-radius point candidates) dropped on a random rough map in random orientations: every contact the oracle reports
+    must lie below the independently restated surface by depth / n_z, carry that triangle's normal and pair index -- and every corner
+    below the surface must be reported (up to the 8-contact cap).  Independent evidence for the cell / triangle indexing that the
+    kernel's terrain query is a transcription of."""
+    from helpers import quat_to_rot
+    t = load_tables(BOX_URDF)
+    o = Oracle(t)
+    rng = np.random.default_rng(2024)
+    xs, ys, X, Y, cx, cy = 33, 29, 6.4, 5.6, 0.4, -0.3
+    H = 0.15 * rng.uniform(-1, 1, (ys, xs))
+    o.set_heightmap(xs, ys, X, Y, cx, cy, H)
+    n = 400
+    gc = np.zeros((n, 7)); gv = np.zeros((n, 6))
+    gc[:, 0] = rng.uniform(cx - 0.4 * X, cx + 0.4 * X, n); gc[:, 1] = rng.uniform(cy - 0.4 * Y, cy + 0.4 * Y, n)
+    gc[:, 2] = rng.uniform(0.0, 0.25, n)
+    q = rng.standard_normal((n, 4)); gc[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    g0 = gc.copy()
+    d = o.step(gc, gv, n_steps=1, debug=True)
+    half = np.array([0.2, 0.15, 0.1])
+    corners = np.array([[sx_, sy_, sz_] for sx_ in (-1, 1) for sy_ in (-1, 1) for sz_ in (-1, 1)]) * half
+    checked = 0
+    for e in range(n):
+        R = quat_to_rot(g0[e, 3:7])
+        W = g0[e, :3] + corners @ R.T
+        below = []
+        for c in W:
+            z, nn, pair = _surface_numpy(H, xs, ys, X, Y, cx, cy, c[0], c[1])
+            if (z - c[2]) * nn[2] > 1e-9:
+                below.append(((z - c[2]) * nn[2], nn, pair, c))
+        K = int(d["ncontacts"][e])
+        pt_feat_point = [k for k in range(K) if np.linalg.norm(d["c_pos"][e, k] - W, axis=1).min() < 1e-12]     # contacts that are box corners
+        assert len(pt_feat_point) >= min(len(below), 8) - (K - len(pt_feat_point))       # corners may be displaced by deeper box-face contacts only
+        for k in pt_feat_point:
+            pos = d["c_pos"][e, k]
+            z, nn, pair = _surface_numpy(H, xs, ys, X, Y, cx, cy, pos[0], pos[1])
+            assert abs(d["c_depth"][e, k] - (z - pos[2]) * nn[2]) < 1e-12
+            assert np.allclose(d["c_normal"][e, k], nn, atol=1e-12)
+            assert d["c_pair"][e, k] == pair
+            checked += 1
+    assert checked > 300
+
+
+def test_random_heightmap_sphere_contacts_against_brute_force_sampling():
+    """Spheres on a random rough map: the oracle's contact (closest point of the 8 triangles around the centre, Voronoi-region formula)
+    against brute force -- every triangle of the 5 x 5 cells around the centre sampled on a dense barycentric grid.  No sampled point
+    may be closer to the centre than the oracle's closest point, and the oracle's point must be (nearly) attained by the samples:
+    independent evidence for the closest-feature routine and for the 2 x 2 cell block being enough for a radius below the pitch."""
+    t = load_tables(SPHERE_URDF)
+    o = Oracle(t)
+    rng = np.random.default_rng(77)
+    xs, ys, X, Y = 21, 17, 4.0, 3.2           # pitch 0.2 m, sphere radius 0.1 m
+    H = 0.08 * rng.uniform(-1, 1, (ys, xs))
+    o.set_heightmap(xs, ys, X, Y, 0.0, 0.0, H)
+    dx, dy = X / (xs - 1), Y / (ys - 1)
+    n = 300
+    gc = np.zeros((n, 7)); gc[:, 3] = 1.0
+    gc[:, 0] = rng.uniform(-0.35 * X, 0.35 * X, n); gc[:, 1] = rng.uniform(-0.35 * Y, 0.35 * Y, n)
+    for e in range(n):                         # centre 0.03 .. 0.17 m above the surface right beneath it: some touch, some do not
+        z, _, _ = _surface_numpy(H, xs, ys, X, Y, 0.0, 0.0, gc[e, 0], gc[e, 1])
+        gc[e, 2] = z + rng.uniform(0.03, 0.17)
+    g0 = gc.copy()
+    d = o.step(gc, np.zeros((n, 6)), n_steps=1, debug=True)
+    m = 40
+    a, b = np.meshgrid(np.arange(m + 1) / m, np.arange(m + 1) / m)
+    keep = a + b <= 1.0 + 1e-12
+    a, b = a[keep], b[keep]                    # barycentric samples, spacing dx / 40 = 5 mm
+    touched = 0
+    for e in range(n):
+        C = g0[e, :3]
+        ix0, iy0 = int((C[0] + X / 2) / dx), int((C[1] + Y / 2) / dy)
+        best = np.inf
+        for iy in range(iy0 - 2, iy0 + 3):
+            for ix in range(ix0 - 2, ix0 + 3):
+                P = lambda i, j: np.array([-X / 2 + i * dx, -Y / 2 + j * dy, H[j, i]])
+                for tri in ((P(ix, iy), P(ix + 1, iy), P(ix + 1, iy + 1)), (P(ix, iy), P(ix + 1, iy + 1), P(ix, iy + 1))):
+                    pts = tri[0] + np.outer(a, tri[1] - tri[0]) + np.outer(b, tri[2] - tri[0])
+                    best = min(best, np.linalg.norm(pts - C, axis=1).min())
+        if d["ncontacts"][e] == 1:
+            dist = 0.1 - d["c_depth"][e, 0]                                # distance centre -> closest terrain point
+            assert dist <= best + 1e-9                                      # nothing sampled is closer than the oracle's point
+            assert best - dist < 4e-3                                       # and the samples come within their spacing of it
+            closest = g0[e, :3] - dist * d["c_normal"][e, 0]
+            z, _, _ = _surface_numpy(H, xs, ys, X, Y, 0.0, 0.0, closest[0], closest[1])
+            assert abs(closest[2] - z) < 1e-9                               # the closest point lies on the surface
+            touched += 1
+        else:
+            assert best >= 0.1 - 1e-9                                       # no contact reported: nothing within the radius
+    assert touched > 60 and n - touched > 30
